@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- matched frames/s of MANet's matching + map-memory hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = what the propagation loop does per frame before the segmentation head
+(test.py:237-259 -> IntVOS.prop_seghead, IntVOS.py:600-661): global matching of the current
+frame against the annotated frame (+ normalisation + global-map memory min), local matching
+against the previous frame (+ local-map memory store/select).  Workload: synthetic DAVIS-480p
+embeddings (C=100, 120x214 at stride 4), 5 objects (N=6 ids), max_distance=12 (the reference
+default, config.py:50), k=1, every reference pixel labelled (R = M = 25 680).
+
+  value : frames/s with inputs resident in HBM (CUDA events on the launching stream, L2 flushed
+          between steps), whole job over all ranks (independent sequences per GPU: weak scaling)
+  e2e   : the same step through the C-ABI session with HOST buffers (pinned H2D of the three
+          embeddings + two label maps, D2H of both maps, inside the timed region)
+  --impl reference : the reference's CPU torch path (oracle port, all host threads), bounded sample
+
+Nothing here reads /root/reference.  oracle/ is used only for the CPU baseline legs.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W, C, N_IDS, D_LOCAL = 120, 214, 100, 6, 12
+M_PIX = H * W
+WORKLOAD = "global+local matching + map-memory update, 480p emb 100x120x214, 5 objects (N=6), max_distance=12, k=1"
+ALGO_FLOP_GLOBAL = 2.0 * M_PIX * M_PIX * C                      # 2*M*R*C, SURVEY.md section 8d
+ALGO_BYTES_LOCAL = 4.0 * (2 * C * H * W + H * W + H * W * N_IDS)
+KERNELS_PER_STEP = 9   # scan, convert, umma, finalize | pool x2, window, upsample-mask-min | local-map store/select
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "tflops": p["bf16_tflops"], "tflops_sustained": p.get("bf16_tflops_sustained"),
+                "source": "measured (MEASURED_PEAKS.json, bf16 burst)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        busy = sorted(sm)[len(sm) // 2:] if sm else []     # upper half ~ samples under load
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_inputs(seed):
+    import torch
+    gen = torch.Generator().manual_seed(seed)
+    mk = lambda: 0.1 * torch.relu(torch.randn(C, H, W, generator=gen))
+    ref, prev = mk(), mk()
+    cur = prev + 0.02 * torch.randn(C, H, W, generator=gen)
+    blob = lambda: torch.randint(0, N_IDS, (H // 8, W // 8 + 1), generator=gen).repeat_interleave(8, 0).repeat_interleave(8, 1)[:H, :W].int().contiguous()
+    return ref, prev, cur, blob(), blob()
+
+
+# ------------------------------------------------------------------------------------------ CPU legs
+def cpu_reference_step(inputs, sample):
+    """One bounded sample of the reference CPU path (oracle port).  Returns seconds for a FULL frame
+    extrapolated from the sample: global = 1 of the reference's 10 query chunks (IntVOS.py:139-152,
+    n_chunks=10 at :610) x all references, scaled x10; local + memory on `sample['rows']` rows of the
+    frame, scaled by H/rows."""
+    import torch
+    from oracle import manet_oracle as O
+    ref, prev, cur, ref_lab, prev_lab = inputs
+    refv, curv, prevv = ref.permute(1, 2, 0), cur.permute(1, 2, 0), prev.permute(1, 2, 0)
+    ids = torch.arange(N_IDS, dtype=torch.int32)
+    t0 = time.perf_counter()
+    chunk = (M_PIX + 9) // 10
+    wrong = ref_lab.reshape(1, -1) != ids.unsqueeze(1)
+    feat, _ = O.nn_features_for_chunk(refv.reshape(-1, C), curv.reshape(-1, C)[:chunk], wrong, 1, None)
+    g = O.normalize_distance(feat)
+    t_global = (time.perf_counter() - t0) * 10
+    rows = sample["rows"]
+    t0 = time.perf_counter()
+    loc = O.local_match(prevv[:rows], curv[:rows], prev_lab[:rows].unsqueeze(-1), ids, D_LOCAL)
+    mem = torch.ones_like(loc)
+    _ = torch.where(loc <= mem, loc, mem)
+    t_local = (time.perf_counter() - t0) * (H / rows)
+    del g
+    return t_global + t_local, t_global, t_local
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    inputs = synth_inputs(0)
+    sample = {"rows": 30}
+    for _ in range(args.warmup):
+        cpu_reference_step(inputs, sample)
+    times, tg, tl = [], [], []
+    for _ in range(args.steps):
+        t, a, b = cpu_reference_step(inputs, sample)
+        times.append(t); tg.append(a); tl.append(b)
+    per_frame = sum(times) / len(times)
+    value = 1.0 / per_frame
+    desc = ("oracle port of the reference CPU torch path; per step: global = 1 of 10 query chunks (2568 queries x 25680 refs, "
+            "N=6) scaled x10, local+memory = 30 of 120 rows scaled x4")
+    line = {"impl": "reference", "metric": "matched frames/sec (global+local, 480p, 5 obj)", "value": value,
+            "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": per_frame * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc,
+                             "global_s_per_frame": sum(tg) / len(tg), "local_s_per_frame": sum(tl) / len(tl)},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg():
+    """Bounded CPU sample for the own-arm line (rank 0, N=1): one warm-up-free pass."""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    inputs = synth_inputs(0)
+    t, tg, tl = cpu_reference_step(inputs, {"rows": 30})
+    t2, tg2, tl2 = cpu_reference_step(inputs, {"rows": 30})
+    t, tg, tl = min(t, t2), min(tg, tg2), min(tl, tl2)
+    return {"value": 1.0 / t, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": "2 passes, best: global 1 of 10 query chunks x10, local+memory 30 of 120 rows x4 (oracle port, torch CPU fp32)",
+            "global_s_per_frame": tg, "local_s_per_frame": tl}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_own_arm(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from cvpr2020_manet_b200 import _lib, engine
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    _lib.check(L.manet_check_device(), "device check")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sess = engine.MatchingSession(H, W, C, N_IDS, D_LOCAL, n_frames=104)
+    ref, prev, cur, ref_lab, prev_lab = synth_inputs(1000 + rank)
+    sess.ref[:], sess.prev[:], sess.cur[:] = ref.numpy(), prev.numpy(), cur.numpy()
+    sess.ref_labels[:], sess.prev_labels[:] = ref_lab.numpy(), prev_lab.numpy()
+    sess.upload(); sess.sync()
+    stream = torch.cuda.ExternalStream(sess.stream, device=dev)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    K, Wm = args.steps, args.warmup
+    L.manet_profile_enable(K + 4)
+    for i in range(Wm):
+        sess.step_device(1 + i % 100, 1, 0)
+    sess.sync()
+    L.manet_profile_reset()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    wall0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        for i in range(K):
+            flush_buf.fill_(i & 0xFF)                      # L2 flush, outside the timed events
+            starts[i].record(stream)
+            sess.step_device(1 + (Wm + i) % 100, 1, 0)
+            stops[i].record(stream)
+    sess.sync()
+    barrier()
+    wall_dev = time.perf_counter() - wall0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    total_s = sum(step_ms) / 1e3
+    # kernel timings recorded inside the library on the same stream
+    prof = {}
+    for slot, name in ((0, "global_tcgen05"), (1, "local_window"), (2, "local_upsample_mask_min")):
+        buf = (ctypes.c_float * (K + 4))()
+        n = ctypes.c_int(0)
+        _lib.check(L.manet_profile_read(slot, buf, K + 4, ctypes.byref(n)), "manet_profile_read")
+        vals = [buf[i] for i in range(n.value)]
+        prof[name] = (sum(vals) / len(vals)) if vals else None
+    L.manet_profile_enable(0)
+
+    # end-to-end through the host-buffer C-ABI session
+    for _ in range(min(3, Wm)):
+        sess.step_host(50, 1, 0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        sess.step_host(1 + i % 100, 1, 0)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([total_s, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_s, e2e_s = float(t[0]), float(t[1])
+
+    sharded = sharded_1080p_leg(dev, rank, world) if os.environ.get("MANET_BENCH_SHARDED", "1") == "1" else None
+
+    if rank == 0:
+        peaks = load_peaks()
+        k_ms = prof["global_tcgen05"]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("global_tcgen05_dram_bytes_per_launch")
+        achieved = (ALGO_FLOP_GLOBAL / (k_ms * 1e-3) / 1e12) if k_ms else None
+        roofline = {"kernel": "gm_umma_kernel (global matching, 3 x fp16-split tcgen05 MMAs per product)",
+                    "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                    "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": traffic,
+                    "kernel_ms": k_ms, "kernel_share_of_step": (k_ms / (total_s * 1e3 / K)) if k_ms else None,
+                    "peak_source": peaks["source"],
+                    "algorithmic_flop_per_launch": ALGO_FLOP_GLOBAL,
+                    "executed_mma_flop_per_launch": 3 * 2.0 * (201 * 128) * 112 * 25856,
+                    "local": {"bound": "hbm", "algorithmic_bytes": ALGO_BYTES_LOCAL,
+                              "window_kernel_ms": prof["local_window"], "min_kernel_ms": prof["local_upsample_mask_min"],
+                              "achieved_gbs": (ALGO_BYTES_LOCAL / ((prof["local_window"] + prof["local_upsample_mask_min"]) * 1e-3) / 1e9)
+                              if prof["local_window"] and prof["local_upsample_mask_min"] else None,
+                              "peak_gbs": peaks["hbm_gbs"]}}
+        line = {"metric": "matched frames/sec (global+local, 480p, 5 obj)", "value": world * K / total_s,
+                "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": total_s * 1e3 / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp16x2-split tensor-core GEMM, fp32 accumulate)",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "parallelism": f"{world} independent sequences (1 per GPU), no data-path collective",
+                           "l2": "flushed between timed steps (256 MiB write outside the event pair)",
+                           "timing": "CUDA events per step on the launching stream, summed; max over ranks"},
+                "e2e": {"value": world * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": sess.h2d_bytes_per_step,
+                        "d2h_bytes_per_step": sess.d2h_bytes_per_step, "ms_per_step": e2e_s * 1e3 / K},
+                "gpu_launches": KERNELS_PER_STEP * K, "clocks": clocks, "roofline": roofline,
+                "wall_s_timed_region": wall_dev}
+        if sharded:
+            line["sharded_global_1080p"] = sharded
+        if world == 1 and os.environ.get("MANET_BENCH_CPU", "1") == "1":
+            line["cpu_baseline"] = cpu_baseline_leg()
+        print(json.dumps(line), flush=True)
+    sess.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def sharded_1080p_leg(dev, rank, world, t_mem=4, iters=5):
+    """BASELINE config 5: large-reference global matching at 1080p shape (M = 129 600, reference =
+    t_mem stacked frames) sharded over the reference axis, combined with all_reduce(MIN)."""
+    import torch
+    import torch.distributed as dist
+    from cvpr2020_manet_b200.distributed import shard_bounds
+    from cvpr2020_manet_b200.networks import IntVOS
+    from cvpr2020_manet_b200 import memory
+    Hb, Wb = 270, 480
+    gen = torch.Generator().manual_seed(5)
+    qry = (0.1 * torch.relu(torch.randn(C, Hb, Wb, generator=gen))).to(dev).permute(1, 2, 0)
+    R = t_mem * Hb * Wb
+    b, e = shard_bounds(R, world, rank)
+    gen2 = torch.Generator().manual_seed(100 + rank)
+    ref = (0.1 * torch.relu(torch.randn(C, e - b, generator=gen2))).to(dev).t().unsqueeze(1)     # [R/G,1,C] view of [C,R/G]
+    lab = torch.randint(0, N_IDS, (e - b, 1, 1), generator=gen2).int().to(dev)
+    times = []
+    for i in range(iters + 2):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        part, _ = IntVOS.nearest_neighbor_features_per_object(ref, qry, lab, 1, N_IDS - 1)
+        if world > 1:
+            dist.all_reduce(part, op=dist.ReduceOp.MIN)
+        out = memory.normalize_distances(part)
+        t.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            times.append(s.elapsed_time(t))
+    ms = torch.tensor([sum(times) / len(times)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms[0])
+    flop = 2.0 * (Hb * Wb) * R * C
+    return {"workload": f"global matching, query 100x270x480, reference {t_mem} stacked frames (R={R}), N=6, sharded over R",
+            "n_gpus": world, "ms": ms, "algorithmic_tflops": flop / (ms * 1e-3) / 1e12, "collective": "all_reduce(MIN) fp32 [M,N]" if world > 1 else None}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    run_own_arm(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,399 @@
+// extern "C" surface of libmanet_b200.so (see include/manet_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+
+namespace manet {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int fail_invalid(const char* what) { set_error("%s", what); return MANET_E_INVALID; }
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
+// implemented in the kernel translation units
+int launch_global_match_simt(const float*, int64_t, int64_t, int64_t, const int32_t*, const uint8_t*, const float*, int64_t,
+                             int64_t, int64_t, int, int, int, float*, cudaStream_t);
+int launch_pairwise_sqdist(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, int, float*,
+                           const float*, float*, cudaStream_t);
+int launch_row_sqnorm(const float*, int64_t, int64_t, int64_t, int, float*, cudaStream_t);
+int launch_global_map_update(const float*, float*, float*, int64_t, int, cudaStream_t);
+bool gm_umma_supported(int C, int N, int k);
+size_t gm_umma_workspace_bytes(int64_t M, int64_t R, int N);
+int launch_global_match_umma(const float*, int64_t, int64_t, int64_t, const int32_t*, const float*, int64_t, int64_t, int64_t,
+                             int, int, int, float*, float*, void*, size_t, cudaStream_t);
+size_t select_workspace_bytes(int64_t R);
+int launch_select_labelled(const int32_t*, int64_t, const float*, int64_t, int64_t, int, int32_t*, float*, int64_t*, void*,
+                           size_t, cudaStream_t);
+size_t local_match_workspace_bytes(int H, int W, int C, int N, int d);
+int launch_local_match(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, const int32_t*,
+                       const int32_t*, int, int, int, int, int, float*, void*, size_t, cudaStream_t);
+int launch_local_window_distances(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, int, int,
+                                  int, int, float*, void*, size_t, cudaStream_t);
+int launch_local_map_store_select(const float*, float*, float*, int, float, float*, int64_t, cudaStream_t);
+int correlation_output_shape(int, int, int, int, int, int, int, int, int*, int*, int*);
+int launch_correlation_forward(const void*, const int64_t*, const void*, const int64_t*, void*, void*, void*, int, int, int, int,
+                               int, int, int, int, int, int, cudaStream_t);
+int launch_correlation_backward(const void*, const int64_t*, const void*, const int64_t*, void*, void*, const void*,
+                                const int64_t*, void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+
+// ---- optional kernel timing pools
+struct ProfPool { cudaEvent_t* start; cudaEvent_t* stop; int cap; int n; };
+static ProfPool g_prof[PROF_SLOTS];
+static bool g_prof_on = false;
+
+void profile_begin(int slot, cudaStream_t stream) {
+    if (!g_prof_on) return;
+    ProfPool& p = g_prof[slot];
+    if (p.n < p.cap) cudaEventRecord(p.start[p.n], stream);
+}
+void profile_end(int slot, cudaStream_t stream) {
+    if (!g_prof_on) return;
+    ProfPool& p = g_prof[slot];
+    if (p.n < p.cap) { cudaEventRecord(p.stop[p.n], stream); ++p.n; }
+}
+
+static int arch_ok() {
+    static int cached = -2;
+    if (cached != -2) return cached;
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+        set_error("no usable CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+        return MANET_E_ARCH;
+    }
+    if (major != 10) {
+        set_error("libmanet_b200 is built for sm_100a only; current device has compute capability %d.x", major);
+        return MANET_E_ARCH;
+    }
+    cached = 0;
+    return 0;
+}
+
+}  // namespace manet
+
+using namespace manet;
+
+#define MANET_REQUIRE(cond, msg) do { if (!(cond)) return fail_invalid(msg); } while (0)
+#define MANET_ARCH() do { int _a = arch_ok(); if (_a) return _a; } while (0)
+
+extern "C" {
+
+int manet_abi_version(void) { return MANET_ABI_VERSION; }
+const char* manet_last_error(void) { return g_err; }
+int manet_check_device(void) { return arch_ok(); }
+
+size_t manet_global_match_workspace_bytes(int64_t M, int64_t R, int C, int N, int k) {
+    if (gm_umma_supported(C, N, k)) return gm_umma_workspace_bytes(M, R, N);
+    return 256;
+}
+
+int manet_global_match(const float* ref, int64_t ref_pix_stride, int64_t ref_ch_stride, int64_t R, const int32_t* labels,
+                       const float* query, int64_t q_pix_stride, int64_t q_ch_stride, int64_t M, int C, int N, int k,
+                       uint32_t flags, float* mem_frame, float* out, void* workspace, size_t workspace_bytes,
+                       manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(query && out && (R == 0 || (ref && labels)), "global match: null pointer");
+    MANET_REQUIRE(M >= 0 && R >= 0 && C >= 1 && N >= 1 && k >= 1, "global match: bad sizes");
+    MANET_REQUIRE(!mem_frame || (flags & MANET_GM_NORMALIZE), "global match: a memory slot requires MANET_GM_NORMALIZE");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int normalize = (flags & MANET_GM_NORMALIZE) ? 1 : 0;
+    if (!(flags & MANET_GM_ENGINE_SIMT) && gm_umma_supported(C, N, k))
+        return launch_global_match_umma(ref, ref_pix_stride, ref_ch_stride, R, labels, query, q_pix_stride, q_ch_stride, M,
+                                        C, N, normalize, mem_frame, out, workspace, workspace_bytes, st);
+    // CUDA-core engine: k > 1, C > 128, N > 64, or forced.  Labels outside [0,N) (incl. -1) never
+    // match, so MANET_GM_DROP_UNLAB needs no extra work here.
+    if (M == 0) return 0;
+    int rc = launch_global_match_simt(ref, ref_pix_stride, ref_ch_stride, R, labels, nullptr, query, q_pix_stride,
+                                      q_ch_stride, M, C, N, k, out, st);
+    if (rc) return rc;
+    if (normalize || mem_frame) return launch_global_map_update(out, mem_frame, out, M * N, normalize, st);
+    return 0;
+}
+
+int manet_global_match_masked(const float* ref, int64_t ref_pix_stride, int64_t ref_ch_stride, int64_t R,
+                              const uint8_t* wrong_label_mask, const float* query, int64_t q_pix_stride,
+                              int64_t q_ch_stride, int64_t M, int C, int N, int k, float* out, void* workspace,
+                              size_t workspace_bytes, manet_stream_t stream) {
+    (void)workspace; (void)workspace_bytes;
+    MANET_ARCH();
+    MANET_REQUIRE(ref && wrong_label_mask && query && out, "global match (masked): null pointer");
+    MANET_REQUIRE(M >= 0 && R >= 1 && C >= 1 && N >= 1 && k >= 1, "global match (masked): bad sizes");
+    if (M == 0) return 0;
+    return launch_global_match_simt(ref, ref_pix_stride, ref_ch_stride, R, nullptr, wrong_label_mask, query, q_pix_stride,
+                                    q_ch_stride, M, C, N, k, out, (cudaStream_t)stream);
+}
+
+int manet_pairwise_sqdist(const float* x, int64_t x_pix_stride, int64_t x_ch_stride, int64_t n, const float* y,
+                          int64_t y_pix_stride, int64_t y_ch_stride, int64_t m, int C, float* d, const float* ys_in,
+                          float* ys_out, manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(x && y && d, "pairwise_sqdist: null pointer");
+    MANET_REQUIRE(n >= 0 && m >= 0 && C >= 1, "pairwise_sqdist: bad sizes");
+    if (n == 0 || m == 0) return 0;
+    return launch_pairwise_sqdist(x, x_pix_stride, x_ch_stride, n, y, y_pix_stride, y_ch_stride, m, C, d, ys_in, ys_out,
+                                  (cudaStream_t)stream);
+}
+
+int manet_row_sqnorm(const float* x, int64_t pix_stride, int64_t ch_stride, int64_t n, int C, float* out,
+                     manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(x && out && n >= 0 && C >= 1, "row_sqnorm: null pointer / bad size");
+    return launch_row_sqnorm(x, pix_stride, ch_stride, n, C, out, (cudaStream_t)stream);
+}
+
+size_t manet_select_labelled_workspace_bytes(int64_t R) { return select_workspace_bytes(R); }
+
+int manet_select_labelled(const int32_t* labels, int64_t R, const float* emb, int64_t pix_stride, int64_t ch_stride, int C,
+                          int32_t* out_labels, float* out_emb, int64_t* count_dev, void* workspace, size_t workspace_bytes,
+                          manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(count_dev && workspace && (R == 0 || (labels && out_labels)), "select_labelled: null pointer");
+    MANET_REQUIRE(R >= 0 && C >= 0, "select_labelled: bad sizes");
+    return launch_select_labelled(labels, R, emb, pix_stride, ch_stride, C, out_labels, out_emb, count_dev, workspace,
+                                  workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t manet_local_match_workspace_bytes(int H, int W, int C, int N, int max_distance) {
+    return local_match_workspace_bytes(H, W, C, N, max_distance);
+}
+
+int manet_local_match(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_sc, const float* query, int64_t q_sy,
+                      int64_t q_sx, int64_t q_sc, const int32_t* labels, const int32_t* gt_ids, int H, int W, int C, int N,
+                      int max_distance, float* out, void* workspace, size_t workspace_bytes, manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(prev && query && labels && gt_ids && out && workspace, "local match: null pointer");
+    return launch_local_match(prev, p_sy, p_sx, p_sc, query, q_sy, q_sx, q_sc, labels, gt_ids, H, W, C, N, max_distance,
+                              out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int manet_local_window_distances(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_sc, const float* y, int64_t y_sy,
+                                 int64_t y_sx, int64_t y_sc, int H, int W, int C, int max_distance, float* out,
+                                 void* workspace, size_t workspace_bytes, manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(x && y && out && workspace, "local window distances: null pointer");
+    return launch_local_window_distances(x, x_sy, x_sx, x_sc, y, y_sy, y_sx, y_sc, H, W, C, max_distance, out, workspace,
+                                         workspace_bytes, (cudaStream_t)stream);
+}
+
+int manet_global_map_update(const float* new_map, float* mem_frame, float* out, int64_t n, int normalize,
+                            manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(new_map && out && n >= 0, "global map update: null pointer / bad size");
+    return launch_global_map_update(new_map, mem_frame, out, n, normalize, (cudaStream_t)stream);
+}
+
+int manet_local_map_store_select(const float* new_map, float* mem_frame_rounds, float* dist_row, int interaction_num,
+                                 float dist_value, float* out, int64_t n, manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(new_map && mem_frame_rounds && dist_row && out && n >= 0, "local map memory: null pointer / bad size");
+    return launch_local_map_store_select(new_map, mem_frame_rounds, dist_row, interaction_num, dist_value, out, n,
+                                         (cudaStream_t)stream);
+}
+
+int manet_correlation_output_shape(int C, int H, int W, int pad_size, int kernel_size, int max_displacement, int stride1,
+                                   int stride2, int* out_channels, int* out_h, int* out_w) {
+    MANET_REQUIRE(out_channels && out_h && out_w, "correlation: null pointer");
+    return correlation_output_shape(C, H, W, pad_size, kernel_size, max_displacement, stride1, stride2, out_channels, out_h,
+                                    out_w);
+}
+
+int manet_correlation_forward(const void* in1, const int64_t* in1_strides, const void* in2, const int64_t* in2_strides,
+                              void* rin1, void* rin2, void* out, int B, int C, int H, int W, int pad_size, int kernel_size,
+                              int max_displacement, int stride1, int stride2, int dtype, manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(in1 && in2 && rin1 && rin2 && in1_strides && in2_strides, "correlation forward: null pointer");
+    MANET_REQUIRE(B >= 1 && C >= 1 && H >= 1 && W >= 1, "correlation forward: bad sizes");
+    return launch_correlation_forward(in1, in1_strides, in2, in2_strides, rin1, rin2, out, B, C, H, W, pad_size, kernel_size,
+                                      max_displacement, stride1, stride2, dtype, (cudaStream_t)stream);
+}
+
+int manet_correlation_backward(const void* in1, const int64_t* in1_strides, const void* in2, const int64_t* in2_strides,
+                               void* rin1, void* rin2, const void* grad_out, const int64_t* grad_out_strides, void* grad_in1,
+                               void* grad_in2, int B, int C, int H, int W, int pad_size, int kernel_size,
+                               int max_displacement, int stride1, int stride2, int dtype, manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(in1 && in2 && rin1 && rin2 && grad_out && grad_in1 && grad_in2 && in1_strides && in2_strides &&
+                  grad_out_strides, "correlation backward: null pointer");
+    MANET_REQUIRE(B >= 1 && C >= 1 && H >= 1 && W >= 1, "correlation backward: bad sizes");
+    return launch_correlation_backward(in1, in1_strides, in2, in2_strides, rin1, rin2, grad_out, grad_out_strides, grad_in1,
+                                       grad_in2, B, C, H, W, pad_size, kernel_size, max_displacement, stride1, stride2,
+                                       dtype, (cudaStream_t)stream);
+}
+
+int manet_profile_enable(int max_records) {
+    for (int s = 0; s < PROF_SLOTS; ++s) {
+        ProfPool& p = g_prof[s];
+        for (int i = 0; i < p.cap; ++i) { cudaEventDestroy(p.start[i]); cudaEventDestroy(p.stop[i]); }
+        delete[] p.start; delete[] p.stop;
+        p.start = p.stop = nullptr; p.cap = p.n = 0;
+        if (max_records > 0) {
+            p.start = new cudaEvent_t[max_records]; p.stop = new cudaEvent_t[max_records];
+            for (int i = 0; i < max_records; ++i) { cudaEventCreate(&p.start[i]); cudaEventCreate(&p.stop[i]); }
+            p.cap = max_records;
+        }
+    }
+    g_prof_on = max_records > 0;
+    return 0;
+}
+
+int manet_profile_reset(void) {
+    for (int s = 0; s < PROF_SLOTS; ++s) g_prof[s].n = 0;
+    return 0;
+}
+
+int manet_profile_read(int slot, float* ms_out, int capacity, int* n_out) {
+    MANET_REQUIRE(slot >= 0 && slot < PROF_SLOTS && n_out, "profile: bad slot");
+    ProfPool& p = g_prof[slot];
+    int n = p.n < capacity ? p.n : capacity;
+    for (int i = 0; i < n; ++i) {
+        cudaError_t e = cudaEventElapsedTime(&ms_out[i], p.start[i], p.stop[i]);
+        if (e != cudaSuccess) { set_error("profile: %s (synchronise the stream first)", cudaGetErrorString(e)); return (int)e; }
+    }
+    *n_out = n;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ session
+struct manet_session {
+    int H, W, C, N, d, n_frames;
+    cudaStream_t stream;
+    // pinned host staging
+    float *h_ref, *h_prev, *h_cur, *h_out_g, *h_out_l;
+    int32_t *h_ref_lab, *h_prev_lab;
+    // device
+    float *d_ref, *d_prev, *d_cur, *d_out_g, *d_out_l, *d_raw_l;
+    int32_t *d_ref_lab, *d_prev_lab, *d_ids;
+    float *d_gmem;        // [n_frames, H*W*N]   global-map memory, ones
+    float *d_lmem;        // [n_frames, 9, H*W*N] local-map memory, zeros (IntVOS.py:645)
+    float *d_ldist;       // [n_frames, 9]
+    void *ws_g, *ws_l; size_t ws_g_bytes, ws_l_bytes;
+};
+
+static __global__ void fill_kernel(float* p, float v, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+manet_session_t* manet_session_create(int H, int W, int C, int N, int max_distance, int n_frames) {
+    if (arch_ok()) return nullptr;
+    if (H < 2 || W < 2 || C < 1 || N < 1 || max_distance < 0 || n_frames < 1) { fail_invalid("session: bad sizes"); return nullptr; }
+    manet_session* s = new (std::nothrow) manet_session();
+    if (!s) return nullptr;
+    memset(s, 0, sizeof(*s));
+    s->H = H; s->W = W; s->C = C; s->N = N; s->d = max_distance; s->n_frames = n_frames;
+    const size_t px = (size_t)H * W, emb = px * C * sizeof(float), map = px * N * sizeof(float);
+    bool ok = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMallocHost(&s->h_ref, emb) == cudaSuccess && cudaMallocHost(&s->h_prev, emb) == cudaSuccess &&
+         cudaMallocHost(&s->h_cur, emb) == cudaSuccess && cudaMallocHost(&s->h_out_g, map) == cudaSuccess &&
+         cudaMallocHost(&s->h_out_l, map) == cudaSuccess && cudaMallocHost(&s->h_ref_lab, px * 4) == cudaSuccess &&
+         cudaMallocHost(&s->h_prev_lab, px * 4) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->d_ref, emb) == cudaSuccess && cudaMalloc(&s->d_prev, emb) == cudaSuccess &&
+         cudaMalloc(&s->d_cur, emb) == cudaSuccess && cudaMalloc(&s->d_out_g, map) == cudaSuccess &&
+         cudaMalloc(&s->d_out_l, map) == cudaSuccess && cudaMalloc(&s->d_raw_l, map) == cudaSuccess &&
+         cudaMalloc(&s->d_ref_lab, px * 4) == cudaSuccess && cudaMalloc(&s->d_prev_lab, px * 4) == cudaSuccess &&
+         cudaMalloc(&s->d_ids, N * 4) == cudaSuccess && cudaMalloc(&s->d_gmem, map * n_frames) == cudaSuccess &&
+         cudaMalloc(&s->d_lmem, map * n_frames * kMemoryRounds) == cudaSuccess &&
+         cudaMalloc(&s->d_ldist, sizeof(float) * n_frames * kMemoryRounds) == cudaSuccess;
+    s->ws_g_bytes = manet_global_match_workspace_bytes((int64_t)px, (int64_t)px, C, N, 1);
+    s->ws_l_bytes = manet_local_match_workspace_bytes(H, W, C, N, max_distance);
+    ok = ok && cudaMalloc(&s->ws_g, s->ws_g_bytes) == cudaSuccess && cudaMalloc(&s->ws_l, s->ws_l_bytes) == cudaSuccess;
+    if (!ok) {
+        set_error("session: allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        manet_session_destroy(s);
+        return nullptr;
+    }
+    int32_t* hid = new int32_t[N];
+    for (int i = 0; i < N; ++i) hid[i] = i;
+    cudaMemcpyAsync(s->d_ids, hid, N * 4, cudaMemcpyHostToDevice, s->stream);
+    fill_kernel<<<148 * 4, 256, 0, s->stream>>>(s->d_gmem, 1.0f, (int64_t)px * N * n_frames);
+    cudaMemsetAsync(s->d_lmem, 0, map * n_frames * kMemoryRounds, s->stream);
+    cudaMemsetAsync(s->d_ldist, 0, sizeof(float) * n_frames * kMemoryRounds, s->stream);
+    cudaStreamSynchronize(s->stream);
+    delete[] hid;
+    return s;
+}
+
+void manet_session_destroy(manet_session_t* s) {
+    if (!s) return;
+    cudaFreeHost(s->h_ref); cudaFreeHost(s->h_prev); cudaFreeHost(s->h_cur); cudaFreeHost(s->h_out_g); cudaFreeHost(s->h_out_l);
+    cudaFreeHost(s->h_ref_lab); cudaFreeHost(s->h_prev_lab);
+    cudaFree(s->d_ref); cudaFree(s->d_prev); cudaFree(s->d_cur); cudaFree(s->d_out_g); cudaFree(s->d_out_l); cudaFree(s->d_raw_l);
+    cudaFree(s->d_ref_lab); cudaFree(s->d_prev_lab); cudaFree(s->d_ids); cudaFree(s->d_gmem); cudaFree(s->d_lmem);
+    cudaFree(s->d_ldist); cudaFree(s->ws_g); cudaFree(s->ws_l);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int manet_session_host_buffers(manet_session_t* s, float** ref, float** prev, float** cur, int32_t** ref_labels,
+                               int32_t** prev_labels, float** out_global, float** out_local) {
+    MANET_REQUIRE(s, "session: null");
+    if (ref) *ref = s->h_ref; if (prev) *prev = s->h_prev; if (cur) *cur = s->h_cur;
+    if (ref_labels) *ref_labels = s->h_ref_lab; if (prev_labels) *prev_labels = s->h_prev_lab;
+    if (out_global) *out_global = s->h_out_g; if (out_local) *out_local = s->h_out_l;
+    return 0;
+}
+
+int manet_session_upload(manet_session_t* s) {
+    MANET_REQUIRE(s, "session: null");
+    const size_t px = (size_t)s->H * s->W, emb = px * s->C * sizeof(float);
+    cudaMemcpyAsync(s->d_ref, s->h_ref, emb, cudaMemcpyHostToDevice, s->stream);
+    cudaMemcpyAsync(s->d_prev, s->h_prev, emb, cudaMemcpyHostToDevice, s->stream);
+    cudaMemcpyAsync(s->d_cur, s->h_cur, emb, cudaMemcpyHostToDevice, s->stream);
+    cudaMemcpyAsync(s->d_ref_lab, s->h_ref_lab, px * 4, cudaMemcpyHostToDevice, s->stream);
+    cudaMemcpyAsync(s->d_prev_lab, s->h_prev_lab, px * 4, cudaMemcpyHostToDevice, s->stream);
+    return check_launch("session upload");
+}
+
+// embeddings are [C,H,W] storage, consumed as [H,W,C] views exactly as IntVOS.py:605-606,625 do
+int manet_session_step_device(manet_session_t* s, int frame, int interaction_num, int start_annotated_frame,
+                              uint32_t flags) {
+    MANET_REQUIRE(s, "session: null");
+    MANET_REQUIRE(frame >= 0 && frame < s->n_frames, "session: frame out of range");
+    MANET_REQUIRE(frame != start_annotated_frame, "session: propagation never visits the annotated frame (1/|f-f0|, IntVOS.py:648)");
+    const int64_t px = (int64_t)s->H * s->W, n = px * s->N;
+    int rc = manet_global_match(s->d_ref, 1, px, px, s->d_ref_lab, s->d_cur, 1, px, px, s->C, s->N, 1,
+                                flags | MANET_GM_NORMALIZE, s->d_gmem + (size_t)frame * n, s->d_out_g, s->ws_g, s->ws_g_bytes,
+                                s->stream);
+    if (rc) return rc;
+    rc = manet_local_match(s->d_prev, s->W, 1, px, s->d_cur, s->W, 1, px, s->d_prev_lab, s->d_ids, s->H, s->W, s->C, s->N,
+                           s->d, s->d_raw_l, s->ws_l, s->ws_l_bytes, s->stream);
+    if (rc) return rc;
+    int df = frame - start_annotated_frame; if (df < 0) df = -df;
+    return manet_local_map_store_select(s->d_raw_l, s->d_lmem + (size_t)frame * kMemoryRounds * n,
+                                        s->d_ldist + (size_t)frame * kMemoryRounds, interaction_num,
+                                        (float)(1.0 / (double)df), s->d_out_l, n, s->stream);
+}
+
+int manet_session_step_host(manet_session_t* s, int frame, int interaction_num, int start_annotated_frame, uint32_t flags) {
+    int rc = manet_session_upload(s);
+    if (rc) return rc;
+    rc = manet_session_step_device(s, frame, interaction_num, start_annotated_frame, flags);
+    if (rc) return rc;
+    const size_t map = (size_t)s->H * s->W * s->N * sizeof(float);
+    cudaMemcpyAsync(s->h_out_g, s->d_out_g, map, cudaMemcpyDeviceToHost, s->stream);
+    cudaMemcpyAsync(s->h_out_l, s->d_out_l, map, cudaMemcpyDeviceToHost, s->stream);
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) { set_error("session step: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
+int manet_session_sync(manet_session_t* s) {
+    MANET_REQUIRE(s, "session: null");
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) { set_error("session sync: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
+manet_stream_t manet_session_stream(manet_session_t* s) { return s ? (manet_stream_t)s->stream : nullptr; }
+
+}  // extern "C"

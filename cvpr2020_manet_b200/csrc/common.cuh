@@ -1,0 +1,59 @@
+// Shared helpers for the MANet B200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/manet_b200.h"
+
+namespace manet {
+
+constexpr float kWrongLabelPad = 1e20f;   // WRONG_LABEL_PADDING_DISTANCE, IntVOS.py:17
+constexpr int kMemoryRounds = 9;          // IntVOS.py:641,645
+
+void set_error(const char* fmt, ...);
+int fail_invalid(const char* what);
+int check_launch(const char* what);       // cudaGetLastError() -> code (+ message)
+
+// Optional per-kernel timing (bench.py's roofline leg): when enabled, launchers bracket the named
+// kernel with cudaEvents taken from a pool; see manet_profile_* in include/manet_b200.h.
+enum ProfileSlot { PROF_GLOBAL_UMMA = 0, PROF_LOCAL_WINDOW = 1, PROF_LOCAL_MIN = 2, PROF_SLOTS = 3 };
+void profile_begin(int slot, cudaStream_t stream);
+void profile_end(int slot, cudaStream_t stream);
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// (sigmoid(x) - 0.5) * 2 in fp32, the caller-side normalisation of IntVOS.py:294, 611-612.
+// +inf and 1e20 map to exactly 1.0f.
+__device__ __forceinline__ float sigmoid_norm(float x) {
+    float s = 1.0f / (1.0f + expf(-x));
+    return (s - 0.5f) * 2.0f;
+}
+
+// Order-preserving float <-> int32 key: signed integer order == float order (no NaNs).
+__device__ __forceinline__ int float_to_key(float f) {
+    int b = __float_as_int(f);
+    return b ^ ((b >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float key_to_float(int k) {
+    return __int_as_float(k ^ ((k >> 31) & 0x7fffffff));
+}
+
+// Simple bump allocator over a caller-provided workspace.
+struct Carver {
+    char* base; size_t off; size_t cap;
+    Carver(void* p, size_t c) : base(reinterpret_cast<char*>(p)), off(0), cap(c) {}
+    template <typename T> T* take(size_t n, size_t align = 256) {
+        off = align_up(off, align);
+        T* r = reinterpret_cast<T*>(base + off);
+        off += n * sizeof(T);
+        return r;
+    }
+    bool ok() const { return off <= cap; }
+};
+
+}  // namespace manet

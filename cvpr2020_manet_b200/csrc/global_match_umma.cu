@@ -1,0 +1,521 @@
+// Global matching on the 5th-generation tensor cores (tcgen05 / TMEM / bulk-TMA), sm_100a.
+//
+// Replaces the reference's chunked  matmul -> [m,N,R] masked broadcast -> min  pipeline
+// (networks/IntVOS.py:23-40, 62-97, 113-157, 160-210).  The query x reference distance matrix is
+// produced tile by tile in tensor memory and reduced in the epilogue; it never reaches HBM.
+//
+// Numerics.  The reference computes d = |q|^2 + |r|^2 - 2 q.r with an fp32 GEMM.  To keep fp32
+// grade results on tensor cores each operand is scaled by a power of two and split into two fp16
+// values x*s = hi + lo (22 significant bits), and the product is evaluated as
+//      q.r  ~=  qh.rh + ql.rh + qh.rl            (three kind::f16 MMAs, fp32 accumulate in TMEM)
+// which drops only the ql.rl term (2^-22 relative).  |r|^2 is added in the epilogue in fp32.
+//
+// Data layout.  A pre-pass (gm_scan_kernel, gm_convert_kernel) buckets the reference pixels by
+// object label (so every 256-column tile belongs to ONE object and the epilogue is a plain
+// row-max), drops unlabelled pixels, and writes both operands as ready-made shared-memory tile
+// images: per 128 rows ("unit"), [part hi|lo][k-block 0|1][128 rows][128 B] with the 128-byte
+// swizzle (16-byte chunk index XOR row%8) already applied.  The main kernel therefore needs no
+// tensor map: plain cp.async.bulk copies land canonical K-major SWIZZLE_128B operands.
+//
+// Main kernel (gm_umma_kernel): persistent, one CTA per SM, 6 warps:
+//   warp 0  bulk-TMA producer        warp 1  tcgen05.mma issuer (+ TMEM allocator)
+//   warps 2-5  epilogue: tcgen05.ld 32 columns at a time, add -s/2*|r|^2, running row max,
+//              flushed with one atomicMax per (query row, object) when the object changes.
+// Tiles are 128 (queries) x 256 (references), accumulators double-buffered in TMEM (2 x 256
+// columns) so the epilogue of tile t overlaps the MMAs of tile t+1.
+#include "common.cuh"
+
+namespace manet {
+
+constexpr int GM_MAXN = 64;            // objects supported by this engine
+constexpr int GM_MAXC = 128;           // channels supported by this engine
+constexpr int GM_BM = 128;             // queries per tile (UMMA M)
+constexpr int GM_BN = 256;             // references per tile (UMMA N)
+constexpr int GM_UNIT_ROWS = 128;
+constexpr int GM_CHUNK_BYTES = 16384;  // one (unit, part, k-block): 128 rows x 128 B
+constexpr int GM_UNIT_BYTES = 4 * GM_CHUNK_BYTES;
+constexpr int GM_THREADS = 192;
+constexpr int GM_STAGES = 2;
+constexpr int GM_STAGE_BYTES = 2 * 2 * GM_CHUNK_BYTES;       // one part of a 256-row tile
+constexpr int GM_SMEM_A = GM_UNIT_BYTES;
+constexpr int GM_SMEM_BAR = GM_SMEM_A + GM_STAGES * GM_STAGE_BYTES;
+constexpr int GM_SMEM_TOTAL = GM_SMEM_BAR + 256 + 1024;     // + barriers + alignment slack
+
+struct GmCtrl {
+    unsigned absmax_bits[2];       // |x| max as raw bits: [0] reference, [1] query
+    int counts[GM_MAXN];           // labelled reference pixels per object
+    int cursors[GM_MAXN];          // scatter cursors
+    int offsets[GM_MAXN + 1];      // first row of each (256-padded) bucket
+    int n_rtiles;                  // number of 256-row reference tiles
+    float scale_q, scale_r;        // power-of-two operand scales
+};
+
+// ------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16, single CTA
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (unused for swizzled K-major, 1)
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024)   [46,48) version = 1   [61,64) layout = 2
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) at [4,6); a/b format F16 (0);
+// a/b K-major (0); n_dim = N>>3 at [17,23); m_dim = M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------ pre-pass
+__device__ __forceinline__ float pow2_scale(unsigned absmax_bits) {
+    float a = __uint_as_float(absmax_bits);
+    if (!(a > 0.f) || !isfinite(a)) return 1.0f;
+    int e = ilogbf(a);                         // a in [2^e, 2^(e+1))
+    int sh = 10 - e;                           // a * 2^sh in [2^10, 2^11)
+    sh = max(-60, min(60, sh));
+    return ldexpf(1.0f, sh);
+}
+
+// byte offset of the 16-byte chunk holding k = 8*j .. 8*j+7 of row `pos` (part 0 = hi, 1 = lo)
+__device__ __forceinline__ size_t image_chunk_offset(int64_t pos, int part, int j) {
+    int64_t unit = pos / GM_UNIT_ROWS; int row = (int)(pos % GM_UNIT_ROWS);
+    int kb = j >> 3, ch = j & 7;
+    return (size_t)unit * GM_UNIT_BYTES + (size_t)part * (2 * GM_CHUNK_BYTES) + (size_t)kb * GM_CHUNK_BYTES +
+           (size_t)(row >> 3) * 1024 + (size_t)(row & 7) * 128 + (size_t)((ch ^ (row & 7)) << 4);
+}
+
+// pass 1: label histogram, per-tensor |x| max, best[] = -inf keys
+__global__ void __launch_bounds__(256)
+gm_scan_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64_t R, const int32_t* __restrict__ labels,
+               const float* __restrict__ query, int64_t qps, int64_t qcs, int64_t M, int C, int N,
+               GmCtrl* __restrict__ ctrl, int* __restrict__ best, int64_t n_best) {
+    __shared__ int hist[GM_MAXN];
+    __shared__ unsigned red[2][8];
+    const int t = threadIdx.x;
+    if (t < GM_MAXN) hist[t] = 0;
+    __syncthreads();
+    float amax_r = 0.f, amax_q = 0.f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + t; i < R + M; i += stride) {
+        if (i < R) {
+            int lab = labels[i];
+            if (lab >= 0 && lab < N) atomicAdd(&hist[lab], 1);
+            const float* p = ref + i * rps;
+            for (int c = 0; c < C; ++c) amax_r = fmaxf(amax_r, fabsf(__ldg(p + (int64_t)c * rcs)));
+        } else {
+            const float* p = query + (i - R) * qps;
+            for (int c = 0; c < C; ++c) amax_q = fmaxf(amax_q, fabsf(__ldg(p + (int64_t)c * qcs)));
+        }
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + t; i < n_best; i += stride) best[i] = INT_MIN;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        amax_r = fmaxf(amax_r, __shfl_xor_sync(0xffffffffu, amax_r, s));
+        amax_q = fmaxf(amax_q, __shfl_xor_sync(0xffffffffu, amax_q, s));
+    }
+    if ((t & 31) == 0) { red[0][t >> 5] = __float_as_uint(amax_r); red[1][t >> 5] = __float_as_uint(amax_q); }
+    __syncthreads();
+    if (t < 2) {
+        unsigned m = 0;
+        for (int w = 0; w < 8; ++w) m = max(m, red[t][w]);
+        if (m) atomicMax(&ctrl->absmax_bits[t], m);      // non-negative floats order like unsigned ints
+    }
+    if (t < N && hist[t]) atomicAdd(&ctrl->counts[t], hist[t]);
+}
+
+// split x*s into fp16 hi + lo, 8 channels -> two 16-byte chunks
+__device__ __forceinline__ void split8(const float (&v)[8], float s, uint4& hi, uint4& lo) {
+    __half h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float x = v[i] * s;
+        h[i] = __float2half_rn(x);
+        l[i] = __float2half_rn(x - __half2float(h[i]));
+    }
+    hi = *reinterpret_cast<uint4*>(h);
+    lo = *reinterpret_cast<uint4*>(l);
+}
+
+__device__ __forceinline__ float convert_row(const float* __restrict__ p, int64_t cs, int C, int nchunks, float s,
+                                             uint8_t* __restrict__ img, int64_t pos) {
+    float sq = 0.f;
+    for (int j = 0; j < nchunks; ++j) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int c = j * 8 + i;
+            v[i] = (p != nullptr && c < C) ? __ldg(p + (int64_t)c * cs) : 0.f;
+            sq = fmaf(v[i], v[i], sq);
+        }
+        uint4 hi, lo;
+        split8(v, s, hi, lo);
+        *reinterpret_cast<uint4*>(img + image_chunk_offset(pos, 0, j)) = hi;
+        *reinterpret_cast<uint4*>(img + image_chunk_offset(pos, 1, j)) = lo;
+    }
+    return sq;
+}
+
+// pass 2: scatter + convert.  Block ranges: [0,nb_ref) reference pixels, [nb_ref, nb_ref+nb_q) query
+// rows (incl. zero padding up to a multiple of 128), then one block per object for bucket padding.
+__global__ void __launch_bounds__(256)
+gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64_t R, const int32_t* __restrict__ labels,
+                  const float* __restrict__ query, int64_t qps, int64_t qcs, int64_t M, int64_t M_pad, int C, int N,
+                  int nb_ref, int nb_q, GmCtrl* __restrict__ ctrl, uint8_t* __restrict__ Aimg, uint8_t* __restrict__ Bimg,
+                  float* __restrict__ xs, float* __restrict__ ysn, int* __restrict__ tile_obj) {
+    __shared__ int off[GM_MAXN + 1];
+    __shared__ int bcnt[GM_MAXN], bbase[GM_MAXN];
+    const int t = threadIdx.x;
+    if (t == 0) {
+        int o = 0;
+        for (int i = 0; i < N; ++i) { off[i] = o; o += (ctrl->counts[i] + GM_BN - 1) / GM_BN * GM_BN; }
+        off[N] = o;
+    }
+    if (t < GM_MAXN) bcnt[t] = 0;
+    __syncthreads();
+    const float s_q = pow2_scale(ctrl->absmax_bits[1]);
+    const float s_r = pow2_scale(ctrl->absmax_bits[0]);
+    const int nchunks = ((C + 15) / 16) * 2;
+    const int b = blockIdx.x;
+    if (b == 0) {
+        if (t <= N) ctrl->offsets[t] = off[t];
+        if (t == 0) { ctrl->n_rtiles = off[N] / GM_BN; ctrl->scale_q = s_q; ctrl->scale_r = s_r; }
+        for (int o = 0; o < N; ++o)
+            for (int tile = off[o] / GM_BN + t; tile < off[o + 1] / GM_BN; tile += 256) tile_obj[tile] = o;
+    }
+    if (b < nb_ref) {
+        const int64_t r = (int64_t)b * 256 + t;
+        int lab = (r < R) ? labels[r] : -1;
+        const bool keep = lab >= 0 && lab < N;
+        int rank = 0;
+        if (keep) rank = atomicAdd(&bcnt[lab], 1);
+        __syncthreads();
+        if (t < N && bcnt[t]) bbase[t] = atomicAdd(&ctrl->cursors[t], bcnt[t]);
+        __syncthreads();
+        if (keep) {
+            const int64_t pos = (int64_t)off[lab] + bbase[lab] + rank;
+            float ys = convert_row(ref + r * rps, rcs, C, nchunks, s_r, Bimg, pos);
+            ysn[pos] = -0.5f * (s_q * s_r) * ys;
+        }
+    } else if (b < nb_ref + nb_q) {
+        const int64_t m = (int64_t)(b - nb_ref) * 256 + t;
+        if (m < M_pad) {
+            float x2 = convert_row(m < M ? query + m * qps : nullptr, qcs, C, nchunks, s_q, Aimg, m);
+            xs[m] = x2;
+        }
+    } else {
+        const int o = b - nb_ref - nb_q;
+        const int64_t pos = (int64_t)off[o] + ctrl->counts[o] + t;     // at most 255 padding rows
+        if (pos < off[o + 1]) {
+            convert_row(nullptr, 0, C, nchunks, 1.0f, Bimg, pos);
+            ysn[pos] = -INFINITY;                                       // never wins the row max
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ main kernel
+struct Ring {
+    int idx; uint32_t phase;
+    __device__ Ring() : idx(0), phase(0) {}
+    __device__ void advance(int n) { if (++idx == n) { idx = 0; phase ^= 1; } }
+};
+
+__global__ void __launch_bounds__(GM_THREADS, 1)
+gm_umma_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg, const float* __restrict__ ysn,
+               const int* __restrict__ tile_obj, const GmCtrl* __restrict__ ctrl, int* __restrict__ best,
+               int n_mtiles, int N, int ksteps) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;            // SWIZZLE_128B atoms need 1024-byte alignment
+    uint8_t* smem = smem_raw + (base - raw);
+    const uint32_t sA = base;
+    const uint32_t sB = base + GM_SMEM_A;
+    const uint32_t bars = base + GM_SMEM_BAR;
+    // barrier slots (8 bytes each)
+    const uint32_t full_b = bars + 0;          // [GM_STAGES]
+    const uint32_t empty_b = bars + 16;        // [GM_STAGES]
+    const uint32_t a_full = bars + 32;
+    const uint32_t a_empty = bars + 40;
+    const uint32_t tmem_full = bars + 48;      // [2]
+    const uint32_t tmem_empty = bars + 64;     // [2]
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + GM_SMEM_BAR + 96);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_rtiles = ctrl->n_rtiles;
+    const long long total = (long long)n_mtiles * n_rtiles;
+    const long long t_begin = total * blockIdx.x / gridDim.x;
+    const long long t_end = total * (blockIdx.x + 1) / gridDim.x;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < GM_STAGES; ++i) { mbar_init(full_b + 8 * i, 1); mbar_init(empty_b + 8 * i, 1); }
+            mbar_init(a_full, 1); mbar_init(a_empty, 1);
+            for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, 4); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------ producer
+        if (lane == 0) {
+            Ring st; uint32_t ae_phase = 0; long long cur_m = -1;
+            for (long long tile = t_begin; tile < t_end; ++tile) {
+                const long long m = tile / n_rtiles; const long long rt = tile % n_rtiles;
+                if (m != cur_m) {
+                    mbar_wait(a_empty, ae_phase ^ 1); ae_phase ^= 1;
+                    mbar_expect_tx(a_full, GM_UNIT_BYTES);
+                    bulk_g2s(sA, Aimg + (size_t)m * GM_UNIT_BYTES, GM_UNIT_BYTES, a_full);
+                    cur_m = m;
+                }
+                for (int part = 0; part < 2; ++part) {
+                    mbar_wait(empty_b + 8 * st.idx, st.phase ^ 1);
+                    const uint32_t fb = full_b + 8 * st.idx;
+                    mbar_expect_tx(fb, GM_STAGE_BYTES);
+                    const uint32_t dst = sB + st.idx * GM_STAGE_BYTES;
+#pragma unroll
+                    for (int unit = 0; unit < 2; ++unit)
+#pragma unroll
+                        for (int kb = 0; kb < 2; ++kb)
+                            bulk_g2s(dst + kb * (2 * GM_CHUNK_BYTES) + unit * GM_CHUNK_BYTES,
+                                     Bimg + ((size_t)(2 * rt + unit) * 4 + part * 2 + kb) * GM_CHUNK_BYTES,
+                                     GM_CHUNK_BYTES, fb);
+                    st.advance(GM_STAGES);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_f16(GM_BM, GM_BN);
+            Ring st, acc; uint32_t af_phase = 0; long long cur_m = -1;
+            for (long long tile = t_begin; tile < t_end; ++tile) {
+                const long long m = tile / n_rtiles;
+                if (m != cur_m) { mbar_wait(a_full, af_phase); af_phase ^= 1; cur_m = m; }
+                mbar_wait(tmem_empty + 8 * acc.idx, acc.phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc.idx * GM_BN;
+                // stage with the hi part of the reference tile: qh.rh then ql.rh
+                mbar_wait(full_b + 8 * st.idx, st.phase);
+                tc_fence_after();
+                {
+                    const uint32_t bB = sB + st.idx * GM_STAGE_BYTES;
+                    for (int k = 0; k < ksteps; ++k)
+                        umma_f16(d_tmem, smem_desc_sw128(sA + (k >> 2) * GM_CHUNK_BYTES + (k & 3) * 32),
+                                 smem_desc_sw128(bB + (k >> 2) * (2 * GM_CHUNK_BYTES) + (k & 3) * 32), idesc, k > 0);
+                    for (int k = 0; k < ksteps; ++k)
+                        umma_f16(d_tmem, smem_desc_sw128(sA + 2 * GM_CHUNK_BYTES + (k >> 2) * GM_CHUNK_BYTES + (k & 3) * 32),
+                                 smem_desc_sw128(bB + (k >> 2) * (2 * GM_CHUNK_BYTES) + (k & 3) * 32), idesc, 1);
+                }
+                tc_commit(empty_b + 8 * st.idx);
+                st.advance(GM_STAGES);
+                // stage with the lo part: qh.rl
+                mbar_wait(full_b + 8 * st.idx, st.phase);
+                tc_fence_after();
+                {
+                    const uint32_t bB = sB + st.idx * GM_STAGE_BYTES;
+                    for (int k = 0; k < ksteps; ++k)
+                        umma_f16(d_tmem, smem_desc_sw128(sA + (k >> 2) * GM_CHUNK_BYTES + (k & 3) * 32),
+                                 smem_desc_sw128(bB + (k >> 2) * (2 * GM_CHUNK_BYTES) + (k & 3) * 32), idesc, 1);
+                }
+                tc_commit(empty_b + 8 * st.idx);
+                st.advance(GM_STAGES);
+                tc_commit(tmem_full + 8 * acc.idx);
+                const bool last_of_m = (tile + 1 == t_end) || ((tile + 1) / n_rtiles != m);
+                if (last_of_m) tc_commit(a_empty);
+                acc.advance(2);
+            }
+        }
+    } else {
+        // ------------------------------------------------ epilogue (warps 2..5)
+        const int quarter = warp & 3;                  // TMEM lanes 32*quarter .. +31
+        const int row = quarter * 32 + lane;
+        Ring acc; long long cur_m = -1; int cur_obj = -1; float run = -INFINITY;
+        for (long long tile = t_begin; tile < t_end; ++tile) {
+            const long long m = tile / n_rtiles; const long long rt = tile % n_rtiles;
+            const int obj = __ldg(tile_obj + rt);
+            if (m != cur_m || obj != cur_obj) {
+                if (cur_m >= 0) atomicMax(best + ((size_t)cur_m * GM_BM + row) * N + cur_obj, float_to_key(run));
+                run = -INFINITY; cur_m = m; cur_obj = obj;
+            }
+            mbar_wait(tmem_full + 8 * acc.idx, acc.phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * GM_BN;
+            const float4* yv = reinterpret_cast<const float4*>(ysn + (size_t)rt * GM_BN);
+#pragma unroll 1
+            for (int ch = 0; ch < GM_BN / 32; ++ch) {
+                uint32_t r[32];
+                tmem_ld32(taddr + ch * 32, r);
+                float4 y[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) y[i] = __ldg(yv + ch * 8 + i);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float a0 = __uint_as_float(r[4 * i + 0]) + y[i].x;
+                    float a1 = __uint_as_float(r[4 * i + 1]) + y[i].y;
+                    float a2 = __uint_as_float(r[4 * i + 2]) + y[i].z;
+                    float a3 = __uint_as_float(r[4 * i + 3]) + y[i].w;
+                    run = fmaxf(fmaxf(run, a0), a1);
+                    run = fmaxf(fmaxf(run, a2), a3);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + 8 * acc.idx);
+            acc.advance(2);
+        }
+        if (cur_m >= 0) atomicMax(best + ((size_t)cur_m * GM_BM + row) * N + cur_obj, float_to_key(run));
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// out[m,o] = |q_m|^2 - (2/s) * max_r (s*(q.r) - s/2*|r|^2)  (= min_r |q-r|^2), 1e20 for absent objects;
+// optional normalisation and global-map memory merge fused (IntVOS.py:611-622).
+__global__ void gm_finalize_kernel(const int* __restrict__ best, const float* __restrict__ xs,
+                                   const GmCtrl* __restrict__ ctrl, int64_t M, int N, int normalize,
+                                   float* __restrict__ mem, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * N) return;
+    const int64_t m = i / N; const int o = (int)(i % N);
+    float v;
+    if (ctrl->counts[o] == 0) {
+        v = kWrongLabelPad;
+    } else {
+        const float two_over_s = 2.0f / (ctrl->scale_q * ctrl->scale_r);
+        v = xs[m] - two_over_s * key_to_float(best[i]);
+    }
+    if (normalize) v = sigmoid_norm(v);
+    if (mem != nullptr) { float old = mem[i]; v = (v <= old) ? v : old; mem[i] = v; }
+    out[i] = v;
+}
+
+// ------------------------------------------------------------------------------------ host side
+struct GmPlan {
+    int64_t M_pad, R_pad_max; int n_mtiles, max_rtiles;
+    size_t off_ctrl, off_tile_obj, off_xs, off_ysn, off_best, off_A, off_B, total;
+};
+
+static GmPlan gm_plan(int64_t M, int64_t R, int N) {
+    GmPlan p;
+    p.M_pad = ceil_div64(M > 0 ? M : 1, GM_BM) * GM_BM;
+    p.n_mtiles = (int)(p.M_pad / GM_BM);
+    p.R_pad_max = ceil_div64((R > 0 ? R : 1) + (int64_t)N * (GM_BN - 1), GM_BN) * GM_BN;
+    p.max_rtiles = (int)(p.R_pad_max / GM_BN);
+    size_t o = 0;
+    p.off_ctrl = o; o = align_up(o + sizeof(GmCtrl), 1024);
+    p.off_tile_obj = o; o = align_up(o + (size_t)p.max_rtiles * sizeof(int), 1024);
+    p.off_xs = o; o = align_up(o + (size_t)p.M_pad * sizeof(float), 1024);
+    p.off_ysn = o; o = align_up(o + (size_t)p.R_pad_max * sizeof(float), 1024);
+    p.off_best = o; o = align_up(o + (size_t)p.M_pad * N * sizeof(int), 1024);
+    p.off_A = o; o = align_up(o + (size_t)p.n_mtiles * GM_UNIT_BYTES, 1024);
+    p.off_B = o; o = align_up(o + (size_t)(p.R_pad_max / GM_UNIT_ROWS) * GM_UNIT_BYTES, 1024);
+    p.total = o + 1024;     // slack so the base can be aligned to 1024 bytes
+    return p;
+}
+
+bool gm_umma_supported(int C, int N, int k) { return k == 1 && C >= 1 && C <= GM_MAXC && N >= 1 && N <= GM_MAXN; }
+
+size_t gm_umma_workspace_bytes(int64_t M, int64_t R, int N) { return gm_plan(M, R, N).total; }
+
+int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t R, const int32_t* labels,
+                             const float* query, int64_t qps, int64_t qcs, int64_t M, int C, int N,
+                             int normalize, float* mem_frame, float* out, void* ws, size_t ws_bytes,
+                             cudaStream_t stream) {
+    GmPlan p = gm_plan(M, R, N);
+    if (ws_bytes < p.total) { set_error("global match: workspace too small (%zu < %zu)", ws_bytes, p.total); return MANET_E_WORKSPACE; }
+    if (M <= 0) return 0;
+    uint8_t* wbase = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(ws), 1024));
+    GmCtrl* ctrl = reinterpret_cast<GmCtrl*>(wbase + p.off_ctrl);
+    int* tile_obj = reinterpret_cast<int*>(wbase + p.off_tile_obj);
+    float* xs = reinterpret_cast<float*>(wbase + p.off_xs);
+    float* ysn = reinterpret_cast<float*>(wbase + p.off_ysn);
+    int* best = reinterpret_cast<int*>(wbase + p.off_best);
+    uint8_t* Aimg = wbase + p.off_A;
+    uint8_t* Bimg = wbase + p.off_B;
+
+    cudaError_t e = cudaMemsetAsync(ctrl, 0, sizeof(GmCtrl), stream);
+    if (e != cudaSuccess) { set_error("global match: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+    const int64_t items = R + M;
+    unsigned g1 = (unsigned)(ceil_div64(items, 256) < 148 * 8 ? ceil_div64(items, 256) : 148 * 8);
+    gm_scan_kernel<<<g1, 256, 0, stream>>>(ref, rps, rcs, R, labels, query, qps, qcs, M, C, N, ctrl, best, p.M_pad * N);
+    const int nb_ref = (int)ceil_div64(R, 256), nb_q = (int)ceil_div64(p.M_pad, 256);
+    gm_convert_kernel<<<nb_ref + nb_q + N, 256, 0, stream>>>(ref, rps, rcs, R, labels, query, qps, qcs, M, p.M_pad, C, N,
+                                                             nb_ref, nb_q, ctrl, Aimg, Bimg, xs, ysn, tile_obj);
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(gm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_TOTAL);
+    }
+    const int ksteps = (C + 15) / 16;
+    profile_begin(PROF_GLOBAL_UMMA, stream);
+    gm_umma_kernel<<<sm_count, GM_THREADS, GM_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles, N, ksteps);
+    profile_end(PROF_GLOBAL_UMMA, stream);
+    gm_finalize_kernel<<<(unsigned)ceil_div64(M * N, 256), 256, 0, stream>>>(best, xs, ctrl, M, N, normalize, mem_frame, out);
+    return check_launch("global match (tcgen05) kernels");
+}
+
+}  // namespace manet

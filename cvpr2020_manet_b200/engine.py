@@ -1,0 +1,125 @@
+"""The matching half of one propagation / interaction step, i.e. everything
+``IntVOS.prop_seghead`` (IntVOS.py:600-661) and ``IntVOS.int_seghead`` (:696-736) do before
+the segmentation head, plus the host-buffer session used for end-to-end timing."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._device import check
+from .config import cfg
+from .memory import (global_map_read_update, local_map_init_for_annotated_frame, local_map_store_select)
+from .networks.IntVOS import (local_previous_frame_nearest_neighbor_features_per_object,
+                              nearest_neighbor_features_per_object)
+
+
+def prop_matching_step(ref_emb, prev_emb, cur_emb, ref_scribble_label, prev_label, n_objects,
+                       k_nearest_neighbors=1, max_distance=None, global_map_tmp_dic=None, local_map_dics=None,
+                       seq_name="seq", frame=0, interaction_num=1, start_annotated_frame=0):
+    """``ref_emb/prev_emb/cur_emb``: ``[C,H,W]`` CUDA tensors; labels ``[H,W]`` int32 at embedding
+    resolution; ``n_objects`` = gt_ids[n].  Returns ``(global_map, local_map)``, both ``[1,H,W,N,1]``."""
+    d = cfg.MODEL_MAX_LOCAL_DISTANCE if max_distance is None else max_distance
+    ref, prev, cur = ref_emb.permute(1, 2, 0), prev_emb.permute(1, 2, 0), cur_emb.permute(1, 2, 0)
+    mem_slot = None
+    if global_map_tmp_dic is not None:
+        if seq_name not in global_map_tmp_dic:
+            h, w = cur.shape[:2]
+            global_map_tmp_dic[seq_name] = torch.ones((104, h, w, int(n_objects) + 1, 1), dtype=torch.float32,
+                                                      device=cur.device)
+        mem_slot = global_map_tmp_dic[seq_name][int(frame)]
+    g, ids = nearest_neighbor_features_per_object(ref, cur, ref_scribble_label.unsqueeze(-1), k_nearest_neighbors,
+                                                  n_objects, n_chunks=10, normalize=True, memory_frame=mem_slot)
+    loc = local_previous_frame_nearest_neighbor_features_per_object(prev, cur, prev_label.unsqueeze(-1), ids, d)
+    if local_map_dics is not None:
+        loc, local_map_dics = local_map_store_select(local_map_dics, seq_name, frame, interaction_num,
+                                                     start_annotated_frame, loc)
+    return g, loc
+
+
+def int_matching_step(ref_emb, scribble_label, n_objects, max_distance=None, global_map_tmp_dic=None,
+                      local_map_dics=None, seq_name="seq", frame=0, interaction_num=1):
+    """Interaction branch: local self-match of the annotated frame merged into the global-map
+    memory; the frame's local-map score for this round is reset (IntVOS.py:696-736).
+    Returns ``(local_map, merged_global_map)``."""
+    d = cfg.MODEL_MAX_LOCAL_DISTANCE if max_distance is None else max_distance
+    ref = ref_emb.permute(1, 2, 0)
+    ids = torch.arange(0, int(n_objects) + 1, dtype=torch.int32, device=ref.device)
+    loc = local_previous_frame_nearest_neighbor_features_per_object(ref, ref, scribble_label.unsqueeze(-1), ids, d)
+    merged = global_map_read_update(global_map_tmp_dic, seq_name, frame, loc)
+    if local_map_dics is not None:
+        local_map_init_for_annotated_frame(local_map_dics, seq_name, frame, interaction_num, loc)
+    return loc, merged
+
+
+class MatchingSession:
+    """Host-buffer propagation steps through ``manet_session_*`` (include/manet_b200.h): the caller
+    fills pinned host buffers with ``[C,H,W]`` embeddings and ``[H,W]`` labels, ``step_host`` uploads
+    them, runs global matching (+normalise, +global-map memory) and local matching (+local-map memory)
+    and downloads the two ``[H,W,N]`` maps."""
+
+    def __init__(self, height, width, channels, n_ids, max_distance=12, n_frames=104):
+        self._lib = _lib.lib()
+        self.shape = (height, width, channels, n_ids)
+        self._h = self._lib.manet_session_create(height, width, channels, n_ids, max_distance, n_frames)
+        if not self._h:
+            raise _lib.ManetError("manet_session_create failed: " + self._lib.manet_last_error().decode())
+        ptrs = [ctypes.c_void_p() for _ in range(7)]
+        check(self._lib.manet_session_host_buffers(self._h, *[ctypes.byref(p) for p in ptrs]), "manet_session_host_buffers")
+        px = height * width
+
+        def view(p, n, dtype):
+            ctype = ctypes.c_float if dtype == np.float32 else ctypes.c_int32
+            return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctype)), shape=(n,))
+
+        self.ref = view(ptrs[0], px * channels, np.float32).reshape(channels, height, width)
+        self.prev = view(ptrs[1], px * channels, np.float32).reshape(channels, height, width)
+        self.cur = view(ptrs[2], px * channels, np.float32).reshape(channels, height, width)
+        self.ref_labels = view(ptrs[3], px, np.int32).reshape(height, width)
+        self.prev_labels = view(ptrs[4], px, np.int32).reshape(height, width)
+        self.out_global = view(ptrs[5], px * n_ids, np.float32).reshape(height, width, n_ids)
+        self.out_local = view(ptrs[6], px * n_ids, np.float32).reshape(height, width, n_ids)
+
+    @property
+    def h2d_bytes_per_step(self):
+        h, w, c, _ = self.shape
+        return 3 * h * w * c * 4 + 2 * h * w * 4
+
+    @property
+    def d2h_bytes_per_step(self):
+        h, w, _, n = self.shape
+        return 2 * h * w * n * 4
+
+    def step_host(self, frame, interaction_num=1, start_annotated_frame=0, drop_unlabelled=True):
+        flags = _lib.GM_DROP_UNLAB if drop_unlabelled else 0
+        check(self._lib.manet_session_step_host(self._h, frame, interaction_num, start_annotated_frame, flags),
+              "manet_session_step_host")
+        return self.out_global, self.out_local
+
+    def upload(self):
+        check(self._lib.manet_session_upload(self._h), "manet_session_upload")
+
+    def step_device(self, frame, interaction_num=1, start_annotated_frame=0, drop_unlabelled=True):
+        flags = _lib.GM_DROP_UNLAB if drop_unlabelled else 0
+        check(self._lib.manet_session_step_device(self._h, frame, interaction_num, start_annotated_frame, flags),
+              "manet_session_step_device")
+
+    def sync(self):
+        check(self._lib.manet_session_sync(self._h), "manet_session_sync")
+
+    @property
+    def stream(self):
+        return self._lib.manet_session_stream(self._h)
+
+    def close(self):
+        if self._h:
+            self._lib.manet_session_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

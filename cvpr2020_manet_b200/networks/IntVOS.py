@@ -1,0 +1,291 @@
+"""Drop-in replacements for the matching functions of the reference's ``networks/IntVOS.py``
+(lines 23-434).  Same names, same arguments, same return shapes -- but every function runs
+hand-written sm_100a kernels through the C ABI in ``include/manet_b200.h``; CPU tensors raise
+``TypeError`` (there is no fallback).
+
+The nn.Module classes of the reference file (IntVOS, DynamicSegHead, ...) are callers of this
+path, not part of it, and are out of scope.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from .. import _lib
+from .._device import as_i32_labels, check, pixel_view, require_cuda, require_f32, stream_ptr, workspace
+from ..config import cfg
+
+USE_CORRELATION_COST = False          # IntVOS.py:15 (kept for API compatibility)
+MODEL_UNFOLD = True                   # IntVOS.py:16
+WRONG_LABEL_PADDING_DISTANCE = 1e20   # IntVOS.py:17
+FORCE_SIMT_ENGINE = False             # debugging/tests: route global matching to the fp32 CUDA-core kernel
+
+
+# --------------------------------------------------------------------------- global matching
+def _pairwise_distances(x, y, ys=None):
+    """``d[i,j] = |x_i|^2 + |y_j|^2 - 2 x_i.y_j`` for x [n,C], y [m,C] (IntVOS.py:23-40).
+    Returns ``(d [n,m], ys [1,m])``; a cached ``ys`` is used as given."""
+    x, n, c, xps, xcs = pixel_view(x, "x")
+    y, m, c2, yps, ycs = pixel_view(y, "y")
+    if c != c2:
+        raise RuntimeError(f"feature dims differ: {c} vs {c2}")
+    dev = x.device
+    d = torch.empty((n, m), dtype=torch.float32, device=dev)
+    ys_in = None
+    if ys is not None:
+        require_f32(ys, "ys")
+        ys_in = ys.reshape(-1).contiguous()
+        if ys_in.numel() != m:
+            raise RuntimeError("ys must hold one squared norm per row of y")
+    ys_out = torch.empty((1, m), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().manet_pairwise_sqdist(
+            x.data_ptr(), xps, xcs, n, y.data_ptr(), yps, ycs, m, c, d.data_ptr(),
+            ys_in.data_ptr() if ys_in is not None else None, ys_out.data_ptr(), stream_ptr(dev)),
+            "manet_pairwise_sqdist")
+    return d, ys_out
+
+
+def _flattened_pairwise_distances(reference_embeddings, query_embeddings, ys):
+    """[..., C] reference x [..., C] query -> ``(dists [M,R], ys)`` (IntVOS.py:43-59)."""
+    return _pairwise_distances(query_embeddings, reference_embeddings, ys)
+
+
+def _row_sqnorm(t):
+    t, n, c, ps, cs = pixel_view(t, "embeddings")
+    out = torch.empty((1, n), dtype=torch.float32, device=t.device)
+    with torch.cuda.device(t.device):
+        check(_lib.lib().manet_row_sqnorm(t.data_ptr(), ps, cs, n, c, out.data_ptr(), stream_ptr(t.device)),
+              "manet_row_sqnorm")
+    return out
+
+
+def _nn_features_per_object_for_chunk(reference_embeddings, query_embeddings, wrong_label_mask,
+                                      k_nearest_neighbors, ys):
+    """Per-object k-NN distance for one chunk given the explicit [N,R] wrong-label mask
+    (IntVOS.py:62-97).  Returns ``(features [m,N,1], ys [1,R])``."""
+    ref, r, c, rps, rcs = pixel_view(reference_embeddings, "reference_embeddings")
+    qry, m, c2, qps, qcs = pixel_view(query_embeddings, "query_embeddings")
+    require_cuda(wrong_label_mask, "wrong_label_mask")
+    n_obj = wrong_label_mask.shape[0]
+    if wrong_label_mask.shape[1] != r or c != c2:
+        raise RuntimeError("wrong_label_mask must be [n_objects, n_reference]; feature dims must agree")
+    k = int(k_nearest_neighbors)
+    if k > r:
+        raise RuntimeError(f"k ({k}) out of range for {r} reference pixels (torch.topk would raise, IntVOS.py:87)")
+    mask = wrong_label_mask.to(torch.uint8).contiguous()
+    dev = qry.device
+    out = torch.empty((m, n_obj, 1), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().manet_global_match_masked(
+            ref.data_ptr(), rps, rcs, r, mask.data_ptr(), qry.data_ptr(), qps, qcs, m, c, n_obj, k,
+            out.data_ptr(), None, 0, stream_ptr(dev)), "manet_global_match_masked")
+    if ys is None:
+        ys = _row_sqnorm(ref)
+    return out, ys
+
+
+def _selected_pixel(ref_labels_flat, ref_emb_flat):
+    """Keep the reference pixels whose label is not -1, order preserved (IntVOS.py:100-109).
+    Returns ``(labels [R'], embeddings [R',C])``; one host sync to learn R' (the reference's
+    masked_select syncs too)."""
+    require_cuda(ref_labels_flat, "ref_labels_flat")
+    emb, r, c, ps, cs = pixel_view(ref_emb_flat, "ref_emb_flat")
+    dev = emb.device
+    labels = as_i32_labels(ref_labels_flat, "ref_labels_flat")
+    if labels.numel() != r:
+        raise RuntimeError("labels and embeddings disagree on the number of pixels")
+    out_lab = torch.empty(r, dtype=torch.int32, device=dev)
+    out_emb = torch.empty((r, c), dtype=torch.float32, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    L = _lib.lib()
+    ws_bytes = L.manet_select_labelled_workspace_bytes(r)
+    ws = workspace(dev, ws_bytes, "select")
+    with torch.cuda.device(dev):
+        check(L.manet_select_labelled(labels.data_ptr(), r, emb.data_ptr(), ps, cs, c, out_lab.data_ptr(),
+                                      out_emb.data_ptr(), count.data_ptr(), ws.data_ptr(), ws.numel(),
+                                      stream_ptr(dev)), "manet_select_labelled")
+    n = int(count.item())
+    out_lab, out_emb = out_lab[:n], out_emb[:n]
+    if ref_labels_flat.dtype != torch.int32:
+        out_lab = out_lab.to(ref_labels_flat.dtype)
+    return out_lab, out_emb
+
+
+def _global_match_raw(ref, r, rps, rcs, labels_i32, qry, m, qps, qcs, c, n_obj, k, flags=0, mem_frame=None):
+    dev = qry.device
+    L = _lib.lib()
+    if FORCE_SIMT_ENGINE:
+        flags |= _lib.GM_ENGINE_SIMT
+    out = torch.empty((m, n_obj, 1), dtype=torch.float32, device=dev)
+    ws_bytes = L.manet_global_match_workspace_bytes(m, r, c, n_obj, k)
+    ws = workspace(dev, ws_bytes, "global")
+    with torch.cuda.device(dev):
+        check(L.manet_global_match(
+            ref.data_ptr() if r else None, rps, rcs, r, labels_i32.data_ptr() if r else None,
+            qry.data_ptr(), qps, qcs, m, c, n_obj, k, flags,
+            mem_frame.data_ptr() if mem_frame is not None else None, out.data_ptr(),
+            ws.data_ptr(), ws.numel(), stream_ptr(dev)), "manet_global_match")
+    return out
+
+
+def _nearest_neighbor_features_per_object_in_chunks(reference_embeddings_flat, query_embeddings_flat,
+                                                    reference_labels_flat, ref_obj_ids, k_nearest_neighbors,
+                                                    n_chunks):
+    """[R,C], [M,C], [R], ids -> ``[M, n_objects, 1]`` (IntVOS.py:113-157).  ``n_chunks`` is
+    accepted and ignored: chunking only bounds the reference's [m,N,R] temporary, which this
+    implementation never builds."""
+    del n_chunks
+    ref, r, c, rps, rcs = pixel_view(reference_embeddings_flat, "reference_embeddings_flat")
+    qry, m, c2, qps, qcs = pixel_view(query_embeddings_flat, "query_embeddings_flat")
+    if c != c2:
+        raise RuntimeError("feature dims differ")
+    labels = as_i32_labels(reference_labels_flat, "reference_labels_flat")
+    ids = ref_obj_ids.reshape(-1)
+    n_obj = ids.numel()
+    k = int(k_nearest_neighbors)
+    consecutive = bool(torch.equal(ids.to("cpu", torch.int64), torch.arange(n_obj)))
+    if not consecutive:
+        # arbitrary id sets: build the explicit mask the reference builds (IntVOS.py:137)
+        if cfg.TEST_MODE:
+            reference_labels_flat, reference_embeddings_flat = _selected_pixel(reference_labels_flat,
+                                                                               reference_embeddings_flat)
+        wrong = reference_labels_flat.reshape(1, -1) != ids.to(reference_labels_flat.device).reshape(-1, 1)
+        feats, _ = _nn_features_per_object_for_chunk(reference_embeddings_flat, query_embeddings_flat, wrong, k, None)
+        return feats
+    if k > 1:
+        kept = int((labels != -1).sum().item()) if cfg.TEST_MODE else r
+        if k > kept:
+            raise RuntimeError(f"k ({k}) out of range for {kept} reference pixels (torch.topk would raise, IntVOS.py:87)")
+    flags = _lib.GM_DROP_UNLAB if cfg.TEST_MODE else 0
+    return _global_match_raw(ref, r, rps, rcs, labels, qry, m, qps, qcs, c, n_obj, k, flags)
+
+
+def nearest_neighbor_features_per_object(reference_embeddings, query_embeddings, reference_labels,
+                                         k_nearest_neighbors, gt_ids=None, n_chunks=100, *,
+                                         normalize=False, memory_frame=None):
+    """Distance from every query pixel to its nearest reference pixel of each object
+    (IntVOS.py:160-210).
+
+    reference_embeddings [..., C] (any leading shape; a multi-frame memory is a taller map),
+    query_embeddings [h,w,C], reference_labels [..., 1] int, ``gt_ids`` = number of objects
+    (0-d tensor / int) or None.  Returns ``(nn_features [1,h,w,N,1] float32, gt_ids [N] int32)``
+    with RAW squared distances and 1e20 for objects absent from the reference.
+
+    Keyword-only extensions (not in the reference): ``normalize=True`` fuses the caller-side
+    ``(sigmoid(x)-0.5)*2`` of IntVOS.py:611-612; ``memory_frame`` (a ``[h,w,N,1]`` slice of the
+    global-map memory) additionally fuses the running-min update of IntVOS.py:620-622.
+    """
+    assert reference_embeddings.size()[:2] == reference_labels.size()[:2]
+    require_f32(query_embeddings, "query_embeddings")
+    h, w, c = query_embeddings.size()
+    dev = query_embeddings.device
+    labels = as_i32_labels(reference_labels, "reference_labels")
+    if gt_ids is None:
+        n_obj = int(labels.max().item()) + 1      # unique(labels)[-1] + 1, IntVOS.py:193-194
+    else:
+        n_obj = int(gt_ids) + 1                   # arange(0, gt_ids + 1), IntVOS.py:200
+    ids = torch.arange(0, n_obj, dtype=torch.int32, device=dev)
+    ref, r, c2, rps, rcs = pixel_view(reference_embeddings, "reference_embeddings")
+    qry, m, _, qps, qcs = pixel_view(query_embeddings, "query_embeddings")
+    if c != c2:
+        raise RuntimeError("feature dims differ")
+    k = int(k_nearest_neighbors)
+    flags = _lib.GM_DROP_UNLAB if cfg.TEST_MODE else 0
+    if k > 1:
+        kept = int((labels != -1).sum().item()) if cfg.TEST_MODE else r
+        if k > kept:
+            raise RuntimeError(f"k ({k}) out of range for {kept} reference pixels (torch.topk would raise, IntVOS.py:87)")
+    mem = None
+    if memory_frame is not None:
+        require_f32(memory_frame, "memory_frame")
+        if not normalize:
+            raise ValueError("memory_frame requires normalize=True (the memory holds normalised maps)")
+        if memory_frame.numel() != m * n_obj or not memory_frame.is_contiguous():
+            raise ValueError("memory_frame must be a contiguous [h,w,N,1] slice of the global-map memory")
+        mem = memory_frame
+    if normalize:
+        flags |= _lib.GM_NORMALIZE
+    out = _global_match_raw(ref, r, rps, rcs, labels, qry, m, qps, qcs, c, n_obj, k, flags, mem)
+    return out.view(1, h, w, n_obj, 1), ids
+
+
+# --------------------------------------------------------------------------- local matching
+def _hwc_strides(t, name):
+    require_f32(t, name)
+    if t.dim() != 3:
+        raise RuntimeError(f"{name} must be [height, width, feature_dim]")
+    return t.stride(0), t.stride(1), t.stride(2)
+
+
+def local_pairwise_distances2(x, y, max_distance=9):
+    """Windowed squared distances between x[y,x] and y[y+dy,x+dx] at half resolution,
+    normalised to [0,1] and bilinearly upsampled: ``[H, W, (2d+1)^2]`` (IntVOS.py:266-296)."""
+    if not cfg.MODEL_LOCAL_DOWNSAMPLE:
+        raise NotImplementedError("MODEL_LOCAL_DOWNSAMPLE=False (IntVOS.py:299-313) is not part of the live path")
+    xs = _hwc_strides(x, "x")
+    ysd = _hwc_strides(y, "y")
+    if x.shape != y.shape:
+        raise RuntimeError("x and y must have the same shape")
+    h, w, c = x.shape
+    d = int(max_distance)
+    dev = x.device
+    L = _lib.lib()
+    out = torch.empty((h, w, (2 * d + 1) ** 2), dtype=torch.float32, device=dev)
+    ws = workspace(dev, L.manet_local_match_workspace_bytes(h, w, c, 1, d), "local")
+    with torch.cuda.device(dev):
+        check(L.manet_local_window_distances(x.data_ptr(), *xs, y.data_ptr(), *ysd, h, w, c, d, out.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), stream_ptr(dev)),
+              "manet_local_window_distances")
+    return out
+
+
+def local_pairwise_distances(x, y, max_distance=9):
+    """Same quantity as :func:`local_pairwise_distances2`; the reference computes it through a
+    correlation op (IntVOS.py:212-265, dead: USE_CORRELATION_COST=False)."""
+    return local_pairwise_distances2(x, y, max_distance)
+
+
+def cross_correlate(x, y, max_distance=9):
+    """Un-normalised local cross-correlation ``[H, W, (2d+1)^2]`` of x with y (IntVOS.py:318-341;
+    the historical implementation multiplied the Correlation op's channel mean back by C,
+    ._bak/networks_old/IntVOS.py:264-274)."""
+    from ..correlation_package.correlation import Correlation
+    require_f32(x, "x")
+    require_f32(y, "y")
+    d = int(max_distance)
+    c = x.shape[-1]
+    op = Correlation(pad_size=d, kernel_size=1, max_displacement=d, stride1=1, stride2=1, corr_multiply=1)
+    corr = op(x.permute(2, 0, 1).unsqueeze(0), y.permute(2, 0, 1).unsqueeze(0))
+    return (corr * c).squeeze(0).permute(1, 2, 0)
+
+
+def local_previous_frame_nearest_neighbor_features_per_object(prev_frame_embedding, query_embedding,
+                                                              prev_frame_labels, gt_ids, max_distance=12):
+    """Nearest-neighbour features restricted to a (2d+1)^2 window around each pixel
+    (IntVOS.py:345-434).  prev/query [H,W,C], labels [H,W,1], gt_ids [N] ->
+    ``[1,H,W,N,1]`` float32 in [0,1] (already normalised)."""
+    if not cfg.MODEL_LOCAL_DOWNSAMPLE:
+        raise NotImplementedError("MODEL_LOCAL_DOWNSAMPLE=False (IntVOS.py:299-313) is not part of the live path")
+    ps = _hwc_strides(prev_frame_embedding, "prev_frame_embedding")
+    qs = _hwc_strides(query_embedding, "query_embedding")
+    if prev_frame_embedding.shape != query_embedding.shape:
+        raise RuntimeError("prev_frame_embedding and query_embedding must have the same shape")
+    h, w, c = query_embedding.shape
+    dev = query_embedding.device
+    labels = as_i32_labels(prev_frame_labels, "prev_frame_labels")
+    if labels.numel() != h * w:
+        raise RuntimeError("prev_frame_labels must be [height, width, 1]")
+    require_cuda(gt_ids, "gt_ids")
+    ids = gt_ids.reshape(-1).to(torch.int32).contiguous()
+    n_obj = ids.numel()
+    d = int(max_distance)
+    L = _lib.lib()
+    out = torch.empty((1, h, w, n_obj, 1), dtype=torch.float32, device=dev)
+    ws = workspace(dev, L.manet_local_match_workspace_bytes(h, w, c, n_obj, d), "local")
+    with torch.cuda.device(dev):
+        check(L.manet_local_match(prev_frame_embedding.data_ptr(), *ps, query_embedding.data_ptr(), *qs,
+                                  labels.data_ptr(), ids.data_ptr(), h, w, c, n_obj, d, out.data_ptr(),
+                                  ws.data_ptr(), ws.numel(), stream_ptr(dev)), "manet_local_match")
+    return out

@@ -1,0 +1,220 @@
+/*
+ * manet_b200.h -- C ABI of the B200-native MANet matching + map-memory hot path.
+ *
+ * Every entry point takes plain device (or, where stated, host) pointers, sizes,
+ * element strides and a CUDA stream; nothing here depends on PyTorch.  All entry
+ * points enqueue work on `stream` and return immediately (no host sync unless
+ * stated); the return value is 0 on success or a non-zero code (a cudaError_t for
+ * CUDA failures, MANET_E_* otherwise) with a message available from
+ * manet_last_error().  Outputs are caller-allocated; inputs are never modified;
+ * map memories are updated in place (they stay owned by the caller), mirroring the
+ * reference's ownership rules.
+ *
+ * The reference has no FFI of its own for the matching path (it is inline torch
+ * code); each function below cites the reference lines whose work it replaces.
+ * The one native interface the reference does have is the pybind module
+ * `correlation_cuda` (correlation_package/correlation_cuda.cc:169-172);
+ * manet_correlation_forward/backward are its C-ABI equivalents.
+ *
+ * "file:line" citations are relative to the reference repository root.
+ */
+#ifndef MANET_B200_H_
+#define MANET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* manet_stream_t; /* a cudaStream_t */
+
+#define MANET_ABI_VERSION 1
+
+/* non-CUDA error codes (CUDA errors are returned as their positive cudaError_t) */
+#define MANET_E_INVALID   (-1) /* bad argument (null pointer, size, unsupported combination) */
+#define MANET_E_WORKSPACE (-2) /* workspace too small */
+#define MANET_E_ARCH      (-3) /* device is not sm_100 (no fallback exists by design) */
+
+/* global-match flags */
+#define MANET_GM_NORMALIZE   1u /* apply (sigmoid(x)-0.5)*2 to the result (IntVOS.py:611-612) */
+#define MANET_GM_DROP_UNLAB  2u /* drop reference pixels labelled -1 first (cfg.TEST_MODE, IntVOS.py:135-136) */
+#define MANET_GM_ENGINE_SIMT 4u /* force the fp32 CUDA-core kernel instead of the tcgen05 kernel */
+
+/* dtype codes for the Correlation op (AT_DISPATCH_FLOATING_TYPES_AND_HALF, correlation_cuda_kernel.cu:386) */
+#define MANET_DT_F32 0
+#define MANET_DT_F16 1
+#define MANET_DT_F64 2
+
+int manet_abi_version(void);
+/* Message of the last failing call on this host thread ("" if none). */
+const char* manet_last_error(void);
+/* 0 if the current CUDA device can run this library (compute capability 10.x). */
+int manet_check_device(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Global matching: nearest_neighbor_features_per_object (networks/IntVOS.py:160-210) with its
+ * helpers _nearest_neighbor_features_per_object_in_chunks (:113-157), _selected_pixel
+ * (:100-109), _nn_features_per_object_for_chunk (:62-97), _pairwise_distances (:23-40).
+ *
+ *   out[m, o] = min over reference pixels r with label o of |q_m - r|^2   (k == 1)
+ *             = mean of the k smallest (short lists padded with their largest) (k > 1)
+ *             = 1e20 when no reference pixel carries label o (k == 1)
+ *
+ * ref    : R reference pixels, element (r, c) at ref[r*ref_pix_stride + c*ref_ch_stride]
+ * labels : [R] int32, object ids; ids outside [0, N) never match; -1 dropped with DROP_UNLAB
+ * query  : M query pixels, element (m, c) at query[m*q_pix_stride + c*q_ch_stride]
+ * out    : [M, N] fp32, object fastest (the reference's [1,h,w,N,1])
+ * mem_frame : optional [M, N] slot of the global-map memory (IntVOS.py:615-622); when non-NULL
+ *             (requires NORMALIZE) out = min(out, mem_frame) and mem_frame = out.
+ * Chunking (n_chunks) is a memory workaround in the reference and has no equivalent here: the
+ * query x reference distance matrix is never materialised.
+ * ------------------------------------------------------------------------------------------ */
+size_t manet_global_match_workspace_bytes(int64_t M, int64_t R, int C, int N, int k);
+
+int manet_global_match(const float* ref, int64_t ref_pix_stride, int64_t ref_ch_stride, int64_t R,
+                       const int32_t* labels,
+                       const float* query, int64_t q_pix_stride, int64_t q_ch_stride, int64_t M,
+                       int C, int N, int k, uint32_t flags,
+                       float* mem_frame, float* out,
+                       void* workspace, size_t workspace_bytes, manet_stream_t stream);
+
+/* Same reduction with an explicit mask instead of labels: wrong_label_mask[o*R + r] != 0 means
+ * reference r does NOT belong to object o (the [N,R] bool tensor of IntVOS.py:137, consumed by
+ * _nn_features_per_object_for_chunk, IntVOS.py:62-97).  CUDA-core fp32 kernel. */
+int manet_global_match_masked(const float* ref, int64_t ref_pix_stride, int64_t ref_ch_stride, int64_t R,
+                              const uint8_t* wrong_label_mask,
+                              const float* query, int64_t q_pix_stride, int64_t q_ch_stride, int64_t M,
+                              int C, int N, int k, float* out,
+                              void* workspace, size_t workspace_bytes, manet_stream_t stream);
+
+/* d[i, j] = |x_i|^2 + |y_j|^2 - 2 x_i.y_j, dense [n, m] fp32 (_pairwise_distances, IntVOS.py:23-40).
+ * ys_in (optional, [m]): cached |y_j|^2 to use instead of recomputing (the `ys` argument of the
+ * reference, IntVOS.py:34-38); ys_out (optional, [m]) receives the |y_j|^2 that were used. */
+int manet_pairwise_sqdist(const float* x, int64_t x_pix_stride, int64_t x_ch_stride, int64_t n,
+                          const float* y, int64_t y_pix_stride, int64_t y_ch_stride, int64_t m,
+                          int C, float* d, const float* ys_in, float* ys_out, manet_stream_t stream);
+
+/* out[i] = |x_i|^2 (the torch.sum(x*x, 1) of IntVOS.py:32,35). */
+int manet_row_sqnorm(const float* x, int64_t pix_stride, int64_t ch_stride, int64_t n, int C, float* out,
+                     manet_stream_t stream);
+
+/* Order-preserving compaction of the pixels whose label != -1 (_selected_pixel, IntVOS.py:100-109).
+ * out_labels [R], out_emb [R, C] row-major (capacity R); *count_dev (device int64) receives R'.
+ * Bit-exact copy of the surviving rows. */
+size_t manet_select_labelled_workspace_bytes(int64_t R);
+int manet_select_labelled(const int32_t* labels, int64_t R,
+                          const float* emb, int64_t pix_stride, int64_t ch_stride, int C,
+                          int32_t* out_labels, float* out_emb, int64_t* count_dev,
+                          void* workspace, size_t workspace_bytes, manet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Local matching: local_previous_frame_nearest_neighbor_features_per_object
+ * (networks/IntVOS.py:345-434) over local_pairwise_distances2 (:266-296, live branch).
+ * prev/query : [H, W, C] views, element (y, x, c) at base[y*sy + x*sx + c*sc]
+ * labels     : [H, W] int32 contiguous; gt_ids : [N] int32 (device)
+ * out        : [H, W, N] fp32 in [0, 1]
+ * ------------------------------------------------------------------------------------------ */
+size_t manet_local_match_workspace_bytes(int H, int W, int C, int N, int max_distance);
+
+int manet_local_match(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_sc,
+                      const float* query, int64_t q_sy, int64_t q_sx, int64_t q_sc,
+                      const int32_t* labels, const int32_t* gt_ids,
+                      int H, int W, int C, int N, int max_distance, float* out,
+                      void* workspace, size_t workspace_bytes, manet_stream_t stream);
+
+/* The windowed distance volume alone (local_pairwise_distances2(x, y, d), IntVOS.py:266-296):
+ * out [H, W, (2d+1)^2], normalised and bilinearly upsampled. */
+int manet_local_window_distances(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_sc,
+                                 const float* y, int64_t y_sy, int64_t y_sx, int64_t y_sc,
+                                 int H, int W, int C, int max_distance, float* out,
+                                 void* workspace, size_t workspace_bytes, manet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Map memory (networks/IntVOS.py:615-622 / 716-723 and 638-661).
+ * ------------------------------------------------------------------------------------------ */
+/* out = min(f(new_map), mem_frame); mem_frame = out.  f = (sigmoid-0.5)*2 when normalize != 0.
+ * mem_frame may be NULL (then only the optional normalisation is applied). n = h*w*N. */
+int manet_global_map_update(const float* new_map, float* mem_frame, float* out, int64_t n,
+                            int normalize, manet_stream_t stream);
+
+/* Propagation-side local-map memory.  mem_frame_rounds: the [9, n] block of this frame inside
+ * the [104, 9, n] memory; dist_row: the [9] row of this frame inside the [104, 9] table.
+ * Stores new_map into round slot (interaction_num-1), writes dist_value there, then
+ * out = this round's map if interaction_num == 1 or dist_row[r] > dist_row[r-1], else the
+ * previous round's stored map.  The comparison happens on the device (the reference syncs the
+ * host at IntVOS.py:654). */
+int manet_local_map_store_select(const float* new_map, float* mem_frame_rounds, float* dist_row,
+                                 int interaction_num, float dist_value, float* out, int64_t n,
+                                 manet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Correlation op: correlation_cuda.forward / .backward
+ * (correlation_package/correlation_cuda.cc:10-87, 89-167; kernels correlation_cuda_kernel.cu:46-334).
+ * in1, in2 : [B, C, H, W] with element strides (sb, sc, sh, sw) of dtype `dtype`
+ * rin1/rin2: caller scratch, [B, H+2p, W+2p, C] contiguous (zero-padded NHWC copies, filled here)
+ * out      : [B, (2*(md/s2)+1)^2, outH, outW] contiguous
+ * ------------------------------------------------------------------------------------------ */
+int manet_correlation_output_shape(int C, int H, int W, int pad_size, int kernel_size,
+                                   int max_displacement, int stride1, int stride2,
+                                   int* out_channels, int* out_h, int* out_w);
+
+int manet_correlation_forward(const void* in1, const int64_t* in1_strides,
+                              const void* in2, const int64_t* in2_strides,
+                              void* rin1, void* rin2, void* out,
+                              int B, int C, int H, int W,
+                              int pad_size, int kernel_size, int max_displacement,
+                              int stride1, int stride2, int dtype, manet_stream_t stream);
+
+int manet_correlation_backward(const void* in1, const int64_t* in1_strides,
+                               const void* in2, const int64_t* in2_strides,
+                               void* rin1, void* rin2,
+                               const void* grad_out, const int64_t* grad_out_strides,
+                               void* grad_in1, void* grad_in2,
+                               int B, int C, int H, int W,
+                               int pad_size, int kernel_size, int max_displacement,
+                               int stride1, int stride2, int dtype, manet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optional kernel timing for benchmarks (no reference equivalent).  After
+ * manet_profile_enable(n) the launchers bracket their dominant kernels with CUDA events on the
+ * launching stream (slot 0: tcgen05 global-matching kernel, 1: local window-distance kernel,
+ * 2: local upsample/mask/min kernel), up to n records per slot.  manet_profile_read returns the
+ * per-launch durations in milliseconds (synchronise the stream first).  enable(0) turns it off.
+ * ------------------------------------------------------------------------------------------ */
+int manet_profile_enable(int max_records);
+int manet_profile_reset(void);
+int manet_profile_read(int slot, float* ms_out, int capacity, int* n_out);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-buffer frame step: what one iteration of the propagation loop (test.py:237-259 ->
+ * IntVOS.prop_seghead, IntVOS.py:600-661) does before the segmentation head, for callers
+ * that hold their tensors in HOST memory.  A session owns device buffers, pinned staging and
+ * a stream; manet_session_step_host copies the inputs host->device, runs global matching
+ * (+normalise +global-map memory), local matching (+local-map memory) and copies the two
+ * [H,W,N] maps back.  Synchronous on return.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct manet_session manet_session_t;
+
+manet_session_t* manet_session_create(int H, int W, int C, int N, int max_distance, int n_frames);
+void manet_session_destroy(manet_session_t* s);
+/* pinned host staging the caller may fill directly (avoids a pageable copy): returns base
+ * pointers of [C,H,W] fp32 buffers for ref / prev / cur and [H,W] int32 for the two label maps */
+int manet_session_host_buffers(manet_session_t* s, float** ref, float** prev, float** cur,
+                               int32_t** ref_labels, int32_t** prev_labels,
+                               float** out_global, float** out_local);
+int manet_session_step_host(manet_session_t* s, int frame, int interaction_num,
+                            int start_annotated_frame, uint32_t flags);
+/* device-resident variant of the same step (inputs already uploaded by a previous
+ * manet_session_step_host or manet_session_upload): no copies, asynchronous on the session stream */
+int manet_session_upload(manet_session_t* s);
+int manet_session_step_device(manet_session_t* s, int frame, int interaction_num,
+                              int start_annotated_frame, uint32_t flags);
+int manet_session_sync(manet_session_t* s);
+manet_stream_t manet_session_stream(manet_session_t* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MANET_B200_H_ */

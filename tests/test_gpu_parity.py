@@ -1,0 +1,373 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden vectors from the
+unmodified reference, against the CPU oracle on seeded inputs, and through size-independent
+properties at BASELINE.json's full sizes.
+
+Tolerances:
+  * ids / selected pixels / absent-object sentinels / memory selection: bit-exact
+  * RAW global distances: |a-b| <= 2e-5 * max(1, |b|)   (fp32 GEMM summation-order noise)
+  * normalised maps (global after (sigmoid-0.5)*2, local output): <= 1e-5 absolute
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RAW_RTOL = 2e-5
+MAP_ATOL = 1e-5
+
+GLOBAL = ["global_k1_A", "global_k1_B_absent", "global_testmode_scribble", "global_k3_A",
+          "global_multiframe_ref", "global_gtids_none", "global_k2_testmode"]
+LOCAL = ["local_d3_even", "local_d4_odd", "local_d12_window_gt_image", "local_d9_A", "local_d2_scaled"]
+
+
+@pytest.fixture(scope="module")
+def api():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from cvpr2020_manet_b200 import _lib
+    _lib.check(_lib.lib().manet_check_device(), "device check")
+    from cvpr2020_manet_b200.networks import IntVOS
+    return IntVOS
+
+
+@pytest.fixture()
+def cfg_guard():
+    from cvpr2020_manet_b200.config import cfg
+    saved = dict(vars(cfg))
+    yield cfg
+    for k, v in saved.items():
+        setattr(cfg, k, v)
+
+
+def raw_close(got, want, rtol=RAW_RTOL):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    err = np.abs(got - want) / np.maximum(1.0, np.abs(want))
+    return float(err.max())
+
+
+def norm_np(x):
+    x = np.asarray(x, np.float64)
+    with np.errstate(over="ignore"):
+        return (1.0 / (1.0 + np.exp(-x)) - 0.5) * 2.0
+
+
+def cuda(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+# ------------------------------------------------------------------ global matching
+@pytest.mark.parametrize("engine", ["tcgen05", "simt"])
+@pytest.mark.parametrize("name", GLOBAL)
+def test_global_matches_reference_golden(api, golden, cfg_guard, name, engine, monkeypatch):
+    g = golden(name)
+    k = int(g["k"])
+    monkeypatch.setattr(api, "FORCE_SIMT_ENGINE", engine == "simt")
+    cfg_guard.TEST_MODE = bool(g["test_mode"])
+    ref = cuda(g["ref_chw"]).permute(1, 2, 0)
+    qry = cuda(g["query_chw"]).permute(1, 2, 0)
+    lab = cuda(g["labels"]).unsqueeze(-1)
+    gt = torch.tensor(int(g["n_obj"])) if int(g["pass_gt"]) else None
+    out, ids = api.nearest_neighbor_features_per_object(ref, qry, lab, k, gt, n_chunks=int(g["n_chunks"]))
+    assert out.shape == g["out"].shape and out.dtype == torch.float32
+    assert ids.dtype == torch.int32 and np.array_equal(ids.cpu().numpy(), g["ids"])
+    got = out.cpu().numpy()
+    absent = g["out"] == np.float32(1e20)
+    assert np.array_equal(got == np.float32(1e20), absent), "absent-object sentinel must be exactly 1e20"
+    assert raw_close(got[~absent], g["out"][~absent]) <= RAW_RTOL
+    assert np.max(np.abs(norm_np(got) - norm_np(g["out"]))) <= MAP_ATOL
+
+
+@pytest.mark.parametrize("seed,dist", [(0, "A"), (1, "B"), (2, "B")])
+def test_global_vs_oracle_seeded_medium(api, cfg_guard, seed, dist):
+    """Medium size (oracle finishes in seconds): M = 60x107, R = 3 stacked frames, N = 6, incl.
+    -1 labels (TEST_MODE), one absent object; both engines; normalised + memory fused variant."""
+    from oracle import manet_oracle as O
+    gen = torch.Generator().manual_seed(seed)
+    C, H, W, N = 100, 60, 107, 6
+    mk = (lambda *s: torch.rand(*s, generator=gen)) if dist == "A" else (lambda *s: 0.1 * torch.relu(torch.randn(*s, generator=gen)))
+    ref_chw, qry_chw = mk(C, 3 * H, W), mk(C, H, W)
+    lab = torch.randint(0, N, (3 * H // 6 + 1, W // 6 + 1), generator=gen).repeat_interleave(6, 0).repeat_interleave(6, 1)[:3 * H, :W].int()
+    lab[lab == 4] = 0
+    lab[torch.rand(3 * H, W, generator=gen) < 0.3] = -1
+    cfg_guard.TEST_MODE = True
+    want, _ = O.global_match(ref_chw.permute(1, 2, 0), qry_chw.permute(1, 2, 0), lab.unsqueeze(-1), 1,
+                             torch.tensor(N - 1), n_chunks=4, test_mode=True)
+    want = want.numpy()
+    ref, qry, labc = ref_chw.cuda().permute(1, 2, 0), qry_chw.cuda().permute(1, 2, 0), lab.cuda().unsqueeze(-1)
+    out, ids = api.nearest_neighbor_features_per_object(ref, qry, labc, 1, torch.tensor(N - 1), n_chunks=10)
+    got = out.cpu().numpy()
+    absent = want == np.float32(1e20)
+    assert absent[..., 4, 0].all() and np.array_equal(got == np.float32(1e20), absent)
+    assert raw_close(got[~absent], want[~absent]) <= RAW_RTOL
+    assert np.max(np.abs(norm_np(got) - norm_np(want))) <= MAP_ATOL
+    # fused normalise + global-map memory (IntVOS.py:611-622)
+    mem = torch.rand(H, W, N, 1, generator=gen).cuda()
+    mem0 = mem.clone()
+    out2, _ = api.nearest_neighbor_features_per_object(ref, qry, labc, 1, torch.tensor(N - 1), normalize=True,
+                                                       memory_frame=mem)
+    want2 = np.minimum(O.normalize_distance(torch.from_numpy(want)).numpy()[0], mem0.cpu().numpy())
+    assert np.max(np.abs(out2.cpu().numpy()[0] - want2)) <= MAP_ATOL
+    assert torch.equal(out2[0], mem), "memory slot must hold the merged map"
+
+
+def test_global_full_480p_properties(api, cfg_guard):
+    """BASELINE size (M = R = 25 680, C = 100, N = 6).  Size-independent properties:
+    (1) self-matching: a query that is itself a reference pixel of object o has distance ~0 to o;
+    (2) the result is invariant to a permutation of the reference pixels (min is order-free);
+    (3) splitting the reference set in two and taking the element-wise min reproduces the result
+        (the identity behind reference-axis sharding);
+    (4) tcgen05 engine == CUDA-core fp32 engine within tolerance."""
+    from cvpr2020_manet_b200 import _lib
+    gen = torch.Generator().manual_seed(7)
+    C, H, W, N = 100, 120, 214, 6
+    emb = (0.1 * torch.relu(torch.randn(C, H, W, generator=gen))).cuda()
+    lab = torch.randint(0, N, (H // 8, W // 8 + 1), generator=gen).repeat_interleave(8, 0).repeat_interleave(8, 1)[:H, :W].int().cuda()
+    e = emb.permute(1, 2, 0)
+    out, _ = api.nearest_neighbor_features_per_object(e, e, lab.unsqueeze(-1), 1, torch.tensor(N - 1))
+    o = out[0, :, :, :, 0]
+    self_d = torch.gather(o, 2, lab.long().unsqueeze(-1))[..., 0]
+    assert float(self_d.abs().max()) <= 1e-4                      # (1): exact value is 0, fp32 cancellation noise only
+    assert float(o.min()) >= -1e-4
+    flat_e, flat_l = e.reshape(-1, C), lab.reshape(-1)
+    perm = torch.randperm(H * W, generator=gen).cuda()
+    out_p, _ = api.nearest_neighbor_features_per_object(flat_e[perm].view(H, W, C), e, flat_l[perm].view(H, W, 1), 1,
+                                                        torch.tensor(N - 1))
+    assert torch.equal(out_p, out)                                # (2) bit-exact
+    half = (H // 2) * W
+    a, _ = api.nearest_neighbor_features_per_object(flat_e[:half].view(-1, 1, C), e, flat_l[:half].view(-1, 1, 1), 1, torch.tensor(N - 1))
+    b, _ = api.nearest_neighbor_features_per_object(flat_e[half:].view(-1, 1, C), e, flat_l[half:].view(-1, 1, 1), 1, torch.tensor(N - 1))
+    # (3): exact for a fixed operand scale; the tcgen05 engine derives its power-of-two scale from
+    # each reference slice, so the two halves may round differently -> fp32-noise tolerance
+    assert raw_close(torch.minimum(a, b).reshape(-1).cpu().numpy(), out.reshape(-1).cpu().numpy()) <= RAW_RTOL
+    simt = api._global_match_raw(flat_e, H * W, 1, H * W, flat_l.contiguous(), flat_e, H * W, 1, H * W, C, N, 1,
+                                 flags=_lib.GM_ENGINE_SIMT)
+    assert raw_close(out.reshape(-1).cpu().numpy(), simt.reshape(-1).cpu().numpy()) <= RAW_RTOL   # (4)
+
+
+def test_global_helpers_match_oracle(api, golden, cfg_guard):
+    from oracle import manet_oracle as O
+    g = golden("global_k1_A")
+    c = g["ref_chw"].shape[0]
+    ref = torch.from_numpy(g["ref_chw"]).permute(1, 2, 0).reshape(-1, c)
+    qry = torch.from_numpy(g["query_chw"]).permute(1, 2, 0).reshape(-1, c)
+    lab = torch.from_numpy(g["labels"]).reshape(-1)
+    d_want, ys_want = O.pairwise_sqdist(qry, ref)
+    d, ys = api._pairwise_distances(qry.cuda(), ref.cuda())
+    assert d.shape == d_want.shape and ys.shape == ys_want.shape
+    assert raw_close(d.cpu().numpy(), d_want.numpy()) <= RAW_RTOL
+    d2, ys2 = api._flattened_pairwise_distances(ref.cuda(), qry.cuda(), ys)
+    assert torch.equal(ys2.reshape(-1), ys.reshape(-1)) and raw_close(d2.cpu().numpy(), d_want.numpy()) <= RAW_RTOL
+    ids = torch.arange(3).int()
+    wrong = lab.unsqueeze(0) != ids.unsqueeze(1)
+    for k in (1, 3):
+        want, _ = O.nn_features_for_chunk(ref, qry, wrong, k, None)
+        got, ys3 = api._nn_features_per_object_for_chunk(ref.cuda(), qry.cuda(), wrong.cuda(), k, None)
+        assert got.shape == want.shape and raw_close(got.cpu().numpy(), want.numpy()) <= RAW_RTOL
+        assert raw_close(ys3.cpu().numpy(), ys_want.numpy()) <= RAW_RTOL
+    got = api._nearest_neighbor_features_per_object_in_chunks(ref.cuda(), qry.cuda(), lab.cuda(), ids.cuda(), 1, 10)
+    want = O.global_match_flat(ref, qry, lab, ids, 1, 10)
+    assert raw_close(got.cpu().numpy(), want.numpy()) <= RAW_RTOL
+    # non-consecutive ids go through the explicit-mask engine
+    ids2 = torch.tensor([2, 0], dtype=torch.int32)
+    got = api._nearest_neighbor_features_per_object_in_chunks(ref.cuda(), qry.cuda(), lab.cuda(), ids2.cuda(), 1, 10)
+    want = O.global_match_flat(ref, qry, lab, ids2, 1, 10)
+    assert raw_close(got.cpu().numpy(), want.numpy()) <= RAW_RTOL
+
+
+def test_selected_pixel_bit_exact(api, golden):
+    g = golden("selected_pixel")
+    l2, e2 = api._selected_pixel(cuda(g["labels"]), cuda(g["emb"]))
+    assert np.array_equal(l2.cpu().numpy(), g["out_labels"]) and np.array_equal(e2.cpu().numpy(), g["out_emb"])
+    # large, ragged, strided (a [C,H,W] permuted view), and the empty result
+    gen = torch.Generator().manual_seed(1)
+    lab = torch.randint(-1, 4, (120 * 214 + 37,), generator=gen).int()
+    emb_cr = torch.rand(20, lab.numel(), generator=gen)
+    l3, e3 = api._selected_pixel(lab.cuda(), emb_cr.cuda().t())
+    keep = lab != -1
+    assert torch.equal(l3.cpu(), lab[keep]) and torch.equal(e3.cpu(), emb_cr.t()[keep])
+    l4, e4 = api._selected_pixel(torch.full((1000,), -1, dtype=torch.int32).cuda(), torch.rand(1000, 4).cuda())
+    assert l4.numel() == 0 and e4.shape == (0, 4)
+
+
+# ------------------------------------------------------------------ local matching
+@pytest.mark.parametrize("name", LOCAL)
+def test_local_matches_reference_golden(api, golden, name):
+    g = golden(name)
+    prev = cuda(g["prev_chw"]).permute(1, 2, 0)
+    cur = cuda(g["cur_chw"]).permute(1, 2, 0)
+    out = api.local_previous_frame_nearest_neighbor_features_per_object(
+        prev, cur, cuda(g["labels"]).unsqueeze(-1), cuda(g["ids"]), max_distance=int(g["d"]))
+    assert out.shape == g["out"].shape
+    got = out.cpu().numpy()
+    assert np.max(np.abs(got - g["out"])) <= MAP_ATOL
+    assert np.array_equal(got == 1.0, g["out"] == 1.0), "saturated / absent entries must be exactly 1.0"
+    if "window" in g:
+        win = api.local_pairwise_distances2(cur, prev, max_distance=int(g["d"]))
+        assert np.max(np.abs(win.cpu().numpy() - g["window"])) <= MAP_ATOL
+
+
+@pytest.mark.parametrize("d", [9, 12, 14])
+def test_local_vs_oracle_half_480p(api, d):
+    """60x106 frame, N = 6, noisy-copy embeddings (distances in the transform's sensitive range),
+    d = 14 exercises the generic-window kernel."""
+    from oracle import manet_oracle as O
+    gen = torch.Generator().manual_seed(d)
+    C, H, W, N = 100, 60, 106, 6
+    prev = 0.1 * torch.relu(torch.randn(C, H, W, generator=gen))
+    cur = prev + 0.02 * torch.randn(C, H, W, generator=gen)
+    lab = torch.randint(0, N, (H // 5, W // 5 + 1), generator=gen).repeat_interleave(5, 0).repeat_interleave(5, 1)[:H, :W].int()
+    lab[lab == 3] = 1
+    ids = torch.arange(N).int()
+    want = O.local_match(prev.permute(1, 2, 0), cur.permute(1, 2, 0), lab.unsqueeze(-1), ids, d).numpy()
+    got = api.local_previous_frame_nearest_neighbor_features_per_object(
+        prev.cuda().permute(1, 2, 0), cur.cuda().permute(1, 2, 0), lab.cuda().unsqueeze(-1), ids.cuda(), d).cpu().numpy()
+    assert np.max(np.abs(got - want)) <= MAP_ATOL
+    assert (got[..., 3, 0] == 1.0).all()
+
+
+def test_local_full_480p_properties(api):
+    """Full 480p, d = 12, N = 6: (1) output in [0,1]; (2) self-matching with labels == o everywhere
+    gives 0 for o (offset (0,0) has distance 0) and exactly 1 for every other object;
+    (3) contiguous [H,W,C] input == permuted [C,H,W] view input, bit-exact."""
+    gen = torch.Generator().manual_seed(3)
+    C, H, W, N = 100, 120, 214, 6
+    emb = torch.rand(C, H, W, generator=gen).cuda()
+    e = emb.permute(1, 2, 0)
+    ids = torch.arange(N, dtype=torch.int32).cuda()
+    lab = torch.full((H, W, 1), 2, dtype=torch.int32).cuda()
+    out = api.local_previous_frame_nearest_neighbor_features_per_object(e, e, lab, ids, 12)[0, :, :, :, 0]
+    assert float(out.min()) >= 0.0 and float(out.max()) <= 1.0
+    assert float(out[..., 2].max()) <= 1e-6
+    others = out[..., [0, 1, 3, 4, 5]]
+    inner = others[24:-24, 24:-24]
+    assert bool((inner == 1.0).all())
+    # label 0 leaks in from the zero padding near the border only (IntVOS.py:401-405)
+    assert bool((out[..., [1, 3, 4, 5]] == 1.0).all())
+    lab2 = torch.randint(0, N, (H, W, 1), generator=gen).int().cuda()
+    prev = torch.rand(C, H, W, generator=gen).cuda().permute(1, 2, 0)
+    a = api.local_previous_frame_nearest_neighbor_features_per_object(prev, e, lab2, ids, 12)
+    b = api.local_previous_frame_nearest_neighbor_features_per_object(prev.contiguous(), e.contiguous(), lab2, ids, 12)
+    assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------ map memory
+def test_memory_session_matches_reference_golden(api, golden, cfg_guard):
+    """Replays the 3-round toy session recorded from the reference's own prop_seghead /
+    int_seghead: maps within tolerance, the local-map round selection and the distance table
+    bit-exact."""
+    from cvpr2020_manet_b200 import engine
+    g = golden("memory_session")
+    cfg_guard.TEST_MODE = True
+    embs = cuda(g["embs"])
+    n_obj, d, T = int(g["n_obj"]), int(g["d"]), embs.shape[0]
+    gmem, lmem = {}, ({}, {})
+    for rnd, ann in g["rounds"]:
+        rnd, ann = int(rnd), int(ann)
+        scr = cuda(g[f"r{rnd}_scribble"])
+        engine.int_matching_step(embs[ann], scr, n_obj, d, gmem, lmem, "s", ann, rnd)
+        for f in list(range(ann + 1, T)) + list(range(ann - 1, -1, -1)):
+            prev_f = f - 1 if f > ann else f + 1
+            pl = cuda(g[f"r{rnd}_f{f}_prev_label"])
+            gm, lm = engine.prop_matching_step(embs[ann], embs[prev_f], embs[f], scr, pl, n_obj, 1, d, gmem, lmem,
+                                               "s", f, rnd, ann)
+            gm = gm[0, :, :, :, 0].permute(2, 0, 1).cpu().numpy()
+            lm = lm[0, :, :, :, 0].permute(2, 0, 1).cpu().numpy()
+            assert np.max(np.abs(gm - g[f"r{rnd}_f{f}_global"])) <= MAP_ATOL, (rnd, f)
+            assert np.max(np.abs(lm - g[f"r{rnd}_f{f}_local"])) <= MAP_ATOL, (rnd, f)
+    assert np.max(np.abs(gmem["s"][:T].cpu().numpy() - g["final_global_mem"])) <= MAP_ATOL
+    assert np.max(np.abs(lmem[0]["s"][:T, :3].cpu().numpy() - g["final_local_mem"])) <= MAP_ATOL
+    assert np.array_equal(lmem[1]["s"][:T, :3].cpu().numpy(), g["final_local_dist"])
+    assert tuple(gmem["s"].shape) == (104,) + g["final_global_mem"].shape[1:]
+    assert tuple(lmem[0]["s"].shape[:2]) == (104, 9) and tuple(lmem[1]["s"].shape) == (104, 9)
+
+
+def test_memory_kernels_exact_semantics(api):
+    from cvpr2020_manet_b200 import memory
+    gen = torch.Generator().manual_seed(0)
+    new = torch.rand(1, 5, 7, 3, 1, generator=gen).cuda()
+    gm = {}
+    out = memory.global_map_read_update(gm, "a", 3, new)
+    assert torch.equal(out, new) and torch.equal(gm["a"][3], new[0]) and bool((gm["a"][2] == 1).all())
+    new2 = torch.rand(1, 5, 7, 3, 1, generator=gen).cuda()
+    out2 = memory.global_map_read_update(gm, "a", 3, new2)
+    assert torch.equal(out2, torch.minimum(new, new2)) and torch.equal(gm["a"][3], out2[0])
+    lm = ({}, {})
+    m1 = torch.rand(1, 5, 7, 3, 1, generator=gen).cuda()
+    o1, lm = memory.local_map_store_select(lm, "a", 10, 1, 7, m1)          # round 1 -> current
+    assert torch.equal(o1, m1) and float(lm[1]["a"][10, 0]) == np.float32(1.0 / 3)
+    m2 = torch.rand(1, 5, 7, 3, 1, generator=gen).cuda()
+    o2, lm = memory.local_map_store_select(lm, "a", 10, 2, 2, m2)          # 1/8 < 1/3 -> previous round's map
+    assert torch.equal(o2, m1) and torch.equal(lm[0]["a"][10, 1], m2[0])
+    o3, lm = memory.local_map_store_select(lm, "a", 10, 3, 9, m2)          # 1/1 > 1/8 -> current
+    assert torch.equal(o3, m2)
+    o4, lm = memory.local_map_store_select(lm, "a", 10, 4, 11, m1)         # tie 1/1 vs 1/1 -> previous (strict >)
+    assert torch.equal(o4, m2)
+    with pytest.raises(ZeroDivisionError):
+        memory.local_map_store_select(lm, "a", 10, 5, 10, m1)
+    with pytest.raises(IndexError):
+        memory.local_map_store_select(lm, "a", 10, 10, 3, m1)
+
+
+def test_host_buffer_session_equals_device_api(api, cfg_guard):
+    from cvpr2020_manet_b200 import engine
+    cfg_guard.TEST_MODE = True
+    gen = torch.Generator().manual_seed(5)
+    C, H, W, N, d = 100, 24, 30, 4, 5
+    s = engine.MatchingSession(H, W, C, N, d, n_frames=8)
+    ref, prev, cur = (0.1 * torch.relu(torch.randn(C, H, W, generator=gen)) for _ in range(3))
+    rl = torch.randint(-1, N, (H, W), generator=gen).int()
+    pl = torch.randint(0, N, (H, W), generator=gen).int()
+    s.ref[:], s.prev[:], s.cur[:] = ref.numpy(), prev.numpy(), cur.numpy()
+    s.ref_labels[:], s.prev_labels[:] = rl.numpy(), pl.numpy()
+    gm, lm = {}, ({}, {})
+    for rnd, ann in ((1, 1), (2, 6)):
+        og, ol = s.step_host(3, rnd, ann)
+        wg, wl = engine.prop_matching_step(ref.cuda(), prev.cuda(), cur.cuda(), rl.cuda(), pl.cuda(), N - 1, 1, d, gm, lm,
+                                           "x", 3, rnd, ann)
+        assert np.array_equal(og, wg[0, :, :, :, 0].cpu().numpy()) and np.array_equal(ol, wl[0, :, :, :, 0].cpu().numpy())
+    s.close()
+
+
+# ------------------------------------------------------------------ Correlation op
+@pytest.mark.parametrize("cfgs", [(3, 1, 3, 1, 1), (4, 1, 4, 2, 2), (2, 3, 1, 1, 1), (0, 1, 0, 1, 1), (4, 1, 4, 1, 2)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.float16])
+def test_correlation_forward_backward_vs_oracle(api, cfgs, dtype):
+    from cvpr2020_manet_b200.correlation_package.correlation import Correlation
+    from oracle import manet_oracle as O
+    pad, ks, md, s1, s2 = cfgs
+    gen = torch.Generator().manual_seed(9)
+    a = torch.randn(2, 37, 11, 13, generator=gen).to(dtype)
+    b = torch.randn(2, 37, 11, 13, generator=gen).to(dtype)
+    want = O.correlation_forward(a.float(), b.float(), pad, ks, md, s1, s2)
+    ac, bc = a.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    out = Correlation(pad, ks, md, s1, s2, 1)(ac, bc)
+    assert out.shape == want.shape and out.dtype == dtype
+    tol = {torch.float32: 2e-6, torch.float64: 2e-6, torch.float16: 3e-3}[dtype]
+    assert float((out.detach().cpu().float() - want).abs().max()) <= tol
+    go = torch.randn(want.shape, generator=gen)
+    ga_w, gb_w = O.correlation_backward(a.float(), b.float(), go, pad, ks, md, s1, s2)
+    out.backward(go.cuda().to(dtype))
+    gtol = {torch.float32: 1e-5, torch.float64: 1e-5, torch.float16: 2e-2}[dtype]
+    assert float((ac.grad.cpu().float() - ga_w).abs().max()) <= gtol
+    assert float((bc.grad.cpu().float() - gb_w).abs().max()) <= gtol
+
+
+def test_correlation_cuda_module_contract_and_manet_usage(api):
+    """correlation_cuda.forward resizes and fills the caller's tensors (correlation_cuda.cc:36-42);
+    MANet's historical use (pad = md = d, k = 1) recovers q.p per offset; cross_correlate is that x C."""
+    from cvpr2020_manet_b200.correlation_package import correlation_cuda
+    gen = torch.Generator().manual_seed(2)
+    C, H, W, d = 100, 20, 26, 4
+    x = torch.rand(1, C, H, W, generator=gen).cuda()
+    y = torch.rand(1, C, H, W, generator=gen).cuda()
+    r1, r2, out = x.new_empty(0), x.new_empty(0), x.new_empty(0)
+    assert correlation_cuda.forward(x, y, r1, r2, out, d, 1, d, 1, 1, 1) == 1
+    assert tuple(r1.shape) == (1, H + 2 * d, W + 2 * d, C) and tuple(out.shape) == (1, (2 * d + 1) ** 2, H, W)
+    assert torch.equal(r1[0, d:-d, d:-d].permute(2, 0, 1), x[0]) and float(r1[0, :d].abs().max()) == 0.0
+    yp = torch.nn.functional.pad(y, (d, d, d, d))
+    for (tj, ti) in [(-d, -d), (0, 0), (2, -3), (d, d)]:
+        want = (x * yp[:, :, d + tj:d + tj + H, d + ti:d + ti + W]).mean(1)
+        assert float((out[:, (tj + d) * (2 * d + 1) + ti + d] - want).abs().max()) <= 1e-6
+    cc = api.cross_correlate(x[0].permute(1, 2, 0), y[0].permute(1, 2, 0), max_distance=d)
+    assert tuple(cc.shape) == (H, W, (2 * d + 1) ** 2)
+    assert float((cc.permute(2, 0, 1) - out[0] * C).abs().max()) <= 1e-4
