@@ -15,99 +15,168 @@
 namespace manet {
 
 // ---------------------------------------------------------------- 1. pooling
-// in: [H,W,C] view with strides (sy,sx,sc);  out: [C][h][w] contiguous
-__global__ void avg_pool2_kernel(const float* __restrict__ in, int64_t sy, int64_t sx, int64_t sc,
-                                 int C, int h, int w, float* __restrict__ out) {
-    int64_t total = (int64_t)C * h * w;
+// in: two [H,W,C] views with strides (sy,sx,sc);  out: [C][h][wp] each, wp = w rounded up to 4
+// (pad columns are written as zero so 16-byte row segments are always readable).
+struct PoolSrc { const float* p; int64_t sy, sx, sc; float* out; };
+
+__global__ void __launch_bounds__(256)
+avg_pool2_kernel(PoolSrc a, PoolSrc b, int C, int h, int w, int wp) {
+    const PoolSrc s = (blockIdx.y == 0) ? a : b;
+    const int64_t total = (int64_t)C * h * wp;
+    const bool vec = (s.sx == 1) && ((s.sy & 1) == 0) && ((s.sc & 1) == 0) && ((reinterpret_cast<uintptr_t>(s.p) & 7) == 0);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
-        int x = (int)(i % w); int64_t r = i / w; int y = (int)(r % h); int c = (int)(r / h);
-        const float* p = in + (int64_t)c * sc + (int64_t)(2 * y) * sy + (int64_t)(2 * x) * sx;
-        // torch avg_pool2d sums the window in row-major order, then divides by 4
-        float s = __ldg(p) + __ldg(p + sx);
-        s += __ldg(p + sy);
-        s += __ldg(p + sy + sx);
-        out[i] = s / 4.0f;
+        int x = (int)(i % wp); int64_t r = i / wp; int y = (int)(r % h); int c = (int)(r / h);
+        float v = 0.f;
+        if (x < w) {
+            const float* p = s.p + (int64_t)c * s.sc + (int64_t)(2 * y) * s.sy + (int64_t)(2 * x) * s.sx;
+            // torch avg_pool2d sums the window in row-major order, then divides by 4
+            float t;
+            if (vec) {
+                float2 r0 = __ldg(reinterpret_cast<const float2*>(p));
+                float2 r1 = __ldg(reinterpret_cast<const float2*>(p + s.sy));
+                t = r0.x + r0.y; t += r1.x; t += r1.y;
+            } else {
+                t = __ldg(p) + __ldg(p + s.sx); t += __ldg(p + s.sy); t += __ldg(p + s.sy + s.sx);
+            }
+            v = t / 4.0f;
+        }
+        s.out[i] = v;
     }
 }
 
 // ---------------------------------------------------------------- 2+3. windowed distances
-// Fast path: lanes <-> 32 consecutive columns u of the previous-frame row; a warp owns DYW
-// window rows; every thread keeps DYW x TX accumulators (TX query pixels of one row).
-// Requires TX + 2d <= 32.
-constexpr int TX = 8;
+// Fast path (max_distance <= 12).  CTA = WTY query rows x WTX query pixels of the half-resolution
+// frame.  Lanes <-> 32 consecutive previous-frame columns u (16-byte aligned origin), a warp owns one
+// query row and WDY window rows; every thread keeps WDY x WTX accumulators as packed fp32 pairs and
+// updates them with FADD2/FFMA2 (sm_100 packed fp32), i.e. (p - q)^2 exactly as the reference's
+// (x - y)^2.  The previous-frame rows needed by the CTA (WTY + 2d rows x 32 columns) are staged in
+// shared memory WCC channels at a time with cp.async, double-buffered.
+constexpr int WTX = 8, WTY = 3, WDY = 5, WCC = 20;
+constexpr int WTHREADS = 32 * WTY * 5;
 
-template <int DYW>
-__global__ void __launch_bounds__(32 * 8)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+    uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(WTHREADS, 1)
 window_dist_kernel(const float* __restrict__ qs, const float* __restrict__ ps,
-                   int C, int h, int w, int d, float* __restrict__ T) {
-    extern __shared__ float q_s[];               // [C][TX]
-    const int win = 2 * d + 1;
-    const int L = win * win;
-    const int x0 = blockIdx.x * TX;
-    const int y = blockIdx.y;
+                   int C, int h, int w, int wp, int d, float* __restrict__ T) {
+    extern __shared__ __align__(16) float wsm[];
+    const int win = 2 * d + 1, L = win * win;
+    const int prows = WTY + 2 * d;
+    const int ngroups = (win + WDY - 1) / WDY;
+    const int x0 = blockIdx.x * WTX, y0 = blockIdx.y * WTY;
+    const int u0 = x0 - ((d + 3) & ~3);                   // 16-byte aligned column origin, u0 <= x0 - d
+    const int off = u0 - x0 + d;                          // dx index of (lane, px i) = lane - i + off
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int nwarps = blockDim.x >> 5;
-    const int64_t plane = (int64_t)h * w;
+    const bool warp_active = wid < WTY * ngroups;         // fewer row groups when max_distance < 10
+    const int qy = wid / ngroups, dy0 = (wid % ngroups) * WDY;
+    const int plane = h * wp;
+    // smem rows are padded to prows_s so that window rows dy0+j beyond the window (last group) stay in range
+    const int prows_s = WTY - 1 + ngroups * WDY;
+    const int p_elems = WCC * prows_s * 32, q_elems = WCC * WTY * WTX;
+    const int buf_elems = p_elems + q_elems;              // buffer b: p at wsm + b*buf_elems, q right after
 
-    for (int i = threadIdx.x; i < C * TX; i += blockDim.x) {
-        int c = i / TX, px = i % TX;
-        q_s[i] = (x0 + px < w) ? __ldg(qs + c * plane + (int64_t)y * w + x0 + px) : 0.f;
+    // staging roles: thread -> (channel parity, row, 16-byte segment); 240 threads per channel parity
+    const int st_half = threadIdx.x / 240, st_t = threadIdx.x % 240;
+    const int st_row = st_t >> 3, st_seg = st_t & 7;
+    const int st_yy = y0 - d + st_row, st_u = u0 + 4 * st_seg;
+    const bool st_ok = (st_half < 2) && (st_row < prows) && (st_yy >= 0) && (st_yy < h) && (st_u >= 0) && (st_u + 3 < wp);
+    const bool st_active = (st_half < 2) && (st_row < prows_s);
+    const float* st_src = ps + (st_ok ? st_yy * wp + st_u : 0);
+    const int st_dst = st_row * 32 + 4 * st_seg;
+    // query roles: thread -> (channel, row, px) for the first WTY*WTX*WCC elements
+    auto stage = [&](int buf, int c0) {
+        float* pb = wsm + buf * buf_elems;
+        if (st_active) {
+#pragma unroll 2
+            for (int cc = st_half; cc < WCC; cc += 2) {
+                const bool ok = st_ok && (c0 + cc < C);
+                cp_async16(pb + cc * prows_s * 32 + st_dst, ok ? st_src + (c0 + cc) * plane : ps, ok);
+            }
+        }
+        // query pixels, negated so the inner loop is a packed add: (p + (-q))
+        for (int i = threadIdx.x; i < q_elems; i += WTHREADS) {
+            int px = i % WTX; int r = (i / WTX) % WTY; int cc = i / (WTX * WTY);
+            int y = y0 + r, x = x0 + px, c = c0 + cc;
+            float v = (c < C && y < h && x < w) ? -__ldg(qs + c * plane + y * wp + x) : 0.f;
+            pb[p_elems + i] = v;
+        }
+        cp_async_commit();
+    };
+
+    float2 acc[WDY][WTX / 2];
+#pragma unroll
+    for (int j = 0; j < WDY; ++j)
+#pragma unroll
+        for (int i = 0; i < WTX / 2; ++i) acc[j][i] = make_float2(0.f, 0.f);
+
+    const int nchunks = (C + WCC - 1) / WCC;
+    stage(0, 0);
+    for (int ch = 0; ch < nchunks; ++ch) {
+        if (ch + 1 < nchunks) { stage((ch + 1) & 1, (ch + 1) * WCC); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        const float* pb = wsm + (ch & 1) * buf_elems + (qy + dy0) * 32 + lane;   // smem row of window row dy0+j: qy + dy0 + j
+        const float* qb = wsm + (ch & 1) * buf_elems + p_elems + qy * WTX;
+        // rows outside the image are zero-filled and simply produce values that the epilogue ignores
+#pragma unroll 4
+        for (int cc = 0; cc < (warp_active ? WCC : 0); ++cc) {
+            const float4 qa = *reinterpret_cast<const float4*>(qb + cc * WTY * WTX);
+            const float4 qc = *reinterpret_cast<const float4*>(qb + cc * WTY * WTX + 4);
+            const float2 nq0 = make_float2(qa.x, qa.y), nq1 = make_float2(qa.z, qa.w);
+            const float2 nq2 = make_float2(qc.x, qc.y), nq3 = make_float2(qc.z, qc.w);
+            float pv[WDY];
+#pragma unroll
+            for (int j = 0; j < WDY; ++j) pv[j] = pb[(cc * prows_s + j) * 32];
+#pragma unroll
+            for (int j = 0; j < WDY; ++j) {
+                const float2 pp = make_float2(pv[j], pv[j]);
+                float2 df;
+                df = __fadd2_rn(pp, nq0); acc[j][0] = __ffma2_rn(df, df, acc[j][0]);
+                df = __fadd2_rn(pp, nq1); acc[j][1] = __ffma2_rn(df, df, acc[j][1]);
+                df = __fadd2_rn(pp, nq2); acc[j][2] = __ffma2_rn(df, df, acc[j][2]);
+                df = __fadd2_rn(pp, nq3); acc[j][3] = __ffma2_rn(df, df, acc[j][3]);
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
-    const int u = x0 - d + lane;                 // previous-frame column owned by this lane
+    const int y = y0 + qy;
+    if (y >= h || !warp_active) return;
+    const int u = u0 + lane;
     const bool u_ok = (u >= 0) && (u < w);
-    for (int dy0 = wid * DYW; dy0 < win; dy0 += nwarps * DYW) {
-        float acc[DYW][TX];
-        const float* prow[DYW];
-        bool row_ok[DYW];
+    // T[(y*w + x0 + i)*L + (dy0+j)*win + lane - i + off]: stepping i moves the pointer by L - 1
+    float* trow = T + ((size_t)y * w + x0) * L + dy0 * win + lane + off;
 #pragma unroll
-        for (int j = 0; j < DYW; ++j) {
-            int yy = y + dy0 + j - d;
-            row_ok[j] = (dy0 + j < win) && (yy >= 0) && (yy < h);
-            int yc = min(max(yy, 0), h - 1);
-            prow[j] = ps + (int64_t)yc * w + min(max(u, 0), w - 1);
+    for (int j = 0; j < WDY; ++j) {
+        const int dyi = dy0 + j;
+        if (dyi >= win) break;
+        const int yy = y + dyi - d;
+        const bool ok = u_ok && (yy >= 0) && (yy < h);
+        float* tp = trow + j * win;
 #pragma unroll
-            for (int i = 0; i < TX; ++i) acc[j][i] = 0.f;
-        }
-        for (int c = 0; c < C; ++c) {
-            float qv[TX];
-            const float4* q4 = reinterpret_cast<const float4*>(q_s + c * TX);
-            float4 a = q4[0], b = q4[1];
-            qv[0] = a.x; qv[1] = a.y; qv[2] = a.z; qv[3] = a.w;
-            qv[4] = b.x; qv[5] = b.y; qv[6] = b.z; qv[7] = b.w;
-#pragma unroll
-            for (int j = 0; j < DYW; ++j) {
-                float pv = __ldg(prow[j] + c * plane);
-#pragma unroll
-                for (int i = 0; i < TX; ++i) {
-                    float df = qv[i] - pv;
-                    acc[j][i] = fmaf(df, df, acc[j][i]);
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < DYW; ++j) {
-            if (dy0 + j >= win) continue;
-#pragma unroll
-            for (int i = 0; i < TX; ++i) {
-                int dxi = lane - i;               // = dx + d
-                if (dxi < 0 || dxi >= win || x0 + i >= w) continue;
-                float v = (row_ok[j] && u_ok) ? sigmoid_norm(acc[j][i]) : 1.0f;
-                T[((int64_t)y * w + x0 + i) * L + (dy0 + j) * win + dxi] = v;
-            }
+        for (int i = 0; i < WTX; ++i) {
+            const int dxi = lane - i + off;
+            const float a = (i & 1) ? acc[j][i >> 1].y : acc[j][i >> 1].x;
+            const float v = ok ? sigmoid_norm_fast(a) : 1.0f;
+            if (dxi >= 0 && dxi < win && x0 + i < w) tp[i * (L - 1)] = v;
         }
     }
 }
 
 // Generic path for any d: one thread per (y, x, l).
 __global__ void window_dist_generic_kernel(const float* __restrict__ qs, const float* __restrict__ ps,
-                                           int C, int h, int w, int d, float* __restrict__ T) {
+                                           int C, int h, int w, int wp, int d, float* __restrict__ T) {
     const int win = 2 * d + 1;
     const int64_t L = (int64_t)win * win;
     const int64_t total = (int64_t)h * w * L;
-    const int64_t plane = (int64_t)h * w;
+    const int64_t plane = (int64_t)h * wp;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         int l = (int)(i % L); int64_t pix = i / L; int x = (int)(pix % w), y = (int)(pix / w);
@@ -115,8 +184,8 @@ __global__ void window_dist_generic_kernel(const float* __restrict__ qs, const f
         float v = 1.0f;
         if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
             float acc = 0.f;
-            const float* a = qs + (int64_t)y * w + x;
-            const float* b = ps + (int64_t)yy * w + xx;
+            const float* a = qs + (int64_t)y * wp + x;
+            const float* b = ps + (int64_t)yy * wp + xx;
             for (int c = 0; c < C; ++c) { float df = __ldg(a + c * plane) - __ldg(b + c * plane); acc = fmaf(df, df, acc); }
             v = sigmoid_norm(acc);
         }
@@ -142,44 +211,79 @@ __device__ __forceinline__ float bilerp(float v00, float v01, float v10, float v
 }
 
 // ---------------------------------------------------------------- 4+5+6. upsample, mask, min
-// One warp per full-resolution pixel; lanes stride over the L window offsets.
-constexpr int NMAX = 8;   // objects per pass
-__global__ void __launch_bounds__(256)
+// One warp per full-resolution pixel, lanes <-> window columns dx, loop over window rows dy.
+// Running minima live in shared memory indexed by the object slot ([slot][thread]: conflict-free),
+// so an element costs one LDS/FMNMX/STS instead of a compare+select per object.  When gt_ids is
+// 0..N-1 (always the case in MANet, IntVOS.py:200,698) the label is the slot; otherwise every
+// matching id is updated.  WIN_T > 0 fixes the window size at compile time so the dy loop unrolls
+// into loads with immediate offsets (no per-iteration 64-bit address arithmetic).
+constexpr int UP_WARPS = 8;
+constexpr int UP_STRIDE = 32 * UP_WARPS;
+
+template <int WIN_T>
+__global__ void __launch_bounds__(UP_STRIDE)
 upsample_mask_min_kernel(const float* __restrict__ T, const int32_t* __restrict__ labels,
                          const int32_t* __restrict__ gt_ids, int H, int W, int h, int w, int d, int N,
                          float* __restrict__ out) {
-    const int win = 2 * d + 1, L = win * win;
-    const int lane = threadIdx.x & 31;
-    const int64_t pix = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (pix >= (int64_t)H * W) return;
-    const int Y = (int)(pix / W), X = (int)(pix % W);
+    extern __shared__ float sbest[];                         // [N][UP_STRIDE]
+    const int win = WIN_T > 0 ? WIN_T : 2 * d + 1;
+    const int L = win * win;
+    const int lane = threadIdx.x & 31, tid = threadIdx.x;
+    const int pix = blockIdx.x * UP_WARPS + (tid >> 5);
+    bool arange = true;
+    for (int o = lane; o < N; o += 32) arange = arange && (gt_ids[o] == o);
+    arange = __all_sync(0xffffffffu, arange);
+    float* mine = sbest + tid;
+    for (int o = 0; o < N; ++o) mine[o * UP_STRIDE] = 1.0f;   // pad value of torch.where(mask, d, ones)
+    if (pix >= H * W) return;
+    const int Y = pix / W, X = pix - Y * W;
     const Lerp ly = make_lerp(Y, h, H), lx = make_lerp(X, w, W);
-    const float* t00 = T + ((int64_t)ly.i0 * w + lx.i0) * L;
-    const float* t01 = T + ((int64_t)ly.i0 * w + lx.i1) * L;
-    const float* t10 = T + ((int64_t)ly.i1 * w + lx.i0) * L;
-    const float* t11 = T + ((int64_t)ly.i1 * w + lx.i1) * L;
-    for (int o0 = 0; o0 < N; o0 += NMAX) {
-        float ids[NMAX], best[NMAX];
+    const float* t00 = T + ((size_t)ly.i0 * w + lx.i0) * L + lane;
+    const float* t01 = T + ((size_t)ly.i0 * w + lx.i1) * L + lane;
+    const float* t10 = T + ((size_t)ly.i1 * w + lx.i0) * L + lane;
+    const float* t11 = T + ((size_t)ly.i1 * w + lx.i1) * L + lane;
+    if (win <= 32) {
+        const int xx = X + 2 * (lane - d);
+        const bool lane_ok = lane < win;
+        const bool col_ok = lane_ok && xx >= 0 && xx < W;
+        const int32_t* lp = labels + (Y - 2 * d) * W + (col_ok ? xx : 0);   // row pointer, advanced by 2W per dy
+        if (lane_ok) {
+            if (arange) {
 #pragma unroll
-        for (int o = 0; o < NMAX; ++o) {
-            ids[o] = (o0 + o < N) ? (float)gt_ids[o0 + o] : -3.0e38f;
-            best[o] = 1.0f;                      // pad value of torch.where(mask, d, ones)
+                for (int dyi = 0; dyi < win; ++dyi) {
+                    const int yy = Y + 2 * (dyi - d);
+                    const int l = dyi * win;
+                    const float u = bilerp(__ldg(t00 + l), __ldg(t01 + l), __ldg(t10 + l), __ldg(t11 + l), ly, lx);
+                    const int lab = (col_ok && yy >= 0 && yy < H) ? __ldg(lp + dyi * 2 * W) : 0;
+                    if ((unsigned)lab < (unsigned)N) { float* b = mine + lab * UP_STRIDE; *b = fminf(*b, u); }
+                }
+            } else {
+                for (int dyi = 0; dyi < win; ++dyi) {
+                    const int yy = Y + 2 * (dyi - d);
+                    const int l = dyi * win;
+                    const float u = bilerp(__ldg(t00 + l), __ldg(t01 + l), __ldg(t10 + l), __ldg(t11 + l), ly, lx);
+                    const float lf = (col_ok && yy >= 0 && yy < H) ? (float)__ldg(lp + dyi * 2 * W) : 0.f;
+                    for (int o = 0; o < N; ++o)
+                        if (lf == (float)gt_ids[o]) { float* b = mine + o * UP_STRIDE; *b = fminf(*b, u); }
+                }
+            }
         }
+    } else {
+        // wide windows: lanes stride over all L offsets
         for (int l = lane; l < L; l += 32) {
-            int dy = l / win - d, dx = l % win - d;
-            float u = bilerp(__ldg(t00 + l), __ldg(t01 + l), __ldg(t10 + l), __ldg(t11 + l), ly, lx);
-            int yy = Y + 2 * dy, xx = X + 2 * dx;
-            float lab = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? (float)__ldg(labels + (int64_t)yy * W + xx) : 0.f;
-#pragma unroll
-            for (int o = 0; o < NMAX; ++o) best[o] = (lab == ids[o]) ? fminf(best[o], u) : best[o];
+            const int dy = l / win - d, dx = l % win - d;
+            const float u = bilerp(__ldg(t00 - lane + l), __ldg(t01 - lane + l), __ldg(t10 - lane + l), __ldg(t11 - lane + l), ly, lx);
+            const int yy = Y + 2 * dy, x2 = X + 2 * dx;
+            const float lf = (yy >= 0 && yy < H && x2 >= 0 && x2 < W) ? (float)__ldg(labels + yy * W + x2) : 0.f;
+            for (int o = 0; o < N; ++o)
+                if (lf == (float)gt_ids[o]) { float* b = mine + o * UP_STRIDE; *b = fminf(*b, u); }
         }
+    }
+    for (int o = 0; o < N; ++o) {
+        float v = mine[o * UP_STRIDE];
 #pragma unroll
-        for (int o = 0; o < NMAX; ++o) {
-            float v = best[o];
-#pragma unroll
-            for (int s = 16; s > 0; s >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, s));
-            if (lane == 0 && o0 + o < N) out[pix * N + o0 + o] = v;
-        }
+        for (int s = 16; s > 0; s >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, s));
+        if (lane == 0) out[(size_t)pix * N + o] = v;
     }
 }
 
@@ -197,11 +301,14 @@ __global__ void upsample_volume_kernel(const float* __restrict__ T, int H, int W
 }
 
 // ---------------------------------------------------------------- host side
+static inline int pooled_pitch(int w) { return (w + 3) & ~3; }
+
 size_t local_match_workspace_bytes(int H, int W, int C, int N, int d) {
     (void)N;
     int h = H / 2, w = W / 2;
     size_t L = (size_t)(2 * d + 1) * (2 * d + 1);
-    return 2 * align_up((size_t)C * h * w * sizeof(float), 256) + align_up((size_t)h * w * L * sizeof(float), 256) + 256;
+    return 2 * align_up((size_t)C * h * pooled_pitch(w) * sizeof(float), 256) +
+           align_up((size_t)h * w * L * sizeof(float), 256) + 256;
 }
 
 static int window_volume(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_sc,
@@ -210,28 +317,32 @@ static int window_volume(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_s
                          float** T_out) {
     if (H < 2 || W < 2 || C < 1 || d < 0) return fail_invalid("local match: need H,W >= 2, C >= 1, max_distance >= 0");
     if (ws_bytes < local_match_workspace_bytes(H, W, C, 1, d)) { set_error("local match: workspace too small"); return MANET_E_WORKSPACE; }
-    const int h = H / 2, w = W / 2;
+    const int h = H / 2, w = W / 2, wp = pooled_pitch(w);
     Carver cv(ws, ws_bytes);
-    float* qs = cv.take<float>((size_t)C * h * w);
-    float* ps = cv.take<float>((size_t)C * h * w);
+    float* qs = cv.take<float>((size_t)C * h * wp);
+    float* ps = cv.take<float>((size_t)C * h * wp);
     const int win = 2 * d + 1;
     float* T = cv.take<float>((size_t)h * w * win * win);
-    int64_t tot = (int64_t)C * h * w;
-    unsigned pg = (unsigned)imin64(ceil_div64(tot, 256), 148 * 8);
-    avg_pool2_kernel<<<pg, 256, 0, stream>>>(x, x_sy, x_sx, x_sc, C, h, w, qs);
-    avg_pool2_kernel<<<pg, 256, 0, stream>>>(y, y_sy, y_sx, y_sc, C, h, w, ps);
-    if (TX + 2 * d <= 32) {
-        constexpr int DYW = 5;
-        int warps = (win + DYW - 1) / DYW; if (warps > 8) warps = 8;
-        dim3 grid((w + TX - 1) / TX, h);
-        size_t smem = (size_t)C * TX * sizeof(float);
+    int64_t tot = (int64_t)C * h * wp;
+    dim3 pg((unsigned)imin64(ceil_div64(tot, 256), 148 * 8), 2);
+    PoolSrc a{x, x_sy, x_sx, x_sc, qs}, b{y, y_sy, y_sx, y_sc, ps};
+    avg_pool2_kernel<<<pg, 256, 0, stream>>>(a, b, C, h, w, wp);
+    if (d <= 12) {
+        const int ngroups = (win + WDY - 1) / WDY;
+        dim3 grid((w + WTX - 1) / WTX, (h + WTY - 1) / WTY);
+        size_t smem = 2 * (size_t)(WCC * (WTY - 1 + ngroups * WDY) * 32 + WCC * WTY * WTX) * sizeof(float);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(window_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            attr_set = true;
+        }
         profile_begin(PROF_LOCAL_WINDOW, stream);
-        window_dist_kernel<DYW><<<grid, warps * 32, smem, stream>>>(qs, ps, C, h, w, d, T);
+        window_dist_kernel<<<grid, WTHREADS, smem, stream>>>(qs, ps, C, h, w, wp, d, T);
         profile_end(PROF_LOCAL_WINDOW, stream);
     } else {
         int64_t total = (int64_t)h * w * win * win;
         unsigned g = (unsigned)imin64(ceil_div64(total, 256), 148 * 32);
-        window_dist_generic_kernel<<<g, 256, 0, stream>>>(qs, ps, C, h, w, d, T);
+        window_dist_generic_kernel<<<g, 256, 0, stream>>>(qs, ps, C, h, w, wp, d, T);
     }
     *T_out = T;
     return check_launch("local window kernels");
@@ -246,8 +357,13 @@ int launch_local_match(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_
     int rc = window_volume(query, q_sy, q_sx, q_sc, prev, p_sy, p_sx, p_sc, H, W, C, d, ws, ws_bytes, stream, &T);
     if (rc) return rc;
     int64_t pix = (int64_t)H * W;
+    const size_t up_smem = (size_t)N * 32 * UP_WARPS * sizeof(float);
+    if (up_smem > 200 * 1024) return fail_invalid("local match: too many objects (N <= 200)");
+    if ((int64_t)H * W * (int64_t)((2 * d + 1) * (2 * d + 1)) >= (1ll << 31)) return fail_invalid("local match: frame x window too large");
+    auto kern = (d == 12) ? upsample_mask_min_kernel<25> : (d == 9) ? upsample_mask_min_kernel<19> : upsample_mask_min_kernel<0>;
+    if (up_smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)up_smem);
     profile_begin(PROF_LOCAL_MIN, stream);
-    upsample_mask_min_kernel<<<(unsigned)ceil_div64(pix, 8), 256, 0, stream>>>(T, labels, gt_ids, H, W, H / 2, W / 2, d, N, out);
+    kern<<<(unsigned)ceil_div64(pix, UP_WARPS), UP_STRIDE, up_smem, stream>>>(T, labels, gt_ids, H, W, H / 2, W / 2, d, N, out);
     profile_end(PROF_LOCAL_MIN, stream);
     return check_launch("upsample_mask_min_kernel");
 }
