@@ -17,12 +17,15 @@
 // swizzle (16-byte chunk index XOR row%8) already applied.  The main kernel therefore needs no
 // tensor map: plain cp.async.bulk copies land canonical K-major SWIZZLE_128B operands.
 //
-// Main kernel (gm_umma_kernel): persistent, one CTA per SM, 6 warps:
+// Main kernel (gm_umma_kernel): persistent, one CTA per SM, 10 warps:
 //   warp 0  bulk-TMA producer        warp 1  tcgen05.mma issuer (+ TMEM allocator)
-//   warps 2-5  epilogue: tcgen05.ld 32 columns at a time, add -s/2*|r|^2, running row max,
+//   warps 2-9  epilogue (two warps per TMEM lane quarter, 128 columns each): software-pipelined
+//              tcgen05.ld of 32 columns at a time, add -s/2*|r|^2, running row max (3-input FMNMX),
 //              flushed with one atomicMax per (query row, object) when the object changes.
 // Tiles are 128 (queries) x 256 (references), accumulators double-buffered in TMEM (2 x 256
 // columns) so the epilogue of tile t overlaps the MMAs of tile t+1.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace manet {
@@ -34,7 +37,8 @@ constexpr int GM_BN = 256;             // references per tile (UMMA N)
 constexpr int GM_UNIT_ROWS = 128;
 constexpr int GM_CHUNK_BYTES = 16384;  // one (unit, part, k-block): 128 rows x 128 B
 constexpr int GM_UNIT_BYTES = 4 * GM_CHUNK_BYTES;
-constexpr int GM_THREADS = 192;
+constexpr int GM_EPI_WARPS = 8;           // two warps per TMEM lane quarter, each takes half of the columns
+constexpr int GM_THREADS = 32 * (2 + GM_EPI_WARPS);
 constexpr int GM_STAGES = 2;
 constexpr int GM_STAGE_BYTES = 2 * 2 * GM_CHUNK_BYTES;       // one part of a 256-row tile
 constexpr int GM_SMEM_A = GM_UNIT_BYTES;
@@ -116,6 +120,45 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+
+// tcgen05.wait::ld that also "touches" the destination registers so the compiler cannot schedule
+// their consumers above the wait.
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
+
+// Row-max of (accumulator + ysn) over this warp's 128 columns of one tile.  TMEM loads are software
+// pipelined (chunk c+1 is in flight while chunk c is reduced) and four independent maxima break the
+// FMNMX dependency chain.
+struct RowMax { float a, b, c, d; };
+__device__ __forceinline__ void epilogue_half_tile(uint32_t taddr, const float4* __restrict__ yv, RowMax& m) {
+    constexpr int NCH = GM_BN / 2 / 32;      // 4 chunks of 32 columns
+    uint32_t r[2][32];
+    tmem_ld32(taddr, r[0]);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+        float4 y[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = __ldg(yv + ch * 8 + i);
+        tmem_ld_wait_dep(r[ch & 1]);
+        if (ch + 1 < NCH) tmem_ld32(taddr + (ch + 1) * 32, r[(ch + 1) & 1]);
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+            const uint32_t* q = r[ch & 1] + 4 * i;
+            m.a = fmaxf(fmaxf(m.a, __uint_as_float(q[0]) + y[i].x), __uint_as_float(q[4]) + y[i + 1].x);
+            m.b = fmaxf(fmaxf(m.b, __uint_as_float(q[1]) + y[i].y), __uint_as_float(q[5]) + y[i + 1].y);
+            m.c = fmaxf(fmaxf(m.c, __uint_as_float(q[2]) + y[i].z), __uint_as_float(q[6]) + y[i + 1].z);
+            m.d = fmaxf(fmaxf(m.d, __uint_as_float(q[3]) + y[i].w), __uint_as_float(q[7]) + y[i + 1].w);
+        }
+    }
+}
+__device__ __forceinline__ float rowmax_value(const RowMax& m) { return fmaxf(fmaxf(m.a, m.b), fmaxf(m.c, m.d)); }
+__device__ __forceinline__ void rowmax_reset(RowMax& m) { m.a = m.b = m.c = m.d = -INFINITY; }
 
 // ------------------------------------------------------------------------------------ pre-pass
 __device__ __forceinline__ float pow2_scale(unsigned absmax_bits) {
@@ -300,7 +343,7 @@ gm_umma_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bim
         if (lane == 0) {
             for (int i = 0; i < GM_STAGES; ++i) { mbar_init(full_b + 8 * i, 1); mbar_init(empty_b + 8 * i, 1); }
             mbar_init(a_full, 1); mbar_init(a_empty, 1);
-            for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, 4); }
+            for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, GM_EPI_WARPS); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -383,45 +426,28 @@ gm_umma_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bim
             }
         }
     } else {
-        // ------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------ epilogue (warps 2..9)
         const int quarter = warp & 3;                  // TMEM lanes 32*quarter .. +31
+        const int half = (warp - 2) >> 2;              // columns [128*half, 128*half + 128) of every tile
         const int row = quarter * 32 + lane;
-        Ring acc; long long cur_m = -1; int cur_obj = -1; float run = -INFINITY;
+        Ring acc; long long cur_m = -1; int cur_obj = -1; RowMax run; rowmax_reset(run);
         for (long long tile = t_begin; tile < t_end; ++tile) {
             const long long m = tile / n_rtiles; const long long rt = tile % n_rtiles;
             const int obj = __ldg(tile_obj + rt);
             if (m != cur_m || obj != cur_obj) {
-                if (cur_m >= 0) atomicMax(best + ((size_t)cur_m * GM_BM + row) * N + cur_obj, float_to_key(run));
-                run = -INFINITY; cur_m = m; cur_obj = obj;
+                if (cur_m >= 0) atomicMax(best + ((size_t)cur_m * GM_BM + row) * N + cur_obj, float_to_key(rowmax_value(run)));
+                rowmax_reset(run); cur_m = m; cur_obj = obj;
             }
             mbar_wait(tmem_full + 8 * acc.idx, acc.phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * GM_BN;
-            const float4* yv = reinterpret_cast<const float4*>(ysn + (size_t)rt * GM_BN);
-#pragma unroll 1
-            for (int ch = 0; ch < GM_BN / 32; ++ch) {
-                uint32_t r[32];
-                tmem_ld32(taddr + ch * 32, r);
-                float4 y[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) y[i] = __ldg(yv + ch * 8 + i);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float a0 = __uint_as_float(r[4 * i + 0]) + y[i].x;
-                    float a1 = __uint_as_float(r[4 * i + 1]) + y[i].y;
-                    float a2 = __uint_as_float(r[4 * i + 2]) + y[i].z;
-                    float a3 = __uint_as_float(r[4 * i + 3]) + y[i].w;
-                    run = fmaxf(fmaxf(run, a0), a1);
-                    run = fmaxf(fmaxf(run, a2), a3);
-                }
-            }
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * GM_BN + half * (GM_BN / 2);
+            epilogue_half_tile(taddr, reinterpret_cast<const float4*>(ysn + (size_t)rt * GM_BN + half * (GM_BN / 2)), run);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty + 8 * acc.idx);
             acc.advance(2);
         }
-        if (cur_m >= 0) atomicMax(best + ((size_t)cur_m * GM_BM + row) * N + cur_obj, float_to_key(run));
+        if (cur_m >= 0) atomicMax(best + ((size_t)cur_m * GM_BM + row) * N + cur_obj, float_to_key(rowmax_value(run)));
     }
 
     tc_fence_before();
@@ -429,6 +455,218 @@ gm_umma_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bim
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------ 2-CTA kernel
+// Same algorithm on CTA pairs (cta_group::2): one tcgen05.mma covers 256 queries x 256 references,
+// each CTA of the pair holding its own 128 query rows (A) and ONE HALF of every reference tile (B).
+// Compared with the single-CTA kernel this halves the L2->SM operand traffic and the shared-memory
+// read bandwidth per MMA, and the freed shared memory buys a 4-deep B ring (32 KB stages).
+//
+// Plain cp.async.bulk can only signal an mbarrier in the destination CTA, so the peer CTA's
+// otherwise idle warp 1 forwards "my half has landed" to the leader with a remote
+// mbarrier.arrive.release.cluster; tcgen05.commit multicasts "stage free"/"accumulator ready" to
+// both CTAs; the peer's epilogue warps release the accumulator remotely.
+constexpr int G2_STAGES = 4;
+constexpr int G2_STAGE_BYTES = 2 * GM_CHUNK_BYTES;            // one part (hi|lo) of this CTA's 128-row half
+constexpr int G2_SMEM_BAR = GM_SMEM_A + G2_STAGES * G2_STAGE_BYTES;
+constexpr int G2_SMEM_TOTAL = G2_SMEM_BAR + 256 + 1024;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAITC_LOOP:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAITC_DONE;\n\t"
+        "bra WAITC_LOOP;\n\t"
+        "WAITC_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_commit2(uint32_t bar) {   // arrive on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
+gm_umma2_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg, const float* __restrict__ ysn,
+                const int* __restrict__ tile_obj, const GmCtrl* __restrict__ ctrl, int* __restrict__ best,
+                int n_mpairs, int N, int ksteps) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    const uint32_t sA = base;
+    const uint32_t sB = base + GM_SMEM_A;
+    const uint32_t bars = base + G2_SMEM_BAR;
+    const uint32_t full_b = bars + 0;            // [4]  local bytes landed
+    const uint32_t empty_b = bars + 32;          // [4]  stage free (multicast commit)
+    const uint32_t peer_full = bars + 64;        // [4]  leader only: peer's half landed
+    const uint32_t a_full = bars + 96;
+    const uint32_t a_empty = bars + 104;
+    const uint32_t peer_a_full = bars + 112;     // leader only
+    const uint32_t tmem_full = bars + 120;       // [2]
+    const uint32_t tmem_empty = bars + 136;      // [2]  leader only, 8 arrivals
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + G2_SMEM_BAR + 160);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int n_rtiles = ctrl->n_rtiles;
+    const long long total = (long long)n_mpairs * n_rtiles;
+    const int n_clusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
+    const long long t_begin = total * cid / n_clusters;
+    const long long t_end = total * (cid + 1) / n_clusters;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < G2_STAGES; ++i) { mbar_init(full_b + 8 * i, 1); mbar_init(empty_b + 8 * i, 1); mbar_init(peer_full + 8 * i, 1); }
+            mbar_init(a_full, 1); mbar_init(a_empty, 1); mbar_init(peer_a_full, 1);
+            for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, 2 * GM_EPI_WARPS); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                           // barriers of both CTAs initialised before any remote arrive
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------ producer (both CTAs: own A rows, own half of B)
+        if (lane == 0) {
+            Ring st; uint32_t ae_phase = 0; long long cur_m = -1;
+            for (long long tile = t_begin; tile < t_end; ++tile) {
+                const long long m = tile / n_rtiles; const long long rt = tile % n_rtiles;
+                if (m != cur_m) {
+                    mbar_wait(a_empty, ae_phase ^ 1); ae_phase ^= 1;
+                    mbar_expect_tx(a_full, GM_UNIT_BYTES);
+                    bulk_g2s(sA, Aimg + (size_t)(2 * m + rank) * GM_UNIT_BYTES, GM_UNIT_BYTES, a_full);
+                    cur_m = m;
+                }
+                for (int part = 0; part < 2; ++part) {
+                    mbar_wait(empty_b + 8 * st.idx, st.phase ^ 1);
+                    const uint32_t fb = full_b + 8 * st.idx;
+                    mbar_expect_tx(fb, G2_STAGE_BYTES);
+                    // (unit, part) = 2 consecutive k-block chunks = exactly this stage's image
+                    bulk_g2s(sB + st.idx * G2_STAGE_BYTES,
+                             Bimg + ((size_t)(2 * rt + rank) * 4 + part * 2) * GM_CHUNK_BYTES, G2_STAGE_BYTES, fb);
+                    st.advance(G2_STAGES);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            if (leader) {
+                // -------------------------------------------- MMA issuer (leader CTA only)
+                constexpr uint32_t idesc = idesc_f16(2 * GM_BM, GM_BN);
+                Ring st, acc; uint32_t af_phase = 0; long long cur_m = -1;
+                for (long long tile = t_begin; tile < t_end; ++tile) {
+                    const long long m = tile / n_rtiles;
+                    if (m != cur_m) { mbar_wait(a_full, af_phase); mbar_wait_cluster(peer_a_full, af_phase); af_phase ^= 1; cur_m = m; }
+                    mbar_wait_cluster(tmem_empty + 8 * acc.idx, acc.phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc.idx * GM_BN;
+                    mbar_wait(full_b + 8 * st.idx, st.phase);
+                    mbar_wait_cluster(peer_full + 8 * st.idx, st.phase);
+                    tc_fence_after();
+                    {
+                        const uint32_t bB = sB + st.idx * G2_STAGE_BYTES;
+                        for (int k = 0; k < ksteps; ++k)
+                            umma2_f16(d_tmem, smem_desc_sw128(sA + (k >> 2) * GM_CHUNK_BYTES + (k & 3) * 32),
+                                      smem_desc_sw128(bB + (k >> 2) * GM_CHUNK_BYTES + (k & 3) * 32), idesc, k > 0);
+                        for (int k = 0; k < ksteps; ++k)
+                            umma2_f16(d_tmem, smem_desc_sw128(sA + 2 * GM_CHUNK_BYTES + (k >> 2) * GM_CHUNK_BYTES + (k & 3) * 32),
+                                      smem_desc_sw128(bB + (k >> 2) * GM_CHUNK_BYTES + (k & 3) * 32), idesc, 1);
+                    }
+                    tc_commit2(empty_b + 8 * st.idx);
+                    st.advance(G2_STAGES);
+                    mbar_wait(full_b + 8 * st.idx, st.phase);
+                    mbar_wait_cluster(peer_full + 8 * st.idx, st.phase);
+                    tc_fence_after();
+                    {
+                        const uint32_t bB = sB + st.idx * G2_STAGE_BYTES;
+                        for (int k = 0; k < ksteps; ++k)
+                            umma2_f16(d_tmem, smem_desc_sw128(sA + (k >> 2) * GM_CHUNK_BYTES + (k & 3) * 32),
+                                      smem_desc_sw128(bB + (k >> 2) * GM_CHUNK_BYTES + (k & 3) * 32), idesc, 1);
+                    }
+                    tc_commit2(empty_b + 8 * st.idx);
+                    st.advance(G2_STAGES);
+                    tc_commit2(tmem_full + 8 * acc.idx);
+                    const bool last_of_m = (tile + 1 == t_end) || ((tile + 1) / n_rtiles != m);
+                    if (last_of_m) tc_commit2(a_empty);
+                    acc.advance(2);
+                }
+            } else {
+                // -------------------------------------------- peer: forward "landed" to the leader
+                const uint32_t r_peer_full = mapa_shared(peer_full, 0), r_peer_a = mapa_shared(peer_a_full, 0);
+                Ring st; uint32_t af_phase = 0; long long cur_m = -1;
+                for (long long tile = t_begin; tile < t_end; ++tile) {
+                    const long long m = tile / n_rtiles;
+                    if (m != cur_m) { mbar_wait(a_full, af_phase); af_phase ^= 1; mbar_arrive_remote(r_peer_a); cur_m = m; }
+                    for (int part = 0; part < 2; ++part) {
+                        mbar_wait(full_b + 8 * st.idx, st.phase);
+                        mbar_arrive_remote(r_peer_full + 8 * st.idx);
+                        st.advance(G2_STAGES);
+                    }
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------ epilogue (warps 2..9 of both CTAs)
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = quarter * 32 + lane;
+        const uint32_t r_tmem_empty = mapa_shared(tmem_empty, 0);
+        Ring acc; long long cur_m = -1; int cur_obj = -1; RowMax run; rowmax_reset(run);
+        for (long long tile = t_begin; tile < t_end; ++tile) {
+            const long long m = tile / n_rtiles; const long long rt = tile % n_rtiles;
+            const int obj = __ldg(tile_obj + rt);
+            if (m != cur_m || obj != cur_obj) {
+                if (cur_m >= 0) atomicMax(best + ((size_t)(2 * cur_m + rank) * GM_BM + row) * N + cur_obj, float_to_key(rowmax_value(run)));
+                rowmax_reset(run); cur_m = m; cur_obj = obj;
+            }
+            mbar_wait(tmem_full + 8 * acc.idx, acc.phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * GM_BN + half * (GM_BN / 2);
+            epilogue_half_tile(taddr, reinterpret_cast<const float4*>(ysn + (size_t)rt * GM_BN + half * (GM_BN / 2)), run);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(r_tmem_empty + 8 * acc.idx);
+            acc.advance(2);
+        }
+        if (cur_m >= 0) atomicMax(best + ((size_t)(2 * cur_m + rank) * GM_BM + row) * N + cur_obj, float_to_key(rowmax_value(run)));
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                           // nobody leaves while the pair may still touch its smem / TMEM
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
@@ -460,7 +698,7 @@ struct GmPlan {
 
 static GmPlan gm_plan(int64_t M, int64_t R, int N) {
     GmPlan p;
-    p.M_pad = ceil_div64(M > 0 ? M : 1, GM_BM) * GM_BM;
+    p.M_pad = ceil_div64(M > 0 ? M : 1, 2 * GM_BM) * (2 * GM_BM);   // CTA pairs own 256 query rows
     p.n_mtiles = (int)(p.M_pad / GM_BM);
     p.R_pad_max = ceil_div64((R > 0 ? R : 1) + (int64_t)N * (GM_BN - 1), GM_BN) * GM_BN;
     p.max_rtiles = (int)(p.R_pad_max / GM_BN);
@@ -505,14 +743,23 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
     gm_convert_kernel<<<nb_ref + nb_q + N, 256, 0, stream>>>(ref, rps, rcs, R, labels, query, qps, qcs, M, p.M_pad, C, N,
                                                              nb_ref, nb_q, ctrl, Aimg, Bimg, xs, ysn, tile_obj);
     static int sm_count = 0;
+    static int use_pair = 0;
     if (sm_count == 0) {
         int dev = 0; cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
         cudaFuncSetAttribute(gm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_TOTAL);
+        cudaFuncSetAttribute(gm_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_TOTAL);
+        // The CTA-pair (cta_group::2) kernel is functionally identical; on B200 it measured 7 % slower
+        // than the single-CTA kernel at 480p (profiles/r01 notes), so it is opt-in.
+        const char* e1 = getenv("MANET_GM_CTA_PAIR");
+        use_pair = (e1 && e1[0] == '1');
     }
     const int ksteps = (C + 15) / 16;
     profile_begin(PROF_GLOBAL_UMMA, stream);
-    gm_umma_kernel<<<sm_count, GM_THREADS, GM_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles, N, ksteps);
+    if (use_pair)
+        gm_umma2_kernel<<<sm_count & ~1, GM_THREADS, G2_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles / 2, N, ksteps);
+    else
+        gm_umma_kernel<<<sm_count, GM_THREADS, GM_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles, N, ksteps);
     profile_end(PROF_GLOBAL_UMMA, stream);
     gm_finalize_kernel<<<(unsigned)ceil_div64(M * N, 256), 256, 0, stream>>>(best, xs, ctrl, M, N, normalize, mem_frame, out);
     return check_launch("global match (tcgen05) kernels");
