@@ -178,7 +178,10 @@ __device__ __forceinline__ size_t image_chunk_offset(int64_t pos, int part, int 
            (size_t)(row >> 3) * 1024 + (size_t)(row & 7) * 128 + (size_t)((ch ^ (row & 7)) << 4);
 }
 
-// pass 1: label histogram, per-tensor |x| max, best[] = -inf keys
+// pass 1: label histogram, per-tensor |x| max, best[] = -inf keys.
+// grid = (pixel blocks, GM_SCAN_CG channel groups): each thread scans C/GM_SCAN_CG channels of one
+// pixel with several loads in flight (the tensors are read once, coalesced along the pixel axis).
+constexpr int GM_SCAN_CG = 4;
 __global__ void __launch_bounds__(256)
 gm_scan_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64_t R, const int32_t* __restrict__ labels,
                const float* __restrict__ query, int64_t qps, int64_t qcs, int64_t M, int C, int N,
@@ -186,22 +189,36 @@ gm_scan_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64_t 
     __shared__ int hist[GM_MAXN];
     __shared__ unsigned red[2][8];
     const int t = threadIdx.x;
+    const int cg = blockIdx.y;
+    const int cpg = (C + GM_SCAN_CG - 1) / GM_SCAN_CG;
+    const int c_begin = cg * cpg, c_end = min(C, c_begin + cpg);
     if (t < GM_MAXN) hist[t] = 0;
     __syncthreads();
     float amax_r = 0.f, amax_q = 0.f;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + t; i < R + M; i += stride) {
-        if (i < R) {
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + t;
+    for (int64_t i = first; i < R + M; i += stride) {
+        const bool is_ref = i < R;
+        const float* p = is_ref ? ref + i * rps : query + (i - R) * qps;
+        const int64_t cs = is_ref ? rcs : qcs;
+        if (is_ref && cg == 0) {
             int lab = labels[i];
             if (lab >= 0 && lab < N) atomicAdd(&hist[lab], 1);
-            const float* p = ref + i * rps;
-            for (int c = 0; c < C; ++c) amax_r = fmaxf(amax_r, fabsf(__ldg(p + (int64_t)c * rcs)));
-        } else {
-            const float* p = query + (i - R) * qps;
-            for (int c = 0; c < C; ++c) amax_q = fmaxf(amax_q, fabsf(__ldg(p + (int64_t)c * qcs)));
         }
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int c = c_begin;
+        for (; c + 4 <= c_end; c += 4) {
+            a0 = fmaxf(a0, fabsf(__ldg(p + (int64_t)c * cs)));
+            a1 = fmaxf(a1, fabsf(__ldg(p + (int64_t)(c + 1) * cs)));
+            a2 = fmaxf(a2, fabsf(__ldg(p + (int64_t)(c + 2) * cs)));
+            a3 = fmaxf(a3, fabsf(__ldg(p + (int64_t)(c + 3) * cs)));
+        }
+        for (; c < c_end; ++c) a0 = fmaxf(a0, fabsf(__ldg(p + (int64_t)c * cs)));
+        const float a = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+        if (is_ref) amax_r = fmaxf(amax_r, a); else amax_q = fmaxf(amax_q, a);
     }
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + t; i < n_best; i += stride) best[i] = INT_MIN;
+    if (cg == 0)
+        for (int64_t i = first; i < n_best; i += stride) best[i] = INT_MIN;
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) {
         amax_r = fmaxf(amax_r, __shfl_xor_sync(0xffffffffu, amax_r, s));
@@ -214,7 +231,7 @@ gm_scan_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64_t 
         for (int w = 0; w < 8; ++w) m = max(m, red[t][w]);
         if (m) atomicMax(&ctrl->absmax_bits[t], m);      // non-negative floats order like unsigned ints
     }
-    if (t < N && hist[t]) atomicAdd(&ctrl->counts[t], hist[t]);
+    if (cg == 0 && t < N && hist[t]) atomicAdd(&ctrl->counts[t], hist[t]);
 }
 
 // split x*s into fp16 hi + lo, 8 channels -> two 16-byte chunks
@@ -230,34 +247,23 @@ __device__ __forceinline__ void split8(const float (&v)[8], float s, uint4& hi, 
     lo = *reinterpret_cast<uint4*>(l);
 }
 
-__device__ __forceinline__ float convert_row(const float* __restrict__ p, int64_t cs, int C, int nchunks, float s,
-                                             uint8_t* __restrict__ img, int64_t pos) {
-    float sq = 0.f;
-    for (int j = 0; j < nchunks; ++j) {
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            int c = j * 8 + i;
-            v[i] = (p != nullptr && c < C) ? __ldg(p + (int64_t)c * cs) : 0.f;
-            sq = fmaf(v[i], v[i], sq);
-        }
-        uint4 hi, lo;
-        split8(v, s, hi, lo);
-        *reinterpret_cast<uint4*>(img + image_chunk_offset(pos, 0, j)) = hi;
-        *reinterpret_cast<uint4*>(img + image_chunk_offset(pos, 1, j)) = lo;
-    }
-    return sq;
-}
-
-// pass 2: scatter + convert.  Block ranges: [0,nb_ref) reference pixels, [nb_ref, nb_ref+nb_q) query
-// rows (incl. zero padding up to a multiple of 128), then one block per object for bucket padding.
+// pass 2: scatter + convert.  One block = 128 source pixels (= one operand unit for queries).
+// Block ranges: [0,nb_ref) reference pixels, [nb_ref, nb_ref+nb_q) query rows (incl. the zero rows
+// that pad M to a multiple of 256), then one block per object for the bucket padding rows.
+// The [64 channels x 128 pixels] slab is read coalesced along the pixel axis into shared memory,
+// then each (row, 16-byte chunk) is converted by one thread so that 8 consecutive lanes write one
+// full 128-byte line of the swizzled tile image.
+constexpr int GM_CV_PIX = 128;
 __global__ void __launch_bounds__(256)
 gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64_t R, const int32_t* __restrict__ labels,
                   const float* __restrict__ query, int64_t qps, int64_t qcs, int64_t M, int64_t M_pad, int C, int N,
                   int nb_ref, int nb_q, GmCtrl* __restrict__ ctrl, uint8_t* __restrict__ Aimg, uint8_t* __restrict__ Bimg,
                   float* __restrict__ xs, float* __restrict__ ysn, int* __restrict__ tile_obj) {
+    __shared__ float tile[64][GM_CV_PIX + 1];
     __shared__ int off[GM_MAXN + 1];
     __shared__ int bcnt[GM_MAXN], bbase[GM_MAXN];
+    __shared__ int64_t pos_s[GM_CV_PIX];
+    __shared__ float rowsq[GM_CV_PIX];
     const int t = threadIdx.x;
     if (t == 0) {
         int o = 0;
@@ -265,6 +271,7 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
         off[N] = o;
     }
     if (t < GM_MAXN) bcnt[t] = 0;
+    if (t < GM_CV_PIX) { rowsq[t] = 0.f; pos_s[t] = -1; }
     __syncthreads();
     const float s_q = pow2_scale(ctrl->absmax_bits[1]);
     const float s_r = pow2_scale(ctrl->absmax_bits[0]);
@@ -274,35 +281,79 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
         if (t <= N) ctrl->offsets[t] = off[t];
         if (t == 0) { ctrl->n_rtiles = off[N] / GM_BN; ctrl->scale_q = s_q; ctrl->scale_r = s_r; }
         for (int o = 0; o < N; ++o)
-            for (int tile = off[o] / GM_BN + t; tile < off[o + 1] / GM_BN; tile += 256) tile_obj[tile] = o;
+            for (int tl = off[o] / GM_BN + t; tl < off[o + 1] / GM_BN; tl += 256) tile_obj[tl] = o;
     }
-    if (b < nb_ref) {
-        const int64_t r = (int64_t)b * 256 + t;
-        int lab = (r < R) ? labels[r] : -1;
+    if (b >= nb_ref + nb_q) {
+        // bucket padding rows: zero operands, -inf bias (never wins the row max)
+        const int o = b - nb_ref - nb_q;
+        const int64_t pos = (int64_t)off[o] + ctrl->counts[o] + t;     // at most 255 padding rows
+        if (pos < off[o + 1]) {
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            for (int j = 0; j < nchunks; ++j) {
+                *reinterpret_cast<uint4*>(Bimg + image_chunk_offset(pos, 0, j)) = z;
+                *reinterpret_cast<uint4*>(Bimg + image_chunk_offset(pos, 1, j)) = z;
+            }
+            ysn[pos] = -INFINITY;
+        }
+        return;
+    }
+    const bool is_ref = b < nb_ref;
+    const int64_t p0 = is_ref ? (int64_t)b * GM_CV_PIX : (int64_t)(b - nb_ref) * GM_CV_PIX;
+    const int64_t P = is_ref ? R : M;
+    const float* src = is_ref ? ref : query;
+    const int64_t ps = is_ref ? rps : qps, cs = is_ref ? rcs : qcs;
+    const float scale = is_ref ? s_r : s_q;
+    uint8_t* img = is_ref ? Bimg : Aimg;
+    // destination row of every source pixel
+    if (is_ref) {
+        int lab = -1, rank = 0;
+        if (t < GM_CV_PIX && p0 + t < R) lab = labels[p0 + t];
         const bool keep = lab >= 0 && lab < N;
-        int rank = 0;
         if (keep) rank = atomicAdd(&bcnt[lab], 1);
         __syncthreads();
         if (t < N && bcnt[t]) bbase[t] = atomicAdd(&ctrl->cursors[t], bcnt[t]);
         __syncthreads();
-        if (keep) {
-            const int64_t pos = (int64_t)off[lab] + bbase[lab] + rank;
-            float ys = convert_row(ref + r * rps, rcs, C, nchunks, s_r, Bimg, pos);
-            ysn[pos] = -0.5f * (s_q * s_r) * ys;
+        if (keep) pos_s[t] = (int64_t)off[lab] + bbase[lab] + rank;
+    } else if (t < GM_CV_PIX && p0 + t < M_pad) {
+        pos_s[t] = p0 + t;
+    }
+    const int px = t & (GM_CV_PIX - 1), chalf = t >> 7;
+    const bool px_ok = p0 + px < P;
+    for (int kb = 0; kb * 64 < C; ++kb) {
+        __syncthreads();                                   // pos_s ready / previous slab consumed
+        const float* sp = src + (p0 + px) * ps;
+#pragma unroll 8
+        for (int c = chalf; c < 64; c += 2) {
+            const int ch = kb * 64 + c;
+            tile[c][px] = (px_ok && ch < C) ? __ldg(sp + (int64_t)ch * cs) : 0.f;
         }
-    } else if (b < nb_ref + nb_q) {
-        const int64_t m = (int64_t)(b - nb_ref) * 256 + t;
-        if (m < M_pad) {
-            float x2 = convert_row(m < M ? query + m * qps : nullptr, qcs, C, nchunks, s_q, Aimg, m);
-            xs[m] = x2;
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = t + 256 * e;
+            const int row = i >> 3, chk = i & 7;
+            const int j = kb * 8 + chk;                    // 16-byte chunk index within the row (8 channels)
+            float v[8];
+            float sq = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { v[k] = tile[chk * 8 + k][row]; sq = fmaf(v[k], v[k], sq); }
+            sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+            sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+            sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+            const int64_t pos = pos_s[row];
+            if (pos >= 0 && j < nchunks) {
+                uint4 hi, lo;
+                split8(v, scale, hi, lo);
+                *reinterpret_cast<uint4*>(img + image_chunk_offset(pos, 0, j)) = hi;
+                *reinterpret_cast<uint4*>(img + image_chunk_offset(pos, 1, j)) = lo;
+            }
+            if (chk == 0) rowsq[row] += sq;                // one lane per row and slab: no race
         }
-    } else {
-        const int o = b - nb_ref - nb_q;
-        const int64_t pos = (int64_t)off[o] + ctrl->counts[o] + t;     // at most 255 padding rows
-        if (pos < off[o + 1]) {
-            convert_row(nullptr, 0, C, nchunks, 1.0f, Bimg, pos);
-            ysn[pos] = -INFINITY;                                       // never wins the row max
-        }
+    }
+    __syncthreads();
+    if (t < GM_CV_PIX && pos_s[t] >= 0) {
+        if (is_ref) ysn[pos_s[t]] = -0.5f * (s_q * s_r) * rowsq[t];
+        else xs[pos_s[t]] = rowsq[t];
     }
 }
 
@@ -737,9 +788,9 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
     cudaError_t e = cudaMemsetAsync(ctrl, 0, sizeof(GmCtrl), stream);
     if (e != cudaSuccess) { set_error("global match: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
     const int64_t items = R + M;
-    unsigned g1 = (unsigned)(ceil_div64(items, 256) < 148 * 8 ? ceil_div64(items, 256) : 148 * 8);
+    dim3 g1((unsigned)(ceil_div64(items, 256) < 148 * 8 ? ceil_div64(items, 256) : 148 * 8), GM_SCAN_CG);
     gm_scan_kernel<<<g1, 256, 0, stream>>>(ref, rps, rcs, R, labels, query, qps, qcs, M, C, N, ctrl, best, p.M_pad * N);
-    const int nb_ref = (int)ceil_div64(R, 256), nb_q = (int)ceil_div64(p.M_pad, 256);
+    const int nb_ref = (int)ceil_div64(R, GM_CV_PIX), nb_q = (int)ceil_div64(p.M_pad, GM_CV_PIX);
     gm_convert_kernel<<<nb_ref + nb_q + N, 256, 0, stream>>>(ref, rps, rcs, R, labels, query, qps, qcs, M, p.M_pad, C, N,
                                                              nb_ref, nb_q, ctrl, Aimg, Bimg, xs, ysn, tile_obj);
     static int sm_count = 0;

@@ -18,9 +18,21 @@ namespace manet {
 // in: two [H,W,C] views with strides (sy,sx,sc);  out: [C][h][wp] each, wp = w rounded up to 4
 // (pad columns are written as zero so 16-byte row segments are always readable).
 struct PoolSrc { const float* p; int64_t sy, sx, sc; float* out; };
+// blockIdx.y == 2: labels [H,W] -> zero-padded [(H+4d), (W+4d)] copy (the F.pad of IntVOS.py:401-404),
+// so the masked-min kernel needs no bounds checks.
+struct LabelPad { const int32_t* labels; int32_t* out; int H, W, pad; };
 
 __global__ void __launch_bounds__(256)
-avg_pool2_kernel(PoolSrc a, PoolSrc b, int C, int h, int w, int wp) {
+avg_pool2_kernel(PoolSrc a, PoolSrc b, LabelPad lp, int C, int h, int w, int wp) {
+    if (blockIdx.y == 2) {
+        if (lp.out == nullptr) return;
+        const int PW = lp.W + 2 * lp.pad, PH = lp.H + 2 * lp.pad;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < PW * PH; i += gridDim.x * blockDim.x) {
+            int x = i % PW - lp.pad, y = i / PW - lp.pad;
+            lp.out[i] = (x >= 0 && x < lp.W && y >= 0 && y < lp.H) ? lp.labels[y * lp.W + x] : 0;
+        }
+        return;
+    }
     const PoolSrc s = (blockIdx.y == 0) ? a : b;
     const int64_t total = (int64_t)C * h * wp;
     const bool vec = (s.sx == 1) && ((s.sy & 1) == 0) && ((s.sc & 1) == 0) && ((reinterpret_cast<uintptr_t>(s.p) & 7) == 0);
@@ -212,17 +224,25 @@ __device__ __forceinline__ float bilerp(float v00, float v01, float v10, float v
 
 // ---------------------------------------------------------------- 4+5+6. upsample, mask, min
 // One warp per full-resolution pixel, lanes <-> window columns dx, loop over window rows dy.
-// Running minima live in shared memory indexed by the object slot ([slot][thread]: conflict-free),
-// so an element costs one LDS/FMNMX/STS instead of a compare+select per object.  When gt_ids is
-// 0..N-1 (always the case in MANet, IntVOS.py:200,698) the label is the slot; otherwise every
-// matching id is updated.  WIN_T > 0 fixes the window size at compile time so the dy loop unrolls
-// into loads with immediate offsets (no per-iteration 64-bit address arithmetic).
+// Labels come from the zero-padded copy (no bounds checks).  Running minima live in shared memory
+// indexed by the object slot ([slot][thread]: conflict-free), so an element costs one
+// LDS/FMNMX/STS instead of a compare+select per object.  When gt_ids is 0..N-1 (always the case in
+// MANet, IntVOS.py:200,698) the label is the slot; otherwise every matching id is updated.
+// WIN_T > 0 fixes the window size at compile time so the dy loop unrolls into loads with immediate
+// offsets (no per-iteration 64-bit address arithmetic).
 constexpr int UP_WARPS = 8;
 constexpr int UP_STRIDE = 32 * UP_WARPS;
 
+__device__ __forceinline__ void smem_min(uint32_t addr, float v) {
+    float o;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o) : "r"(addr));
+    o = fminf(o, v);
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(o) : "memory");
+}
+
 template <int WIN_T>
 __global__ void __launch_bounds__(UP_STRIDE)
-upsample_mask_min_kernel(const float* __restrict__ T, const int32_t* __restrict__ labels,
+upsample_mask_min_kernel(const float* __restrict__ T, const int32_t* __restrict__ plabels,
                          const int32_t* __restrict__ gt_ids, int H, int W, int h, int w, int d, int N,
                          float* __restrict__ out) {
     extern __shared__ float sbest[];                         // [N][UP_STRIDE]
@@ -236,47 +256,45 @@ upsample_mask_min_kernel(const float* __restrict__ T, const int32_t* __restrict_
     float* mine = sbest + tid;
     for (int o = 0; o < N; ++o) mine[o * UP_STRIDE] = 1.0f;   // pad value of torch.where(mask, d, ones)
     if (pix >= H * W) return;
+    const uint32_t mine_s = (uint32_t)__cvta_generic_to_shared(mine);
     const int Y = pix / W, X = pix - Y * W;
     const Lerp ly = make_lerp(Y, h, H), lx = make_lerp(X, w, W);
-    const float* t00 = T + ((size_t)ly.i0 * w + lx.i0) * L + lane;
-    const float* t01 = T + ((size_t)ly.i0 * w + lx.i1) * L + lane;
-    const float* t10 = T + ((size_t)ly.i1 * w + lx.i0) * L + lane;
-    const float* t11 = T + ((size_t)ly.i1 * w + lx.i1) * L + lane;
+    const float* t00 = T + ((size_t)ly.i0 * w + lx.i0) * L;
+    const float* t01 = T + ((size_t)ly.i0 * w + lx.i1) * L;
+    const float* t10 = T + ((size_t)ly.i1 * w + lx.i0) * L;
+    const float* t11 = T + ((size_t)ly.i1 * w + lx.i1) * L;
+    const int PW = W + 4 * d;                                 // padded label pitch; pixel (Y,X) sits at (Y+2d, X+2d)
     if (win <= 32) {
-        const int xx = X + 2 * (lane - d);
-        const bool lane_ok = lane < win;
-        const bool col_ok = lane_ok && xx >= 0 && xx < W;
-        const int32_t* lp = labels + (Y - 2 * d) * W + (col_ok ? xx : 0);   // row pointer, advanced by 2W per dy
-        if (lane_ok) {
+        if (lane < win) {
+            // label of window element (dyi, lane): padded[(Y + 2*dyi) * PW + X + 2*lane]
+            const int32_t* lp = plabels + (size_t)Y * PW + X + 2 * lane;
+            t00 += lane; t01 += lane; t10 += lane; t11 += lane;
             if (arange) {
 #pragma unroll
                 for (int dyi = 0; dyi < win; ++dyi) {
-                    const int yy = Y + 2 * (dyi - d);
                     const int l = dyi * win;
                     const float u = bilerp(__ldg(t00 + l), __ldg(t01 + l), __ldg(t10 + l), __ldg(t11 + l), ly, lx);
-                    const int lab = (col_ok && yy >= 0 && yy < H) ? __ldg(lp + dyi * 2 * W) : 0;
-                    if ((unsigned)lab < (unsigned)N) { float* b = mine + lab * UP_STRIDE; *b = fminf(*b, u); }
+                    const int lab = __ldg(lp + (size_t)(2 * dyi) * PW);
+                    if ((unsigned)lab < (unsigned)N) smem_min(mine_s + lab * (UP_STRIDE * 4), u);
                 }
             } else {
                 for (int dyi = 0; dyi < win; ++dyi) {
-                    const int yy = Y + 2 * (dyi - d);
                     const int l = dyi * win;
                     const float u = bilerp(__ldg(t00 + l), __ldg(t01 + l), __ldg(t10 + l), __ldg(t11 + l), ly, lx);
-                    const float lf = (col_ok && yy >= 0 && yy < H) ? (float)__ldg(lp + dyi * 2 * W) : 0.f;
+                    const float lf = (float)__ldg(lp + (size_t)(2 * dyi) * PW);
                     for (int o = 0; o < N; ++o)
-                        if (lf == (float)gt_ids[o]) { float* b = mine + o * UP_STRIDE; *b = fminf(*b, u); }
+                        if (lf == (float)gt_ids[o]) smem_min(mine_s + o * (UP_STRIDE * 4), u);
                 }
             }
         }
     } else {
         // wide windows: lanes stride over all L offsets
         for (int l = lane; l < L; l += 32) {
-            const int dy = l / win - d, dx = l % win - d;
-            const float u = bilerp(__ldg(t00 - lane + l), __ldg(t01 - lane + l), __ldg(t10 - lane + l), __ldg(t11 - lane + l), ly, lx);
-            const int yy = Y + 2 * dy, x2 = X + 2 * dx;
-            const float lf = (yy >= 0 && yy < H && x2 >= 0 && x2 < W) ? (float)__ldg(labels + yy * W + x2) : 0.f;
+            const int dyi = l / win, dxi = l % win;
+            const float u = bilerp(__ldg(t00 + l), __ldg(t01 + l), __ldg(t10 + l), __ldg(t11 + l), ly, lx);
+            const float lf = (float)__ldg(plabels + (size_t)(Y + 2 * dyi) * PW + X + 2 * dxi);
             for (int o = 0; o < N; ++o)
-                if (lf == (float)gt_ids[o]) { float* b = mine + o * UP_STRIDE; *b = fminf(*b, u); }
+                if (lf == (float)gt_ids[o]) smem_min(mine_s + o * (UP_STRIDE * 4), u);
         }
     }
     for (int o = 0; o < N; ++o) {
@@ -308,13 +326,14 @@ size_t local_match_workspace_bytes(int H, int W, int C, int N, int d) {
     int h = H / 2, w = W / 2;
     size_t L = (size_t)(2 * d + 1) * (2 * d + 1);
     return 2 * align_up((size_t)C * h * pooled_pitch(w) * sizeof(float), 256) +
-           align_up((size_t)h * w * L * sizeof(float), 256) + 256;
+           align_up((size_t)h * w * L * sizeof(float), 256) +
+           align_up((size_t)(H + 4 * d) * (W + 4 * d) * sizeof(int32_t), 256) + 256;
 }
 
 static int window_volume(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_sc,
                          const float* y, int64_t y_sy, int64_t y_sx, int64_t y_sc,
                          int H, int W, int C, int d, void* ws, size_t ws_bytes, cudaStream_t stream,
-                         float** T_out) {
+                         float** T_out, const int32_t* labels = nullptr, int32_t** plabels_out = nullptr) {
     if (H < 2 || W < 2 || C < 1 || d < 0) return fail_invalid("local match: need H,W >= 2, C >= 1, max_distance >= 0");
     if (ws_bytes < local_match_workspace_bytes(H, W, C, 1, d)) { set_error("local match: workspace too small"); return MANET_E_WORKSPACE; }
     const int h = H / 2, w = W / 2, wp = pooled_pitch(w);
@@ -323,10 +342,13 @@ static int window_volume(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_s
     float* ps = cv.take<float>((size_t)C * h * wp);
     const int win = 2 * d + 1;
     float* T = cv.take<float>((size_t)h * w * win * win);
+    int32_t* plab = cv.take<int32_t>((size_t)(H + 4 * d) * (W + 4 * d));
     int64_t tot = (int64_t)C * h * wp;
-    dim3 pg((unsigned)imin64(ceil_div64(tot, 256), 148 * 8), 2);
+    dim3 pg((unsigned)imin64(ceil_div64(tot, 256), 148 * 8), labels ? 3 : 2);
     PoolSrc a{x, x_sy, x_sx, x_sc, qs}, b{y, y_sy, y_sx, y_sc, ps};
-    avg_pool2_kernel<<<pg, 256, 0, stream>>>(a, b, C, h, w, wp);
+    LabelPad lpad{labels, labels ? plab : nullptr, H, W, 2 * d};
+    avg_pool2_kernel<<<pg, 256, 0, stream>>>(a, b, lpad, C, h, w, wp);
+    if (plabels_out) *plabels_out = plab;
     if (d <= 12) {
         const int ngroups = (win + WDY - 1) / WDY;
         dim3 grid((w + WTX - 1) / WTX, (h + WTY - 1) / WTY);
@@ -354,7 +376,8 @@ int launch_local_match(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_
                        float* out, void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (N < 1) return fail_invalid("local match: N must be >= 1");
     float* T = nullptr;
-    int rc = window_volume(query, q_sy, q_sx, q_sc, prev, p_sy, p_sx, p_sc, H, W, C, d, ws, ws_bytes, stream, &T);
+    int32_t* plab = nullptr;
+    int rc = window_volume(query, q_sy, q_sx, q_sc, prev, p_sy, p_sx, p_sc, H, W, C, d, ws, ws_bytes, stream, &T, labels, &plab);
     if (rc) return rc;
     int64_t pix = (int64_t)H * W;
     const size_t up_smem = (size_t)N * 32 * UP_WARPS * sizeof(float);
@@ -363,7 +386,7 @@ int launch_local_match(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_
     auto kern = (d == 12) ? upsample_mask_min_kernel<25> : (d == 9) ? upsample_mask_min_kernel<19> : upsample_mask_min_kernel<0>;
     if (up_smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)up_smem);
     profile_begin(PROF_LOCAL_MIN, stream);
-    kern<<<(unsigned)ceil_div64(pix, UP_WARPS), UP_STRIDE, up_smem, stream>>>(T, labels, gt_ids, H, W, H / 2, W / 2, d, N, out);
+    kern<<<(unsigned)ceil_div64(pix, UP_WARPS), UP_STRIDE, up_smem, stream>>>(T, plab, gt_ids, H, W, H / 2, W / 2, d, N, out);
     profile_end(PROF_LOCAL_MIN, stream);
     return check_launch("upsample_mask_min_kernel");
 }
