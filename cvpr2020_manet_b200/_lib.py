@@ -49,6 +49,9 @@ SIGNATURES = {
     "manet_session_destroy": (None, [_P]),
     "manet_session_host_buffers": (c_int, [_P] + [POINTER(_P)] * 7),
     "manet_session_step_host": (c_int, [_P, _I, _I, _I, c_uint32]),
+    "manet_session_slot_buffers": (c_int, [_P, _I] + [POINTER(_P)] * 7),
+    "manet_session_submit_host": (c_int, [_P, _I, _I, _I, _I, c_uint32]),
+    "manet_session_wait": (c_int, [_P, _I]),
     "manet_session_upload": (c_int, [_P]),
     "manet_session_step_device": (c_int, [_P, _I, _I, _I, c_uint32]),
     "manet_session_sync": (c_int, [_P]),

@@ -265,18 +265,25 @@ int manet_profile_read(int slot, float* ms_out, int capacity, int* n_out) {
 }
 
 // ------------------------------------------------------------------------------------------ session
+// Two input/output slots so that the host->device copy of step i+1 overlaps the kernels of step i
+// (manet_session_submit_host / manet_session_wait); manet_session_step_host is submit+wait on slot 0.
+struct SessionSlot {
+    float *h_ref, *h_prev, *h_cur, *h_out_g, *h_out_l;          // pinned host staging
+    int32_t *h_ref_lab, *h_prev_lab;
+    float *d_ref, *d_prev, *d_cur, *d_out_g, *d_out_l, *d_raw_l; // device
+    int32_t *d_ref_lab, *d_prev_lab;
+    cudaEvent_t ev_up, ev_done;
+};
+
 struct manet_session {
     int H, W, C, N, d, n_frames;
-    cudaStream_t stream;
-    // pinned host staging
-    float *h_ref, *h_prev, *h_cur, *h_out_g, *h_out_l;
-    int32_t *h_ref_lab, *h_prev_lab;
-    // device
-    float *d_ref, *d_prev, *d_cur, *d_out_g, *d_out_l, *d_raw_l;
-    int32_t *d_ref_lab, *d_prev_lab, *d_ids;
-    float *d_gmem;        // [n_frames, H*W*N]   global-map memory, ones
-    float *d_lmem;        // [n_frames, 9, H*W*N] local-map memory, zeros (IntVOS.py:645)
-    float *d_ldist;       // [n_frames, 9]
+    cudaStream_t stream;          // compute (+ device->host) stream
+    cudaStream_t copy_stream;     // host->device stream
+    SessionSlot slot[2];
+    int32_t* d_ids;
+    float* d_gmem;        // [n_frames, H*W*N]   global-map memory, ones
+    float* d_lmem;        // [n_frames, 9, H*W*N] local-map memory, zeros (IntVOS.py:645)
+    float* d_ldist;       // [n_frames, 9]
     void *ws_g, *ws_l; size_t ws_g_bytes, ws_l_bytes;
 };
 
@@ -292,16 +299,22 @@ manet_session_t* manet_session_create(int H, int W, int C, int N, int max_distan
     memset(s, 0, sizeof(*s));
     s->H = H; s->W = W; s->C = C; s->N = N; s->d = max_distance; s->n_frames = n_frames;
     const size_t px = (size_t)H * W, emb = px * C * sizeof(float), map = px * N * sizeof(float);
-    bool ok = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaMallocHost(&s->h_ref, emb) == cudaSuccess && cudaMallocHost(&s->h_prev, emb) == cudaSuccess &&
-         cudaMallocHost(&s->h_cur, emb) == cudaSuccess && cudaMallocHost(&s->h_out_g, map) == cudaSuccess &&
-         cudaMallocHost(&s->h_out_l, map) == cudaSuccess && cudaMallocHost(&s->h_ref_lab, px * 4) == cudaSuccess &&
-         cudaMallocHost(&s->h_prev_lab, px * 4) == cudaSuccess;
-    ok = ok && cudaMalloc(&s->d_ref, emb) == cudaSuccess && cudaMalloc(&s->d_prev, emb) == cudaSuccess &&
-         cudaMalloc(&s->d_cur, emb) == cudaSuccess && cudaMalloc(&s->d_out_g, map) == cudaSuccess &&
-         cudaMalloc(&s->d_out_l, map) == cudaSuccess && cudaMalloc(&s->d_raw_l, map) == cudaSuccess &&
-         cudaMalloc(&s->d_ref_lab, px * 4) == cudaSuccess && cudaMalloc(&s->d_prev_lab, px * 4) == cudaSuccess &&
-         cudaMalloc(&s->d_ids, N * 4) == cudaSuccess && cudaMalloc(&s->d_gmem, map * n_frames) == cudaSuccess &&
+    bool ok = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i) {
+        SessionSlot& t = s->slot[i];
+        ok = ok && cudaMallocHost(&t.h_ref, emb) == cudaSuccess && cudaMallocHost(&t.h_prev, emb) == cudaSuccess &&
+             cudaMallocHost(&t.h_cur, emb) == cudaSuccess && cudaMallocHost(&t.h_out_g, map) == cudaSuccess &&
+             cudaMallocHost(&t.h_out_l, map) == cudaSuccess && cudaMallocHost(&t.h_ref_lab, px * 4) == cudaSuccess &&
+             cudaMallocHost(&t.h_prev_lab, px * 4) == cudaSuccess;
+        ok = ok && cudaMalloc(&t.d_ref, emb) == cudaSuccess && cudaMalloc(&t.d_prev, emb) == cudaSuccess &&
+             cudaMalloc(&t.d_cur, emb) == cudaSuccess && cudaMalloc(&t.d_out_g, map) == cudaSuccess &&
+             cudaMalloc(&t.d_out_l, map) == cudaSuccess && cudaMalloc(&t.d_raw_l, map) == cudaSuccess &&
+             cudaMalloc(&t.d_ref_lab, px * 4) == cudaSuccess && cudaMalloc(&t.d_prev_lab, px * 4) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&t.ev_up, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&t.ev_done, cudaEventDisableTiming) == cudaSuccess;
+    }
+    ok = ok && cudaMalloc(&s->d_ids, N * 4) == cudaSuccess && cudaMalloc(&s->d_gmem, map * n_frames) == cudaSuccess &&
          cudaMalloc(&s->d_lmem, map * n_frames * kMemoryRounds) == cudaSuccess &&
          cudaMalloc(&s->d_ldist, sizeof(float) * n_frames * kMemoryRounds) == cudaSuccess;
     s->ws_g_bytes = manet_global_match_workspace_bytes((int64_t)px, (int64_t)px, C, N, 1);
@@ -325,71 +338,112 @@ manet_session_t* manet_session_create(int H, int W, int C, int N, int max_distan
 
 void manet_session_destroy(manet_session_t* s) {
     if (!s) return;
-    cudaFreeHost(s->h_ref); cudaFreeHost(s->h_prev); cudaFreeHost(s->h_cur); cudaFreeHost(s->h_out_g); cudaFreeHost(s->h_out_l);
-    cudaFreeHost(s->h_ref_lab); cudaFreeHost(s->h_prev_lab);
-    cudaFree(s->d_ref); cudaFree(s->d_prev); cudaFree(s->d_cur); cudaFree(s->d_out_g); cudaFree(s->d_out_l); cudaFree(s->d_raw_l);
-    cudaFree(s->d_ref_lab); cudaFree(s->d_prev_lab); cudaFree(s->d_ids); cudaFree(s->d_gmem); cudaFree(s->d_lmem);
-    cudaFree(s->d_ldist); cudaFree(s->ws_g); cudaFree(s->ws_l);
+    for (int i = 0; i < 2; ++i) {
+        SessionSlot& t = s->slot[i];
+        cudaFreeHost(t.h_ref); cudaFreeHost(t.h_prev); cudaFreeHost(t.h_cur); cudaFreeHost(t.h_out_g); cudaFreeHost(t.h_out_l);
+        cudaFreeHost(t.h_ref_lab); cudaFreeHost(t.h_prev_lab);
+        cudaFree(t.d_ref); cudaFree(t.d_prev); cudaFree(t.d_cur); cudaFree(t.d_out_g); cudaFree(t.d_out_l); cudaFree(t.d_raw_l);
+        cudaFree(t.d_ref_lab); cudaFree(t.d_prev_lab);
+        if (t.ev_up) cudaEventDestroy(t.ev_up);
+        if (t.ev_done) cudaEventDestroy(t.ev_done);
+    }
+    cudaFree(s->d_ids); cudaFree(s->d_gmem); cudaFree(s->d_lmem); cudaFree(s->d_ldist); cudaFree(s->ws_g); cudaFree(s->ws_l);
     if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     delete s;
+}
+
+int manet_session_slot_buffers(manet_session_t* s, int slot, float** ref, float** prev, float** cur, int32_t** ref_labels,
+                               int32_t** prev_labels, float** out_global, float** out_local) {
+    MANET_REQUIRE(s && (slot == 0 || slot == 1), "session: null / bad slot");
+    SessionSlot& t = s->slot[slot];
+    if (ref) *ref = t.h_ref; if (prev) *prev = t.h_prev; if (cur) *cur = t.h_cur;
+    if (ref_labels) *ref_labels = t.h_ref_lab; if (prev_labels) *prev_labels = t.h_prev_lab;
+    if (out_global) *out_global = t.h_out_g; if (out_local) *out_local = t.h_out_l;
+    return 0;
 }
 
 int manet_session_host_buffers(manet_session_t* s, float** ref, float** prev, float** cur, int32_t** ref_labels,
                                int32_t** prev_labels, float** out_global, float** out_local) {
-    MANET_REQUIRE(s, "session: null");
-    if (ref) *ref = s->h_ref; if (prev) *prev = s->h_prev; if (cur) *cur = s->h_cur;
-    if (ref_labels) *ref_labels = s->h_ref_lab; if (prev_labels) *prev_labels = s->h_prev_lab;
-    if (out_global) *out_global = s->h_out_g; if (out_local) *out_local = s->h_out_l;
-    return 0;
+    return manet_session_slot_buffers(s, 0, ref, prev, cur, ref_labels, prev_labels, out_global, out_local);
+}
+
+static int session_upload_slot(manet_session_t* s, int slot, cudaStream_t st) {
+    SessionSlot& t = s->slot[slot];
+    const size_t px = (size_t)s->H * s->W, emb = px * s->C * sizeof(float);
+    cudaMemcpyAsync(t.d_ref, t.h_ref, emb, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(t.d_cur, t.h_cur, emb, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(t.d_ref_lab, t.h_ref_lab, px * 4, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(t.d_prev, t.h_prev, emb, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(t.d_prev_lab, t.h_prev_lab, px * 4, cudaMemcpyHostToDevice, st);
+    return check_launch("session upload");
 }
 
 int manet_session_upload(manet_session_t* s) {
     MANET_REQUIRE(s, "session: null");
-    const size_t px = (size_t)s->H * s->W, emb = px * s->C * sizeof(float);
-    cudaMemcpyAsync(s->d_ref, s->h_ref, emb, cudaMemcpyHostToDevice, s->stream);
-    cudaMemcpyAsync(s->d_prev, s->h_prev, emb, cudaMemcpyHostToDevice, s->stream);
-    cudaMemcpyAsync(s->d_cur, s->h_cur, emb, cudaMemcpyHostToDevice, s->stream);
-    cudaMemcpyAsync(s->d_ref_lab, s->h_ref_lab, px * 4, cudaMemcpyHostToDevice, s->stream);
-    cudaMemcpyAsync(s->d_prev_lab, s->h_prev_lab, px * 4, cudaMemcpyHostToDevice, s->stream);
-    return check_launch("session upload");
+    return session_upload_slot(s, 0, s->stream);
 }
 
 // embeddings are [C,H,W] storage, consumed as [H,W,C] views exactly as IntVOS.py:605-606,625 do
+static int session_step_slot(manet_session_t* s, int slot, int frame, int interaction_num, int start_annotated_frame,
+                             uint32_t flags) {
+    MANET_REQUIRE(frame >= 0 && frame < s->n_frames, "session: frame out of range");
+    MANET_REQUIRE(frame != start_annotated_frame, "session: propagation never visits the annotated frame (1/|f-f0|, IntVOS.py:648)");
+    SessionSlot& t = s->slot[slot];
+    const int64_t px = (int64_t)s->H * s->W, n = px * s->N;
+    int rc = manet_global_match(t.d_ref, 1, px, px, t.d_ref_lab, t.d_cur, 1, px, px, s->C, s->N, 1,
+                                flags | MANET_GM_NORMALIZE, s->d_gmem + (size_t)frame * n, t.d_out_g, s->ws_g, s->ws_g_bytes,
+                                s->stream);
+    if (rc) return rc;
+    rc = manet_local_match(t.d_prev, s->W, 1, px, t.d_cur, s->W, 1, px, t.d_prev_lab, s->d_ids, s->H, s->W, s->C, s->N,
+                           s->d, t.d_raw_l, s->ws_l, s->ws_l_bytes, s->stream);
+    if (rc) return rc;
+    int df = frame - start_annotated_frame; if (df < 0) df = -df;
+    return manet_local_map_store_select(t.d_raw_l, s->d_lmem + (size_t)frame * kMemoryRounds * n,
+                                        s->d_ldist + (size_t)frame * kMemoryRounds, interaction_num,
+                                        (float)(1.0 / (double)df), t.d_out_l, n, s->stream);
+}
+
 int manet_session_step_device(manet_session_t* s, int frame, int interaction_num, int start_annotated_frame,
                               uint32_t flags) {
     MANET_REQUIRE(s, "session: null");
-    MANET_REQUIRE(frame >= 0 && frame < s->n_frames, "session: frame out of range");
-    MANET_REQUIRE(frame != start_annotated_frame, "session: propagation never visits the annotated frame (1/|f-f0|, IntVOS.py:648)");
-    const int64_t px = (int64_t)s->H * s->W, n = px * s->N;
-    int rc = manet_global_match(s->d_ref, 1, px, px, s->d_ref_lab, s->d_cur, 1, px, px, s->C, s->N, 1,
-                                flags | MANET_GM_NORMALIZE, s->d_gmem + (size_t)frame * n, s->d_out_g, s->ws_g, s->ws_g_bytes,
-                                s->stream);
+    return session_step_slot(s, 0, frame, interaction_num, start_annotated_frame, flags);
+}
+
+int manet_session_submit_host(manet_session_t* s, int slot, int frame, int interaction_num, int start_annotated_frame,
+                              uint32_t flags) {
+    MANET_REQUIRE(s && (slot == 0 || slot == 1), "session: null / bad slot");
+    SessionSlot& t = s->slot[slot];
+    int rc = session_upload_slot(s, slot, s->copy_stream);
     if (rc) return rc;
-    rc = manet_local_match(s->d_prev, s->W, 1, px, s->d_cur, s->W, 1, px, s->d_prev_lab, s->d_ids, s->H, s->W, s->C, s->N,
-                           s->d, s->d_raw_l, s->ws_l, s->ws_l_bytes, s->stream);
+    cudaEventRecord(t.ev_up, s->copy_stream);
+    cudaStreamWaitEvent(s->stream, t.ev_up, 0);
+    rc = session_step_slot(s, slot, frame, interaction_num, start_annotated_frame, flags);
     if (rc) return rc;
-    int df = frame - start_annotated_frame; if (df < 0) df = -df;
-    return manet_local_map_store_select(s->d_raw_l, s->d_lmem + (size_t)frame * kMemoryRounds * n,
-                                        s->d_ldist + (size_t)frame * kMemoryRounds, interaction_num,
-                                        (float)(1.0 / (double)df), s->d_out_l, n, s->stream);
+    const size_t map = (size_t)s->H * s->W * s->N * sizeof(float);
+    cudaMemcpyAsync(t.h_out_g, t.d_out_g, map, cudaMemcpyDeviceToHost, s->stream);
+    cudaMemcpyAsync(t.h_out_l, t.d_out_l, map, cudaMemcpyDeviceToHost, s->stream);
+    cudaEventRecord(t.ev_done, s->stream);
+    return check_launch("session submit");
+}
+
+int manet_session_wait(manet_session_t* s, int slot) {
+    MANET_REQUIRE(s && (slot == 0 || slot == 1), "session: null / bad slot");
+    cudaError_t e = cudaEventSynchronize(s->slot[slot].ev_done);
+    if (e != cudaSuccess) { set_error("session wait: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
 }
 
 int manet_session_step_host(manet_session_t* s, int frame, int interaction_num, int start_annotated_frame, uint32_t flags) {
-    int rc = manet_session_upload(s);
+    int rc = manet_session_submit_host(s, 0, frame, interaction_num, start_annotated_frame, flags);
     if (rc) return rc;
-    rc = manet_session_step_device(s, frame, interaction_num, start_annotated_frame, flags);
-    if (rc) return rc;
-    const size_t map = (size_t)s->H * s->W * s->N * sizeof(float);
-    cudaMemcpyAsync(s->h_out_g, s->d_out_g, map, cudaMemcpyDeviceToHost, s->stream);
-    cudaMemcpyAsync(s->h_out_l, s->d_out_l, map, cudaMemcpyDeviceToHost, s->stream);
-    cudaError_t e = cudaStreamSynchronize(s->stream);
-    if (e != cudaSuccess) { set_error("session step: %s", cudaGetErrorString(e)); return (int)e; }
-    return 0;
+    return manet_session_wait(s, 0);
 }
 
 int manet_session_sync(manet_session_t* s) {
     MANET_REQUIRE(s, "session: null");
-    cudaError_t e = cudaStreamSynchronize(s->stream);
+    cudaError_t e = cudaStreamSynchronize(s->copy_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
     if (e != cudaSuccess) { set_error("session sync: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;
 }

@@ -66,21 +66,27 @@ class MatchingSession:
         self._h = self._lib.manet_session_create(height, width, channels, n_ids, max_distance, n_frames)
         if not self._h:
             raise _lib.ManetError("manet_session_create failed: " + self._lib.manet_last_error().decode())
-        ptrs = [ctypes.c_void_p() for _ in range(7)]
-        check(self._lib.manet_session_host_buffers(self._h, *[ctypes.byref(p) for p in ptrs]), "manet_session_host_buffers")
         px = height * width
 
         def view(p, n, dtype):
             ctype = ctypes.c_float if dtype == np.float32 else ctypes.c_int32
             return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctype)), shape=(n,))
 
-        self.ref = view(ptrs[0], px * channels, np.float32).reshape(channels, height, width)
-        self.prev = view(ptrs[1], px * channels, np.float32).reshape(channels, height, width)
-        self.cur = view(ptrs[2], px * channels, np.float32).reshape(channels, height, width)
-        self.ref_labels = view(ptrs[3], px, np.int32).reshape(height, width)
-        self.prev_labels = view(ptrs[4], px, np.int32).reshape(height, width)
-        self.out_global = view(ptrs[5], px * n_ids, np.float32).reshape(height, width, n_ids)
-        self.out_local = view(ptrs[6], px * n_ids, np.float32).reshape(height, width, n_ids)
+        self.slots = []
+        for slot in (0, 1):
+            ptrs = [ctypes.c_void_p() for _ in range(7)]
+            check(self._lib.manet_session_slot_buffers(self._h, slot, *[ctypes.byref(p) for p in ptrs]),
+                  "manet_session_slot_buffers")
+            self.slots.append(dict(
+                ref=view(ptrs[0], px * channels, np.float32).reshape(channels, height, width),
+                prev=view(ptrs[1], px * channels, np.float32).reshape(channels, height, width),
+                cur=view(ptrs[2], px * channels, np.float32).reshape(channels, height, width),
+                ref_labels=view(ptrs[3], px, np.int32).reshape(height, width),
+                prev_labels=view(ptrs[4], px, np.int32).reshape(height, width),
+                out_global=view(ptrs[5], px * n_ids, np.float32).reshape(height, width, n_ids),
+                out_local=view(ptrs[6], px * n_ids, np.float32).reshape(height, width, n_ids)))
+        for k, v in self.slots[0].items():      # slot 0 doubles as the plain synchronous interface
+            setattr(self, k, v)
 
     @property
     def h2d_bytes_per_step(self):
@@ -97,6 +103,16 @@ class MatchingSession:
         check(self._lib.manet_session_step_host(self._h, frame, interaction_num, start_annotated_frame, flags),
               "manet_session_step_host")
         return self.out_global, self.out_local
+
+    def submit_host(self, slot, frame, interaction_num=1, start_annotated_frame=0, drop_unlabelled=True):
+        """Enqueue upload -> step -> download for ``slot`` (0 or 1) and return immediately."""
+        flags = _lib.GM_DROP_UNLAB if drop_unlabelled else 0
+        check(self._lib.manet_session_submit_host(self._h, slot, frame, interaction_num, start_annotated_frame, flags),
+              "manet_session_submit_host")
+
+    def wait(self, slot):
+        check(self._lib.manet_session_wait(self._h, slot), "manet_session_wait")
+        return self.slots[slot]["out_global"], self.slots[slot]["out_local"]
 
     def upload(self):
         check(self._lib.manet_session_upload(self._h), "manet_session_upload")

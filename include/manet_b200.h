@@ -206,6 +206,18 @@ int manet_session_host_buffers(manet_session_t* s, float** ref, float** prev, fl
                                float** out_global, float** out_local);
 int manet_session_step_host(manet_session_t* s, int frame, int interaction_num,
                             int start_annotated_frame, uint32_t flags);
+/* Pipelined form: the session has two input/output slots (0 and 1), each with its own pinned host
+ * buffers (manet_session_slot_buffers).  manet_session_submit_host enqueues upload -> step ->
+ * download for one slot and returns at once (uploads run on a separate copy stream, so the upload
+ * of one slot overlaps the kernels of the other); manet_session_wait blocks until that slot's
+ * outputs are in its host buffers.  Steps execute in submission order (the map memories are shared).
+ * manet_session_step_host == submit(slot 0) + wait(slot 0). */
+int manet_session_slot_buffers(manet_session_t* s, int slot, float** ref, float** prev, float** cur,
+                               int32_t** ref_labels, int32_t** prev_labels,
+                               float** out_global, float** out_local);
+int manet_session_submit_host(manet_session_t* s, int slot, int frame, int interaction_num,
+                              int start_annotated_frame, uint32_t flags);
+int manet_session_wait(manet_session_t* s, int slot);
 /* device-resident variant of the same step (inputs already uploaded by a previous
  * manet_session_step_host or manet_session_upload): no copies, asynchronous on the session stream */
 int manet_session_upload(manet_session_t* s);

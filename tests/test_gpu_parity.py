@@ -325,6 +325,18 @@ def test_host_buffer_session_equals_device_api(api, cfg_guard):
         wg, wl = engine.prop_matching_step(ref.cuda(), prev.cuda(), cur.cuda(), rl.cuda(), pl.cuda(), N - 1, 1, d, gm, lm,
                                            "x", 3, rnd, ann)
         assert np.array_equal(og, wg[0, :, :, :, 0].cpu().numpy()) and np.array_equal(ol, wl[0, :, :, :, 0].cpu().numpy())
+    # pipelined two-slot form: same results, in submission order
+    for slot in (0, 1):
+        for k in ("ref", "prev", "cur", "ref_labels", "prev_labels"):
+            s.slots[slot][k][:] = s.slots[0][k]
+    s.submit_host(0, 4, 1, 1)
+    s.submit_host(1, 5, 1, 1)
+    a_g, a_l = (x.copy() for x in s.wait(0))
+    b_g, b_l = (x.copy() for x in s.wait(1))
+    w4 = engine.prop_matching_step(ref.cuda(), prev.cuda(), cur.cuda(), rl.cuda(), pl.cuda(), N - 1, 1, d, gm, lm, "x", 4, 1, 1)
+    w5 = engine.prop_matching_step(ref.cuda(), prev.cuda(), cur.cuda(), rl.cuda(), pl.cuda(), N - 1, 1, d, gm, lm, "x", 5, 1, 1)
+    assert np.array_equal(a_g, w4[0][0, :, :, :, 0].cpu().numpy()) and np.array_equal(a_l, w4[1][0, :, :, :, 0].cpu().numpy())
+    assert np.array_equal(b_g, w5[0][0, :, :, :, 0].cpu().numpy()) and np.array_equal(b_l, w5[1][0, :, :, :, 0].cpu().numpy())
     s.close()
 
 
