@@ -39,7 +39,9 @@ M_PIX = H * W
 WORKLOAD = "global+local matching + map-memory update, 480p emb 100x120x214, 5 objects (N=6), max_distance=12, k=1"
 ALGO_FLOP_GLOBAL = 2.0 * M_PIX * M_PIX * C                      # 2*M*R*C, SURVEY.md section 8d
 ALGO_BYTES_LOCAL = 4.0 * (2 * C * H * W + H * W + H * W * N_IDS)
-KERNELS_PER_STEP = 9   # scan, convert, umma, finalize | pool x2, window, upsample-mask-min | local-map store/select
+# executed tensor-core work: 3 fp16 products x K padded 100->112 x M padded to 256 x R padded per 256-row bucket
+EXEC_FLOP_GLOBAL = 3 * 2.0 * (101 * 256) * 112 * (103 * 256)
+KERNELS_PER_STEP = 8   # scan, convert, umma, finalize | pool(+label pad), window, upsample-mask-min | local-map store/select
 
 
 def load_peaks():
@@ -273,13 +275,15 @@ def run_own_arm(args, rank, local_rank, world):
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("global_tcgen05_dram_bytes_per_launch")
         achieved = (ALGO_FLOP_GLOBAL / (k_ms * 1e-3) / 1e12) if k_ms else None
-        roofline = {"kernel": "gm_umma_kernel (global matching, 3 x fp16-split tcgen05 MMAs per product)",
+        roofline = {"kernel": "gm_umma2_kernel (global matching, cta_group::2 tcgen05, 3 fp16-split MMAs per product)",
                     "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                     "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": traffic,
+                    "achieved_executed": (EXEC_FLOP_GLOBAL / (k_ms * 1e-3) / 1e12) if k_ms else None,
+                    "frac_executed": (EXEC_FLOP_GLOBAL / (k_ms * 1e-3) / 1e12 / peaks["tflops"]) if k_ms else None,
                     "kernel_ms": k_ms, "kernel_share_of_step": (k_ms / (total_s * 1e3 / K)) if k_ms else None,
                     "peak_source": peaks["source"],
                     "algorithmic_flop_per_launch": ALGO_FLOP_GLOBAL,
-                    "executed_mma_flop_per_launch": 3 * 2.0 * (201 * 128) * 112 * 25856,
+                    "executed_mma_flop_per_launch": EXEC_FLOP_GLOBAL,
                     "local": {"bound": "hbm", "algorithmic_bytes": ALGO_BYTES_LOCAL,
                               "window_kernel_ms": prof["local_window"], "min_kernel_ms": prof["local_upsample_mask_min"],
                               "achieved_gbs": (ALGO_BYTES_LOCAL / ((prof["local_window"] + prof["local_upsample_mask_min"]) * 1e-3) / 1e9)

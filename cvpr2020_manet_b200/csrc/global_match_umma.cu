@@ -39,8 +39,8 @@ constexpr int GM_CHUNK_BYTES = 16384;  // one (unit, part, k-block): 128 rows x 
 constexpr int GM_UNIT_BYTES = 4 * GM_CHUNK_BYTES;
 constexpr int GM_EPI_WARPS = 8;           // two warps per TMEM lane quarter, each takes half of the columns
 constexpr int GM_THREADS = 32 * (2 + GM_EPI_WARPS);
-constexpr int GM_STAGES = 2;
-constexpr int GM_STAGE_BYTES = 2 * 2 * GM_CHUNK_BYTES;       // one part of a 256-row tile
+constexpr int GM_STAGES = 4;
+constexpr int GM_STAGE_BYTES = 2 * GM_CHUNK_BYTES;           // one (part, k-block) of a 256-row tile: 256 rows x 128 B
 constexpr int GM_SMEM_A = GM_UNIT_BYTES;
 constexpr int GM_SMEM_BAR = GM_SMEM_A + GM_STAGES * GM_STAGE_BYTES;
 constexpr int GM_SMEM_TOTAL = GM_SMEM_BAR + 256 + 1024;     // + barriers + alignment slack
@@ -60,7 +60,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {      // call from ONE lane
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -80,6 +80,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// One lane of a converged warp.  The MMA / bulk-copy instructions take warp-uniform operands (uniform
+// registers in SASS): the issuing warps therefore run their loops with ALL lanes (uniform control flow,
+// uniform address arithmetic) and elect a lane only around the instruction itself.  Wrapping the whole
+// loop in `if (lane == 0)` makes every operand "divergent" for the compiler, which then emits an
+// ELECT/R2UR waterfall of ~30 instructions per MMA -- measured: 4200 instead of 2700 cycles per tile.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -377,18 +387,19 @@ gm_umma_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bim
     const uint32_t bars = base + GM_SMEM_BAR;
     // barrier slots (8 bytes each)
     const uint32_t full_b = bars + 0;          // [GM_STAGES]
-    const uint32_t empty_b = bars + 16;        // [GM_STAGES]
-    const uint32_t a_full = bars + 32;
-    const uint32_t a_empty = bars + 40;
-    const uint32_t tmem_full = bars + 48;      // [2]
-    const uint32_t tmem_empty = bars + 64;     // [2]
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + GM_SMEM_BAR + 96);
+    const uint32_t empty_b = bars + 32;        // [GM_STAGES]
+    const uint32_t a_full = bars + 64;
+    const uint32_t a_empty = bars + 72;
+    const uint32_t tmem_full = bars + 80;      // [2]
+    const uint32_t tmem_empty = bars + 96;     // [2]
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + GM_SMEM_BAR + 112);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_rtiles = ctrl->n_rtiles;
     const long long total = (long long)n_mtiles * n_rtiles;
     const long long t_begin = total * blockIdx.x / gridDim.x;
     const long long t_end = total * (blockIdx.x + 1) / gridDim.x;
+    const int nkb = ksteps > 4 ? 2 : 1;                     // K blocks of 64 actually used (C <= 64 -> one)
 
     if (warp == 1) {
         if (lane == 0) {
@@ -407,74 +418,78 @@ gm_umma_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bim
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ------------------------------------------------ producer
-        if (lane == 0) {
-            Ring st; uint32_t ae_phase = 0; long long cur_m = -1;
-            for (long long tile = t_begin; tile < t_end; ++tile) {
-                const long long m = tile / n_rtiles; const long long rt = tile % n_rtiles;
-                if (m != cur_m) {
-                    mbar_wait(a_empty, ae_phase ^ 1); ae_phase ^= 1;
+        // ------------------------------------------------ producer (whole warp, one elected lane issues)
+        Ring st; uint32_t ae_phase = 0; long long cur_m = -1;
+        for (long long tile = t_begin; tile < t_end; ++tile) {
+            const long long m = tile / n_rtiles; const long long rt = tile % n_rtiles;
+            if (m != cur_m) {
+                mbar_wait(a_empty, ae_phase ^ 1); ae_phase ^= 1;
+                if (elect_one()) {
                     mbar_expect_tx(a_full, GM_UNIT_BYTES);
                     bulk_g2s(sA, Aimg + (size_t)m * GM_UNIT_BYTES, GM_UNIT_BYTES, a_full);
-                    cur_m = m;
                 }
-                for (int part = 0; part < 2; ++part) {
+                __syncwarp();
+                cur_m = m;
+            }
+            for (int part = 0; part < 2; ++part) {
+                for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(empty_b + 8 * st.idx, st.phase ^ 1);
                     const uint32_t fb = full_b + 8 * st.idx;
-                    mbar_expect_tx(fb, GM_STAGE_BYTES);
                     const uint32_t dst = sB + st.idx * GM_STAGE_BYTES;
-#pragma unroll
-                    for (int unit = 0; unit < 2; ++unit)
-#pragma unroll
-                        for (int kb = 0; kb < 2; ++kb)
-                            bulk_g2s(dst + kb * (2 * GM_CHUNK_BYTES) + unit * GM_CHUNK_BYTES,
-                                     Bimg + ((size_t)(2 * rt + unit) * 4 + part * 2 + kb) * GM_CHUNK_BYTES,
-                                     GM_CHUNK_BYTES, fb);
+                    const uint8_t* src = Bimg + ((size_t)(2 * rt) * 4 + part * 2 + kb) * GM_CHUNK_BYTES;
+                    if (elect_one()) {
+                        mbar_expect_tx(fb, GM_STAGE_BYTES);
+                        bulk_g2s(dst, src, GM_CHUNK_BYTES, fb);
+                        bulk_g2s(dst + GM_CHUNK_BYTES, src + 4 * GM_CHUNK_BYTES, GM_CHUNK_BYTES, fb);
+                    }
+                    __syncwarp();
                     st.advance(GM_STAGES);
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = idesc_f16(GM_BM, GM_BN);
-            Ring st, acc; uint32_t af_phase = 0; long long cur_m = -1;
-            for (long long tile = t_begin; tile < t_end; ++tile) {
-                const long long m = tile / n_rtiles;
-                if (m != cur_m) { mbar_wait(a_full, af_phase); af_phase ^= 1; cur_m = m; }
-                mbar_wait(tmem_empty + 8 * acc.idx, acc.phase ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc.idx * GM_BN;
-                // stage with the hi part of the reference tile: qh.rh then ql.rh
-                mbar_wait(full_b + 8 * st.idx, st.phase);
-                tc_fence_after();
-                {
-                    const uint32_t bB = sB + st.idx * GM_STAGE_BYTES;
-                    for (int k = 0; k < ksteps; ++k)
-                        umma_f16(d_tmem, smem_desc_sw128(sA + (k >> 2) * GM_CHUNK_BYTES + (k & 3) * 32),
-                                 smem_desc_sw128(bB + (k >> 2) * (2 * GM_CHUNK_BYTES) + (k & 3) * 32), idesc, k > 0);
-                    for (int k = 0; k < ksteps; ++k)
-                        umma_f16(d_tmem, smem_desc_sw128(sA + 2 * GM_CHUNK_BYTES + (k >> 2) * GM_CHUNK_BYTES + (k & 3) * 32),
-                                 smem_desc_sw128(bB + (k >> 2) * (2 * GM_CHUNK_BYTES) + (k & 3) * 32), idesc, 1);
+        // ------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
+        constexpr uint32_t idesc = idesc_f16(GM_BM, GM_BN);
+        const uint64_t descA_hi = smem_desc_sw128(sA), descA_lo = smem_desc_sw128(sA + 2 * GM_CHUNK_BYTES);
+        Ring st, acc; uint32_t af_phase = 0; long long cur_m = -1;
+        for (long long tile = t_begin; tile < t_end; ++tile) {
+            const long long m = tile / n_rtiles;
+            if (m != cur_m) { mbar_wait(a_full, af_phase); af_phase ^= 1; cur_m = m; }
+            mbar_wait(tmem_empty + 8 * acc.idx, acc.phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc.idx * GM_BN;
+            // B arrives in (part, k-block) stages of 256 rows x 64 K: [hi,kb0] [hi,kb1] [lo,kb0] [lo,kb1].
+            // hi stages feed qh.rh and ql.rh, lo stages feed qh.rl; a stage is released as soon as its
+            // MMAs retire so the producer can refill it while the rest of the tile is still computing.
+            // Descriptors differ only in the start-address field (>>4): +2 per K step of 32 bytes,
+            // +(16 KB >> 4) per A k-block.
+            for (int part = 0; part < 2; ++part) {
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(full_b + 8 * st.idx, st.phase);
+                    tc_fence_after();
+                    const uint64_t descB = smem_desc_sw128(sB + st.idx * GM_STAGE_BYTES);
+                    const uint64_t dA = descA_hi + (uint64_t)(kb * (GM_CHUNK_BYTES >> 4));
+                    const uint64_t dAl = descA_lo + (uint64_t)(kb * (GM_CHUNK_BYTES >> 4));
+                    const int k_end = min(ksteps - 4 * kb, 4);
+                    if (elect_one()) {
+                        for (int k = 0; k < k_end; ++k)
+                            umma_f16(d_tmem, dA + 2 * k, descB + 2 * k, idesc, (part | kb | k) ? 1u : 0u);
+                        if (part == 0)
+                            for (int k = 0; k < k_end; ++k)
+                                umma_f16(d_tmem, dAl + 2 * k, descB + 2 * k, idesc, 1u);
+                        tc_commit(empty_b + 8 * st.idx);
+                    }
+                    __syncwarp();
+                    st.advance(GM_STAGES);
                 }
-                tc_commit(empty_b + 8 * st.idx);
-                st.advance(GM_STAGES);
-                // stage with the lo part: qh.rl
-                mbar_wait(full_b + 8 * st.idx, st.phase);
-                tc_fence_after();
-                {
-                    const uint32_t bB = sB + st.idx * GM_STAGE_BYTES;
-                    for (int k = 0; k < ksteps; ++k)
-                        umma_f16(d_tmem, smem_desc_sw128(sA + (k >> 2) * GM_CHUNK_BYTES + (k & 3) * 32),
-                                 smem_desc_sw128(bB + (k >> 2) * (2 * GM_CHUNK_BYTES) + (k & 3) * 32), idesc, 1);
-                }
-                tc_commit(empty_b + 8 * st.idx);
-                st.advance(GM_STAGES);
-                tc_commit(tmem_full + 8 * acc.idx);
-                const bool last_of_m = (tile + 1 == t_end) || ((tile + 1) / n_rtiles != m);
-                if (last_of_m) tc_commit(a_empty);
-                acc.advance(2);
             }
+            const bool last_of_m = (tile + 1 == t_end) || ((tile + 1) / n_rtiles != m);
+            if (elect_one()) {
+                tc_commit(tmem_full + 8 * acc.idx);
+                if (last_of_m) tc_commit(a_empty);
+            }
+            __syncwarp();
+            acc.advance(2);
         }
     } else {
         // ------------------------------------------------ epilogue (warps 2..9)
@@ -608,81 +623,100 @@ gm_umma2_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bi
 
     if (warp == 0) {
         // ------------------------------------------------ producer (both CTAs: own A rows, own half of B)
-        if (lane == 0) {
-            Ring st; uint32_t ae_phase = 0; long long cur_m = -1;
-            for (long long tile = t_begin; tile < t_end; ++tile) {
-                const long long m = tile / n_rtiles; const long long rt = tile % n_rtiles;
-                if (m != cur_m) {
-                    mbar_wait(a_empty, ae_phase ^ 1); ae_phase ^= 1;
+        Ring st; uint32_t ae_phase = 0; long long cur_m = -1;
+        for (long long tile = t_begin; tile < t_end; ++tile) {
+            const long long m = tile / n_rtiles; const long long rt = tile % n_rtiles;
+            if (m != cur_m) {
+                mbar_wait(a_empty, ae_phase ^ 1); ae_phase ^= 1;
+                if (elect_one()) {
                     mbar_expect_tx(a_full, GM_UNIT_BYTES);
                     bulk_g2s(sA, Aimg + (size_t)(2 * m + rank) * GM_UNIT_BYTES, GM_UNIT_BYTES, a_full);
-                    cur_m = m;
                 }
-                for (int part = 0; part < 2; ++part) {
-                    mbar_wait(empty_b + 8 * st.idx, st.phase ^ 1);
-                    const uint32_t fb = full_b + 8 * st.idx;
+                __syncwarp();
+                cur_m = m;
+            }
+            for (int part = 0; part < 2; ++part) {
+                mbar_wait(empty_b + 8 * st.idx, st.phase ^ 1);
+                const uint32_t fb = full_b + 8 * st.idx;
+                if (elect_one()) {
                     mbar_expect_tx(fb, G2_STAGE_BYTES);
                     // (unit, part) = 2 consecutive k-block chunks = exactly this stage's image
                     bulk_g2s(sB + st.idx * G2_STAGE_BYTES,
                              Bimg + ((size_t)(2 * rt + rank) * 4 + part * 2) * GM_CHUNK_BYTES, G2_STAGE_BYTES, fb);
-                    st.advance(G2_STAGES);
                 }
+                __syncwarp();
+                st.advance(G2_STAGES);
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            if (leader) {
-                // -------------------------------------------- MMA issuer (leader CTA only)
-                constexpr uint32_t idesc = idesc_f16(2 * GM_BM, GM_BN);
-                Ring st, acc; uint32_t af_phase = 0; long long cur_m = -1;
-                for (long long tile = t_begin; tile < t_end; ++tile) {
-                    const long long m = tile / n_rtiles;
-                    if (m != cur_m) { mbar_wait(a_full, af_phase); mbar_wait_cluster(peer_a_full, af_phase); af_phase ^= 1; cur_m = m; }
-                    mbar_wait_cluster(tmem_empty + 8 * acc.idx, acc.phase ^ 1);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + acc.idx * GM_BN;
-                    mbar_wait(full_b + 8 * st.idx, st.phase);
-                    mbar_wait_cluster(peer_full + 8 * st.idx, st.phase);
-                    tc_fence_after();
-                    {
-                        const uint32_t bB = sB + st.idx * G2_STAGE_BYTES;
-                        for (int k = 0; k < ksteps; ++k)
-                            umma2_f16(d_tmem, smem_desc_sw128(sA + (k >> 2) * GM_CHUNK_BYTES + (k & 3) * 32),
-                                      smem_desc_sw128(bB + (k >> 2) * GM_CHUNK_BYTES + (k & 3) * 32), idesc, k > 0);
-                        for (int k = 0; k < ksteps; ++k)
-                            umma2_f16(d_tmem, smem_desc_sw128(sA + 2 * GM_CHUNK_BYTES + (k >> 2) * GM_CHUNK_BYTES + (k & 3) * 32),
-                                      smem_desc_sw128(bB + (k >> 2) * GM_CHUNK_BYTES + (k & 3) * 32), idesc, 1);
+        if (leader) {
+            // -------------------------------------------- MMA issuer (leader CTA only; whole warp, elected lane issues)
+            constexpr uint32_t idesc = idesc_f16(2 * GM_BM, GM_BN);
+            const uint64_t descA_hi = smem_desc_sw128(sA), descA_lo = smem_desc_sw128(sA + 2 * GM_CHUNK_BYTES);
+            Ring st, acc; uint32_t af_phase = 0; long long cur_m = -1;
+            for (long long tile = t_begin; tile < t_end; ++tile) {
+                const long long m = tile / n_rtiles;
+                if (m != cur_m) { mbar_wait(a_full, af_phase); mbar_wait_cluster(peer_a_full, af_phase); af_phase ^= 1; cur_m = m; }
+                mbar_wait_cluster(tmem_empty + 8 * acc.idx, acc.phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc.idx * GM_BN;
+                // k-step k lives in k-block k>>2 (16 KB apart) at byte offset 32*(k&3): descriptor += (k>>2)*1024 + (k&3)*2
+                mbar_wait(full_b + 8 * st.idx, st.phase);
+                mbar_wait_cluster(peer_full + 8 * st.idx, st.phase);
+                tc_fence_after();
+                {
+                    const uint64_t descB = smem_desc_sw128(sB + st.idx * G2_STAGE_BYTES);
+                    if (elect_one()) {
+                        for (int k = 0; k < ksteps; ++k) {
+                            const uint64_t o = (uint64_t)((k >> 2) * (GM_CHUNK_BYTES >> 4) + (k & 3) * 2);
+                            umma2_f16(d_tmem, descA_hi + o, descB + o, idesc, k > 0);
+                        }
+                        for (int k = 0; k < ksteps; ++k) {
+                            const uint64_t o = (uint64_t)((k >> 2) * (GM_CHUNK_BYTES >> 4) + (k & 3) * 2);
+                            umma2_f16(d_tmem, descA_lo + o, descB + o, idesc, 1);
+                        }
+                        tc_commit2(empty_b + 8 * st.idx);
                     }
-                    tc_commit2(empty_b + 8 * st.idx);
-                    st.advance(G2_STAGES);
-                    mbar_wait(full_b + 8 * st.idx, st.phase);
-                    mbar_wait_cluster(peer_full + 8 * st.idx, st.phase);
-                    tc_fence_after();
-                    {
-                        const uint32_t bB = sB + st.idx * G2_STAGE_BYTES;
-                        for (int k = 0; k < ksteps; ++k)
-                            umma2_f16(d_tmem, smem_desc_sw128(sA + (k >> 2) * GM_CHUNK_BYTES + (k & 3) * 32),
-                                      smem_desc_sw128(bB + (k >> 2) * GM_CHUNK_BYTES + (k & 3) * 32), idesc, 1);
-                    }
-                    tc_commit2(empty_b + 8 * st.idx);
-                    st.advance(G2_STAGES);
-                    tc_commit2(tmem_full + 8 * acc.idx);
-                    const bool last_of_m = (tile + 1 == t_end) || ((tile + 1) / n_rtiles != m);
-                    if (last_of_m) tc_commit2(a_empty);
-                    acc.advance(2);
+                    __syncwarp();
                 }
-            } else {
-                // -------------------------------------------- peer: forward "landed" to the leader
-                const uint32_t r_peer_full = mapa_shared(peer_full, 0), r_peer_a = mapa_shared(peer_a_full, 0);
-                Ring st; uint32_t af_phase = 0; long long cur_m = -1;
-                for (long long tile = t_begin; tile < t_end; ++tile) {
-                    const long long m = tile / n_rtiles;
-                    if (m != cur_m) { mbar_wait(a_full, af_phase); af_phase ^= 1; mbar_arrive_remote(r_peer_a); cur_m = m; }
-                    for (int part = 0; part < 2; ++part) {
-                        mbar_wait(full_b + 8 * st.idx, st.phase);
-                        mbar_arrive_remote(r_peer_full + 8 * st.idx);
-                        st.advance(G2_STAGES);
+                st.advance(G2_STAGES);
+                mbar_wait(full_b + 8 * st.idx, st.phase);
+                mbar_wait_cluster(peer_full + 8 * st.idx, st.phase);
+                tc_fence_after();
+                const bool last_of_m = (tile + 1 == t_end) || ((tile + 1) / n_rtiles != m);
+                {
+                    const uint64_t descB = smem_desc_sw128(sB + st.idx * G2_STAGE_BYTES);
+                    if (elect_one()) {
+                        for (int k = 0; k < ksteps; ++k) {
+                            const uint64_t o = (uint64_t)((k >> 2) * (GM_CHUNK_BYTES >> 4) + (k & 3) * 2);
+                            umma2_f16(d_tmem, descA_hi + o, descB + o, idesc, 1);
+                        }
+                        tc_commit2(empty_b + 8 * st.idx);
+                        tc_commit2(tmem_full + 8 * acc.idx);
+                        if (last_of_m) tc_commit2(a_empty);
                     }
+                    __syncwarp();
+                }
+                st.advance(G2_STAGES);
+                acc.advance(2);
+            }
+        } else {
+            // -------------------------------------------- peer: forward "landed" to the leader
+            const uint32_t r_peer_full = mapa_shared(peer_full, 0), r_peer_a = mapa_shared(peer_a_full, 0);
+            Ring st; uint32_t af_phase = 0; long long cur_m = -1;
+            for (long long tile = t_begin; tile < t_end; ++tile) {
+                const long long m = tile / n_rtiles;
+                if (m != cur_m) {
+                    mbar_wait(a_full, af_phase); af_phase ^= 1;
+                    if (elect_one()) mbar_arrive_remote(r_peer_a);
+                    __syncwarp();
+                    cur_m = m;
+                }
+                for (int part = 0; part < 2; ++part) {
+                    mbar_wait(full_b + 8 * st.idx, st.phase);
+                    if (elect_one()) mbar_arrive_remote(r_peer_full + 8 * st.idx);
+                    __syncwarp();
+                    st.advance(G2_STAGES);
                 }
             }
         }
@@ -718,6 +752,170 @@ gm_umma2_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bi
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------ multicast-pair kernel
+// The single-CTA kernel streams 128 KB of reference operand per 128x256 tile, and with 148 CTAs that
+// makes it L2->SM bandwidth bound (~4200 cycles/tile against an MMA floor of 2688).  Here two CTAs of a
+// cluster work on neighbouring query tiles (2*mp, 2*mp+1) and sweep the SAME reference tiles: each CTA
+// fetches one half (128 rows) of every B stage and multicasts it into both CTAs' shared memory
+// (cp.async.bulk ... .multicast::cluster), halving the L2 reads.  MMAs stay cta_group::1; the only
+// cross-CTA signalling is the stage-free barrier, which collects one tcgen05.commit from each CTA
+// (multicast commit), because a stage is rewritten in both CTAs at once.
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar) {   // arrive on `bar` in both CTAs of the cluster
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
+gm_umma_mc_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg, const float* __restrict__ ysn,
+                  const int* __restrict__ tile_obj, const GmCtrl* __restrict__ ctrl, int* __restrict__ best,
+                  int n_mpairs, int N, int ksteps) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    const uint32_t sA = base;
+    const uint32_t sB = base + GM_SMEM_A;
+    const uint32_t bars = base + GM_SMEM_BAR;
+    const uint32_t full_b = bars + 0;          // [GM_STAGES] 1 arrival + 32 KB (16 KB own copy + 16 KB from the peer)
+    const uint32_t empty_b = bars + 32;        // [GM_STAGES] 2 arrivals: this CTA's and the peer's MMA commits
+    const uint32_t a_full = bars + 64;
+    const uint32_t a_empty = bars + 72;
+    const uint32_t tmem_full = bars + 80;      // [2]
+    const uint32_t tmem_empty = bars + 96;     // [2]
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + GM_SMEM_BAR + 112);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int n_rtiles = ctrl->n_rtiles;
+    const long long total = (long long)n_mpairs * n_rtiles;
+    const int n_clusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
+    const long long t_begin = total * cid / n_clusters;
+    const long long t_end = total * (cid + 1) / n_clusters;
+    const int nkb = ksteps > 4 ? 2 : 1;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < GM_STAGES; ++i) { mbar_init(full_b + 8 * i, 1); mbar_init(empty_b + 8 * i, 2); }
+            mbar_init(a_full, 1); mbar_init(a_empty, 1);
+            for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, GM_EPI_WARPS); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                         // both CTAs' barriers exist before any multicast lands
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------ producer: own A tile, one half of every B stage (multicast)
+        Ring st; uint32_t ae_phase = 0; long long cur_m = -1;
+        for (long long tile = t_begin; tile < t_end; ++tile) {
+            const long long mp = tile / n_rtiles; const long long rt = tile % n_rtiles;
+            if (mp != cur_m) {
+                mbar_wait(a_empty, ae_phase ^ 1); ae_phase ^= 1;
+                if (elect_one()) {
+                    mbar_expect_tx(a_full, GM_UNIT_BYTES);
+                    bulk_g2s(sA, Aimg + (size_t)(2 * mp + rank) * GM_UNIT_BYTES, GM_UNIT_BYTES, a_full);
+                }
+                __syncwarp();
+                cur_m = mp;
+            }
+            for (int part = 0; part < 2; ++part) {
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait_cluster(empty_b + 8 * st.idx, st.phase ^ 1);      // free in BOTH CTAs
+                    const uint32_t fb = full_b + 8 * st.idx;
+                    if (elect_one()) {
+                        mbar_expect_tx(fb, GM_STAGE_BYTES);
+                        bulk_g2s_mc(sB + st.idx * GM_STAGE_BYTES + rank * GM_CHUNK_BYTES,
+                                    Bimg + ((size_t)(2 * rt + rank) * 4 + part * 2 + kb) * GM_CHUNK_BYTES,
+                                    GM_CHUNK_BYTES, fb, (uint16_t)3);
+                    }
+                    __syncwarp();
+                    st.advance(GM_STAGES);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer (cta_group::1, own query tile)
+        constexpr uint32_t idesc = idesc_f16(GM_BM, GM_BN);
+        const uint64_t descA_hi = smem_desc_sw128(sA), descA_lo = smem_desc_sw128(sA + 2 * GM_CHUNK_BYTES);
+        Ring st, acc; uint32_t af_phase = 0; long long cur_m = -1;
+        for (long long tile = t_begin; tile < t_end; ++tile) {
+            const long long mp = tile / n_rtiles;
+            if (mp != cur_m) { mbar_wait(a_full, af_phase); af_phase ^= 1; cur_m = mp; }
+            mbar_wait(tmem_empty + 8 * acc.idx, acc.phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc.idx * GM_BN;
+            for (int part = 0; part < 2; ++part) {
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait_cluster(full_b + 8 * st.idx, st.phase);
+                    tc_fence_after();
+                    const uint64_t descB = smem_desc_sw128(sB + st.idx * GM_STAGE_BYTES);
+                    const uint64_t dA = descA_hi + (uint64_t)(kb * (GM_CHUNK_BYTES >> 4));
+                    const uint64_t dAl = descA_lo + (uint64_t)(kb * (GM_CHUNK_BYTES >> 4));
+                    const int k_end = min(ksteps - 4 * kb, 4);
+                    if (elect_one()) {
+                        for (int k = 0; k < k_end; ++k)
+                            umma_f16(d_tmem, dA + 2 * k, descB + 2 * k, idesc, (part | kb | k) ? 1u : 0u);
+                        if (part == 0)
+                            for (int k = 0; k < k_end; ++k)
+                                umma_f16(d_tmem, dAl + 2 * k, descB + 2 * k, idesc, 1u);
+                        tc_commit_mc(empty_b + 8 * st.idx);
+                    }
+                    __syncwarp();
+                    st.advance(GM_STAGES);
+                }
+            }
+            const bool last_of_m = (tile + 1 == t_end) || ((tile + 1) / n_rtiles != mp);
+            if (elect_one()) {
+                tc_commit(tmem_full + 8 * acc.idx);
+                if (last_of_m) tc_commit(a_empty);
+            }
+            __syncwarp();
+            acc.advance(2);
+        }
+    } else {
+        // ------------------------------------------------ epilogue (warps 2..9), identical to the single-CTA kernel
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = quarter * 32 + lane;
+        Ring acc; long long cur_m = -1; int cur_obj = -1; RowMax run; rowmax_reset(run);
+        for (long long tile = t_begin; tile < t_end; ++tile) {
+            const long long mp = tile / n_rtiles; const long long rt = tile % n_rtiles;
+            const int obj = __ldg(tile_obj + rt);
+            if (mp != cur_m || obj != cur_obj) {
+                if (cur_m >= 0) atomicMax(best + ((size_t)(2 * cur_m + rank) * GM_BM + row) * N + cur_obj, float_to_key(rowmax_value(run)));
+                rowmax_reset(run); cur_m = mp; cur_obj = obj;
+            }
+            mbar_wait(tmem_full + 8 * acc.idx, acc.phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * GM_BN + half * (GM_BN / 2);
+            epilogue_half_tile(taddr, reinterpret_cast<const float4*>(ysn + (size_t)rt * GM_BN + half * (GM_BN / 2)), run);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + 8 * acc.idx);
+            acc.advance(2);
+        }
+        if (cur_m >= 0) atomicMax(best + ((size_t)(2 * cur_m + rank) * GM_BM + row) * N + cur_obj, float_to_key(rowmax_value(run)));
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                         // the peer may still multicast into / commit onto this CTA
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
@@ -794,20 +992,21 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
     gm_convert_kernel<<<nb_ref + nb_q + N, 256, 0, stream>>>(ref, rps, rcs, R, labels, query, qps, qcs, M, p.M_pad, C, N,
                                                              nb_ref, nb_q, ctrl, Aimg, Bimg, xs, ysn, tile_obj);
     static int sm_count = 0;
-    static int use_pair = 0;
+    static int variant = 2;       // 0: single CTA, 1: multicast pair, 2: cta_group::2 pair (default)
     if (sm_count == 0) {
         int dev = 0; cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
         cudaFuncSetAttribute(gm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_TOTAL);
+        cudaFuncSetAttribute(gm_umma_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_TOTAL);
         cudaFuncSetAttribute(gm_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_TOTAL);
-        // The CTA-pair (cta_group::2) kernel is functionally identical; on B200 it measured 7 % slower
-        // than the single-CTA kernel at 480p (profiles/r01 notes), so it is opt-in.
-        const char* e1 = getenv("MANET_GM_CTA_PAIR");
-        use_pair = (e1 && e1[0] == '1');
+        const char* e1 = getenv("MANET_GM_VARIANT");               // A/B switch for profiling
+        if (e1 && e1[0] >= '0' && e1[0] <= '2') variant = e1[0] - '0';
     }
     const int ksteps = (C + 15) / 16;
     profile_begin(PROF_GLOBAL_UMMA, stream);
-    if (use_pair)
+    if (variant == 1)
+        gm_umma_mc_kernel<<<sm_count & ~1, GM_THREADS, GM_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles / 2, N, ksteps);
+    else if (variant == 2)
         gm_umma2_kernel<<<sm_count & ~1, GM_THREADS, G2_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles / 2, N, ksteps);
     else
         gm_umma_kernel<<<sm_count, GM_THREADS, GM_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles, N, ksteps);
