@@ -39,8 +39,8 @@ M_PIX = H * W
 WORKLOAD = "global+local matching + map-memory update, 480p emb 100x120x214, 5 objects (N=6), max_distance=12, k=1"
 ALGO_FLOP_GLOBAL = 2.0 * M_PIX * M_PIX * C                      # 2*M*R*C, SURVEY.md section 8d
 ALGO_BYTES_LOCAL = 4.0 * (2 * C * H * W + H * W + H * W * N_IDS)
-# executed tensor-core work: 3 fp16 products x K padded 100->112 x M padded to 256 x R padded per 256-row bucket
-EXEC_FLOP_GLOBAL = 3 * 2.0 * (101 * 256) * 112 * (103 * 256)
+# executed tensor-core work: M padded to 256, R padded per 256-row bucket, K steps of 16 (see gm_fold_remainder)
+EXEC_FLOP_GLOBAL = 2.0 * (101 * 256) * (103 * 256) * 16 * 19   # 19 K=16 MMA steps per tile (7 + 6 + 6, remainder folded)
 KERNELS_PER_STEP = 8   # scan, convert, umma, finalize | pool(+label pad), window, upsample-mask-min | local-map store/select
 
 

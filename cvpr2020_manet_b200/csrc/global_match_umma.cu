@@ -52,6 +52,7 @@ struct GmCtrl {
     int offsets[GM_MAXN + 1];      // first row of each (256-padded) bucket
     int n_rtiles;                  // number of 256-row reference tiles
     float scale_q, scale_r;        // power-of-two operand scales
+    int bias_fold;                 // 1: -s/2*|r|^2 travels through the GEMM (gm_bias_plan), epilogue is a bare max
 };
 
 // ------------------------------------------------------------------------------------ PTX
@@ -146,6 +147,8 @@ __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[32]) {
 // pipelined (chunk c+1 is in flight while chunk c is reduced) and four independent maxima break the
 // FMNMX dependency chain.
 struct RowMax { float a, b, c, d; };
+// BIAS_IN_ACC: the accumulator already contains the bias (gm_bias_plan) -> bare max, no loads.
+template <bool BIAS_IN_ACC>
 __device__ __forceinline__ void epilogue_half_tile(uint32_t taddr, const float4* __restrict__ yv, RowMax& m) {
     constexpr int NCH = GM_BN / 2 / 32;      // 4 chunks of 32 columns
     uint32_t r[2][32];
@@ -153,17 +156,29 @@ __device__ __forceinline__ void epilogue_half_tile(uint32_t taddr, const float4*
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
         float4 y[8];
+        if (!BIAS_IN_ACC) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = __ldg(yv + ch * 8 + i);
+            for (int i = 0; i < 8; ++i) y[i] = __ldg(yv + ch * 8 + i);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         tmem_ld_wait_dep(r[ch & 1]);
         if (ch + 1 < NCH) tmem_ld32(taddr + (ch + 1) * 32, r[(ch + 1) & 1]);
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {
             const uint32_t* q = r[ch & 1] + 4 * i;
-            m.a = fmaxf(fmaxf(m.a, __uint_as_float(q[0]) + y[i].x), __uint_as_float(q[4]) + y[i + 1].x);
-            m.b = fmaxf(fmaxf(m.b, __uint_as_float(q[1]) + y[i].y), __uint_as_float(q[5]) + y[i + 1].y);
-            m.c = fmaxf(fmaxf(m.c, __uint_as_float(q[2]) + y[i].z), __uint_as_float(q[6]) + y[i + 1].z);
-            m.d = fmaxf(fmaxf(m.d, __uint_as_float(q[3]) + y[i].w), __uint_as_float(q[7]) + y[i + 1].w);
+            if (BIAS_IN_ACC) {
+                m.a = fmaxf(fmaxf(m.a, __uint_as_float(q[0])), __uint_as_float(q[4]));
+                m.b = fmaxf(fmaxf(m.b, __uint_as_float(q[1])), __uint_as_float(q[5]));
+                m.c = fmaxf(fmaxf(m.c, __uint_as_float(q[2])), __uint_as_float(q[6]));
+                m.d = fmaxf(fmaxf(m.d, __uint_as_float(q[3])), __uint_as_float(q[7]));
+            } else {
+                m.a = fmaxf(fmaxf(m.a, __uint_as_float(q[0]) + y[i].x), __uint_as_float(q[4]) + y[i + 1].x);
+                m.b = fmaxf(fmaxf(m.b, __uint_as_float(q[1]) + y[i].y), __uint_as_float(q[5]) + y[i + 1].y);
+                m.c = fmaxf(fmaxf(m.c, __uint_as_float(q[2]) + y[i].z), __uint_as_float(q[6]) + y[i + 1].z);
+                m.d = fmaxf(fmaxf(m.d, __uint_as_float(q[3]) + y[i].w), __uint_as_float(q[7]) + y[i + 1].w);
+            }
         }
     }
 }
@@ -186,6 +201,34 @@ __device__ __forceinline__ size_t image_chunk_offset(int64_t pos, int part, int 
     int kb = j >> 3, ch = j & 7;
     return (size_t)unit * GM_UNIT_BYTES + (size_t)part * (2 * GM_CHUNK_BYTES) + (size_t)kb * GM_CHUNK_BYTES +
            (size_t)(row >> 3) * 1024 + (size_t)(row & 7) * 128 + (size_t)((ch ^ (row & 7)) << 4);
+}
+
+// K = C is padded to a multiple of 16 (one kind::f16 MMA step).  When only 1..5 channels spill into the
+// last step, the three products' remainders (3 x (C%16) <= 15 columns) are packed into that single step
+// of the hi image, and the ql.rh / qh.rl products run one step fewer: 3*ceil(C/16) - 2 MMAs per tile
+// instead of 3*ceil(C/16)  (C = 100: 19 instead of 21, -9.5 % tensor work).
+__host__ __device__ inline bool gm_fold_remainder(int C) { return (C % 16) >= 1 && (C % 16) <= 5 && C > 16; }
+
+// Bias fold.  The epilogue needs t = s*(q.r) - s/2*|r|^2.  When the folded remainder step has four spare
+// columns (C%16 <= 4) the bias is fed through the tensor core as well: the reference row carries
+// -s/2*|r|^2 split into three fp16 pieces v1,v2,v3 (33 bits) and the query row the matching power-of-two
+// weights c1,c2,c3, so sum(c_j*v_j) reproduces the fp32 bias to 2^-33.  The fourth column pair (c4 = 2^15,
+// v4 = -65504 on padding rows only) pushes bucket-padding columns below any real value.  Removing the
+// per-element FADD and the bias loads makes the epilogue (the limiter, see profiles/) ~3x cheaper.
+// eb = exponent bound of |bias| <= 0.5*C*s*amax_r^2; the weights stay normal fp16 for 23 <= eb <= 30.
+struct GmBiasPlan { bool on; float c1, c2, c3, c4; };
+__device__ __forceinline__ GmBiasPlan gm_bias_plan(int C, float s_q, float s_r, unsigned absmax_r_bits) {
+    GmBiasPlan p; p.on = false; p.c1 = p.c2 = p.c3 = p.c4 = 1.f;
+    if (!gm_fold_remainder(C) || (C % 16) > 4) return p;
+    const float amax = __uint_as_float(absmax_r_bits);
+    const float bound = 0.5f * (float)C * (s_q * s_r) * amax * amax * 1.01f;
+    if (!isfinite(bound)) return p;
+    int eb = (bound > 0.f) ? ilogbf(bound) + 1 : 23;
+    eb = max(eb, 23);
+    if (eb > 30) return p;
+    p.on = true;
+    p.c1 = ldexpf(1.0f, eb - 15); p.c2 = ldexpf(1.0f, eb - 26); p.c3 = ldexpf(1.0f, eb - 37); p.c4 = 32768.0f;
+    return p;
 }
 
 // pass 1: label histogram, per-tensor |x| max, best[] = -inf keys.
@@ -286,10 +329,14 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
     const float s_q = pow2_scale(ctrl->absmax_bits[1]);
     const float s_r = pow2_scale(ctrl->absmax_bits[0]);
     const int nchunks = ((C + 15) / 16) * 2;
+    const int rem = max(C % 16, 1);
+    const bool fold = gm_fold_remainder(C);
+    const int j_fold = nchunks - 2;                        // first 16-byte chunk of the last k-step
+    const GmBiasPlan bias = gm_bias_plan(C, s_q, s_r, ctrl->absmax_bits[0]);
     const int b = blockIdx.x;
     if (b == 0) {
         if (t <= N) ctrl->offsets[t] = off[t];
-        if (t == 0) { ctrl->n_rtiles = off[N] / GM_BN; ctrl->scale_q = s_q; ctrl->scale_r = s_r; }
+        if (t == 0) { ctrl->n_rtiles = off[N] / GM_BN; ctrl->scale_q = s_q; ctrl->scale_r = s_r; ctrl->bias_fold = bias.on ? 1 : 0; }
         for (int o = 0; o < N; ++o)
             for (int tl = off[o] / GM_BN + t; tl < off[o + 1] / GM_BN; tl += 256) tile_obj[tl] = o;
     }
@@ -304,6 +351,10 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
                 *reinterpret_cast<uint4*>(Bimg + image_chunk_offset(pos, 1, j)) = z;
             }
             ysn[pos] = -INFINITY;
+            if (bias.on) {                                  // columns 12..15 of the folded step: v1..v4
+                __half v[4] = {__float2half_rn(-65504.f), __float2half_rn(0.f), __float2half_rn(0.f), __float2half_rn(-65504.f)};
+                *reinterpret_cast<uint2*>(Bimg + image_chunk_offset(pos, 0, j_fold + 1) + 8) = *reinterpret_cast<uint2*>(v);
+            }
         }
         return;
     }
@@ -353,7 +404,27 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
             const int64_t pos = pos_s[row];
             if (pos >= 0 && j < nchunks) {
                 uint4 hi, lo;
-                split8(v, scale, hi, lo);
+                if (fold && j >= j_fold) {
+                    // Folded remainder K step (see gm_fold_remainder): the last C%16 <= 5 channels of all three
+                    // products share ONE k-step of the hi image:  queries [qh | ql | qh | 0], references
+                    // [rh | rh | rl | 0]  ->  qh.rh + ql.rh + qh.rl for those channels in a single MMA.
+                    __half comb[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int p16 = (j - j_fold) * 8 + k;          // position within the 16-wide k-step
+                        const int g = p16 / rem, i = p16 - g * rem;    // group 0..2 (>=3: zero padding), channel i
+                        float x = 0.f;
+                        if (g < 3) x = tile[(C - rem) - kb * 64 + i][row] * scale;
+                        const __half h = __float2half_rn(x);
+                        const __half l = __float2half_rn(x - __half2float(h));
+                        const bool want_lo = is_ref ? (g == 2) : (g == 1);
+                        comb[k] = (g < 3) ? (want_lo ? l : h) : __float2half_rn(0.f);
+                    }
+                    hi = *reinterpret_cast<uint4*>(comb);
+                    lo = make_uint4(0, 0, 0, 0);
+                } else {
+                    split8(v, scale, hi, lo);
+                }
                 *reinterpret_cast<uint4*>(img + image_chunk_offset(pos, 0, j)) = hi;
                 *reinterpret_cast<uint4*>(img + image_chunk_offset(pos, 1, j)) = lo;
             }
@@ -362,8 +433,24 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
     }
     __syncthreads();
     if (t < GM_CV_PIX && pos_s[t] >= 0) {
-        if (is_ref) ysn[pos_s[t]] = -0.5f * (s_q * s_r) * rowsq[t];
-        else xs[pos_s[t]] = rowsq[t];
+        const int64_t pos = pos_s[t];
+        __half v[4];
+        if (is_ref) {
+            const float bval = -0.5f * (s_q * s_r) * rowsq[t];
+            ysn[pos] = bval;
+            // three-piece fp16 split of the bias against the weights c1 > c2 > c3 (each step is exact in fp32)
+            const __half v1 = __float2half_rn(bval / bias.c1);
+            const float r1 = bval - bias.c1 * __half2float(v1);
+            const __half v2 = __float2half_rn(r1 / bias.c2);
+            const float r2 = r1 - bias.c2 * __half2float(v2);
+            v[0] = v1; v[1] = v2; v[2] = __float2half_rn(r2 / bias.c3); v[3] = __float2half_rn(0.f);
+        } else {
+            xs[pos] = rowsq[t];
+            v[0] = __float2half_rn(bias.c1); v[1] = __float2half_rn(bias.c2);
+            v[2] = __float2half_rn(bias.c3); v[3] = __float2half_rn(bias.c4);
+        }
+        if (bias.on)
+            *reinterpret_cast<uint2*>(img + image_chunk_offset(pos, 0, j_fold + 1) + 8) = *reinterpret_cast<uint2*>(v);
     }
 }
 
@@ -377,7 +464,7 @@ struct Ring {
 __global__ void __launch_bounds__(GM_THREADS, 1)
 gm_umma_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg, const float* __restrict__ ysn,
                const int* __restrict__ tile_obj, const GmCtrl* __restrict__ ctrl, int* __restrict__ best,
-               int n_mtiles, int N, int ksteps) {
+               int n_mtiles, int N, int ksteps, int ksteps_lo) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;            // SWIZZLE_128B atoms need 1024-byte alignment
@@ -396,10 +483,12 @@ gm_umma_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bim
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_rtiles = ctrl->n_rtiles;
+    const bool bias_in_acc = ctrl->bias_fold != 0;
     const long long total = (long long)n_mtiles * n_rtiles;
     const long long t_begin = total * blockIdx.x / gridDim.x;
     const long long t_end = total * (blockIdx.x + 1) / gridDim.x;
     const int nkb = ksteps > 4 ? 2 : 1;                     // K blocks of 64 actually used (C <= 64 -> one)
+    const int nkb_lo = ksteps_lo > 4 ? 2 : 1;               // ... by the lo-part products
 
     if (warp == 1) {
         if (lane == 0) {
@@ -432,7 +521,7 @@ gm_umma_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bim
                 cur_m = m;
             }
             for (int part = 0; part < 2; ++part) {
-                for (int kb = 0; kb < nkb; ++kb) {
+                for (int kb = 0; kb < (part ? nkb_lo : nkb); ++kb) {
                     mbar_wait(empty_b + 8 * st.idx, st.phase ^ 1);
                     const uint32_t fb = full_b + 8 * st.idx;
                     const uint32_t dst = sB + st.idx * GM_STAGE_BYTES;
@@ -464,18 +553,21 @@ gm_umma_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bim
             // Descriptors differ only in the start-address field (>>4): +2 per K step of 32 bytes,
             // +(16 KB >> 4) per A k-block.
             for (int part = 0; part < 2; ++part) {
-                for (int kb = 0; kb < nkb; ++kb) {
+                for (int kb = 0; kb < (part ? nkb_lo : nkb); ++kb) {
                     mbar_wait(full_b + 8 * st.idx, st.phase);
                     tc_fence_after();
                     const uint64_t descB = smem_desc_sw128(sB + st.idx * GM_STAGE_BYTES);
                     const uint64_t dA = descA_hi + (uint64_t)(kb * (GM_CHUNK_BYTES >> 4));
                     const uint64_t dAl = descA_lo + (uint64_t)(kb * (GM_CHUNK_BYTES >> 4));
-                    const int k_end = min(ksteps - 4 * kb, 4);
+                    // qh.rh runs over all K steps (its last one may be the folded remainder step);
+                    // ql.rh and qh.rl stop at ksteps_lo
+                    const int k_hh = min((part ? ksteps_lo : ksteps) - 4 * kb, 4);
+                    const int k_lh = min(ksteps_lo - 4 * kb, 4);
                     if (elect_one()) {
-                        for (int k = 0; k < k_end; ++k)
+                        for (int k = 0; k < k_hh; ++k)
                             umma_f16(d_tmem, dA + 2 * k, descB + 2 * k, idesc, (part | kb | k) ? 1u : 0u);
                         if (part == 0)
-                            for (int k = 0; k < k_end; ++k)
+                            for (int k = 0; k < k_lh; ++k)
                                 umma_f16(d_tmem, dAl + 2 * k, descB + 2 * k, idesc, 1u);
                         tc_commit(empty_b + 8 * st.idx);
                     }
@@ -507,7 +599,8 @@ gm_umma_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bim
             mbar_wait(tmem_full + 8 * acc.idx, acc.phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * GM_BN + half * (GM_BN / 2);
-            epilogue_half_tile(taddr, reinterpret_cast<const float4*>(ysn + (size_t)rt * GM_BN + half * (GM_BN / 2)), run);
+            if (bias_in_acc) epilogue_half_tile<true>(taddr, nullptr, run);
+            else epilogue_half_tile<false>(taddr, reinterpret_cast<const float4*>(ysn + (size_t)rt * GM_BN + half * (GM_BN / 2)), run);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty + 8 * acc.idx);
@@ -577,7 +670,10 @@ __device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t adesc, uint6
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
 gm_umma2_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg, const float* __restrict__ ysn,
                 const int* __restrict__ tile_obj, const GmCtrl* __restrict__ ctrl, int* __restrict__ best,
-                int n_mpairs, int N, int ksteps) {
+                int n_mpairs, int N, int ksteps, int ksteps_lo) {
+#ifdef GM_TRACE
+    long long tr_wait_full = 0, tr_epi = 0, tr_mma_wait_acc = 0, tr_mma_wait_b = 0, tr_total = clock64();
+#endif
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -599,6 +695,7 @@ gm_umma2_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bi
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int n_rtiles = ctrl->n_rtiles;
+    const bool bias_in_acc = ctrl->bias_fold != 0;
     const long long total = (long long)n_mpairs * n_rtiles;
     const int n_clusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
     const long long t_begin = total * cid / n_clusters;
@@ -657,13 +754,22 @@ gm_umma2_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bi
             for (long long tile = t_begin; tile < t_end; ++tile) {
                 const long long m = tile / n_rtiles;
                 if (m != cur_m) { mbar_wait(a_full, af_phase); mbar_wait_cluster(peer_a_full, af_phase); af_phase ^= 1; cur_m = m; }
+#ifdef GM_TRACE
+                long long c0 = clock64();
+#endif
                 mbar_wait_cluster(tmem_empty + 8 * acc.idx, acc.phase ^ 1);
                 tc_fence_after();
+#ifdef GM_TRACE
+                long long c1 = clock64(); tr_mma_wait_acc += c1 - c0;
+#endif
                 const uint32_t d_tmem = tmem_base + acc.idx * GM_BN;
                 // k-step k lives in k-block k>>2 (16 KB apart) at byte offset 32*(k&3): descriptor += (k>>2)*1024 + (k&3)*2
                 mbar_wait(full_b + 8 * st.idx, st.phase);
                 mbar_wait_cluster(peer_full + 8 * st.idx, st.phase);
                 tc_fence_after();
+#ifdef GM_TRACE
+                tr_mma_wait_b += clock64() - c1;
+#endif
                 {
                     const uint64_t descB = smem_desc_sw128(sB + st.idx * G2_STAGE_BYTES);
                     if (elect_one()) {
@@ -671,7 +777,7 @@ gm_umma2_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bi
                             const uint64_t o = (uint64_t)((k >> 2) * (GM_CHUNK_BYTES >> 4) + (k & 3) * 2);
                             umma2_f16(d_tmem, descA_hi + o, descB + o, idesc, k > 0);
                         }
-                        for (int k = 0; k < ksteps; ++k) {
+                        for (int k = 0; k < ksteps_lo; ++k) {
                             const uint64_t o = (uint64_t)((k >> 2) * (GM_CHUNK_BYTES >> 4) + (k & 3) * 2);
                             umma2_f16(d_tmem, descA_lo + o, descB + o, idesc, 1);
                         }
@@ -680,14 +786,20 @@ gm_umma2_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bi
                     __syncwarp();
                 }
                 st.advance(G2_STAGES);
+#ifdef GM_TRACE
+                long long c2 = clock64();
+#endif
                 mbar_wait(full_b + 8 * st.idx, st.phase);
                 mbar_wait_cluster(peer_full + 8 * st.idx, st.phase);
                 tc_fence_after();
+#ifdef GM_TRACE
+                tr_mma_wait_b += clock64() - c2;
+#endif
                 const bool last_of_m = (tile + 1 == t_end) || ((tile + 1) / n_rtiles != m);
                 {
                     const uint64_t descB = smem_desc_sw128(sB + st.idx * G2_STAGE_BYTES);
                     if (elect_one()) {
-                        for (int k = 0; k < ksteps; ++k) {
+                        for (int k = 0; k < ksteps_lo; ++k) {
                             const uint64_t o = (uint64_t)((k >> 2) * (GM_CHUNK_BYTES >> 4) + (k & 3) * 2);
                             umma2_f16(d_tmem, descA_hi + o, descB + o, idesc, 1);
                         }
@@ -734,18 +846,33 @@ gm_umma2_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bi
                 if (cur_m >= 0) atomicMax(best + ((size_t)(2 * cur_m + rank) * GM_BM + row) * N + cur_obj, float_to_key(rowmax_value(run)));
                 rowmax_reset(run); cur_m = m; cur_obj = obj;
             }
+#ifdef GM_TRACE
+            long long e0 = clock64();
+#endif
             mbar_wait(tmem_full + 8 * acc.idx, acc.phase);
             tc_fence_after();
+#ifdef GM_TRACE
+            long long e1 = clock64(); tr_wait_full += e1 - e0;
+#endif
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * GM_BN + half * (GM_BN / 2);
-            epilogue_half_tile(taddr, reinterpret_cast<const float4*>(ysn + (size_t)rt * GM_BN + half * (GM_BN / 2)), run);
+            if (bias_in_acc) epilogue_half_tile<true>(taddr, nullptr, run);
+            else epilogue_half_tile<false>(taddr, reinterpret_cast<const float4*>(ysn + (size_t)rt * GM_BN + half * (GM_BN / 2)), run);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(r_tmem_empty + 8 * acc.idx);
+#ifdef GM_TRACE
+            tr_epi += clock64() - e1;
+#endif
             acc.advance(2);
         }
         if (cur_m >= 0) atomicMax(best + ((size_t)(2 * cur_m + rank) * GM_BM + row) * N + cur_obj, float_to_key(rowmax_value(run)));
     }
 
+#ifdef GM_TRACE
+    if ((blockIdx.x == 0 || blockIdx.x == 1 || blockIdx.x == 80) && lane == 0 && (warp == 1 || warp == 2 || warp == 9))
+        printf("cta %d warp %d tiles %lld total %lld | mma: wait_acc %lld wait_b %lld | epi: wait_full %lld work %lld\n", blockIdx.x, warp,
+               t_end - t_begin, clock64() - tr_total, tr_mma_wait_acc, tr_mma_wait_b, tr_wait_full, tr_epi);
+#endif
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                           // nobody leaves while the pair may still touch its smem / TMEM
@@ -775,7 +902,7 @@ __device__ __forceinline__ void tc_commit_mc(uint32_t bar) {   // arrive on `bar
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
 gm_umma_mc_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg, const float* __restrict__ ysn,
                   const int* __restrict__ tile_obj, const GmCtrl* __restrict__ ctrl, int* __restrict__ best,
-                  int n_mpairs, int N, int ksteps) {
+                  int n_mpairs, int N, int ksteps, int ksteps_lo) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -794,11 +921,13 @@ gm_umma_mc_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int n_rtiles = ctrl->n_rtiles;
+    const bool bias_in_acc = ctrl->bias_fold != 0;
     const long long total = (long long)n_mpairs * n_rtiles;
     const int n_clusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
     const long long t_begin = total * cid / n_clusters;
     const long long t_end = total * (cid + 1) / n_clusters;
     const int nkb = ksteps > 4 ? 2 : 1;
+    const int nkb_lo = ksteps_lo > 4 ? 2 : 1;
 
     if (warp == 1) {
         if (lane == 0) {
@@ -832,7 +961,7 @@ gm_umma_mc_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ 
                 cur_m = mp;
             }
             for (int part = 0; part < 2; ++part) {
-                for (int kb = 0; kb < nkb; ++kb) {
+                for (int kb = 0; kb < (part ? nkb_lo : nkb); ++kb) {
                     mbar_wait_cluster(empty_b + 8 * st.idx, st.phase ^ 1);      // free in BOTH CTAs
                     const uint32_t fb = full_b + 8 * st.idx;
                     if (elect_one()) {
@@ -858,18 +987,21 @@ gm_umma_mc_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ 
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc.idx * GM_BN;
             for (int part = 0; part < 2; ++part) {
-                for (int kb = 0; kb < nkb; ++kb) {
+                for (int kb = 0; kb < (part ? nkb_lo : nkb); ++kb) {
                     mbar_wait_cluster(full_b + 8 * st.idx, st.phase);
                     tc_fence_after();
                     const uint64_t descB = smem_desc_sw128(sB + st.idx * GM_STAGE_BYTES);
                     const uint64_t dA = descA_hi + (uint64_t)(kb * (GM_CHUNK_BYTES >> 4));
                     const uint64_t dAl = descA_lo + (uint64_t)(kb * (GM_CHUNK_BYTES >> 4));
-                    const int k_end = min(ksteps - 4 * kb, 4);
+                    // qh.rh runs over all K steps (its last one may be the folded remainder step);
+                    // ql.rh and qh.rl stop at ksteps_lo
+                    const int k_hh = min((part ? ksteps_lo : ksteps) - 4 * kb, 4);
+                    const int k_lh = min(ksteps_lo - 4 * kb, 4);
                     if (elect_one()) {
-                        for (int k = 0; k < k_end; ++k)
+                        for (int k = 0; k < k_hh; ++k)
                             umma_f16(d_tmem, dA + 2 * k, descB + 2 * k, idesc, (part | kb | k) ? 1u : 0u);
                         if (part == 0)
-                            for (int k = 0; k < k_end; ++k)
+                            for (int k = 0; k < k_lh; ++k)
                                 umma_f16(d_tmem, dAl + 2 * k, descB + 2 * k, idesc, 1u);
                         tc_commit_mc(empty_b + 8 * st.idx);
                     }
@@ -901,7 +1033,8 @@ gm_umma_mc_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ 
             mbar_wait(tmem_full + 8 * acc.idx, acc.phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * GM_BN + half * (GM_BN / 2);
-            epilogue_half_tile(taddr, reinterpret_cast<const float4*>(ysn + (size_t)rt * GM_BN + half * (GM_BN / 2)), run);
+            if (bias_in_acc) epilogue_half_tile<true>(taddr, nullptr, run);
+            else epilogue_half_tile<false>(taddr, reinterpret_cast<const float4*>(ysn + (size_t)rt * GM_BN + half * (GM_BN / 2)), run);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty + 8 * acc.idx);
@@ -1003,13 +1136,14 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
         if (e1 && e1[0] >= '0' && e1[0] <= '2') variant = e1[0] - '0';
     }
     const int ksteps = (C + 15) / 16;
+    const int ksteps_lo = gm_fold_remainder(C) ? ksteps - 1 : ksteps;
     profile_begin(PROF_GLOBAL_UMMA, stream);
     if (variant == 1)
-        gm_umma_mc_kernel<<<sm_count & ~1, GM_THREADS, GM_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles / 2, N, ksteps);
+        gm_umma_mc_kernel<<<sm_count & ~1, GM_THREADS, GM_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles / 2, N, ksteps, ksteps_lo);
     else if (variant == 2)
-        gm_umma2_kernel<<<sm_count & ~1, GM_THREADS, G2_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles / 2, N, ksteps);
+        gm_umma2_kernel<<<sm_count & ~1, GM_THREADS, G2_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles / 2, N, ksteps, ksteps_lo);
     else
-        gm_umma_kernel<<<sm_count, GM_THREADS, GM_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles, N, ksteps);
+        gm_umma_kernel<<<sm_count, GM_THREADS, GM_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles, N, ksteps, ksteps_lo);
     profile_end(PROF_GLOBAL_UMMA, stream);
     gm_finalize_kernel<<<(unsigned)ceil_div64(M * N, 256), 256, 0, stream>>>(best, xs, ctrl, M, N, normalize, mem_frame, out);
     return check_launch("global match (tcgen05) kernels");
