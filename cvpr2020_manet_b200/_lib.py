@@ -17,6 +17,7 @@ HEADER_PATH = os.path.join(os.path.dirname(PKG_DIR), "include", "manet_b200.h")
 GM_NORMALIZE = 1
 GM_DROP_UNLAB = 2
 GM_ENGINE_SIMT = 4
+STEP_SERIAL = 16
 DT_F32, DT_F16, DT_F64 = 0, 1, 2
 
 _I64, _I, _P, _SZ, _F = c_int64, c_int, c_void_p, c_size_t, c_float

@@ -277,8 +277,10 @@ struct SessionSlot {
 
 struct manet_session {
     int H, W, C, N, d, n_frames;
-    cudaStream_t stream;          // compute (+ device->host) stream
+    cudaStream_t stream;          // compute (+ device->host) stream: global-matching branch, joins
+    cudaStream_t local_stream;    // local-matching branch (independent of the global branch until the join)
     cudaStream_t copy_stream;     // host->device stream
+    cudaEvent_t ev_fork, ev_join;
     SessionSlot slot[2];
     int32_t* d_ids;
     float* d_gmem;        // [n_frames, H*W*N]   global-map memory, ones
@@ -300,7 +302,10 @@ manet_session_t* manet_session_create(int H, int W, int C, int N, int max_distan
     s->H = H; s->W = W; s->C = C; s->N = N; s->d = max_distance; s->n_frames = n_frames;
     const size_t px = (size_t)H * W, emb = px * C * sizeof(float), map = px * N * sizeof(float);
     bool ok = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+              cudaStreamCreateWithFlags(&s->local_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i) {
         SessionSlot& t = s->slot[i];
         ok = ok && cudaMallocHost(&t.h_ref, emb) == cudaSuccess && cudaMallocHost(&t.h_prev, emb) == cudaSuccess &&
@@ -349,7 +354,10 @@ void manet_session_destroy(manet_session_t* s) {
     }
     cudaFree(s->d_ids); cudaFree(s->d_gmem); cudaFree(s->d_lmem); cudaFree(s->d_ldist); cudaFree(s->ws_g); cudaFree(s->ws_l);
     if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->local_stream) cudaStreamDestroy(s->local_stream);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
     delete s;
 }
 
@@ -391,17 +399,35 @@ static int session_step_slot(manet_session_t* s, int slot, int frame, int intera
     MANET_REQUIRE(frame != start_annotated_frame, "session: propagation never visits the annotated frame (1/|f-f0|, IntVOS.py:648)");
     SessionSlot& t = s->slot[slot];
     const int64_t px = (int64_t)s->H * s->W, n = px * s->N;
-    int rc = manet_global_match(t.d_ref, 1, px, px, t.d_ref_lab, t.d_cur, 1, px, px, s->C, s->N, 1,
-                                flags | MANET_GM_NORMALIZE, s->d_gmem + (size_t)frame * n, t.d_out_g, s->ws_g, s->ws_g_bytes,
-                                s->stream);
-    if (rc) return rc;
-    rc = manet_local_match(t.d_prev, s->W, 1, px, t.d_cur, s->W, 1, px, t.d_prev_lab, s->d_ids, s->H, s->W, s->C, s->N,
-                           s->d, t.d_raw_l, s->ws_l, s->ws_l_bytes, s->stream);
+    // The two branches share no data until the caller reads both maps: fork the local branch onto its
+    // own stream so its small kernels can fill the machine around the (tensor-bound) global-matching GEMM.
+    const bool fork = !(flags & MANET_STEP_SERIAL);
+    cudaStream_t ls = fork ? s->local_stream : s->stream;
+    const uint32_t gm_flags = (flags & ~MANET_STEP_SERIAL) | MANET_GM_NORMALIZE;
+    if (fork) {
+        cudaEventRecord(s->ev_fork, s->stream);
+        cudaStreamWaitEvent(s->local_stream, s->ev_fork, 0);
+    } else {
+        int rc0 = manet_global_match(t.d_ref, 1, px, px, t.d_ref_lab, t.d_cur, 1, px, px, s->C, s->N, 1, gm_flags,
+                                     s->d_gmem + (size_t)frame * n, t.d_out_g, s->ws_g, s->ws_g_bytes, s->stream);
+        if (rc0) return rc0;
+    }
+    int rc = manet_local_match(t.d_prev, s->W, 1, px, t.d_cur, s->W, 1, px, t.d_prev_lab, s->d_ids, s->H, s->W, s->C, s->N,
+                               s->d, t.d_raw_l, s->ws_l, s->ws_l_bytes, ls);
     if (rc) return rc;
     int df = frame - start_annotated_frame; if (df < 0) df = -df;
-    return manet_local_map_store_select(t.d_raw_l, s->d_lmem + (size_t)frame * kMemoryRounds * n,
-                                        s->d_ldist + (size_t)frame * kMemoryRounds, interaction_num,
-                                        (float)(1.0 / (double)df), t.d_out_l, n, s->stream);
+    rc = manet_local_map_store_select(t.d_raw_l, s->d_lmem + (size_t)frame * kMemoryRounds * n,
+                                      s->d_ldist + (size_t)frame * kMemoryRounds, interaction_num,
+                                      (float)(1.0 / (double)df), t.d_out_l, n, ls);
+    if (rc) return rc;
+    if (fork) {
+        cudaEventRecord(s->ev_join, s->local_stream);
+        rc = manet_global_match(t.d_ref, 1, px, px, t.d_ref_lab, t.d_cur, 1, px, px, s->C, s->N, 1, gm_flags,
+                                s->d_gmem + (size_t)frame * n, t.d_out_g, s->ws_g, s->ws_g_bytes, s->stream);
+        if (rc) return rc;
+        cudaStreamWaitEvent(s->stream, s->ev_join, 0);
+    }
+    return check_launch("session step");
 }
 
 int manet_session_step_device(manet_session_t* s, int frame, int interaction_num, int start_annotated_frame,

@@ -117,8 +117,8 @@ class MatchingSession:
     def upload(self):
         check(self._lib.manet_session_upload(self._h), "manet_session_upload")
 
-    def step_device(self, frame, interaction_num=1, start_annotated_frame=0, drop_unlabelled=True):
-        flags = _lib.GM_DROP_UNLAB if drop_unlabelled else 0
+    def step_device(self, frame, interaction_num=1, start_annotated_frame=0, drop_unlabelled=True, serial=False):
+        flags = (_lib.GM_DROP_UNLAB if drop_unlabelled else 0) | (_lib.STEP_SERIAL if serial else 0)
         check(self._lib.manet_session_step_device(self._h, frame, interaction_num, start_annotated_frame, flags),
               "manet_session_step_device")
 

@@ -41,6 +41,9 @@ typedef void* manet_stream_t; /* a cudaStream_t */
 #define MANET_GM_NORMALIZE   1u /* apply (sigmoid(x)-0.5)*2 to the result (IntVOS.py:611-612) */
 #define MANET_GM_DROP_UNLAB  2u /* drop reference pixels labelled -1 first (cfg.TEST_MODE, IntVOS.py:135-136) */
 #define MANET_GM_ENGINE_SIMT 4u /* force the fp32 CUDA-core kernel instead of the tcgen05 kernel */
+/* session-step flag: run the local-matching branch on the same stream as the global branch (the
+ * default forks it onto a second stream so its kernels overlap the pre/post passes of the GEMM) */
+#define MANET_STEP_SERIAL    16u
 
 /* dtype codes for the Correlation op (AT_DISPATCH_FLOATING_TYPES_AND_HALF, correlation_cuda_kernel.cu:386) */
 #define MANET_DT_F32 0
