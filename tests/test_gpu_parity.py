@@ -383,3 +383,109 @@ def test_correlation_cuda_module_contract_and_manet_usage(api):
     cc = api.cross_correlate(x[0].permute(1, 2, 0), y[0].permute(1, 2, 0), max_distance=d)
     assert tuple(cc.shape) == (H, W, (2 * d + 1) ** 2)
     assert float((cc.permute(2, 0, 1) - out[0] * C).abs().max()) <= 1e-4
+
+
+# ------------------------------------------------------------------ engine edge cases
+@pytest.mark.parametrize("C", [1, 7, 16, 17, 20, 21, 33, 64, 65, 69, 100, 112, 113, 128, 130])
+def test_global_tcgen05_channel_counts(api, C):
+    """Every K layout of the tensor-core engine against the fp32 CUDA-core engine: C%16 == 0 (no remainder),
+    1..4 (remainder + bias folded into one MMA step), 5 (remainder folded, bias in the epilogue), 6..15 (plain
+    padding), one k-block (C <= 64) and two, and C > 128 (routed to the CUDA-core engine)."""
+    gen = torch.Generator().manual_seed(C)
+    H, W, Hr, N = 19, 23, 31, 5
+    ref = (torch.randn(C, Hr, W, generator=gen) * 0.7).cuda().permute(1, 2, 0)
+    qry = (torch.randn(C, H, W, generator=gen) * 0.7).cuda().permute(1, 2, 0)
+    lab = torch.randint(-1, N, (Hr, W, 1), generator=gen).int().cuda()
+    lab[lab == 3] = 1
+    api.FORCE_SIMT_ENGINE = True
+    try:
+        want, _ = api.nearest_neighbor_features_per_object(ref, qry, lab, 1, torch.tensor(N - 1))
+    finally:
+        api.FORCE_SIMT_ENGINE = False
+    got, ids = api.nearest_neighbor_features_per_object(ref, qry, lab, 1, torch.tensor(N - 1))
+    assert ids.tolist() == list(range(N))
+    absent = want == 1e20
+    assert bool(absent[..., 3, 0].all()) and torch.equal(got == 1e20, absent)
+    err = ((got - want).abs() / want.abs().clamp(min=1.0))[~absent]
+    assert float(err.max()) <= RAW_RTOL
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1, 1, 1), (3, 5, 2, 2, 2), (16, 16, 1, 300, 64), (9, 7, 40, 1, 3)])
+def test_global_small_and_ragged_shapes(api, shape):
+    """Tiny / ragged problems (fewer rows than one 256-row tile, one object, 64 objects, single query)."""
+    H, W, Hr, Wr, N = shape
+    gen = torch.Generator().manual_seed(sum(shape))
+    C = 100
+    ref = torch.rand(C, Hr, Wr, generator=gen).cuda().permute(1, 2, 0)
+    qry = torch.rand(C, H, W, generator=gen).cuda().permute(1, 2, 0)
+    lab = torch.randint(0, N, (Hr, Wr, 1), generator=gen).int().cuda()
+    api.FORCE_SIMT_ENGINE = True
+    try:
+        want, _ = api.nearest_neighbor_features_per_object(ref, qry, lab, 1, torch.tensor(N - 1))
+    finally:
+        api.FORCE_SIMT_ENGINE = False
+    got, _ = api.nearest_neighbor_features_per_object(ref, qry, lab, 1, torch.tensor(N - 1))
+    absent = want == 1e20
+    assert torch.equal(got == 1e20, absent)
+    if (~absent).any():
+        err = ((got - want).abs() / want.abs().clamp(min=1.0))[~absent]
+        assert float(err.max()) <= RAW_RTOL
+
+
+def test_global_all_unlabelled_and_scale_extremes(api, cfg_guard):
+    """No labelled reference pixel at all -> every object absent (documented deviation: the reference raises);
+    operands of very different magnitude (power-of-two scaling, bias-fold fallback) keep fp32-grade accuracy."""
+    cfg_guard.TEST_MODE = True
+    gen = torch.Generator().manual_seed(4)
+    C, H, W, N = 100, 12, 14, 3
+    ref = torch.rand(C, H, W, generator=gen).cuda().permute(1, 2, 0)
+    qry = torch.rand(C, H, W, generator=gen).cuda().permute(1, 2, 0)
+    lab = torch.full((H, W, 1), -1, dtype=torch.int32).cuda()
+    out, _ = api.nearest_neighbor_features_per_object(ref, qry, lab, 1, torch.tensor(N - 1))
+    assert bool((out == 1e20).all())
+    lab = torch.randint(0, N, (H, W, 1), generator=gen).int().cuda()
+    for sr, sq in [(1e-3, 1e3), (3e4, 2e-2), (1e-6, 1e-6), (50.0, 50.0)]:
+        r2, q2 = (ref * sr).contiguous(), (qry * sq).contiguous()
+        api.FORCE_SIMT_ENGINE = True
+        try:
+            want, _ = api.nearest_neighbor_features_per_object(r2, q2, lab, 1, torch.tensor(N - 1))
+        finally:
+            api.FORCE_SIMT_ENGINE = False
+        got, _ = api.nearest_neighbor_features_per_object(r2, q2, lab, 1, torch.tensor(N - 1))
+        scale = float(want.abs().max())
+        assert float((got - want).abs().max()) <= 3e-5 * max(scale, 1.0), (sr, sq)
+
+
+def test_global_k_greater_than_one_matches_oracle(api, cfg_guard):
+    from oracle import manet_oracle as O
+    gen = torch.Generator().manual_seed(8)
+    C, H, W, N = 40, 14, 15, 4
+    ref_chw, qry_chw = torch.rand(C, H, W, generator=gen), torch.rand(C, H, W, generator=gen)
+    lab = torch.randint(0, N, (H, W), generator=gen).int()
+    lab[lab == 2] = 0
+    lab[0, :3] = 2                                       # object 2 has only 3 pixels: k=5 pads with its largest
+    for k in (2, 5):
+        want, _ = O.global_match(ref_chw.permute(1, 2, 0), qry_chw.permute(1, 2, 0), lab.unsqueeze(-1), k,
+                                 torch.tensor(N - 1), n_chunks=3)
+        got, _ = api.nearest_neighbor_features_per_object(ref_chw.cuda().permute(1, 2, 0), qry_chw.cuda().permute(1, 2, 0),
+                                                          lab.cuda().unsqueeze(-1), k, torch.tensor(N - 1))
+        assert raw_close(got.cpu().numpy(), want.numpy()) <= RAW_RTOL
+    with pytest.raises(RuntimeError, match="out of range"):
+        api.nearest_neighbor_features_per_object(ref_chw.cuda().permute(1, 2, 0)[:1, :2], qry_chw.cuda().permute(1, 2, 0),
+                                                 lab.cuda().unsqueeze(-1)[:1, :2], 5, torch.tensor(N - 1))
+
+
+def test_local_edge_shapes_and_ids(api):
+    """Odd sizes, window larger than the half-resolution frame, one object, non-consecutive gt_ids, d = 0."""
+    from oracle import manet_oracle as O
+    gen = torch.Generator().manual_seed(12)
+    for (H, W, C, d, ids) in [(7, 9, 5, 3, [0, 1, 2]), (6, 6, 100, 12, [0]), (15, 11, 33, 0, [0, 1]),
+                              (20, 22, 100, 5, [3, 0, 7]), (9, 30, 64, 2, [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])]:
+        prev = torch.rand(C, H, W, generator=gen) * 0.3
+        cur = prev + 0.05 * torch.randn(C, H, W, generator=gen)
+        lab = torch.randint(0, 8, (H, W), generator=gen).int()
+        idt = torch.tensor(ids, dtype=torch.int32)
+        want = O.local_match(prev.permute(1, 2, 0), cur.permute(1, 2, 0), lab.unsqueeze(-1), idt, d).numpy()
+        got = api.local_previous_frame_nearest_neighbor_features_per_object(
+            prev.cuda().permute(1, 2, 0), cur.cuda().permute(1, 2, 0), lab.cuda().unsqueeze(-1), idt.cuda(), d).cpu().numpy()
+        assert got.shape == want.shape and np.max(np.abs(got - want)) <= MAP_ATOL, (H, W, C, d)
