@@ -17,6 +17,7 @@ HEADER_PATH = os.path.join(os.path.dirname(PKG_DIR), "include", "manet_b200.h")
 GM_NORMALIZE = 1
 GM_DROP_UNLAB = 2
 GM_ENGINE_SIMT = 4
+LM_ENGINE_SIMT = 1
 STEP_SERIAL = 16
 DT_F32, DT_F16, DT_F64 = 0, 1, 2
 
@@ -36,6 +37,8 @@ SIGNATURES = {
     "manet_select_labelled": (c_int, [_P, _I64, _P, _I64, _I64, _I, _P, _P, _P, _P, _SZ, _P]),
     "manet_local_match_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
     "manet_local_match": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _P, _P, _I, _I, _I, _I, _I, _P, _P, _SZ, _P]),
+    "manet_local_match_ex": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _P, _P, _I, _I, _I, _I, _I, c_uint32, _P, _P, _SZ, _P]),
+    "manet_local_window_distances_ex": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I, _I, _I, _I, c_uint32, _P, _P, _SZ, _P]),
     "manet_local_window_distances": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I, _I, _I, _I, _P, _P, _SZ, _P]),
     "manet_global_map_update": (c_int, [_P, _P, _P, _I64, _I, _P]),
     "manet_local_map_store_select": (c_int, [_P, _P, _P, _I, _F, _P, _I64, _P]),

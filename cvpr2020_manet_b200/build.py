@@ -19,7 +19,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libmanet_b200.so")
 OBJDIR = os.path.join(PKG, "build")
-SOURCES = ["api.cu", "global_match_simt.cu", "global_match_umma.cu", "select_pixels.cu", "local_match.cu",
+SOURCES = ["api.cu", "global_match_simt.cu", "global_match_umma.cu", "select_pixels.cu", "local_match.cu", "local_match_umma.cu",
            "map_memory.cu", "correlation.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -54,7 +54,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         s, o = job
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        extra = os.environ.get("MANET_NVCC_EXTRA", "").split()      # e.g. -DLM_TRACE / -DGM_TRACE for in-kernel cycle traces
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {s}:\n{r.stdout}\n{r.stderr}")

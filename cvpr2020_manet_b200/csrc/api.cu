@@ -38,9 +38,9 @@ int launch_select_labelled(const int32_t*, int64_t, const float*, int64_t, int64
                            size_t, cudaStream_t);
 size_t local_match_workspace_bytes(int H, int W, int C, int N, int d);
 int launch_local_match(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, const int32_t*,
-                       const int32_t*, int, int, int, int, int, float*, void*, size_t, cudaStream_t);
+                       const int32_t*, int, int, int, int, int, uint32_t, float*, void*, size_t, cudaStream_t);
 int launch_local_window_distances(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, int, int,
-                                  int, int, float*, void*, size_t, cudaStream_t);
+                                  int, int, uint32_t, float*, void*, size_t, cudaStream_t);
 int launch_local_map_store_select(const float*, float*, float*, int, float, float*, int64_t, cudaStream_t);
 int correlation_output_shape(int, int, int, int, int, int, int, int, int*, int*, int*);
 int launch_correlation_forward(const void*, const int64_t*, const void*, const int64_t*, void*, void*, void*, int, int, int, int,
@@ -168,22 +168,37 @@ size_t manet_local_match_workspace_bytes(int H, int W, int C, int N, int max_dis
     return local_match_workspace_bytes(H, W, C, N, max_distance);
 }
 
-int manet_local_match(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_sc, const float* query, int64_t q_sy,
-                      int64_t q_sx, int64_t q_sc, const int32_t* labels, const int32_t* gt_ids, int H, int W, int C, int N,
-                      int max_distance, float* out, void* workspace, size_t workspace_bytes, manet_stream_t stream) {
+int manet_local_match_ex(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_sc, const float* query, int64_t q_sy,
+                         int64_t q_sx, int64_t q_sc, const int32_t* labels, const int32_t* gt_ids, int H, int W, int C, int N,
+                         int max_distance, uint32_t flags, float* out, void* workspace, size_t workspace_bytes,
+                         manet_stream_t stream) {
     MANET_ARCH();
     MANET_REQUIRE(prev && query && labels && gt_ids && out && workspace, "local match: null pointer");
     return launch_local_match(prev, p_sy, p_sx, p_sc, query, q_sy, q_sx, q_sc, labels, gt_ids, H, W, C, N, max_distance,
-                              out, workspace, workspace_bytes, (cudaStream_t)stream);
+                              flags, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int manet_local_match(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_sc, const float* query, int64_t q_sy,
+                      int64_t q_sx, int64_t q_sc, const int32_t* labels, const int32_t* gt_ids, int H, int W, int C, int N,
+                      int max_distance, float* out, void* workspace, size_t workspace_bytes, manet_stream_t stream) {
+    return manet_local_match_ex(prev, p_sy, p_sx, p_sc, query, q_sy, q_sx, q_sc, labels, gt_ids, H, W, C, N, max_distance, 0u,
+                                out, workspace, workspace_bytes, stream);
+}
+
+int manet_local_window_distances_ex(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_sc, const float* y, int64_t y_sy,
+                                    int64_t y_sx, int64_t y_sc, int H, int W, int C, int max_distance, uint32_t flags,
+                                    float* out, void* workspace, size_t workspace_bytes, manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(x && y && out && workspace, "local window distances: null pointer");
+    return launch_local_window_distances(x, x_sy, x_sx, x_sc, y, y_sy, y_sx, y_sc, H, W, C, max_distance, flags, out,
+                                         workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int manet_local_window_distances(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_sc, const float* y, int64_t y_sy,
                                  int64_t y_sx, int64_t y_sc, int H, int W, int C, int max_distance, float* out,
                                  void* workspace, size_t workspace_bytes, manet_stream_t stream) {
-    MANET_ARCH();
-    MANET_REQUIRE(x && y && out && workspace, "local window distances: null pointer");
-    return launch_local_window_distances(x, x_sy, x_sx, x_sc, y, y_sy, y_sx, y_sc, H, W, C, max_distance, out, workspace,
-                                         workspace_bytes, (cudaStream_t)stream);
+    return manet_local_window_distances_ex(x, x_sy, x_sx, x_sc, y, y_sy, y_sx, y_sc, H, W, C, max_distance, 0u, out,
+                                           workspace, workspace_bytes, stream);
 }
 
 int manet_global_map_update(const float* new_map, float* mem_frame, float* out, int64_t n, int normalize,

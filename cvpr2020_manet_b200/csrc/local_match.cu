@@ -10,6 +10,8 @@
 //   6. out[Y,X,o] = min(1, min_{l: lab==id_o} U[l,Y,X])          (:428-432)
 // The reference materialises C*h*w*L floats three times (unfold, difference, square);
 // here the only intermediate is T [h, w, L] (16 MB at 480p / d=12), which stays in L2.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace manet {
@@ -321,8 +323,7 @@ __global__ void upsample_volume_kernel(const float* __restrict__ T, int H, int W
 // ---------------------------------------------------------------- host side
 static inline int pooled_pitch(int w) { return (w + 3) & ~3; }
 
-size_t local_match_workspace_bytes(int H, int W, int C, int N, int d) {
-    (void)N;
+static size_t simt_workspace_bytes(int H, int W, int C, int d) {
     int h = H / 2, w = W / 2;
     size_t L = (size_t)(2 * d + 1) * (2 * d + 1);
     return 2 * align_up((size_t)C * h * pooled_pitch(w) * sizeof(float), 256) +
@@ -330,12 +331,22 @@ size_t local_match_workspace_bytes(int H, int W, int C, int N, int d) {
            align_up((size_t)(H + 4 * d) * (W + 4 * d) * sizeof(int32_t), 256) + 256;
 }
 
+size_t lm_umma_workspace_bytes(int H, int W, int C, int d);
+
+// large enough for either engine
+size_t local_match_workspace_bytes(int H, int W, int C, int N, int d) {
+    (void)N;
+    if (H < 2 || W < 2 || C < 1 || d < 0) return 256;
+    size_t a = simt_workspace_bytes(H, W, C, d), b = lm_umma_workspace_bytes(H, W, C, d);
+    return a > b ? a : b;
+}
+
 static int window_volume(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_sc,
                          const float* y, int64_t y_sy, int64_t y_sx, int64_t y_sc,
                          int H, int W, int C, int d, void* ws, size_t ws_bytes, cudaStream_t stream,
                          float** T_out, const int32_t* labels = nullptr, int32_t** plabels_out = nullptr) {
     if (H < 2 || W < 2 || C < 1 || d < 0) return fail_invalid("local match: need H,W >= 2, C >= 1, max_distance >= 0");
-    if (ws_bytes < local_match_workspace_bytes(H, W, C, 1, d)) { set_error("local match: workspace too small"); return MANET_E_WORKSPACE; }
+    if (ws_bytes < simt_workspace_bytes(H, W, C, d)) { set_error("local match: workspace too small"); return MANET_E_WORKSPACE; }
     const int h = H / 2, w = W / 2, wp = pooled_pitch(w);
     Carver cv(ws, ws_bytes);
     float* qs = cv.take<float>((size_t)C * h * wp);
@@ -370,11 +381,27 @@ static int window_volume(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_s
     return check_launch("local window kernels");
 }
 
+// tcgen05 engine (local_match_umma.cu)
+bool lm_umma_supported(int H, int W, int C, int N, int d);
+size_t lm_umma_workspace_bytes(int H, int W, int C, int d);
+int launch_local_match_umma(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, const int32_t*,
+                            const int32_t*, int, int, int, int, int, float*, float**, void*, size_t, cudaStream_t);
+
+static bool lm_force_simt() {
+    static int cached = -1;
+    if (cached < 0) { const char* e = getenv("MANET_LM_ENGINE"); cached = (e && (e[0] == 's' || e[0] == 'S')) ? 1 : 0; }
+    return cached == 1;
+}
+
 int launch_local_match(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_sc,
                        const float* query, int64_t q_sy, int64_t q_sx, int64_t q_sc,
                        const int32_t* labels, const int32_t* gt_ids, int H, int W, int C, int N, int d,
-                       float* out, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                       uint32_t flags, float* out, void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (N < 1) return fail_invalid("local match: N must be >= 1");
+    if (H < 2 || W < 2 || C < 1 || d < 0) return fail_invalid("local match: need H,W >= 2, C >= 1, max_distance >= 0");
+    if (!(flags & MANET_LM_ENGINE_SIMT) && !lm_force_simt() && lm_umma_supported(H, W, C, N, d))
+        return launch_local_match_umma(prev, p_sy, p_sx, p_sc, query, q_sy, q_sx, q_sc, labels, gt_ids, H, W, C, N, d, out,
+                                       nullptr, ws, ws_bytes, stream);
     float* T = nullptr;
     int32_t* plab = nullptr;
     int rc = window_volume(query, q_sy, q_sx, q_sc, prev, p_sy, p_sx, p_sc, H, W, C, d, ws, ws_bytes, stream, &T, labels, &plab);
@@ -393,10 +420,16 @@ int launch_local_match(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_
 
 int launch_local_window_distances(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_sc,
                                   const float* y, int64_t y_sy, int64_t y_sx, int64_t y_sc,
-                                  int H, int W, int C, int d, float* out, void* ws, size_t ws_bytes,
+                                  int H, int W, int C, int d, uint32_t flags, float* out, void* ws, size_t ws_bytes,
                                   cudaStream_t stream) {
     float* T = nullptr;
-    int rc = window_volume(x, x_sy, x_sx, x_sc, y, y_sy, y_sx, y_sc, H, W, C, d, ws, ws_bytes, stream, &T);
+    if (H < 2 || W < 2 || C < 1 || d < 0) return fail_invalid("local match: need H,W >= 2, C >= 1, max_distance >= 0");
+    int rc;
+    if (!(flags & MANET_LM_ENGINE_SIMT) && !lm_force_simt() && lm_umma_supported(H, W, C, 1, d))
+        rc = launch_local_match_umma(y, y_sy, y_sx, y_sc, x, x_sy, x_sx, x_sc, nullptr, nullptr, H, W, C, 1, d, nullptr, &T, ws,
+                                     ws_bytes, stream);
+    else
+        rc = window_volume(x, x_sy, x_sx, x_sc, y, y_sy, y_sx, y_sc, H, W, C, d, ws, ws_bytes, stream, &T);
     if (rc) return rc;
     const int L = (2 * d + 1) * (2 * d + 1);
     int64_t total = (int64_t)H * W * L;

@@ -19,6 +19,7 @@ from ..config import cfg
 USE_CORRELATION_COST = False          # IntVOS.py:15 (kept for API compatibility)
 MODEL_UNFOLD = True                   # IntVOS.py:16
 WRONG_LABEL_PADDING_DISTANCE = 1e20   # IntVOS.py:17
+FORCE_SIMT_LOCAL_ENGINE = False       # same for local matching (exact difference form on CUDA cores)
 FORCE_SIMT_ENGINE = False             # debugging/tests: route global matching to the fp32 CUDA-core kernel
 
 
@@ -219,6 +220,10 @@ def _hwc_strides(t, name):
     return t.stride(0), t.stride(1), t.stride(2)
 
 
+def _local_flags():
+    return _lib.LM_ENGINE_SIMT if FORCE_SIMT_LOCAL_ENGINE else 0
+
+
 def local_pairwise_distances2(x, y, max_distance=9):
     """Windowed squared distances between x[y,x] and y[y+dy,x+dx] at half resolution,
     normalised to [0,1] and bilinearly upsampled: ``[H, W, (2d+1)^2]`` (IntVOS.py:266-296)."""
@@ -235,8 +240,8 @@ def local_pairwise_distances2(x, y, max_distance=9):
     out = torch.empty((h, w, (2 * d + 1) ** 2), dtype=torch.float32, device=dev)
     ws = workspace(dev, L.manet_local_match_workspace_bytes(h, w, c, 1, d), "local")
     with torch.cuda.device(dev):
-        check(L.manet_local_window_distances(x.data_ptr(), *xs, y.data_ptr(), *ysd, h, w, c, d, out.data_ptr(),
-                                             ws.data_ptr(), ws.numel(), stream_ptr(dev)),
+        check(L.manet_local_window_distances_ex(x.data_ptr(), *xs, y.data_ptr(), *ysd, h, w, c, d, _local_flags(),
+                                                out.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)),
               "manet_local_window_distances")
     return out
 
@@ -285,7 +290,7 @@ def local_previous_frame_nearest_neighbor_features_per_object(prev_frame_embeddi
     out = torch.empty((1, h, w, n_obj, 1), dtype=torch.float32, device=dev)
     ws = workspace(dev, L.manet_local_match_workspace_bytes(h, w, c, n_obj, d), "local")
     with torch.cuda.device(dev):
-        check(L.manet_local_match(prev_frame_embedding.data_ptr(), *ps, query_embedding.data_ptr(), *qs,
-                                  labels.data_ptr(), ids.data_ptr(), h, w, c, n_obj, d, out.data_ptr(),
-                                  ws.data_ptr(), ws.numel(), stream_ptr(dev)), "manet_local_match")
+        check(L.manet_local_match_ex(prev_frame_embedding.data_ptr(), *ps, query_embedding.data_ptr(), *qs,
+                                     labels.data_ptr(), ids.data_ptr(), h, w, c, n_obj, d, _local_flags(), out.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), stream_ptr(dev)), "manet_local_match")
     return out

@@ -41,6 +41,8 @@ typedef void* manet_stream_t; /* a cudaStream_t */
 #define MANET_GM_NORMALIZE   1u /* apply (sigmoid(x)-0.5)*2 to the result (IntVOS.py:611-612) */
 #define MANET_GM_DROP_UNLAB  2u /* drop reference pixels labelled -1 first (cfg.TEST_MODE, IntVOS.py:135-136) */
 #define MANET_GM_ENGINE_SIMT 4u /* force the fp32 CUDA-core kernel instead of the tcgen05 kernel */
+/* local-match flag (the *_ex entry points) */
+#define MANET_LM_ENGINE_SIMT 1u /* force the fp32 CUDA-core kernels (exact difference form) instead of the tcgen05 kernel */
 /* session-step flag: run the local-matching branch on the same stream as the global branch (the
  * default forks it onto a second stream so its kernels overlap the pre/post passes of the GEMM) */
 #define MANET_STEP_SERIAL    16u
@@ -127,12 +129,26 @@ int manet_local_match(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_s
                       int H, int W, int C, int N, int max_distance, float* out,
                       void* workspace, size_t workspace_bytes, manet_stream_t stream);
 
+/* Same with flags (MANET_LM_ENGINE_SIMT).  manet_local_match == flags 0: the tcgen05 engine whenever the
+ * shape allows it (max_distance <= 12, C <= 128, H,W >= 6, N limited by shared memory: <= 11 at
+ * max_distance 12), the CUDA-core engine otherwise. */
+int manet_local_match_ex(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_sc,
+                         const float* query, int64_t q_sy, int64_t q_sx, int64_t q_sc,
+                         const int32_t* labels, const int32_t* gt_ids,
+                         int H, int W, int C, int N, int max_distance, uint32_t flags, float* out,
+                         void* workspace, size_t workspace_bytes, manet_stream_t stream);
+
 /* The windowed distance volume alone (local_pairwise_distances2(x, y, d), IntVOS.py:266-296):
  * out [H, W, (2d+1)^2], normalised and bilinearly upsampled. */
 int manet_local_window_distances(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_sc,
                                  const float* y, int64_t y_sy, int64_t y_sx, int64_t y_sc,
                                  int H, int W, int C, int max_distance, float* out,
                                  void* workspace, size_t workspace_bytes, manet_stream_t stream);
+
+int manet_local_window_distances_ex(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_sc,
+                                    const float* y, int64_t y_sy, int64_t y_sx, int64_t y_sc,
+                                    int H, int W, int C, int max_distance, uint32_t flags, float* out,
+                                    void* workspace, size_t workspace_bytes, manet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Map memory (networks/IntVOS.py:615-622 / 716-723 and 638-661).

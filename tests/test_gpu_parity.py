@@ -190,8 +190,13 @@ def test_selected_pixel_bit_exact(api, golden):
 
 
 # ------------------------------------------------------------------ local matching
+LOCAL_ENGINES = ["tcgen05", "simt"]
+
+
+@pytest.mark.parametrize("engine", LOCAL_ENGINES)
 @pytest.mark.parametrize("name", LOCAL)
-def test_local_matches_reference_golden(api, golden, name):
+def test_local_matches_reference_golden(api, golden, name, engine, monkeypatch):
+    monkeypatch.setattr(api, "FORCE_SIMT_LOCAL_ENGINE", engine == "simt")
     g = golden(name)
     prev = cuda(g["prev_chw"]).permute(1, 2, 0)
     cur = cuda(g["cur_chw"]).permute(1, 2, 0)
@@ -206,11 +211,13 @@ def test_local_matches_reference_golden(api, golden, name):
         assert np.max(np.abs(win.cpu().numpy() - g["window"])) <= MAP_ATOL
 
 
+@pytest.mark.parametrize("engine", LOCAL_ENGINES)
 @pytest.mark.parametrize("d", [9, 12, 14])
-def test_local_vs_oracle_half_480p(api, d):
+def test_local_vs_oracle_half_480p(api, d, engine, monkeypatch):
     """60x106 frame, N = 6, noisy-copy embeddings (distances in the transform's sensitive range),
-    d = 14 exercises the generic-window kernel."""
+    d = 14 exercises the generic-window kernel (CUDA-core engine in both parametrisations)."""
     from oracle import manet_oracle as O
+    monkeypatch.setattr(api, "FORCE_SIMT_LOCAL_ENGINE", engine == "simt")
     gen = torch.Generator().manual_seed(d)
     C, H, W, N = 100, 60, 106, 6
     prev = 0.1 * torch.relu(torch.randn(C, H, W, generator=gen))
@@ -225,10 +232,13 @@ def test_local_vs_oracle_half_480p(api, d):
     assert (got[..., 3, 0] == 1.0).all()
 
 
-def test_local_full_480p_properties(api):
+@pytest.mark.parametrize("engine", LOCAL_ENGINES)
+def test_local_full_480p_properties(api, engine, monkeypatch):
     """Full 480p, d = 12, N = 6: (1) output in [0,1]; (2) self-matching with labels == o everywhere
-    gives 0 for o (offset (0,0) has distance 0) and exactly 1 for every other object;
-    (3) contiguous [H,W,C] input == permuted [C,H,W] view input, bit-exact."""
+    gives 0 for o (offset (0,0) has distance 0; the tensor-core engine evaluates the GEMM form on
+    tile-centred operands, so "0" is within the map tolerance instead of exact) and exactly 1 for
+    every other object; (3) contiguous [H,W,C] input == permuted [C,H,W] view input, bit-exact."""
+    monkeypatch.setattr(api, "FORCE_SIMT_LOCAL_ENGINE", engine == "simt")
     gen = torch.Generator().manual_seed(3)
     C, H, W, N = 100, 120, 214, 6
     emb = torch.rand(C, H, W, generator=gen).cuda()
@@ -237,7 +247,7 @@ def test_local_full_480p_properties(api):
     lab = torch.full((H, W, 1), 2, dtype=torch.int32).cuda()
     out = api.local_previous_frame_nearest_neighbor_features_per_object(e, e, lab, ids, 12)[0, :, :, :, 0]
     assert float(out.min()) >= 0.0 and float(out.max()) <= 1.0
-    assert float(out[..., 2].max()) <= 1e-6
+    assert float(out[..., 2].max()) <= (1e-6 if engine == "simt" else MAP_ATOL)
     others = out[..., [0, 1, 3, 4, 5]]
     inner = others[24:-24, 24:-24]
     assert bool((inner == 1.0).all())
@@ -475,12 +485,17 @@ def test_global_k_greater_than_one_matches_oracle(api, cfg_guard):
                                                  lab.cuda().unsqueeze(-1)[:1, :2], 5, torch.tensor(N - 1))
 
 
-def test_local_edge_shapes_and_ids(api):
-    """Odd sizes, window larger than the half-resolution frame, one object, non-consecutive gt_ids, d = 0."""
+@pytest.mark.parametrize("engine", LOCAL_ENGINES)
+def test_local_edge_shapes_and_ids(api, engine, monkeypatch):
+    """Odd sizes, window larger than the half-resolution frame, one object, non-consecutive / duplicate
+    gt_ids, d = 0, many objects."""
     from oracle import manet_oracle as O
+    monkeypatch.setattr(api, "FORCE_SIMT_LOCAL_ENGINE", engine == "simt")
     gen = torch.Generator().manual_seed(12)
     for (H, W, C, d, ids) in [(7, 9, 5, 3, [0, 1, 2]), (6, 6, 100, 12, [0]), (15, 11, 33, 0, [0, 1]),
-                              (20, 22, 100, 5, [3, 0, 7]), (9, 30, 64, 2, [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])]:
+                              (20, 22, 100, 5, [3, 0, 7]), (9, 30, 64, 2, [0, 1, 2, 3, 4, 5, 6, 7, 8, 9]),
+                              (33, 47, 100, 7, [0, 1, 1, 5]), (41, 64, 128, 12, [0, 1, 2, 3, 4, 5, 6, 7]),
+                              (64, 50, 17, 9, [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12]), (120, 214, 100, 1, [0, 2])]:
         prev = torch.rand(C, H, W, generator=gen) * 0.3
         cur = prev + 0.05 * torch.randn(C, H, W, generator=gen)
         lab = torch.randint(0, 8, (H, W), generator=gen).int()
