@@ -54,12 +54,15 @@ constexpr int LM_THREADS = LM_CONV_THREADS + 32 + LM_EPI_THREADS;   // 416
 constexpr int LM_EPI_T0 = LM_CONV_THREADS + 32;
 constexpr int LM_A_BYTES = 4 * 16384;                   // [hi|lo][k-block 0|1][128 rows][128 B]
 constexpr int LM_POOL_PX = 32;
+constexpr int LM_LABN = 12;                              // raw labels a thread keeps in registers across the first prologue barrier
 constexpr int LM_CONV_BATCH = 5;                         // operand chunks a converter thread keeps in flight
 
 // PyTorch upsample_bilinear2d, align_corners=True: scale=(in-1)/(out-1); src=scale*dst; i0=floor(src)
 // (clamped), w1 = src - i0.  Same arithmetic as make_lerp in local_match.cu; host and device agree bit for bit.
-__host__ __device__ inline int lm_lerp(int dst, int in_size, int out_size, float* w1) {
-    const float scale = (out_size > 1) ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+__host__ __device__ inline float lm_lerp_scale(int in_size, int out_size) {
+    return (out_size > 1) ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+}
+__host__ __device__ inline int lm_lerp(int dst, int in_size, float scale, float* w1) {
     const float src = scale * (float)dst;
     int i0 = (int)src;
     if (i0 > in_size - 1) i0 = in_size - 1;
@@ -67,9 +70,9 @@ __host__ __device__ inline int lm_lerp(int dst, int in_size, int out_size, float
     return i0;
 }
 // first output index whose source cell is >= i0 (lm_lerp is monotone in dst)
-__host__ __device__ inline int lm_first_out(int i0, int in_size, int out_size) {
+__host__ __device__ inline int lm_first_out(int i0, int in_size, int out_size, float scale) {
     int lo = 0, hi = out_size;                           // smallest dst in [0,out] with lerp(dst) >= i0
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (lm_lerp(mid, in_size, out_size, nullptr) >= i0) hi = mid; else lo = mid + 1; }
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (lm_lerp(mid, in_size, scale, nullptr) >= i0) hi = mid; else lo = mid + 1; }
     return lo;
 }
 
@@ -77,6 +80,7 @@ struct LmGeom {
     int h, w, Cp, ksteps, nkb, D2, WC, NB, ntx, nty;
     int lab_rows, lab_pitch;                             // shared-memory label window (bytes)
     int max_units;
+    float sy, sx;                                        // bilinear source scales (h-1)/(H-1), (w-1)/(W-1), computed once on the host
     // shared-memory byte offsets
     int off_B, off_T, off_min, off_lab, off_ys, off_xs, off_mu, off_units, off_tab, off_bar, total;
 };
@@ -99,12 +103,13 @@ static bool lm_geometry(int H, int W, int C, int N, int d, LmGeom* g) {
     g->ntx = (w + LM_CW - 1) / LM_CW;
     // worst tile: number of <=2x2 output blocks and the span of full-resolution pixels it covers
     int max_uy = 0, max_ys = 0, max_ux = 0, max_xs = 0;
+    g->sy = lm_lerp_scale(h, H); g->sx = lm_lerp_scale(w, W);
     for (int t = 0; t < g->nty; ++t) {
         int units = 0, first = -1, last = -1;
         for (int c = 0; c < LM_CH; ++c) {
             const int y0 = t * LM_CH + c;
             if (y0 >= h) break;
-            const int a = lm_first_out(y0, h, H), b = lm_first_out(y0 + 1, h, H);
+            const int a = lm_first_out(y0, h, H, g->sy), b = lm_first_out(y0 + 1, h, H, g->sy);
             if (b > a) { units += (b - a + 1) / 2; if (first < 0) first = a; last = b - 1; }
         }
         if (units > max_uy) max_uy = units;
@@ -115,7 +120,7 @@ static bool lm_geometry(int H, int W, int C, int N, int d, LmGeom* g) {
         for (int c = 0; c < LM_CW; ++c) {
             const int x0 = t * LM_CW + c;
             if (x0 >= w) break;
-            const int a = lm_first_out(x0, w, W), b = lm_first_out(x0 + 1, w, W);
+            const int a = lm_first_out(x0, w, W, g->sx), b = lm_first_out(x0 + 1, w, W, g->sx);
             if (b > a) { units += (b - a + 1) / 2; if (first < 0) first = a; last = b - 1; }
         }
         if (units > max_ux) max_ux = units;
@@ -125,6 +130,7 @@ static bool lm_geometry(int H, int W, int C, int N, int d, LmGeom* g) {
     if (g->max_units > LM_MAXUNITS || g->max_units < 1) return false;
     g->lab_rows = max_ys + 2 * d + 2;                    // (span) + 2*(ndy-1) + one spare row for the 2x2 block
     g->lab_pitch = lm_round_up(max_xs + 4 * d + 2, 16);
+    if (g->lab_rows * g->lab_pitch > LM_LABN * LM_THREADS) return false;   // the prologue keeps the window in registers
     int o = LM_A_BYTES;
     g->off_B = o; o += 2 * (g->NB / 2) * 256;            // 2 stages x [hi|lo][NB/2 rows][128 B] (one k-block of two rows)
     g->off_T = o; o += LM_TSLOTS * g->D2 * 128 * 4;
@@ -251,35 +257,75 @@ __device__ __forceinline__ float lm_pow2_scale(float a) {
     return ldexpf(1.0f, sh);
 }
 
-// One (row, 16-byte chunk) of an operand image: 8 channels of (x - mu) * s -> fp16 hi + lo, written to the
-// K-major SWIZZLE_128B position of `row`; returns the sum of squares of the 8 centred values.
-__device__ __forceinline__ float lm_convert_chunk(float4 a, float4 b, bool valid, const float* __restrict__ mu8,
-                                                  float s, uint8_t* img_hi, uint8_t* img_lo, int row, int chk, bool store) {
-    float v[8];
-    const float4 m0 = *reinterpret_cast<const float4*>(mu8), m1 = *reinterpret_cast<const float4*>(mu8 + 4);
-    v[0] = a.x - m0.x; v[1] = a.y - m0.y; v[2] = a.z - m0.z; v[3] = a.w - m0.w;
-    v[4] = b.x - m1.x; v[5] = b.y - m1.y; v[6] = b.z - m1.z; v[7] = b.w - m1.w;
+// One (row, 16-byte chunk) of an operand image: 8 channels of x*s - mu*s -> fp16 hi + lo, written at byte offset `o`
+// (the K-major SWIZZLE_128B position of the row); returns the sum of squares of the 8 SCALED centred values.
+#ifdef LM_TRACE
+#define LM_TT(i) { long long _n = clock64(); if (tt) tt[i] += _n - _t0; _t0 = _n; }
+#else
+#define LM_TT(i)
+#endif
+__device__ __forceinline__ float lm_convert_chunk(float4 a, float4 b, bool valid, const float* __restrict__ mus8,
+                                                  float s, uint8_t* img_hi, uint8_t* img_lo, int o, bool store, long long* tt = nullptr) {
+#ifdef LM_TRACE
+    long long _t0 = clock64();
+#endif
+    const float4 m0 = *reinterpret_cast<const float4*>(mus8), m1 = *reinterpret_cast<const float4*>(mus8 + 4);
+    float x[8] = {fmaf(a.x, s, -m0.x), fmaf(a.y, s, -m0.y), fmaf(a.z, s, -m0.z), fmaf(a.w, s, -m0.w),
+                  fmaf(b.x, s, -m1.x), fmaf(b.y, s, -m1.y), fmaf(b.z, s, -m1.z), fmaf(b.w, s, -m1.w)};
     if (!valid) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = 0.f;
+        for (int k = 0; k < 8; ++k) x[k] = 0.f;
     }
-    float sq = 0.f;
+    LM_TT(0)
+    float s0 = 0.f, s1 = 0.f;
     __half2 hh[4], ll[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        sq = fmaf(v[2 * k], v[2 * k], sq);
-        sq = fmaf(v[2 * k + 1], v[2 * k + 1], sq);
-        const float2 x = make_float2(v[2 * k] * s, v[2 * k + 1] * s);
-        hh[k] = __float22half2_rn(x);
+        s0 = fmaf(x[2 * k], x[2 * k], s0);
+        s1 = fmaf(x[2 * k + 1], x[2 * k + 1], s1);
+        hh[k] = __floats2half2_rn(x[2 * k], x[2 * k + 1]);
         const float2 back = __half22float2(hh[k]);
-        ll[k] = __float22half2_rn(make_float2(x.x - back.x, x.y - back.y));
+        ll[k] = __floats2half2_rn(x[2 * k] - back.x, x[2 * k + 1] - back.y);
     }
+    LM_TT(1)
     if (store) {
-        const int o = (row >> 3) * 1024 + (row & 7) * 128 + ((chk ^ (row & 7)) << 4);
         *reinterpret_cast<uint4*>(img_hi + o) = *reinterpret_cast<uint4*>(hh);
         *reinterpret_cast<uint4*>(img_lo + o) = *reinterpret_cast<uint4*>(ll);
     }
-    return sq;
+    LM_TT(2)
+    return s0 + s1;
+}
+
+// register-only form of lm_convert_chunk (the caller stores): returns the sum of squares
+__device__ __forceinline__ float lm_split_chunk(float4 a, float4 b, bool valid, float4 m0, float4 m1, float s, uint4& hi, uint4& lo) {
+    float x[8] = {fmaf(a.x, s, -m0.x), fmaf(a.y, s, -m0.y), fmaf(a.z, s, -m0.z), fmaf(a.w, s, -m0.w),
+                  fmaf(b.x, s, -m1.x), fmaf(b.y, s, -m1.y), fmaf(b.z, s, -m1.z), fmaf(b.w, s, -m1.w)};
+    if (!valid) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = 0.f;
+    }
+    float s0 = 0.f, s1 = 0.f;
+    __half2 hh[4], ll[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        s0 = fmaf(x[2 * k], x[2 * k], s0);
+        s1 = fmaf(x[2 * k + 1], x[2 * k + 1], s1);
+        hh[k] = __floats2half2_rn(x[2 * k], x[2 * k + 1]);
+        const float2 back = __half22float2(hh[k]);
+        ll[k] = __floats2half2_rn(x[2 * k] - back.x, x[2 * k + 1] - back.y);
+    }
+    hi = *reinterpret_cast<uint4*>(hh);
+    lo = *reinterpret_cast<uint4*>(ll);
+    return s0 + s1;
+}
+
+// T = (sigmoid(D) - 0.5) * 2 = 1 - 2 / (1 + e^D) from arg = D * log2(e): two MUFU ops, abs error < 3e-7;
+// arg = +inf (outside the image) gives exactly 1.
+__device__ __forceinline__ float lm_transform(float arg) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(arg));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return fmaf(-2.0f, r, 1.0f);
 }
 
 __device__ __forceinline__ void lm_smem_min(uint32_t addr, float v) {
@@ -287,6 +333,14 @@ __device__ __forceinline__ void lm_smem_min(uint32_t addr, float v) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o) : "r"(addr));
     o = fminf(o, v);
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(o) : "memory");
+}
+
+// 16-byte read-only load that the compiler may not sink towards its first use (volatile asm keeps its place among the
+// mbarrier waits): this is what makes the converters' prefetch distance real.
+__device__ __forceinline__ float4 ldg_nc_v4_early(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
 }
 
 // loads of one converter batch: LM_CONV_BATCH (row, 16-byte chunk) tasks of one B stage, kept in registers
@@ -335,6 +389,7 @@ lm_umma_kernel(const LmParams P) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef LM_TRACE
     long long tr0 = clock64(), tr_pro = 0, tr_w1 = 0, tr_w2 = 0, tr_a = 0, tr_b = 0, tr_c = 0;
+    long long tr_t[4] = {0, 0, 0, 0};
 #define TR(var, expr) { long long _t = clock64(); expr; var += clock64() - _t; }
 #else
 #define TR(var, expr) { expr; }
@@ -355,14 +410,26 @@ lm_umma_kernel(const LmParams P) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sTab[50])), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    int lab_raw[LM_LABN];
+    const int lab_total = do_cells ? G.lab_rows * G.lab_pitch : 0;
     {
-        // global |x| max of the pooled frames -> operand scale
+        // All global loads of the prologue are issued here, before the first barrier: |x| max blocks, the query tile
+        // (for its mean), the label window and the ids.
+        const int Ymin = lm_first_out(qy0, h, P.H, G.sy), Xmin = lm_first_out(qx0, w, P.W, G.sx);
+        if (do_cells) {
+            // label window origin in the zero-padded label image: (Ymin + 2*dyA, Xmin)
+            const int PW = P.W + 4 * d, PH = P.H + 4 * d;
+#pragma unroll
+            for (int t = 0; t < LM_LABN; ++t) {
+                const int i = tid + t * LM_THREADS;
+                const int ry = i / G.lab_pitch, rx = i - ry * G.lab_pitch;
+                const int yy = Ymin + 2 * dyA + ry, xx = Xmin + rx;
+                lab_raw[t] = INT_MIN;
+                if (i < lab_total && yy < PH && xx < PW) lab_raw[t] = __ldg(P.plabels + (size_t)yy * PW + xx);
+            }
+        }
         float m = 0.f;
         for (int i = tid; i < P.n_blkmax; i += LM_THREADS) m = fmaxf(m, __ldg(P.blkmax + i));
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        float* red = reinterpret_cast<float*>(sLab);                 // scratch (the label window is filled later)
-        if (lane == 0) red[warp] = m;
         // partial channel sums of the query tile (scratch: the B stages); all loads of a thread in flight together
         float* psum = reinterpret_cast<float*>(sB);
         const int Gc = Cp >> 2, S = LM_THREADS / Gc;
@@ -384,48 +451,59 @@ lm_umma_kernel(const LmParams P) {
             }
             reinterpret_cast<float4*>(psum + (size_t)sub * Cp)[g4] = acc;
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) sXs[warp] = m;                                // scratch: sXs is written by the converters later
         // bilinear tables: for every cell row / column of this tile the first output index and the count
         if (tid < LM_CH) {
             const int y0 = qy0 + tid;
             int a = 0, n = 0;
-            if (y0 < h) { a = lm_first_out(y0, h, P.H); n = lm_first_out(y0 + 1, h, P.H) - a; }
+            if (y0 < h) { a = lm_first_out(y0, h, P.H, G.sy); n = lm_first_out(y0 + 1, h, P.H, G.sy) - a; }
             sTab[tid] = a; sTab[8 + tid] = n;
         } else if (tid >= 32 && tid < 32 + LM_CW) {
             const int c = tid - 32, x0 = qx0 + c;
             int a = 0, n = 0;
-            if (x0 < w) { a = lm_first_out(x0, w, P.W); n = lm_first_out(x0 + 1, w, P.W) - a; }
+            if (x0 < w) { a = lm_first_out(x0, w, P.W, G.sx); n = lm_first_out(x0 + 1, w, P.W, G.sx) - a; }
             sTab[16 + c] = a; sTab[32 + c] = n;
         } else if (tid == 64) {
             sTab[48] = 0;
         } else if (tid >= 96 && tid < 96 + N && do_cells) {
-            // slot of an id = the first gt_ids entry holding the same (float-compared) value (IntVOS.py:406-408)
-            const int o = tid - 96;
-            const float id = (float)__ldg(P.gt_ids + o);
-            int c = o;
-            for (int k = o - 1; k >= 0; --k) if ((float)__ldg(P.gt_ids + k) == id) c = k;
-            sTab[64 + o] = __ldg(P.gt_ids + o); sTab[128 + o] = c;
+                        sTab[64 + (tid - 96)] = __ldg(P.gt_ids + (tid - 96));
         }
     }
+#ifdef LM_TRACE
+    tr_t[0] = clock64() - tr0;
+#endif
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+#ifdef LM_TRACE
+    tr_t[1] = clock64() - tr0;
+#endif
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&sTab[50]);
+    float scale;
     {
-        float* red = reinterpret_cast<float*>(sLab);
         float m = 0.f;
-        for (int k = 0; k < LM_THREADS / 32; ++k) m = fmaxf(m, red[k]);
+        for (int k = 0; k < LM_THREADS / 32; ++k) m = fmaxf(m, sXs[k]);
+        scale = lm_pow2_scale(m);
         const float* psum = reinterpret_cast<const float*>(sB);
         const int Gc = Cp >> 2, S = LM_THREADS / Gc;
         if (tid < Cp) {
             float a = 0.f;
             for (int k = 0; k < S; ++k) a += psum[(size_t)k * Cp + tid];
             const int cnt = min(LM_TH, h - qy0) * min(LM_TW, w - qx0);
-            sMu[tid] = a / (float)cnt;
+            sMu[tid] = (a / (float)cnt) * scale;                      // mu * s: the converters evaluate x*s - mu*s in one FFMA
         } else if (tid < LM_MAXC) {
             sMu[tid] = 0.f;
         }
-        __syncthreads();                                              // red[] / psum consumed before they are reused
-        if (tid == 0) sTab[49] = __float_as_int(lm_pow2_scale(m));
+        // slot of an id = the first gt_ids entry holding the same (float-compared) value (IntVOS.py:406-408)
+        if (tid >= LM_THREADS - 32 && tid < LM_THREADS - 32 + N && do_cells) {
+            const int o = tid - (LM_THREADS - 32);
+            const float id = (float)sTab[64 + o];
+            int c = o;
+            for (int k = o - 1; k >= 0; --k) if ((float)sTab[64 + k] == id) c = k;
+            sTab[128 + o] = c;
+        }
         // units: every cell's outputs in blocks of <= 2x2; block (0,0) keeps the cell's index, the rest is appended
         if (tid < LM_NCELL && do_cells) {
             const int cy = tid / LM_CW, cx = tid % LM_CW;
@@ -442,38 +520,26 @@ lm_umma_kernel(const LmParams P) {
             }
         }
         if (do_cells) {
-            // label window -> slot bytes.  Window origin in the zero-padded label image: (Ymin + 2*dyA, Xmin).
-            const int Ymin = sTab[0], Xmin = sTab[16];
-            const int PW = P.W + 4 * d, PH = P.H + 4 * d;
-            const int total = G.lab_rows * G.lab_pitch;
-            for (int i0 = tid; i0 < total; i0 += 4 * LM_THREADS) {
-                int lv[4];
+            // label window -> slot bytes
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int i = i0 + t * LM_THREADS;
-                    const int ry = i / G.lab_pitch, rx = i - ry * G.lab_pitch;
-                    const int yy = Ymin + 2 * dyA + ry, xx = Xmin + rx;
-                    lv[t] = INT_MIN;
-                    if (i < total && yy < PH && xx < PW) lv[t] = __ldg(P.plabels + (size_t)yy * PW + xx);
-                }
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int i = i0 + t * LM_THREADS;
-                    if (i < total) {
-                        int slot = N;
-                        if (lv[t] != INT_MIN) {
-                            const float lf = (float)lv[t];
-                            for (int o = N - 1; o >= 0; --o) if (lf == (float)sTab[64 + o]) slot = o;
-                        }
-                        sLab[i] = (uint8_t)slot;
+            for (int t = 0; t < LM_LABN; ++t) {
+                const int i = tid + t * LM_THREADS;
+                if (i < lab_total) {
+                    int slot = N;
+                    if (lab_raw[t] != INT_MIN) {
+                        const float lf = (float)lab_raw[t];
+                        for (int o = N - 1; o >= 0; --o) if (lf == (float)sTab[64 + o]) slot = o;
                     }
+                    sLab[i] = (uint8_t)slot;
                 }
             }
             for (int i = tid; i < (N + 1) * 4 * LM_EPI_THREADS; i += LM_THREADS) sMin[i] = 1.0f;
         }
     }
+#ifdef LM_TRACE
+    tr_t[2] = clock64() - tr0;
+#endif
     __syncthreads();
-    const float scale = __int_as_float(sTab[49]);
     const int ksteps = G.ksteps, nkb = G.nkb;
     const int n_stages = n_chunks * nkb * 2;                         // B stage = (chunk, k-block, pair of rows)
 #ifdef LM_TRACE
@@ -504,8 +570,9 @@ lm_umma_kernel(const LmParams P) {
                 const int row = i >> 3, chk = i & 7, j = kb * 8 + chk;
                 const int y = qy0 + (row >> 4), x = qx0 + (row & 15);
                 const bool valid = (y < h) && (x < w) && (j * 8 < Cp);
+                const int o = (row >> 3) * 1024 + (row & 7) * 128 + ((chk ^ (row & 7)) << 4);
                 float sq = lm_convert_chunk(va[e], vb[e], valid, sMu + j * 8, scale, sA + kb * 16384, sA + 2 * 16384 + kb * 16384,
-                                            row, chk, j < 2 * ksteps);
+                                            o, j < 2 * ksteps);
                 sq += __shfl_xor_sync(0xffffffffu, sq, 1);
                 sq += __shfl_xor_sync(0xffffffffu, sq, 2);
                 sq += __shfl_xor_sync(0xffffffffu, sq, 4);
@@ -517,47 +584,76 @@ lm_umma_kernel(const LmParams P) {
         // B: stage q = (chunk c, k-block kb, row pair hf): 2 previous-frame rows x WC columns x 64 channels, hi and lo.
         // The loads of stage q+1 are issued before stage q is converted, so L2 latency hides behind the conversion.
         const int per_thread = NBH / 16;                             // (NBH rows x 8 chunks) / 128 threads  (<= LM_CONV_BATCH)
+        // per-task constants (the same for every stage): row of the pair, window column, swizzled byte offset
+        int t_off[LM_CONV_BATCH], t_px[LM_CONV_BATCH], t_n[LM_CONV_BATCH];
+        bool t_row1[LM_CONV_BATCH], t_xok[LM_CONV_BATCH];
+        const int chk = ct & 7;
+#pragma unroll
+        for (int t = 0; t < LM_CONV_BATCH; ++t) {
+            const int n = (ct + LM_CONV_THREADS * t) >> 3;
+            t_n[t] = n;
+            t_row1[t] = n >= WC;
+            const int cc = n - (t_row1[t] ? WC : 0);
+            t_px[t] = px0 + cc;
+            t_xok[t] = (t < per_thread) && (t_px[t] >= 0) && (t_px[t] < w);
+            t_off[t] = (n >> 3) * 1024 + (n & 7) * 128 + ((chk ^ (n & 7)) << 4);
+        }
         auto issue = [&](int q, LmBatch& bt) {
             const int hf = q & 1, kb = (q >> 1) % nkb, c = (q >> 1) / nkb;
             const int r0 = r_first + c * LM_ROWS + 2 * hf;
+            const int j = kb * 8 + chk;
+            const bool jok = j * 8 < Cp;
 #pragma unroll
             for (int t = 0; t < LM_CONV_BATCH; ++t) {
-                const int i = ct + LM_CONV_THREADS * t;
-                const int n = i >> 3, j = kb * 8 + (i & 7);
-                const int jr = n / WC, cc = n - jr * WC;
-                const int py = r0 + jr, pxx = px0 + cc;
+                const int py = r0 + (t_row1[t] ? 1 : 0);
                 bt.a[t] = bt.b[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if ((t < per_thread) && (py >= 0) && (py < h) && (pxx >= 0) && (pxx < w) && (j * 8 < Cp)) {
-                    const float4* src = reinterpret_cast<const float4*>(P.Pp + ((size_t)py * w + pxx) * Cp + j * 8);
-                    bt.a[t] = __ldg(src); bt.b[t] = __ldg(src + 1);
+                if (t_xok[t] && jok && (py >= 0) && (py < h)) {
+                    const float4* src = reinterpret_cast<const float4*>(P.Pp + ((size_t)py * w + t_px[t]) * Cp + j * 8);
+                    bt.a[t] = ldg_nc_v4_early(src); bt.b[t] = ldg_nc_v4_early(src + 1);
                 }
             }
         };
         auto convert = [&](int q, const LmBatch& bt) {
             const int hf = q & 1, kb = (q >> 1) % nkb, c = (q >> 1) / nkb;
             const int buf = c & 1, sl = q & 1, r0 = r_first + c * LM_ROWS + 2 * hf;
-            float* ys = sYs + buf * NB + hf * NBH;
+            const int j = kb * 8 + chk;
+            const bool jok = j * 8 < Cp, st_ok = j < 2 * ksteps;
+            float* __restrict__ ys = sYs + buf * NB + hf * NBH;
             if (kb == 0 && hf == 0 && c >= 2) TR(tr_w1, mbar_wait_sleep(tmem_empty + 8 * buf, ((c >> 1) & 1) ^ 1));   // drain(c-2) has read ys[buf]
             TR(tr_w2, mbar_wait_sleep(b_empty + 8 * sl, ((q >> 1) & 1) ^ 1));
 #ifdef LM_TRACE
             long long _tb = clock64();
 #endif
             uint8_t* st_hi = sB + sl * (NBH * 256); uint8_t* st_lo = st_hi + NBH * 128;
+            // No shared-memory LOAD sits between the tasks (mu is read once up front, the norm reductions and ys updates are
+            // batched at the end): the operand stores go through byte pointers and may alias anything, so a load after
+            // them would serialise the tasks' dependent chains (measured: 800 cycles per task).
+            const float4 m0 = *reinterpret_cast<const float4*>(sMu + j * 8), m1 = *reinterpret_cast<const float4*>(sMu + j * 8 + 4);
+            float sq[LM_CONV_BATCH];
+            bool inside[LM_CONV_BATCH];
 #pragma unroll
             for (int t = 0; t < LM_CONV_BATCH; ++t) {
-                if (t < per_thread) {                                // warp-uniform
-                    const int i = ct + LM_CONV_THREADS * t;
-                    const int n = i >> 3, chk = i & 7, j = kb * 8 + chk;
-                    const int jr = n / WC, cc = n - jr * WC;
-                    const int py = r0 + jr, pxx = px0 + cc;
-                    const bool inside = (py >= 0) && (py < h) && (pxx >= 0) && (pxx < w);
-                    float sq = lm_convert_chunk(bt.a[t], bt.b[t], inside && (j * 8 < Cp), sMu + j * 8, scale, st_hi, st_lo, n, chk,
-                                                j < 2 * ksteps);
-                    sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-                    sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-                    sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-                    if (chk == 0) ys[n] = (kb == 0) ? (inside ? sq : INFINITY) : ys[n] + sq;   // outside the image: +inf -> T = 1
+                const int py = r0 + (t_row1[t] ? 1 : 0);
+                inside[t] = t_xok[t] && (py >= 0) && (py < h);
+                uint4 hi, lo;
+                sq[t] = lm_split_chunk(bt.a[t], bt.b[t], inside[t] && jok, m0, m1, scale, hi, lo);
+                if (st_ok && t < per_thread) {
+                    *reinterpret_cast<uint4*>(st_hi + t_off[t]) = hi;
+                    *reinterpret_cast<uint4*>(st_lo + t_off[t]) = lo;
                 }
+            }
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+#pragma unroll
+                for (int t = 0; t < LM_CONV_BATCH; ++t) sq[t] += __shfl_xor_sync(0xffffffffu, sq[t], o);
+            }
+            if (chk == 0) {
+                float prev[LM_CONV_BATCH];
+#pragma unroll
+                for (int t = 0; t < LM_CONV_BATCH; ++t) prev[t] = (kb != 0 && t < per_thread) ? ys[t_n[t]] : 0.f;
+#pragma unroll
+                for (int t = 0; t < LM_CONV_BATCH; ++t)
+                    if (t < per_thread) ys[t_n[t]] = (kb == 0) ? (inside[t] ? sq[t] : INFINITY) : prev[t] + sq[t];   // outside the image: +inf -> T = 1
             }
             fence_proxy_async_smem();
             mbar_arrive(b_full + 8 * sl);
@@ -610,7 +706,7 @@ lm_umma_kernel(const LmParams P) {
         const int wq = warp & 3;                                     // TMEM lane quarter this warp may read
         const int sub = ew >> 2;                                     // rows {2*sub, 2*sub+1} of every chunk
         const int m = wq * 32 + lane, qy = m >> 4, qx = m & 15;
-        const float inv = 2.0f / (scale * scale);
+        const float karg = 1.4426950408889634f / (scale * scale);   // D * log2(e) = (xs' + ys' - 2 acc) * karg  (norms are scaled by s^2)
         const int L = D2 * D2;
         // ---- this thread's unit
         const int n_units = do_cells ? min(LM_NCELL + sTab[48], LM_MAXUNITS) : 0;
@@ -628,8 +724,8 @@ lm_umma_kernel(const LmParams P) {
         float wy1[2] = {0.f, 0.f}, wx1[2] = {0.f, 0.f};
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            if (k < ny) lm_lerp(Y0 + k, h, P.H, &wy1[k]);
-            if (k < nx) lm_lerp(X0 + k, w, P.W, &wx1[k]);
+            if (k < ny) lm_lerp(Y0 + k, h, G.sy, &wy1[k]);
+            if (k < nx) lm_lerp(X0 + k, w, G.sx, &wx1[k]);
         }
         const float wy0[2] = {1.0f - wy1[0], 1.0f - wy1[1]}, wx0[2] = {1.0f - wx1[0], 1.0f - wx1[1]};
         const int dx_lo = (parts == 2 && part == 1) ? (D2 + 1) / 2 : 0;
@@ -687,9 +783,8 @@ lm_umma_kernel(const LmParams P) {
                         float tv[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            float dist = fmaf(-inv, __uint_as_float(acc[g8 * 8 + e]), xs_m + yv[e]);
-                            dist = fmaxf(dist, 0.f);
-                            tv[e] = fmaxf(sigmoid_norm_fast(dist), 0.f);
+                            // rounding can leave D (hence T) a hair below zero; the merge clamps
+                            tv[e] = lm_transform(fmaf(-2.0f, __uint_as_float(acc[g8 * 8 + e]), xs_m + yv[e]) * karg);
                         }
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
@@ -762,7 +857,7 @@ lm_umma_kernel(const LmParams P) {
                     unsigned* o = reinterpret_cast<unsigned*>(P.out) + ((size_t)Y * P.W + X) * N;
                     for (int ob = 0; ob < N; ++ob) {
                         const float v = *reinterpret_cast<volatile float*>(&sMin[(size_t)(sTab[128 + ob] * 4 + k) * LM_EPI_THREADS + et]);
-                        if (v < 1.0f) atomicMin(o + ob, __float_as_uint(v));
+                        if (v < 1.0f) atomicMin(o + ob, __float_as_uint(fmaxf(v, 0.f)));
                     }
                 }
             }
@@ -771,8 +866,10 @@ lm_umma_kernel(const LmParams P) {
 
 #ifdef LM_TRACE
     if ((blockIdx.x == 0 || blockIdx.x == 71 || blockIdx.x == 140) && lane == 0 && (warp == 0 || warp == 4 || warp == 5 || warp == 12))
-        printf("cta %d warp %d total %lld prologue %lld | wait1 %lld wait2 %lld | convB/drain %lld cells %lld (chunks %d)\n", blockIdx.x, warp,
-               clock64() - tr0, tr_pro, tr_w1, tr_w2, tr_a + tr_b, tr_c, n_chunks);
+        printf("cta %d warp %d total %lld prologue %lld | wait1 %lld wait2 %lld | loadwait/drain %lld convB %lld fence/cells %lld (chunks %d)\n", blockIdx.x, warp,
+               clock64() - tr0, tr_pro, tr_w1, tr_w2, tr_a, tr_b, tr_c, n_chunks);
+    if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 3 || warp == 4 || warp == 7 || warp == 12))
+        printf("warp %d prologue: loads issued+tables %lld, after sync1 %lld, phase2 done %lld, all %lld\n", warp, tr_t[0], tr_t[1], tr_t[2], tr_pro);
 #endif
     tc_fence_before();
     __syncthreads();
