@@ -56,7 +56,8 @@ constexpr int LM_EPI_T0 = 64;                           // warp 0: bulk-copy pro
 constexpr int LM_THREADS = LM_EPI_T0 + LM_EPI_THREADS;  // 320
 constexpr int LM_A_BYTES = 4 * 16384;                   // [hi|lo][k-block 0|1][128 rows][128 B]
 constexpr int LM_POOL_PX = 32;
-constexpr int LM_LABN = 20;                              // raw labels an epilogue thread keeps in registers across the first prologue barrier
+constexpr int LM_LABW = 6;                               // 4-byte words of the label window an epilogue thread copies
+constexpr int LM_MAXN = 64;                              // label slots are bytes; also bounds the shared-memory minima
 constexpr int LM_MU_SAMPLES = 16;                        // pool blocks whose channel sums make up mu
 
 // PyTorch upsample_bilinear2d, align_corners=True: scale=(in-1)/(out-1); src=scale*dst; i0=floor(src)
@@ -83,6 +84,7 @@ struct LmGeom {
     int h, w, Cp, ksteps, nkb, D2, WC, WB, ntx, nty;
     int XL, YT, WI, HI;                                  // padded previous-frame image: pixel (y, x) lives at (y + YT, x + XL)
     int nbx;                                             // pool blocks per row
+    int PW8;                                             // pitch of the padded label-slot image (bytes)
     int lab_rows, lab_pitch;                             // shared-memory label window (bytes)
     int max_units;
     float sy, sx;                                        // bilinear source scales (h-1)/(H-1), (w-1)/(W-1), computed once on the host
@@ -94,7 +96,7 @@ static inline int lm_round_up(int x, int a) { return (x + a - 1) / a * a; }
 
 // Everything the launch needs that depends only on the shape.  ok == false -> use the CUDA-core engine.
 static bool lm_geometry(int H, int W, int C, int N, int d, LmGeom* g) {
-    if (d < 0 || d > LM_MAXD || C < 1 || C > LM_MAXC || N < 1) return false;
+    if (d < 0 || d > LM_MAXD || C < 1 || C > LM_MAXC || N < 1 || N > LM_MAXN) return false;
     const int h = H / 2, w = W / 2;
     if (h < 3 || w < 3) return false;
     g->h = h; g->w = w;
@@ -108,9 +110,10 @@ static bool lm_geometry(int H, int W, int C, int N, int d, LmGeom* g) {
     g->ntx = (w + LM_CW - 1) / LM_CW;
     g->XL = lm_round_up(d, 8);
     g->YT = d;
-    g->WI = g->XL + lm_round_up(w + d + 30, 8);
+    g->WI = lm_round_up(g->XL + w + d + 30, 32);
     g->HI = g->YT + (g->nty - 1) * LM_CH + 2 * d + LM_TH + 10;
     g->nbx = (w + LM_POOL_PX - 1) / LM_POOL_PX;
+    g->PW8 = lm_round_up(W + 4 * d, 4);
     // worst tile: number of <=2x2 output blocks and the span of full-resolution pixels it covers
     int max_uy = 0, max_ys = 0, max_ux = 0, max_xs = 0;
     g->sy = lm_lerp_scale(h, H); g->sx = lm_lerp_scale(w, W);
@@ -139,8 +142,8 @@ static bool lm_geometry(int H, int W, int C, int N, int d, LmGeom* g) {
     g->max_units = max_uy * max_ux;
     if (g->max_units > LM_MAXUNITS || g->max_units < 1) return false;
     g->lab_rows = max_ys + 2 * d + 2;                    // (span) + 2*(ndy-1) + one spare row for the 2x2 block
-    g->lab_pitch = lm_round_up(max_xs + 4 * d + 2, 16);
-    if (g->lab_rows * g->lab_pitch > LM_LABN * LM_EPI_THREADS) return false;   // the prologue keeps the window in registers
+    g->lab_pitch = lm_round_up(max_xs + 4 * d + 2 + 3, 16);             // + 3: the window starts at a multiple of 4 columns
+    if (g->lab_rows * g->lab_pitch > 4 * LM_LABW * LM_EPI_THREADS) return false;
     int o = LM_A_BYTES;
     g->off_B = o; o += 2 * (512 * g->WB);                // 2 stages x [hi|lo][2 rows][WB columns][128 B] (one k-block of two rows)
     g->off_T = o; o += LM_TSLOTS * g->D2 * 128 * 4;
@@ -159,25 +162,38 @@ bool lm_umma_supported(int H, int W, int C, int N, int d) { LmGeom g; return lm_
 
 // ------------------------------------------------------------------------------------ pre-pass 1
 // 2x2 average pool of both frames into pixel-major [h][w][Cp] (Cp = C rounded up to 8, zero filled),
-// per-block |x| max and (query frame) channel sums, zero-padded label copy and the 1.0 fill of the output
-// (the pad value of torch.where(mask, d, ones), IntVOS.py:428-431, and the identity of the atomicMin merge).
+// per-block |x| max and (query frame) channel sums; labels -> zero-padded image of object SLOTS (bytes:
+// index of the first gt_ids entry with the same float value, IntVOS.py:406-408; N = none), and the 1.0 fill of
+// the output (the pad value of torch.where(mask, d, ones), IntVOS.py:428-431, and the identity of the atomicMin merge).
 struct LmPoolSrc { const float* p; int64_t sy, sx, sc; float* out; };
-struct LmAux { const int32_t* labels; int32_t* plabels; int H, W, pad; float* out; int64_t n_out; };
+struct LmMuBlocks { int blk[LM_MU_SAMPLES]; int count; };   // pool blocks of the query frame whose channel sums make up mu; their pixel count
+struct LmAux { const int32_t* labels; const int32_t* gt_ids; uint8_t* plab8; int H, W, pad, PW8, N; float* out; int64_t n_out; };
 
 __global__ void __launch_bounds__(256)
 lm_pool_kernel(LmPoolSrc a, LmPoolSrc b, LmAux aux, int C, int Cp, int h, int w, float* __restrict__ blkmax,
-               float* __restrict__ blksum) {
+               float* __restrict__ blksum, LmMuBlocks mub) {
     extern __shared__ float ptile[];                     // [LM_POOL_PX][Cp + 1]
     __shared__ float red[8];
+    __shared__ float sid[LM_MAXN];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (blockIdx.z == 2) {
         const int64_t nthreads = (int64_t)gridDim.x * gridDim.y * blockDim.x;
         const int64_t first = ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + t;
-        if (aux.plabels != nullptr) {
-            const int PW = aux.W + 2 * aux.pad, PH = aux.H + 2 * aux.pad;
-            for (int64_t i = first; i < (int64_t)PW * PH; i += nthreads) {
-                const int x = (int)(i % PW) - aux.pad, y = (int)(i / PW) - aux.pad;
-                aux.plabels[i] = (x >= 0 && x < aux.W && y >= 0 && y < aux.H) ? aux.labels[(int64_t)y * aux.W + x] : 0;
+        if (aux.plab8 != nullptr) {
+            if (t < aux.N) sid[t] = (float)__ldg(aux.gt_ids + t);
+            __syncthreads();
+            const int PW8 = aux.PW8, PH = aux.H + 2 * aux.pad, N = aux.N;
+            int slot0 = N;                               // slot of label 0 (outside the frame)
+            for (int o = N - 1; o >= 0; --o) if (sid[o] == 0.f) slot0 = o;
+            for (int64_t i = first; i < (int64_t)PW8 * PH; i += nthreads) {
+                const int x = (int)(i % PW8) - aux.pad, y = (int)(i / PW8) - aux.pad;
+                int slot = slot0;
+                if (x >= 0 && x < aux.W && y >= 0 && y < aux.H) {
+                    const float lf = (float)__ldg(aux.labels + (int64_t)y * aux.W + x);
+                    slot = N;
+                    for (int o = N - 1; o >= 0; --o) if (sid[o] == lf) slot = o;
+                }
+                aux.plab8[i] = (uint8_t)slot;
             }
         }
         if (aux.out != nullptr)
@@ -188,29 +204,42 @@ lm_pool_kernel(LmPoolSrc a, LmPoolSrc b, LmAux aux, int C, int Cp, int h, int w,
     const int y = blockIdx.y, x0 = blockIdx.x * LM_POOL_PX, x = x0 + lane;
     const int pitch = Cp + 1;
     const bool vec = (s.sx == 1) && ((s.sy & 1) == 0) && ((s.sc & 1) == 0) && ((reinterpret_cast<uintptr_t>(s.p) & 7) == 0);
-    float amax = 0.f;
-    float* bsum = blksum + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * Cp;
-    for (int c = warp; c < Cp; c += 8) {
-        float v = 0.f;
-        if (c < C && x < w) {
-            const float* p = s.p + (int64_t)c * s.sc + (int64_t)(2 * y) * s.sy + (int64_t)(2 * x) * s.sx;
-            float sum;                                   // torch avg_pool2d: row-major window sum, then / 4
-            if (vec) {
-                const float2 r0 = __ldg(reinterpret_cast<const float2*>(p));
-                const float2 r1 = __ldg(reinterpret_cast<const float2*>(p + s.sy));
-                sum = r0.x + r0.y; sum += r1.x; sum += r1.y;
-            } else {
-                sum = __ldg(p) + __ldg(p + s.sx); sum += __ldg(p + s.sy); sum += __ldg(p + s.sy + s.sx);
-            }
-            v = sum / 4.0f;
-        }
-        ptile[lane * pitch + c] = v;
-        amax = fmaxf(amax, fabsf(v));
-        if (blockIdx.z == 0) {                           // channel sum over the block's pixels (fixed order: deterministic)
-            float cs = v;
+    bool want_sum = false;
+    {
+        const int me = blockIdx.y * gridDim.x + blockIdx.x;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, o);
-            if (lane == 0) bsum[c] = cs;
+        for (int k = 0; k < LM_MU_SAMPLES; ++k) want_sum = want_sum || (mub.blk[k] == me);
+    }
+    float amax = 0.f;
+    const int K = (Cp + 7) >> 3;                         // channels per warp: c = warp + 8 k
+    const float* px = s.p + (int64_t)(2 * y) * s.sy + (int64_t)(2 * x) * s.sx;
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        // all loads of the batch first (16 x 8 bytes in flight per thread), then the arithmetic
+        float2 r0[8], r1[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = warp + 8 * (k0 + i);
+            r0[i] = r1[i] = make_float2(0.f, 0.f);
+            if (c < C && x < w) {
+                const float* p = px + (int64_t)c * s.sc;
+                if (vec) {
+                    r0[i] = __ldg(reinterpret_cast<const float2*>(p));
+                    r1[i] = __ldg(reinterpret_cast<const float2*>(p + s.sy));
+                } else {
+                    r0[i] = make_float2(__ldg(p), __ldg(p + s.sx));
+                    r1[i] = make_float2(__ldg(p + s.sy), __ldg(p + s.sy + s.sx));
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = warp + 8 * (k0 + i);
+            if (c < Cp) {                                // warp-uniform
+                float sum = r0[i].x + r0[i].y; sum += r1[i].x; sum += r1[i].y;   // torch avg_pool2d: row-major window sum, then / 4
+                const float v = sum / 4.0f;
+                ptile[lane * pitch + c] = v;
+                amax = fmaxf(amax, fabsf(v));
+            }
         }
     }
 #pragma unroll
@@ -219,7 +248,20 @@ lm_pool_kernel(LmPoolSrc a, LmPoolSrc b, LmAux aux, int C, int Cp, int h, int w,
     __syncthreads();
     const int npx = min(LM_POOL_PX, w - x0);
     float* dst = s.out + ((int64_t)y * w + x0) * Cp;
-    for (int i = t; i < npx * Cp; i += 256) dst[i] = ptile[(i / Cp) * pitch + (i % Cp)];
+    if (lane * 4 < Cp) {                                 // Cp <= 128: a lane owns 4 consecutive channels (Cp is a multiple of 8)
+#pragma unroll
+        for (int p = warp; p < LM_POOL_PX; p += 8) {
+            if (p < npx) {
+                const float* src = ptile + p * pitch + lane * 4;
+                *reinterpret_cast<float4*>(dst + (size_t)p * Cp + lane * 4) = make_float4(src[0], src[1], src[2], src[3]);
+            }
+        }
+    }
+    if (blockIdx.z == 0 && want_sum && t < Cp) {         // channel sums of the block's pixels (fixed order: deterministic)
+        float cs = 0.f;
+        for (int p = 0; p < LM_POOL_PX; ++p) cs += ptile[p * pitch + t];
+        blksum[((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * Cp + t] = cs;
+    }
     if (t == 0) {
         float m = red[0];
         for (int k = 1; k < 8; ++k) m = fmaxf(m, red[k]);
@@ -237,15 +279,17 @@ __device__ __forceinline__ float lm_pow2_scale(float a) {
 // ------------------------------------------------------------------------------------ pre-pass 2
 // Operand images.  Every (pixel, 8-channel chunk): x*s - mu*s -> fp16 hi + lo, written at the K-major
 // SWIZZLE_128B position of the pixel's row (16-byte chunk index XOR row % 8), plus the squared norm of the
-// scaled centred vector.
-//   blockIdx.y == 0: previous frame, one block per padded image row iy (pixel row iy - YT):
+// scaled centred vector.  One block = 32 pixels x 16 chunks, a thread owns chunk t%8 of both k-blocks.
+//   blocks [0, HI * WI/32): previous frame, 32 columns of the padded image row iy (pixel row iy - YT):
 //       Bimg[iy][kb][hi|lo][ix][128 B], Ys[iy][ix] (+inf outside the frame -> T = 1, IntVOS.py:287-294)
-//   blockIdx.y == 1: query frame, one block per tile: Aimg[tile][hi|lo][kb][128 pixels][128 B], Xs[tile][128]
+//   then 4 blocks per tile: query frame, Aimg[tile][hi|lo][kb][128 pixels][128 B], Xs[tile][128]
+// Block 0 also publishes the scale for the main kernel.
 struct LmConvParams {
     const float* Pq; const float* Pp;                    // pooled [h][w][Cp]
     const float* blkmax; int n_blkmax;
     const float* blksum;                                 // [h * nbx][Cp] channel sums of the query frame's pool blocks
-    uint8_t* Aimg; float* Xs; uint8_t* Bimg; float* Ys;
+    uint8_t* Aimg; float* Xs; uint8_t* Bimg; float* Ys; float* stats;
+    LmMuBlocks mub;
     LmGeom g;
 };
 
@@ -270,106 +314,92 @@ __device__ __forceinline__ float lm_split8(float4 a, float4 b, float4 m0, float4
 __global__ void __launch_bounds__(256)
 lm_convert_kernel(const LmConvParams P) {
     const LmGeom& G = P.g;
-    __shared__ float sMu[LM_MAXC];                       // mu * s
+    __shared__ __align__(16) float sMu[LM_MAXC];         // mu * s
     __shared__ float red[8];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int h = G.h, w = G.w, Cp = G.Cp;
-    const bool is_b = blockIdx.y == 0;
-    if (is_b ? ((int)blockIdx.x >= G.HI) : ((int)blockIdx.x >= G.ntx * G.nty)) return;
-    // scale: power of two from the largest |x| of both pooled frames
+    const int chk = t & 7, pr = t >> 3;
+    const int XS = G.WI >> 5, nB = G.HI * XS;
+    const bool is_b = (int)blockIdx.x < nB;
+    // ---- this thread's pixel; its loads go out first (they do not depend on the statistics)
+    int iy = 0, ix = 0, tile = 0, row = 0;
+    bool inside;
+    const float* src;
+    if (is_b) {
+        iy = blockIdx.x / XS; ix = (blockIdx.x % XS) * 32 + pr;
+        const int py = iy - G.YT, px = ix - G.XL;
+        inside = (py >= 0) && (py < h) && (px >= 0) && (px < w);
+        src = P.Pp + ((size_t)py * w + px) * Cp;
+    } else {
+        const int bb = blockIdx.x - nB;
+        tile = bb >> 2; row = (bb & 3) * 32 + pr;
+        const int y = (tile / G.ntx) * LM_CH + (row >> 4), x = (tile % G.ntx) * LM_CW + (row & 15);
+        inside = (y < h) && (x < w);
+        src = P.Pq + ((size_t)y * w + x) * Cp;
+    }
+    float4 va[2], vb[2];
+    bool ok[2];
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb) {
+        const int j = kb * 8 + chk;
+        ok[kb] = inside && (j * 8 < Cp) && (kb < G.nkb);
+        va[kb] = vb[kb] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok[kb]) { va[kb] = __ldg(reinterpret_cast<const float4*>(src + j * 8)); vb[kb] = __ldg(reinterpret_cast<const float4*>(src + j * 8 + 4)); }
+    }
+    // ---- scale: power of two from the largest |x| of both pooled frames
     float m = 0.f;
     for (int i = t; i < P.n_blkmax; i += 256) m = fmaxf(m, __ldg(P.blkmax + i));
+    // mu: mean of LM_MU_SAMPLES pool blocks spread evenly over the query frame (any common vector is exact; a
+    // representative one keeps the cancelling terms small)
+    float mu = 0.f;
+    if (t < Cp) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < LM_MU_SAMPLES; ++k) a += __ldg(P.blksum + (size_t)P.mub.blk[k] * Cp + t);
+        mu = a / (float)P.mub.count;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) red[warp] = m;
-    // mu: mean of LM_MU_SAMPLES pool blocks spread evenly over the query frame (any common vector is exact; a
-    // representative one keeps the cancelling terms small)
-    const int nblk = h * G.nbx;
-    if (t < LM_MAXC) {
-        float a = 0.f; int cnt = 0;
-        if (t < Cp) {
-            for (int k = 0; k < LM_MU_SAMPLES; ++k) {
-                const int blk = (int)(((int64_t)(2 * k + 1) * nblk) / (2 * LM_MU_SAMPLES));
-                a += __ldg(P.blksum + (int64_t)blk * Cp + t);
-                cnt += min(LM_POOL_PX, w - (blk % G.nbx) * LM_POOL_PX);
-            }
-        }
-        sMu[t] = (t < Cp) ? a / (float)cnt : 0.f;
-    }
     __syncthreads();
     m = red[0];
 #pragma unroll
     for (int k = 1; k < 8; ++k) m = fmaxf(m, red[k]);
     const float s = lm_pow2_scale(m);
-    __syncthreads();
-    if (t < LM_MAXC) sMu[t] *= s;
+    if (t < LM_MAXC) sMu[t] = mu * s;
+    if (blockIdx.x == 0 && t == 0) P.stats[0] = s;
     __syncthreads();
 
-    const int chk = t & 7;
-    if (is_b) {
-        const int iy = blockIdx.x, py = iy - G.YT;
-        const bool row_in = (py >= 0) && (py < h);
-        uint8_t* rowimg = P.Bimg + (size_t)iy * G.nkb * 2 * G.WI * 128;
-        for (int kb = 0; kb < G.nkb; ++kb) {
+    float sq = 0.f;
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb) {
+        if (kb < G.nkb) {
             const int j = kb * 8 + chk;
             const bool jok = j * 8 < Cp;
             const float4 m0 = jok ? *reinterpret_cast<const float4*>(sMu + j * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 m1 = jok ? *reinterpret_cast<const float4*>(sMu + j * 8 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int ix = t >> 3; ix < G.WI; ix += 32) {
-                const int px = ix - G.XL;
-                const bool inside = row_in && (px >= 0) && (px < w);
-                float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
-                if (inside && jok) {
-                    const float4* src = reinterpret_cast<const float4*>(P.Pp + ((size_t)py * w + px) * Cp + j * 8);
-                    va = __ldg(src); vb = __ldg(src + 1);
-                }
-                uint4 hi, lo;
-                float sq = lm_split8(va, vb, m0, m1, s, hi, lo);
-                if (!(inside && jok)) { hi = make_uint4(0u, 0u, 0u, 0u); lo = hi; sq = 0.f; }
+            uint4 hi, lo;
+            const float q = lm_split8(va[kb], vb[kb], m0, m1, s, hi, lo);
+            if (ok[kb]) sq += q; else { hi = make_uint4(0u, 0u, 0u, 0u); lo = hi; }
+            if (is_b) {
+                uint8_t* rowimg = P.Bimg + (size_t)iy * G.nkb * 2 * G.WI * 128;
                 const size_t o = (size_t)ix * 128 + ((chk ^ (ix & 7)) << 4);
                 *reinterpret_cast<uint4*>(rowimg + (size_t)(kb * 2 + 0) * G.WI * 128 + o) = hi;
                 *reinterpret_cast<uint4*>(rowimg + (size_t)(kb * 2 + 1) * G.WI * 128 + o) = lo;
-                sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-                sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-                sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-                if (chk == 0) {
-                    float* ys = P.Ys + (size_t)iy * G.WI + ix;
-                    *ys = (kb == 0) ? (inside ? sq : INFINITY) : *ys + sq;
-                }
-            }
-        }
-    } else {
-        const int tile = blockIdx.x, ty = tile / G.ntx, tx = tile % G.ntx;
-        const int qy0 = ty * LM_CH, qx0 = tx * LM_CW;
-        uint8_t* img = P.Aimg + (size_t)tile * LM_A_BYTES;
-        for (int kb = 0; kb < 2; ++kb) {
-            const int j = kb * 8 + chk;
-            const bool jok = (j * 8 < Cp) && (kb < G.nkb);
-            const float4 m0 = jok ? *reinterpret_cast<const float4*>(sMu + j * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 m1 = jok ? *reinterpret_cast<const float4*>(sMu + j * 8 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int row = t >> 3; row < 128; row += 32) {
-                const int y = qy0 + (row >> 4), x = qx0 + (row & 15);
-                const bool inside = (y < h) && (x < w);
-                float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
-                if (inside && jok) {
-                    const float4* src = reinterpret_cast<const float4*>(P.Pq + ((size_t)y * w + x) * Cp + j * 8);
-                    va = __ldg(src); vb = __ldg(src + 1);
-                }
-                uint4 hi, lo;
-                float sq = lm_split8(va, vb, m0, m1, s, hi, lo);
-                if (!(inside && jok)) { hi = make_uint4(0u, 0u, 0u, 0u); lo = hi; sq = 0.f; }
+            } else {
+                uint8_t* img = P.Aimg + (size_t)tile * LM_A_BYTES;
                 const int o = (row >> 3) * 1024 + (row & 7) * 128 + ((chk ^ (row & 7)) << 4);
                 *reinterpret_cast<uint4*>(img + kb * 16384 + o) = hi;
                 *reinterpret_cast<uint4*>(img + 2 * 16384 + kb * 16384 + o) = lo;
-                sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-                sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-                sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-                if (chk == 0) {
-                    float* xs = P.Xs + (size_t)tile * 128 + row;
-                    *xs = (kb == 0) ? sq : *xs + sq;
-                }
             }
         }
+    }
+    sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+    sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+    sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+    if (chk == 0) {
+        if (is_b) P.Ys[(size_t)iy * G.WI + ix] = inside ? sq : INFINITY;
+        else P.Xs[(size_t)tile * 128 + row] = sq;
     }
 }
 
@@ -377,8 +407,8 @@ lm_convert_kernel(const LmConvParams P) {
 struct LmParams {
     const uint8_t* Aimg; const float* Xs;                // query operand images / norms per tile
     const uint8_t* Bimg; const float* Ys;                // previous-frame padded operand image / norms
-    const float* blkmax; int n_blkmax;
-    const int32_t* plabels;                              // zero-padded labels [(H+4d)][(W+4d)] (null: volume only)
+    const float* stats;                                  // [0] = operand scale (lm_convert_kernel)
+    const uint8_t* plab8;                                // zero-padded label slots [(H+4d)][PW8] bytes (null: volume only)
     const int32_t* gt_ids;
     float* out;                                          // [H][W][N], pre-filled with 1.0 (null: volume only)
     float* T_vol;                                        // optional [h][w][L] dump of the transformed distances
@@ -457,7 +487,7 @@ lm_umma_kernel(const LmParams P) {
     int2* sUnits = reinterpret_cast<int2*>(smem + G.off_units);
     int* sTab = reinterpret_cast<int*>(smem + G.off_tab);
     // sTab: [0..7] rowY0, [8..15] rowNy, [16..31] colX0, [32..47] colNx, [48] extra-unit counter,
-    //       [50] tmem slot, [52..59] per-warp |x| max, [64..64+N) slot ids, [128..128+N) canonical slot
+    //       [50] tmem slot, [64..64+N) slot ids, [128..128+N) canonical slot
     const uint32_t bars = base + G.off_bar;
     const uint32_t a_full = bars + 0;
     const uint32_t b_full = bars + 8;          // [2]  stage landed (bulk copies)
@@ -488,27 +518,33 @@ lm_umma_kernel(const LmParams P) {
     // ------------------------------------------------------------------ epilogue prologue, part 1: every global load is issued
     // before the first barrier (|x| max blocks, label window, ids)
     const int et = tid - LM_EPI_T0;
-    int lab_raw[LM_LABN];
     const int lab_total = do_cells ? G.lab_rows * G.lab_pitch : 0;
+    const int Ymin = lm_first_out(qy0, h, P.H, G.sy), Xmin = lm_first_out(qx0, w, P.W, G.sx);
+    const int Xal = Xmin & ~3;                                       // the label window starts at a multiple of 4 columns
+    float scale = 1.0f;
     if (warp >= 2) {
-        const int Ymin = lm_first_out(qy0, h, P.H, G.sy), Xmin = lm_first_out(qx0, w, P.W, G.sx);
         if (do_cells) {
-            // label window origin in the zero-padded label image: (Ymin + 2*dyA, Xmin)
-            const int PW = P.W + 4 * d, PH = P.H + 4 * d;
+            // label window origin in the zero-padded slot image: (Ymin + 2*dyA, Xal); 4 slots per load
+            const int PH = P.H + 4 * d, LPW = G.lab_pitch >> 2;
+            uint32_t wv[LM_LABW];
 #pragma unroll
-            for (int t = 0; t < LM_LABN; ++t) {
+            for (int t = 0; t < LM_LABW; ++t) {
                 const int i = et + t * LM_EPI_THREADS;
-                const int ry = i / G.lab_pitch, rx = i - ry * G.lab_pitch;
-                const int yy = Ymin + 2 * dyA + ry, xx = Xmin + rx;
-                lab_raw[t] = INT_MIN;
-                if (i < lab_total && yy < PH && xx < PW) lab_raw[t] = __ldg(P.plabels + (size_t)yy * PW + xx);
+                const int ry = i / LPW, rx = (i - ry * LPW) * 4;
+                const int yy = Ymin + 2 * dyA + ry, xx = Xal + rx;
+                wv[t] = 0x01010101u * (uint32_t)N;
+                if (4 * i < lab_total && yy < PH && xx + 3 < G.PW8)
+                    wv[t] = __ldg(reinterpret_cast<const uint32_t*>(P.plab8 + (size_t)yy * G.PW8 + xx));
             }
-        }
-        float m = 0.f;
-        for (int i = et; i < P.n_blkmax; i += LM_EPI_THREADS) m = fmaxf(m, __ldg(P.blkmax + i));
+            scale = __ldg(P.stats);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0) reinterpret_cast<float*>(sTab)[52 + (warp - 2)] = m;
+            for (int t = 0; t < LM_LABW; ++t) {
+                const int i = et + t * LM_EPI_THREADS;
+                if (4 * i < lab_total) reinterpret_cast<uint32_t*>(sLab)[i] = wv[t];
+            }
+        } else {
+            scale = __ldg(P.stats);
+        }
         // bilinear tables: for every cell row / column of this tile the first output index and the count
         if (et < LM_CH) {
             const int y0 = qy0 + et;
@@ -525,6 +561,8 @@ lm_umma_kernel(const LmParams P) {
         } else if (et >= 96 && et < 96 + N && do_cells) {
             sTab[64 + (et - 96)] = __ldg(P.gt_ids + (et - 96));
         }
+        if (do_cells)
+            for (int i = et; i < (N + 1) * 4 * LM_EPI_THREADS; i += LM_EPI_THREADS) sMin[i] = 1.0f;
     }
     tc_fence_before();
     __syncthreads();
@@ -603,11 +641,7 @@ lm_umma_kernel(const LmParams P) {
         }
     } else {
         // ------------------------------------------------------------------ epilogue prologue, part 2
-        float scale;
         {
-            float m = 0.f;
-            for (int k = 0; k < LM_EPI_WARPS; ++k) m = fmaxf(m, reinterpret_cast<const float*>(sTab)[52 + k]);
-            scale = lm_pow2_scale(m);
             // slot of an id = the first gt_ids entry holding the same (float-compared) value (IntVOS.py:406-408)
             if (et >= LM_EPI_THREADS - 32 && et < LM_EPI_THREADS - 32 + N && do_cells) {
                 const int o = et - (LM_EPI_THREADS - 32);
@@ -630,22 +664,6 @@ lm_umma_kernel(const LmParams P) {
                                                         (Y0 + 2 * by) | ((X0 + 2 * bx) << 16));
                         }
                 }
-            }
-            if (do_cells) {
-                // label window -> slot bytes
-#pragma unroll
-                for (int t = 0; t < LM_LABN; ++t) {
-                    const int i = et + t * LM_EPI_THREADS;
-                    if (i < lab_total) {
-                        int slot = N;
-                        if (lab_raw[t] != INT_MIN) {
-                            const float lf = (float)lab_raw[t];
-                            for (int o = N - 1; o >= 0; --o) if (lf == (float)sTab[64 + o]) slot = o;
-                        }
-                        sLab[i] = (uint8_t)slot;
-                    }
-                }
-                for (int i = et; i < (N + 1) * 4 * LM_EPI_THREADS; i += LM_EPI_THREADS) sMin[i] = 1.0f;
             }
         }
         epi_bar_sync();
@@ -682,7 +700,7 @@ lm_umma_kernel(const LmParams P) {
         const int dx_lo = (parts == 2 && part == 1) ? (D2 + 1) / 2 : 0;
         const int dx_hi = (parts == 2 && part == 0) ? (D2 + 1) / 2 : D2;
         const int LP = G.lab_pitch;
-        const uint8_t* lab0 = sLab + (Y0 - sTab[0]) * LP + (X0 - sTab[16]);
+        const uint8_t* lab0 = sLab + (Y0 - Ymin) * LP + (X0 - Xal);
         // minima: [slot][output k][thread]; outputs this unit does not have go to the spare slot N
         uint32_t min_base[4]; int min_stride[4];
 #pragma unroll
@@ -835,7 +853,7 @@ size_t lm_umma_workspace_bytes(int H, int W, int C, int d) {
     const size_t L = (size_t)g.D2 * g.D2;
     return 2 * align_up((size_t)g.h * g.w * g.Cp * sizeof(float), 256) + align_up((size_t)8192 * sizeof(float), 256) +
            align_up((size_t)g.h * g.nbx * g.Cp * sizeof(float), 256) +
-           align_up((size_t)(H + 4 * d) * (W + 4 * d) * sizeof(int32_t), 256) +
+           align_up((size_t)(H + 4 * d) * g.PW8, 256) + 256 +
            align_up((size_t)g.h * g.w * L * sizeof(float), 256) +
            align_up((size_t)g.ntx * g.nty * LM_A_BYTES, 256) + align_up((size_t)g.ntx * g.nty * 128 * sizeof(float), 256) +
            align_up(lm_img_bytes_b(g), 256) + align_up((size_t)g.HI * g.WI * sizeof(float), 256) + 2048;
@@ -859,23 +877,31 @@ int launch_local_match_umma(const float* prev, int64_t p_sy, int64_t p_sx, int64
     float* Pp = cv.take<float>((size_t)g.h * g.w * g.Cp);
     float* blkmax = cv.take<float>(8192);
     float* blksum = cv.take<float>((size_t)g.h * g.nbx * g.Cp);
-    int32_t* plab = cv.take<int32_t>((size_t)(H + 4 * d) * (W + 4 * d));
+    uint8_t* plab8 = cv.take<uint8_t>((size_t)(H + 4 * d) * g.PW8);
+    float* stats = cv.take<float>(16);
     float* Tvol = cv.take<float>((size_t)g.h * g.w * g.D2 * g.D2);
     uint8_t* Aimg = cv.take<uint8_t>((size_t)n_tiles * LM_A_BYTES, 1024);
     float* Xs = cv.take<float>((size_t)n_tiles * 128);
     uint8_t* Bimg = cv.take<uint8_t>(lm_img_bytes_b(g), 1024);
     float* Ys = cv.take<float>((size_t)g.HI * g.WI);
     LmPoolSrc a{query, q_sy, q_sx, q_sc, Pq}, b{prev, p_sy, p_sx, p_sc, Pp};
-    LmAux aux{labels, labels ? plab : nullptr, H, W, 2 * d, labels ? out : nullptr, (int64_t)H * W * N};
+    LmAux aux{labels, gt_ids, labels ? plab8 : nullptr, H, W, 2 * d, g.PW8, N, labels ? out : nullptr, (int64_t)H * W * N};
     const size_t pool_smem = (size_t)LM_POOL_PX * (g.Cp + 1) * sizeof(float);
-    lm_pool_kernel<<<dim3(g.nbx, g.h, 3), 256, pool_smem, stream>>>(a, b, aux, C, g.Cp, g.h, g.w, blkmax, blksum);
+    LmMuBlocks mub;
+    mub.count = 0;
+    for (int k = 0; k < LM_MU_SAMPLES; ++k) {           // evenly spread over the query frame (duplicates are harmless)
+        mub.blk[k] = (int)(((int64_t)(2 * k + 1) * g.h * g.nbx) / (2 * LM_MU_SAMPLES));
+        const int rest = g.w - (mub.blk[k] % g.nbx) * LM_POOL_PX;
+        mub.count += rest < LM_POOL_PX ? rest : LM_POOL_PX;
+    }
+    lm_pool_kernel<<<dim3(g.nbx, g.h, 3), 256, pool_smem, stream>>>(a, b, aux, C, g.Cp, g.h, g.w, blkmax, blksum, mub);
     LmConvParams CP;
     memset(&CP, 0, sizeof(CP));
     CP.Pq = Pq; CP.Pp = Pp; CP.blkmax = blkmax; CP.n_blkmax = n_blk; CP.blksum = blksum;
-    CP.Aimg = Aimg; CP.Xs = Xs; CP.Bimg = Bimg; CP.Ys = Ys; CP.g = g;
-    lm_convert_kernel<<<dim3(g.HI > n_tiles ? g.HI : n_tiles, 2), 256, 0, stream>>>(CP);
-    P.Aimg = Aimg; P.Xs = Xs; P.Bimg = Bimg; P.Ys = Ys; P.blkmax = blkmax; P.n_blkmax = n_blk;
-    P.plabels = labels ? plab : nullptr; P.gt_ids = gt_ids; P.out = labels ? out : nullptr;
+    CP.Aimg = Aimg; CP.Xs = Xs; CP.Bimg = Bimg; CP.Ys = Ys; CP.stats = stats; CP.mub = mub; CP.g = g;
+    lm_convert_kernel<<<g.HI * (g.WI >> 5) + 4 * n_tiles, 256, 0, stream>>>(CP);
+    P.Aimg = Aimg; P.Xs = Xs; P.Bimg = Bimg; P.Ys = Ys; P.stats = stats;
+    P.plab8 = labels ? plab8 : nullptr; P.gt_ids = gt_ids; P.out = labels ? out : nullptr;
     P.T_vol = T_out ? Tvol : nullptr;
     P.H = H; P.W = W; P.C = C; P.N = labels ? N : 1; P.d = d;
     static bool attr_set = false;
