@@ -46,14 +46,17 @@ constexpr int LM_TH = 8, LM_TW = 16;                    // query tile (half-res 
 constexpr int LM_CH = LM_TH - 1, LM_CW = LM_TW - 1;     // bilinear cells per tile
 constexpr int LM_NCELL = LM_CH * LM_CW;                 // 105
 constexpr int LM_ROWS = 4;                              // previous-frame rows per chunk
-constexpr int LM_TSLOTS = LM_ROWS + 1;                  // + the last row of the previous chunk
+constexpr int LM_TSLOTS = 5;                            // ring of transformed rows between the drain and the cells warps
 constexpr int LM_MAXD = 12;
 constexpr int LM_MAXC = 128;
 constexpr int LM_MAXUNITS = 256;
-constexpr int LM_EPI_WARPS = 8;
+constexpr int LM_FREE_SLOTS = 23;                       // unit slots of the first 128 not taken by a cell's first block
+constexpr int LM_DRAIN_WARPS = 4;                       // one per TMEM lane quarter
+constexpr int LM_DRAIN_T0 = 64;                         // warp 0: bulk-copy producer, warp 1: MMA issuer
+constexpr int LM_EPI_WARPS = 8;                         // "cells" warps
 constexpr int LM_EPI_THREADS = 32 * LM_EPI_WARPS;       // 256
-constexpr int LM_EPI_T0 = 64;                           // warp 0: bulk-copy producer, warp 1: MMA issuer
-constexpr int LM_THREADS = LM_EPI_T0 + LM_EPI_THREADS;  // 320
+constexpr int LM_EPI_T0 = LM_DRAIN_T0 + 32 * LM_DRAIN_WARPS;   // 192
+constexpr int LM_THREADS = LM_EPI_T0 + LM_EPI_THREADS;  // 448
 constexpr int LM_A_BYTES = 4 * 16384;                   // [hi|lo][k-block 0|1][128 rows][128 B]
 constexpr int LM_POOL_PX = 32;
 constexpr int LM_LABW = 6;                               // 4-byte words of the label window an epilogue thread copies
@@ -92,7 +95,7 @@ struct LmGeom {
     int off_B, off_T, off_min, off_lab, off_ys, off_xs, off_units, off_tab, off_bar, total;
 };
 
-static inline int lm_round_up(int x, int a) { return (x + a - 1) / a * a; }
+__host__ __device__ static inline int lm_round_up(int x, int a) { return (x + a - 1) / a * a; }
 
 // Everything the launch needs that depends only on the shape.  ok == false -> use the CUDA-core engine.
 static bool lm_geometry(int H, int W, int C, int N, int d, LmGeom* g) {
@@ -148,12 +151,12 @@ static bool lm_geometry(int H, int W, int C, int N, int d, LmGeom* g) {
     g->off_B = o; o += 2 * (512 * g->WB);                // 2 stages x [hi|lo][2 rows][WB columns][128 B] (one k-block of two rows)
     g->off_T = o; o += LM_TSLOTS * g->D2 * 128 * 4;
     g->off_min = o; o += (N + 1) * 4 * LM_EPI_THREADS * 4;
-    g->off_lab = o; o += lm_round_up(g->lab_rows * g->lab_pitch, 16);
+    g->off_lab = o; o += 2 * (lm_round_up(g->lab_rows * g->lab_pitch, 16) + 16);   // byte table + the same shifted by one byte (aligned 16-bit pair loads)
     g->off_ys = o; o += 2 * LM_ROWS * g->WB * 4;
     g->off_xs = o; o += 128 * 4;
     g->off_units = o; o += LM_MAXUNITS * 8;
     g->off_tab = o; o += 1024;
-    g->off_bar = o; o += 128;
+    g->off_bar = o; o += 256;
     g->total = o + 1024;                                 // slack: the base is aligned to 1024 bytes
     return g->total <= 227 * 1024;
 }
@@ -492,9 +495,11 @@ lm_umma_kernel(const LmParams P) {
     const uint32_t a_full = bars + 0;
     const uint32_t b_full = bars + 8;          // [2]  stage landed (bulk copies)
     const uint32_t b_empty = bars + 24;        // [2]  stage consumed by the MMAs
-    const uint32_t tmem_full = bars + 40;      // [2]
-    const uint32_t tmem_empty = bars + 56;     // [2]
-    const uint32_t ys_full = bars + 72;        // [2]
+    const uint32_t tmem_full = bars + 40;      // [2 buffers][2 row pairs]
+    const uint32_t tmem_empty = bars + 72;     // [2]
+    const uint32_t ys_full = bars + 88;        // [2]
+    const uint32_t t_full = bars + 104;        // [LM_TSLOTS]  row of T written by the four drain warps
+    const uint32_t t_empty = bars + 144;       // [LM_TSLOTS]  row of T no longer needed by the cells warps
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef LM_TRACE
@@ -506,70 +511,26 @@ lm_umma_kernel(const LmParams P) {
             mbar_init(a_full, 1);
             for (int i = 0; i < 2; ++i) {
                 mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1);
-                mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, LM_EPI_WARPS);
+                mbar_init(tmem_full + 16 * i, 1); mbar_init(tmem_full + 16 * i + 8, 1); mbar_init(tmem_empty + 8 * i, LM_DRAIN_WARPS);
                 mbar_init(ys_full + 8 * i, 1);
             }
+            for (int i = 0; i < LM_TSLOTS; ++i) { mbar_init(t_full + 8 * i, LM_DRAIN_WARPS); mbar_init(t_empty + 8 * i, LM_EPI_WARPS); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sTab[50])), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // ------------------------------------------------------------------ epilogue prologue, part 1: every global load is issued
-    // before the first barrier (|x| max blocks, label window, ids)
     const int et = tid - LM_EPI_T0;
     const int lab_total = do_cells ? G.lab_rows * G.lab_pitch : 0;
-    const int Ymin = lm_first_out(qy0, h, P.H, G.sy), Xmin = lm_first_out(qx0, w, P.W, G.sx);
-    const int Xal = Xmin & ~3;                                       // the label window starts at a multiple of 4 columns
-    float scale = 1.0f;
-    if (warp >= 2) {
-        if (do_cells) {
-            // label window origin in the zero-padded slot image: (Ymin + 2*dyA, Xal); 4 slots per load
-            const int PH = P.H + 4 * d, LPW = G.lab_pitch >> 2;
-            uint32_t wv[LM_LABW];
-#pragma unroll
-            for (int t = 0; t < LM_LABW; ++t) {
-                const int i = et + t * LM_EPI_THREADS;
-                const int ry = i / LPW, rx = (i - ry * LPW) * 4;
-                const int yy = Ymin + 2 * dyA + ry, xx = Xal + rx;
-                wv[t] = 0x01010101u * (uint32_t)N;
-                if (4 * i < lab_total && yy < PH && xx + 3 < G.PW8)
-                    wv[t] = __ldg(reinterpret_cast<const uint32_t*>(P.plab8 + (size_t)yy * G.PW8 + xx));
-            }
-            scale = __ldg(P.stats);
-#pragma unroll
-            for (int t = 0; t < LM_LABW; ++t) {
-                const int i = et + t * LM_EPI_THREADS;
-                if (4 * i < lab_total) reinterpret_cast<uint32_t*>(sLab)[i] = wv[t];
-            }
-        } else {
-            scale = __ldg(P.stats);
-        }
-        // bilinear tables: for every cell row / column of this tile the first output index and the count
-        if (et < LM_CH) {
-            const int y0 = qy0 + et;
-            int a = 0, n = 0;
-            if (y0 < h) { a = lm_first_out(y0, h, P.H, G.sy); n = lm_first_out(y0 + 1, h, P.H, G.sy) - a; }
-            sTab[et] = a; sTab[8 + et] = n;
-        } else if (et >= 32 && et < 32 + LM_CW) {
-            const int c = et - 32, x0 = qx0 + c;
-            int a = 0, n = 0;
-            if (x0 < w) { a = lm_first_out(x0, w, P.W, G.sx); n = lm_first_out(x0 + 1, w, P.W, G.sx) - a; }
-            sTab[16 + c] = a; sTab[32 + c] = n;
-        } else if (et == 64) {
-            sTab[48] = 0;
-        } else if (et >= 96 && et < 96 + N && do_cells) {
-            sTab[64 + (et - 96)] = __ldg(P.gt_ids + (et - 96));
-        }
-        if (do_cells)
-            for (int i = et; i < (N + 1) * 4 * LM_EPI_THREADS; i += LM_EPI_THREADS) sMin[i] = 1.0f;
-    }
+    const int lab_table = lm_round_up(lab_total, 16) + 16;           // bytes per label table
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&sTab[50]);
     const int ksteps = G.ksteps, nkb = G.nkb;
-    const int n_stages = n_chunks * nkb * 2;                         // B stage = (chunk, k-block, pair of rows)
+    const int n_stages = n_chunks * nkb * 2;                         // B stage = (chunk, pair of rows, k-block)
+    const int n_trows = n_chunks * LM_ROWS;                          // rows of T that pass through the ring
     const uint32_t stage_bytes = 512u * (uint32_t)WB, row_bytes = 128u * (uint32_t)WB;
 
     if (warp == 0) {
@@ -583,7 +544,7 @@ lm_umma_kernel(const LmParams P) {
         const uint8_t* bimg = P.Bimg + (size_t)(xa + G.XL) * 128;
         const float* ysrc = P.Ys + (xa + G.XL);
         for (int q = 0; q < n_stages; ++q) {
-            const int hf = q & 1, kb = (q >> 1) % nkb, c = (q >> 1) / nkb;
+            const int kb = q % nkb, hf = (q / nkb) & 1, c = q / (2 * nkb);
             const int buf = c & 1, sl = q & 1, r0 = r_first + c * LM_ROWS;
             if (kb == 0 && hf == 0) {
                 mbar_wait_sleep(tmem_empty + 8 * buf, ((c >> 1) & 1) ^ 1);   // drain(c-2) has read ys[buf]
@@ -616,7 +577,7 @@ lm_umma_kernel(const LmParams P) {
         mbar_wait_sleep(a_full, 0);
         tc_fence_after();
         for (int q = 0; q < n_stages; ++q) {
-            const int hf = q & 1, kb = (q >> 1) % nkb, c = (q >> 1) / nkb;
+            const int kb = q % nkb, hf = (q / nkb) & 1, c = q / (2 * nkb);
             const int buf = c & 1, sl = q & 1;
             if (kb == 0 && hf == 0) { TR(tr_w1, mbar_wait_sleep(tmem_empty + 8 * buf, ((c >> 1) & 1) ^ 1)); }
             TR(tr_w2, mbar_wait_sleep(b_full + 8 * sl, (q >> 1) & 1));
@@ -635,30 +596,157 @@ lm_umma_kernel(const LmParams P) {
                     umma_f16(d_tmem, dA_lo + a_off + o, dB_lo + o, idesc, 1u);
                 }
                 tc_commit(b_empty + 8 * sl);
-                if (kb == nkb - 1 && hf == 1) tc_commit(tmem_full + 8 * buf);
+                if (kb == nkb - 1) tc_commit(tmem_full + 16 * buf + 8 * hf);
             }
             __syncwarp();
         }
-    } else {
-        // ------------------------------------------------------------------ epilogue prologue, part 2
+    } else if (warp < 2 + LM_DRAIN_WARPS) {
+        // ------------------------------------------------------------------ drain: accumulator -> distance -> transform -> T ring
+        const int wq = warp & 3;                                     // TMEM lane quarter this warp may read
+        const int m = wq * 32 + lane, qy = m >> 4, qx = m & 15;
+        const float scale = __ldg(P.stats);
+        const float karg = 1.4426950408889634f / (scale * scale);   // D * log2(e) = (xs' + ys' - 2 acc) * karg  (norms are scaled by s^2)
+        const int L = D2 * D2;
+        TR(tr_w1, mbar_wait_sleep(a_full, 0));
+        const float xs_m = sXs[m];
+        const bool q_in = (qy0 + qy < h) && (qx0 + qx < w);
+        for (int c = 0; c < n_chunks; ++c) {
+            const int buf = c & 1, r0 = r_first + c * LM_ROWS;
+            const float* ys = sYs + buf * LM_ROWS * WB + off8;
+            TR(tr_w1, mbar_wait_sleep(ys_full + 8 * buf, (c >> 1) & 1));
+#ifdef LM_TRACE
+            long long _ta = clock64();
+#endif
+#pragma unroll 1
+            for (int jr = 0; jr < LM_ROWS; ++jr) {
+                if ((jr & 1) == 0) { TR(tr_w1, mbar_wait_sleep(tmem_full + 16 * buf + 8 * (jr >> 1), (c >> 1) & 1)); tc_fence_after(); }
+                const int r = r0 + jr, k = r - r_first;
+                const int slot = k % LM_TSLOTS;
+                const int dyi = r - (qy0 + qy) + d;                  // window row of this (query row, previous row) pair
+                // a query row needs exactly the previous rows with dyA <= dyi <= dyB (as top AND as bottom row of a cell)
+                const bool row_used = VOL ? (dyi >= 0 && dyi < D2) : (dyi >= dyA && dyi <= dyB);
+                if (do_cells) { TR(tr_w2, mbar_wait_sleep(t_empty + 8 * slot, ((k / LM_TSLOTS) & 1) ^ 1)); }   // the cells warps are done with the row this one replaces
+                if (__any_sync(0xffffffffu, row_used)) {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * 256 + jr * WB + off8);
+                    uint32_t acc[40];
+#pragma unroll
+                    for (int g8 = 0; g8 < 5; ++g8)
+                        if (g8 * 8 < WC) tmem_ld8(taddr + g8 * 8, acc + g8 * 8);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int g8 = 0; g8 < 5; ++g8)
+                        if (g8 * 8 < WC) reg_fence8(acc + g8 * 8);
+                    float* trow = sT + (size_t)slot * D2 * 128 + m - qx * 128;      // element (dx = cidx - qx) at trow[cidx*128]
+                    float* tvol = nullptr;
+                    if (VOL && q_in && row_used) tvol = P.T_vol + ((size_t)(qy0 + qy) * w + (qx0 + qx)) * L + dyi * D2 - qx;
+                    const float* ysr = ys + jr * WB;
+#pragma unroll
+                    for (int g8 = 0; g8 < 5; ++g8) {
+                        if (g8 * 8 < WC) {                           // warp-uniform; inside: straight-line code, predicated stores
+                            float tv[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                // rounding can leave D (hence T) a hair below zero; the merge clamps
+                                tv[e] = lm_transform(fmaf(-2.0f, __uint_as_float(acc[g8 * 8 + e]), xs_m + ysr[g8 * 8 + e]) * karg);
+                            }
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const int cidx = g8 * 8 + e;
+                                const bool ok = ((unsigned)(cidx - qx) < (unsigned)D2) && row_used;
+                                if (VOL) { if (ok && tvol) tvol[cidx] = tv[e]; }
+                                else if (ok) trow[cidx * 128] = tv[e];
+                            }
+                        }
+                    }
+                }
+                if (do_cells) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t_full + 8 * slot);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + 8 * buf);
+#ifdef LM_TRACE
+            tr_a += clock64() - _ta;
+#endif
+        }
+    } else if (do_cells) {
+        // ------------------------------------------------------------------ cells prologue, part 1: every global load is issued
+        // before the first barrier (label window, ids)
+        const int Ymin = lm_first_out(qy0, h, P.H, G.sy), Xmin = lm_first_out(qx0, w, P.W, G.sx);
+        const int Xal = Xmin & ~3;                                       // the label window starts at a multiple of 4 columns
         {
+            // label window origin in the zero-padded slot image: (Ymin + 2*dyA, Xal); 4 slots per load
+            const int PH = P.H + 4 * d, LPW = G.lab_pitch >> 2;
+            uint32_t wv[LM_LABW];
+#pragma unroll
+            for (int t = 0; t < LM_LABW; ++t) {
+                const int i = et + t * LM_EPI_THREADS;
+                const int ry = i / LPW, rx = (i - ry * LPW) * 4;
+                const int yy = Ymin + 2 * dyA + ry, xx = Xal + rx;
+                wv[t] = 0x01010101u * (uint32_t)N;
+                if (4 * i < lab_total && yy < PH && xx + 3 < G.PW8)
+                    wv[t] = __ldg(reinterpret_cast<const uint32_t*>(P.plab8 + (size_t)yy * G.PW8 + xx));
+            }
+            // bilinear tables: for every cell row / column of this tile the first output index and the count
+            if (et < LM_CH) {
+                const int y0 = qy0 + et;
+                int a = 0, n = 0;
+                if (y0 < h) { a = lm_first_out(y0, h, P.H, G.sy); n = lm_first_out(y0 + 1, h, P.H, G.sy) - a; }
+                sTab[et] = a; sTab[8 + et] = n;
+            } else if (et >= 32 && et < 32 + LM_CW) {
+                const int c = et - 32, x0 = qx0 + c;
+                int a = 0, n = 0;
+                if (x0 < w) { a = lm_first_out(x0, w, P.W, G.sx); n = lm_first_out(x0 + 1, w, P.W, G.sx) - a; }
+                sTab[16 + c] = a; sTab[32 + c] = n;
+            } else if (et == 64) {
+                sTab[48] = 0;
+            } else if (et >= 96 && et < 96 + N) {
+                sTab[64 + (et - 96)] = __ldg(P.gt_ids + (et - 96));
+            }
+            for (int i = et; i < (N + 1) * 4 * LM_EPI_THREADS; i += LM_EPI_THREADS) sMin[i] = 1.0f;
+            for (int i = et; i < LM_MAXUNITS; i += LM_EPI_THREADS) sUnits[i] = make_int2(0, 0);
+#pragma unroll
+            for (int t = 0; t < LM_LABW; ++t) {
+                const int i = et + t * LM_EPI_THREADS;
+                if (4 * i < lab_total) reinterpret_cast<uint32_t*>(sLab)[i] = wv[t];
+            }
+        }
+        epi_bar_sync();
+        // ------------------------------------------------------------------ cells prologue, part 2
+        {
+            // second label table: the first one shifted by one byte
+#pragma unroll
+            for (int t = 0; t < LM_LABW; ++t) {
+                const int i = et + t * LM_EPI_THREADS;
+                if (4 * i < lab_total) {
+                    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(sLab);
+                    reinterpret_cast<uint32_t*>(sLab + lab_table)[i] = __funnelshift_r(w32[i], w32[i + 1], 8);
+                }
+            }
             // slot of an id = the first gt_ids entry holding the same (float-compared) value (IntVOS.py:406-408)
-            if (et >= LM_EPI_THREADS - 32 && et < LM_EPI_THREADS - 32 + N && do_cells) {
+            if (et >= LM_EPI_THREADS - 32 && et < LM_EPI_THREADS - 32 + N) {
                 const int o = et - (LM_EPI_THREADS - 32);
                 const float id = (float)sTab[64 + o];
                 int c = o;
                 for (int k = o - 1; k >= 0; --k) if ((float)sTab[64 + k] == id) c = k;
                 sTab[128 + o] = c;
             }
-            // units: every cell's outputs in blocks of <= 2x2; block (0,0) keeps the cell's index, the rest is appended
-            if (et < LM_NCELL && do_cells) {
+            // units: every cell's outputs in blocks of <= 2x2.  Slot layout: a warp of the first 128 slots holds two cell rows
+            // (lanes 0-14 and 15-29), so its T loads (word 16*cy + cx) and label loads fall into distinct banks; blocks beyond
+            // the first of a cell go to the free slots (lanes 30-31 of the first three warps, 111-127, then 128...).
+            if (et < LM_NCELL) {
                 const int cy = et / LM_CW, cx = et % LM_CW;
                 const int Y0 = sTab[cy], ny = sTab[8 + cy], X0 = sTab[16 + cx], nx = sTab[32 + cx];
-                sUnits[et] = make_int2(0, 0);
                 if (ny > 0 && nx > 0) {
                     for (int by = 0; 2 * by < ny; ++by)
                         for (int bx = 0; 2 * bx < nx; ++bx) {
-                            const int idx = (by | bx) ? LM_NCELL + atomicAdd(&sTab[48], 1) : et;
+                            int idx = 32 * (cy >> 1) + 15 * (cy & 1) + cx;
+                            if (by | bx) {
+                                const int e = atomicAdd(&sTab[48], 1);
+                                idx = e < 6 ? 32 * (e >> 1) + 30 + (e & 1) : (e < LM_FREE_SLOTS ? 111 + (e - 6) : 128 + (e - LM_FREE_SLOTS));
+                            }
                             if (idx < LM_MAXUNITS)
                                 sUnits[idx] = make_int2(cy | (cx << 8) | (min(2, ny - 2 * by) << 16) | (min(2, nx - 2 * bx) << 24),
                                                         (Y0 + 2 * by) | ((X0 + 2 * bx) << 16));
@@ -670,20 +758,13 @@ lm_umma_kernel(const LmParams P) {
 #ifdef LM_TRACE
         tr_pro = clock64() - tr0;
 #endif
-        // ------------------------------------------------------------------ epilogue: drain + cells
-        const int ew = et >> 5;
-        const int wq = warp & 3;                                     // TMEM lane quarter this warp may read
-        const int sub = ew >> 2;                                     // rows {2*sub, 2*sub+1} of every chunk
-        const int m = wq * 32 + lane, qy = m >> 4, qx = m & 15;
-        const float karg = 1.4426950408889634f / (scale * scale);   // D * log2(e) = (xs' + ys' - 2 acc) * karg  (norms are scaled by s^2)
-        const int L = D2 * D2;
+        // ------------------------------------------------------------------ cells: bilinear upsample + label mask + per-object min
         // ---- this thread's unit
-        const int n_units = do_cells ? min(LM_NCELL + sTab[48], LM_MAXUNITS) : 0;
-        const int parts = (n_units <= LM_EPI_THREADS / 2) ? 2 : 1;
+        const int parts = (sTab[48] <= LM_FREE_SLOTS) ? 2 : 1;
         const int U = LM_EPI_THREADS / parts;
         const int u = et % U, part = et / U;
         int cy = 0, cx = 0, ny = 0, nx = 0, Y0 = 0, X0 = 0;
-        if (u < n_units) {
+        {
             const int2 un = sUnits[u];
             cy = un.x & 255; cx = (un.x >> 8) & 255; ny = (un.x >> 16) & 255; nx = (un.x >> 24) & 255;
             Y0 = un.y & 0xffff; X0 = (un.y >> 16) & 0xffff;
@@ -700,7 +781,9 @@ lm_umma_kernel(const LmParams P) {
         const int dx_lo = (parts == 2 && part == 1) ? (D2 + 1) / 2 : 0;
         const int dx_hi = (parts == 2 && part == 0) ? (D2 + 1) / 2 : D2;
         const int LP = G.lab_pitch;
-        const uint8_t* lab0 = sLab + (Y0 - Ymin) * LP + (X0 - Xal);
+        // (X0 - Xal) odd: the shifted table holds the same bytes one position earlier, so every pair load is 2-byte aligned
+        const int lab_off = (Y0 - Ymin) * LP + (X0 - Xal);
+        const uint8_t* lab0 = sLab + ((lab_off & 1) ? lab_table + lab_off - 1 : lab_off);
         // minima: [slot][output k][thread]; outputs this unit does not have go to the spare slot N
         uint32_t min_base[4]; int min_stride[4];
 #pragma unroll
@@ -709,121 +792,68 @@ lm_umma_kernel(const LmParams P) {
             min_base[k] = smem_u32(sMin) + (uint32_t)(((have ? 0 : N * 4) + k) * LM_EPI_THREADS + et) * 4u;
             min_stride[k] = have ? 4 * LM_EPI_THREADS * 4 : 0;
         }
-        TR(tr_w1, mbar_wait_sleep(a_full, 0));
-        const float xs_m = sXs[m];
-        const bool q_in = (qy0 + qy < h) && (qx0 + qx < w);
-
-        for (int c = 0; c < n_chunks; ++c) {
-            const int buf = c & 1, r0 = r_first + c * LM_ROWS;
-            const float* ys = sYs + buf * LM_ROWS * WB + off8;
-            TR(tr_w1, mbar_wait_sleep(tmem_full + 8 * buf, (c >> 1) & 1); mbar_wait_sleep(ys_full + 8 * buf, (c >> 1) & 1));
-            tc_fence_after();
-            TR(tr_w2, epi_bar_sync());                               // cells(c-1) finished with the T slots we overwrite
-#ifdef LM_TRACE
-            long long _ta = clock64();
-#endif
-            // ---- drain: accumulator -> distance -> transform -> sT[slot][dx][pixel]
+        // pairs (previous row r-1 over query row y0, previous row r over query row y0+1), one ring row at a time
+        TR(tr_w1, mbar_wait_sleep(t_full, 0));
 #pragma unroll 1
-            for (int jj = 0; jj < 2; ++jj) {
-                const int jr = 2 * sub + jj, r = r0 + jr;
-                const int slot = (r - r_first) % LM_TSLOTS;
-                const int dyi = r - (qy0 + qy) + d;                  // window row of this (query row, previous row) pair
-                // a query row needs exactly the previous rows with dyA <= dyi <= dyB (as top AND as bottom row of a cell)
-                const bool row_used = VOL ? (dyi >= 0 && dyi < D2) : (dyi >= dyA && dyi <= dyB);
-                if (!__any_sync(0xffffffffu, row_used)) continue;
-                const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * 256 + jr * WB + off8);
-                uint32_t acc[40];
-#pragma unroll
-                for (int g8 = 0; g8 < 5; ++g8)
-                    if (g8 * 8 < WC) tmem_ld8(taddr + g8 * 8, acc + g8 * 8);
-                tmem_ld_wait();
-#pragma unroll
-                for (int g8 = 0; g8 < 5; ++g8)
-                    if (g8 * 8 < WC) reg_fence8(acc + g8 * 8);
-                float* trow = sT + (size_t)slot * D2 * 128 + m - qx * 128;      // element (dx = cidx - qx) at trow[cidx*128]
-                float* tvol = nullptr;
-                if (VOL && q_in && row_used) tvol = P.T_vol + ((size_t)(qy0 + qy) * w + (qx0 + qx)) * L + dyi * D2 - qx;
-                const float* ysr = ys + jr * WB;
-#pragma unroll
-                for (int g8 = 0; g8 < 5; ++g8) {
-                    if (g8 * 8 < WC) {                               // warp-uniform; inside: straight-line code, predicated stores
-                        float tv[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            // rounding can leave D (hence T) a hair below zero; the merge clamps
-                            tv[e] = lm_transform(fmaf(-2.0f, __uint_as_float(acc[g8 * 8 + e]), xs_m + ysr[g8 * 8 + e]) * karg);
-                        }
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int cidx = g8 * 8 + e;
-                            const bool ok = ((unsigned)(cidx - qx) < (unsigned)D2) && row_used;
-                            if (VOL) { if (ok && tvol) tvol[cidx] = tv[e]; }
-                            else if (ok) trow[cidx * 128] = tv[e];
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty + 8 * buf);
-#ifdef LM_TRACE
-            tr_a += clock64() - _ta;
-#endif
-            TR(tr_w2, epi_bar_sync());                               // T rows of chunk c complete
+        for (int k = 1; k < n_trows; ++k) {
+            const int r = r_first + k;
+            const int slot_t = (k - 1) % LM_TSLOTS, slot_b = k % LM_TSLOTS;
+            TR(tr_w1, mbar_wait_sleep(t_full + 8 * slot_b, (k / LM_TSLOTS) & 1));
 #ifdef LM_TRACE
             long long _tc = clock64();
 #endif
-            // ---- cells: pairs (previous row r-1 over query row y0, previous row r over query row y0+1)
-            if (active) {
-#pragma unroll 1
-                for (int rr = 0; rr < LM_ROWS; ++rr) {
-                    const int r = r0 + rr;
-                    if (r == r_first) continue;
-                    const int dyi = (r - 1) - y0c + d;
-                    if (dyi < dyA || dyi > dyB) continue;
-                    const float* Tt = sT + (size_t)((r - 1 - r_first) % LM_TSLOTS) * D2 * 128 + m00;
-                    const float* Tb = sT + (size_t)((r - r_first) % LM_TSLOTS) * D2 * 128 + m00 + LM_TW;
-                    const uint8_t* lp = lab0 + 2 * (dyi - dyA) * LP;
+            const int dyi = (r - 1) - y0c + d;
+            if (active && dyi >= dyA && dyi <= dyB) {
+                const float* Tt = sT + (size_t)slot_t * D2 * 128 + m00;
+                const float* Tb = sT + (size_t)slot_b * D2 * 128 + m00 + LM_TW;
+                const uint8_t* lp = lab0 + 2 * (dyi - dyA) * LP;
 #pragma unroll 2
-                    for (int dxi = dx_lo; dxi < dx_hi; ++dxi) {
-                        const float v00 = Tt[dxi * 128], v01 = Tt[dxi * 128 + 1];
-                        const float v10 = Tb[dxi * 128], v11 = Tb[dxi * 128 + 1];
-                        const uint8_t* l2 = lp + 2 * dxi;
-                        const int lab[4] = {l2[0], l2[1], l2[LP], l2[LP + 1]};
-                        float ht[2], hb[2];
+                for (int dxi = dx_lo; dxi < dx_hi; ++dxi) {
+                    const float v00 = Tt[dxi * 128], v01 = Tt[dxi * 128 + 1];
+                    const float v10 = Tb[dxi * 128], v11 = Tb[dxi * 128 + 1];
+                    const uint32_t la = *reinterpret_cast<const uint16_t*>(lp + 2 * dxi), lb = *reinterpret_cast<const uint16_t*>(lp + 2 * dxi + LP);
+                    const int lab[4] = {(int)(la & 255u), (int)(la >> 8), (int)(lb & 255u), (int)(lb >> 8)};
+                    float ht[2], hb[2];
 #pragma unroll
-                        for (int ix = 0; ix < 2; ++ix) {
-                            ht[ix] = wx0[ix] * v00 + wx1[ix] * v01;
-                            hb[ix] = wx0[ix] * v10 + wx1[ix] * v11;
-                        }
-                        // the four running minima never alias (different output planes): load all, then store all
-                        uint32_t ad[4]; float old[4];
+                    for (int ix = 0; ix < 2; ++ix) {
+                        ht[ix] = wx0[ix] * v00 + wx1[ix] * v01;
+                        hb[ix] = wx0[ix] * v10 + wx1[ix] * v11;
+                    }
+                    // the four running minima never alias (different output planes): load all, then store all
+                    uint32_t ad[4]; float old[4];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            ad[k] = min_base[k] + (uint32_t)(lab[k] * min_stride[k]);
-                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(old[k]) : "r"(ad[k]));
-                        }
+                    for (int kk = 0; kk < 4; ++kk) {
+                        ad[kk] = min_base[kk] + (uint32_t)(lab[kk] * min_stride[kk]);
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(old[kk]) : "r"(ad[kk]));
+                    }
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const float uval = wy0[k >> 1] * ht[k & 1] + wy1[k >> 1] * hb[k & 1];
-                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad[k]), "f"(fminf(old[k], uval)));
-                        }
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const float uval = wy0[kk >> 1] * ht[kk & 1] + wy1[kk >> 1] * hb[kk & 1];
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad[kk]), "f"(fminf(old[kk], uval)));
                     }
                 }
             }
 #ifdef LM_TRACE
             tr_c += clock64() - _tc;
 #endif
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty + 8 * slot_t);      // row k-1 may be replaced
         }
-        // ---- merge into the output (both halves of the dy range and both dx parts): atomicMin on float bits
+        // ---- merge: the dx parts of a unit are combined in shared memory (part p takes outputs 2p, 2p+1), the two halves of
+        // the dy range with atomicMin on the float bits of the pre-filled output
+        epi_bar_sync();
         if (active) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int kk = 0; kk < 4; ++kk) {
+                const int k = (parts == 2) ? 2 * part + (kk & 1) : kk;
+                if (parts == 2 && kk >= 2) break;
                 if ((k >> 1) < ny && (k & 1) < nx) {
                     const int Y = Y0 + (k >> 1), X = X0 + (k & 1);
                     unsigned* o = reinterpret_cast<unsigned*>(P.out) + ((size_t)Y * P.W + X) * N;
                     for (int ob = 0; ob < N; ++ob) {
-                        const float v = *reinterpret_cast<volatile float*>(&sMin[(size_t)(sTab[128 + ob] * 4 + k) * LM_EPI_THREADS + et]);
+                        const float* mp = &sMin[(size_t)(sTab[128 + ob] * 4 + k) * LM_EPI_THREADS + u];
+                        float v = mp[0];
+                        if (parts == 2) v = fminf(v, mp[U]);
                         if (v < 1.0f) atomicMin(o + ob, __float_as_uint(fmaxf(v, 0.f)));
                     }
                 }
@@ -832,7 +862,7 @@ lm_umma_kernel(const LmParams P) {
     }
 
 #ifdef LM_TRACE
-    if ((blockIdx.x == 0 || blockIdx.x == 71 || blockIdx.x == 140) && lane == 0 && (warp == 1 || warp == 2 || warp == 9))
+    if ((blockIdx.x == 0 || blockIdx.x == 71 || blockIdx.x == 140) && lane == 0 && (warp == 1 || warp == 2 || warp == 6 || warp == 13))
         printf("cta %d warp %d total %lld prologue %lld | wait1 %lld wait2 %lld | drain %lld cells %lld (chunks %d)\n", blockIdx.x, warp,
                clock64() - tr0, tr_pro, tr_w1, tr_w2, tr_a, tr_c, n_chunks);
 #endif
