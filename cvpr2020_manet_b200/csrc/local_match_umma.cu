@@ -75,11 +75,17 @@ __host__ __device__ inline int lm_lerp(int dst, int in_size, float scale, float*
     if (w1) *w1 = src - (float)i0;
     return i0;
 }
-// first output index whose source cell is >= i0 (lm_lerp is monotone in dst)
+// first output index whose source cell is >= i0 (lm_lerp is monotone in dst): a closed-form guess one below
+// i0 / scale, then at most a few steps checked with lm_lerp itself, so the answer is exact for any rounding.
 __host__ __device__ inline int lm_first_out(int i0, int in_size, int out_size, float scale) {
-    int lo = 0, hi = out_size;                           // smallest dst in [0,out] with lerp(dst) >= i0
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (lm_lerp(mid, in_size, scale, nullptr) >= i0) hi = mid; else lo = mid + 1; }
-    return lo;
+    if (i0 <= 0) return 0;
+    if (!(scale > 0.f)) return out_size;
+    int dst = (int)((float)i0 / scale) - 1;
+    if (dst > out_size) dst = out_size;
+    if (dst < 0) dst = 0;
+    while (dst > 0 && lm_lerp(dst - 1, in_size, scale, nullptr) >= i0) --dst;
+    while (dst < out_size && lm_lerp(dst, in_size, scale, nullptr) < i0) ++dst;
+    return dst;
 }
 __host__ __device__ inline int lm_floor8(int x) { return x & ~7; }   // two's complement: floors negative x too
 
@@ -151,10 +157,10 @@ static bool lm_geometry(int H, int W, int C, int N, int d, LmGeom* g) {
     g->off_B = o; o += 2 * (512 * g->WB);                // 2 stages x [hi|lo][2 rows][WB columns][128 B] (one k-block of two rows)
     g->off_T = o; o += LM_TSLOTS * g->D2 * 128 * 4;
     g->off_min = o; o += (N + 1) * 4 * LM_EPI_THREADS * 4;
-    g->off_lab = o; o += 2 * (lm_round_up(g->lab_rows * g->lab_pitch, 16) + 16);   // byte table + the same shifted by one byte (aligned 16-bit pair loads)
+    g->off_lab = o; o += lm_round_up(g->lab_rows * g->lab_pitch, 16);
     g->off_ys = o; o += 2 * LM_ROWS * g->WB * 4;
     g->off_xs = o; o += 128 * 4;
-    g->off_units = o; o += LM_MAXUNITS * 8;
+    g->off_units = o; o += LM_MAXUNITS * 8 + 1024;
     g->off_tab = o; o += 1024;
     g->off_bar = o; o += 256;
     g->total = o + 1024;                                 // slack: the base is aligned to 1024 bytes
@@ -419,18 +425,27 @@ struct LmParams {
     LmGeom g;
 };
 
-// mbarrier wait that lets the hardware suspend the thread (time hint, as CUTLASS does) instead of spinning:
-// the waiting warps of this kernel share their schedulers with the warps doing the work.
+#ifndef LM_ABL
+#define LM_ABL 0
+#endif
+#ifndef LM_BACKOFF_NS
+#define LM_BACKOFF_NS 96
+#endif
+// mbarrier wait for the warps that are ahead of the critical path (producer, MMA issuer, drain): between polls the warp
+// sleeps, so its polling does not take issue slots from the cells warps that share its scheduler (measured: the polls
+// were 23 % of all issued instructions).
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "WAITS_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@p bra WAITS_DONE;\n\t"
-        "bra WAITS_LOOP;\n\t"
+        "WAITS_LOOP:\n\t"
+        "nanosleep.u32 %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAITS_LOOP;\n\t"
         "WAITS_DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+        "}" ::"r"(bar), "r"(parity), "n"(LM_BACKOFF_NS) : "memory");
 }
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(LM_EPI_THREADS) : "memory"); }
@@ -453,6 +468,17 @@ __device__ __forceinline__ float lm_transform(float arg) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(arg));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
     return fmaf(-2.0f, r, 1.0f);
+}
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
 }
 
 #ifdef LM_TRACE
@@ -523,11 +549,14 @@ lm_umma_kernel(const LmParams P) {
     }
     const int et = tid - LM_EPI_T0;
     const int lab_total = do_cells ? G.lab_rows * G.lab_pitch : 0;
-    const int lab_table = lm_round_up(lab_total, 16) + 16;           // bytes per label table
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&sTab[50]);
+#ifdef LM_TRACE
+    long long* tl = reinterpret_cast<long long*>(sUnits + 128);   // [0..39] drain publishes row k, [40..79] cells finish pair k
+    const long long tr_sync = clock64() - tr0; long long tr_e1 = 0, tr_e2 = 0, tr_e3 = 0;
+#endif
     const int ksteps = G.ksteps, nkb = G.nkb;
     const int n_stages = n_chunks * nkb * 2;                         // B stage = (chunk, pair of rows, k-block)
     const int n_trows = n_chunks * LM_ROWS;                          // rows of T that pass through the ring
@@ -576,12 +605,19 @@ lm_umma_kernel(const LmParams P) {
         const uint64_t dA_hi = smem_desc_sw128(base), dA_lo = smem_desc_sw128(base + 2 * 16384);
         mbar_wait_sleep(a_full, 0);
         tc_fence_after();
+#ifdef LM_TRACE
+        tr_e1 = clock64() - tr0;
+#endif
         for (int q = 0; q < n_stages; ++q) {
             const int kb = q % nkb, hf = (q / nkb) & 1, c = q / (2 * nkb);
             const int buf = c & 1, sl = q & 1;
             if (kb == 0 && hf == 0) { TR(tr_w1, mbar_wait_sleep(tmem_empty + 8 * buf, ((c >> 1) & 1) ^ 1)); }
             TR(tr_w2, mbar_wait_sleep(b_full + 8 * sl, (q >> 1) & 1));
             tc_fence_after();
+#ifdef LM_TRACE
+            if (q == 0) tr_e2 = clock64() - tr0;
+            if (q == 1) tr_e3 = clock64() - tr0;
+#endif
             const uint32_t d_tmem = tmem_base + buf * 256 + hf * 2 * WB;
             const uint64_t dB_hi = smem_desc_sw128(base + G.off_B + sl * stage_bytes);
             const uint64_t dB_lo = smem_desc_sw128(base + G.off_B + sl * stage_bytes + 2 * row_bytes);
@@ -593,7 +629,9 @@ lm_umma_kernel(const LmParams P) {
                     umma_f16(d_tmem, dA_hi + a_off + o, dB_hi + o, idesc, (kb | k) ? 1u : 0u);
                     umma_f16(d_tmem, dA_lo + a_off + o, dB_hi + o, idesc, 1u);
                     umma_f16(d_tmem, dA_hi + a_off + o, dB_lo + o, idesc, 1u);
+#ifndef LM_DROP_LOLO
                     umma_f16(d_tmem, dA_lo + a_off + o, dB_lo + o, idesc, 1u);
+#endif
                 }
                 tc_commit(b_empty + 8 * sl);
                 if (kb == nkb - 1) tc_commit(tmem_full + 16 * buf + 8 * hf);
@@ -620,13 +658,22 @@ lm_umma_kernel(const LmParams P) {
 #pragma unroll 1
             for (int jr = 0; jr < LM_ROWS; ++jr) {
                 if ((jr & 1) == 0) { TR(tr_w1, mbar_wait_sleep(tmem_full + 16 * buf + 8 * (jr >> 1), (c >> 1) & 1)); tc_fence_after(); }
+#ifdef LM_TRACE
+                if (c == 0 && jr == 0) tr_e1 = clock64() - tr0;
+                if (c == 0 && jr == 2) tr_e2 = clock64() - tr0;
+                if (c == 1 && jr == 0) tr_e3 = clock64() - tr0;
+#endif
                 const int r = r0 + jr, k = r - r_first;
                 const int slot = k % LM_TSLOTS;
                 const int dyi = r - (qy0 + qy) + d;                  // window row of this (query row, previous row) pair
                 // a query row needs exactly the previous rows with dyA <= dyi <= dyB (as top AND as bottom row of a cell)
                 const bool row_used = VOL ? (dyi >= 0 && dyi < D2) : (dyi >= dyA && dyi <= dyB);
                 if (do_cells) { TR(tr_w2, mbar_wait_sleep(t_empty + 8 * slot, ((k / LM_TSLOTS) & 1) ^ 1)); }   // the cells warps are done with the row this one replaces
+#if LM_ABL == 3      /* no drain work */
+                if (false) {
+#else
                 if (__any_sync(0xffffffffu, row_used)) {
+#endif
                     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * 256 + jr * WB + off8);
                     uint32_t acc[40];
 #pragma unroll
@@ -662,6 +709,9 @@ lm_umma_kernel(const LmParams P) {
                 if (do_cells) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(t_full + 8 * slot);
+#ifdef LM_TRACE
+                    if (warp == 2 && lane == 0 && k < 40) tl[k] = clock64() - tr0;
+#endif
                 }
             }
             tc_fence_before();
@@ -716,15 +766,6 @@ lm_umma_kernel(const LmParams P) {
         epi_bar_sync();
         // ------------------------------------------------------------------ cells prologue, part 2
         {
-            // second label table: the first one shifted by one byte
-#pragma unroll
-            for (int t = 0; t < LM_LABW; ++t) {
-                const int i = et + t * LM_EPI_THREADS;
-                if (4 * i < lab_total) {
-                    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(sLab);
-                    reinterpret_cast<uint32_t*>(sLab + lab_table)[i] = __funnelshift_r(w32[i], w32[i + 1], 8);
-                }
-            }
             // slot of an id = the first gt_ids entry holding the same (float-compared) value (IntVOS.py:406-408)
             if (et >= LM_EPI_THREADS - 32 && et < LM_EPI_THREADS - 32 + N) {
                 const int o = et - (LM_EPI_THREADS - 32);
@@ -777,13 +818,10 @@ lm_umma_kernel(const LmParams P) {
             if (k < ny) lm_lerp(Y0 + k, h, G.sy, &wy1[k]);
             if (k < nx) lm_lerp(X0 + k, w, G.sx, &wx1[k]);
         }
-        const float wy0[2] = {1.0f - wy1[0], 1.0f - wy1[1]}, wx0[2] = {1.0f - wx1[0], 1.0f - wx1[1]};
         const int dx_lo = (parts == 2 && part == 1) ? (D2 + 1) / 2 : 0;
         const int dx_hi = (parts == 2 && part == 0) ? (D2 + 1) / 2 : D2;
         const int LP = G.lab_pitch;
-        // (X0 - Xal) odd: the shifted table holds the same bytes one position earlier, so every pair load is 2-byte aligned
-        const int lab_off = (Y0 - Ymin) * LP + (X0 - Xal);
-        const uint8_t* lab0 = sLab + ((lab_off & 1) ? lab_table + lab_off - 1 : lab_off);
+        const uint8_t* lab0 = sLab + (Y0 - Ymin) * LP + (X0 - Xal);
         // minima: [slot][output k][thread]; outputs this unit does not have go to the spare slot N
         uint32_t min_base[4]; int min_stride[4];
 #pragma unroll
@@ -793,17 +831,27 @@ lm_umma_kernel(const LmParams P) {
             min_stride[k] = have ? 4 * LM_EPI_THREADS * 4 : 0;
         }
         // pairs (previous row r-1 over query row y0, previous row r over query row y0+1), one ring row at a time
-        TR(tr_w1, mbar_wait_sleep(t_full, 0));
+#if LM_ABL == 1
+        float abl[4] = {1.f, 1.f, 1.f, 1.f};
+#endif
+        TR(tr_w1, mbar_wait(t_full, 0));
 #pragma unroll 1
         for (int k = 1; k < n_trows; ++k) {
             const int r = r_first + k;
             const int slot_t = (k - 1) % LM_TSLOTS, slot_b = k % LM_TSLOTS;
-            TR(tr_w1, mbar_wait_sleep(t_full + 8 * slot_b, (k / LM_TSLOTS) & 1));
+            TR(tr_w1, mbar_wait(t_full + 8 * slot_b, (k / LM_TSLOTS) & 1));
 #ifdef LM_TRACE
             long long _tc = clock64();
 #endif
             const int dyi = (r - 1) - y0c + d;
+#if LM_ABL == 2      /* no cells work at all */
+            if (false) {
+#else
             if (active && dyi >= dyA && dyi <= dyB) {
+#endif
+                // The kernel is issue bound (ncu: the warps of this loop are "selected"/"not selected" most of the time), so
+                // the loop is written for instruction count: byte label loads (no extraction), bilinear weights in
+                // difference form (12 FP instructions for the four outputs instead of 16).
                 const float* Tt = sT + (size_t)slot_t * D2 * 128 + m00;
                 const float* Tb = sT + (size_t)slot_b * D2 * 128 + m00 + LM_TW;
                 const uint8_t* lp = lab0 + 2 * (dyi - dyA) * LP;
@@ -811,36 +859,46 @@ lm_umma_kernel(const LmParams P) {
                 for (int dxi = dx_lo; dxi < dx_hi; ++dxi) {
                     const float v00 = Tt[dxi * 128], v01 = Tt[dxi * 128 + 1];
                     const float v10 = Tb[dxi * 128], v11 = Tb[dxi * 128 + 1];
-                    const uint32_t la = *reinterpret_cast<const uint16_t*>(lp + 2 * dxi), lb = *reinterpret_cast<const uint16_t*>(lp + 2 * dxi + LP);
-                    const int lab[4] = {(int)(la & 255u), (int)(la >> 8), (int)(lb & 255u), (int)(lb >> 8)};
-                    float ht[2], hb[2];
+                    const uint8_t* l2 = lp + 2 * dxi;
+                    const int lab[4] = {l2[0], l2[1], l2[LP], l2[LP + 1]};
+                    const float dt = v01 - v00, db = v11 - v10;
+                    float top[2], dv[2];
 #pragma unroll
                     for (int ix = 0; ix < 2; ++ix) {
-                        ht[ix] = wx0[ix] * v00 + wx1[ix] * v01;
-                        hb[ix] = wx0[ix] * v10 + wx1[ix] * v11;
+                        top[ix] = fmaf(wx1[ix], dt, v00);
+                        dv[ix] = fmaf(wx1[ix], db, v10) - top[ix];
                     }
                     // the four running minima never alias (different output planes): load all, then store all
                     uint32_t ad[4]; float old[4];
+#if LM_ABL == 1      /* no shared-memory minima: fold everything into registers (wrong results, timing only) */
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) abl[kk] = fminf(abl[kk], fmaf(wy1[kk >> 1], dv[kk & 1], top[kk & 1]) + (float)lab[kk]);
+#else
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
                         ad[kk] = min_base[kk] + (uint32_t)(lab[kk] * min_stride[kk]);
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(old[kk]) : "r"(ad[kk]));
+                        old[kk] = lds_f32(ad[kk]);
                     }
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
-                        const float uval = wy0[kk >> 1] * ht[kk & 1] + wy1[kk >> 1] * hb[kk & 1];
+                        const float uval = fmaf(wy1[kk >> 1], dv[kk & 1], top[kk & 1]);
                         asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad[kk]), "f"(fminf(old[kk], uval)));
                     }
+#endif
                 }
             }
 #ifdef LM_TRACE
             tr_c += clock64() - _tc;
+            if (warp == 6 && lane == 0 && k < 40) { tl[40 + k] = clock64() - tr0; tl[80 + k] = _tc - tr0; }
 #endif
             __syncwarp();
             if (lane == 0) mbar_arrive(t_empty + 8 * slot_t);      // row k-1 may be replaced
         }
         // ---- merge: the dx parts of a unit are combined in shared memory (part p takes outputs 2p, 2p+1), the two halves of
         // the dy range with atomicMin on the float bits of the pre-filled output
+#if LM_ABL == 1
+        if (abl[0] + abl[1] + abl[2] + abl[3] == -1.f) sMin[et] = 0.f;
+#endif
         epi_bar_sync();
         if (active) {
 #pragma unroll
@@ -863,11 +921,17 @@ lm_umma_kernel(const LmParams P) {
 
 #ifdef LM_TRACE
     if ((blockIdx.x == 0 || blockIdx.x == 71 || blockIdx.x == 140) && lane == 0 && (warp == 1 || warp == 2 || warp == 6 || warp == 13))
-        printf("cta %d warp %d total %lld prologue %lld | wait1 %lld wait2 %lld | drain %lld cells %lld (chunks %d)\n", blockIdx.x, warp,
-               clock64() - tr0, tr_pro, tr_w1, tr_w2, tr_a, tr_c, n_chunks);
+        printf("cta %d warp %d total %lld prologue %lld | wait1 %lld wait2 %lld | drain %lld cells %lld (chunks %d) | sync %lld e1 %lld e2 %lld e3 %lld\n", blockIdx.x, warp,
+               clock64() - tr0, tr_pro, tr_w1, tr_w2, tr_a, tr_c, n_chunks, tr_sync, tr_e1, tr_e2, tr_e3);
 #endif
     tc_fence_before();
     __syncthreads();
+#ifdef LM_TRACE
+    if (blockIdx.x == 71 && tid == 0) {
+        printf("TL end %lld\n", clock64() - tr0);
+        for (int k = 0; k < n_trows; ++k) printf("TL row %2d drain-published %6lld | cells start %6lld end %6lld\n", k, tl[k], tl[80 + k], tl[40 + k]);
+    }
+#endif
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
