@@ -24,17 +24,27 @@
 // q.p = qh.ph + ql.ph + qh.pl + ql.pl in four kind::f16 MMAs with fp32 accumulation (the same scheme as
 // global_match_umma.cu).  Absolute error of D: about 2^-22 |q-mu| |p-mu|.
 //
-// Three launches.  lm_pool_kernel: pooling, |x| max and channel sums per block, label padding, output
-// fill.  lm_convert_kernel: mu and the scale, then every operand exactly once, already in the K-major
-// SWIZZLE_128B layout the MMA reads: the previous frame as a zero/inf padded image
-// [row][k-block][hi|lo][column][64 halves] plus its norms, the query frame as one 64 KB image per tile.
-// lm_umma_kernel: item = (tile, half of the dy range): 2 x 72 = 144 CTAs at 480p, one wave.  Warp 0
-// feeds shared memory with plain bulk copies (no tensor map: the images ARE the shared-memory layout),
-// warp 1 issues the MMAs, warps 2-9 are the epilogue (TMEM drain, then "cells": one thread per bilinear
-// cell = the <= 2x2 full-resolution pixels that interpolate between the same four half-resolution
-// pixels, so the four T values are loaded once per window offset).  Running minima live in shared
-// memory [object][output][thread] (conflict free); the two halves of the dy range are merged with
-// atomicMin on the (non-negative) float bits of the pre-filled output.
+// Three launches.  lm_pool_kernel: pooling, |x| max and channel sums per block, labels -> padded image of
+// object slots (bytes), output fill.  lm_convert_kernel: mu and the scale, then every operand exactly once:
+// the previous frame as a zero/inf padded image [row][k-block][hi|lo][column][64 halves], already in the
+// K-major SWIZZLE_128B layout the MMA reads, plus its norms; the query frame per tile as plain pixel rows.
+// lm_umma_kernel: item = (tile, half of the dy range): 2 x 72 = 144 CTAs at 480p, one wave, 14 warps:
+//   warp 0      bulk-copy producer: ring of up to four 24 KB B stages (the images ARE the shared-memory
+//               layout, no tensor map); the ring is deep because the copy -> MMA loop is latency bound
+//   warp 1      MMA issuer: A comes from TENSOR MEMORY (tcgen05.mma with a TMEM A operand), which frees 64 KB
+//               of shared memory for the ring and halves the operand reads from shared memory
+//   warps 2-5   drain, one per TMEM lane quarter: first store the query tile's rows into tensor memory
+//               (tcgen05.st), then per previous-frame row: tcgen05.ld -> distance -> transform -> a ring of
+//               five T rows in shared memory, T[row][dx][pixel]
+//   warps 6-13  "cells": one thread per bilinear cell = the <= 2x2 full-resolution pixels that interpolate
+//               between the same four half-resolution pixels (the four T values are loaded once per window
+//               offset), two threads per cell splitting the dx range.  Running minima live in shared memory
+//               [object][output][thread] (conflict free).
+// Rows travel drain -> cells through mbarriers per ring slot; the accumulator is handed over per pair of
+// rows.  The two halves of the dy range are merged with atomicMin on the (non-negative) float bits of the
+// pre-filled output.  What bounds it (ncu + in-kernel cycle traces, profiles/README.md): instruction issue
+// (~0.65 IPC per scheduler in steady state: cells 40 instructions per offset, drain 9 per element) and the
+// staggered use of the ring (a cell row needs 13 of a CTA's 20 rows).
 #include <string.h>
 
 #include "common.cuh"
@@ -57,7 +67,10 @@ constexpr int LM_EPI_WARPS = 8;                         // "cells" warps
 constexpr int LM_EPI_THREADS = 32 * LM_EPI_WARPS;       // 256
 constexpr int LM_EPI_T0 = LM_DRAIN_T0 + 32 * LM_DRAIN_WARPS;   // 192
 constexpr int LM_THREADS = LM_EPI_T0 + LM_EPI_THREADS;  // 448
-constexpr int LM_A_BYTES = 4 * 16384;                   // [hi|lo][k-block 0|1][128 rows][128 B]
+constexpr int LM_A_ROW = 512;                          // query operand image: [hi|lo][16 chunks of 8 halves][128 pixels][16 B]
+constexpr int LM_A_BYTES = 128 * LM_A_ROW;              // per tile; the A operand lives in tensor memory, not in shared memory
+constexpr int LM_A_COL_HI = 192, LM_A_COL_LO = 448;     // TMEM columns of A (hi, lo): the gaps behind the two accumulator buffers
+constexpr int LM_MAX_STAGES = 4;
 constexpr int LM_POOL_PX = 32;
 constexpr int LM_LABW = 6;                               // 4-byte words of the label window an epilogue thread copies
 constexpr int LM_MAXN = 64;                              // label slots are bytes; also bounds the shared-memory minima
@@ -98,7 +111,8 @@ struct LmGeom {
     int max_units;
     float sy, sx;                                        // bilinear source scales (h-1)/(H-1), (w-1)/(W-1), computed once on the host
     // shared-memory byte offsets
-    int off_B, off_T, off_min, off_lab, off_ys, off_xs, off_units, off_tab, off_bar, total;
+    int nst;                                             // B stages in the ring
+    int off_B, off_T, off_min, off_lab, off_ys, off_units, off_tab, off_bar, total;
 };
 
 __host__ __device__ static inline int lm_round_up(int x, int a) { return (x + a - 1) / a * a; }
@@ -153,17 +167,20 @@ static bool lm_geometry(int H, int W, int C, int N, int d, LmGeom* g) {
     g->lab_rows = max_ys + 2 * d + 2;                    // (span) + 2*(ndy-1) + one spare row for the 2x2 block
     g->lab_pitch = lm_round_up(max_xs + 4 * d + 2 + 3, 16);             // + 3: the window starts at a multiple of 4 columns
     if (g->lab_rows * g->lab_pitch > 4 * LM_LABW * LM_EPI_THREADS) return false;
-    int o = LM_A_BYTES;
-    g->off_B = o; o += 2 * (512 * g->WB);                // 2 stages x [hi|lo][2 rows][WB columns][128 B] (one k-block of two rows)
-    g->off_T = o; o += LM_TSLOTS * g->D2 * 128 * 4;
-    g->off_min = o; o += (N + 1) * 4 * LM_EPI_THREADS * 4;
-    g->off_lab = o; o += lm_round_up(g->lab_rows * g->lab_pitch, 16);
-    g->off_ys = o; o += 2 * LM_ROWS * g->WB * 4;
-    g->off_xs = o; o += 128 * 4;
-    g->off_units = o; o += LM_MAXUNITS * 8 + 1024;
-    g->off_tab = o; o += 1024;
-    g->off_bar = o; o += 256;
-    g->total = o + 1024;                                 // slack: the base is aligned to 1024 bytes
+    // the ring of B stages takes what is left (the bulk-copy -> MMA loop is latency bound: bytes in flight are what counts)
+    for (g->nst = LM_MAX_STAGES; g->nst >= 2; --g->nst) {
+        int o = 0;
+        g->off_B = o; o += g->nst * (512 * g->WB);       // stage = [hi|lo][2 rows][WB columns][128 B] (one k-block of two rows)
+        g->off_T = o; o += LM_TSLOTS * g->D2 * 128 * 4;
+        g->off_min = o; o += (N + 1) * 4 * LM_EPI_THREADS * 4;
+        g->off_lab = o; o += lm_round_up(g->lab_rows * g->lab_pitch, 16);
+        g->off_ys = o; o += 2 * LM_ROWS * g->WB * 4;
+        g->off_units = o; o += LM_MAXUNITS * 8 + 1024;
+        g->off_tab = o; o += 1024;
+        g->off_bar = o; o += 256;
+        g->total = o + 1024;                             // slack: the base is aligned to 1024 bytes
+        if (g->total <= 227 * 1024) break;
+    }
     return g->total <= 227 * 1024;
 }
 
@@ -291,7 +308,8 @@ __device__ __forceinline__ float lm_pow2_scale(float a) {
 // scaled centred vector.  One block = 32 pixels x 16 chunks, a thread owns chunk t%8 of both k-blocks.
 //   blocks [0, HI * WI/32): previous frame, 32 columns of the padded image row iy (pixel row iy - YT):
 //       Bimg[iy][kb][hi|lo][ix][128 B], Ys[iy][ix] (+inf outside the frame -> T = 1, IntVOS.py:287-294)
-//   then 4 blocks per tile: query frame, Aimg[tile][hi|lo][kb][128 pixels][128 B], Xs[tile][128]
+//   then 4 blocks per tile: query frame, Aimg[tile][hi|lo][chunk][128 pixels][16 B] (the main kernel stores a pixel's chunks
+//       into its tensor-memory lane; chunk-major keeps those loads coalesced), Xs[tile][128]
 // Block 0 also publishes the scale for the main kernel.
 struct LmConvParams {
     const float* Pq; const float* Pp;                    // pooled [h][w][Cp]
@@ -396,10 +414,9 @@ lm_convert_kernel(const LmConvParams P) {
                 *reinterpret_cast<uint4*>(rowimg + (size_t)(kb * 2 + 0) * G.WI * 128 + o) = hi;
                 *reinterpret_cast<uint4*>(rowimg + (size_t)(kb * 2 + 1) * G.WI * 128 + o) = lo;
             } else {
-                uint8_t* img = P.Aimg + (size_t)tile * LM_A_BYTES;
-                const int o = (row >> 3) * 1024 + (row & 7) * 128 + ((chk ^ (row & 7)) << 4);
-                *reinterpret_cast<uint4*>(img + kb * 16384 + o) = hi;
-                *reinterpret_cast<uint4*>(img + 2 * 16384 + kb * 16384 + o) = lo;
+                uint4* img = reinterpret_cast<uint4*>(P.Aimg + (size_t)tile * LM_A_BYTES);
+                img[j * 128 + row] = hi;
+                img[(16 + j) * 128 + row] = lo;
             }
         }
     }
@@ -407,8 +424,10 @@ lm_convert_kernel(const LmConvParams P) {
     sq += __shfl_xor_sync(0xffffffffu, sq, 2);
     sq += __shfl_xor_sync(0xffffffffu, sq, 4);
     if (chk == 0) {
-        if (is_b) P.Ys[(size_t)iy * G.WI + ix] = inside ? sq : INFINITY;
-        else P.Xs[(size_t)tile * 128 + row] = sq;
+        // norms in units of the transform's exponent: D * log2(e) = (xs' + ys' - 2 acc) * log2(e) / s^2
+        const float karg = 1.4426950408889634f / (s * s);
+        if (is_b) P.Ys[(size_t)iy * G.WI + ix] = inside ? sq * karg : INFINITY;
+        else P.Xs[(size_t)tile * 128 + row] = sq * karg;
     }
 }
 
@@ -425,9 +444,6 @@ struct LmParams {
     LmGeom g;
 };
 
-#ifndef LM_ABL
-#define LM_ABL 0
-#endif
 #ifndef LM_BACKOFF_NS
 #define LM_BACKOFF_NS 96
 #endif
@@ -450,6 +466,19 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(LM_EPI_THREADS) : "memory"); }
 
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, uint4 a, uint4 b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, kind::f16, single CTA: A = 128 lanes (rows) x 8 columns (16 halves) per K step
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -475,10 +504,42 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
     uint32_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
+}
+// One window offset of a bilinear cell: the four T corners and the four label slots of its <= 2x2 outputs.
+struct LmOff { float v00, v01, v10, v11; uint32_t l0, l1, l2, l3; };
+// k: offsets ahead of the running pointers (compile-time: the addresses are register + immediate)
+__device__ __forceinline__ void lm_off_load(LmOff& x, uint32_t pa, uint32_t pb, uint32_t pl, uint32_t pl2, int k) {
+    x.v00 = lds_f32(pa + 512u * k); x.v01 = lds_f32(pa + 512u * k + 4u);
+    x.v10 = lds_f32(pb + 512u * k); x.v11 = lds_f32(pb + 512u * k + 4u);
+    x.l0 = lds_u8(pl + 2u * k); x.l1 = lds_u8(pl + 2u * k + 1u);
+    x.l2 = lds_u8(pl2 + 2u * k); x.l3 = lds_u8(pl2 + 2u * k + 1u);
+}
+__device__ __forceinline__ void lm_off_update(const LmOff& x, const float (&wx1)[2], const float (&wy1)[2],
+                                              const uint32_t (&min_base)[4], const int (&min_stride)[4]) {
+    const float dt = x.v01 - x.v00, db = x.v11 - x.v10;
+    float top[2], dv[2];
+#pragma unroll
+    for (int ix = 0; ix < 2; ++ix) {
+        top[ix] = fmaf(wx1[ix], dt, x.v00);
+        dv[ix] = fmaf(wx1[ix], db, x.v10) - top[ix];
+    }
+    const uint32_t lab[4] = {x.l0, x.l1, x.l2, x.l3};
+    // the four running minima never alias (different output planes): load all, then store all
+    uint32_t ad[4]; float old[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        ad[kk] = min_base[kk] + lab[kk] * (uint32_t)min_stride[kk];
+        old[kk] = lds_f32(ad[kk]);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        const float uval = fmaf(wy1[kk >> 1], dv[kk & 1], top[kk & 1]);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad[kk]), "f"(fminf(old[kk], uval)));
+    }
 }
 
 #ifdef LM_TRACE
@@ -512,20 +573,19 @@ lm_umma_kernel(const LmParams P) {
     float* sMin = reinterpret_cast<float*>(smem + G.off_min);
     uint8_t* sLab = smem + G.off_lab;
     float* sYs = reinterpret_cast<float*>(smem + G.off_ys);
-    float* sXs = reinterpret_cast<float*>(smem + G.off_xs);
     int2* sUnits = reinterpret_cast<int2*>(smem + G.off_units);
     int* sTab = reinterpret_cast<int*>(smem + G.off_tab);
     // sTab: [0..7] rowY0, [8..15] rowNy, [16..31] colX0, [32..47] colNx, [48] extra-unit counter,
     //       [50] tmem slot, [64..64+N) slot ids, [128..128+N) canonical slot
     const uint32_t bars = base + G.off_bar;
-    const uint32_t a_full = bars + 0;
-    const uint32_t b_full = bars + 8;          // [2]  stage landed (bulk copies)
-    const uint32_t b_empty = bars + 24;        // [2]  stage consumed by the MMAs
-    const uint32_t tmem_full = bars + 40;      // [2 buffers][2 row pairs]
-    const uint32_t tmem_empty = bars + 72;     // [2]
-    const uint32_t ys_full = bars + 88;        // [2]
-    const uint32_t t_full = bars + 104;        // [LM_TSLOTS]  row of T written by the four drain warps
-    const uint32_t t_empty = bars + 144;       // [LM_TSLOTS]  row of T no longer needed by the cells warps
+    const uint32_t a_full = bars + 0;          //      A rows stored to tensor memory by the four drain warps
+    const uint32_t b_full = bars + 8;          // [4]  stage landed (bulk copies)
+    const uint32_t b_empty = bars + 40;        // [4]  stage consumed by the MMAs
+    const uint32_t tmem_full = bars + 72;      // [2 buffers][2 row pairs]
+    const uint32_t tmem_empty = bars + 104;    // [2]
+    const uint32_t ys_full = bars + 120;       // [2]
+    const uint32_t t_full = bars + 136;        // [LM_TSLOTS]  row of T written by the four drain warps
+    const uint32_t t_empty = bars + 176;       // [LM_TSLOTS]  row of T no longer needed by the cells warps
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef LM_TRACE
@@ -534,9 +594,9 @@ lm_umma_kernel(const LmParams P) {
 
     if (warp == 1) {
         if (lane == 0) {
-            mbar_init(a_full, 1);
+            mbar_init(a_full, LM_DRAIN_WARPS);
+            for (int i = 0; i < LM_MAX_STAGES; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
             for (int i = 0; i < 2; ++i) {
-                mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1);
                 mbar_init(tmem_full + 16 * i, 1); mbar_init(tmem_full + 16 * i + 8, 1); mbar_init(tmem_empty + 8 * i, LM_DRAIN_WARPS);
                 mbar_init(ys_full + 8 * i, 1);
             }
@@ -558,23 +618,18 @@ lm_umma_kernel(const LmParams P) {
     const long long tr_sync = clock64() - tr0; long long tr_e1 = 0, tr_e2 = 0, tr_e3 = 0;
 #endif
     const int ksteps = G.ksteps, nkb = G.nkb;
+    const int nst = G.nst;
     const int n_stages = n_chunks * nkb * 2;                         // B stage = (chunk, pair of rows, k-block)
     const int n_trows = n_chunks * LM_ROWS;                          // rows of T that pass through the ring
     const uint32_t stage_bytes = 512u * (uint32_t)WB, row_bytes = 128u * (uint32_t)WB;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ bulk-copy producer (whole warp, one elected lane issues)
-        if (elect_one()) {
-            mbar_expect_tx(a_full, LM_A_BYTES + 128 * 4);
-            bulk_g2s(base, P.Aimg + (size_t)tile * LM_A_BYTES, LM_A_BYTES, a_full);
-            bulk_g2s(base + G.off_xs, P.Xs + (size_t)tile * 128, 128 * 4, a_full);
-        }
-        __syncwarp();
         const uint8_t* bimg = P.Bimg + (size_t)(xa + G.XL) * 128;
         const float* ysrc = P.Ys + (xa + G.XL);
         for (int q = 0; q < n_stages; ++q) {
             const int kb = q % nkb, hf = (q / nkb) & 1, c = q / (2 * nkb);
-            const int buf = c & 1, sl = q & 1, r0 = r_first + c * LM_ROWS;
+            const int buf = c & 1, sl = q % nst, use = q / nst, r0 = r_first + c * LM_ROWS;
             if (kb == 0 && hf == 0) {
                 mbar_wait_sleep(tmem_empty + 8 * buf, ((c >> 1) & 1) ^ 1);   // drain(c-2) has read ys[buf]
                 if (elect_one()) {
@@ -585,7 +640,7 @@ lm_umma_kernel(const LmParams P) {
                 }
                 __syncwarp();
             }
-            mbar_wait_sleep(b_empty + 8 * sl, ((q >> 1) & 1) ^ 1);
+            mbar_wait_sleep(b_empty + 8 * sl, (use & 1) ^ 1);
             if (elect_one()) {
                 mbar_expect_tx(b_full + 8 * sl, stage_bytes);
                 const uint32_t dst = base + G.off_B + sl * stage_bytes;
@@ -602,7 +657,7 @@ lm_umma_kernel(const LmParams P) {
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
         const uint32_t idesc = idesc_f16(128, 2 * WB);
-        const uint64_t dA_hi = smem_desc_sw128(base), dA_lo = smem_desc_sw128(base + 2 * 16384);
+        const uint32_t tA_hi = tmem_base + LM_A_COL_HI, tA_lo = tmem_base + LM_A_COL_LO;   // 8 columns (16 halves) per K step
         mbar_wait_sleep(a_full, 0);
         tc_fence_after();
 #ifdef LM_TRACE
@@ -610,9 +665,9 @@ lm_umma_kernel(const LmParams P) {
 #endif
         for (int q = 0; q < n_stages; ++q) {
             const int kb = q % nkb, hf = (q / nkb) & 1, c = q / (2 * nkb);
-            const int buf = c & 1, sl = q & 1;
+            const int buf = c & 1, sl = q % nst, use = q / nst;
             if (kb == 0 && hf == 0) { TR(tr_w1, mbar_wait_sleep(tmem_empty + 8 * buf, ((c >> 1) & 1) ^ 1)); }
-            TR(tr_w2, mbar_wait_sleep(b_full + 8 * sl, (q >> 1) & 1));
+            TR(tr_w2, mbar_wait_sleep(b_full + 8 * sl, use & 1));
             tc_fence_after();
 #ifdef LM_TRACE
             if (q == 0) tr_e2 = clock64() - tr0;
@@ -622,15 +677,16 @@ lm_umma_kernel(const LmParams P) {
             const uint64_t dB_hi = smem_desc_sw128(base + G.off_B + sl * stage_bytes);
             const uint64_t dB_lo = smem_desc_sw128(base + G.off_B + sl * stage_bytes + 2 * row_bytes);
             const int ks = min(ksteps - 4 * kb, 4);
-            const uint64_t a_off = (uint64_t)(kb * (16384 >> 4));
+            const uint32_t a_off = (uint32_t)(kb * 32);
             if (elect_one()) {
                 for (int k = 0; k < ks; ++k) {
                     const uint64_t o = (uint64_t)(2 * k);
-                    umma_f16(d_tmem, dA_hi + a_off + o, dB_hi + o, idesc, (kb | k) ? 1u : 0u);
-                    umma_f16(d_tmem, dA_lo + a_off + o, dB_hi + o, idesc, 1u);
-                    umma_f16(d_tmem, dA_hi + a_off + o, dB_lo + o, idesc, 1u);
+                    const uint32_t ac = a_off + 8u * (uint32_t)k;
+                    umma_f16_ts(d_tmem, tA_hi + ac, dB_hi + o, idesc, (kb | k) ? 1u : 0u);
+                    umma_f16_ts(d_tmem, tA_lo + ac, dB_hi + o, idesc, 1u);
+                    umma_f16_ts(d_tmem, tA_hi + ac, dB_lo + o, idesc, 1u);
 #ifndef LM_DROP_LOLO
-                    umma_f16(d_tmem, dA_lo + a_off + o, dB_lo + o, idesc, 1u);
+                    umma_f16_ts(d_tmem, tA_lo + ac, dB_lo + o, idesc, 1u);
 #endif
                 }
                 tc_commit(b_empty + 8 * sl);
@@ -643,10 +699,28 @@ lm_umma_kernel(const LmParams P) {
         const int wq = warp & 3;                                     // TMEM lane quarter this warp may read
         const int m = wq * 32 + lane, qy = m >> 4, qx = m & 15;
         const float scale = __ldg(P.stats);
-        const float karg = 1.4426950408889634f / (scale * scale);   // D * log2(e) = (xs' + ys' - 2 acc) * karg  (norms are scaled by s^2)
+        const float m2k = -2.0f * 1.4426950408889634f / (scale * scale);   // D * log2(e) = xs'' + ys'' + m2k * acc  (norms arrive pre-multiplied)
         const int L = D2 * D2;
-        TR(tr_w1, mbar_wait_sleep(a_full, 0));
-        const float xs_m = sXs[m];
+        const float xs_m = __ldg(P.Xs + (size_t)tile * 128 + m);
+        {
+            // A operand: this thread's pixel row (hi, lo: 16 halves = 8 TMEM columns per K step) -> tensor memory
+            const uint4* arow = reinterpret_cast<const uint4*>(P.Aimg + (size_t)tile * LM_A_BYTES) + m;
+            const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
+#pragma unroll 1
+            for (int part = 0; part < 2; ++part) {
+                uint4 v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = (j < 2 * ksteps) ? __ldg(arow + (part * 16 + j) * 128) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (k < ksteps)
+                        tmem_st8(lane_base + (part ? LM_A_COL_LO : LM_A_COL_HI) + 8 * k, v[2 * k], v[2 * k + 1]);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+        }
         const bool q_in = (qy0 + qy < h) && (qx0 + qx < w);
         for (int c = 0; c < n_chunks; ++c) {
             const int buf = c & 1, r0 = r_first + c * LM_ROWS;
@@ -669,11 +743,7 @@ lm_umma_kernel(const LmParams P) {
                 // a query row needs exactly the previous rows with dyA <= dyi <= dyB (as top AND as bottom row of a cell)
                 const bool row_used = VOL ? (dyi >= 0 && dyi < D2) : (dyi >= dyA && dyi <= dyB);
                 if (do_cells) { TR(tr_w2, mbar_wait_sleep(t_empty + 8 * slot, ((k / LM_TSLOTS) & 1) ^ 1)); }   // the cells warps are done with the row this one replaces
-#if LM_ABL == 3      /* no drain work */
-                if (false) {
-#else
                 if (__any_sync(0xffffffffu, row_used)) {
-#endif
                     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * 256 + jr * WB + off8);
                     uint32_t acc[40];
 #pragma unroll
@@ -694,7 +764,7 @@ lm_umma_kernel(const LmParams P) {
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
                                 // rounding can leave D (hence T) a hair below zero; the merge clamps
-                                tv[e] = lm_transform(fmaf(-2.0f, __uint_as_float(acc[g8 * 8 + e]), xs_m + ysr[g8 * 8 + e]) * karg);
+                                tv[e] = lm_transform(fmaf(m2k, __uint_as_float(acc[g8 * 8 + e]), xs_m + ysr[g8 * 8 + e]));
                             }
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
@@ -831,9 +901,6 @@ lm_umma_kernel(const LmParams P) {
             min_stride[k] = have ? 4 * LM_EPI_THREADS * 4 : 0;
         }
         // pairs (previous row r-1 over query row y0, previous row r over query row y0+1), one ring row at a time
-#if LM_ABL == 1
-        float abl[4] = {1.f, 1.f, 1.f, 1.f};
-#endif
         TR(tr_w1, mbar_wait(t_full, 0));
 #pragma unroll 1
         for (int k = 1; k < n_trows; ++k) {
@@ -844,47 +911,35 @@ lm_umma_kernel(const LmParams P) {
             long long _tc = clock64();
 #endif
             const int dyi = (r - 1) - y0c + d;
-#if LM_ABL == 2      /* no cells work at all */
-            if (false) {
-#else
             if (active && dyi >= dyA && dyi <= dyB) {
-#endif
-                // The kernel is issue bound (ncu: the warps of this loop are "selected"/"not selected" most of the time), so
-                // the loop is written for instruction count: byte label loads (no extraction), bilinear weights in
-                // difference form (12 FP instructions for the four outputs instead of 16).
-                const float* Tt = sT + (size_t)slot_t * D2 * 128 + m00;
-                const float* Tb = sT + (size_t)slot_b * D2 * 128 + m00 + LM_TW;
-                const uint8_t* lp = lab0 + 2 * (dyi - dyA) * LP;
-#pragma unroll 2
-                for (int dxi = dx_lo; dxi < dx_hi; ++dxi) {
-                    const float v00 = Tt[dxi * 128], v01 = Tt[dxi * 128 + 1];
-                    const float v10 = Tb[dxi * 128], v11 = Tb[dxi * 128 + 1];
-                    const uint8_t* l2 = lp + 2 * dxi;
-                    const int lab[4] = {l2[0], l2[1], l2[LP], l2[LP + 1]};
-                    const float dt = v01 - v00, db = v11 - v10;
-                    float top[2], dv[2];
-#pragma unroll
-                    for (int ix = 0; ix < 2; ++ix) {
-                        top[ix] = fmaf(wx1[ix], dt, v00);
-                        dv[ix] = fmaf(wx1[ix], db, v10) - top[ix];
-                    }
-                    // the four running minima never alias (different output planes): load all, then store all
-                    uint32_t ad[4]; float old[4];
-#if LM_ABL == 1      /* no shared-memory minima: fold everything into registers (wrong results, timing only) */
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) abl[kk] = fminf(abl[kk], fmaf(wy1[kk >> 1], dv[kk & 1], top[kk & 1]) + (float)lab[kk]);
-#else
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        ad[kk] = min_base[kk] + (uint32_t)(lab[kk] * min_stride[kk]);
-                        old[kk] = lds_f32(ad[kk]);
-                    }
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const float uval = fmaf(wy1[kk >> 1], dv[kk & 1], top[kk & 1]);
-                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad[kk]), "f"(fminf(old[kk], uval)));
-                    }
-#endif
+                // Two bounds meet in this loop.  Issue slots: with all cells warps busy the SM issues ~0.8 instructions per
+                // scheduler and cycle, so an offset is written for instruction count (byte label loads, bilinear weights in
+                // difference form, immediate address offsets).  Latency: ptxas may not move a shared-memory load above a
+                // possibly aliasing store, so left alone every offset exposes load -> FP -> min chains (~170 cycles);
+                // the loads of offset dx+1 are therefore issued, in program order, before the minima of offset dx are updated
+                // (two register sets, no rotation moves).
+                uint32_t pa = smem_u32(sT + (size_t)slot_t * D2 * 128 + m00) + 512u * dx_lo;
+                uint32_t pb = smem_u32(sT + (size_t)slot_b * D2 * 128 + m00 + LM_TW) + 512u * dx_lo;
+                uint32_t pl = smem_u32(lab0 + 2 * (dyi - dyA) * LP) + 2u * dx_lo;
+                uint32_t pl2 = pl + LP;
+                LmOff A, B;
+                const int n = dx_hi - dx_lo;
+                lm_off_load(A, pa, pb, pl, pl2, 0);
+                int i = 0;
+#pragma unroll 1
+                for (; i + 2 < n; i += 2) {
+                    lm_off_load(B, pa, pb, pl, pl2, 1);
+                    lm_off_update(A, wx1, wy1, min_base, min_stride);
+                    lm_off_load(A, pa, pb, pl, pl2, 2);
+                    lm_off_update(B, wx1, wy1, min_base, min_stride);
+                    pa += 1024u; pb += 1024u; pl += 4u; pl2 += 4u;
+                }
+                if (n - i == 2) {
+                    lm_off_load(B, pa, pb, pl, pl2, 1);
+                    lm_off_update(A, wx1, wy1, min_base, min_stride);
+                    lm_off_update(B, wx1, wy1, min_base, min_stride);
+                } else {
+                    lm_off_update(A, wx1, wy1, min_base, min_stride);
                 }
             }
 #ifdef LM_TRACE
@@ -896,9 +951,6 @@ lm_umma_kernel(const LmParams P) {
         }
         // ---- merge: the dx parts of a unit are combined in shared memory (part p takes outputs 2p, 2p+1), the two halves of
         // the dy range with atomicMin on the float bits of the pre-filled output
-#if LM_ABL == 1
-        if (abl[0] + abl[1] + abl[2] + abl[3] == -1.f) sMin[et] = 0.f;
-#endif
         epi_bar_sync();
         if (active) {
 #pragma unroll
