@@ -41,7 +41,7 @@ ALGO_FLOP_GLOBAL = 2.0 * M_PIX * M_PIX * C                      # 2*M*R*C, SURVE
 ALGO_BYTES_LOCAL = 4.0 * (2 * C * H * W + H * W + H * W * N_IDS)
 # executed tensor-core work: M padded to 256, R padded per 256-row bucket, K steps of 16 (see gm_fold_remainder)
 EXEC_FLOP_GLOBAL = 2.0 * (101 * 256) * (103 * 256) * 16 * 19   # 19 K=16 MMA steps per tile (7 + 6 + 6, remainder folded)
-KERNELS_PER_STEP = 8   # scan, convert, umma, finalize | pool(+label pad), window, upsample-mask-min | local-map store/select
+KERNELS_PER_STEP = 8   # gm_scan, gm_convert, gm_umma2, gm_finalize | lm_pool, lm_convert, lm_umma | local-map store/select
 
 
 def load_peaks():
@@ -233,7 +233,7 @@ def run_own_arm(args, rank, local_rank, world):
     serial_s, _ = timed_pass(serial=True)
     # kernel timings recorded inside the library on the launching stream (serial pass)
     prof = {}
-    for slot, name in ((0, "global_tcgen05"), (1, "local_window"), (2, "local_upsample_mask_min")):
+    for slot, name in ((0, "global_tcgen05"), (1, "local_main"), (2, "local_prepass")):
         buf = (ctypes.c_float * (K + 4))()
         n = ctypes.c_int(0)
         _lib.check(L.manet_profile_read(slot, buf, K + 4, ctypes.byref(n)), "manet_profile_read")
@@ -292,10 +292,14 @@ def run_own_arm(args, rank, local_rank, world):
                     "peak_source": peaks["source"],
                     "algorithmic_flop_per_launch": ALGO_FLOP_GLOBAL,
                     "executed_mma_flop_per_launch": EXEC_FLOP_GLOBAL,
-                    "local": {"bound": "hbm", "algorithmic_bytes": ALGO_BYTES_LOCAL,
-                              "window_kernel_ms": prof["local_window"], "min_kernel_ms": prof["local_upsample_mask_min"],
-                              "achieved_gbs": (ALGO_BYTES_LOCAL / ((prof["local_window"] + prof["local_upsample_mask_min"]) * 1e-3) / 1e9)
-                              if prof["local_window"] and prof["local_upsample_mask_min"] else None,
+                    "local": {"kernels": "lm_pool + lm_convert (pre-pass), lm_umma_kernel (tcgen05 banded GEMM + transform + bilinear cells + per-object min)"
+                                         if os.environ.get("MANET_LM_ENGINE", "")[:1].lower() != "s" else
+                                         "window_dist_kernel, upsample_mask_min_kernel (CUDA-core engine; pre-pass not timed)",
+                              "bound": "hbm (north star); measured bound: instruction issue, see DESIGN.md section 4",
+                              "algorithmic_bytes": ALGO_BYTES_LOCAL,
+                              "main_kernel_ms": prof["local_main"], "prepass_ms": prof["local_prepass"],
+                              "achieved_gbs": (ALGO_BYTES_LOCAL / ((prof["local_main"] + prof["local_prepass"]) * 1e-3) / 1e9)
+                              if prof["local_main"] and prof["local_prepass"] else None,
                               "peak_gbs": peaks["hbm_gbs"]}}
         line = {"metric": "matched frames/sec (global+local, 480p, 5 obj)", "value": world * K / total_s,
                 "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": total_s * 1e3 / K,

@@ -1040,12 +1040,14 @@ int launch_local_match_umma(const float* prev, int64_t p_sy, int64_t p_sx, int64
         const int rest = g.w - (mub.blk[k] % g.nbx) * LM_POOL_PX;
         mub.count += rest < LM_POOL_PX ? rest : LM_POOL_PX;
     }
+    profile_begin(PROF_LOCAL_MIN, stream);                // tcgen05 engine: slot 2 = the two pre-pass kernels, slot 1 = the main kernel
     lm_pool_kernel<<<dim3(g.nbx, g.h, 3), 256, pool_smem, stream>>>(a, b, aux, C, g.Cp, g.h, g.w, blkmax, blksum, mub);
     LmConvParams CP;
     memset(&CP, 0, sizeof(CP));
     CP.Pq = Pq; CP.Pp = Pp; CP.blkmax = blkmax; CP.n_blkmax = n_blk; CP.blksum = blksum;
     CP.Aimg = Aimg; CP.Xs = Xs; CP.Bimg = Bimg; CP.Ys = Ys; CP.stats = stats; CP.mub = mub; CP.g = g;
     lm_convert_kernel<<<g.HI * (g.WI >> 5) + 4 * n_tiles, 256, 0, stream>>>(CP);
+    profile_end(PROF_LOCAL_MIN, stream);
     P.Aimg = Aimg; P.Xs = Xs; P.Bimg = Bimg; P.Ys = Ys; P.stats = stats;
     P.plab8 = labels ? plab8 : nullptr; P.gt_ids = gt_ids; P.out = labels ? out : nullptr;
     P.T_vol = T_out ? Tvol : nullptr;

@@ -10,7 +10,7 @@ try:
     d=json.loads(open('gpurun_out/bench.log').read().strip().splitlines()[-1])
     r=d['roofline']
     print('value',round(d['value'],1),'fps  ms/step',round(d['ms_per_step'],4),' e2e',round(d['e2e']['value'],1))
-    print('umma ms',r['kernel_ms'],'frac',r['frac'],' window ms',r['local']['window_kernel_ms'],' min ms',r['local']['min_kernel_ms'])
+    print('umma ms',r['kernel_ms'],'frac',r['frac'],' local main ms',r['local']['main_kernel_ms'],' prepass ms',r['local']['prepass_ms'])
     print('clocks',d['clocks'])
 except Exception as e:
     print('bench parse failed',e); print(open('gpurun_out/bench.log').read()[-2000:])

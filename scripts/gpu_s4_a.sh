@@ -13,7 +13,7 @@ for f in ('bench_umma','bench_simt'):
         d=json.loads(open(f'gpurun_out/{f}.log').read().strip().splitlines()[-1])
         r=d['roofline']
         print(f,'value',round(d['value'],1),'ms/step',round(d['ms_per_step'],4),'single',round(d['single_stream']['ms_per_step'],4),'e2e',round(d['e2e']['value'],1),
-              'umma ms',round(r['kernel_ms'],4),'window ms',r['local']['window_kernel_ms'],'min ms',r['local']['min_kernel_ms'])
+              'umma ms',round(r['kernel_ms'],4),'local main ms',r['local']['main_kernel_ms'],'prepass ms',r['local']['prepass_ms'])
     except Exception as e:
         print(f,'parse failed',e); print(open(f'gpurun_out/{f}.log').read()[-1500:])
 PY
