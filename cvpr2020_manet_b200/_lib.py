@@ -40,6 +40,11 @@ SIGNATURES = {
     "manet_local_match_ex": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _P, _P, _I, _I, _I, _I, _I, c_uint32, _P, _P, _SZ, _P]),
     "manet_local_window_distances_ex": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I, _I, _I, _I, c_uint32, _P, _P, _SZ, _P]),
     "manet_local_window_distances": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I, _I, _I, _I, _P, _P, _SZ, _P]),
+    "manet_global_match_argmin": (c_int, [_P, _I64, _I64, _I64, _P, _P, _I64, _I64, _I64, _I, _I, _P, _P, _P]),
+    "manet_global_match_backward": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I, _I, _P, _P, _P, _P, _P]),
+    "manet_local_match_grad_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
+    "manet_local_match_argmin": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _SZ, _P]),
+    "manet_local_match_backward": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
     "manet_global_map_update": (c_int, [_P, _P, _P, _I64, _I, _P]),
     "manet_local_map_store_select": (c_int, [_P, _P, _P, _I, _F, _P, _I64, _P]),
     "manet_correlation_output_shape": (c_int, [_I, _I, _I, _I, _I, _I, _I, _I, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),

@@ -42,6 +42,15 @@ int launch_local_match(const float*, int64_t, int64_t, int64_t, const float*, in
 int launch_local_window_distances(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, int, int,
                                   int, int, uint32_t, float*, void*, size_t, cudaStream_t);
 int launch_local_map_store_select(const float*, float*, float*, int, float, float*, int64_t, cudaStream_t);
+int launch_global_match_argmin(const float*, int64_t, int64_t, int64_t, const int32_t*, const float*, int64_t, int64_t, int64_t,
+                               int, int, float*, int32_t*, cudaStream_t);
+int launch_global_match_backward(const float*, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, int, int,
+                                 const int32_t*, const float*, float*, float*, cudaStream_t);
+size_t local_match_grad_workspace_bytes(int H, int W, int C, int d);
+int launch_local_match_argmin(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, const int32_t*,
+                              const int32_t*, int, int, int, int, int, float*, int32_t*, void*, size_t, cudaStream_t);
+int launch_local_match_backward(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, int, int, int,
+                                int, int, const int32_t*, const float*, float*, float*, void*, size_t, cudaStream_t);
 int correlation_output_shape(int, int, int, int, int, int, int, int, int*, int*, int*);
 int launch_correlation_forward(const void*, const int64_t*, const void*, const int64_t*, void*, void*, void*, int, int, int, int,
                                int, int, int, int, int, int, cudaStream_t);
@@ -199,6 +208,53 @@ int manet_local_window_distances(const float* x, int64_t x_sy, int64_t x_sx, int
                                  void* workspace, size_t workspace_bytes, manet_stream_t stream) {
     return manet_local_window_distances_ex(x, x_sy, x_sx, x_sc, y, y_sy, y_sx, y_sc, H, W, C, max_distance, 0u, out,
                                            workspace, workspace_bytes, stream);
+}
+
+int manet_global_match_argmin(const float* ref, int64_t ref_pix_stride, int64_t ref_ch_stride, int64_t R,
+                              const int32_t* labels, const float* query, int64_t q_pix_stride, int64_t q_ch_stride,
+                              int64_t M, int C, int N, float* out, int32_t* out_idx, manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(query && out && out_idx && (R == 0 || (ref && labels)), "global match (argmin): null pointer");
+    MANET_REQUIRE(M >= 0 && R >= 0 && C >= 1 && N >= 1, "global match (argmin): bad sizes");
+    return launch_global_match_argmin(ref, ref_pix_stride, ref_ch_stride, R, labels, query, q_pix_stride, q_ch_stride, M, C, N,
+                                      out, out_idx, (cudaStream_t)stream);
+}
+
+int manet_global_match_backward(const float* ref, int64_t ref_pix_stride, int64_t ref_ch_stride, int64_t R,
+                                const float* query, int64_t q_pix_stride, int64_t q_ch_stride, int64_t M, int C, int N,
+                                const int32_t* idx, const float* grad_out, float* grad_query, float* grad_ref,
+                                manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(query && idx && grad_out && (R == 0 || ref), "global match backward: null pointer");
+    MANET_REQUIRE(M >= 0 && R >= 0 && C >= 1 && N >= 1, "global match backward: bad sizes");
+    return launch_global_match_backward(ref, ref_pix_stride, ref_ch_stride, query, q_pix_stride, q_ch_stride, M, C, N, idx,
+                                        grad_out, grad_query, grad_ref, (cudaStream_t)stream);
+}
+
+size_t manet_local_match_grad_workspace_bytes(int H, int W, int C, int N, int max_distance) {
+    (void)N;
+    return local_match_grad_workspace_bytes(H, W, C, max_distance);
+}
+
+int manet_local_match_argmin(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_sc, const float* query, int64_t q_sy,
+                             int64_t q_sx, int64_t q_sc, const int32_t* labels, const int32_t* gt_ids, int H, int W, int C,
+                             int N, int max_distance, float* out, int32_t* out_idx, void* workspace, size_t workspace_bytes,
+                             manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(prev && query && labels && gt_ids && out && out_idx && workspace, "local match (argmin): null pointer");
+    return launch_local_match_argmin(prev, p_sy, p_sx, p_sc, query, q_sy, q_sx, q_sc, labels, gt_ids, H, W, C, N, max_distance,
+                                     out, out_idx, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int manet_local_match_backward(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_sc, const float* query, int64_t q_sy,
+                               int64_t q_sx, int64_t q_sc, int H, int W, int C, int N, int max_distance, const int32_t* idx,
+                               const float* grad_out, float* grad_prev, float* grad_query, void* workspace,
+                               size_t workspace_bytes, manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(prev && query && idx && grad_out && workspace, "local match backward: null pointer");
+    MANET_REQUIRE(N >= 1, "local match backward: N must be >= 1");
+    return launch_local_match_backward(prev, p_sy, p_sx, p_sc, query, q_sy, q_sx, q_sc, H, W, C, N, max_distance, idx, grad_out,
+                                       grad_prev, grad_query, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int manet_global_map_update(const float* new_map, float* mem_frame, float* out, int64_t n, int normalize,

@@ -216,3 +216,107 @@ int launch_global_map_update(const float* nw, float* mem, float* out, int64_t n,
 }
 
 }  // namespace manet
+
+// ------------------------------------------------------------------------------------ autograd support (k = 1)
+// The reference's matching functions are differentiable torch graphs (train_stage1.py:126 back-propagates through them,
+// SURVEY.md section 8f-1).  For k = 1 the gradient of min_r |q - r|^2 flows through the arg-min reference pixel only:
+// d/dq = 2 (q - r*) g, d/dr* = -2 (q - r*) g.  Forward-for-training = this fp32 kernel, which also returns r*.
+namespace manet {
+
+__global__ void __launch_bounds__(SIMT_THREADS)
+global_match_argmin_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64_t R,
+                           const int32_t* __restrict__ labels, const float* __restrict__ query, int64_t qps, int64_t qcs,
+                           int64_t M, int C, int N, float* __restrict__ out, int32_t* __restrict__ out_idx) {
+    __shared__ float Qs[CK][TQ + 1];
+    __shared__ float Rs[CK][TR + 1];
+    __shared__ float D[TQ][TR + 1];
+    __shared__ float xs[TQ], ys[TR];
+    __shared__ int lab[TR];
+    extern __shared__ float dyn[];                       // best value [N][TQ], best index [N][TQ]
+    float* bestv = dyn;
+    int* besti = reinterpret_cast<int*>(dyn + (size_t)N * TQ);
+
+    const int t = threadIdx.x;
+    const int64_t m0 = (int64_t)blockIdx.x * TQ;
+    if (t < TQ) xs[t] = (m0 + t < M) ? sq_norm(query + (m0 + t) * qps, qcs, C) : 0.f;
+    for (int i = t; i < N * TQ; i += SIMT_THREADS) { bestv[i] = INFINITY; besti[i] = -1; }
+    __syncthreads();
+    for (int64_t r0 = 0; r0 < R; r0 += TR) {
+        if (t < TR) {
+            bool ok = r0 + t < R;
+            ys[t] = ok ? sq_norm(ref + (r0 + t) * rps, rcs, C) : 0.f;
+            lab[t] = ok ? labels[r0 + t] : -1;
+        }
+        float acc[4][4];
+        tile_dot(query, qps, qcs, m0, M, ref, rps, rcs, r0, R, C, Qs, Rs, acc);
+        const int ty = t / 16, tx = t % 16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                D[ty * 4 + i][tx * 4 + j] = (xs[ty * 4 + i] + ys[tx * 4 + j]) - 2.f * acc[i][j];
+        __syncthreads();
+        const int nr = (int)min((int64_t)TR, R - r0);
+        for (int p = t; p < N * TQ; p += SIMT_THREADS) {
+            const int m = p % TQ, o = p / TQ;
+            float bv = bestv[p]; int bi = besti[p];
+            for (int j = 0; j < nr; ++j)
+                if (lab[j] == o && D[m][j] < bv) { bv = D[m][j]; bi = (int)(r0 + j); }   // first occurrence wins ties
+            bestv[p] = bv; besti[p] = bi;
+        }
+        __syncthreads();
+    }
+    for (int p = t; p < N * TQ; p += SIMT_THREADS) {
+        const int m = p % TQ, o = p / TQ;
+        if (m0 + m >= M) continue;
+        out[(m0 + m) * N + o] = (besti[p] < 0) ? kWrongLabelPad : bestv[p];
+        out_idx[(m0 + m) * N + o] = besti[p];
+    }
+}
+
+// one warp per query pixel; grad_ref must be zero on entry (scatter-add)
+__global__ void __launch_bounds__(256)
+global_match_backward_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs,
+                             const float* __restrict__ query, int64_t qps, int64_t qcs, int64_t M, int C, int N,
+                             const int32_t* __restrict__ idx, const float* __restrict__ grad_out,
+                             float* __restrict__ grad_query, float* __restrict__ grad_ref) {
+    const int lane = threadIdx.x & 31;
+    const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (m >= M) return;
+    for (int c = lane; c < C; c += 32) {
+        const float q = __ldg(query + m * qps + (int64_t)c * qcs);
+        float gq = 0.f;
+        for (int o = 0; o < N; ++o) {
+            const int r = idx[m * N + o];
+            if (r < 0) continue;                         // absent object: constant 1e20, no gradient
+            const float g = grad_out[m * N + o];
+            const float t2 = 2.f * g * (q - __ldg(ref + (int64_t)r * rps + (int64_t)c * rcs));
+            gq += t2;
+            if (grad_ref) atomicAdd(grad_ref + (int64_t)r * C + c, -t2);
+        }
+        if (grad_query) grad_query[m * C + c] = gq;
+    }
+}
+
+int launch_global_match_argmin(const float* ref, int64_t rps, int64_t rcs, int64_t R, const int32_t* labels,
+                               const float* query, int64_t qps, int64_t qcs, int64_t M, int C, int N, float* out,
+                               int32_t* out_idx, cudaStream_t stream) {
+    size_t dyn = (size_t)N * TQ * 2 * sizeof(float);
+    if (dyn > 160 * 1024) return fail_invalid("global match (argmin): too many objects");
+    if (M == 0) return 0;
+    cudaFuncSetAttribute(global_match_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    global_match_argmin_kernel<<<(unsigned)ceil_div64(M, TQ), SIMT_THREADS, dyn, stream>>>(ref, rps, rcs, R, labels, query, qps,
+                                                                                             qcs, M, C, N, out, out_idx);
+    return check_launch("global_match_argmin_kernel");
+}
+
+int launch_global_match_backward(const float* ref, int64_t rps, int64_t rcs, const float* query, int64_t qps, int64_t qcs,
+                                 int64_t M, int C, int N, const int32_t* idx, const float* grad_out, float* grad_query,
+                                 float* grad_ref, cudaStream_t stream) {
+    if (M == 0) return 0;
+    global_match_backward_kernel<<<(unsigned)ceil_div64(M, 8), 256, 0, stream>>>(ref, rps, rcs, query, qps, qcs, M, C, N, idx,
+                                                                                grad_out, grad_query, grad_ref);
+    return check_launch("global_match_backward_kernel");
+}
+
+}  // namespace manet

@@ -438,4 +438,171 @@ int launch_local_window_distances(const float* x, int64_t x_sy, int64_t x_sx, in
     return check_launch("upsample_volume_kernel");
 }
 
+
+// ---------------------------------------------------------------- autograd support
+// The reference's local matching is a differentiable torch graph (train_stage1.py:126).  Per output (Y, X, object) the
+// gradient flows through the arg-min window offset l* only (none when the result is the pad value 1):
+//   out = U[l*] = bilinear(T[l*]) -> four half-resolution corners, T = tanh(D / 2) -> dT/dD = (1 - T^2) / 2,
+//   D = sum_c (qs - ps)^2 -> dD/dqs = 2 (qs - ps) = -dD/dps, avg_pool2d -> a quarter to each of the 2x2 inputs.
+// Forward-for-training = the CUDA-core window kernels plus an arg-min flavour of the masked-min kernel.
+__global__ void __launch_bounds__(UP_STRIDE)
+local_min_argmin_kernel(const float* __restrict__ T, const int32_t* __restrict__ plabels, const int32_t* __restrict__ gt_ids,
+                        int H, int W, int h, int w, int d, int N, float* __restrict__ out, int32_t* __restrict__ out_idx) {
+    extern __shared__ float sbest[];                         // value [N][UP_STRIDE], offset [N][UP_STRIDE]
+    float* bv = sbest;
+    int* bi = reinterpret_cast<int*>(sbest + (size_t)N * UP_STRIDE);
+    const int win = 2 * d + 1, L = win * win;
+    const int lane = threadIdx.x & 31, tid = threadIdx.x;
+    const int pix = blockIdx.x * UP_WARPS + (tid >> 5);
+    for (int o = 0; o < N; ++o) { bv[o * UP_STRIDE + tid] = 1.0f; bi[o * UP_STRIDE + tid] = -1; }
+    if (pix >= H * W) return;
+    const int Y = pix / W, X = pix - Y * W;
+    const Lerp ly = make_lerp(Y, h, H), lx = make_lerp(X, w, W);
+    const float* t00 = T + ((size_t)ly.i0 * w + lx.i0) * L;
+    const float* t01 = T + ((size_t)ly.i0 * w + lx.i1) * L;
+    const float* t10 = T + ((size_t)ly.i1 * w + lx.i0) * L;
+    const float* t11 = T + ((size_t)ly.i1 * w + lx.i1) * L;
+    const int PW = W + 4 * d;
+    for (int l = lane; l < L; l += 32) {
+        const int dyi = l / win, dxi = l % win;
+        const float u = bilerp(__ldg(t00 + l), __ldg(t01 + l), __ldg(t10 + l), __ldg(t11 + l), ly, lx);
+        const float lf = (float)__ldg(plabels + (size_t)(Y + 2 * dyi) * PW + X + 2 * dxi);
+        for (int o = 0; o < N; ++o)
+            if (lf == (float)gt_ids[o] && u < bv[o * UP_STRIDE + tid]) { bv[o * UP_STRIDE + tid] = u; bi[o * UP_STRIDE + tid] = l; }
+    }
+    for (int o = 0; o < N; ++o) {
+        float v = bv[o * UP_STRIDE + tid]; int i = bi[o * UP_STRIDE + tid];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            const float v2 = __shfl_xor_sync(0xffffffffu, v, s);
+            const int i2 = __shfl_xor_sync(0xffffffffu, i, s);
+            if (v2 < v || (v2 == v && i2 >= 0 && (i < 0 || i2 < i))) { v = v2; i = i2; }
+        }
+        if (lane == 0) { out[(size_t)pix * N + o] = v; out_idx[(size_t)pix * N + o] = i; }
+    }
+}
+
+// dT[y, x, l*] += w_y w_x g for the four corners of every (pixel, object) with an arg-min
+__global__ void local_scatter_dt_kernel(const int32_t* __restrict__ idx, const float* __restrict__ grad_out, int H, int W,
+                                        int h, int w, int L, int N, float* __restrict__ dT) {
+    const int64_t total = (int64_t)H * W * N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int l = idx[i];
+        if (l < 0) continue;
+        const float g = grad_out[i];
+        const int64_t pix = i / N;
+        const int X = (int)(pix % W), Y = (int)(pix / W);
+        const Lerp ly = make_lerp(Y, h, H), lx = make_lerp(X, w, W);
+        atomicAdd(dT + ((size_t)ly.i0 * w + lx.i0) * L + l, ly.w0 * lx.w0 * g);
+        atomicAdd(dT + ((size_t)ly.i0 * w + lx.i1) * L + l, ly.w0 * lx.w1 * g);
+        atomicAdd(dT + ((size_t)ly.i1 * w + lx.i0) * L + l, ly.w1 * lx.w0 * g);
+        atomicAdd(dT + ((size_t)ly.i1 * w + lx.i1) * L + l, ly.w1 * lx.w1 * g);
+    }
+}
+
+// one warp per half-resolution query pixel; dps must be zero on entry (scatter-add)
+__global__ void __launch_bounds__(256)
+local_backward_dist_kernel(const float* __restrict__ qs, const float* __restrict__ ps, const float* __restrict__ T,
+                           const float* __restrict__ dT, int C, int h, int w, int wp, int d, float* __restrict__ dqs,
+                           float* __restrict__ dps) {
+    const int lane = threadIdx.x & 31;
+    const int pix = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (pix >= h * w) return;
+    const int y = pix / w, x = pix - y * w;
+    const int win = 2 * d + 1, L = win * win;
+    const size_t plane = (size_t)h * wp;
+    float gq[4] = {0.f, 0.f, 0.f, 0.f};                      // channels lane, lane+32, ... (C <= 128)
+    for (int l = 0; l < L; ++l) {
+        const float dt = dT[(size_t)pix * L + l];
+        if (dt == 0.f) continue;                             // warp-uniform
+        const int yy = y + l / win - d, xx = x + l % win - d;
+        if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;   // outside: T is the constant 1
+        const float t = T[(size_t)pix * L + l];
+        const float dD = 0.5f * (1.0f - t * t) * dt;
+        if (dD == 0.f) continue;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = lane + 32 * k;
+            if (c < C) {
+                const float t2 = 2.f * dD * (qs[c * plane + (size_t)y * wp + x] - ps[c * plane + (size_t)yy * wp + xx]);
+                gq[k] += t2;
+                atomicAdd(dps + c * plane + (size_t)yy * wp + xx, -t2);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = lane + 32 * k;
+        if (c < C) dqs[c * plane + (size_t)y * wp + x] = gq[k];
+    }
+}
+
+// avg_pool2d backward: [C][h][wp] pooled gradient -> [H][W][C]
+__global__ void local_unpool_kernel(const float* __restrict__ dpool, int C, int H, int W, int h, int w, int wp,
+                                    float* __restrict__ grad) {
+    const int64_t total = (int64_t)H * W * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C); const int64_t pix = i / C; const int X = (int)(pix % W), Y = (int)(pix / W);
+        float v = 0.f;
+        if (Y < 2 * h && X < 2 * w) v = dpool[((size_t)c * h + (Y >> 1)) * wp + (X >> 1)] * 0.25f;
+        grad[i] = v;
+    }
+}
+
+size_t local_match_grad_workspace_bytes(int H, int W, int C, int d) {
+    if (H < 2 || W < 2 || C < 1 || d < 0) return 256;
+    const int h = H / 2, w = W / 2;
+    const size_t L = (size_t)(2 * d + 1) * (2 * d + 1);
+    return simt_workspace_bytes(H, W, C, d) + align_up((size_t)h * w * L * sizeof(float), 256) +
+           2 * align_up((size_t)C * h * pooled_pitch(w) * sizeof(float), 256) + 1024;
+}
+
+int launch_local_match_argmin(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_sc,
+                              const float* query, int64_t q_sy, int64_t q_sx, int64_t q_sc,
+                              const int32_t* labels, const int32_t* gt_ids, int H, int W, int C, int N, int d,
+                              float* out, int32_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (N < 1) return fail_invalid("local match: N must be >= 1");
+    float* T = nullptr; int32_t* plab = nullptr;
+    int rc = window_volume(query, q_sy, q_sx, q_sc, prev, p_sy, p_sx, p_sc, H, W, C, d, ws, ws_bytes, stream, &T, labels, &plab);
+    if (rc) return rc;
+    const size_t smem = (size_t)N * UP_STRIDE * 2 * sizeof(float);
+    if (smem > 200 * 1024) return fail_invalid("local match: too many objects (N <= 100)");
+    if (smem > 48 * 1024) cudaFuncSetAttribute(local_min_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    local_min_argmin_kernel<<<(unsigned)ceil_div64((int64_t)H * W, UP_WARPS), UP_STRIDE, smem, stream>>>(T, plab, gt_ids, H, W, H / 2,
+                                                                                                   W / 2, d, N, out, out_idx);
+    return check_launch("local_min_argmin_kernel");
+}
+
+int launch_local_match_backward(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_sc,
+                                const float* query, int64_t q_sy, int64_t q_sx, int64_t q_sc,
+                                int H, int W, int C, int N, int d, const int32_t* idx, const float* grad_out,
+                                float* grad_prev, float* grad_query, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (C > 128) return fail_invalid("local match backward: C <= 128");
+    if (ws_bytes < local_match_grad_workspace_bytes(H, W, C, d)) { set_error("local match backward: workspace too small"); return MANET_E_WORKSPACE; }
+    float* T = nullptr;
+    int rc = window_volume(query, q_sy, q_sx, q_sc, prev, p_sy, p_sx, p_sc, H, W, C, d, ws, ws_bytes, stream, &T);
+    if (rc) return rc;
+    const int h = H / 2, w = W / 2, wp = pooled_pitch(w), win = 2 * d + 1, L = win * win;
+    // window_volume carved qs, ps, T, plab from the front of the workspace in this order; the gradient buffers follow
+    Carver cv(ws, ws_bytes);
+    float* qs = cv.take<float>((size_t)C * h * wp);
+    float* ps = cv.take<float>((size_t)C * h * wp);
+    cv.take<float>((size_t)h * w * L);
+    cv.take<int32_t>((size_t)(H + 4 * d) * (W + 4 * d));
+    float* dT = cv.take<float>((size_t)h * w * L);
+    float* dqs = cv.take<float>((size_t)C * h * wp);
+    float* dps = cv.take<float>((size_t)C * h * wp);
+    cudaMemsetAsync(dT, 0, (size_t)h * w * L * sizeof(float), stream);
+    cudaMemsetAsync(dqs, 0, (size_t)C * h * wp * sizeof(float), stream);
+    cudaMemsetAsync(dps, 0, (size_t)C * h * wp * sizeof(float), stream);
+    const int64_t tot = (int64_t)H * W * N;
+    local_scatter_dt_kernel<<<(unsigned)imin64(ceil_div64(tot, 256), 148 * 16), 256, 0, stream>>>(idx, grad_out, H, W, h, w, L, N, dT);
+    local_backward_dist_kernel<<<(unsigned)ceil_div64((int64_t)h * w, 8), 256, 0, stream>>>(qs, ps, T, dT, C, h, w, wp, d, dqs, dps);
+    const int64_t tot2 = (int64_t)H * W * C;
+    const unsigned g2 = (unsigned)imin64(ceil_div64(tot2, 256), 148 * 16);
+    if (grad_query) local_unpool_kernel<<<g2, 256, 0, stream>>>(dqs, C, H, W, h, w, wp, grad_query);
+    if (grad_prev) local_unpool_kernel<<<g2, 256, 0, stream>>>(dps, C, H, W, h, w, wp, grad_prev);
+    return check_launch("local match backward kernels");
+}
+
 }  // namespace manet

@@ -23,6 +23,96 @@ FORCE_SIMT_LOCAL_ENGINE = False       # same for local matching (exact differenc
 FORCE_SIMT_ENGINE = False             # debugging/tests: route global matching to the fp32 CUDA-core kernel
 
 
+# --------------------------------------------------------------------------- autograd
+def _wants_grad(*tensors):
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+
+
+class _GlobalMatchK1(torch.autograd.Function):
+    """k = 1 global matching with gradients (the reference back-propagates through
+    IntVOS.py:160-210 in train_stage1.py:126): forward on the fp32 CUDA-core kernel that also
+    returns the arg-min reference pixel, backward = gather/scatter through it."""
+
+    @staticmethod
+    def forward(ctx, reference_embeddings, query_embeddings, labels_i32, n_obj):
+        ref, r, c, rps, rcs = pixel_view(reference_embeddings.detach(), "reference_embeddings")
+        qry, m, _, qps, qcs = pixel_view(query_embeddings.detach(), "query_embeddings")
+        dev = qry.device
+        out = torch.empty((m, n_obj, 1), dtype=torch.float32, device=dev)
+        idx = torch.empty((m, n_obj), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().manet_global_match_argmin(
+                ref.data_ptr() if r else None, rps, rcs, r, labels_i32.data_ptr() if r else None,
+                qry.data_ptr(), qps, qcs, m, c, n_obj, out.data_ptr(), idx.data_ptr(), stream_ptr(dev)),
+                "manet_global_match_argmin")
+        ctx.save_for_backward(reference_embeddings, query_embeddings, idx)
+        ctx.n_obj = n_obj
+        ctx.mark_non_differentiable(idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        reference_embeddings, query_embeddings, idx = ctx.saved_tensors
+        ref, r, c, rps, rcs = pixel_view(reference_embeddings.detach(), "reference_embeddings")
+        qry, m, _, qps, qcs = pixel_view(query_embeddings.detach(), "query_embeddings")
+        dev = qry.device
+        g = grad_out.contiguous().float()
+        need_ref, need_q = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        grad_ref = torch.zeros((r, c), dtype=torch.float32, device=dev) if need_ref else None
+        grad_q = torch.empty((m, c), dtype=torch.float32, device=dev) if need_q else None
+        with torch.cuda.device(dev):
+            check(_lib.lib().manet_global_match_backward(
+                ref.data_ptr() if r else None, rps, rcs, r, qry.data_ptr(), qps, qcs, m, c, ctx.n_obj,
+                idx.data_ptr(), g.data_ptr(), grad_q.data_ptr() if need_q else None,
+                grad_ref.data_ptr() if need_ref else None, stream_ptr(dev)), "manet_global_match_backward")
+        return (grad_ref.view(reference_embeddings.shape) if need_ref else None,
+                grad_q.view(query_embeddings.shape) if need_q else None, None, None)
+
+
+class _LocalMatch(torch.autograd.Function):
+    """Local matching with gradients (IntVOS.py:345-434 under autograd): forward on the CUDA-core
+    kernels plus the arg-min window offset, backward through bilinear corners, the transform,
+    the squared differences and the 2x2 average pool."""
+
+    @staticmethod
+    def forward(ctx, prev_frame_embedding, query_embedding, labels_i32, ids_i32, d):
+        prev, qry = prev_frame_embedding.detach(), query_embedding.detach()
+        h, w, c = qry.shape
+        n_obj = ids_i32.numel()
+        dev = qry.device
+        L = _lib.lib()
+        out = torch.empty((1, h, w, n_obj, 1), dtype=torch.float32, device=dev)
+        idx = torch.empty((h, w, n_obj), dtype=torch.int32, device=dev)
+        ws = workspace(dev, L.manet_local_match_grad_workspace_bytes(h, w, c, n_obj, d), "local_grad")
+        with torch.cuda.device(dev):
+            check(L.manet_local_match_argmin(prev.data_ptr(), *prev.stride(), qry.data_ptr(), *qry.stride(),
+                                             labels_i32.data_ptr(), ids_i32.data_ptr(), h, w, c, n_obj, d, out.data_ptr(),
+                                             idx.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)),
+                  "manet_local_match_argmin")
+        ctx.save_for_backward(prev_frame_embedding, query_embedding, idx)
+        ctx.d, ctx.n_obj = d, n_obj
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        prev_frame_embedding, query_embedding, idx = ctx.saved_tensors
+        prev, qry = prev_frame_embedding.detach(), query_embedding.detach()
+        h, w, c = qry.shape
+        dev = qry.device
+        L = _lib.lib()
+        g = grad_out.contiguous().float()
+        need_p, need_q = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gp = torch.empty((h, w, c), dtype=torch.float32, device=dev) if need_p else None
+        gq = torch.empty((h, w, c), dtype=torch.float32, device=dev) if need_q else None
+        ws = workspace(dev, L.manet_local_match_grad_workspace_bytes(h, w, c, ctx.n_obj, ctx.d), "local_grad")
+        with torch.cuda.device(dev):
+            check(L.manet_local_match_backward(prev.data_ptr(), *prev.stride(), qry.data_ptr(), *qry.stride(), h, w, c,
+                                               ctx.n_obj, ctx.d, idx.data_ptr(), g.data_ptr(),
+                                               gp.data_ptr() if need_p else None, gq.data_ptr() if need_q else None,
+                                               ws.data_ptr(), ws.numel(), stream_ptr(dev)), "manet_local_match_backward")
+        return gp, gq, None, None, None
+
+
 # --------------------------------------------------------------------------- global matching
 def _pairwise_distances(x, y, ys=None):
     """``d[i,j] = |x_i|^2 + |y_j|^2 - 2 x_i.y_j`` for x [n,C], y [m,C] (IntVOS.py:23-40).
@@ -159,6 +249,10 @@ def _nearest_neighbor_features_per_object_in_chunks(reference_embeddings_flat, q
         kept = int((labels != -1).sum().item()) if cfg.TEST_MODE else r
         if k > kept:
             raise RuntimeError(f"k ({k}) out of range for {kept} reference pixels (torch.topk would raise, IntVOS.py:87)")
+    if _wants_grad(reference_embeddings_flat, query_embeddings_flat):
+        if k != 1:
+            raise NotImplementedError("gradients through global matching are implemented for k_nearest_neighbors == 1")
+        return _GlobalMatchK1.apply(reference_embeddings_flat, query_embeddings_flat, labels, n_obj)
     flags = _lib.GM_DROP_UNLAB if cfg.TEST_MODE else 0
     return _global_match_raw(ref, r, rps, rcs, labels, qry, m, qps, qcs, c, n_obj, k, flags)
 
@@ -206,6 +300,12 @@ def nearest_neighbor_features_per_object(reference_embeddings, query_embeddings,
         if memory_frame.numel() != m * n_obj or not memory_frame.is_contiguous():
             raise ValueError("memory_frame must be a contiguous [h,w,N,1] slice of the global-map memory")
         mem = memory_frame
+    if _wants_grad(reference_embeddings, query_embeddings):
+        if k != 1 or normalize or mem is not None:
+            raise NotImplementedError("gradients through global matching: k_nearest_neighbors == 1, raw distances "
+                                      "(apply the normalisation in torch, as the reference does at IntVOS.py:611-612)")
+        out = _GlobalMatchK1.apply(reference_embeddings, query_embeddings, labels, n_obj)
+        return out.view(1, h, w, n_obj, 1), ids
     if normalize:
         flags |= _lib.GM_NORMALIZE
     out = _global_match_raw(ref, r, rps, rcs, labels, qry, m, qps, qcs, c, n_obj, k, flags, mem)
@@ -286,6 +386,8 @@ def local_previous_frame_nearest_neighbor_features_per_object(prev_frame_embeddi
     ids = gt_ids.reshape(-1).to(torch.int32).contiguous()
     n_obj = ids.numel()
     d = int(max_distance)
+    if _wants_grad(prev_frame_embedding, query_embedding):
+        return _LocalMatch.apply(prev_frame_embedding, query_embedding, labels, ids, d)
     L = _lib.lib()
     out = torch.empty((1, h, w, n_obj, 1), dtype=torch.float32, device=dev)
     ws = workspace(dev, L.manet_local_match_workspace_bytes(h, w, c, n_obj, d), "local")

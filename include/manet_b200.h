@@ -151,6 +151,39 @@ int manet_local_window_distances_ex(const float* x, int64_t x_sy, int64_t x_sx, 
                                     void* workspace, size_t workspace_bytes, manet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Autograd support.  The reference's matching functions are differentiable
+ * torch graphs (train_stage1.py:126 back-propagates through networks/IntVOS.py:160-210 and
+ * :345-434).  For k = 1 the gradient flows through the arg-min only, so "forward for training" is
+ * a forward that also returns the arg-min, and backward is a gather/scatter.  fp32 CUDA-core kernels.
+ * ------------------------------------------------------------------------------------------ */
+/* Global matching, k = 1, labels compared with 0..N-1 (labels outside, e.g. -1, never match).
+ * out [M,N] raw squared distances (1e20 = absent object), out_idx [M,N] index of the nearest
+ * reference pixel (-1 = absent).  Same values as manet_global_match(..., MANET_GM_ENGINE_SIMT). */
+int manet_global_match_argmin(const float* ref, int64_t ref_pix_stride, int64_t ref_ch_stride, int64_t R,
+                              const int32_t* labels, const float* query, int64_t q_pix_stride,
+                              int64_t q_ch_stride, int64_t M, int C, int N, float* out, int32_t* out_idx,
+                              manet_stream_t stream);
+/* grad_query [M,C] = sum_o 2 g (q - r*), grad_ref [R,C] -= 2 g (q - r*) (grad_ref must be zeroed by
+ * the caller; either output may be NULL). */
+int manet_global_match_backward(const float* ref, int64_t ref_pix_stride, int64_t ref_ch_stride, int64_t R,
+                                const float* query, int64_t q_pix_stride, int64_t q_ch_stride, int64_t M,
+                                int C, int N, const int32_t* idx, const float* grad_out, float* grad_query,
+                                float* grad_ref, manet_stream_t stream);
+/* Local matching: out [H,W,N] as manet_local_match, out_idx [H,W,N] = arg-min window offset
+ * l = (dy+d)(2d+1) + (dx+d), -1 where the result is the pad value 1. */
+size_t manet_local_match_grad_workspace_bytes(int H, int W, int C, int N, int max_distance);
+int manet_local_match_argmin(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_sc, const float* query,
+                             int64_t q_sy, int64_t q_sx, int64_t q_sc, const int32_t* labels,
+                             const int32_t* gt_ids, int H, int W, int C, int N, int max_distance, float* out,
+                             int32_t* out_idx, void* workspace, size_t workspace_bytes, manet_stream_t stream);
+/* grad_prev / grad_query: contiguous [H,W,C] (either may be NULL).  Chain: bilinear corners ->
+ * d tanh(D/2) -> 2 (qs - ps) -> avg_pool2d. */
+int manet_local_match_backward(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_sc, const float* query,
+                               int64_t q_sy, int64_t q_sx, int64_t q_sc, int H, int W, int C, int N,
+                               int max_distance, const int32_t* idx, const float* grad_out, float* grad_prev,
+                               float* grad_query, void* workspace, size_t workspace_bytes, manet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Map memory (networks/IntVOS.py:615-622 / 716-723 and 638-661).
  * ------------------------------------------------------------------------------------------ */
 /* out = min(f(new_map), mem_frame); mem_frame = out.  f = (sigmoid-0.5)*2 when normalize != 0.

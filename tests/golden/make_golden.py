@@ -181,6 +181,41 @@ def memory_session_case():
          final_local_dist=lmem[1]["s"][:T, :3], **log)
 
 
+def gradient_cases():
+    """Gradients of the UNMODIFIED reference (torch autograd through its own graph): the training use of the
+    path (train_stage1.py:126).  loss = sum(w * normalised map) as the model consumes the maps."""
+    # global, k = 1
+    gen = torch.Generator().manual_seed(31)
+    c, hr, wr, h, w, nobj = 32, 11, 13, 10, 12, 2
+    ref = 0.3 * torch.randn(c, hr, wr, generator=gen)
+    qry = 0.3 * torch.randn(c, h, w, generator=gen)
+    lab = blob_labels(gen, hr, wr, nobj + 1)
+    wts = torch.rand(1, h, w, nobj + 1, 1, generator=gen)
+    mod = ref_shim.load_reference(test_mode=False)
+    r, q = ref.clone().requires_grad_(True), qry.clone().requires_grad_(True)
+    with ref_shim.cpu_cuda_identity():
+        out, _ = mod.nearest_neighbor_features_per_object(r.permute(1, 2, 0), q.permute(1, 2, 0), lab.unsqueeze(-1), 1,
+                                                          torch.tensor(nobj), n_chunks=5)
+        (((torch.sigmoid(out) - 0.5) * 2) * wts).sum().backward()
+    save("grad_global_k1", ref_chw=ref, query_chw=qry, labels=lab, weights=wts, n_obj=nobj, out=out,
+         grad_ref_chw=r.grad, grad_query_chw=q.grad)
+    # local
+    gen = torch.Generator().manual_seed(32)
+    c, h, w, nobj, d = 16, 14, 18, 2, 3
+    prev = 0.3 * torch.randn(c, h, w, generator=gen)
+    cur = prev + 0.15 * torch.randn(c, h, w, generator=gen)
+    lab = blob_labels(gen, h, w, nobj + 1, cell=3)
+    ids = torch.arange(0, nobj + 1).int()
+    wts = torch.rand(1, h, w, nobj + 1, 1, generator=gen)
+    p, q = prev.clone().requires_grad_(True), cur.clone().requires_grad_(True)
+    with ref_shim.cpu_cuda_identity():
+        out = mod.local_previous_frame_nearest_neighbor_features_per_object(p.permute(1, 2, 0), q.permute(1, 2, 0),
+                                                                            lab.unsqueeze(-1), ids, max_distance=d)
+        (out * wts).sum().backward()
+    save("grad_local_d3", prev_chw=prev, cur_chw=cur, labels=lab, ids=ids, weights=wts, d=d, out=out,
+         grad_prev_chw=p.grad, grad_query_chw=q.grad)
+
+
 if __name__ == "__main__":
     assert ref_shim.reference_available(), "run this where /root/reference is mounted"
     torch.set_num_threads(4)
@@ -188,3 +223,4 @@ if __name__ == "__main__":
     selected_pixel_case()
     local_cases()
     memory_session_case()
+    gradient_cases()

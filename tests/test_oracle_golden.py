@@ -120,3 +120,27 @@ def test_normalize_is_exact_one_for_sentinel():
     x = torch.tensor([1e20, 0.0, 40.0])
     y = O.normalize_distance(x)
     assert y[0].item() == 1.0 and y[1].item() == 0.0 and y[2].item() == 1.0
+
+
+# ------------------------------------------------------------------ gradients
+def test_oracle_autograd_matches_reference_gradients(golden):
+    """torch autograd through the oracle == autograd through the unmodified reference (golden vectors)."""
+    g = golden("grad_global_k1")
+    r = torch.from_numpy(g["ref_chw"]).requires_grad_(True)
+    q = torch.from_numpy(g["query_chw"]).requires_grad_(True)
+    out, _ = O.global_match(r.permute(1, 2, 0), q.permute(1, 2, 0), torch.from_numpy(g["labels"]).unsqueeze(-1), 1,
+                            torch.tensor(int(g["n_obj"])), 5)
+    (((torch.sigmoid(out) - 0.5) * 2) * torch.from_numpy(g["weights"])).sum().backward()
+    assert np.array_equal(out.detach().numpy(), g["out"])
+    assert np.abs(r.grad.numpy() - g["grad_ref_chw"]).max() <= 1e-6 * max(1.0, np.abs(g["grad_ref_chw"]).max())
+    assert np.abs(q.grad.numpy() - g["grad_query_chw"]).max() <= 1e-6 * max(1.0, np.abs(g["grad_query_chw"]).max())
+
+    g = golden("grad_local_d3")
+    p = torch.from_numpy(g["prev_chw"]).requires_grad_(True)
+    q = torch.from_numpy(g["cur_chw"]).requires_grad_(True)
+    out = O.local_match(p.permute(1, 2, 0), q.permute(1, 2, 0), torch.from_numpy(g["labels"]).unsqueeze(-1),
+                        torch.from_numpy(g["ids"]), int(g["d"]))
+    (out * torch.from_numpy(g["weights"])).sum().backward()
+    assert np.array_equal(out.detach().numpy(), g["out"])
+    assert np.abs(p.grad.numpy() - g["grad_prev_chw"]).max() <= 1e-6 * max(1.0, np.abs(g["grad_prev_chw"]).max())
+    assert np.abs(q.grad.numpy() - g["grad_query_chw"]).max() <= 1e-6 * max(1.0, np.abs(g["grad_query_chw"]).max())
