@@ -18,6 +18,7 @@ GM_NORMALIZE = 1
 GM_DROP_UNLAB = 2
 GM_ENGINE_SIMT = 4
 LM_ENGINE_SIMT = 1
+LM_ENGINE_TENSOR = 2
 STEP_SERIAL = 16
 DT_F32, DT_F16, DT_F64 = 0, 1, 2
 

@@ -25,7 +25,8 @@ struct PoolSrc { const float* p; int64_t sy, sx, sc; float* out; };
 struct LabelPad { const int32_t* labels; int32_t* out; int H, W, pad; };
 
 __global__ void __launch_bounds__(256)
-avg_pool2_kernel(PoolSrc a, PoolSrc b, LabelPad lp, int C, int h, int w, int wp) {
+avg_pool2_kernel(PoolSrc a, PoolSrc b, LabelPad lp, int C, int h, int w, int wp, const float* __restrict__ guard) {
+    if (guard != nullptr && !(guard[1] > kLocalGuardG)) return;   // the tensor-core engine serves this call
     if (blockIdx.y == 2) {
         if (lp.out == nullptr) return;
         const int PW = lp.W + 2 * lp.pad, PH = lp.H + 2 * lp.pad;
@@ -79,7 +80,8 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 __global__ void __launch_bounds__(WTHREADS, 1)
 window_dist_kernel(const float* __restrict__ qs, const float* __restrict__ ps,
-                   int C, int h, int w, int wp, int d, float* __restrict__ T) {
+                   int C, int h, int w, int wp, int d, float* __restrict__ T, const float* __restrict__ guard) {
+    if (guard != nullptr && !(guard[1] > kLocalGuardG)) return;
     extern __shared__ __align__(16) float wsm[];
     const int win = 2 * d + 1, L = win * win;
     const int prows = WTY + 2 * d;
@@ -186,7 +188,9 @@ window_dist_kernel(const float* __restrict__ qs, const float* __restrict__ ps,
 
 // Generic path for any d: one thread per (y, x, l).
 __global__ void window_dist_generic_kernel(const float* __restrict__ qs, const float* __restrict__ ps,
-                                           int C, int h, int w, int wp, int d, float* __restrict__ T) {
+                                           int C, int h, int w, int wp, int d, float* __restrict__ T,
+                                           const float* __restrict__ guard) {
+    if (guard != nullptr && !(guard[1] > kLocalGuardG)) return;
     const int win = 2 * d + 1;
     const int64_t L = (int64_t)win * win;
     const int64_t total = (int64_t)h * w * L;
@@ -246,18 +250,19 @@ template <int WIN_T>
 __global__ void __launch_bounds__(UP_STRIDE)
 upsample_mask_min_kernel(const float* __restrict__ T, const int32_t* __restrict__ plabels,
                          const int32_t* __restrict__ gt_ids, int H, int W, int h, int w, int d, int N,
-                         float* __restrict__ out) {
+                         float* __restrict__ out, const float* __restrict__ guard) {
+    if (guard != nullptr && !(guard[1] > kLocalGuardG)) return;
     extern __shared__ float sbest[];                         // [N][UP_STRIDE]
     const int win = WIN_T > 0 ? WIN_T : 2 * d + 1;
     const int L = win * win;
     const int lane = threadIdx.x & 31, tid = threadIdx.x;
-    const int pix = blockIdx.x * UP_WARPS + (tid >> 5);
     bool arange = true;
     for (int o = lane; o < N; o += 32) arange = arange && (gt_ids[o] == o);
     arange = __all_sync(0xffffffffu, arange);
     float* mine = sbest + tid;
+    // grid-stride over pixels (a warp each): a capped grid keeps the guarded launch cheap when it exits at once
+    for (int pix = blockIdx.x * UP_WARPS + (tid >> 5); pix < H * W; pix += gridDim.x * UP_WARPS) {
     for (int o = 0; o < N; ++o) mine[o * UP_STRIDE] = 1.0f;   // pad value of torch.where(mask, d, ones)
-    if (pix >= H * W) return;
     const uint32_t mine_s = (uint32_t)__cvta_generic_to_shared(mine);
     const int Y = pix / W, X = pix - Y * W;
     const Lerp ly = make_lerp(Y, h, H), lx = make_lerp(X, w, W);
@@ -305,11 +310,15 @@ upsample_mask_min_kernel(const float* __restrict__ T, const int32_t* __restrict_
         for (int s = 16; s > 0; s >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, s));
         if (lane == 0) out[(size_t)pix * N + o] = v;
     }
+    }
 }
 
 // local_pairwise_distances2 as a standalone op: the upsampled volume [H, W, L]
+// T_alt / guard: when both engines ran behind the device-side guard, read the volume of the one that served the call
 __global__ void upsample_volume_kernel(const float* __restrict__ T, int H, int W, int h, int w, int L,
-                                       float* __restrict__ out) {
+                                       float* __restrict__ out, const float* __restrict__ T_alt,
+                                       const float* __restrict__ guard) {
+    if (guard != nullptr && guard[1] > kLocalGuardG) T = T_alt;
     const int64_t total = (int64_t)H * W * L;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -337,14 +346,15 @@ size_t lm_umma_workspace_bytes(int H, int W, int C, int d);
 size_t local_match_workspace_bytes(int H, int W, int C, int N, int d) {
     (void)N;
     if (H < 2 || W < 2 || C < 1 || d < 0) return 256;
-    size_t a = simt_workspace_bytes(H, W, C, d), b = lm_umma_workspace_bytes(H, W, C, d);
-    return a > b ? a : b;
+    // the guarded default runs the tensor-core pipeline and, behind the device-side guard, the CUDA-core one
+    return align_up(lm_umma_workspace_bytes(H, W, C, d), 1024) + simt_workspace_bytes(H, W, C, d);
 }
 
 static int window_volume(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_sc,
                          const float* y, int64_t y_sy, int64_t y_sx, int64_t y_sc,
                          int H, int W, int C, int d, void* ws, size_t ws_bytes, cudaStream_t stream,
-                         float** T_out, const int32_t* labels = nullptr, int32_t** plabels_out = nullptr) {
+                         float** T_out, const int32_t* labels = nullptr, int32_t** plabels_out = nullptr,
+                         const float* guard = nullptr) {
     if (H < 2 || W < 2 || C < 1 || d < 0) return fail_invalid("local match: need H,W >= 2, C >= 1, max_distance >= 0");
     if (ws_bytes < simt_workspace_bytes(H, W, C, d)) { set_error("local match: workspace too small"); return MANET_E_WORKSPACE; }
     const int h = H / 2, w = W / 2, wp = pooled_pitch(w);
@@ -355,10 +365,10 @@ static int window_volume(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_s
     float* T = cv.take<float>((size_t)h * w * win * win);
     int32_t* plab = cv.take<int32_t>((size_t)(H + 4 * d) * (W + 4 * d));
     int64_t tot = (int64_t)C * h * wp;
-    dim3 pg((unsigned)imin64(ceil_div64(tot, 256), 148 * 8), labels ? 3 : 2);
+    dim3 pg((unsigned)imin64(ceil_div64(tot, 256), 148 * 4), labels ? 3 : 2);
     PoolSrc a{x, x_sy, x_sx, x_sc, qs}, b{y, y_sy, y_sx, y_sc, ps};
     LabelPad lpad{labels, labels ? plab : nullptr, H, W, 2 * d};
-    avg_pool2_kernel<<<pg, 256, 0, stream>>>(a, b, lpad, C, h, w, wp);
+    avg_pool2_kernel<<<pg, 256, 0, stream>>>(a, b, lpad, C, h, w, wp, guard);
     if (plabels_out) *plabels_out = plab;
     if (d <= 12) {
         const int ngroups = (win + WDY - 1) / WDY;
@@ -369,13 +379,13 @@ static int window_volume(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_s
             cudaFuncSetAttribute(window_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
             attr_set = true;
         }
-        profile_begin(PROF_LOCAL_WINDOW, stream);
-        window_dist_kernel<<<grid, WTHREADS, smem, stream>>>(qs, ps, C, h, w, wp, d, T);
-        profile_end(PROF_LOCAL_WINDOW, stream);
+        if (!guard) profile_begin(PROF_LOCAL_WINDOW, stream);
+        window_dist_kernel<<<grid, WTHREADS, smem, stream>>>(qs, ps, C, h, w, wp, d, T, guard);
+        if (!guard) profile_end(PROF_LOCAL_WINDOW, stream);
     } else {
         int64_t total = (int64_t)h * w * win * win;
         unsigned g = (unsigned)imin64(ceil_div64(total, 256), 148 * 32);
-        window_dist_generic_kernel<<<g, 256, 0, stream>>>(qs, ps, C, h, w, wp, d, T);
+        window_dist_generic_kernel<<<g, 256, 0, stream>>>(qs, ps, C, h, w, wp, d, T, guard);
     }
     *T_out = T;
     return check_launch("local window kernels");
@@ -385,12 +395,34 @@ static int window_volume(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_s
 bool lm_umma_supported(int H, int W, int C, int N, int d);
 size_t lm_umma_workspace_bytes(int H, int W, int C, int d);
 int launch_local_match_umma(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, const int32_t*,
-                            const int32_t*, int, int, int, int, int, float*, float**, void*, size_t, cudaStream_t);
+                            const int32_t*, int, int, int, int, int, float*, float**, void*, size_t, cudaStream_t, bool,
+                            const float**);
 
 static bool lm_force_simt() {
     static int cached = -1;
     if (cached < 0) { const char* e = getenv("MANET_LM_ENGINE"); cached = (e && (e[0] == 's' || e[0] == 'S')) ? 1 : 0; }
     return cached == 1;
+}
+
+// 0: CUDA-core kernels only; 1: tensor-core kernels only (caller vouches for the numerics); 2: tensor-core kernels
+// guarded on the device by G = max |x - mu|^2 (common.cuh), CUDA-core kernels take over when the guard trips
+static int lm_engine_mode(uint32_t flags, int H, int W, int C, int N, int d) {
+    if ((flags & MANET_LM_ENGINE_SIMT) || lm_force_simt() || !lm_umma_supported(H, W, C, N, d)) return 0;
+    return (flags & MANET_LM_ENGINE_TENSOR) ? 1 : 2;
+}
+
+static int simt_masked_min(const float* T, const int32_t* plab, const int32_t* gt_ids, int H, int W, int N, int d, float* out,
+                           const float* guard, cudaStream_t stream) {
+    int64_t pix = (int64_t)H * W;
+    const size_t up_smem = (size_t)N * 32 * UP_WARPS * sizeof(float);
+    if (up_smem > 200 * 1024) return fail_invalid("local match: too many objects (N <= 200)");
+    if ((int64_t)H * W * (int64_t)((2 * d + 1) * (2 * d + 1)) >= (1ll << 31)) return fail_invalid("local match: frame x window too large");
+    auto kern = (d == 12) ? upsample_mask_min_kernel<25> : (d == 9) ? upsample_mask_min_kernel<19> : upsample_mask_min_kernel<0>;
+    if (up_smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)up_smem);
+    if (!guard) profile_begin(PROF_LOCAL_MIN, stream);
+    kern<<<(unsigned)imin64(ceil_div64(pix, UP_WARPS), 148 * 8), UP_STRIDE, up_smem, stream>>>(T, plab, gt_ids, H, W, H / 2, W / 2, d, N, out, guard);
+    if (!guard) profile_end(PROF_LOCAL_MIN, stream);
+    return check_launch("upsample_mask_min_kernel");
 }
 
 int launch_local_match(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_sc,
@@ -399,42 +431,56 @@ int launch_local_match(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_
                        uint32_t flags, float* out, void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (N < 1) return fail_invalid("local match: N must be >= 1");
     if (H < 2 || W < 2 || C < 1 || d < 0) return fail_invalid("local match: need H,W >= 2, C >= 1, max_distance >= 0");
-    if (!(flags & MANET_LM_ENGINE_SIMT) && !lm_force_simt() && lm_umma_supported(H, W, C, N, d))
-        return launch_local_match_umma(prev, p_sy, p_sx, p_sc, query, q_sy, q_sx, q_sc, labels, gt_ids, H, W, C, N, d, out,
-                                       nullptr, ws, ws_bytes, stream);
+    const int mode = lm_engine_mode(flags, H, W, C, N, d);
+    const float* guard = nullptr;
+    char* simt_ws = reinterpret_cast<char*>(ws);
+    size_t simt_bytes = ws_bytes;
+    if (mode != 0) {
+        int rc = launch_local_match_umma(prev, p_sy, p_sx, p_sc, query, q_sy, q_sx, q_sc, labels, gt_ids, H, W, C, N, d, out,
+                                         nullptr, ws, ws_bytes, stream, mode == 2, &guard);
+        if (rc || mode == 1) return rc;
+        const size_t used = align_up(lm_umma_workspace_bytes(H, W, C, d), 1024);
+        if (ws_bytes < used + simt_workspace_bytes(H, W, C, d)) { set_error("local match: workspace too small"); return MANET_E_WORKSPACE; }
+        simt_ws += used; simt_bytes -= used;
+    }
     float* T = nullptr;
     int32_t* plab = nullptr;
-    int rc = window_volume(query, q_sy, q_sx, q_sc, prev, p_sy, p_sx, p_sc, H, W, C, d, ws, ws_bytes, stream, &T, labels, &plab);
+    int rc = window_volume(query, q_sy, q_sx, q_sc, prev, p_sy, p_sx, p_sc, H, W, C, d, simt_ws, simt_bytes, stream, &T, labels, &plab,
+                           guard);
     if (rc) return rc;
-    int64_t pix = (int64_t)H * W;
-    const size_t up_smem = (size_t)N * 32 * UP_WARPS * sizeof(float);
-    if (up_smem > 200 * 1024) return fail_invalid("local match: too many objects (N <= 200)");
-    if ((int64_t)H * W * (int64_t)((2 * d + 1) * (2 * d + 1)) >= (1ll << 31)) return fail_invalid("local match: frame x window too large");
-    auto kern = (d == 12) ? upsample_mask_min_kernel<25> : (d == 9) ? upsample_mask_min_kernel<19> : upsample_mask_min_kernel<0>;
-    if (up_smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)up_smem);
-    profile_begin(PROF_LOCAL_MIN, stream);
-    kern<<<(unsigned)ceil_div64(pix, UP_WARPS), UP_STRIDE, up_smem, stream>>>(T, plab, gt_ids, H, W, H / 2, W / 2, d, N, out);
-    profile_end(PROF_LOCAL_MIN, stream);
-    return check_launch("upsample_mask_min_kernel");
+    return simt_masked_min(T, plab, gt_ids, H, W, N, d, out, guard, stream);
 }
 
 int launch_local_window_distances(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_sc,
                                   const float* y, int64_t y_sy, int64_t y_sx, int64_t y_sc,
                                   int H, int W, int C, int d, uint32_t flags, float* out, void* ws, size_t ws_bytes,
                                   cudaStream_t stream) {
-    float* T = nullptr;
     if (H < 2 || W < 2 || C < 1 || d < 0) return fail_invalid("local match: need H,W >= 2, C >= 1, max_distance >= 0");
-    int rc;
-    if (!(flags & MANET_LM_ENGINE_SIMT) && !lm_force_simt() && lm_umma_supported(H, W, C, 1, d))
-        rc = launch_local_match_umma(y, y_sy, y_sx, y_sc, x, x_sy, x_sx, x_sc, nullptr, nullptr, H, W, C, 1, d, nullptr, &T, ws,
-                                     ws_bytes, stream);
-    else
-        rc = window_volume(x, x_sy, x_sx, x_sc, y, y_sy, y_sx, y_sc, H, W, C, d, ws, ws_bytes, stream, &T);
-    if (rc) return rc;
+    const int mode = lm_engine_mode(flags, H, W, C, 1, d);
+    const float* guard = nullptr;
+    float* T_tensor = nullptr; float* T_simt = nullptr;
+    char* simt_ws = reinterpret_cast<char*>(ws);
+    size_t simt_bytes = ws_bytes;
+    if (mode != 0) {
+        int rc = launch_local_match_umma(y, y_sy, y_sx, y_sc, x, x_sy, x_sx, x_sc, nullptr, nullptr, H, W, C, 1, d, nullptr,
+                                         &T_tensor, ws, ws_bytes, stream, mode == 2, &guard);
+        if (rc) return rc;
+        const size_t used = align_up(lm_umma_workspace_bytes(H, W, C, d), 1024);
+        if (mode == 2) {
+            if (ws_bytes < used + simt_workspace_bytes(H, W, C, d)) { set_error("local match: workspace too small"); return MANET_E_WORKSPACE; }
+            simt_ws += used; simt_bytes -= used;
+        }
+    }
+    if (mode != 1) {
+        int rc = window_volume(x, x_sy, x_sx, x_sc, y, y_sy, y_sx, y_sc, H, W, C, d, simt_ws, simt_bytes, stream, &T_simt, nullptr,
+                               nullptr, guard);
+        if (rc) return rc;
+    }
     const int L = (2 * d + 1) * (2 * d + 1);
     int64_t total = (int64_t)H * W * L;
     unsigned g = (unsigned)imin64(ceil_div64(total, 256), 148 * 32);
-    upsample_volume_kernel<<<g, 256, 0, stream>>>(T, H, W, H / 2, W / 2, L, out);
+    upsample_volume_kernel<<<g, 256, 0, stream>>>(mode != 0 ? T_tensor : T_simt, H, W, H / 2, W / 2, L, out, T_simt,
+                                                  mode == 2 ? guard : nullptr);
     return check_launch("upsample_volume_kernel");
 }
 

@@ -193,7 +193,7 @@ bool lm_umma_supported(int H, int W, int C, int N, int d) { LmGeom g; return lm_
 // the output (the pad value of torch.where(mask, d, ones), IntVOS.py:428-431, and the identity of the atomicMin merge).
 struct LmPoolSrc { const float* p; int64_t sy, sx, sc; float* out; };
 struct LmMuBlocks { int blk[LM_MU_SAMPLES]; int count; };   // pool blocks of the query frame whose channel sums make up mu; their pixel count
-struct LmAux { const int32_t* labels; const int32_t* gt_ids; uint8_t* plab8; int H, W, pad, PW8, N; float* out; int64_t n_out; };
+struct LmAux { const int32_t* labels; const int32_t* gt_ids; uint8_t* plab8; int H, W, pad, PW8, N; float* out; int64_t n_out; float* stats; };
 
 __global__ void __launch_bounds__(256)
 lm_pool_kernel(LmPoolSrc a, LmPoolSrc b, LmAux aux, int C, int Cp, int h, int w, float* __restrict__ blkmax,
@@ -205,6 +205,7 @@ lm_pool_kernel(LmPoolSrc a, LmPoolSrc b, LmAux aux, int C, int Cp, int h, int w,
     if (blockIdx.z == 2) {
         const int64_t nthreads = (int64_t)gridDim.x * gridDim.y * blockDim.x;
         const int64_t first = ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + t;
+        if (first == 0) aux.stats[1] = 0.f;              // guard statistic G, accumulated by lm_convert_kernel (atomicMax)
         if (aux.plab8 != nullptr) {
             if (t < aux.N) sid[t] = (float)__ldg(aux.gt_ids + t);
             __syncthreads();
@@ -423,6 +424,13 @@ lm_convert_kernel(const LmConvParams P) {
     sq += __shfl_xor_sync(0xffffffffu, sq, 1);
     sq += __shfl_xor_sync(0xffffffffu, sq, 2);
     sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+    {
+        // guard statistic: G = max |x - mu|^2 (unscaled) over the pixels of both frames
+        float gmax = inside ? sq / (s * s) : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+        if (lane == 0 && gmax > 0.f) atomicMax(reinterpret_cast<int*>(P.stats + 1), __float_as_int(gmax));
+    }
     if (chk == 0) {
         // norms in units of the transform's exponent: D * log2(e) = (xs' + ys' - 2 acc) * log2(e) / s^2
         const float karg = 1.4426950408889634f / (s * s);
@@ -435,7 +443,8 @@ lm_convert_kernel(const LmConvParams P) {
 struct LmParams {
     const uint8_t* Aimg; const float* Xs;                // query operand images / norms per tile
     const uint8_t* Bimg; const float* Ys;                // previous-frame padded operand image / norms
-    const float* stats;                                  // [0] = operand scale (lm_convert_kernel)
+    const float* stats;                                  // [0] = operand scale, [1] = guard statistic G (lm_convert_kernel)
+    int guarded;                                         // != 0: leave the call to the CUDA-core kernels when G > kLocalGuardG
     const uint8_t* plab8;                                // zero-padded label slots [(H+4d)][PW8] bytes (null: volume only)
     const int32_t* gt_ids;
     float* out;                                          // [H][W][N], pre-filled with 1.0 (null: volume only)
@@ -556,6 +565,7 @@ lm_umma_kernel(const LmParams P) {
     const int tile = blockIdx.x >> 1, half = blockIdx.x & 1;
     const int dyA = half ? d + 1 : 0, dyB = half ? 2 * d : d;        // window rows (dy + d) of this item
     if (dyA > dyB) return;                                           // d == 0: nothing for the second half
+    if (P.guarded && __ldg(P.stats + 1) > kLocalGuardG) return;      // uniform over the grid: the exact kernels serve this call
     const int ty = tile / G.ntx, tx = tile % G.ntx;
     const int qy0 = ty * LM_CH, qx0 = tx * LM_CW;
     const int r_first = qy0 + dyA - d;                               // first previous-frame row needed
@@ -1009,7 +1019,8 @@ size_t lm_umma_workspace_bytes(int H, int W, int C, int d) {
 int launch_local_match_umma(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_sc,
                             const float* query, int64_t q_sy, int64_t q_sx, int64_t q_sc,
                             const int32_t* labels, const int32_t* gt_ids, int H, int W, int C, int N, int d,
-                            float* out, float** T_out, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                            float* out, float** T_out, void* ws, size_t ws_bytes, cudaStream_t stream, bool guarded,
+                            const float** guard_out) {
     LmParams P;
     memset(&P, 0, sizeof(P));
     if (!lm_geometry(H, W, C, labels ? N : 1, d, &P.g)) return fail_invalid("local match (tcgen05): unsupported shape");
@@ -1031,7 +1042,7 @@ int launch_local_match_umma(const float* prev, int64_t p_sy, int64_t p_sx, int64
     uint8_t* Bimg = cv.take<uint8_t>(lm_img_bytes_b(g), 1024);
     float* Ys = cv.take<float>((size_t)g.HI * g.WI);
     LmPoolSrc a{query, q_sy, q_sx, q_sc, Pq}, b{prev, p_sy, p_sx, p_sc, Pp};
-    LmAux aux{labels, gt_ids, labels ? plab8 : nullptr, H, W, 2 * d, g.PW8, N, labels ? out : nullptr, (int64_t)H * W * N};
+    LmAux aux{labels, gt_ids, labels ? plab8 : nullptr, H, W, 2 * d, g.PW8, N, labels ? out : nullptr, (int64_t)H * W * N, stats};
     const size_t pool_smem = (size_t)LM_POOL_PX * (g.Cp + 1) * sizeof(float);
     LmMuBlocks mub;
     mub.count = 0;
@@ -1048,7 +1059,8 @@ int launch_local_match_umma(const float* prev, int64_t p_sy, int64_t p_sx, int64
     CP.Aimg = Aimg; CP.Xs = Xs; CP.Bimg = Bimg; CP.Ys = Ys; CP.stats = stats; CP.mub = mub; CP.g = g;
     lm_convert_kernel<<<g.HI * (g.WI >> 5) + 4 * n_tiles, 256, 0, stream>>>(CP);
     profile_end(PROF_LOCAL_MIN, stream);
-    P.Aimg = Aimg; P.Xs = Xs; P.Bimg = Bimg; P.Ys = Ys; P.stats = stats;
+    P.Aimg = Aimg; P.Xs = Xs; P.Bimg = Bimg; P.Ys = Ys; P.stats = stats; P.guarded = guarded ? 1 : 0;
+    if (guard_out) *guard_out = stats;
     P.plab8 = labels ? plab8 : nullptr; P.gt_ids = gt_ids; P.out = labels ? out : nullptr;
     P.T_vol = T_out ? Tvol : nullptr;
     P.H = H; P.W = W; P.C = C; P.N = labels ? N : 1; P.d = d;

@@ -20,6 +20,7 @@ USE_CORRELATION_COST = False          # IntVOS.py:15 (kept for API compatibility
 MODEL_UNFOLD = True                   # IntVOS.py:16
 WRONG_LABEL_PADDING_DISTANCE = 1e20   # IntVOS.py:17
 FORCE_SIMT_LOCAL_ENGINE = False       # same for local matching (exact difference form on CUDA cores)
+FORCE_TENSOR_LOCAL_ENGINE = False     # tests/benchmarks: tcgen05 local engine without the device-side numerics guard
 FORCE_SIMT_ENGINE = False             # debugging/tests: route global matching to the fp32 CUDA-core kernel
 
 
@@ -321,7 +322,9 @@ def _hwc_strides(t, name):
 
 
 def _local_flags():
-    return _lib.LM_ENGINE_SIMT if FORCE_SIMT_LOCAL_ENGINE else 0
+    if FORCE_SIMT_LOCAL_ENGINE:
+        return _lib.LM_ENGINE_SIMT
+    return _lib.LM_ENGINE_TENSOR if FORCE_TENSOR_LOCAL_ENGINE else 0
 
 
 def local_pairwise_distances2(x, y, max_distance=9):

@@ -43,6 +43,7 @@ typedef void* manet_stream_t; /* a cudaStream_t */
 #define MANET_GM_ENGINE_SIMT 4u /* force the fp32 CUDA-core kernel instead of the tcgen05 kernel */
 /* local-match flag (the *_ex entry points) */
 #define MANET_LM_ENGINE_SIMT 1u /* force the fp32 CUDA-core kernels (exact difference form) instead of the tcgen05 kernel */
+#define MANET_LM_ENGINE_TENSOR 2u /* force the tcgen05 kernels without the device-side numerics guard (see manet_local_match_ex) */
 /* session-step flag: run the local-matching branch on the same stream as the global branch (the
  * default forks it onto a second stream so its kernels overlap the pre/post passes of the GEMM) */
 #define MANET_STEP_SERIAL    16u
@@ -129,9 +130,13 @@ int manet_local_match(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_s
                       int H, int W, int C, int N, int max_distance, float* out,
                       void* workspace, size_t workspace_bytes, manet_stream_t stream);
 
-/* Same with flags (MANET_LM_ENGINE_SIMT).  manet_local_match == flags 0: the tcgen05 engine whenever the
- * shape allows it (max_distance <= 12, C <= 128, H,W >= 6, N limited by shared memory: <= 11 at
- * max_distance 12), the CUDA-core engine otherwise. */
+/* Same with flags.  manet_local_match == flags 0 = the guarded default: when the shape allows it
+ * (max_distance <= 12, C <= 128, H,W >= 6, N <= 64 and within shared memory) the tcgen05 engine computes
+ * the map, and a statistic it takes on the device, G = max |x - mu|^2 over both pooled frames, decides
+ * whether its GEMM-form numerics hold the 1e-5 parity bound (G <= 10; measured error 6.6e-7 * G).  If not,
+ * the CUDA-core kernels (the reference's exact difference form) enqueued behind it produce the result;
+ * whichever pipeline is not needed exits at once.  No host synchronisation either way.
+ * MANET_LM_ENGINE_SIMT: CUDA-core kernels only.  MANET_LM_ENGINE_TENSOR: tcgen05 kernels only, no guard. */
 int manet_local_match_ex(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_sc,
                          const float* query, int64_t q_sy, int64_t q_sx, int64_t q_sc,
                          const int32_t* labels, const int32_t* gt_ids,
