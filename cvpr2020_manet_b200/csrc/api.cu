@@ -358,6 +358,7 @@ struct manet_session {
     float* d_lmem;        // [n_frames, 9, H*W*N] local-map memory, zeros (IntVOS.py:645)
     float* d_ldist;       // [n_frames, 9]
     void *ws_g, *ws_l; size_t ws_g_bytes, ws_l_bytes;
+    long long stream_count;   // MANET_STEP_STREAM: steps since the sequence started (ring of three frame buffers)
 };
 
 static __global__ void fill_kernel(float* p, float v, int64_t n) {
@@ -464,26 +465,30 @@ int manet_session_upload(manet_session_t* s) {
 }
 
 // embeddings are [C,H,W] storage, consumed as [H,W,C] views exactly as IntVOS.py:605-606,625 do
+struct StepInputs { const float *ref, *prev, *cur; const int32_t *ref_lab, *prev_lab; };
+
 static int session_step_slot(manet_session_t* s, int slot, int frame, int interaction_num, int start_annotated_frame,
-                             uint32_t flags) {
+                             uint32_t flags, const StepInputs* in = nullptr) {
     MANET_REQUIRE(frame >= 0 && frame < s->n_frames, "session: frame out of range");
     MANET_REQUIRE(frame != start_annotated_frame, "session: propagation never visits the annotated frame (1/|f-f0|, IntVOS.py:648)");
     SessionSlot& t = s->slot[slot];
+    const StepInputs own{t.d_ref, t.d_prev, t.d_cur, t.d_ref_lab, t.d_prev_lab};
+    if (!in) in = &own;
     const int64_t px = (int64_t)s->H * s->W, n = px * s->N;
     // The two branches share no data until the caller reads both maps: fork the local branch onto its
     // own stream so its small kernels can fill the machine around the (tensor-bound) global-matching GEMM.
     const bool fork = !(flags & MANET_STEP_SERIAL);
     cudaStream_t ls = fork ? s->local_stream : s->stream;
-    const uint32_t gm_flags = (flags & ~MANET_STEP_SERIAL) | MANET_GM_NORMALIZE;
+    const uint32_t gm_flags = (flags & ~(MANET_STEP_SERIAL | MANET_STEP_STREAM | MANET_STEP_STREAM_RESET)) | MANET_GM_NORMALIZE;
     if (fork) {
         cudaEventRecord(s->ev_fork, s->stream);
         cudaStreamWaitEvent(s->local_stream, s->ev_fork, 0);
     } else {
-        int rc0 = manet_global_match(t.d_ref, 1, px, px, t.d_ref_lab, t.d_cur, 1, px, px, s->C, s->N, 1, gm_flags,
+        int rc0 = manet_global_match(in->ref, 1, px, px, in->ref_lab, in->cur, 1, px, px, s->C, s->N, 1, gm_flags,
                                      s->d_gmem + (size_t)frame * n, t.d_out_g, s->ws_g, s->ws_g_bytes, s->stream);
         if (rc0) return rc0;
     }
-    int rc = manet_local_match(t.d_prev, s->W, 1, px, t.d_cur, s->W, 1, px, t.d_prev_lab, s->d_ids, s->H, s->W, s->C, s->N,
+    int rc = manet_local_match(in->prev, s->W, 1, px, in->cur, s->W, 1, px, in->prev_lab, s->d_ids, s->H, s->W, s->C, s->N,
                                s->d, t.d_raw_l, s->ws_l, s->ws_l_bytes, ls);
     if (rc) return rc;
     int df = frame - start_annotated_frame; if (df < 0) df = -df;
@@ -493,7 +498,7 @@ static int session_step_slot(manet_session_t* s, int slot, int frame, int intera
     if (rc) return rc;
     if (fork) {
         cudaEventRecord(s->ev_join, s->local_stream);
-        rc = manet_global_match(t.d_ref, 1, px, px, t.d_ref_lab, t.d_cur, 1, px, px, s->C, s->N, 1, gm_flags,
+        rc = manet_global_match(in->ref, 1, px, px, in->ref_lab, in->cur, 1, px, px, s->C, s->N, 1, gm_flags,
                                 s->d_gmem + (size_t)frame * n, t.d_out_g, s->ws_g, s->ws_g_bytes, s->stream);
         if (rc) return rc;
         cudaStreamWaitEvent(s->stream, s->ev_join, 0);
@@ -511,12 +516,37 @@ int manet_session_submit_host(manet_session_t* s, int slot, int frame, int inter
                               uint32_t flags) {
     MANET_REQUIRE(s && (slot == 0 || slot == 1), "session: null / bad slot");
     SessionSlot& t = s->slot[slot];
-    int rc = session_upload_slot(s, slot, s->copy_stream);
-    if (rc) return rc;
-    cudaEventRecord(t.ev_up, s->copy_stream);
-    cudaStreamWaitEvent(s->stream, t.ev_up, 0);
-    rc = session_step_slot(s, slot, frame, interaction_num, start_annotated_frame, flags);
-    if (rc) return rc;
+    int rc;
+    if (flags & MANET_STEP_STREAM) {
+        // Streaming propagation (test.py:237-259 driven from host memory): the annotated frame and its scribble labels
+        // are uploaded when the sequence starts, and the previous frame of step i is the current frame of step i-1, which
+        // is already on the device.  A ring of three frame buffers lets the upload of step i+2 overlap the kernels of
+        // step i+1 (which still reads frame i as its previous frame): step i's current frame lives in ring[i % 3].
+        if (flags & MANET_STEP_STREAM_RESET) s->stream_count = 0;
+        float* ring[3] = {s->slot[0].d_cur, s->slot[1].d_cur, s->slot[0].d_prev};
+        const long long i = s->stream_count;
+        const size_t px = (size_t)s->H * s->W, emb = px * s->C * sizeof(float);
+        if (i == 0) {
+            cudaMemcpyAsync(s->slot[0].d_ref, t.h_ref, emb, cudaMemcpyHostToDevice, s->copy_stream);
+            cudaMemcpyAsync(s->slot[0].d_ref_lab, t.h_ref_lab, px * 4, cudaMemcpyHostToDevice, s->copy_stream);
+            cudaMemcpyAsync(ring[2], t.h_prev, emb, cudaMemcpyHostToDevice, s->copy_stream);
+        }
+        cudaMemcpyAsync(ring[i % 3], t.h_cur, emb, cudaMemcpyHostToDevice, s->copy_stream);
+        cudaMemcpyAsync(t.d_prev_lab, t.h_prev_lab, px * 4, cudaMemcpyHostToDevice, s->copy_stream);
+        cudaEventRecord(t.ev_up, s->copy_stream);
+        cudaStreamWaitEvent(s->stream, t.ev_up, 0);
+        const StepInputs in{s->slot[0].d_ref, ring[(i + 2) % 3], ring[i % 3], s->slot[0].d_ref_lab, t.d_prev_lab};
+        rc = session_step_slot(s, slot, frame, interaction_num, start_annotated_frame, flags, &in);
+        if (rc) return rc;
+        s->stream_count = i + 1;
+    } else {
+        rc = session_upload_slot(s, slot, s->copy_stream);
+        if (rc) return rc;
+        cudaEventRecord(t.ev_up, s->copy_stream);
+        cudaStreamWaitEvent(s->stream, t.ev_up, 0);
+        rc = session_step_slot(s, slot, frame, interaction_num, start_annotated_frame, flags);
+        if (rc) return rc;
+    }
     const size_t map = (size_t)s->H * s->W * s->N * sizeof(float);
     cudaMemcpyAsync(t.h_out_g, t.d_out_g, map, cudaMemcpyDeviceToHost, s->stream);
     cudaMemcpyAsync(t.h_out_l, t.d_out_l, map, cudaMemcpyDeviceToHost, s->stream);

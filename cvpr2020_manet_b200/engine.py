@@ -104,9 +104,20 @@ class MatchingSession:
               "manet_session_step_host")
         return self.out_global, self.out_local
 
-    def submit_host(self, slot, frame, interaction_num=1, start_annotated_frame=0, drop_unlabelled=True):
-        """Enqueue upload -> step -> download for ``slot`` (0 or 1) and return immediately."""
+    @property
+    def h2d_bytes_per_streamed_step(self):
+        h, w, c, _ = self.shape
+        return h * w * c * 4 + h * w * 4
+
+    def submit_host(self, slot, frame, interaction_num=1, start_annotated_frame=0, drop_unlabelled=True,
+                    stream=False, reset=False):
+        """Enqueue upload -> step -> download for ``slot`` (0 or 1) and return immediately.
+        ``stream=True``: streaming propagation (MANET_STEP_STREAM): after the first step of a sequence
+        (``reset=True``) only ``cur`` and ``prev_labels`` of the slot are uploaded; the annotated frame stays
+        on the device and the previous frame is the last step's current frame."""
         flags = _lib.GM_DROP_UNLAB if drop_unlabelled else 0
+        if stream:
+            flags |= _lib.STEP_STREAM | (_lib.STEP_STREAM_RESET if reset else 0)
         check(self._lib.manet_session_submit_host(self._h, slot, frame, interaction_num, start_annotated_frame, flags),
               "manet_session_submit_host")
 

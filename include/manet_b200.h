@@ -47,6 +47,13 @@ typedef void* manet_stream_t; /* a cudaStream_t */
 /* session-step flag: run the local-matching branch on the same stream as the global branch (the
  * default forks it onto a second stream so its kernels overlap the pre/post passes of the GEMM) */
 #define MANET_STEP_SERIAL    16u
+/* manet_session_submit_host / _step_host only: streaming propagation.  The first streamed step of a sequence
+ * (or one carrying MANET_STEP_STREAM_RESET) uploads ref, ref_labels, prev, cur and prev_labels; every later step
+ * uploads only its new inputs, cur and prev_labels: the annotated frame stays on the device and the previous
+ * frame of step i is the current frame of step i-1 (the propagation loop of test.py:237-259).  Submit steps
+ * alternating slots 0,1 and wait for step i before submitting step i+2 (the usual two-slot protocol). */
+#define MANET_STEP_STREAM        32u
+#define MANET_STEP_STREAM_RESET  64u
 
 /* dtype codes for the Correlation op (AT_DISPATCH_FLOATING_TYPES_AND_HALF, correlation_cuda_kernel.cu:386) */
 #define MANET_DT_F32 0

@@ -350,6 +350,43 @@ def test_host_buffer_session_equals_device_api(api, cfg_guard):
     s.close()
 
 
+def test_streaming_session_equals_device_api(api, cfg_guard):
+    """MANET_STEP_STREAM: a 7-frame propagation where only the new frame and the new previous-frame labels are
+    uploaded per step must give exactly the maps of the device API fed with (ref, frame[i-1], frame[i])."""
+    from cvpr2020_manet_b200 import engine
+    cfg_guard.TEST_MODE = True
+    gen = torch.Generator().manual_seed(9)
+    C, H, W, N, d, T = 100, 24, 30, 4, 5, 8
+    frames = [0.1 * torch.relu(torch.randn(C, H, W, generator=gen)) for _ in range(T)]
+    labels = [torch.randint(0, N, (H, W), generator=gen).int() for _ in range(T)]
+    rl = torch.randint(-1, N, (H, W), generator=gen).int()
+    s = engine.MatchingSession(H, W, C, N, d, n_frames=T + 1)
+    gm, lm = {}, ({}, {})
+    got = {}
+
+    def fill(slot, i):
+        b = s.slots[slot]
+        b["cur"][:] = frames[i].numpy(); b["prev_labels"][:] = labels[i - 1].numpy()
+        if i == 1:                                   # first step of the sequence: everything
+            b["ref"][:] = frames[0].numpy(); b["prev"][:] = frames[0].numpy(); b["ref_labels"][:] = rl.numpy()
+        else:                                        # later steps: poison what must not be read
+            b["ref"][:] = np.nan; b["prev"][:] = np.nan; b["ref_labels"][:] = -7
+
+    fill(0, 1); s.submit_host(0, 1, 1, 0, stream=True, reset=True)
+    fill(1, 2); s.submit_host(1, 2, 1, 0, stream=True)
+    for i in range(1, T):
+        og, ol = s.wait((i - 1) % 2)
+        got[i] = (og.copy(), ol.copy())
+        if i + 2 < T:
+            fill((i - 1) % 2, i + 2); s.submit_host((i - 1) % 2, i + 2, 1, 0, stream=True)
+    for i in range(1, T):
+        wg, wl = engine.prop_matching_step(frames[0].cuda(), frames[i - 1].cuda(), frames[i].cuda(), rl.cuda(),
+                                           labels[i - 1].cuda(), N - 1, 1, d, gm, lm, "x", i, 1, 0)
+        assert np.array_equal(got[i][0], wg[0, :, :, :, 0].cpu().numpy()), i
+        assert np.array_equal(got[i][1], wl[0, :, :, :, 0].cpu().numpy()), i
+    s.close()
+
+
 # ------------------------------------------------------------------ Correlation op
 @pytest.mark.parametrize("cfgs", [(3, 1, 3, 1, 1), (4, 1, 4, 2, 2), (2, 3, 1, 1, 1), (0, 1, 0, 1, 1), (4, 1, 4, 1, 2)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.float16])
