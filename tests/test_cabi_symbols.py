@@ -64,3 +64,20 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_reference_correlation_extension_loads_if_built():
+    """oracle/_ref/correlation_cuda_ref.so (the reference's own extension, built by oracle/build_ref_correlation.py)
+    imports and exposes the reference's pybind surface (correlation_cuda.cc:169-172).  No compute without a GPU."""
+    import importlib.util
+    import os
+
+    import pytest
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "correlation_cuda_ref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref not built here")
+    import torch  # noqa: F401  (libtorch symbols)
+    spec = importlib.util.spec_from_file_location("correlation_cuda_ref", so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert callable(mod.forward) and callable(mod.backward)
