@@ -22,9 +22,13 @@ PARITY PIN: the reference ships no tests or golden vectors for this path
 runs the UNMODIFIED reference (via ``oracle/ref_shim.py``) in the build
 container and commits its inputs/outputs under ``tests/golden/``;
 ``tests/test_oracle_golden.py`` checks this oracle against those vectors.
+Gradients: ``tests/golden/grad_*.npz`` hold the reference's own autograd results.
 The native ``correlation_cuda`` extension cannot be executed without a GPU, so
-the Correlation restatement is pinned only by ``oracle/naive.py`` and by its
-defining formula ("parity unpinned" for that row).
+the Correlation RESTATEMENT here is checked by ``oracle/naive.py`` and by its
+defining formula only; the Correlation PRODUCT kernels are pinned directly
+against the reference's own extension, compiled into ``oracle/_ref/`` by
+``oracle/build_ref_correlation.py`` and run next to ours on the GPU
+(``tests/test_gpu_reference_corr.py``).
 """
 from __future__ import annotations
 
