@@ -41,7 +41,8 @@ ALGO_FLOP_GLOBAL = 2.0 * M_PIX * M_PIX * C                      # 2*M*R*C, SURVE
 ALGO_BYTES_LOCAL = 4.0 * (2 * C * H * W + H * W + H * W * N_IDS)
 # executed tensor-core work: M padded to 256, R padded per 256-row bucket, K steps of 16 (see gm_fold_remainder)
 EXEC_FLOP_GLOBAL = 2.0 * (101 * 256) * (103 * 256) * 16 * 19   # 19 K=16 MMA steps per tile (7 + 6 + 6, remainder folded)
-KERNELS_PER_STEP = 8   # gm_scan, gm_convert, gm_umma2, gm_finalize | lm_pool, lm_convert, lm_umma | local-map store/select
+KERNELS_PER_STEP = 11  # gm_scan, gm_convert, gm_umma2, gm_finalize | lm_pool, lm_convert, lm_umma + the three guarded CUDA-core local
+                       # kernels (exit at once unless the numerics guard trips) | local-map store/select
 
 
 def load_peaks():
