@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(256)
 gm_scan_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64_t R, const int32_t* __restrict__ labels,
                const float* __restrict__ query, int64_t qps, int64_t qcs, int64_t M, int C, int N,
                GmCtrl* __restrict__ ctrl, int* __restrict__ best, int64_t n_best) {
+    pdl_enter();
     __shared__ int hist[GM_MAXN];
     __shared__ unsigned red[2][8];
     const int t = threadIdx.x;
@@ -225,6 +226,7 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
                   const float* __restrict__ query, int64_t qps, int64_t qcs, int64_t M, int64_t M_pad, int C, int N,
                   int nb_ref, int nb_q, GmCtrl* __restrict__ ctrl, uint8_t* __restrict__ Aimg, uint8_t* __restrict__ Bimg,
                   float* __restrict__ xs, float* __restrict__ ysn, int* __restrict__ tile_obj) {
+    pdl_enter();
     __shared__ float tile[64][GM_CV_PIX + 1];
     __shared__ int off[GM_MAXN + 1];
     __shared__ int bcnt[GM_MAXN], bbase[GM_MAXN];
@@ -584,6 +586,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
 gm_umma2_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg, const float* __restrict__ ysn,
                 const int* __restrict__ tile_obj, const GmCtrl* __restrict__ ctrl, int* __restrict__ best,
                 int n_mpairs, int N, int ksteps, int ksteps_lo) {
+    pdl_enter();
 #ifdef GM_TRACE
     long long tr_wait_full = 0, tr_epi = 0, tr_mma_wait_acc = 0, tr_mma_wait_b = 0, tr_total = clock64();
 #endif
@@ -970,6 +973,7 @@ gm_umma_mc_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ 
 __global__ void gm_finalize_kernel(const int* __restrict__ best, const float* __restrict__ xs,
                                    const GmCtrl* __restrict__ ctrl, int64_t M, int N, int normalize,
                                    float* __restrict__ mem, float* __restrict__ out) {
+    pdl_enter();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M * N) return;
     const int64_t m = i / N; const int o = (int)(i % N);
@@ -1033,10 +1037,10 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
     if (e != cudaSuccess) { set_error("global match: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
     const int64_t items = R + M;
     dim3 g1((unsigned)(ceil_div64(items, 256) < 148 * 8 ? ceil_div64(items, 256) : 148 * 8), GM_SCAN_CG);
-    gm_scan_kernel<<<g1, 256, 0, stream>>>(ref, rps, rcs, R, labels, query, qps, qcs, M, C, N, ctrl, best, p.M_pad * N);
+    launch_k(gm_scan_kernel, g1, dim3(256), 0, stream, ref, rps, rcs, R, labels, query, qps, qcs, M, C, N, ctrl, best, p.M_pad * N);
     const int nb_ref = (int)ceil_div64(R, GM_CV_PIX), nb_q = (int)ceil_div64(p.M_pad, GM_CV_PIX);
-    gm_convert_kernel<<<nb_ref + nb_q + N, 256, 0, stream>>>(ref, rps, rcs, R, labels, query, qps, qcs, M, p.M_pad, C, N,
-                                                             nb_ref, nb_q, ctrl, Aimg, Bimg, xs, ysn, tile_obj);
+    launch_k(gm_convert_kernel, dim3(nb_ref + nb_q + N), dim3(256), 0, stream, ref, rps, rcs, R, labels, query, qps, qcs, M, p.M_pad, C, N,
+             nb_ref, nb_q, ctrl, Aimg, Bimg, xs, ysn, tile_obj);
     static int sm_count = 0;
     static int variant = 2;       // 0: single CTA, 1: multicast pair, 2: cta_group::2 pair (default)
     if (sm_count == 0) {
@@ -1054,11 +1058,11 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
     if (variant == 1)
         gm_umma_mc_kernel<<<sm_count & ~1, GM_THREADS, GM_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles / 2, N, ksteps, ksteps_lo);
     else if (variant == 2)
-        gm_umma2_kernel<<<sm_count & ~1, GM_THREADS, G2_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles / 2, N, ksteps, ksteps_lo);
+        launch_k(gm_umma2_kernel, dim3(sm_count & ~1), dim3(GM_THREADS), (size_t)G2_SMEM_TOTAL, stream, Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles / 2, N, ksteps, ksteps_lo);
     else
         gm_umma_kernel<<<sm_count, GM_THREADS, GM_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles, N, ksteps, ksteps_lo);
     profile_end(PROF_GLOBAL_UMMA, stream);
-    gm_finalize_kernel<<<(unsigned)ceil_div64(M * N, 256), 256, 0, stream>>>(best, xs, ctrl, M, N, normalize, mem_frame, out);
+    launch_k(gm_finalize_kernel, dim3((unsigned)ceil_div64(M * N, 256)), dim3(256), 0, stream, best, xs, ctrl, M, N, normalize, mem_frame, out);
     return check_launch("global match (tcgen05) kernels");
 }
 

@@ -26,6 +26,7 @@ struct LabelPad { const int32_t* labels; int32_t* out; int H, W, pad; };
 
 __global__ void __launch_bounds__(256)
 avg_pool2_kernel(PoolSrc a, PoolSrc b, LabelPad lp, int C, int h, int w, int wp, const float* __restrict__ guard) {
+    pdl_enter();
     if (guard != nullptr && !(guard[1] > kLocalGuardG)) return;   // the tensor-core engine serves this call
     if (blockIdx.y == 2) {
         if (lp.out == nullptr) return;
@@ -81,6 +82,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 __global__ void __launch_bounds__(WTHREADS, 1)
 window_dist_kernel(const float* __restrict__ qs, const float* __restrict__ ps,
                    int C, int h, int w, int wp, int d, float* __restrict__ T, const float* __restrict__ guard) {
+    pdl_enter();
     if (guard != nullptr && !(guard[1] > kLocalGuardG)) return;
     extern __shared__ __align__(16) float wsm[];
     const int win = 2 * d + 1, L = win * win;
@@ -251,6 +253,7 @@ __global__ void __launch_bounds__(UP_STRIDE)
 upsample_mask_min_kernel(const float* __restrict__ T, const int32_t* __restrict__ plabels,
                          const int32_t* __restrict__ gt_ids, int H, int W, int h, int w, int d, int N,
                          float* __restrict__ out, const float* __restrict__ guard) {
+    pdl_enter();
     if (guard != nullptr && !(guard[1] > kLocalGuardG)) return;
     extern __shared__ float sbest[];                         // [N][UP_STRIDE]
     const int win = WIN_T > 0 ? WIN_T : 2 * d + 1;
@@ -368,7 +371,7 @@ static int window_volume(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_s
     dim3 pg((unsigned)imin64(ceil_div64(tot, 256), 148 * 4), labels ? 3 : 2);
     PoolSrc a{x, x_sy, x_sx, x_sc, qs}, b{y, y_sy, y_sx, y_sc, ps};
     LabelPad lpad{labels, labels ? plab : nullptr, H, W, 2 * d};
-    avg_pool2_kernel<<<pg, 256, 0, stream>>>(a, b, lpad, C, h, w, wp, guard);
+    launch_k(avg_pool2_kernel, pg, dim3(256), 0, stream, a, b, lpad, C, h, w, wp, guard);
     if (plabels_out) *plabels_out = plab;
     if (d <= 12) {
         const int ngroups = (win + WDY - 1) / WDY;
@@ -380,7 +383,7 @@ static int window_volume(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_s
             attr_set = true;
         }
         if (!guard) profile_begin(PROF_LOCAL_WINDOW, stream);
-        window_dist_kernel<<<grid, WTHREADS, smem, stream>>>(qs, ps, C, h, w, wp, d, T, guard);
+        launch_k(window_dist_kernel, grid, dim3(WTHREADS), smem, stream, (const float*)qs, (const float*)ps, C, h, w, wp, d, T, guard);
         if (!guard) profile_end(PROF_LOCAL_WINDOW, stream);
     } else {
         int64_t total = (int64_t)h * w * win * win;
@@ -420,7 +423,7 @@ static int simt_masked_min(const float* T, const int32_t* plab, const int32_t* g
     auto kern = (d == 12) ? upsample_mask_min_kernel<25> : (d == 9) ? upsample_mask_min_kernel<19> : upsample_mask_min_kernel<0>;
     if (up_smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)up_smem);
     if (!guard) profile_begin(PROF_LOCAL_MIN, stream);
-    kern<<<(unsigned)imin64(ceil_div64(pix, UP_WARPS), 148 * 8), UP_STRIDE, up_smem, stream>>>(T, plab, gt_ids, H, W, H / 2, W / 2, d, N, out, guard);
+    launch_k(kern, dim3((unsigned)imin64(ceil_div64(pix, UP_WARPS), 148 * 8)), dim3(UP_STRIDE), up_smem, stream, T, plab, gt_ids, H, W, H / 2, W / 2, d, N, out, guard);
     if (!guard) profile_end(PROF_LOCAL_MIN, stream);
     return check_launch("upsample_mask_min_kernel");
 }

@@ -198,6 +198,7 @@ struct LmAux { const int32_t* labels; const int32_t* gt_ids; uint8_t* plab8; int
 __global__ void __launch_bounds__(256)
 lm_pool_kernel(LmPoolSrc a, LmPoolSrc b, LmAux aux, int C, int Cp, int h, int w, float* __restrict__ blkmax,
                float* __restrict__ blksum, LmMuBlocks mub) {
+    pdl_enter();
     extern __shared__ float ptile[];                     // [LM_POOL_PX][Cp + 1]
     __shared__ float red[8];
     __shared__ float sid[LM_MAXN];
@@ -341,6 +342,7 @@ __device__ __forceinline__ float lm_split8(float4 a, float4 b, float4 m0, float4
 
 __global__ void __launch_bounds__(256)
 lm_convert_kernel(const LmConvParams P) {
+    pdl_enter();
     const LmGeom& G = P.g;
     __shared__ __align__(16) float sMu[LM_MAXC];         // mu * s
     __shared__ float red[8];
@@ -560,6 +562,7 @@ __device__ __forceinline__ void lm_off_update(const LmOff& x, const float (&wx1)
 template <bool VOL>
 __global__ void __launch_bounds__(LM_THREADS, 1)
 lm_umma_kernel(const LmParams P) {
+    pdl_enter();
     const LmGeom& G = P.g;
     const int d = P.d, D2 = G.D2, WC = G.WC, WB = G.WB, h = G.h, w = G.w, N = P.N;
     const int tile = blockIdx.x >> 1, half = blockIdx.x & 1;
@@ -1052,12 +1055,12 @@ int launch_local_match_umma(const float* prev, int64_t p_sy, int64_t p_sx, int64
         mub.count += rest < LM_POOL_PX ? rest : LM_POOL_PX;
     }
     profile_begin(PROF_LOCAL_MIN, stream);                // tcgen05 engine: slot 2 = the two pre-pass kernels, slot 1 = the main kernel
-    lm_pool_kernel<<<dim3(g.nbx, g.h, 3), 256, pool_smem, stream>>>(a, b, aux, C, g.Cp, g.h, g.w, blkmax, blksum, mub);
+    launch_k(lm_pool_kernel, dim3(g.nbx, g.h, 3), dim3(256), pool_smem, stream, a, b, aux, C, g.Cp, g.h, g.w, blkmax, blksum, mub);
     LmConvParams CP;
     memset(&CP, 0, sizeof(CP));
     CP.Pq = Pq; CP.Pp = Pp; CP.blkmax = blkmax; CP.n_blkmax = n_blk; CP.blksum = blksum;
     CP.Aimg = Aimg; CP.Xs = Xs; CP.Bimg = Bimg; CP.Ys = Ys; CP.stats = stats; CP.mub = mub; CP.g = g;
-    lm_convert_kernel<<<g.HI * (g.WI >> 5) + 4 * n_tiles, 256, 0, stream>>>(CP);
+    launch_k(lm_convert_kernel, dim3(g.HI * (g.WI >> 5) + 4 * n_tiles), dim3(256), 0, stream, CP);
     profile_end(PROF_LOCAL_MIN, stream);
     P.Aimg = Aimg; P.Xs = Xs; P.Bimg = Bimg; P.Ys = Ys; P.stats = stats; P.guarded = guarded ? 1 : 0;
     if (guard_out) *guard_out = stats;
@@ -1071,8 +1074,8 @@ int launch_local_match_umma(const float* prev, int64_t p_sy, int64_t p_sx, int64
         attr_set = true;
     }
     profile_begin(PROF_LOCAL_WINDOW, stream);
-    if (labels) lm_umma_kernel<false><<<2 * n_tiles, LM_THREADS, g.total, stream>>>(P);
-    else lm_umma_kernel<true><<<2 * n_tiles, LM_THREADS, g.total, stream>>>(P);
+    if (labels) launch_k(lm_umma_kernel<false>, dim3(2 * n_tiles), dim3(LM_THREADS), (size_t)g.total, stream, P);
+    else launch_k(lm_umma_kernel<true>, dim3(2 * n_tiles), dim3(LM_THREADS), (size_t)g.total, stream, P);
     profile_end(PROF_LOCAL_WINDOW, stream);
     if (T_out) *T_out = Tvol;
     return check_launch("local match (tcgen05) kernels");

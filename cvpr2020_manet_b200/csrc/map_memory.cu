@@ -12,6 +12,7 @@ namespace manet {
 __global__ void local_map_store_select_kernel(const float* __restrict__ nw, float* __restrict__ mem_rounds,
                                               float* __restrict__ dist_row, int r, float dist_value,
                                               float* __restrict__ out, int64_t n) {
+    pdl_enter();
     // dist_row[r] is written below by one thread and read by nobody (dist_value is by value);
     // dist_row[r-1] is read-only here.
     const bool take_new = (r == 0) || (dist_value > dist_row[r - 1]);
@@ -32,8 +33,8 @@ int launch_local_map_store_select(const float* nw, float* mem_rounds, float* dis
         return fail_invalid("local map memory: interaction_num must be in [1, 9] (IntVOS.py:641)");
     if (n <= 0) return 0;
     unsigned grid = (unsigned)imin64(ceil_div64(n, 256), 148 * 8);
-    local_map_store_select_kernel<<<grid, 256, 0, stream>>>(nw, mem_rounds, dist_row, interaction_num - 1,
-                                                            dist_value, out, n);
+    launch_k(local_map_store_select_kernel, dim3(grid), dim3(256), 0, stream, nw, mem_rounds, dist_row, interaction_num - 1,
+             dist_value, out, n);
     return check_launch("local_map_store_select_kernel");
 }
 
