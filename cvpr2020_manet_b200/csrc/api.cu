@@ -58,6 +58,13 @@ int launch_correlation_forward(const void*, const int64_t*, const void*, const i
 int launch_correlation_backward(const void*, const int64_t*, const void*, const int64_t*, void*, void*, const void*,
                                 const int64_t*, void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 
+size_t seghead_packed_bytes();
+size_t seghead_workspace_bytes(int N, int H, int W);
+int launch_seghead_pack(const float* const*, int, float, void*, cudaStream_t);
+int seghead_forward_tensor(const void*, int, const float*, const int64_t*, int, int, int, float*, void*, size_t, cudaStream_t);
+int seghead_forward_parts(const void*, const float*, int64_t, int64_t, int64_t, int, const float*, const float*, const int32_t*,
+                          const int32_t*, int, int, int, float*, void*, size_t, cudaStream_t);
+
 // ---- optional kernel timing pools
 struct ProfPool { cudaEvent_t* start; cudaEvent_t* stop; int cap; int n; };
 static ProfPool g_prof[PROF_SLOTS];
@@ -281,6 +288,41 @@ int manet_local_map_store_select(const float* new_map, float* mem_frame_rounds, 
     MANET_REQUIRE(new_map && mem_frame_rounds && dist_row && out && n >= 0, "local map memory: null pointer / bad size");
     return launch_local_map_store_select(new_map, mem_frame_rounds, dist_row, interaction_num, dist_value, out, n,
                                          (cudaStream_t)stream);
+}
+
+size_t manet_seghead_packed_bytes(void) { return seghead_packed_bytes(); }
+
+size_t manet_seghead_workspace_bytes(int n_objects, int H, int W) {
+    if (n_objects < 1 || H < 1 || W < 1) return 0;
+    return seghead_workspace_bytes(n_objects, H, W);
+}
+
+int manet_seghead_pack(const float* const* params, int n_params, int in_dim, float bn_eps, void* packed, manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(params && packed, "seghead pack: null pointer");
+    MANET_REQUIRE(n_params == MANET_SEGHEAD_N_PARAMS, "seghead pack: expected 50 parameter tensors (4 x 12 + conv.weight, conv.bias)");
+    for (int i = 0; i < n_params; ++i) MANET_REQUIRE(params[i], "seghead pack: null parameter tensor");
+    return launch_seghead_pack(params, in_dim, bn_eps, packed, (cudaStream_t)stream);
+}
+
+int manet_seghead_forward(const void* packed, int in_dim, const float* x, const int64_t* x_strides, int n_objects, int H, int W,
+                          float* logits, void* workspace, size_t workspace_bytes, manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(packed && x && x_strides && logits && workspace, "seghead forward: null pointer");
+    return seghead_forward_tensor(packed, in_dim, x, x_strides, n_objects, H, W, logits, workspace, workspace_bytes,
+                                  (cudaStream_t)stream);
+}
+
+int manet_seghead_forward_parts(const void* packed, const float* emb, int64_t emb_ch_stride, int64_t emb_row_stride,
+                                int64_t emb_col_stride, int C, const float* global_map, const float* local_map,
+                                const int32_t* prev_labels, const int32_t* gt_ids, int n_objects, int H, int W, float* logits,
+                                void* workspace, size_t workspace_bytes, manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(packed && emb && global_map && local_map && prev_labels && gt_ids && logits && workspace,
+                  "seghead forward: null pointer");
+    MANET_REQUIRE(C >= 1 && C + 3 <= 128, "seghead forward: embedding channels + 3 must be <= 128");
+    return seghead_forward_parts(packed, emb, emb_ch_stride, emb_row_stride, emb_col_stride, C, global_map, local_map,
+                                 prev_labels, gt_ids, n_objects, H, W, logits, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int manet_correlation_output_shape(int C, int H, int W, int pad_size, int kernel_size, int max_displacement, int stride1,

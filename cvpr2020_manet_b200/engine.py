@@ -54,6 +54,69 @@ def int_matching_step(ref_emb, scribble_label, n_objects, max_distance=None, glo
     return loc, merged
 
 
+def prop_seghead(ref_frame_embedding=None, previous_frame_embedding=None, current_frame_embedding=None,
+                 ref_scribble_label=None, previous_frame_mask=None, normalize_nearest_neighbor_distances=True,
+                 use_local_map=True, seq_names=None, gt_ids=None, k_nearest_neighbors=1, global_map_tmp_dic=None,
+                 local_map_dics=None, interaction_num=None, start_annotated_frame=None, frame_num=None,
+                 dynamic_seghead=None):
+    """``IntVOS.prop_seghead`` (IntVOS.py:583-681) with the reference's arguments and return forms:
+    embeddings ``[bs,C,h,w]``, ``ref_scribble_label`` ``[bs,1,h,w]`` (TEST_MODE: already at embedding
+    resolution, IntVOS.py:593-594) or full resolution (nearest-downscaled, :596), ``previous_frame_mask``
+    ``[bs,1,Hf,Wf]``; returns ``{seq: pred [1,N,h,w]}`` (+ the memories that were passed in).
+    Matching, both memories and the head run on the sm_100a kernels; a ``DynamicSegHead`` of this package
+    is fed by its parts (no repeat/cat, :663-670), any other callable receives the ``to_cat`` tensor."""
+    from .networks.seghead import DynamicSegHead
+    dic_tmp = {}
+    bs, c, h, w = current_frame_embedding.size()
+    if cfg.TEST_MODE:
+        scale_ref = ref_scribble_label.float()
+    else:
+        scale_ref = torch.nn.functional.interpolate(ref_scribble_label.float(), size=(h, w), mode="nearest")
+    scale_ref = scale_ref.int()
+    scale_prev = torch.nn.functional.interpolate(previous_frame_mask.float(), size=(h, w), mode="nearest").int()
+    for n in range(bs):
+        cur = current_frame_embedding[n].permute(1, 2, 0)
+        ref = ref_frame_embedding[n].permute(1, 2, 0)
+        prev = previous_frame_embedding[n].permute(1, 2, 0)
+        ref_label = scale_ref[n].permute(1, 2, 0)
+        prev_label = scale_prev[n].permute(1, 2, 0)
+        seq = seq_names[n]
+        mem_slot = None
+        if global_map_tmp_dic is not None:
+            if seq not in global_map_tmp_dic:
+                global_map_tmp_dic[seq] = torch.ones((104, h, w, int(gt_ids[n]) + 1, 1), dtype=torch.float32, device=cur.device)
+            mem_slot = global_map_tmp_dic[seq][int(frame_num[n])]
+        if normalize_nearest_neighbor_distances:
+            g, ids = nearest_neighbor_features_per_object(ref, cur, ref_label, k_nearest_neighbors, gt_ids[n], n_chunks=10,
+                                                          normalize=True, memory_frame=mem_slot)
+        else:
+            g, ids = nearest_neighbor_features_per_object(ref, cur, ref_label, k_nearest_neighbors, gt_ids[n], n_chunks=10)
+            if mem_slot is not None:
+                g = global_map_read_update(global_map_tmp_dic, seq, frame_num[n], g)
+        if use_local_map:
+            loc = local_previous_frame_nearest_neighbor_features_per_object(prev, cur, prev_label, ids,
+                                                                            cfg.MODEL_MAX_LOCAL_DISTANCE)
+        else:
+            loc, _ = nearest_neighbor_features_per_object(prev, cur, prev_label, k_nearest_neighbors, gt_ids[n],
+                                                          n_chunks=20, normalize=True)
+        if local_map_dics is not None:
+            loc, local_map_dics = local_map_store_select(local_map_dics, seq, frame_num[n], interaction_num,
+                                                         start_annotated_frame, loc)
+        if isinstance(dynamic_seghead, DynamicSegHead):
+            pred = dynamic_seghead.forward_parts(current_frame_embedding[n], g, loc, prev_label, ids)
+        else:
+            to_cat_prev = (prev_label.float() == ids.float()).unsqueeze(-1).permute(2, 3, 0, 1).float()
+            to_cat = torch.cat((current_frame_embedding[n].unsqueeze(0).repeat((ids.size(0), 1, 1, 1)),
+                                g.squeeze(0).permute(2, 3, 0, 1), loc.squeeze(0).permute(2, 3, 0, 1), to_cat_prev), 1)
+            pred = dynamic_seghead(to_cat)
+        dic_tmp[seq] = pred.permute(1, 0, 2, 3)
+    if global_map_tmp_dic is None:
+        return dic_tmp
+    if local_map_dics is None:
+        return dic_tmp, global_map_tmp_dic
+    return dic_tmp, global_map_tmp_dic, local_map_dics
+
+
 class MatchingSession:
     """Host-buffer propagation steps through ``manet_session_*`` (include/manet_b200.h): the caller
     fills pinned host buffers with ``[C,H,W]`` embeddings and ``[H,W]`` labels, ``step_host`` uploads

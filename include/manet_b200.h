@@ -241,6 +241,46 @@ int manet_correlation_backward(const void* in1, const int64_t* in1_strides,
                                int stride1, int stride2, int dtype, manet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * DynamicSegHead, inference form (networks/IntVOS.py:488-525: four _split_separable_conv2d blocks
+ * [depthwise 7x7 -> BN -> ReLU -> 1x1 conv to 256 -> BN -> ReLU] and a final 1x1 conv to one
+ * logit), the consumer of both matching maps (IntVOS.py:663-671).  Batch norm uses its running
+ * statistics (model.eval(), as test.py runs it); training-mode statistics are out of scope.
+ *
+ * manet_seghead_pack folds every conv+BN pair and writes the device-side parameter blob the
+ * forward calls read (`packed`: manet_seghead_packed_bytes() bytes, caller-allocated, 1024-byte
+ * aligned).  `params` is a HOST array of MANET_SEGHEAD_N_PARAMS DEVICE pointers to contiguous
+ * fp32 tensors in state_dict order: for layer1..layer4
+ *   conv1.weight [C,1,7,7], conv1.bias [C], bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var [C],
+ *   conv2.weight [256,C,1,1], conv2.bias [256], bn2.weight, bn2.bias, bn2.running_mean, bn2.running_var [256]
+ * (C = in_dim for layer1, 256 after), then conv.weight [1,256,1,1], conv.bias [1].
+ *
+ * manet_seghead_forward:   x [n_objects, in_dim, H, W] fp32 with element strides x_strides[4]
+ *                          (the tensor `dynamic_seghead(to_cat)` receives, IntVOS.py:670-671)
+ *                          -> logits [n_objects, H, W] fp32 (pred_ of IntVOS.py:671 without its unit channel).
+ * manet_seghead_forward_parts: the same head fed by the parts of `to_cat` (IntVOS.py:663-670) without
+ *                          materialising the repeat/cat: emb = current-frame embedding [C,H,W] (element
+ *                          strides), global_map / local_map = [H,W,n_objects] fp32 (the matchers'
+ *                          [1,H,W,N,1] outputs), prev_labels [H,W] int32, gt_ids [n_objects] int32
+ *                          (channel C+2 = prev_labels == gt_ids[n], IntVOS.py:663).
+ * in_dim <= 128, embed dim fixed at 256 (cfg.MODEL_HEAD_EMBEDDING_DIM).  Numerics: depthwise convs in
+ * fp32; 1x1 convs as fp16 hi/lo split tensor-core products with fp32 accumulation (fp32 grade).
+ * ------------------------------------------------------------------------------------------ */
+#define MANET_SEGHEAD_N_PARAMS 50
+size_t manet_seghead_packed_bytes(void);
+size_t manet_seghead_workspace_bytes(int n_objects, int H, int W);
+int manet_seghead_pack(const float* const* params, int n_params, int in_dim, float bn_eps, void* packed,
+                       manet_stream_t stream);
+int manet_seghead_forward(const void* packed, int in_dim, const float* x, const int64_t* x_strides,
+                          int n_objects, int H, int W, float* logits,
+                          void* workspace, size_t workspace_bytes, manet_stream_t stream);
+int manet_seghead_forward_parts(const void* packed, const float* emb, int64_t emb_ch_stride,
+                                int64_t emb_row_stride, int64_t emb_col_stride, int C,
+                                const float* global_map, const float* local_map,
+                                const int32_t* prev_labels, const int32_t* gt_ids,
+                                int n_objects, int H, int W, float* logits,
+                                void* workspace, size_t workspace_bytes, manet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Optional kernel timing for benchmarks (no reference equivalent).  After
  * manet_profile_enable(n) the launchers bracket their dominant kernels with CUDA events on the
  * launching stream (slot 0: tcgen05 global-matching kernel, 1: local window-distance kernel,

@@ -312,3 +312,49 @@ def correlation_backward(in1, in2, grad_out, pad_size, kernel_size, max_displace
     out = correlation_forward(a, b, pad_size, kernel_size, max_displacement, stride1, stride2)
     ga, gb = torch.autograd.grad(out, (a, b), grad_out.float())
     return ga.to(in1.dtype), gb.to(in2.dtype)
+
+
+# ------------------------------------------------------------------------------- DynamicSegHead
+SEGHEAD_BN_EPS = 1e-5      # SynchronizedBatchNorm2d default eps (networks/sync_batchnorm/batchnorm.py)
+
+
+def seghead_param_names():
+    """state_dict keys of the reference's DynamicSegHead (IntVOS.py:488-525) in the order the C ABI packs them."""
+    names = []
+    for layer in range(1, 5):
+        p = f"layer{layer}."
+        names += [p + "conv1.weight", p + "conv1.bias", p + "bn1.weight", p + "bn1.bias", p + "bn1.running_mean",
+                  p + "bn1.running_var", p + "conv2.weight", p + "conv2.bias", p + "bn2.weight", p + "bn2.bias",
+                  p + "bn2.running_mean", p + "bn2.running_var"]
+    return names + ["conv.weight", "conv.bias"]
+
+
+def dynamic_seghead_forward(state: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
+    """Eval-mode forward of DynamicSegHead (IntVOS.py:519-525): four _split_separable_conv2d blocks
+    (:488-508: depthwise 7x7, BN, ReLU, 1x1 conv, BN, ReLU) and the final 1x1 conv.  ``x``: [N,Cin,H,W] ->
+    [N,1,H,W]."""
+    for layer in range(1, 5):
+        p = f"layer{layer}."
+        w1 = state[p + "conv1.weight"]
+        x = F.conv2d(x, w1, state[p + "conv1.bias"], stride=1, padding=(w1.shape[-1] - 1) // 2, groups=w1.shape[0])
+        x = F.batch_norm(x, state[p + "bn1.running_mean"], state[p + "bn1.running_var"], state[p + "bn1.weight"],
+                         state[p + "bn1.bias"], False, 0.0, SEGHEAD_BN_EPS)
+        x = F.relu(x)
+        x = F.conv2d(x, state[p + "conv2.weight"], state[p + "conv2.bias"])
+        x = F.batch_norm(x, state[p + "bn2.running_mean"], state[p + "bn2.running_var"], state[p + "bn2.weight"],
+                         state[p + "bn2.bias"], False, 0.0, SEGHEAD_BN_EPS)
+        x = F.relu(x)
+    return F.conv2d(x, state["conv.weight"], state["conv.bias"])
+
+
+def seghead_features(cur_emb: torch.Tensor, global_map: torch.Tensor, local_map: torch.Tensor,
+                     prev_label: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    """The ``to_cat`` tensor of prop_seghead (IntVOS.py:663-670): ``cur_emb`` [C,H,W], maps [1,H,W,N,1],
+    ``prev_label`` [H,W] int, ``ids`` [N] -> [N, C+3, H, W]."""
+    n = ids.shape[0]
+    prev = (prev_label.unsqueeze(-1).float() == ids.float())                    # [H,W,N]
+    to_cat_emb = cur_emb.unsqueeze(0).repeat((n, 1, 1, 1))
+    to_cat_g = global_map.squeeze(0).permute(2, 3, 0, 1)
+    to_cat_prev = prev.unsqueeze(-1).permute(2, 3, 0, 1).float()
+    to_cat_l = local_map.squeeze(0).permute(2, 3, 0, 1)
+    return torch.cat((to_cat_emb, to_cat_g, to_cat_l, to_cat_prev), 1)

@@ -1,0 +1,94 @@
+"""Golden vectors for DynamicSegHead: runs the UNMODIFIED reference class
+(``/root/reference/networks/IntVOS.py:510-525``) in eval mode on CPU through ``oracle/ref_shim.py``.
+Build container only:
+
+    python tests/golden/make_golden_seghead.py
+
+The weights are the reference's own initialisation (kaiming-normal convs) with randomised batch-norm
+affine parameters and running statistics, so that the BN folding is exercised.  fp16-compressible they
+are not: the file is ~1.2 MB.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import ref_shim  # noqa: E402
+from oracle import manet_oracle as O  # noqa: E402
+
+
+def main():
+    ref = ref_shim.load_reference()
+    torch.manual_seed(7)
+    head = ref.DynamicSegHead()
+    gen = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        for name, mod in head.named_modules():
+            if name.endswith("bn1") or name.endswith("bn2"):
+                c = mod.weight.shape[0]
+                mod.weight.copy_(0.5 + torch.rand(c, generator=gen))
+                mod.bias.copy_(0.2 * torch.randn(c, generator=gen))
+                mod.running_mean.copy_(0.1 * torch.randn(c, generator=gen))
+                mod.running_var.copy_(0.5 + torch.rand(c, generator=gen))
+    head.eval()
+    n, c, h, w = 3, 100, 21, 37          # ragged against the 8x16 pixel tiles
+    cur = 0.1 * torch.relu(torch.randn(c, h, w, generator=gen))
+    gmap = torch.rand(1, h, w, n, 1, generator=gen)
+    lmap = torch.rand(1, h, w, n, 1, generator=gen)
+    lmap[0, :4, :, 1, 0] = 1.0
+    prev = torch.randint(0, n, (h // 3, w // 3 + 1), generator=gen).repeat_interleave(3, 0).repeat_interleave(3, 1)[:h, :w].int()
+    ids = torch.arange(n, dtype=torch.int32)
+    x = O.seghead_features(cur, gmap, lmap, prev, ids)
+    with torch.no_grad():
+        y = head(x)
+    state = {k: v.detach().clone() for k, v in head.state_dict().items()}
+    mine = O.dynamic_seghead_forward(state, x)
+    print("oracle vs reference max abs diff:", float((mine - y).abs().max()), "logit range", float(y.min()), float(y.max()))
+    out = {"cur": cur.numpy(), "gmap": gmap.numpy(), "lmap": lmap.numpy(), "prev": prev.numpy(), "ids": ids.numpy(),
+           "y": y.numpy()}                      # x = oracle.seghead_features(cur, gmap, lmap, prev, ids)
+    for k in O.seghead_param_names():
+        out["p:" + k] = state[k].numpy()
+    np.savez_compressed(os.path.join(HERE, "seghead_ref.npz"), **out)
+    print("wrote seghead_ref.npz", os.path.getsize(os.path.join(HERE, "seghead_ref.npz")) // 1024, "KB")
+    prop_seghead_case(head)
+
+
+def prop_seghead_case(head):
+    """The reference's own IntVOS.prop_seghead (IntVOS.py:583-681) end to end -- matching, both memories and the
+    head above -- for two propagation steps of one round; weights are those of seghead_ref.npz."""
+    import types
+    c, h, w, nobj, d = 100, 18, 22, 2, 3
+    mod = ref_shim.load_reference(test_mode=True, max_local_distance=d)
+    gen = torch.Generator().manual_seed(23)
+    embs = torch.stack([0.1 * torch.relu(torch.randn(c, h, w, generator=gen)) for _ in range(3)])
+    scr = torch.full((h, w), -1, dtype=torch.int32)
+    scr[3, 2:12] = 0
+    scr[9, 5:20] = 1
+    scr[12:16, 7] = 2
+    fake_self = types.SimpleNamespace()
+    gmem, lmem = {}, ({}, {})
+    out = {"embs": embs.numpy(), "scribble": scr.numpy(), "n_obj": nobj, "d": d}
+    with ref_shim.cpu_cuda_identity(), torch.no_grad():
+        for f in (1, 2):
+            pl = torch.randint(0, nobj + 1, (h // 2, w // 2), generator=gen).repeat_interleave(2, 0).repeat_interleave(2, 1).int()
+            res = mod.IntVOS.prop_seghead(fake_self, ref_frame_embedding=embs[0:1], previous_frame_embedding=embs[f - 1:f],
+                                          current_frame_embedding=embs[f:f + 1], ref_scribble_label=scr.view(1, 1, h, w).float(),
+                                          previous_frame_mask=pl.view(1, 1, h, w).float(),
+                                          normalize_nearest_neighbor_distances=True, use_local_map=True, seq_names=["s"],
+                                          gt_ids=torch.tensor([nobj]), k_nearest_neighbors=1, global_map_tmp_dic=gmem,
+                                          local_map_dics=lmem, interaction_num=1, start_annotated_frame=0, frame_num=[f],
+                                          dynamic_seghead=head)
+            out[f"f{f}_prev_mask"] = pl.numpy()
+            out[f"f{f}_pred"] = res[0]["s"].numpy()
+    np.savez_compressed(os.path.join(HERE, "prop_seghead_ref.npz"), **out)
+    print("wrote prop_seghead_ref.npz", {k: np.asarray(v).shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

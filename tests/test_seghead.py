@@ -1,0 +1,191 @@
+"""DynamicSegHead (reference networks/IntVOS.py:488-525 and the feature assembly :663-671).
+
+CPU part: the oracle restatement against golden vectors recorded from the UNMODIFIED reference class
+(tests/golden/make_golden_seghead.py) and the host-side contract of the drop-in module.
+GPU part (-m gpu): the sm_100a kernels through the C ABI against those goldens, against the oracle at the
+480p / 5-object size, and on edge shapes.
+
+Tolerance: logits |a-b| <= 2e-5 * max(1, max|b|).  The depthwise convs are fp32; the 1x1 convs run as fp16 hi/lo
+split tensor-core products (22+ significant bits per operand, fp32 accumulation) -- fp32 grade, like the matchers.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import manet_oracle as O
+
+LOGIT_RTOL = 2e-5
+
+
+def load_state(g):
+    return {k[2:]: torch.from_numpy(g[k]) for k in g if k.startswith("p:")}
+
+
+def logit_err(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    return float(np.abs(got - want).max() / max(1.0, np.abs(want).max()))
+
+
+# ------------------------------------------------------------------------------------------------ CPU
+def test_oracle_seghead_matches_reference(golden):
+    g = golden("seghead_ref")
+    x = O.seghead_features(torch.from_numpy(g["cur"]), torch.from_numpy(g["gmap"]), torch.from_numpy(g["lmap"]),
+                           torch.from_numpy(g["prev"]), torch.from_numpy(g["ids"]))
+    assert x.shape == (3, 103, 21, 37)
+    y = O.dynamic_seghead_forward(load_state(g), x)
+    assert np.array_equal(y.numpy(), g["y"])          # same torch ops on the same host: bit-exact
+
+
+def test_oracle_prop_seghead_matches_reference(golden):
+    """The reference's IntVOS.prop_seghead end to end (matching + memories + head) against the oracle pieces."""
+    g, gh = golden("prop_seghead_ref"), golden("seghead_ref")
+    state = load_state(gh)
+    embs = torch.from_numpy(g["embs"])
+    scr = torch.from_numpy(g["scribble"])
+    nobj, d = int(g["n_obj"]), int(g["d"])
+    gm, lm = {}, ({}, {})
+    ids = torch.arange(nobj + 1, dtype=torch.int32)
+    for f in (1, 2):
+        pl = torch.from_numpy(g[f"f{f}_prev_mask"])
+        gmap, lmap = O.prop_matching_step(embs[0], embs[f - 1], embs[f], scr, pl, nobj, 1, d, True, gm, lm, "s", f, 1, 0)
+        pred = O.dynamic_seghead_forward(state, O.seghead_features(embs[f], gmap, lmap, pl, ids)).permute(1, 0, 2, 3)
+        assert logit_err(pred.numpy(), g[f"f{f}_pred"]) <= 1e-6
+
+
+def test_module_contract():
+    from cvpr2020_manet_b200.networks.seghead import DynamicSegHead, param_names
+    head = DynamicSegHead()
+    assert param_names() == O.seghead_param_names()
+    ref_shapes = {"layer1.conv1.weight": (103, 1, 7, 7), "layer1.conv2.weight": (256, 103, 1, 1),
+                  "layer4.conv1.weight": (256, 1, 7, 7), "layer4.bn2.running_var": (256,), "conv.weight": (1, 256, 1, 1),
+                  "conv.bias": (1,)}
+    sd = head.state_dict()
+    for k, shp in ref_shapes.items():
+        assert tuple(sd[k].shape) == shp
+    head.eval()
+    with pytest.raises(TypeError):                    # CPU tensors: no fallback
+        head(torch.zeros(1, 103, 8, 8))
+    with pytest.raises(ValueError):
+        DynamicSegHead(in_dim=103, embed_dim=128)
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.fixture(scope="module")
+def gpu_head(golden):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from cvpr2020_manet_b200.networks.seghead import DynamicSegHead
+    g = golden("seghead_ref")
+    head = DynamicSegHead()
+    head.load_state_dict(load_state(g), strict=False)
+    return head.cuda().eval(), g
+
+
+@pytest.mark.gpu
+def test_gpu_seghead_golden(gpu_head):
+    head, g = gpu_head
+    x = O.seghead_features(torch.from_numpy(g["cur"]), torch.from_numpy(g["gmap"]), torch.from_numpy(g["lmap"]),
+                           torch.from_numpy(g["prev"]), torch.from_numpy(g["ids"]))
+    y = head(x.cuda())
+    assert y.shape == g["y"].shape
+    assert logit_err(y.cpu().numpy(), g["y"]) <= LOGIT_RTOL
+    # non-contiguous input (channels-last storage) gives the same result
+    y2 = head(x.cuda().permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2))
+    assert torch.equal(y, y2)
+    # fed by its parts: no repeat/cat (IntVOS.py:663-670)
+    y3 = head.forward_parts(torch.from_numpy(g["cur"]).cuda(), torch.from_numpy(g["gmap"]).cuda(),
+                            torch.from_numpy(g["lmap"]).cuda(), torch.from_numpy(g["prev"]).cuda(),
+                            torch.from_numpy(g["ids"]).cuda())
+    assert torch.equal(y, y3)
+
+
+@pytest.mark.gpu
+def test_gpu_seghead_training_mode_raises(gpu_head):
+    head, _ = gpu_head
+    head.train()
+    try:
+        with pytest.raises(NotImplementedError):
+            head(torch.zeros(1, 103, 8, 8, device="cuda"))
+    finally:
+        head.eval()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,h,w,scale", [(1, 5, 7, 1.0), (2, 8, 16, 1.0), (1, 9, 17, 1.0), (3, 30, 54, 1e3), (2, 16, 33, 1e-4),
+                                         (1, 12, 20, 0.0)])
+def test_gpu_seghead_edge_shapes(gpu_head, n, h, w, scale):
+    """Tiles smaller than / ragged against the 8x16 pixel unit, one object, large and tiny dynamic range (the
+    per-pixel operand scale), all-zero input."""
+    head, g = gpu_head
+    gen = torch.Generator().manual_seed(h * 100 + w)
+    x = scale * torch.randn(n, 103, h, w, generator=gen)
+    want = O.dynamic_seghead_forward(load_state(g), x)
+    got = head(x.cuda())
+    assert logit_err(got.cpu().numpy(), want.numpy()) <= LOGIT_RTOL
+
+
+@pytest.mark.gpu
+def test_gpu_seghead_repacks_after_weight_update(gpu_head):
+    head, g = gpu_head
+    x = torch.randn(1, 103, 10, 18, generator=torch.Generator().manual_seed(5))
+    state = load_state(g)
+    before = head(x.cuda()).clone()
+    saved = head.conv.bias.detach().clone()
+    try:
+        with torch.no_grad():
+            head.conv.bias.add_(1.5)
+        after = head(x.cuda())
+        assert torch.allclose(after, before + 1.5, atol=1e-4)
+    finally:
+        with torch.no_grad():
+            head.conv.bias.copy_(saved)
+    assert torch.equal(head(x.cuda()), before)
+    assert logit_err(before.cpu().numpy(), O.dynamic_seghead_forward(state, x).numpy()) <= LOGIT_RTOL
+
+
+@pytest.mark.gpu
+def test_gpu_seghead_480p_five_objects(gpu_head):
+    """BASELINE shape: [6, 103, 120, 214] against the oracle (torch CPU fp32)."""
+    head, g = gpu_head
+    gen = torch.Generator().manual_seed(3)
+    cur = 0.1 * torch.relu(torch.randn(100, 120, 214, generator=gen))
+    gmap = torch.rand(1, 120, 214, 6, 1, generator=gen)
+    lmap = torch.rand(1, 120, 214, 6, 1, generator=gen)
+    prev = torch.randint(0, 6, (15, 27), generator=gen).repeat_interleave(8, 0).repeat_interleave(8, 1)[:120, :214].int()
+    ids = torch.arange(6, dtype=torch.int32)
+    want = O.dynamic_seghead_forward(load_state(g), O.seghead_features(cur, gmap, lmap, prev, ids))
+    got = head.forward_parts(cur.cuda(), gmap.cuda(), lmap.cuda(), prev.cuda(), ids.cuda())
+    assert got.shape == (6, 1, 120, 214)
+    assert logit_err(got.cpu().numpy(), want.numpy()) <= LOGIT_RTOL
+    # determinism (the two column halves of the last layer meet in one atomicAdd pair per logit)
+    again = head.forward_parts(cur.cuda(), gmap.cuda(), lmap.cuda(), prev.cuda(), ids.cuda())
+    assert torch.equal(got, again)
+
+
+@pytest.mark.gpu
+def test_gpu_prop_seghead_matches_reference(golden, gpu_head):
+    """engine.prop_seghead (the reference's signature, IntVOS.py:583-681) against the reference's own run."""
+    from cvpr2020_manet_b200 import engine
+    from cvpr2020_manet_b200.config import cfg
+    head, _ = gpu_head
+    g = golden("prop_seghead_ref")
+    saved = (cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE)
+    cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE = True, int(g["d"])
+    try:
+        embs = torch.from_numpy(g["embs"]).cuda()
+        scr = torch.from_numpy(g["scribble"]).cuda()
+        h, w = scr.shape
+        gm, lm = {}, ({}, {})
+        for f in (1, 2):
+            pl = torch.from_numpy(g[f"f{f}_prev_mask"]).cuda()
+            res, gm, lm = engine.prop_seghead(ref_frame_embedding=embs[0:1], previous_frame_embedding=embs[f - 1:f],
+                                              current_frame_embedding=embs[f:f + 1],
+                                              ref_scribble_label=scr.view(1, 1, h, w).float(),
+                                              previous_frame_mask=pl.view(1, 1, h, w).float(), seq_names=["s"],
+                                              gt_ids=torch.tensor([int(g["n_obj"])]), k_nearest_neighbors=1,
+                                              global_map_tmp_dic=gm, local_map_dics=lm, interaction_num=1,
+                                              start_annotated_frame=0, frame_num=[f], dynamic_seghead=head)
+            assert res["s"].shape == g[f"f{f}_pred"].shape
+            # the maps entering the head are within 1e-5 of the reference's; the head's Lipschitz factor is O(10)
+            assert logit_err(res["s"].cpu().numpy(), g[f"f{f}_pred"]) <= 2e-4
+    finally:
+        cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE = saved
