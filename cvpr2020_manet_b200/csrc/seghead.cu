@@ -146,87 +146,139 @@ sh_assemble_kernel(ShSource s, int in_dim, int N, int H, int W, float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------- depthwise 7x7
-template <int C>
-__global__ void __launch_bounds__(C, 1)
-sh_dw_kernel(const float* __restrict__ X, const float* __restrict__ dwW, const float* __restrict__ dwB,
-             uint8_t* __restrict__ Aimg, float* __restrict__ rinv, int H, int W, int TX, int TY) {
-    pdl_enter();
-    __shared__ unsigned pixmax[SH_UNIT];
-    const int c = threadIdx.x, lane = c & 31;
-    const int unit = blockIdx.x;
-    const int tx = unit % TX, ty = (unit / TX) % TY, n = unit / (TX * TY);
-    float w[49];
+// One thread per channel PAIR (sm_100 packed fp32: one FFMA2 does both channels; inputs, weights and results are
+// natural float2 in NHWC), 8x16 pixel tile per CTA, processed as four passes of 4 rows x 8 columns (32 float2
+// accumulators).  The input rows of a pass (14 pixels x C channels) travel through a 4-deep shared-memory ring
+// filled by 8-byte cp.async copies: every thread copies and later reads only ITS OWN slots, so the ring needs no
+// CTA barrier -- it is a per-thread asynchronous prefetch, three rows ahead.  A warp covers 64 channels = one
+// 128-byte row of a k-block of the operand image, so its hi (and lo) stores of a pixel are one full line.
+// History (ncu, profiles/): one channel per thread, 64 accumulators at 255 registers (8 warps per SM): 314 us per
+// layer, issue slots 43 % busy, top stall "wait" (fixed-latency FFMA chains, 2 warps per scheduler); 32 accumulators
+// under a 128-register cap (16 warps per SM): 217 us, 59 % of the issued instructions are not FFMAs (copies, loads,
+// predicates, the per-pixel scale/split/store) -> channel pairs halve everything but the FMA pipe time.
+constexpr int DW_RING = 4;
+constexpr int DW_PW = 8, DW_PH = 4;            // pass: 4 rows x 8 columns of output pixels
+constexpr int DW_IN_W = DW_PW + 6;             // input pixels per row of a pass
+constexpr int DW_IN_H = DW_PH + 6;             // input rows of a pass
+
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void red_max_shared_if(unsigned* addr, unsigned v, bool p) {      // predicated, no branch
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q red.shared.max.u32 [%0], %1;\n\t}" ::"r"(smem_u32(addr)), "r"(v), "r"((unsigned)p) : "memory");
+}
+
+// one pass: INTERIOR = the 10 x 14 input window lies inside the image (no zero-fill predicates)
+template <int C, bool INTERIOR>
+__device__ __forceinline__ void dw_pass(const float* __restrict__ Xn, const float2 (&w)[49], float2 b, uint32_t ring,
+                                        const float2* ringp, unsigned* pixmax, uint8_t* img, float* rinv_unit, int py0, int px0,
+                                        int ty, int tx, int H, int W, int lane) {
+    const int y0 = ty * SH_TH + py0 - 3, x0 = tx * SH_TW + px0 - 3;
+    // src-size 0 = zero fill without touching the (possibly out-of-image) source address
+    auto issue_row = [&](int r) {
+        const int gy = y0 + r;
+        const uint32_t dst = ring + (uint32_t)((r % DW_RING) * DW_IN_W * C * 4);
+        const float* rowp = Xn + ((long long)gy * W + x0) * C;
+        const bool rowok = INTERIOR || (gy >= 0 && gy < H);
 #pragma unroll
-    for (int t = 0; t < 49; ++t) w[t] = __ldg(dwW + t * C + c);
-    const float b = __ldg(dwB + c);
-    constexpr size_t UNIT_BYTES = (size_t)(C / 64) * 2 * SH_CHUNK;
-    // this thread's 32-bit slot inside a 128-byte row: even lanes store the hi halves of channels (c, c+1),
-    // odd lanes the lo halves of (c-1, c)
-    uint8_t* img = Aimg + (size_t)unit * UNIT_BYTES + (size_t)((c >> 6) * 2 + (lane & 1)) * SH_CHUNK + (size_t)((c & 6) * 2);
-    const int chunk = (c & 63) >> 3;
-    for (int i = c; i < SH_UNIT; i += C) pixmax[i] = 0;
-    __syncthreads();
-    const float* Xn = X + (size_t)n * H * W * C + c;
-#pragma unroll 1
-    for (int s = 0; s < 2; ++s) {
-        float acc[4][16];
+        for (int j = 0; j < DW_IN_W; ++j) {
+            const bool ok = INTERIOR || (rowok && (unsigned)(x0 + j) < (unsigned)W);
+            cp_async8(dst + (uint32_t)(j * C * 4), rowp + j * C, ok ? 8u : 0u);
+        }
+        cp_async_commit();
+    };
+    float2 acc[DW_PH][DW_PW];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < DW_PH; ++i)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
-        const int y0 = ty * SH_TH + s * 4 - 3, x0 = tx * SH_TW - 3;
+        for (int j = 0; j < DW_PW; ++j) acc[i][j] = make_float2(0.f, 0.f);
+    issue_row(0); issue_row(1); issue_row(2);
 #pragma unroll
-        for (int iy = 0; iy < 10; ++iy) {
-            const int gy = y0 + iy;
-            const bool rowok = gy >= 0 && gy < H;
-            float in[22];
+    for (int iy = 0; iy < DW_IN_H; ++iy) {
+        if (iy + 3 < DW_IN_H) issue_row(iy + 3); else cp_async_commit();     // uniform group counting
+        cp_async_wait<3>();                                                     // row iy has landed
+        float2 in[DW_IN_W];
 #pragma unroll
-            for (int j = 0; j < 22; ++j) {
-                const int gx = x0 + j;
-                in[j] = (rowok && gx >= 0 && gx < W) ? __ldg(Xn + ((size_t)gy * W + gx) * C) : 0.f;
-            }
+        for (int j = 0; j < DW_IN_W; ++j) in[j] = ringp[((iy % DW_RING) * DW_IN_W + j) * (C / 2)];
+        // ox innermost: consecutive FFMA2s hit different accumulators
 #pragma unroll
-            for (int oy = 0; oy < 4; ++oy) {
+        for (int dx = 0; dx < 7; ++dx)
+#pragma unroll
+            for (int oy = 0; oy < DW_PH; ++oy) {
                 const int dy = iy - oy;
                 if (dy >= 0 && dy < 7) {
 #pragma unroll
-                    for (int ox = 0; ox < 16; ++ox)
-#pragma unroll
-                        for (int dx = 0; dx < 7; ++dx) acc[oy][ox] = fmaf(w[dy * 7 + dx], in[ox + dx], acc[oy][ox]);
+                    for (int ox = 0; ox < DW_PW; ++ox) acc[oy][ox] = __ffma2_rn(w[dy * 7 + dx], in[ox + dx], acc[oy][ox]);
                 }
             }
+    }
+    // folded bias + ReLU; the pixel's maximum over all channels picks its scale
+#pragma unroll
+    for (int oy = 0; oy < DW_PH; ++oy) {
+        const bool yok = INTERIOR || ty * SH_TH + py0 + oy < H;
+#pragma unroll
+        for (int ox = 0; ox < DW_PW; ++ox) {
+            const bool ok = INTERIOR || (yok && tx * SH_TW + px0 + ox < W);
+            float2 v = __fadd2_rn(acc[oy][ox], b);
+            v.x = ok ? fmaxf(v.x, 0.f) : 0.f; v.y = ok ? fmaxf(v.y, 0.f) : 0.f;
+            acc[oy][ox] = v;
+            const unsigned m = __reduce_max_sync(0xffffffffu, max(__float_as_uint(v.x), __float_as_uint(v.y)));
+            red_max_shared_if(&pixmax[(py0 + oy) * SH_TW + px0 + ox], m, lane == 0);
         }
-        // folded bias + ReLU; the pixel's maximum over all channels picks its scale
+    }
+    __syncthreads();
 #pragma unroll
-        for (int oy = 0; oy < 4; ++oy) {
-            const bool yok = ty * SH_TH + s * 4 + oy < H;
+    for (int oy = 0; oy < DW_PH; ++oy) {
 #pragma unroll
-            for (int ox = 0; ox < 16; ++ox) {
-                const float v = (yok && tx * SH_TW + ox < W) ? fmaxf(acc[oy][ox] + b, 0.f) : 0.f;
-                acc[oy][ox] = v;
-                const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(v));
-                if (lane == 0 && m) atomicMax(&pixmax[(s * 4 + oy) * 16 + ox], m);
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int oy = 0; oy < 4; ++oy) {
-#pragma unroll
-            for (int ox = 0; ox < 16; ++ox) {
-                const int row = (s * 4 + oy) * 16 + ox;
-                const unsigned se = sh_scale_exp(pixmax[row]);
-                const float x = acc[oy][ox] * __uint_as_float(se << 23);
-                const __half hi = __float2half_rn(x);
-                const __half lo = __float2half_rn(x - __half2float(hi));
-                const unsigned hb = __half_as_ushort(hi), lb = __half_as_ushort(lo);
-                const unsigned oh = __shfl_xor_sync(0xffffffffu, hb, 1), ol = __shfl_xor_sync(0xffffffffu, lb, 1);
-                const unsigned word = (lane & 1) ? (ol | (lb << 16)) : (hb | (oh << 16));
-                *reinterpret_cast<uint32_t*>(img + (size_t)(row >> 3) * 1024 + (size_t)(row & 7) * 128 + (size_t)((chunk ^ (row & 7)) << 4)) = word;
-                if (c == 0) rinv[(size_t)unit * SH_UNIT + row] = __uint_as_float((254u - se) << 23);
-            }
+        for (int ox = 0; ox < DW_PW; ++ox) {
+            const int row = (py0 + oy) * SH_TW + px0 + ox;
+            const unsigned se = sh_scale_exp(pixmax[row]);
+            const float sc = __uint_as_float(se << 23);
+            const float2 x = make_float2(acc[oy][ox].x * sc, acc[oy][ox].y * sc);
+            const __half2 hi = __float22half2_rn(x);
+            const float2 hf = __half22float2(hi);
+            const __half2 lo = __float22half2_rn(make_float2(x.x - hf.x, x.y - hf.y));
+            uint8_t* dst = img + (size_t)(row >> 3) * 1024 + (size_t)(row & 7) * 128 + (size_t)((((lane >> 2) ^ (row & 7)) << 4));
+            *reinterpret_cast<__half2*>(dst) = hi;
+            *reinterpret_cast<__half2*>(dst + SH_CHUNK) = lo;
+            if (threadIdx.x == 0) rinv_unit[row] = __uint_as_float((254u - se) << 23);
         }
     }
 }
+
+template <int C>
+__global__ void __launch_bounds__(C / 2, 2)
+sh_dw_kernel(const float* __restrict__ X, const float* __restrict__ dwW, const float* __restrict__ dwB,
+             uint8_t* __restrict__ Aimg, float* __restrict__ rinv, int H, int W, int TX, int TY) {
+    pdl_enter();
+    extern __shared__ float dw_ring[];                       // [DW_RING][DW_IN_W][C]
+    __shared__ unsigned pixmax[SH_UNIT];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5; // channels 2t, 2t+1; warp = k-block
+    const int unit = blockIdx.x;
+    const int tx = unit % TX, ty = (unit / TX) % TY, n = unit / (TX * TY);
+    float2 w[49];
+#pragma unroll
+    for (int i = 0; i < 49; ++i) w[i] = __ldg(reinterpret_cast<const float2*>(dwW + i * C) + t);
+    const float2 b = __ldg(reinterpret_cast<const float2*>(dwB) + t);
+    constexpr size_t UNIT_BYTES = (size_t)(C / 64) * 2 * SH_CHUNK;
+    uint8_t* img = Aimg + (size_t)unit * UNIT_BYTES + (size_t)(warp * 2) * SH_CHUNK + (size_t)((lane & 3) * 4);
+    for (int i = t; i < SH_UNIT; i += C / 2) pixmax[i] = 0;
+    __syncthreads();
+    const float* Xn = X + (size_t)n * H * W * C + 2 * t;
+    const uint32_t ring = smem_u32(dw_ring) + (uint32_t)t * 8;
+    const float2* ringp = reinterpret_cast<const float2*>(dw_ring) + t;
+    float* rinv_unit = rinv + (size_t)unit * SH_UNIT;
+    const bool tile_interior = ty * SH_TH - 3 >= 0 && ty * SH_TH + SH_TH + 3 <= H && tx * SH_TW - 3 >= 0 && tx * SH_TW + SH_TW + 3 <= W;
+#pragma unroll 1
+    for (int pass = 0; pass < (SH_TH / DW_PH) * (SH_TW / DW_PW); ++pass) {
+        const int py0 = (pass >> 1) * DW_PH, px0 = (pass & 1) * DW_PW;      // pass origin inside the tile
+        if (tile_interior) dw_pass<C, true>(Xn, w, b, ring, ringp, pixmax, img, rinv_unit, py0, px0, ty, tx, H, W, lane);
+        else dw_pass<C, false>(Xn, w, b, ring, ringp, pixmax, img, rinv_unit, py0, px0, ty, tx, H, W, lane);
+    }
+}
+template <int C> constexpr size_t dw_smem_bytes() { return (size_t)DW_RING * DW_IN_W * C * 4; }
 
 // ---------------------------------------------------------------------------------------------- 1x1 conv GEMM
 constexpr int PW_STAGES = 2;
@@ -235,7 +287,8 @@ constexpr int PW_B_BYTES = 4 * SH_CHUNK;                  // hi | lo of one k-bl
 constexpr int PW_STAGE_BYTES = PW_A_BYTES + PW_B_BYTES;   // 96 KB
 constexpr int PW_SMEM_TAB = PW_STAGES * PW_STAGE_BYTES;   // cinv[256] | bias2[256] | w5[256]
 constexpr int PW_SMEM_BAR = PW_SMEM_TAB + 3 * SH_MID * 4;
-constexpr int PW_SMEM_TOTAL = PW_SMEM_BAR + 128 + 1024;
+constexpr int PW_SMEM_EPI = PW_SMEM_BAR + 128;               // 8 warps x 2 KB transposition buffers (NHWC stores)
+constexpr int PW_SMEM_TOTAL = PW_SMEM_EPI + 8 * 2048 + 1024;
 constexpr int PW_EPI_WARPS = 8;
 constexpr int PW_THREADS = 32 * (2 + PW_EPI_WARPS);
 enum { PW_RELU_NHWC = 0, PW_FINAL = 1 };
@@ -337,6 +390,7 @@ sh_pw_kernel(const uint8_t* __restrict__ Aimg, const float* __restrict__ rinv, c
         const float4* bv4 = reinterpret_cast<const float4*>(tab + SH_MID + half * 128);
         const float4* wv4 = reinterpret_cast<const float4*>(tab + 2 * SH_MID + half * 128);
         const float bias5 = (MODE == PW_FINAL && half == 0) ? __ldg(b5) : 0.f;
+        uint8_t* wbuf = smem + PW_SMEM_EPI + (warp - 2) * 2048;
         PwRing acc;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const int tx = unit % TX, ty = (unit / TX) % TY, n = unit / (TX * TY);
@@ -349,25 +403,50 @@ sh_pw_kernel(const uint8_t* __restrict__ Aimg, const float* __restrict__ rinv, c
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * SH_MID + half * 128;
             float dot = bias5;
             uint32_t r[2][32];
+            // NHWC stores: a thread owns one pixel row of the accumulator, so direct stores would touch 32 cache lines
+            // per instruction (measured: the epilogue, not the MMAs, bound the kernel).  16-column pieces go through a
+            // per-warp 2 KB buffer (XOR-swizzled, conflict free) and leave as 8 pixels x 64 contiguous bytes per store.
+            int pix_it[4]; bool ok_it[4];
+            if (MODE == PW_RELU_NHWC) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    pix_it[it] = __shfl_sync(0xffffffffu, (int)pix, it * 8 + (lane >> 2));
+                    ok_it[it] = __shfl_sync(0xffffffffu, (int)valid, it * 8 + (lane >> 2)) != 0;
+                }
+            }
             tmem_ld32(taddr, r[0]);
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 tmem_ld_wait_dep(r[ch & 1]);
                 if (ch + 1 < 4) tmem_ld32(taddr + (ch + 1) * 32, r[(ch + 1) & 1]);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float4 cv = cv4[ch * 8 + i], bv = bv4[ch * 8 + i];
-                    const uint32_t* q = r[ch & 1] + 4 * i;
-                    float4 v;
-                    v.x = fmaxf(fmaf(__uint_as_float(q[0]) * ri, cv.x, bv.x), 0.f);
-                    v.y = fmaxf(fmaf(__uint_as_float(q[1]) * ri, cv.y, bv.y), 0.f);
-                    v.z = fmaxf(fmaf(__uint_as_float(q[2]) * ri, cv.z, bv.z), 0.f);
-                    v.w = fmaxf(fmaf(__uint_as_float(q[3]) * ri, cv.w, bv.w), 0.f);
+                for (int sub = 0; sub < 2; ++sub) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 cv = cv4[ch * 8 + sub * 4 + i], bv = bv4[ch * 8 + sub * 4 + i];
+                        const uint32_t* q = r[ch & 1] + 16 * sub + 4 * i;
+                        float4 v;
+                        v.x = fmaxf(fmaf(__uint_as_float(q[0]) * ri, cv.x, bv.x), 0.f);
+                        v.y = fmaxf(fmaf(__uint_as_float(q[1]) * ri, cv.y, bv.y), 0.f);
+                        v.z = fmaxf(fmaf(__uint_as_float(q[2]) * ri, cv.z, bv.z), 0.f);
+                        v.w = fmaxf(fmaf(__uint_as_float(q[3]) * ri, cv.w, bv.w), 0.f);
+                        if (MODE == PW_RELU_NHWC) {
+                            *reinterpret_cast<float4*>(wbuf + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) = v;
+                        } else {
+                            const float4 wv = wv4[ch * 8 + sub * 4 + i];
+                            dot = fmaf(v.x, wv.x, dot); dot = fmaf(v.y, wv.y, dot); dot = fmaf(v.z, wv.z, dot); dot = fmaf(v.w, wv.w, dot);
+                        }
+                    }
                     if (MODE == PW_RELU_NHWC) {
-                        if (valid) *reinterpret_cast<float4*>(out + pix * SH_MID + half * 128 + ch * 32 + i * 4) = v;
-                    } else {
-                        const float4 wv = wv4[ch * 8 + i];
-                        dot = fmaf(v.x, wv.x, dot); dot = fmaf(v.y, wv.y, dot); dot = fmaf(v.z, wv.z, dot); dot = fmaf(v.w, wv.w, dot);
+                        __syncwarp();
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) {
+                            const int rr = it * 8 + (lane >> 2), j = lane & 3;
+                            const float4 v = *reinterpret_cast<const float4*>(wbuf + rr * 64 + ((j ^ ((rr >> 1) & 3)) << 4));
+                            if (ok_it[it])
+                                *reinterpret_cast<float4*>(out + (size_t)pix_it[it] * SH_MID + half * 128 + ch * 32 + sub * 16 + j * 4) = v;
+                        }
+                        __syncwarp();
                     }
                 }
             }
@@ -434,6 +513,8 @@ int launch_seghead_forward(const void* packed, int in_dim, const ShSource& src, 
     if (!attr_done) {
         cudaFuncSetAttribute(sh_pw_kernel<PW_RELU_NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_TOTAL);
         cudaFuncSetAttribute(sh_pw_kernel<PW_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_TOTAL);
+        cudaFuncSetAttribute(sh_dw_kernel<SH_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes<SH_MID>());
+        cudaFuncSetAttribute(sh_dw_kernel<SH_IN_PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes<SH_IN_PAD>());
         attr_done = true;
     }
     const ShLayout L = sh_layout();
@@ -454,8 +535,8 @@ int launch_seghead_forward(const void* packed, int in_dim, const ShSource& src, 
     for (int i = 0; i < SH_LAYERS; ++i) {
         const float* dwW = reinterpret_cast<const float*>(pk + L.l[i].dwW);
         const float* dwB = reinterpret_cast<const float*>(pk + L.l[i].dwB);
-        if (i == 0) launch_k(sh_dw_kernel<SH_IN_PAD>, dim3(units), dim3(SH_IN_PAD), 0, stream, (const float*)x0, dwW, dwB, aimg, rinv, H, W, TX, TY);
-        else launch_k(sh_dw_kernel<SH_MID>, dim3(units), dim3(SH_MID), 0, stream, (const float*)y, dwW, dwB, aimg, rinv, H, W, TX, TY);
+        if (i == 0) launch_k(sh_dw_kernel<SH_IN_PAD>, dim3(units), dim3(SH_IN_PAD / 2), dw_smem_bytes<SH_IN_PAD>(), stream, (const float*)x0, dwW, dwB, aimg, rinv, H, W, TX, TY);
+        else launch_k(sh_dw_kernel<SH_MID>, dim3(units), dim3(SH_MID / 2), dw_smem_bytes<SH_MID>(), stream, (const float*)y, dwW, dwB, aimg, rinv, H, W, TX, TY);
         const float* cinv = reinterpret_cast<const float*>(pk + L.l[i].cinv);
         const float* bias2 = reinterpret_cast<const float*>(pk + L.l[i].bias2);
         const float* w5 = reinterpret_cast<const float*>(pk + L.w5);
