@@ -3,18 +3,28 @@
 // Reference: networks/IntVOS.py:488-525 (_split_separable_conv2d x4 + 1x1 conv), fed by the feature assembly of
 // prop_seghead, IntVOS.py:663-671 (repeat of the embedding per object + cat of global map, local map, previous mask).
 // Inference form: batch norm uses its running statistics (model.eval(), test.py), so every conv+BN pair folds into
-// one affine map at pack time (sh_pack_*).
+// one affine map at pack time (sh_pack_*).  Activations stay in the reference's NCHW layout between layers.
 //
-// Per layer:   x [N,H,W,Cin] --depthwise 7x7 + BN + ReLU--> a --1x1 conv Cin->256 + BN + ReLU--> y [N,H,W,256]
-//   * sh_dw_kernel<C>   fp32 CUDA cores, one thread per channel (NHWC: a warp reads 128 contiguous bytes per pixel),
-//     8x16 pixel tile per CTA = one 128-row GEMM unit, 4x16 register strip x 49 taps per thread.  The result is
-//     written straight as the tensor-core operand: per pixel a power-of-two scale (so the row fills fp16's range),
-//     x*s = hi + lo in fp16, laid out as the 128-byte-swizzled K-major shared-memory image of the unit.
+// Per layer:   x [N,Cin,H,W] --depthwise 7x7 + BN + ReLU--> a --1x1 conv Cin->256 + BN + ReLU--> y [N,256,H,W]
+//   * sh_dw_kernel   fp32 CUDA cores.  A warp owns one channel at a time over an 8x32 pixel tile (two 128-row GEMM
+//     units): each lane computes a 2x4 block of outputs from a 8x10 window read with 128-bit shared-memory loads,
+//     the 49 taps are warp-uniform registers.  The channel's input plane (14x38 with halo) arrives through a
+//     per-warp double buffer filled by cp.async, so the loop over channels is a compact rolled loop with no CTA
+//     barrier.  Eight channels at a time are converted to the tensor-core operand: x*2^e = hi + lo in fp16, written
+//     as 16-byte chunks of the 128-byte-swizzled K-major shared-memory image of the unit.
+//     The scale 2^e is one power of two per layer, derived on the device from a BOUND of the layer's outputs
+//     (sum|w'| * max|input| + max|b'|, the max coming from the previous kernel's epilogue): hi+lo carries 22
+//     significant bits of every element that matters and an absolute error below 2^-39 of the bound for the rest.
 //   * sh_pw_kernel<MODE> persistent tcgen05 GEMM, M = 128 pixels, N = 256 output channels, K = Cin in blocks of 64;
 //     a . w ~= ah.wh + al.wh + ah.wl (three kind::f16 MMAs, fp32 accumulate in TMEM: fp32-grade like the matchers);
 //     operands arrive by plain bulk copies (the images ARE the smem layout); epilogue: un-scale, + bias, ReLU,
-//     -> NHWC fp32 for the next layer, or (last layer) the 256->1 conv as a dot product in registers -> logits.
-// The distance maps enter through sh_assemble_kernel, which replaces the reference's repeat/cat (IntVOS.py:663-670).
+//     -> NCHW fp32 for the next layer (+ its maximum), or (last layer) the 256->1 conv as a dot product in
+//     registers -> logits.
+// The first layer reads the embedding and the two maps where they lie (no repeat/cat, IntVOS.py:663-670).
+//
+// History of the depthwise kernel (profiles/README.md): thread = channel over NHWC with the whole 7x7 window unrolled
+// (298 us per layer; ncu: stall "wait", then "no_instruction": a 40-60 KB straight-line body streams through the
+// 32 KB instruction cache) -> this form (compact body, 16 warps per SM).
 #include "common.cuh"
 #include "umma_ptx.cuh"
 
@@ -22,13 +32,14 @@ namespace manet {
 
 constexpr int SH_MID = 256;              // cfg.MODEL_HEAD_EMBEDDING_DIM (config.py in the reference)
 constexpr int SH_IN_PAD = 128;           // layer-1 channels (MODEL_SEMANTIC_EMBEDDING_DIM + 3 = 103) padded to 2 K blocks
-constexpr int SH_TH = 8, SH_TW = 16;     // pixel tile of one unit
+constexpr int SH_TH = 4, SH_TW = 32;     // pixel tile of one unit (a warp's 32 accumulator rows = one 128-byte run of a channel plane)
 constexpr int SH_UNIT = SH_TH * SH_TW;   // 128 rows = UMMA M
 constexpr int SH_CHUNK = 16384;          // 128 rows x 128 B: one (k-block, part) of a unit
 constexpr int SH_LAYERS = 4;
+constexpr int SH_WROW = 52;              // per channel: 49 taps, bias, 2 pad (13 x 16 bytes)
 
 // ---------------------------------------------------------------------------------------------- packed parameters
-struct ShLayerOff { size_t dwW, dwB, Bimg, cinv, bias2; int cin_p; };
+struct ShLayerOff { size_t dwW, bound, Bimg, cinv, bias2; int cin_p; };
 struct ShLayout { ShLayerOff l[SH_LAYERS]; size_t w5, b5, total; };
 
 static ShLayout sh_layout() {
@@ -36,8 +47,8 @@ static ShLayout sh_layout() {
     for (int i = 0; i < SH_LAYERS; ++i) {
         const int cp = i == 0 ? SH_IN_PAD : SH_MID;
         L.l[i].cin_p = cp;
-        L.l[i].dwW = off; off = align_up(off + (size_t)49 * cp * 4, 1024);
-        L.l[i].dwB = off; off = align_up(off + (size_t)cp * 4, 1024);
+        L.l[i].dwW = off; off = align_up(off + (size_t)SH_WROW * cp * 4, 1024);
+        L.l[i].bound = off; off = align_up(off + 8, 1024);            // max_c sum_t |w'|, max_c |b'| as float bits
         L.l[i].Bimg = off; off = align_up(off + (size_t)(cp / 64) * 4 * SH_CHUNK, 1024);
         L.l[i].cinv = off; off = align_up(off + SH_MID * 4, 1024);
         L.l[i].bias2 = off; off = align_up(off + SH_MID * 4, 1024);
@@ -52,20 +63,32 @@ static ShLayout sh_layout() {
 // [2^10, 2^11)), as raw exponent arithmetic; the clamps keep both the scale and its inverse normal numbers
 __device__ __forceinline__ unsigned sh_scale_exp(unsigned bits) { int eb = (int)(bits >> 23) & 0xff; return (unsigned)max(1, min(264 - eb, 253)); }
 
-// depthwise conv + BN1 folded: w'[t][c] = w[c][t] * g/sqrt(var+eps), b' = (cb - mean) * g/sqrt(var+eps) + beta
+// Layer scale (biased exponent of 2^e): bound = wsum * max|input| + bmax  <  2^(eb-126)  =>  bound * 2^e < 2^14,
+// a factor four below fp16's largest finite value.  Both kernels of a layer evaluate this from the same three numbers.
+__device__ __forceinline__ unsigned sh_layer_scale_exp(const unsigned* __restrict__ amax_in, const unsigned* __restrict__ bound) {
+    const float b = fmaf(__uint_as_float(__ldg(bound)), __uint_as_float(__ldg(amax_in)), __uint_as_float(__ldg(bound + 1)));
+    const int eb = (int)(__float_as_uint(b) >> 23) & 0xff;
+    return (unsigned)max(1, min(267 - eb, 253));
+}
+
+// depthwise conv + BN1 folded: w'[c][t] = w[c][t] * g/sqrt(var+eps), b' = (cb - mean) * g/sqrt(var+eps) + beta
 __global__ void sh_pack_dw_kernel(const float* __restrict__ w, const float* __restrict__ cb, const float* __restrict__ g,
                                   const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ var,
-                                  float eps, int C, int Cp, float* __restrict__ dwW, float* __restrict__ dwB) {
+                                  float eps, int C, int Cp, float* __restrict__ dwW, unsigned* __restrict__ bound) {
     pdl_enter();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= Cp) return;
+    float* row = dwW + (size_t)c * SH_WROW;
     if (c < C) {
         const float s = g[c] / sqrtf(var[c] + eps);
-        for (int t = 0; t < 49; ++t) dwW[t * Cp + c] = w[c * 49 + t] * s;
-        dwB[c] = (cb[c] - mean[c]) * s + beta[c];
+        float sum = 0.f;
+        for (int t = 0; t < 49; ++t) { const float v = w[c * 49 + t] * s; row[t] = v; sum += fabsf(v); }
+        const float b = (cb[c] - mean[c]) * s + beta[c];
+        row[49] = b; row[50] = 0.f; row[51] = 0.f;
+        atomicMax(bound, __float_as_uint(sum * 1.0001f));
+        atomicMax(bound + 1, __float_as_uint(fabsf(b)));
     } else {
-        for (int t = 0; t < 49; ++t) dwW[t * Cp + c] = 0.f;
-        dwB[c] = 0.f;
+        for (int t = 0; t < SH_WROW; ++t) row[t] = 0.f;
     }
 }
 
@@ -108,177 +131,232 @@ __global__ void sh_pack_final_kernel(const float* __restrict__ w, const float* _
     if (k == 0) b5[0] = b[0];
 }
 
-// ---------------------------------------------------------------------------------------------- feature assembly
-// x0[n][y][x][c] (NHWC, 128 channels, zero padded) from either the [N,Cin,H,W] tensor the reference head receives
-// (any strides) or directly from its parts (IntVOS.py:663-670): c < C0 the current-frame embedding (shared by all
-// objects), C0 the global map, C0+1 the local map, C0+2 the previous-frame mask (label == id).
+// ---------------------------------------------------------------------------------------------- layer-1 input
+// Channels c < c0 come from a strided tensor (the [N,Cin,H,W] input of the reference head, or the current-frame
+// embedding shared by all objects: sn = 0); in "parts" mode channels c0, c0+1, c0+2 (global map, local map, previous
+// mask; IntVOS.py:663-670) come from the planar `extras` [N,3,H,W] written by sh_extras_kernel.
 struct ShSource {
-    const float* x; int64_t sn, sc, sh, sw;          // generic tensor (parts mode: the embedding, sn = 0)
-    const float* gmap; const float* lmap;            // [H,W,N] fp32 (the matchers' [1,H,W,N,1] outputs), or null
-    const int32_t* prev; const int32_t* ids;         // [H,W] int32, [N] int32
-    int c0;                                          // channels taken from x
+    const float* x; int64_t sn, sc, sh, sw;
+    int c0;
+    const float* extras;
 };
 
+// max |x| over a strided [n,c,h,w] tensor -> atomicMax on float bits (one atomic per block: thousands of atomics on
+// one address serialise in L2 -- the first version spent 20 of its 26 us there)
 __global__ void __launch_bounds__(256)
-sh_assemble_kernel(ShSource s, int in_dim, int N, int H, int W, float* __restrict__ x0) {
+sh_absmax_kernel(const float* __restrict__ x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, int N, int C, int H, int W,
+                 unsigned* __restrict__ amax) {
     pdl_enter();
-    __shared__ float tile[SH_IN_PAD][33];
-    const int xb = blockIdx.x * 32, y = blockIdx.y, n = blockIdx.z;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int gx = xb + lane;
-    for (int c = warp; c < SH_IN_PAD; c += 8) {
-        float v = 0.f;
-        if (gx < W && c < in_dim) {
-            if (c < s.c0) v = __ldg(s.x + n * s.sn + c * s.sc + y * s.sh + gx * s.sw);
-            else if (c == s.c0) v = __ldg(s.gmap + ((size_t)y * W + gx) * N + n);
-            else if (c == s.c0 + 1) v = __ldg(s.lmap + ((size_t)y * W + gx) * N + n);
-            else v = (__ldg(s.prev + (size_t)y * W + gx) == __ldg(s.ids + n)) ? 1.f : 0.f;
-        }
-        tile[c][lane] = v;
-    }
+    __shared__ unsigned smax;
+    if (threadIdx.x == 0) smax = 0;
     __syncthreads();
-    for (int p = warp; p < 32; p += 8) {
-        if (xb + p >= W) break;
-        float* dst = x0 + (((size_t)n * H + y) * W + xb + p) * SH_IN_PAD;
-#pragma unroll
-        for (int k = 0; k < SH_IN_PAD / 32; ++k) dst[lane + 32 * k] = tile[lane + 32 * k][p];
+    const int rows = N * C * H, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float m = 0.f;
+    for (int r = blockIdx.x * 8 + warp; r < rows; r += gridDim.x * 8) {          // a warp per row, 8 rows in flight per block
+        const int y = r % H, c = (r / H) % C, n = r / (H * C);
+        const float* p = x + n * sn + c * sc + y * sh;
+        for (int i = lane; i < W; i += 32) m = fmaxf(m, fabsf(__ldg(p + i * sw)));
     }
+    const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+    if (lane == 0 && wm) atomicMax(&smax, wm);
+    __syncthreads();
+    if (threadIdx.x == 0 && smax) atomicMax(amax, smax);
+}
+
+// extras[n][0] = global map, [n][1] = local map (both given as [H,W,N]), [n][2] = (prev == ids[n]); also their max
+__global__ void __launch_bounds__(256)
+sh_extras_kernel(const float* __restrict__ gmap, const float* __restrict__ lmap, const int32_t* __restrict__ prev,
+                 const int32_t* __restrict__ ids, int N, int HW, float* __restrict__ extras, unsigned* __restrict__ amax) {
+    pdl_enter();
+    float m = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        const int pl = __ldg(prev + i);
+        for (int n = 0; n < N; ++n) {
+            const float g = __ldg(gmap + (size_t)i * N + n), l = __ldg(lmap + (size_t)i * N + n);
+            const float k = (pl == __ldg(ids + n)) ? 1.f : 0.f;
+            float* e = extras + (size_t)n * 3 * HW + i;
+            e[0] = g; e[HW] = l; e[2 * (size_t)HW] = k;
+            m = fmaxf(m, fmaxf(fmaxf(fabsf(g), fabsf(l)), k));
+        }
+    }
+    const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+    if ((threadIdx.x & 31) == 0 && wm) atomicMax(amax, wm);      // <= 8 per block, a few hundred in all
 }
 
 // ---------------------------------------------------------------------------------------------- depthwise 7x7
-// One thread per channel PAIR (sm_100 packed fp32: one FFMA2 does both channels; inputs, weights and results are
-// natural float2 in NHWC), 8x16 pixel tile per CTA, processed as four passes of 4 rows x 8 columns (32 float2
-// accumulators).  The input rows of a pass (14 pixels x C channels) travel through a 4-deep shared-memory ring
-// filled by 8-byte cp.async copies: every thread copies and later reads only ITS OWN slots, so the ring needs no
-// CTA barrier -- it is a per-thread asynchronous prefetch, three rows ahead.  A warp covers 64 channels = one
-// 128-byte row of a k-block of the operand image, so its hi (and lo) stores of a pixel are one full line.
-// History (ncu, profiles/): one channel per thread, 64 accumulators at 255 registers (8 warps per SM): 314 us per
-// layer, issue slots 43 % busy, top stall "wait" (fixed-latency FFMA chains, 2 warps per scheduler); 32 accumulators
-// under a 128-register cap (16 warps per SM): 217 us, 59 % of the issued instructions are not FFMAs (copies, loads,
-// predicates, the per-pixel scale/split/store) -> channel pairs halve everything but the FMA pipe time.
-constexpr int DW_RING = 4;
-constexpr int DW_PW = 8, DW_PH = 4;            // pass: 4 rows x 8 columns of output pixels
-constexpr int DW_IN_W = DW_PW + 6;             // input pixels per row of a pass
-constexpr int DW_IN_H = DW_PH + 6;             // input rows of a pass
+// Work item = (16x32 pixel tile, chunk of 8 channels), pulled by WARPS from an atomic counter (warps are fully
+// independent: private double-buffered input plane, private 8-plane output block).  A lane computes a 4x4 block of
+// outputs from a 10x10 window (128-bit shared-memory loads): 6.25 loaded floats per output.  With 2x4 blocks
+// (10 per output) the kernel was shared-memory bound: 130 wavefronts against 98 FMA-issue cycles per channel.
+constexpr int DW_TH = 16, DW_TW = 32;              // warp tile = four units stacked vertically
+constexpr int DW_IH = DW_TH + 6, DW_IW = DW_TW + 6;
+constexpr int DW_PITCH = 40;                       // floats per staged row (16-byte aligned 128-bit loads)
+constexpr int DW_PLANE = DW_IH * DW_PITCH;         // 880 floats per channel plane
+constexpr int DW_WARPS = 4;
+constexpr int DW_WARP_FLOATS = 2 * DW_PLANE + 8 * DW_TH * DW_TW + 2 * 64;   // double-buffered input plane, 8 output planes, double-buffered taps
+constexpr int DW_SMEM = DW_WARPS * DW_WARP_FLOATS * 4;              // 94,720 B: two CTAs per SM
 
-__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void red_max_shared_if(unsigned* addr, unsigned v, bool p) {      // predicated, no branch
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q red.shared.max.u32 [%0], %1;\n\t}" ::"r"(smem_u32(addr)), "r"(v), "r"((unsigned)p) : "memory");
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
-// one pass: INTERIOR = the 10 x 14 input window lies inside the image (no zero-fill predicates)
-template <int C, bool INTERIOR>
-__device__ __forceinline__ void dw_pass(const float* __restrict__ Xn, const float2 (&w)[49], float2 b, uint32_t ring,
-                                        const float2* ringp, unsigned* pixmax, uint8_t* img, float* rinv_unit, int py0, int px0,
-                                        int ty, int tx, int H, int W, int lane) {
-    const int y0 = ty * SH_TH + py0 - 3, x0 = tx * SH_TW + px0 - 3;
-    // src-size 0 = zero fill without touching the (possibly out-of-image) source address
-    auto issue_row = [&](int r) {
-        const int gy = y0 + r;
-        const uint32_t dst = ring + (uint32_t)((r % DW_RING) * DW_IN_W * C * 4);
-        const float* rowp = Xn + ((long long)gy * W + x0) * C;
-        const bool rowok = INTERIOR || (gy >= 0 && gy < H);
+template <int CP>
+__global__ void __launch_bounds__(DW_WARPS * 32, 2)
+sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned* __restrict__ amax_in,
+             const unsigned* __restrict__ bound, uint8_t* __restrict__ Aimg, unsigned* __restrict__ counter,
+             int N, int H, int W, int TX2, int TY16) {
+    pdl_enter();
+    extern __shared__ __align__(16) float dw_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* inbuf = dw_smem + warp * DW_WARP_FLOATS;
+    float* outbuf = inbuf + 2 * DW_PLANE;
+    const float* wbuf = outbuf + 8 * DW_TH * DW_TW;
+    const uint32_t in_s = smem_u32(inbuf), w_s = smem_u32(wbuf);
+    const int by = lane >> 3, bx = lane & 7;                       // this lane's 4x4 output block
+    const float scale = __uint_as_float(sh_layer_scale_exp(amax_in, bound) << 23);
+    constexpr size_t UNIT_BYTES = (size_t)(CP / 64) * 2 * SH_CHUNK;
+    constexpr int CHUNKS = CP / 8;
+    const int n_items = N * TY16 * TX2 * CHUNKS;
+
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = (int)atomicAdd(counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        // chunk fastest: the warps of an SM share a tile's input neighbourhood in L1/L2
+        const int cid = item % CHUNKS, tile = item / CHUNKS;
+        const int tx2 = tile % TX2, ty = (tile / TX2) % TY16, n = tile / (TX2 * TY16);
+        const int y0 = ty * DW_TH - 3, x0 = tx2 * DW_TW - 3;
+        uint8_t* img_tile = Aimg + (size_t)(((size_t)n * TY16 + ty) * 4 * TX2 + tx2) * UNIT_BYTES;   // unit (n, 4*ty + uy, tx2)
+
+        // stage channel c: its 22 x 38 input window (zero outside the image / beyond the real channels: src-size 0 =
+        // zero fill) and its 49 taps + bias.  One pointer walks the rows; `interior` tiles skip the predicates.
+        const bool interior = y0 >= 0 && y0 + DW_IH <= H && x0 >= 0 && x0 + DW_IW <= W;
+        const unsigned rlo = (unsigned)max(0, -y0), rcnt = (unsigned)max(0, min(DW_IH, H - y0) - (int)rlo);
+        auto issue = [&](int c, int buf) {
+            const float* base; int64_t sy, sx;
+            if (c < src.c0) { base = src.x + n * src.sn + c * src.sc; sy = src.sh; sx = src.sw; }
+            else { base = src.extras + ((size_t)n * 3 + (c - src.c0)) * H * W; sy = W; sx = 1; }
+            const float* p0 = base + (int64_t)y0 * sy + (int64_t)(x0 + lane) * sx;
+            const float* p1 = p0 + 32 * sx;
+            const uint32_t dst = in_s + (uint32_t)(buf * DW_PLANE + lane) * 4;
+            if (lane < SH_WROW / 4) cp_async16(w_s + (uint32_t)(buf * 64 + lane * 4) * 4, dwW + (size_t)c * SH_WROW + lane * 4);
+            if (interior && c < C) {
 #pragma unroll
-        for (int j = 0; j < DW_IN_W; ++j) {
-            const bool ok = INTERIOR || (rowok && (unsigned)(x0 + j) < (unsigned)W);
-            cp_async8(dst + (uint32_t)(j * C * 4), rowp + j * C, ok ? 8u : 0u);
-        }
-        cp_async_commit();
-    };
-    float2 acc[DW_PH][DW_PW];
+                for (int r = 0; r < DW_IH; ++r) {
+                    cp_async4(dst + r * DW_PITCH * 4, p0, 4u);
+                    if (lane < DW_IW - 32) cp_async4(dst + (r * DW_PITCH + 32) * 4, p1, 4u);
+                    p0 += sy; p1 += sy;
+                }
+            } else {
+                const bool cok = c < C;
+                const unsigned sz0 = (cok && (unsigned)(x0 + lane) < (unsigned)W) ? 4u : 0u;
+                const unsigned sz1 = (cok && (unsigned)(x0 + 32 + lane) < (unsigned)W) ? 4u : 0u;
 #pragma unroll
-    for (int i = 0; i < DW_PH; ++i)
-#pragma unroll
-        for (int j = 0; j < DW_PW; ++j) acc[i][j] = make_float2(0.f, 0.f);
-    issue_row(0); issue_row(1); issue_row(2);
-#pragma unroll
-    for (int iy = 0; iy < DW_IN_H; ++iy) {
-        if (iy + 3 < DW_IN_H) issue_row(iy + 3); else cp_async_commit();     // uniform group counting
-        cp_async_wait<3>();                                                     // row iy has landed
-        float2 in[DW_IN_W];
-#pragma unroll
-        for (int j = 0; j < DW_IN_W; ++j) in[j] = ringp[((iy % DW_RING) * DW_IN_W + j) * (C / 2)];
-        // ox innermost: consecutive FFMA2s hit different accumulators
-#pragma unroll
-        for (int dx = 0; dx < 7; ++dx)
-#pragma unroll
-            for (int oy = 0; oy < DW_PH; ++oy) {
-                const int dy = iy - oy;
-                if (dy >= 0 && dy < 7) {
-#pragma unroll
-                    for (int ox = 0; ox < DW_PW; ++ox) acc[oy][ox] = __ffma2_rn(w[dy * 7 + dx], in[ox + dx], acc[oy][ox]);
+                for (int r = 0; r < DW_IH; ++r) {
+                    const bool rok = (unsigned)r - rlo < rcnt;
+                    cp_async4(dst + r * DW_PITCH * 4, p0, rok ? sz0 : 0u);
+                    if (lane < DW_IW - 32) cp_async4(dst + (r * DW_PITCH + 32) * 4, p1, rok ? sz1 : 0u);
+                    p0 += sy; p1 += sy;
                 }
             }
-    }
-    // folded bias + ReLU; the pixel's maximum over all channels picks its scale
-#pragma unroll
-    for (int oy = 0; oy < DW_PH; ++oy) {
-        const bool yok = INTERIOR || ty * SH_TH + py0 + oy < H;
-#pragma unroll
-        for (int ox = 0; ox < DW_PW; ++ox) {
-            const bool ok = INTERIOR || (yok && tx * SH_TW + px0 + ox < W);
-            float2 v = __fadd2_rn(acc[oy][ox], b);
-            v.x = ok ? fmaxf(v.x, 0.f) : 0.f; v.y = ok ? fmaxf(v.y, 0.f) : 0.f;
-            acc[oy][ox] = v;
-            const unsigned m = __reduce_max_sync(0xffffffffu, max(__float_as_uint(v.x), __float_as_uint(v.y)));
-            red_max_shared_if(&pixmax[(py0 + oy) * SH_TW + px0 + ox], m, lane == 0);
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int oy = 0; oy < DW_PH; ++oy) {
-#pragma unroll
-        for (int ox = 0; ox < DW_PW; ++ox) {
-            const int row = (py0 + oy) * SH_TW + px0 + ox;
-            const unsigned se = sh_scale_exp(pixmax[row]);
-            const float sc = __uint_as_float(se << 23);
-            const float2 x = make_float2(acc[oy][ox].x * sc, acc[oy][ox].y * sc);
-            const __half2 hi = __float22half2_rn(x);
-            const float2 hf = __half22float2(hi);
-            const __half2 lo = __float22half2_rn(make_float2(x.x - hf.x, x.y - hf.y));
-            uint8_t* dst = img + (size_t)(row >> 3) * 1024 + (size_t)(row & 7) * 128 + (size_t)((((lane >> 2) ^ (row & 7)) << 4));
-            *reinterpret_cast<__half2*>(dst) = hi;
-            *reinterpret_cast<__half2*>(dst + SH_CHUNK) = lo;
-            if (threadIdx.x == 0) rinv_unit[row] = __uint_as_float((254u - se) << 23);
-        }
-    }
-}
+            cp_async_commit();
+        };
 
-template <int C>
-__global__ void __launch_bounds__(C / 2, 2)
-sh_dw_kernel(const float* __restrict__ X, const float* __restrict__ dwW, const float* __restrict__ dwB,
-             uint8_t* __restrict__ Aimg, float* __restrict__ rinv, int H, int W, int TX, int TY) {
-    pdl_enter();
-    extern __shared__ float dw_ring[];                       // [DW_RING][DW_IN_W][C]
-    __shared__ unsigned pixmax[SH_UNIT];
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5; // channels 2t, 2t+1; warp = k-block
-    const int unit = blockIdx.x;
-    const int tx = unit % TX, ty = (unit / TX) % TY, n = unit / (TX * TY);
-    float2 w[49];
-#pragma unroll
-    for (int i = 0; i < 49; ++i) w[i] = __ldg(reinterpret_cast<const float2*>(dwW + i * C) + t);
-    const float2 b = __ldg(reinterpret_cast<const float2*>(dwB) + t);
-    constexpr size_t UNIT_BYTES = (size_t)(C / 64) * 2 * SH_CHUNK;
-    uint8_t* img = Aimg + (size_t)unit * UNIT_BYTES + (size_t)(warp * 2) * SH_CHUNK + (size_t)((lane & 3) * 4);
-    for (int i = t; i < SH_UNIT; i += C / 2) pixmax[i] = 0;
-    __syncthreads();
-    const float* Xn = X + (size_t)n * H * W * C + 2 * t;
-    const uint32_t ring = smem_u32(dw_ring) + (uint32_t)t * 8;
-    const float2* ringp = reinterpret_cast<const float2*>(dw_ring) + t;
-    float* rinv_unit = rinv + (size_t)unit * SH_UNIT;
-    const bool tile_interior = ty * SH_TH - 3 >= 0 && ty * SH_TH + SH_TH + 3 <= H && tx * SH_TW - 3 >= 0 && tx * SH_TW + SH_TW + 3 <= W;
+        if (cid * 8 >= C) {
+            // padding chunk (layer 1: channels 104..127): zeros
 #pragma unroll 1
-    for (int pass = 0; pass < (SH_TH / DW_PH) * (SH_TW / DW_PW); ++pass) {
-        const int py0 = (pass >> 1) * DW_PH, px0 = (pass & 1) * DW_PW;      // pass origin inside the tile
-        if (tile_interior) dw_pass<C, true>(Xn, w, b, ring, ringp, pixmax, img, rinv_unit, py0, px0, ty, tx, H, W, lane);
-        else dw_pass<C, false>(Xn, w, b, ring, ringp, pixmax, img, rinv_unit, py0, px0, ty, tx, H, W, lane);
+            for (int j = 0; j < (DW_TH * DW_TW) / 32; ++j) {
+                const int px = lane + 32 * j, y = px >> 5, row = (y & 3) * SH_TW + (px & 31);
+                uint8_t* dst = img_tile + (size_t)(y >> 2) * TX2 * UNIT_BYTES + (size_t)((cid >> 3) * 2) * SH_CHUNK + (size_t)(row >> 3) * 1024 +
+                               (size_t)(row & 7) * 128 + (size_t)(((cid & 7) ^ (row & 7)) << 4);
+                *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(dst + SH_CHUNK) = make_uint4(0, 0, 0, 0);
+            }
+            continue;
+        }
+
+        issue(cid * 8, 0);
+#pragma unroll 1
+        for (int k = 0; k < 8; ++k) {
+            const int c = cid * 8 + k, buf = k & 1;
+            if (k + 1 < 8) issue(c + 1, buf ^ 1); else cp_async_commit();
+            cp_async_wait<1>();
+            __syncwarp();
+            float w[SH_WROW];
+            {
+                const float4* wp = reinterpret_cast<const float4*>(wbuf + buf * 64);
+#pragma unroll
+                for (int q = 0; q < SH_WROW / 4; ++q) {
+                    const float4 v = wp[q];
+                    w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+                }
+            }
+            const float* pl = inbuf + buf * DW_PLANE + (4 * by) * DW_PITCH + 4 * bx;
+            float acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll
+            for (int iy = 0; iy < 10; ++iy) {
+                const float4 a = *reinterpret_cast<const float4*>(pl + iy * DW_PITCH);
+                const float4 b = *reinterpret_cast<const float4*>(pl + iy * DW_PITCH + 4);
+                const float2 d = *reinterpret_cast<const float2*>(pl + iy * DW_PITCH + 8);
+                const float in[10] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y};
+#pragma unroll
+                for (int dx = 0; dx < 7; ++dx)
+#pragma unroll
+                    for (int oy = 0; oy < 4; ++oy) {
+                        const int dy = iy - oy;
+                        if (dy >= 0 && dy < 7) {
+#pragma unroll
+                            for (int ox = 0; ox < 4; ++ox) acc[oy][ox] = fmaf(w[dy * 7 + dx], in[ox + dx], acc[oy][ox]);
+                        }
+                    }
+            }
+            // folded bias + ReLU -> this channel's plane of the 8-channel output block
+#pragma unroll
+            for (int oy = 0; oy < 4; ++oy) {
+                float4 v;
+                v.x = fmaxf(acc[oy][0] + w[49], 0.f); v.y = fmaxf(acc[oy][1] + w[49], 0.f);
+                v.z = fmaxf(acc[oy][2] + w[49], 0.f); v.w = fmaxf(acc[oy][3] + w[49], 0.f);
+                *reinterpret_cast<float4*>(outbuf + k * (DW_TH * DW_TW) + (4 * by + oy) * DW_TW + 4 * bx) = v;
+            }
+            __syncwarp();                   // plane reads done before the next prefetch may overwrite; out plane visible
+        }
+        // eight channels complete: scale, split into fp16 hi + lo, one 16-byte chunk per pixel and part
+        {
+            const int kb = cid >> 3, c8 = cid & 7;
+#pragma unroll 2
+            for (int j = 0; j < (DW_TH * DW_TW) / 32; ++j) {
+                const int px = lane + 32 * j, y = px >> 5;
+                const int row = (y & 3) * SH_TW + (px & 31);
+                float f[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) f[q] = outbuf[q * (DW_TH * DW_TW) + px] * scale;
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const __half2 h = __floats2half2_rn(f[2 * q], f[2 * q + 1]);
+                    const float2 hf = __half22float2(h);
+                    const __half2 l = __floats2half2_rn(f[2 * q] - hf.x, f[2 * q + 1] - hf.y);
+                    hi[q] = *reinterpret_cast<const uint32_t*>(&h); lo[q] = *reinterpret_cast<const uint32_t*>(&l);
+                }
+                uint8_t* dst = img_tile + (size_t)(y >> 2) * TX2 * UNIT_BYTES + (size_t)(kb * 2) * SH_CHUNK + (size_t)(row >> 3) * 1024 +
+                               (size_t)(row & 7) * 128 + (size_t)((c8 ^ (row & 7)) << 4);
+                *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(dst + SH_CHUNK) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            __syncwarp();
+        }
     }
 }
-template <int C> constexpr size_t dw_smem_bytes() { return (size_t)DW_RING * DW_IN_W * C * 4; }
 
 // ---------------------------------------------------------------------------------------------- 1x1 conv GEMM
 constexpr int PW_STAGES = 2;
@@ -287,11 +365,10 @@ constexpr int PW_B_BYTES = 4 * SH_CHUNK;                  // hi | lo of one k-bl
 constexpr int PW_STAGE_BYTES = PW_A_BYTES + PW_B_BYTES;   // 96 KB
 constexpr int PW_SMEM_TAB = PW_STAGES * PW_STAGE_BYTES;   // cinv[256] | bias2[256] | w5[256]
 constexpr int PW_SMEM_BAR = PW_SMEM_TAB + 3 * SH_MID * 4;
-constexpr int PW_SMEM_EPI = PW_SMEM_BAR + 128;               // 8 warps x 2 KB transposition buffers (NHWC stores)
-constexpr int PW_SMEM_TOTAL = PW_SMEM_EPI + 8 * 2048 + 1024;
+constexpr int PW_SMEM_TOTAL = PW_SMEM_BAR + 128 + 1024;
 constexpr int PW_EPI_WARPS = 8;
 constexpr int PW_THREADS = 32 * (2 + PW_EPI_WARPS);
-enum { PW_RELU_NHWC = 0, PW_FINAL = 1 };
+enum { PW_RELU_NCHW = 0, PW_FINAL = 1 };
 
 struct PwRing {
     int idx; uint32_t phase;
@@ -301,9 +378,10 @@ struct PwRing {
 
 template <int MODE>
 __global__ void __launch_bounds__(PW_THREADS, 1)
-sh_pw_kernel(const uint8_t* __restrict__ Aimg, const float* __restrict__ rinv, const uint8_t* __restrict__ Bimg,
-             const float* __restrict__ cinv, const float* __restrict__ bias2, const float* __restrict__ w5,
-             const float* __restrict__ b5, float* __restrict__ out, int n_units, int nkb, int H, int W, int TX, int TY) {
+sh_pw_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ amax_in, const unsigned* __restrict__ bound,
+             const uint8_t* __restrict__ Bimg, const float* __restrict__ cinv, const float* __restrict__ bias2,
+             const float* __restrict__ w5, const float* __restrict__ b5, float* __restrict__ out, unsigned* __restrict__ amax_out,
+             int n_units, int nkb, int H, int W, int TX, int TY) {
     pdl_enter();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -341,6 +419,7 @@ sh_pw_kernel(const uint8_t* __restrict__ Aimg, const float* __restrict__ rinv, c
         // ------------------------------------------------ producer: one stage = k-block kb of the unit (A) and of the weights (B)
         PwRing st;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            if (((unit / TX) % TY) * SH_TH >= H) continue;            // unit rows below the image (tile padding): nothing to do
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(empty_b + 8 * st.idx, st.phase ^ 1);
                 const uint32_t fb = full_b + 8 * st.idx;
@@ -359,6 +438,7 @@ sh_pw_kernel(const uint8_t* __restrict__ Aimg, const float* __restrict__ rinv, c
         constexpr uint32_t idesc = idesc_f16(SH_UNIT, SH_MID);
         PwRing st, acc;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            if (((unit / TX) % TY) * SH_TH >= H) continue;
             mbar_wait(tmem_empty + 8 * acc.idx, acc.phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc.idx * SH_MID;
@@ -390,63 +470,45 @@ sh_pw_kernel(const uint8_t* __restrict__ Aimg, const float* __restrict__ rinv, c
         const float4* bv4 = reinterpret_cast<const float4*>(tab + SH_MID + half * 128);
         const float4* wv4 = reinterpret_cast<const float4*>(tab + 2 * SH_MID + half * 128);
         const float bias5 = (MODE == PW_FINAL && half == 0) ? __ldg(b5) : 0.f;
-        uint8_t* wbuf = smem + PW_SMEM_EPI + (warp - 2) * 2048;
+        const float ri = __uint_as_float((254u - sh_layer_scale_exp(amax_in, bound)) << 23);     // 1 / layer scale
+        const size_t plane = (size_t)H * W;
+        float vmax = 0.f;
         PwRing acc;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const int tx = unit % TX, ty = (unit / TX) % TY, n = unit / (TX * TY);
-            const int py = ty * SH_TH + (row >> 4), px = tx * SH_TW + (row & 15);
+            if (ty * SH_TH >= H) continue;
+            const int py = ty * SH_TH + (row >> 5), px = tx * SH_TW + (row & 31);
             const bool valid = py < H && px < W;
-            const size_t pix = ((size_t)n * H + py) * W + px;
-            const float ri = __ldg(rinv + (size_t)unit * SH_UNIT + row);
+            // NCHW: a warp's 32 pixels are one 128-byte run of every channel plane
+            float* op = out + ((size_t)n * SH_MID + half * 128) * plane + (size_t)py * W + px;
             mbar_wait(tmem_full + 8 * acc.idx, acc.phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * SH_MID + half * 128;
             float dot = bias5;
             uint32_t r[2][32];
-            // NHWC stores: a thread owns one pixel row of the accumulator, so direct stores would touch 32 cache lines
-            // per instruction (measured: the epilogue, not the MMAs, bound the kernel).  16-column pieces go through a
-            // per-warp 2 KB buffer (XOR-swizzled, conflict free) and leave as 8 pixels x 64 contiguous bytes per store.
-            int pix_it[4]; bool ok_it[4];
-            if (MODE == PW_RELU_NHWC) {
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    pix_it[it] = __shfl_sync(0xffffffffu, (int)pix, it * 8 + (lane >> 2));
-                    ok_it[it] = __shfl_sync(0xffffffffu, (int)valid, it * 8 + (lane >> 2)) != 0;
-                }
-            }
             tmem_ld32(taddr, r[0]);
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 tmem_ld_wait_dep(r[ch & 1]);
                 if (ch + 1 < 4) tmem_ld32(taddr + (ch + 1) * 32, r[(ch + 1) & 1]);
 #pragma unroll
-                for (int sub = 0; sub < 2; ++sub) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 cv = cv4[ch * 8 + sub * 4 + i], bv = bv4[ch * 8 + sub * 4 + i];
-                        const uint32_t* q = r[ch & 1] + 16 * sub + 4 * i;
-                        float4 v;
-                        v.x = fmaxf(fmaf(__uint_as_float(q[0]) * ri, cv.x, bv.x), 0.f);
-                        v.y = fmaxf(fmaf(__uint_as_float(q[1]) * ri, cv.y, bv.y), 0.f);
-                        v.z = fmaxf(fmaf(__uint_as_float(q[2]) * ri, cv.z, bv.z), 0.f);
-                        v.w = fmaxf(fmaf(__uint_as_float(q[3]) * ri, cv.w, bv.w), 0.f);
-                        if (MODE == PW_RELU_NHWC) {
-                            *reinterpret_cast<float4*>(wbuf + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) = v;
-                        } else {
-                            const float4 wv = wv4[ch * 8 + sub * 4 + i];
-                            dot = fmaf(v.x, wv.x, dot); dot = fmaf(v.y, wv.y, dot); dot = fmaf(v.z, wv.z, dot); dot = fmaf(v.w, wv.w, dot);
+                for (int i = 0; i < 8; ++i) {
+                    const float4 cv = cv4[ch * 8 + i], bv = bv4[ch * 8 + i];
+                    const uint32_t* q = r[ch & 1] + 4 * i;
+                    float4 v;
+                    v.x = fmaxf(fmaf(__uint_as_float(q[0]) * ri, cv.x, bv.x), 0.f);
+                    v.y = fmaxf(fmaf(__uint_as_float(q[1]) * ri, cv.y, bv.y), 0.f);
+                    v.z = fmaxf(fmaf(__uint_as_float(q[2]) * ri, cv.z, bv.z), 0.f);
+                    v.w = fmaxf(fmaf(__uint_as_float(q[3]) * ri, cv.w, bv.w), 0.f);
+                    if (MODE == PW_RELU_NCHW) {
+                        if (valid) {
+                            float* o = op + (size_t)(ch * 32 + i * 4) * plane;
+                            o[0] = v.x; o[plane] = v.y; o[2 * plane] = v.z; o[3 * plane] = v.w;
+                            vmax = fmaxf(fmaxf(vmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
                         }
-                    }
-                    if (MODE == PW_RELU_NHWC) {
-                        __syncwarp();
-#pragma unroll
-                        for (int it = 0; it < 4; ++it) {
-                            const int rr = it * 8 + (lane >> 2), j = lane & 3;
-                            const float4 v = *reinterpret_cast<const float4*>(wbuf + rr * 64 + ((j ^ ((rr >> 1) & 3)) << 4));
-                            if (ok_it[it])
-                                *reinterpret_cast<float4*>(out + (size_t)pix_it[it] * SH_MID + half * 128 + ch * 32 + sub * 16 + j * 4) = v;
-                        }
-                        __syncwarp();
+                    } else {
+                        const float4 wv = wv4[ch * 8 + i];
+                        dot = fmaf(v.x, wv.x, dot); dot = fmaf(v.y, wv.y, dot); dot = fmaf(v.z, wv.z, dot); dot = fmaf(v.w, wv.w, dot);
                     }
                 }
             }
@@ -454,8 +516,12 @@ sh_pw_kernel(const uint8_t* __restrict__ Aimg, const float* __restrict__ rinv, c
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty + 8 * acc.idx);
             // two column halves -> two addends on a zero-initialised logit: order independent
-            if (MODE == PW_FINAL && valid) atomicAdd(out + pix, dot);
+            if (MODE == PW_FINAL && valid) atomicAdd(out + ((size_t)n * H + py) * W + px, dot);
             acc.advance(2);
+        }
+        if (MODE == PW_RELU_NCHW) {          // the next layer's scale needs max|y| (y >= 0: bit order = value order)
+            const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
+            if (lane == 0 && wm) atomicMax(amax_out, wm);
         }
     }
 
@@ -470,12 +536,12 @@ sh_pw_kernel(const uint8_t* __restrict__ Aimg, const float* __restrict__ rinv, c
 // ---------------------------------------------------------------------------------------------- host side
 size_t seghead_packed_bytes() { return sh_layout().total; }
 
-static inline int sh_units(int N, int H, int W) { return N * (int)ceil_div64(H, SH_TH) * (int)ceil_div64(W, SH_TW); }
+static inline int sh_tx2(int W) { return (int)ceil_div64(W, DW_TW); }
+static inline int sh_ty16(int H) { return (int)ceil_div64(H, DW_TH); }
 
 size_t seghead_workspace_bytes(int N, int H, int W) {
-    const size_t px = (size_t)N * H * W, units = (size_t)sh_units(N, H, W);
-    return align_up(px * SH_IN_PAD * 4, 1024) + align_up(units * (SH_MID / 64) * 2 * SH_CHUNK, 1024) +
-           align_up(units * SH_UNIT * 4, 1024) + align_up(px * SH_MID * 4, 1024) + 4096;
+    const size_t px = (size_t)N * H * W, units = (size_t)N * sh_ty16(H) * sh_tx2(W) * 4;
+    return align_up(px * 3 * 4, 1024) + align_up(units * (SH_MID / 64) * 2 * SH_CHUNK, 1024) + align_up(px * SH_MID * 4, 1024) + 4096;
 }
 
 // params: 50 device pointers, per layer (dw.weight [C,1,7,7], dw.bias, bn1.weight, bn1.bias, bn1.running_mean,
@@ -488,8 +554,10 @@ int launch_seghead_pack(const float* const* p, int in_dim, float eps, void* pack
     for (int i = 0; i < SH_LAYERS; ++i) {
         const float* const* q = p + 12 * i;
         const int C = i == 0 ? in_dim : SH_MID, Cp = L.l[i].cin_p;
+        cudaError_t e = cudaMemsetAsync(base + L.l[i].bound, 0, 8, stream);
+        if (e != cudaSuccess) { set_error("seghead pack: memset: %s", cudaGetErrorString(e)); return (int)e; }
         launch_k(sh_pack_dw_kernel, dim3((Cp + 127) / 128), dim3(128), 0, stream, q[0], q[1], q[2], q[3], q[4], q[5], eps, C, Cp,
-                 reinterpret_cast<float*>(base + L.l[i].dwW), reinterpret_cast<float*>(base + L.l[i].dwB));
+                 reinterpret_cast<float*>(base + L.l[i].dwW), reinterpret_cast<unsigned*>(base + L.l[i].bound));
         launch_k(sh_pack_pw_kernel, dim3(SH_MID), dim3(256), 0, stream, q[6], q[7], q[8], q[9], q[10], q[11], eps, C, Cp,
                  base + L.l[i].Bimg, reinterpret_cast<float*>(base + L.l[i].cinv), reinterpret_cast<float*>(base + L.l[i].bias2));
     }
@@ -504,50 +572,70 @@ static int sh_sm_count() {
     return sms;
 }
 
-int launch_seghead_forward(const void* packed, int in_dim, const ShSource& src, int N, int H, int W, float* logits, void* ws,
-                           size_t ws_bytes, cudaStream_t stream) {
+struct ShParts { const float* gmap; const float* lmap; const int32_t* prev; const int32_t* ids; };
+
+static int launch_seghead_forward(const void* packed, int in_dim, ShSource src, const ShParts* parts, int N, int H, int W,
+                                  float* logits, void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (in_dim < 1 || in_dim > SH_IN_PAD) return fail_invalid("seghead: in_dim must be in [1, 128]");
     if (N < 1 || H < 1 || W < 1) return fail_invalid("seghead: bad sizes");
     if (ws_bytes < seghead_workspace_bytes(N, H, W)) { set_error("seghead: workspace too small"); return MANET_E_WORKSPACE; }
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(sh_pw_kernel<PW_RELU_NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_TOTAL);
+        cudaFuncSetAttribute(sh_pw_kernel<PW_RELU_NCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_TOTAL);
         cudaFuncSetAttribute(sh_pw_kernel<PW_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_TOTAL);
-        cudaFuncSetAttribute(sh_dw_kernel<SH_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes<SH_MID>());
-        cudaFuncSetAttribute(sh_dw_kernel<SH_IN_PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes<SH_IN_PAD>());
+        cudaFuncSetAttribute(sh_dw_kernel<SH_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
+        cudaFuncSetAttribute(sh_dw_kernel<SH_IN_PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
         attr_done = true;
     }
     const ShLayout L = sh_layout();
     const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
     const size_t px = (size_t)N * H * W;
-    const int TX = (int)ceil_div64(W, SH_TW), TY = (int)ceil_div64(H, SH_TH), units = N * TX * TY;
+    const int TX2 = sh_tx2(W), TY16 = sh_ty16(H), TX = TX2, TY = 4 * TY16, tiles = N * TX2 * TY16, units = 4 * tiles;
     Carver cv(ws, ws_bytes);
-    float* x0 = cv.take<float>(px * SH_IN_PAD, 1024);
+    unsigned* amax = cv.take<unsigned>(16, 1024);                 // [0] layer-1 input, [1..3] outputs of layers 1..3, [8..11] work counters
+    float* extras = cv.take<float>(px * 3, 1024);
     uint8_t* aimg = cv.take<uint8_t>((size_t)units * (SH_MID / 64) * 2 * SH_CHUNK, 1024);
-    float* rinv = cv.take<float>((size_t)units * SH_UNIT, 1024);
     float* y = cv.take<float>(px * SH_MID, 1024);
     if (!cv.ok()) { set_error("seghead: workspace too small"); return MANET_E_WORKSPACE; }
 
     cudaError_t e = cudaMemsetAsync(logits, 0, px * sizeof(float), stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(amax, 0, 16 * sizeof(unsigned), stream);
     if (e != cudaSuccess) { set_error("seghead: memset: %s", cudaGetErrorString(e)); return (int)e; }
-    launch_k(sh_assemble_kernel, dim3((unsigned)ceil_div64(W, 32), H, N), dim3(256), 0, stream, src, in_dim, N, H, W, x0);
-    const int grid = units < sh_sm_count() ? units : sh_sm_count();
+    const int sms = sh_sm_count();
+    if (parts) {
+        launch_k(sh_absmax_kernel, dim3((unsigned)imin64(ceil_div64((int64_t)src.c0 * H, 8), 4 * sms)), dim3(256), 0, stream, src.x, (int64_t)0, src.sc,
+                 src.sh, src.sw, 1, src.c0, H, W, amax);
+        launch_k(sh_extras_kernel, dim3((unsigned)imin64(ceil_div64((int64_t)H * W, 256), 2 * sms)), dim3(256), 0, stream,
+                 parts->gmap, parts->lmap, parts->prev, parts->ids, N, H * W, extras, amax);
+        src.extras = extras;
+    } else {
+        launch_k(sh_absmax_kernel, dim3((unsigned)imin64(ceil_div64((int64_t)N * in_dim * H, 8), 4 * sms)), dim3(256), 0, stream, src.x, src.sn, src.sc,
+                 src.sh, src.sw, N, in_dim, H, W, amax);
+    }
+    const int grid = units < sms ? units : sms;
+    ShSource ysrc = {};
+    ysrc.x = y; ysrc.sn = (int64_t)SH_MID * H * W; ysrc.sc = (int64_t)H * W; ysrc.sh = W; ysrc.sw = 1; ysrc.c0 = SH_MID;
     for (int i = 0; i < SH_LAYERS; ++i) {
         const float* dwW = reinterpret_cast<const float*>(pk + L.l[i].dwW);
-        const float* dwB = reinterpret_cast<const float*>(pk + L.l[i].dwB);
-        if (i == 0) launch_k(sh_dw_kernel<SH_IN_PAD>, dim3(units), dim3(SH_IN_PAD / 2), dw_smem_bytes<SH_IN_PAD>(), stream, (const float*)x0, dwW, dwB, aimg, rinv, H, W, TX, TY);
-        else launch_k(sh_dw_kernel<SH_MID>, dim3(units), dim3(SH_MID / 2), dw_smem_bytes<SH_MID>(), stream, (const float*)y, dwW, dwB, aimg, rinv, H, W, TX, TY);
+        const unsigned* bound = reinterpret_cast<const unsigned*>(pk + L.l[i].bound);
+        const int dw_grid = (int)imin64(2 * sms, ceil_div64((int64_t)tiles * (L.l[i].cin_p / 8), DW_WARPS));
+        if (i == 0)
+            launch_k(sh_dw_kernel<SH_IN_PAD>, dim3(dw_grid), dim3(DW_WARPS * 32), DW_SMEM, stream, src, in_dim, dwW,
+                     (const unsigned*)amax, bound, aimg, amax + 8 + i, N, H, W, TX2, TY16);
+        else
+            launch_k(sh_dw_kernel<SH_MID>, dim3(dw_grid), dim3(DW_WARPS * 32), DW_SMEM, stream, ysrc, SH_MID, dwW,
+                     (const unsigned*)(amax + i), bound, aimg, amax + 8 + i, N, H, W, TX2, TY16);
         const float* cinv = reinterpret_cast<const float*>(pk + L.l[i].cinv);
         const float* bias2 = reinterpret_cast<const float*>(pk + L.l[i].bias2);
         const float* w5 = reinterpret_cast<const float*>(pk + L.w5);
         const float* b5 = reinterpret_cast<const float*>(pk + L.b5);
         const int nkb = L.l[i].cin_p / 64;
         if (i + 1 < SH_LAYERS)
-            launch_k(sh_pw_kernel<PW_RELU_NHWC>, dim3(grid), dim3(PW_THREADS), PW_SMEM_TOTAL, stream, (const uint8_t*)aimg,
-                     (const float*)rinv, pk + L.l[i].Bimg, cinv, bias2, w5, b5, y, units, nkb, H, W, TX, TY);
+            launch_k(sh_pw_kernel<PW_RELU_NCHW>, dim3(grid), dim3(PW_THREADS), PW_SMEM_TOTAL, stream, (const uint8_t*)aimg,
+                     (const unsigned*)(amax + i), bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, y, amax + i + 1, units, nkb, H, W, TX, TY);
         else
             launch_k(sh_pw_kernel<PW_FINAL>, dim3(grid), dim3(PW_THREADS), PW_SMEM_TOTAL, stream, (const uint8_t*)aimg,
-                     (const float*)rinv, pk + L.l[i].Bimg, cinv, bias2, w5, b5, logits, units, nkb, H, W, TX, TY);
+                     (const unsigned*)(amax + i), bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, logits, amax + 7, units, nkb, H, W, TX, TY);
     }
     return check_launch("seghead forward kernels");
 }
@@ -556,7 +644,7 @@ int seghead_forward_tensor(const void* packed, int in_dim, const float* x, const
                            float* logits, void* ws, size_t ws_bytes, cudaStream_t stream) {
     ShSource s = {};
     s.x = x; s.sn = strides[0]; s.sc = strides[1]; s.sh = strides[2]; s.sw = strides[3]; s.c0 = in_dim;
-    return launch_seghead_forward(packed, in_dim, s, N, H, W, logits, ws, ws_bytes, stream);
+    return launch_seghead_forward(packed, in_dim, s, nullptr, N, H, W, logits, ws, ws_bytes, stream);
 }
 
 int seghead_forward_parts(const void* packed, const float* emb, int64_t sc, int64_t sh, int64_t sw, int C0, const float* gmap,
@@ -564,8 +652,8 @@ int seghead_forward_parts(const void* packed, const float* emb, int64_t sc, int6
                           void* ws, size_t ws_bytes, cudaStream_t stream) {
     ShSource s = {};
     s.x = emb; s.sn = 0; s.sc = sc; s.sh = sh; s.sw = sw; s.c0 = C0;
-    s.gmap = gmap; s.lmap = lmap; s.prev = prev; s.ids = ids;
-    return launch_seghead_forward(packed, C0 + 3, s, N, H, W, logits, ws, ws_bytes, stream);
+    ShParts parts = {gmap, lmap, prev, ids};
+    return launch_seghead_forward(packed, C0 + 3, s, &parts, N, H, W, logits, ws, ws_bytes, stream);
 }
 
 }  // namespace manet
