@@ -288,6 +288,7 @@ def run_own_arm(args, rank, local_rank, world):
     total_s, e2e_s, e2e_sync_s, serial_s, e2e_stream_s = (float(t[i]) for i in range(5))
 
     sharded = sharded_1080p_leg(dev, rank, world) if os.environ.get("MANET_BENCH_SHARDED", "1") == "1" else None
+    seghead = seghead_leg(dev) if rank == 0 and os.environ.get("MANET_BENCH_SEGHEAD", "1") == "1" else None
 
     if rank == 0:
         peaks = load_peaks()
@@ -338,12 +339,65 @@ def run_own_arm(args, rank, local_rank, world):
                 "wall_s_timed_region": wall_dev}
         if sharded:
             line["sharded_global_1080p"] = sharded
+        if seghead:
+            line["seghead"] = seghead
+            line["frame_step_with_seghead"] = {"ms": total_s * 1e3 / K + seghead["ms"],
+                                               "frames_per_s": 1e3 / (total_s * 1e3 / K + seghead["ms"]),
+                                               "note": "matching step (value) + DynamicSegHead, the two device-timed parts of one propagation frame"}
         if world == 1 and os.environ.get("MANET_BENCH_CPU", "1") == "1":
             line["cpu_baseline"] = cpu_baseline_leg()
         print(json.dumps(line), flush=True)
     sess.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def seghead_leg(dev, iters=10):
+    """SURVEY 8f-2, the step right after the matching path: DynamicSegHead (IntVOS.py:488-525) on the step's own
+    outputs at the headline shape (480p embedding, 5 objects), fed by its parts (no repeat/cat, IntVOS.py:663-670).
+    Random-init weights of the reference architecture; CUDA events, L2 flushed between iterations."""
+    import torch
+    from cvpr2020_manet_b200.networks.seghead import DynamicSegHead
+    torch.manual_seed(0)
+    head = DynamicSegHead().to(dev).eval()
+    gen = torch.Generator().manual_seed(77)
+    cur = (0.1 * torch.relu(torch.randn(C, H, W, generator=gen))).to(dev)
+    gmap = torch.rand(1, H, W, N_IDS, 1, generator=gen).to(dev)
+    lmap = torch.rand(1, H, W, N_IDS, 1, generator=gen).to(dev)
+    prev = torch.randint(0, N_IDS, (H // 8 + 1, W // 8 + 1), generator=gen).repeat_interleave(8, 0).repeat_interleave(8, 1)[:H, :W].int().to(dev)
+    ids = torch.arange(N_IDS, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    times = []
+    for i in range(iters + 3):
+        flush.fill_(i & 0xFF)
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        out = head.forward_parts(cur, gmap, lmap, prev, ids)
+        t.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            times.append(s.elapsed_time(t))
+    ms = sum(times) / len(times)
+    px = N_IDS * H * W
+    flop_pw = 2.0 * px * ((C + 3) * 256 + 3 * 256 * 256 + 256)
+    flop_dw = 2.0 * px * 49 * ((C + 3) + 3 * 256)
+    res = {"workload": f"DynamicSegHead forward, input [{N_IDS},{C + 3},{H},{W}] assembled from its parts, random-init weights",
+           "ms": ms, "kernels_per_call": 10, "checksum": float(out.sum()),
+           "pointwise_gflop": flop_pw / 1e9, "depthwise_gflop": flop_dw / 1e9,
+           "achieved_tflops_algorithmic": (flop_pw + flop_dw) / (ms * 1e-3) / 1e12,
+           "numerics": "depthwise fp32 CUDA cores; 1x1 convs as 3 fp16-split tcgen05 products, fp32 accumulate"}
+    if os.environ.get("MANET_BENCH_CPU", "1") == "1":
+        from oracle import manet_oracle as O
+        state = {k: v.detach().cpu() for k, v in head.state_dict().items()}
+        x = O.seghead_features(cur.cpu(), gmap.cpu(), lmap.cpu(), prev.cpu(), ids.cpu())
+        torch.set_num_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            want = O.dynamic_seghead_forward(state, x)
+        res["cpu_oracle_ms"] = (time.perf_counter() - t0) * 1e3
+        res["cpu_cores"] = os.cpu_count()
+        res["max_abs_err_vs_oracle"] = float((out.cpu() - want).abs().max())
+    return res
 
 
 def sharded_1080p_leg(dev, rank, world, t_mem=4, iters=5):

@@ -6,12 +6,13 @@
 // one affine map at pack time (sh_pack_*).  Activations stay in the reference's NCHW layout between layers.
 //
 // Per layer:   x [N,Cin,H,W] --depthwise 7x7 + BN + ReLU--> a --1x1 conv Cin->256 + BN + ReLU--> y [N,256,H,W]
-//   * sh_dw_kernel   fp32 CUDA cores.  A warp owns one channel at a time over an 8x32 pixel tile (two 128-row GEMM
-//     units): each lane computes a 2x4 block of outputs from a 8x10 window read with 128-bit shared-memory loads,
-//     the 49 taps are warp-uniform registers.  The channel's input plane (14x38 with halo) arrives through a
-//     per-warp double buffer filled by cp.async, so the loop over channels is a compact rolled loop with no CTA
-//     barrier.  Eight channels at a time are converted to the tensor-core operand: x*2^e = hi + lo in fp16, written
-//     as 16-byte chunks of the 128-byte-swizzled K-major shared-memory image of the unit.
+//   * sh_dw_kernel   fp32 CUDA cores.  Work item = (16x32 pixel tile = four 128-row GEMM units, chunk of 8 channels),
+//     pulled by warps from an atomic counter.  A warp owns one channel at a time: each lane computes a 4x4 block of
+//     outputs from a 10x10 window read with 128-bit shared-memory loads, the 49 taps are warp-uniform registers.  The
+//     channel's input plane (22x38 with halo) and taps arrive through a per-warp double buffer filled by cp.async, so
+//     the loop over channels is a compact rolled loop with no CTA barrier.  Eight channels at a time are converted to
+//     the tensor-core operand: x*2^e = hi + lo in fp16, written as 16-byte chunks of the 128-byte-swizzled K-major
+//     shared-memory image of the unit.
 //     The scale 2^e is one power of two per layer, derived on the device from a BOUND of the layer's outputs
 //     (sum|w'| * max|input| + max|b'|, the max coming from the previous kernel's epilogue): hi+lo carries 22
 //     significant bits of every element that matters and an absolute error below 2^-39 of the bound for the rest.
@@ -22,9 +23,14 @@
 //     registers -> logits.
 // The first layer reads the embedding and the two maps where they lie (no repeat/cat, IntVOS.py:663-670).
 //
-// History of the depthwise kernel (profiles/README.md): thread = channel over NHWC with the whole 7x7 window unrolled
-// (298 us per layer; ncu: stall "wait", then "no_instruction": a 40-60 KB straight-line body streams through the
-// 32 KB instruction cache) -> this form (compact body, 16 warps per SM).
+// History of the depthwise kernel (ncu evidence in profiles/README.md), us per 256-channel layer at 480p x 6 objects:
+//   thread = channel over NHWC, 7x7 window fully unrolled, plain loads / cp.async ring        298-314  stall "wait"
+//   ... 32 accumulators under a 128-register cap / channel pairs on FFMA2                      217 / 186  stall "no_instruction":
+//       a 40-60 KB straight-line body streams through the 32 KB instruction cache
+//   warp = channel, lane = 2x4 pixel block, compact rolled loop, NCHW, per-layer scale         247  shared-memory bound
+//   4x4 blocks (6.25 instead of 10 loaded floats per output), warp-level work items            238  57 % of issued instructions not FFMA
+//   one-pointer cp.async staging, taps through shared memory                                   162  (this file) issue 67 %, FMA pipe 44 %
+//   same with channel pairs on FFMA2 (7 warps per SM fit)                                      178  stall "wait": too few warps
 #include "common.cuh"
 #include "umma_ptx.cuh"
 

@@ -189,3 +189,50 @@ def test_gpu_prop_seghead_matches_reference(golden, gpu_head):
             assert logit_err(res["s"].cpu().numpy(), g[f"f{f}_pred"]) <= 2e-4
     finally:
         cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE = saved
+
+
+@pytest.mark.gpu
+def test_gpu_propagation_sequence_with_head(golden, gpu_head):
+    """BASELINE config 3 in miniature: two interaction rounds of forward propagation over a short sequence through
+    engine.prop_seghead (matching + both memories + head), against the oracle driven in lock step.  The previous-frame
+    labels of both sides are the ORACLE's argmax, so every frame compares like with like."""
+    from cvpr2020_manet_b200 import engine
+    from cvpr2020_manet_b200.config import cfg
+    head, gh = gpu_head
+    state = load_state(gh)
+    saved = (cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE)
+    c, h, w, nobj, d, T = 100, 20, 28, 2, 3, 6
+    cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE = True, d
+    try:
+        gen = torch.Generator().manual_seed(99)
+        base = 0.1 * torch.relu(torch.randn(c, h, w, generator=gen))
+        embs = torch.stack([base + 0.02 * t * torch.randn(c, h, w, generator=gen) for t in range(T)])
+        ids = torch.arange(nobj + 1, dtype=torch.int32)
+        gm_o, lm_o, gm_g, lm_g = {}, ({}, {}), {}, ({}, {})
+        embs_g = embs.cuda()
+        for rnd, ann in ((1, 0), (2, 1)):
+            scr = torch.full((h, w), -1, dtype=torch.int32)
+            scr[2 + rnd, 3:15] = 0
+            scr[10, 5 + rnd:20] = 1
+            if rnd == 1:
+                scr[14:18, 9] = 2                       # object 2 absent from the second round's scribble
+            prev_lab = torch.randint(0, nobj + 1, (h // 2, w // 2), generator=gen).repeat_interleave(2, 0).repeat_interleave(2, 1).int()
+            for f in range(ann + 1, T):
+                gmap, lmap = O.prop_matching_step(embs[ann], embs[f - 1], embs[f], scr, prev_lab, nobj, 1, d, True, gm_o, lm_o,
+                                                  "s", f, rnd, ann)
+                want = O.dynamic_seghead_forward(state, O.seghead_features(embs[f], gmap, lmap, prev_lab, ids)).permute(1, 0, 2, 3)
+                res, gm_g, lm_g = engine.prop_seghead(ref_frame_embedding=embs_g[ann:ann + 1],
+                                                      previous_frame_embedding=embs_g[f - 1:f],
+                                                      current_frame_embedding=embs_g[f:f + 1],
+                                                      ref_scribble_label=scr.cuda().view(1, 1, h, w).float(),
+                                                      previous_frame_mask=prev_lab.cuda().view(1, 1, h, w).float(),
+                                                      seq_names=["s"], gt_ids=torch.tensor([nobj]), k_nearest_neighbors=1,
+                                                      global_map_tmp_dic=gm_g, local_map_dics=lm_g, interaction_num=rnd,
+                                                      start_annotated_frame=ann, frame_num=[f], dynamic_seghead=head)
+                assert logit_err(res["s"].cpu().numpy(), want.numpy()) <= 2e-4, (rnd, f)
+                prev_lab = want[0].argmax(0).int()
+        assert float((gm_g["s"].cpu() - gm_o["s"]).abs().max()) <= 1e-5
+        assert float((lm_g[0]["s"].cpu() - lm_o[0]["s"]).abs().max()) <= 1e-5
+        assert torch.equal(lm_g[1]["s"].cpu(), lm_o[1]["s"])
+    finally:
+        cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE = saved
