@@ -31,6 +31,8 @@
 //   4x4 blocks (6.25 instead of 10 loaded floats per output), warp-level work items            238  57 % of issued instructions not FFMA
 //   one-pointer cp.async staging, taps through shared memory                                   162  (this file) issue 67 %, FMA pipe 44 %
 //   same with channel pairs on FFMA2 (7 warps per SM fit)                                      178  stall "wait": too few warps
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "umma_ptx.cuh"
 
@@ -539,6 +541,205 @@ sh_pw_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ amax
     }
 }
 
+// ---------------------------------------------------------------------------------------------- 1x1 conv GEMM on CTA pairs
+// (opt-in variant, MANET_SH_PW_PAIR=1; parity-tested, measured slightly slower than the single-CTA kernel)
+// Same GEMM with cta_group::2: one tcgen05.mma covers TWO units (M = 256, one unit per CTA of the pair) x 256 output
+// channels, each CTA holding its own unit's A stage and ONE HALF (128 rows) of the weight stage.  Per SM that halves the
+// weight bytes pulled from L2 and read from shared memory per MMA -- the single-CTA kernel's limiter (its MMAs read
+// 96 B/clk and its bulk copies write 62 B/clk against 128 B/clk of shared memory; here 64 + 42) -- and the freed
+// shared memory buys a third stage.  Protocol as in gm_umma2_kernel: plain bulk copies signal only the local CTA, so
+// the peer's warp 1 forwards "my stage landed" to the leader with a remote mbarrier arrive; tcgen05.commit multicasts
+// "stage free" / "accumulator ready" to both CTAs; both CTAs' epilogue warps release the accumulator on the leader.
+constexpr int PW2_STAGES = 3;
+constexpr int PW2_STAGE_BYTES = 4 * SH_CHUNK;               // A hi|lo (32 KB) + this CTA's half of B hi|lo (32 KB)
+constexpr int PW2_SMEM_TAB = PW2_STAGES * PW2_STAGE_BYTES;  // cinv[256] | bias2[256] | w5[256]
+constexpr int PW2_SMEM_BAR = PW2_SMEM_TAB + 3 * SH_MID * 4;
+constexpr int PW2_SMEM_TOTAL = PW2_SMEM_BAR + 256 + 1024;
+
+__device__ __forceinline__ bool sh_unit_valid(int unit, int TX, int TY, int H) { return ((unit / TX) % TY) * SH_TH < H; }
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PW_THREADS, 1)
+sh_pw2_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ amax_in, const unsigned* __restrict__ bound,
+              const uint8_t* __restrict__ Bimg, const float* __restrict__ cinv, const float* __restrict__ bias2,
+              const float* __restrict__ w5, const float* __restrict__ b5, float* __restrict__ out, unsigned* __restrict__ amax_out,
+              int n_units, int nkb, int H, int W, int TX, int TY) {
+    pdl_enter();
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    float* tab = reinterpret_cast<float*>(smem + PW2_SMEM_TAB);
+    const uint32_t bars = base + PW2_SMEM_BAR;
+    const uint32_t full_b = bars + 0;            // [3]  local bytes landed
+    const uint32_t empty_b = bars + 24;          // [3]  stage free (multicast commit)
+    const uint32_t peer_full = bars + 48;        // [3]  leader only: the peer's stage landed
+    const uint32_t tmem_full = bars + 72;        // [2]
+    const uint32_t tmem_empty = bars + 88;       // [2]  leader only, 16 arrivals
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + PW2_SMEM_BAR + 112);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const size_t unit_bytes = (size_t)nkb * PW_A_BYTES;
+    const int n_pairs = n_units >> 1, n_clusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
+
+    for (int i = threadIdx.x; i < SH_MID; i += PW_THREADS) {
+        tab[i] = cinv[i]; tab[SH_MID + i] = bias2[i]; tab[2 * SH_MID + i] = (MODE == PW_FINAL) ? w5[i] : 0.f;
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < PW2_STAGES; ++i) { mbar_init(full_b + 8 * i, 1); mbar_init(empty_b + 8 * i, 1); mbar_init(peer_full + 8 * i, 1); }
+            for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, 2 * PW_EPI_WARPS); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                           // barriers of both CTAs initialised before any remote arrive
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------ producer (both CTAs): own unit's A, own half of the weights
+        PwRing st;
+        for (int pair = cid; pair < n_pairs; pair += n_clusters) {
+            if (!sh_unit_valid(2 * pair, TX, TY, H) && !sh_unit_valid(2 * pair + 1, TX, TY, H)) continue;
+            const int unit = 2 * pair + (int)rank;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(empty_b + 8 * st.idx, st.phase ^ 1);
+                const uint32_t fb = full_b + 8 * st.idx;
+                const uint32_t dst = base + st.idx * PW2_STAGE_BYTES;
+                if (elect_one()) {
+                    mbar_expect_tx(fb, PW2_STAGE_BYTES);
+                    bulk_g2s(dst, Aimg + (size_t)unit * unit_bytes + (size_t)kb * PW_A_BYTES, PW_A_BYTES, fb);
+                    const uint8_t* bsrc = Bimg + (size_t)kb * PW_B_BYTES + (size_t)rank * SH_CHUNK;     // rows 128*rank .. +127
+                    bulk_g2s(dst + 2 * SH_CHUNK, bsrc, SH_CHUNK, fb);                                    // hi
+                    bulk_g2s(dst + 3 * SH_CHUNK, bsrc + 2 * SH_CHUNK, SH_CHUNK, fb);                     // lo
+                }
+                __syncwarp();
+                st.advance(PW2_STAGES);
+            }
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            // -------------------------------------------- MMA issuer (leader CTA; whole warp runs the loop, one elected lane issues)
+            constexpr uint32_t idesc = idesc_f16(2 * SH_UNIT, SH_MID);
+            PwRing st, acc;
+            for (int pair = cid; pair < n_pairs; pair += n_clusters) {
+                if (!sh_unit_valid(2 * pair, TX, TY, H) && !sh_unit_valid(2 * pair + 1, TX, TY, H)) continue;
+                mbar_wait_cluster(tmem_empty + 8 * acc.idx, acc.phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc.idx * SH_MID;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(full_b + 8 * st.idx, st.phase);
+                    mbar_wait_cluster(peer_full + 8 * st.idx, st.phase);
+                    tc_fence_after();
+                    const uint32_t sA = base + st.idx * PW2_STAGE_BYTES;
+                    const uint64_t dAh = smem_desc_sw128(sA), dAl = smem_desc_sw128(sA + SH_CHUNK);
+                    const uint64_t dBh = smem_desc_sw128(sA + 2 * SH_CHUNK), dBl = smem_desc_sw128(sA + 3 * SH_CHUNK);
+                    if (elect_one()) {
+                        for (int k = 0; k < 4; ++k) umma2_f16(d_tmem, dAh + 2 * k, dBh + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k) umma2_f16(d_tmem, dAl + 2 * k, dBh + 2 * k, idesc, 1u);
+                        for (int k = 0; k < 4; ++k) umma2_f16(d_tmem, dAh + 2 * k, dBl + 2 * k, idesc, 1u);
+                        tc_commit2(empty_b + 8 * st.idx);
+                    }
+                    __syncwarp();
+                    st.advance(PW2_STAGES);
+                }
+                if (elect_one()) tc_commit2(tmem_full + 8 * acc.idx);
+                __syncwarp();
+                acc.advance(2);
+            }
+        } else {
+            // -------------------------------------------- peer: forward "my stage landed" to the leader
+            const uint32_t r_peer_full = mapa_shared(peer_full, 0);
+            PwRing st;
+            for (int pair = cid; pair < n_pairs; pair += n_clusters) {
+                if (!sh_unit_valid(2 * pair, TX, TY, H) && !sh_unit_valid(2 * pair + 1, TX, TY, H)) continue;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(full_b + 8 * st.idx, st.phase);
+                    if (elect_one()) mbar_arrive_remote(r_peer_full + 8 * st.idx);
+                    __syncwarp();
+                    st.advance(PW2_STAGES);
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------ epilogue: warps 2..9 of both CTAs, own unit x all 256 channels
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = quarter * 32 + lane;
+        const float4* cv4 = reinterpret_cast<const float4*>(tab + half * 128);
+        const float4* bv4 = reinterpret_cast<const float4*>(tab + SH_MID + half * 128);
+        const float4* wv4 = reinterpret_cast<const float4*>(tab + 2 * SH_MID + half * 128);
+        const float bias5 = (MODE == PW_FINAL && half == 0) ? __ldg(b5) : 0.f;
+        const float ri = __uint_as_float((254u - sh_layer_scale_exp(amax_in, bound)) << 23);     // 1 / layer scale
+        const size_t plane = (size_t)H * W;
+        const uint32_t r_tmem_empty = mapa_shared(tmem_empty, 0);
+        float vmax = 0.f;
+        PwRing acc;
+        for (int pair = cid; pair < n_pairs; pair += n_clusters) {
+            if (!sh_unit_valid(2 * pair, TX, TY, H) && !sh_unit_valid(2 * pair + 1, TX, TY, H)) continue;
+            const int unit = 2 * pair + (int)rank;
+            const int tx = unit % TX, ty = (unit / TX) % TY, n = unit / (TX * TY);
+            const int py = ty * SH_TH + (row >> 5), px = tx * SH_TW + (row & 31);
+            const bool valid = py < H && px < W;
+            float* op = out + ((size_t)n * SH_MID + half * 128) * plane + (size_t)py * W + px;
+            mbar_wait(tmem_full + 8 * acc.idx, acc.phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * SH_MID + half * 128;
+            float dot = bias5;
+            uint32_t r[2][32];
+            tmem_ld32(taddr, r[0]);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                tmem_ld_wait_dep(r[ch & 1]);
+                if (ch + 1 < 4) tmem_ld32(taddr + (ch + 1) * 32, r[(ch + 1) & 1]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 cv = cv4[ch * 8 + i], bv = bv4[ch * 8 + i];
+                    const uint32_t* q = r[ch & 1] + 4 * i;
+                    float4 v;
+                    v.x = fmaxf(fmaf(__uint_as_float(q[0]) * ri, cv.x, bv.x), 0.f);
+                    v.y = fmaxf(fmaf(__uint_as_float(q[1]) * ri, cv.y, bv.y), 0.f);
+                    v.z = fmaxf(fmaf(__uint_as_float(q[2]) * ri, cv.z, bv.z), 0.f);
+                    v.w = fmaxf(fmaf(__uint_as_float(q[3]) * ri, cv.w, bv.w), 0.f);
+                    if (MODE == PW_RELU_NCHW) {
+                        if (valid) {
+                            float* o = op + (size_t)(ch * 32 + i * 4) * plane;
+                            o[0] = v.x; o[plane] = v.y; o[2 * plane] = v.z; o[3 * plane] = v.w;
+                            vmax = fmaxf(fmaxf(vmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+                        }
+                    } else {
+                        const float4 wv = wv4[ch * 8 + i];
+                        dot = fmaf(v.x, wv.x, dot); dot = fmaf(v.y, wv.y, dot); dot = fmaf(v.z, wv.z, dot); dot = fmaf(v.w, wv.w, dot);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(r_tmem_empty + 8 * acc.idx);
+            if (MODE == PW_FINAL && valid) atomicAdd(out + ((size_t)n * H + py) * W + px, dot);
+            acc.advance(2);
+        }
+        if (MODE == PW_RELU_NCHW) {
+            const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
+            if (lane == 0 && wm) atomicMax(amax_out, wm);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                           // nobody leaves while the pair may still touch its smem / TMEM
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 size_t seghead_packed_bytes() { return sh_layout().total; }
 
@@ -589,6 +790,8 @@ static int launch_seghead_forward(const void* packed, int in_dim, ShSource src, 
     if (!attr_done) {
         cudaFuncSetAttribute(sh_pw_kernel<PW_RELU_NCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_TOTAL);
         cudaFuncSetAttribute(sh_pw_kernel<PW_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_TOTAL);
+        cudaFuncSetAttribute(sh_pw2_kernel<PW_RELU_NCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW2_SMEM_TOTAL);
+        cudaFuncSetAttribute(sh_pw2_kernel<PW_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW2_SMEM_TOTAL);
         cudaFuncSetAttribute(sh_dw_kernel<SH_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
         cudaFuncSetAttribute(sh_dw_kernel<SH_IN_PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
         attr_done = true;
@@ -636,12 +839,26 @@ static int launch_seghead_forward(const void* packed, int in_dim, ShSource src, 
         const float* w5 = reinterpret_cast<const float*>(pk + L.w5);
         const float* b5 = reinterpret_cast<const float*>(pk + L.b5);
         const int nkb = L.l[i].cin_p / 64;
-        if (i + 1 < SH_LAYERS)
-            launch_k(sh_pw_kernel<PW_RELU_NCHW>, dim3(grid), dim3(PW_THREADS), PW_SMEM_TOTAL, stream, (const uint8_t*)aimg,
-                     (const unsigned*)(amax + i), bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, y, amax + i + 1, units, nkb, H, W, TX, TY);
-        else
-            launch_k(sh_pw_kernel<PW_FINAL>, dim3(grid), dim3(PW_THREADS), PW_SMEM_TOTAL, stream, (const uint8_t*)aimg,
-                     (const unsigned*)(amax + i), bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, logits, amax + 7, units, nkb, H, W, TX, TY);
+        // single-CTA kernel by default; MANET_SH_PW_PAIR=1 selects the CTA-pair (cta_group::2) kernel.  Measured on B200
+        // (480p, N = 6): 64 / 51 us (single) against 72 / 54 us (pair) per layer / last layer -- halving the weight traffic
+        // does not help, so operand supply is not what holds the tensor pipe at ~55 % (ncu: 72 % active in the last layer).
+        static const bool single = [] { const char* e = getenv("MANET_SH_PW_PAIR"); return !(e && e[0] == '1'); }();
+        const int grid2 = (units < sms ? units : sms) & ~1;
+        if (single || grid2 < 2) {
+            if (i + 1 < SH_LAYERS)
+                launch_k(sh_pw_kernel<PW_RELU_NCHW>, dim3(grid), dim3(PW_THREADS), PW_SMEM_TOTAL, stream, (const uint8_t*)aimg,
+                         (const unsigned*)(amax + i), bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, y, amax + i + 1, units, nkb, H, W, TX, TY);
+            else
+                launch_k(sh_pw_kernel<PW_FINAL>, dim3(grid), dim3(PW_THREADS), PW_SMEM_TOTAL, stream, (const uint8_t*)aimg,
+                         (const unsigned*)(amax + i), bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, logits, amax + 7, units, nkb, H, W, TX, TY);
+        } else {
+            if (i + 1 < SH_LAYERS)
+                launch_k(sh_pw2_kernel<PW_RELU_NCHW>, dim3(grid2), dim3(PW_THREADS), PW2_SMEM_TOTAL, stream, (const uint8_t*)aimg,
+                         (const unsigned*)(amax + i), bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, y, amax + i + 1, units, nkb, H, W, TX, TY);
+            else
+                launch_k(sh_pw2_kernel<PW_FINAL>, dim3(grid2), dim3(PW_THREADS), PW2_SMEM_TOTAL, stream, (const uint8_t*)aimg,
+                         (const unsigned*)(amax + i), bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, logits, amax + 7, units, nkb, H, W, TX, TY);
+        }
     }
     return check_launch("seghead forward kernels");
 }

@@ -236,3 +236,30 @@ def test_gpu_propagation_sequence_with_head(golden, gpu_head):
         assert torch.equal(lm_g[1]["s"].cpu(), lm_o[1]["s"])
     finally:
         cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE = saved
+
+
+@pytest.mark.gpu
+def test_gpu_seghead_pair_gemm_variant(golden):
+    """The opt-in CTA-pair (cta_group::2) 1x1-conv kernel (MANET_SH_PW_PAIR=1, read once per process) gives the same
+    logits as the default kernel: run in a subprocess so the switch takes effect."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, torch, sys\n"
+        "sys.path.insert(0, '.')\n"
+        "from cvpr2020_manet_b200.networks.seghead import DynamicSegHead\n"
+        "g = dict(np.load('tests/golden/seghead_ref.npz'))\n"
+        "head = DynamicSegHead(); head.load_state_dict({k[2:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('p:')}, strict=False)\n"
+        "head = head.cuda().eval()\n"
+        "x = torch.randn(3, 103, 37, 70, generator=torch.Generator().manual_seed(1)).cuda()\n"
+        "np.save(sys.argv[1], head(x).cpu().numpy())\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flag in ("0", "1"):
+        path = os.path.join(root, "gpurun_out", f"_pair_variant_{flag}.npy")
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        env = dict(os.environ, MANET_SH_PW_PAIR=flag)
+        subprocess.run([sys.executable, "-c", code, path], check=True, cwd=root, env=env, timeout=300)
+        outs.append(np.load(path))
+    assert logit_err(outs[1], outs[0]) <= 2e-6
