@@ -289,6 +289,7 @@ def run_own_arm(args, rank, local_rank, world):
 
     sharded = sharded_1080p_leg(dev, rank, world) if os.environ.get("MANET_BENCH_SHARDED", "1") == "1" else None
     seghead = seghead_leg(dev) if rank == 0 and os.environ.get("MANET_BENCH_SEGHEAD", "1") == "1" else None
+    propagation = propagation_leg(dev) if rank == 0 and os.environ.get("MANET_BENCH_SEGHEAD", "1") == "1" else None
 
     if rank == 0:
         peaks = load_peaks()
@@ -339,6 +340,8 @@ def run_own_arm(args, rank, local_rank, world):
                 "wall_s_timed_region": wall_dev}
         if sharded:
             line["sharded_global_1080p"] = sharded
+        if propagation:
+            line["propagation_50"] = propagation
         if seghead:
             line["seghead"] = seghead
             line["frame_step_with_seghead"] = {"ms": total_s * 1e3 / K + seghead["ms"],
@@ -398,6 +401,53 @@ def seghead_leg(dev, iters=10):
         res["cpu_cores"] = os.cpu_count()
         res["max_abs_err_vs_oracle"] = float((out.cpu() - want).abs().max())
     return res
+
+
+def propagation_leg(dev, T=50):
+    """BASELINE config 3: propagation over a synthetic 50-frame 480p sequence, 5 objects -- per frame global matching
+    against the annotated frame + global-map memory, local matching against the previous frame + local-map memory, the
+    dynamic head, bilinear upsample to 480x854 + argmax, labels fed to the next frame (test.py:237-259), all on the
+    device through engine.propagate_sequence.  Embeddings are synthetic (the backbone is out of scope) and resident."""
+    import torch
+    from cvpr2020_manet_b200 import engine
+    from cvpr2020_manet_b200.config import cfg
+    from cvpr2020_manet_b200.networks.seghead import DynamicSegHead
+    torch.manual_seed(0)
+    head = DynamicSegHead().to(dev).eval()
+    gen = torch.Generator().manual_seed(321)
+    base = 0.1 * torch.relu(torch.randn(C, H, W, generator=gen))
+    embs = torch.empty(T, C, H, W, device=dev)
+    for t in range(T):
+        embs[t] = (base + 0.01 * t * torch.randn(C, H, W, generator=gen)).to(dev)
+    scr = torch.full((H, W), -1, dtype=torch.int32)
+    for o in range(N_IDS):
+        scr[10 + 15 * o, 20:150] = o
+        scr[5 + 15 * o:25 + 15 * o, 30 + 25 * o] = o
+    first = torch.randint(0, N_IDS, (H // 8 + 1, W // 8 + 1), generator=gen).repeat_interleave(8, 0).repeat_interleave(8, 1)[:H, :W].int()
+    saved = (cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE)
+    cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE = True, D_LOCAL
+    try:
+        res = {}
+        for rep in range(2):                                   # first pass warms workspaces / packs the weights
+            gm, lm = {}, ({}, {})
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            s.record()
+            out, _ = engine.propagate_sequence(embs, range(1, T), 0, scr.to(dev), first.to(dev), N_IDS - 1, head, (480, 854),
+                                               gm, lm, "bench", 1, D_LOCAL)
+            e.record()
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            res = {"frames": T - 1, "device_ms_per_frame": s.elapsed_time(e) / (T - 1), "wall_ms_per_frame": wall * 1e3 / (T - 1),
+                   "frames_per_s": (T - 1) / wall}
+        hist = torch.bincount(out[T - 1].flatten(), minlength=N_IDS).tolist()
+        res.update({"workload": f"{T}-frame 480p propagation, 5 objects: matching + memories + DynamicSegHead + upsample/argmax per frame, "
+                                "synthetic resident embeddings, random-init head", "last_frame_label_histogram": hist,
+                    "timing": "CUDA events around the whole loop (device) and host wall clock including all launches"})
+        return res
+    finally:
+        cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE = saved
 
 
 def sharded_1080p_leg(dev, rank, world, t_mem=4, iters=5):

@@ -65,6 +65,8 @@ int seghead_forward_tensor(const void*, int, const float*, const int64_t*, int, 
 int seghead_forward_parts(const void*, const float*, int64_t, int64_t, int64_t, int, const float*, const float*, const int32_t*,
                           const int32_t*, int, int, int, float*, void*, size_t, cudaStream_t);
 
+int launch_upsample_argmax(const float*, int, int, int, int, int, int64_t*, int32_t*, cudaStream_t);
+
 // ---- optional kernel timing pools
 struct ProfPool { cudaEvent_t* start; cudaEvent_t* stop; int cap; int n; };
 static ProfPool g_prof[PROF_SLOTS];
@@ -323,6 +325,13 @@ int manet_seghead_forward_parts(const void* packed, const float* emb, int64_t em
     MANET_REQUIRE(C >= 1 && C + 3 <= 128, "seghead forward: embedding channels + 3 must be <= 128");
     return seghead_forward_parts(packed, emb, emb_ch_stride, emb_row_stride, emb_col_stride, C, global_map, local_map,
                                  prev_labels, gt_ids, n_objects, H, W, logits, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int manet_upsample_argmax(const float* logits, int n_objects, int h, int w, int out_h, int out_w, int64_t* labels_full,
+                          int32_t* labels_small, manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(logits, "upsample_argmax: null pointer");
+    return launch_upsample_argmax(logits, n_objects, h, w, out_h, out_w, labels_full, labels_small, (cudaStream_t)stream);
 }
 
 int manet_correlation_output_shape(int C, int H, int W, int pad_size, int kernel_size, int max_displacement, int stride1,

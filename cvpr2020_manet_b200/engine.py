@@ -117,6 +117,53 @@ def prop_seghead(ref_frame_embedding=None, previous_frame_embedding=None, curren
     return dic_tmp, global_map_tmp_dic, local_map_dics
 
 
+def upsample_argmax(pred, size, want_full=True, want_small=True):
+    """The label step of the propagation loop (test.py:253-256 followed by IntVOS.py:598-599): ``pred`` ``[1,N,h,w]``
+    logits -> ``(labels [1,Hf,Wf] int64, small [h,w] int32)`` where ``labels = argmax(interpolate(pred, size, 'bilinear',
+    align_corners=True), dim=1)`` and ``small`` is its nearest-neighbour downscale to ``(h,w)`` (what the next
+    ``prop_seghead`` derives from ``previous_frame_mask``).  One kernel; the upsampled logits are never built."""
+    from ._device import require_f32, stream_ptr
+    require_f32(pred, "pred")
+    if pred.dim() != 4 or pred.shape[0] != 1:
+        raise ValueError(f"pred must be [1,N,h,w], got {tuple(pred.shape)}")
+    _, n, h, w = pred.shape
+    hf, wf = int(size[0]), int(size[1])
+    p = pred.contiguous()
+    dev = p.device
+    full = torch.empty((1, hf, wf), dtype=torch.int64, device=dev) if want_full else None
+    small = torch.empty((h, w), dtype=torch.int32, device=dev) if want_small else None
+    with torch.cuda.device(dev):
+        check(_lib.lib().manet_upsample_argmax(p.data_ptr(), n, h, w, hf, wf, full.data_ptr() if want_full else None,
+                                               small.data_ptr() if want_small else None, stream_ptr(dev)),
+              "manet_upsample_argmax")
+    return full, small
+
+
+def propagate_sequence(embedding_memory, frames, ref_frame, ref_scribble_label, prev_label_small, n_objects, dynamic_seghead,
+                       size, global_map_tmp_dic, local_map_dics, seq_name="seq", interaction_num=1, max_distance=None,
+                       keep_full=True):
+    """One direction of the propagation loop of test.py:237-259 (or :262-285 backwards), entirely on the device:
+    per frame global + local matching with both memories, the dynamic head on its parts, bilinear upsample + argmax.
+    ``embedding_memory`` ``[T,C,h,w]``; ``frames`` the frame indices in visiting order (each frame's previous frame is
+    the one visited before it, the first one's is ``ref_frame``); ``ref_scribble_label`` ``[h,w]`` int32 at embedding
+    resolution (cfg.TEST_MODE form); ``prev_label_small`` ``[h,w]`` int32 labels of ``ref_frame``.
+    Returns ``{frame: labels [1,Hf,Wf] int64}`` (empty when ``keep_full`` is False) and the last small label map."""
+    out = {}
+    prev_frame, prev_small = int(ref_frame), prev_label_small
+    ids = torch.arange(0, int(n_objects) + 1, dtype=torch.int32, device=embedding_memory.device)
+    for f in frames:
+        f = int(f)
+        g, loc = prop_matching_step(embedding_memory[ref_frame], embedding_memory[prev_frame], embedding_memory[f],
+                                    ref_scribble_label, prev_small, n_objects, 1, max_distance, global_map_tmp_dic,
+                                    local_map_dics, seq_name, f, interaction_num, ref_frame)
+        pred = dynamic_seghead.forward_parts(embedding_memory[f], g, loc, prev_small, ids).permute(1, 0, 2, 3)
+        full, prev_small = upsample_argmax(pred, size, want_full=keep_full)
+        if keep_full:
+            out[f] = full
+        prev_frame = f
+    return out, prev_small
+
+
 class MatchingSession:
     """Host-buffer propagation steps through ``manet_session_*`` (include/manet_b200.h): the caller
     fills pinned host buffers with ``[C,H,W]`` embeddings and ``[H,W]`` labels, ``step_host`` uploads

@@ -281,6 +281,16 @@ int manet_seghead_forward_parts(const void* packed, const float* emb, int64_t em
                                 void* workspace, size_t workspace_bytes, manet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Frame glue between two propagation steps (test.py:253-256 and IntVOS.py:598-599):
+ *   labels_full  [out_h,out_w] int64 = argmax_n bilinear_upsample(logits [n_objects,h,w], align_corners=True)
+ *   labels_small [h,w] int32         = nearest-downscale of labels_full to (h,w): the previous-frame labels the next
+ *                                      step's local matching and head consume
+ * Either output may be null.  The upsampled logits are never materialised.
+ * ------------------------------------------------------------------------------------------ */
+int manet_upsample_argmax(const float* logits, int n_objects, int h, int w, int out_h, int out_w,
+                          int64_t* labels_full, int32_t* labels_small, manet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Optional kernel timing for benchmarks (no reference equivalent).  After
  * manet_profile_enable(n) the launchers bracket their dominant kernels with CUDA events on the
  * launching stream (slot 0: tcgen05 global-matching kernel, 1: local window-distance kernel,

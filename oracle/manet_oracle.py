@@ -358,3 +358,12 @@ def seghead_features(cur_emb: torch.Tensor, global_map: torch.Tensor, local_map:
     to_cat_prev = prev.unsqueeze(-1).permute(2, 3, 0, 1).float()
     to_cat_l = local_map.squeeze(0).permute(2, 3, 0, 1)
     return torch.cat((to_cat_emb, to_cat_g, to_cat_l, to_cat_prev), 1)
+
+
+def upsample_argmax(pred: torch.Tensor, size) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """test.py:253-256 and IntVOS.py:598-599: ``pred`` [1,N,h,w] -> (labels [1,Hf,Wf] int64, nearest-downscaled labels
+    [h,w] int32, the upsampled logits [1,N,Hf,Wf] for tie analysis)."""
+    up = F.interpolate(pred, size=tuple(size), mode="bilinear", align_corners=True)
+    lab = torch.argmax(up, dim=1)
+    small = F.interpolate(lab.unsqueeze(0).float(), size=pred.shape[-2:], mode="nearest").int()[0, 0]
+    return lab, small, up
