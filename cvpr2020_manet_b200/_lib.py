@@ -60,6 +60,7 @@ SIGNATURES = {
     "manet_seghead_forward": (c_int, [_P, _I, _P, POINTER(_I64), _I, _I, _I, _P, _P, _SZ, _P]),
     "manet_seghead_forward_parts": (c_int, [_P, _P, _I64, _I64, _I64, _I, _P, _P, _P, _P, _I, _I, _I, _P, _P, _SZ, _P]),
     "manet_upsample_argmax": (c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "manet_rough_roi": (c_int, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "manet_profile_enable": (c_int, [_I]),
     "manet_profile_reset": (c_int, []),
     "manet_profile_read": (c_int, [_I, POINTER(c_float), _I, POINTER(c_int)]),

@@ -67,6 +67,8 @@ int seghead_forward_parts(const void*, const float*, int64_t, int64_t, int64_t, 
 
 int launch_upsample_argmax(const float*, int, int, int, int, int, int64_t*, int32_t*, cudaStream_t);
 
+int launch_rough_roi(const int32_t*, int, int, int, int, int32_t*, int*, cudaStream_t);
+
 // ---- optional kernel timing pools
 struct ProfPool { cudaEvent_t* start; cudaEvent_t* stop; int cap; int n; };
 static ProfPool g_prof[PROF_SLOTS];
@@ -332,6 +334,13 @@ int manet_upsample_argmax(const float* logits, int n_objects, int h, int w, int 
     MANET_ARCH();
     MANET_REQUIRE(logits, "upsample_argmax: null pointer");
     return launch_upsample_argmax(logits, n_objects, h, w, out_h, out_w, labels_full, labels_small, (cudaStream_t)stream);
+}
+
+int manet_rough_roi(const int32_t* labels, int batch, int H, int W, int dist, int32_t* out, int32_t* box_workspace,
+                    manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(labels && out && box_workspace, "rough_roi: null pointer");
+    return launch_rough_roi(labels, batch, H, W, dist, out, box_workspace, (cudaStream_t)stream);
 }
 
 int manet_correlation_output_shape(int C, int H, int W, int pad_size, int kernel_size, int max_displacement, int stride1,

@@ -139,6 +139,21 @@ def upsample_argmax(pred, size, want_full=True, want_small=True):
     return full, small
 
 
+def rough_ROI(ref_scribble_labels, dist=20):
+    """``rough_ROI`` of test.py:323-343 (same name, same argument): ``[b,1,h,w]`` scribble labels (-1 = unlabelled) ->
+    labels kept inside the scribbles' bounding box grown by 20, 0 outside.  Device-side box reduction, no host sync."""
+    from ._device import require_cuda, stream_ptr
+    require_cuda(ref_scribble_labels, "ref_scribble_labels")
+    b, _, h, w = ref_scribble_labels.shape
+    lab = ref_scribble_labels.reshape(b, h, w).to(torch.int32).contiguous()
+    out = torch.empty_like(lab)
+    box = torch.empty(4 * b, dtype=torch.int32, device=lab.device)
+    with torch.cuda.device(lab.device):
+        check(_lib.lib().manet_rough_roi(lab.data_ptr(), b, h, w, int(dist), out.data_ptr(), box.data_ptr(), stream_ptr(lab.device)),
+              "manet_rough_roi")
+    return out.view(b, 1, h, w).to(ref_scribble_labels.dtype)
+
+
 def propagate_sequence(embedding_memory, frames, ref_frame, ref_scribble_label, prev_label_small, n_objects, dynamic_seghead,
                        size, global_map_tmp_dic, local_map_dics, seq_name="seq", interaction_num=1, max_distance=None,
                        keep_full=True):

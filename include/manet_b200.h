@@ -290,6 +290,13 @@ int manet_seghead_forward_parts(const void* packed, const float* emb, int64_t em
 int manet_upsample_argmax(const float* logits, int n_objects, int h, int w, int out_h, int out_w,
                           int64_t* labels_full, int32_t* labels_small, manet_stream_t stream);
 
+/* rough_ROI (test.py:323-343), first-round scribbles: labels [batch,H,W] int32 -> out: inside the bounding box of the
+ * labelled pixels (label != -1) grown by `dist` (reference: 20; slice ends as in the reference, exclusive) the labels are
+ * kept, outside they become 0.  box_workspace: 4*batch int32 (receives {h_min, w_min, h_max, w_max}).  No host sync
+ * (the reference's nonzero()/min()/max() are).  An image without any labelled pixel (the reference raises) gives all 0. */
+int manet_rough_roi(const int32_t* labels, int batch, int H, int W, int dist, int32_t* out,
+                    int32_t* box_workspace, manet_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Optional kernel timing for benchmarks (no reference equivalent).  After
  * manet_profile_enable(n) the launchers bracket their dominant kernels with CUDA events on the

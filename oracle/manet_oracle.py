@@ -367,3 +367,15 @@ def upsample_argmax(pred: torch.Tensor, size) -> Tuple[torch.Tensor, torch.Tenso
     lab = torch.argmax(up, dim=1)
     small = F.interpolate(lab.unsqueeze(0).float(), size=pred.shape[-2:], mode="nearest").int()[0, 0]
     return lab, small, up
+
+
+def rough_roi(ref_scribble_labels: torch.Tensor, dist: int = 20) -> torch.Tensor:
+    """test.py:323-343 restated (``[b,1,h,w]``; bounding box of label != -1 grown by ``dist``, reference slice ends)."""
+    b, _, h, w = ref_scribble_labels.shape
+    keep = torch.zeros_like(ref_scribble_labels, dtype=torch.bool)
+    for i in range(b):
+        nz = (ref_scribble_labels[i, 0] != -1).nonzero()
+        (h_min, w_min), _ = torch.min(nz, 0)
+        (h_max, w_max), _ = torch.max(nz, 0)
+        keep[i, 0, max(int(h_min) - dist, 0):min(int(h_max) + dist, h - 1), max(int(w_min) - dist, 0):min(int(w_max) + dist, w - 1)] = True
+    return torch.where(keep, ref_scribble_labels, torch.zeros_like(ref_scribble_labels))

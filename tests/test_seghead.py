@@ -347,3 +347,42 @@ def test_gpu_propagate_sequence(golden, gpu_head):
         assert torch.equal(last_small.cpu(), prev_small)
     finally:
         cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE = saved
+
+
+def test_oracle_rough_roi_matches_reference():
+    """oracle.rough_roi against the reference's own function (test.py:323-343), parsed out of the script when the
+    reference tree is mounted (test.py as a whole imports packages this image lacks)."""
+    import ast
+    import os
+    path = "/root/reference/test.py"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not mounted")
+    tree = ast.parse(open(path).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "rough_ROI")
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    gen = torch.Generator().manual_seed(2)
+    for h, w in ((120, 214), (30, 41), (64, 64)):
+        lab = torch.full((2, 1, h, w), -1.0)
+        for b in range(2):
+            y, x = int(torch.randint(0, h, (1,), generator=gen)), int(torch.randint(0, w - 5, (1,), generator=gen))
+            lab[b, 0, y, x:x + 5] = float(b + 1)
+            lab[b, 0, min(h - 1, y + 7), min(w - 1, x + 2)] = 0.0
+        assert torch.equal(O.rough_roi(lab), ns["rough_ROI"](lab))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("h,w,dtype", [(120, 214, torch.float32), (30, 41, torch.int32), (25, 300, torch.float32)])
+def test_gpu_rough_roi(h, w, dtype):
+    from cvpr2020_manet_b200 import engine
+    gen = torch.Generator().manual_seed(h)
+    lab = torch.full((3, 1, h, w), -1, dtype=dtype)
+    for b in range(3):
+        for o in range(3):
+            y, x = int(torch.randint(0, h, (1,), generator=gen)), int(torch.randint(0, w - 4, (1,), generator=gen))
+            lab[b, 0, y, x:x + 4] = o
+    lab[2, 0, 0, 0] = 1
+    lab[2, 0, h - 1, w - 1] = 2                         # box reaches every border
+    got = engine.rough_ROI(lab.cuda())
+    assert got.dtype == dtype
+    assert torch.equal(got.cpu(), O.rough_roi(lab))
