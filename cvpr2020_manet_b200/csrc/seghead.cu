@@ -254,7 +254,15 @@ sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned*
             const float* p1 = p0 + 32 * sx;
             const uint32_t dst = in_s + (uint32_t)(buf * DW_PLANE + lane) * 4;
             if (lane < SH_WROW / 4) cp_async16(w_s + (uint32_t)(buf * 64 + lane * 4) * 4, dwW + (size_t)c * SH_WROW + lane * 4);
-            if (interior && c < C) {
+            if (interior && c < C && sx == 1) {
+                // contiguous rows (every layer but a strided first-layer input): one pointer, the second copy at +32 floats
+#pragma unroll
+                for (int r = 0; r < DW_IH; ++r) {
+                    cp_async4(dst + r * DW_PITCH * 4, p0, 4u);
+                    if (lane < DW_IW - 32) cp_async4(dst + (r * DW_PITCH + 32) * 4, p0 + 32, 4u);
+                    p0 += sy;
+                }
+            } else if (interior && c < C) {
 #pragma unroll
                 for (int r = 0; r < DW_IH; ++r) {
                     cp_async4(dst + r * DW_PITCH * 4, p0, 4u);
@@ -311,12 +319,17 @@ sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned*
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+            // window rows one ahead: the loads of row iy+1 are in flight while row iy is multiplied
+            float4 na = *reinterpret_cast<const float4*>(pl), nb = *reinterpret_cast<const float4*>(pl + 4);
+            float2 nd = *reinterpret_cast<const float2*>(pl + 8);
 #pragma unroll
             for (int iy = 0; iy < 10; ++iy) {
-                const float4 a = *reinterpret_cast<const float4*>(pl + iy * DW_PITCH);
-                const float4 b = *reinterpret_cast<const float4*>(pl + iy * DW_PITCH + 4);
-                const float2 d = *reinterpret_cast<const float2*>(pl + iy * DW_PITCH + 8);
-                const float in[10] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y};
+                const float in[10] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w, nd.x, nd.y};
+                if (iy + 1 < 10) {
+                    na = *reinterpret_cast<const float4*>(pl + (iy + 1) * DW_PITCH);
+                    nb = *reinterpret_cast<const float4*>(pl + (iy + 1) * DW_PITCH + 4);
+                    nd = *reinterpret_cast<const float2*>(pl + (iy + 1) * DW_PITCH + 8);
+                }
 #pragma unroll
                 for (int dx = 0; dx < 7; ++dx)
 #pragma unroll
@@ -328,12 +341,14 @@ sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned*
                         }
                     }
             }
-            // folded bias + ReLU -> this channel's plane of the 8-channel output block
+            // folded bias + ReLU, already multiplied by the layer's operand scale (a power of two: exact) -> this
+            // channel's plane of the 8-channel output block
+            const float bs = w[49] * scale;
 #pragma unroll
             for (int oy = 0; oy < 4; ++oy) {
                 float4 v;
-                v.x = fmaxf(acc[oy][0] + w[49], 0.f); v.y = fmaxf(acc[oy][1] + w[49], 0.f);
-                v.z = fmaxf(acc[oy][2] + w[49], 0.f); v.w = fmaxf(acc[oy][3] + w[49], 0.f);
+                v.x = fmaxf(fmaf(acc[oy][0], scale, bs), 0.f); v.y = fmaxf(fmaf(acc[oy][1], scale, bs), 0.f);
+                v.z = fmaxf(fmaf(acc[oy][2], scale, bs), 0.f); v.w = fmaxf(fmaf(acc[oy][3], scale, bs), 0.f);
                 *reinterpret_cast<float4*>(outbuf + k * (DW_TH * DW_TW) + (4 * by + oy) * DW_TW + 4 * bx) = v;
             }
             __syncwarp();                   // plane reads done before the next prefetch may overwrite; out plane visible
@@ -347,7 +362,7 @@ sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned*
                 const int row = (y & 3) * SH_TW + (px & 31);
                 float f[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) f[q] = outbuf[q * (DW_TH * DW_TW) + px] * scale;
+                for (int q = 0; q < 8; ++q) f[q] = outbuf[q * (DW_TH * DW_TW) + px];
                 uint32_t hi[4], lo[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -384,6 +399,8 @@ struct PwRing {
     __device__ void advance(int n) { if (++idx == n) { idx = 0; phase ^= 1; } }
 };
 
+// Units are walked in DESCENDING order: the depthwise kernel has just written the operand images in ascending order
+// (172 MB against 126 MB of L2), so the highest units are the ones still in L2.
 template <int MODE>
 __global__ void __launch_bounds__(PW_THREADS, 1)
 sh_pw_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ amax_in, const unsigned* __restrict__ bound,
@@ -391,6 +408,9 @@ sh_pw_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ amax
              const float* __restrict__ w5, const float* __restrict__ b5, float* __restrict__ out, unsigned* __restrict__ amax_out,
              int n_units, int nkb, int H, int W, int TX, int TY) {
     pdl_enter();
+#ifdef PW_TRACE
+    long long tr_a = 0, tr_b = 0, tr_c = 0, tr_t0 = clock64();
+#endif
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -426,10 +446,16 @@ sh_pw_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ amax
     if (warp == 0) {
         // ------------------------------------------------ producer: one stage = k-block kb of the unit (A) and of the weights (B)
         PwRing st;
-        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        for (int unit = n_units - 1 - (int)blockIdx.x; unit >= 0; unit -= (int)gridDim.x) {   // descending: see the kernel comment
             if (((unit / TX) % TY) * SH_TH >= H) continue;            // unit rows below the image (tile padding): nothing to do
             for (int kb = 0; kb < nkb; ++kb) {
+#ifdef PW_TRACE
+                long long c0 = clock64();
+#endif
                 mbar_wait(empty_b + 8 * st.idx, st.phase ^ 1);
+#ifdef PW_TRACE
+                tr_a += clock64() - c0;
+#endif
                 const uint32_t fb = full_b + 8 * st.idx;
                 const uint32_t dst = base + st.idx * PW_STAGE_BYTES;
                 if (elect_one()) {
@@ -445,13 +471,25 @@ sh_pw_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ amax
         // ------------------------------------------------ MMA issuer (whole warp runs the loop, one elected lane issues)
         constexpr uint32_t idesc = idesc_f16(SH_UNIT, SH_MID);
         PwRing st, acc;
-        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        for (int unit = n_units - 1 - (int)blockIdx.x; unit >= 0; unit -= (int)gridDim.x) {   // descending: see the kernel comment
             if (((unit / TX) % TY) * SH_TH >= H) continue;
+#ifdef PW_TRACE
+            long long c0 = clock64();
+#endif
             mbar_wait(tmem_empty + 8 * acc.idx, acc.phase ^ 1);
+#ifdef PW_TRACE
+            tr_a += clock64() - c0;
+#endif
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc.idx * SH_MID;
             for (int kb = 0; kb < nkb; ++kb) {
+#ifdef PW_TRACE
+                long long c1 = clock64();
+#endif
                 mbar_wait(full_b + 8 * st.idx, st.phase);
+#ifdef PW_TRACE
+                tr_b += clock64() - c1;
+#endif
                 tc_fence_after();
                 const uint32_t sA = base + st.idx * PW_STAGE_BYTES, sB = sA + PW_A_BYTES;
                 const uint64_t dAh = smem_desc_sw128(sA), dAl = smem_desc_sw128(sA + SH_CHUNK);
@@ -482,14 +520,20 @@ sh_pw_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ amax
         const size_t plane = (size_t)H * W;
         float vmax = 0.f;
         PwRing acc;
-        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        for (int unit = n_units - 1 - (int)blockIdx.x; unit >= 0; unit -= (int)gridDim.x) {   // descending: see the kernel comment
             const int tx = unit % TX, ty = (unit / TX) % TY, n = unit / (TX * TY);
             if (ty * SH_TH >= H) continue;
             const int py = ty * SH_TH + (row >> 5), px = tx * SH_TW + (row & 31);
             const bool valid = py < H && px < W;
             // NCHW: a warp's 32 pixels are one 128-byte run of every channel plane
             float* op = out + ((size_t)n * SH_MID + half * 128) * plane + (size_t)py * W + px;
+#ifdef PW_TRACE
+            long long c0 = clock64();
+#endif
             mbar_wait(tmem_full + 8 * acc.idx, acc.phase);
+#ifdef PW_TRACE
+            long long c1 = clock64(); tr_a += c1 - c0;
+#endif
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * SH_MID + half * 128;
             float dot = bias5;
@@ -525,6 +569,9 @@ sh_pw_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ amax
             if (lane == 0) mbar_arrive(tmem_empty + 8 * acc.idx);
             // two column halves -> two addends on a zero-initialised logit: order independent
             if (MODE == PW_FINAL && valid) atomicAdd(out + ((size_t)n * H + py) * W + px, dot);
+#ifdef PW_TRACE
+            tr_b += clock64() - c1;
+#endif
             acc.advance(2);
         }
         if (MODE == PW_RELU_NCHW) {          // the next layer's scale needs max|y| (y >= 0: bit order = value order)
@@ -533,6 +580,12 @@ sh_pw_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ amax
         }
     }
 
+#ifdef PW_TRACE
+    if ((blockIdx.x == 0 || blockIdx.x == 77) && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 9))
+        printf("pw<%d> cta %d warp %d total %lld | producer: wait_empty(a) / mma: wait_acc(a) wait_data(b) / epi: wait_full(a) work(b): a %lld b %lld\n", MODE, blockIdx.x, warp,
+               clock64() - tr_t0, tr_a, tr_b);
+    (void)tr_c;
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -550,9 +603,17 @@ sh_pw_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ amax
 // shared memory buys a third stage.  Protocol as in gm_umma2_kernel: plain bulk copies signal only the local CTA, so
 // the peer's warp 1 forwards "my stage landed" to the leader with a remote mbarrier arrive; tcgen05.commit multicasts
 // "stage free" / "accumulator ready" to both CTAs; both CTAs' epilogue warps release the accumulator on the leader.
-constexpr int PW2_STAGES = 3;
-constexpr int PW2_STAGE_BYTES = 4 * SH_CHUNK;               // A hi|lo (32 KB) + this CTA's half of B hi|lo (32 KB)
-constexpr int PW2_SMEM_TAB = PW2_STAGES * PW2_STAGE_BYTES;  // cinv[256] | bias2[256] | w5[256]
+// Weights RESIDENT: with the pair each CTA needs only half of the weight image (K = 256: 128 KB), which fits next to two
+// 32 KB stages of the unit's own operand -- so the per-unit traffic per SM drops from 384 KB (single-CTA kernel: its
+// in-kernel trace shows the MMA warp waiting for stage data a third of the time, a 96 KB stage taking ~2100 cycles =
+// ~46 B/clk per SM against 62 needed) to the unit's 128 KB.
+// Stages are 16 KB (the hi OR the lo part of one k-block of the unit) in a ring of five: the unit images come from HBM, and
+// what bounds a latency of ~3000 cycles is the bytes in flight (two 32 KB stages: 77 / 66 us per layer; five of 16 KB: below).
+constexpr int PW2_STAGES = 5;
+constexpr int PW2_STAGE_BYTES = SH_CHUNK;                   // hi or lo part of one k-block of this CTA's unit
+constexpr int PW2_B_BYTES = 4 * 2 * SH_CHUNK;               // resident: [kb][hi|lo][128 rows][128 B], up to 4 k-blocks
+constexpr int PW2_SMEM_A = PW2_B_BYTES;
+constexpr int PW2_SMEM_TAB = PW2_SMEM_A + PW2_STAGES * PW2_STAGE_BYTES;  // cinv[256] | bias2[256] | w5[256]
 constexpr int PW2_SMEM_BAR = PW2_SMEM_TAB + 3 * SH_MID * 4;
 constexpr int PW2_SMEM_TOTAL = PW2_SMEM_BAR + 256 + 1024;
 
@@ -565,18 +626,23 @@ sh_pw2_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ ama
               const float* __restrict__ w5, const float* __restrict__ b5, float* __restrict__ out, unsigned* __restrict__ amax_out,
               int n_units, int nkb, int H, int W, int TX, int TY) {
     pdl_enter();
+#ifdef PW_TRACE
+    long long tr_a = 0, tr_b = 0, tr_c = 0, tr_t0 = clock64();
+#endif
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - raw);
     float* tab = reinterpret_cast<float*>(smem + PW2_SMEM_TAB);
     const uint32_t bars = base + PW2_SMEM_BAR;
-    const uint32_t full_b = bars + 0;            // [3]  local bytes landed
-    const uint32_t empty_b = bars + 24;          // [3]  stage free (multicast commit)
-    const uint32_t peer_full = bars + 48;        // [3]  leader only: the peer's stage landed
-    const uint32_t tmem_full = bars + 72;        // [2]
-    const uint32_t tmem_empty = bars + 88;       // [2]  leader only, 16 arrivals
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + PW2_SMEM_BAR + 112);
+    const uint32_t full_b = bars + 0;            // [5]  local bytes landed
+    const uint32_t empty_b = bars + 40;          // [5]  stage free (multicast commit)
+    const uint32_t peer_full = bars + 80;        // [5]  leader only: the peer's stage landed
+    const uint32_t tmem_full = bars + 120;       // [2]
+    const uint32_t tmem_empty = bars + 136;      // [2]  leader only, 16 arrivals
+    const uint32_t b_full = bars + 152;          // resident weights landed (local)
+    const uint32_t peer_b_full = bars + 160;     // leader only: the peer's weights landed
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + PW2_SMEM_BAR + 168);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
@@ -590,6 +656,7 @@ sh_pw2_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ ama
         if (lane == 0) {
             for (int i = 0; i < PW2_STAGES; ++i) { mbar_init(full_b + 8 * i, 1); mbar_init(empty_b + 8 * i, 1); mbar_init(peer_full + 8 * i, 1); }
             for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, 2 * PW_EPI_WARPS); }
+            mbar_init(b_full, 1); mbar_init(peer_b_full, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -603,21 +670,33 @@ sh_pw2_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ ama
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ------------------------------------------------ producer (both CTAs): own unit's A, own half of the weights
+        // ------------------------------------------------ producer (both CTAs): own half of the weights once, then own unit's A
+        if (elect_one()) {
+            mbar_expect_tx(b_full, (uint32_t)nkb * 2 * SH_CHUNK);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const uint8_t* bsrc = Bimg + (size_t)kb * PW_B_BYTES + (size_t)rank * SH_CHUNK;          // rows 128*rank .. +127
+                bulk_g2s(base + (kb * 2) * SH_CHUNK, bsrc, SH_CHUNK, b_full);                             // hi
+                bulk_g2s(base + (kb * 2 + 1) * SH_CHUNK, bsrc + 2 * SH_CHUNK, SH_CHUNK, b_full);           // lo
+            }
+        }
+        __syncwarp();
         PwRing st;
-        for (int pair = cid; pair < n_pairs; pair += n_clusters) {
+        for (int pair = n_pairs - 1 - cid; pair >= 0; pair -= n_clusters) {
             if (!sh_unit_valid(2 * pair, TX, TY, H) && !sh_unit_valid(2 * pair + 1, TX, TY, H)) continue;
             const int unit = 2 * pair + (int)rank;
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int sp = 0; sp < 2 * nkb; ++sp) {               // (k-block, part) in image order: kb0.hi, kb0.lo, kb1.hi, ...
+#ifdef PW_TRACE
+                long long c0 = clock64();
+#endif
                 mbar_wait(empty_b + 8 * st.idx, st.phase ^ 1);
+#ifdef PW_TRACE
+                tr_a += clock64() - c0;
+#endif
                 const uint32_t fb = full_b + 8 * st.idx;
-                const uint32_t dst = base + st.idx * PW2_STAGE_BYTES;
+                const uint32_t dst = base + PW2_SMEM_A + st.idx * PW2_STAGE_BYTES;
                 if (elect_one()) {
                     mbar_expect_tx(fb, PW2_STAGE_BYTES);
-                    bulk_g2s(dst, Aimg + (size_t)unit * unit_bytes + (size_t)kb * PW_A_BYTES, PW_A_BYTES, fb);
-                    const uint8_t* bsrc = Bimg + (size_t)kb * PW_B_BYTES + (size_t)rank * SH_CHUNK;     // rows 128*rank .. +127
-                    bulk_g2s(dst + 2 * SH_CHUNK, bsrc, SH_CHUNK, fb);                                    // hi
-                    bulk_g2s(dst + 3 * SH_CHUNK, bsrc + 2 * SH_CHUNK, SH_CHUNK, fb);                     // lo
+                    bulk_g2s(dst, Aimg + (size_t)unit * unit_bytes + (size_t)sp * SH_CHUNK, SH_CHUNK, fb);
                 }
                 __syncwarp();
                 st.advance(PW2_STAGES);
@@ -628,22 +707,42 @@ sh_pw2_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ ama
             // -------------------------------------------- MMA issuer (leader CTA; whole warp runs the loop, one elected lane issues)
             constexpr uint32_t idesc = idesc_f16(2 * SH_UNIT, SH_MID);
             PwRing st, acc;
-            for (int pair = cid; pair < n_pairs; pair += n_clusters) {
+            mbar_wait(b_full, 0);
+            mbar_wait_cluster(peer_b_full, 0);
+            for (int pair = n_pairs - 1 - cid; pair >= 0; pair -= n_clusters) {
                 if (!sh_unit_valid(2 * pair, TX, TY, H) && !sh_unit_valid(2 * pair + 1, TX, TY, H)) continue;
+#ifdef PW_TRACE
+                long long c0 = clock64();
+#endif
                 mbar_wait_cluster(tmem_empty + 8 * acc.idx, acc.phase ^ 1);
+#ifdef PW_TRACE
+                tr_a += clock64() - c0;
+#endif
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc.idx * SH_MID;
-                for (int kb = 0; kb < nkb; ++kb) {
+                for (int sp = 0; sp < 2 * nkb; ++sp) {
+#ifdef PW_TRACE
+                    long long c1 = clock64();
+#endif
                     mbar_wait(full_b + 8 * st.idx, st.phase);
+#ifdef PW_TRACE
+                    long long c2 = clock64(); tr_b += c2 - c1;
+#endif
                     mbar_wait_cluster(peer_full + 8 * st.idx, st.phase);
+#ifdef PW_TRACE
+                    tr_c += clock64() - c2;
+#endif
                     tc_fence_after();
-                    const uint32_t sA = base + st.idx * PW2_STAGE_BYTES;
-                    const uint64_t dAh = smem_desc_sw128(sA), dAl = smem_desc_sw128(sA + SH_CHUNK);
-                    const uint64_t dBh = smem_desc_sw128(sA + 2 * SH_CHUNK), dBl = smem_desc_sw128(sA + 3 * SH_CHUNK);
+                    const int kb = sp >> 1;
+                    const uint64_t dA = smem_desc_sw128(base + PW2_SMEM_A + st.idx * PW2_STAGE_BYTES);
+                    const uint64_t dBh = smem_desc_sw128(base + (kb * 2) * SH_CHUNK), dBl = smem_desc_sw128(base + (kb * 2 + 1) * SH_CHUNK);
                     if (elect_one()) {
-                        for (int k = 0; k < 4; ++k) umma2_f16(d_tmem, dAh + 2 * k, dBh + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                        for (int k = 0; k < 4; ++k) umma2_f16(d_tmem, dAl + 2 * k, dBh + 2 * k, idesc, 1u);
-                        for (int k = 0; k < 4; ++k) umma2_f16(d_tmem, dAh + 2 * k, dBl + 2 * k, idesc, 1u);
+                        if ((sp & 1) == 0) {      // hi part: ah.wh, ah.wl
+                            for (int k4 = 0; k4 < 4; ++k4) umma2_f16(d_tmem, dA + 2 * k4, dBh + 2 * k4, idesc, (sp | k4) ? 1u : 0u);
+                            for (int k4 = 0; k4 < 4; ++k4) umma2_f16(d_tmem, dA + 2 * k4, dBl + 2 * k4, idesc, 1u);
+                        } else {                  // lo part: al.wh
+                            for (int k4 = 0; k4 < 4; ++k4) umma2_f16(d_tmem, dA + 2 * k4, dBh + 2 * k4, idesc, 1u);
+                        }
                         tc_commit2(empty_b + 8 * st.idx);
                     }
                     __syncwarp();
@@ -657,9 +756,12 @@ sh_pw2_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ ama
             // -------------------------------------------- peer: forward "my stage landed" to the leader
             const uint32_t r_peer_full = mapa_shared(peer_full, 0);
             PwRing st;
-            for (int pair = cid; pair < n_pairs; pair += n_clusters) {
+            mbar_wait(b_full, 0);
+            if (elect_one()) mbar_arrive_remote(mapa_shared(peer_b_full, 0));
+            __syncwarp();
+            for (int pair = n_pairs - 1 - cid; pair >= 0; pair -= n_clusters) {
                 if (!sh_unit_valid(2 * pair, TX, TY, H) && !sh_unit_valid(2 * pair + 1, TX, TY, H)) continue;
-                for (int kb = 0; kb < nkb; ++kb) {
+                for (int sp = 0; sp < 2 * nkb; ++sp) {
                     mbar_wait(full_b + 8 * st.idx, st.phase);
                     if (elect_one()) mbar_arrive_remote(r_peer_full + 8 * st.idx);
                     __syncwarp();
@@ -681,14 +783,20 @@ sh_pw2_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ ama
         const uint32_t r_tmem_empty = mapa_shared(tmem_empty, 0);
         float vmax = 0.f;
         PwRing acc;
-        for (int pair = cid; pair < n_pairs; pair += n_clusters) {
+        for (int pair = n_pairs - 1 - cid; pair >= 0; pair -= n_clusters) {
             if (!sh_unit_valid(2 * pair, TX, TY, H) && !sh_unit_valid(2 * pair + 1, TX, TY, H)) continue;
             const int unit = 2 * pair + (int)rank;
             const int tx = unit % TX, ty = (unit / TX) % TY, n = unit / (TX * TY);
             const int py = ty * SH_TH + (row >> 5), px = tx * SH_TW + (row & 31);
             const bool valid = py < H && px < W;
             float* op = out + ((size_t)n * SH_MID + half * 128) * plane + (size_t)py * W + px;
+#ifdef PW_TRACE
+            long long c0 = clock64();
+#endif
             mbar_wait(tmem_full + 8 * acc.idx, acc.phase);
+#ifdef PW_TRACE
+            long long c1 = clock64(); tr_a += c1 - c0;
+#endif
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * SH_MID + half * 128;
             float dot = bias5;
@@ -723,6 +831,9 @@ sh_pw2_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ ama
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(r_tmem_empty + 8 * acc.idx);
             if (MODE == PW_FINAL && valid) atomicAdd(out + ((size_t)n * H + py) * W + px, dot);
+#ifdef PW_TRACE
+            tr_b += clock64() - c1;
+#endif
             acc.advance(2);
         }
         if (MODE == PW_RELU_NCHW) {
@@ -731,6 +842,11 @@ sh_pw2_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ ama
         }
     }
 
+#ifdef PW_TRACE
+    if ((blockIdx.x == 0 || blockIdx.x == 1 || blockIdx.x == 76) && lane == 0 && (warp == 0 || warp == 1 || warp == 2))
+        printf("pw2<%d> cta %d warp %d total %lld | producer: wait_empty(a) / mma: wait_acc(a) wait_own(b) wait_peer(c) / epi: wait_full(a) work(b): a %lld b %lld c %lld\n",
+               MODE, blockIdx.x, warp, clock64() - tr_t0, tr_a, tr_b, tr_c);
+#endif
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                           // nobody leaves while the pair may still touch its smem / TMEM
