@@ -594,6 +594,217 @@ sh_pw_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ amax
     }
 }
 
+// ---------------------------------------------------------------------------------------------- 1x1 conv GEMM, weight stages multicast
+// The single-CTA kernel above moves (384 KB of operands + 128 KB of activations) per unit between L2 and the SM, and its time
+// is exactly that volume at ~51 B/clk per SM (in-kernel trace, profiles/README.md); two thirds of the operand bytes are the
+// weight stages, identical for every CTA.  Here the CTAs of a cluster (2 or 4) each fetch 1/CL of every weight stage and
+// MULTICAST it into all CTAs' shared memory: L2 serves the weights once per cluster.  MMAs stay cta_group::1 and the data
+// path has no forwarding hop; the only coupling is the stage-free barrier, which collects one multicast tcgen05.commit
+// from every CTA of the cluster (a stage is rewritten in all of them at once).  Clusters advance in lock step, so every
+// CTA runs the same number of rounds; CTAs without a unit in the last round take part with their weight share only.
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mcast(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(PW_THREADS, 1)
+sh_pwm_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ amax_in, const unsigned* __restrict__ bound,
+              const uint8_t* __restrict__ Bimg, const float* __restrict__ cinv, const float* __restrict__ bias2,
+              const float* __restrict__ w5, const float* __restrict__ b5, float* __restrict__ out, unsigned* __restrict__ amax_out,
+              int n_valid, int nkb, int H, int W, int TX, int TY, int TYV) {
+    pdl_enter();
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    float* tab = reinterpret_cast<float*>(smem + PW_SMEM_TAB);
+    const uint32_t bars = base + PW_SMEM_BAR;
+    const uint32_t full_b = bars + 0;          // [2]  1 arrival + own A bytes + the whole weight stage (CL multicast shares)
+    const uint32_t empty_b = bars + 16;        // [2]  CL arrivals: every CTA's MMA commit
+    const uint32_t tmem_full = bars + 32;      // [2]
+    const uint32_t tmem_empty = bars + 48;     // [2]
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + PW_SMEM_BAR + 64);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank(), CL = cluster_nctarank();
+    const uint16_t mask = (uint16_t)((1u << CL) - 1u);
+    const uint32_t share = PW_B_BYTES / CL;
+    const size_t unit_bytes = (size_t)nkb * PW_A_BYTES;
+    const int rounds = (n_valid + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    for (int i = threadIdx.x; i < SH_MID; i += PW_THREADS) {
+        tab[i] = cinv[i]; tab[SH_MID + i] = bias2[i]; tab[2 * SH_MID + i] = (MODE == PW_FINAL) ? w5[i] : 0.f;
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < PW_STAGES; ++i) { mbar_init(full_b + 8 * i, 1); mbar_init(empty_b + 8 * i, CL); }
+            for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, PW_EPI_WARPS); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                         // every CTA's barriers exist before any multicast lands
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // round i of this CTA: valid-unit index (descending, freshest operand images first) -> unit, or -1
+    auto unit_of = [&](int i) -> int {
+        const int u = n_valid - 1 - (i * (int)gridDim.x + (int)blockIdx.x);
+        if (u < 0) return -1;
+        const int tx = u % TX, tyv = (u / TX) % TYV, n = u / (TX * TYV);
+        return (n * TY + tyv) * TX + tx;
+    };
+
+    if (warp == 0) {
+        // ------------------------------------------------ producer: own unit's A stage, 1/CL of the weight stage for everybody
+        PwRing st;
+        for (int i = 0; i < rounds; ++i) {
+            const int unit = unit_of(i);
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait_cluster(empty_b + 8 * st.idx, st.phase ^ 1);           // free in ALL CTAs of the cluster
+                const uint32_t fb = full_b + 8 * st.idx;
+                const uint32_t dst = base + st.idx * PW_STAGE_BYTES;
+                if (elect_one()) {
+                    mbar_expect_tx(fb, (unit >= 0 ? PW_A_BYTES : 0) + PW_B_BYTES);
+                    if (unit >= 0) bulk_g2s(dst, Aimg + (size_t)unit * unit_bytes + (size_t)kb * PW_A_BYTES, PW_A_BYTES, fb);
+                    bulk_g2s_mcast(dst + PW_A_BYTES + rank * share, Bimg + (size_t)kb * PW_B_BYTES + (size_t)rank * share, share, fb, mask);
+                }
+                __syncwarp();
+                st.advance(PW_STAGES);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = idesc_f16(SH_UNIT, SH_MID);
+        PwRing st, acc;
+        for (int i = 0; i < rounds; ++i) {
+            mbar_wait(tmem_empty + 8 * acc.idx, acc.phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc.idx * SH_MID;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(full_b + 8 * st.idx, st.phase);
+                tc_fence_after();
+                const uint32_t sA = base + st.idx * PW_STAGE_BYTES, sB = sA + PW_A_BYTES;
+                const uint64_t dAh = smem_desc_sw128(sA), dAl = smem_desc_sw128(sA + SH_CHUNK);
+                const uint64_t dBh = smem_desc_sw128(sB), dBl = smem_desc_sw128(sB + 2 * SH_CHUNK);
+                if (elect_one()) {
+                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, dAh + 2 * k, dBh + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, dAl + 2 * k, dBh + 2 * k, idesc, 1u);
+                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, dAh + 2 * k, dBl + 2 * k, idesc, 1u);
+                    tc_commit_mcast(empty_b + 8 * st.idx, mask);
+                }
+                __syncwarp();
+                st.advance(PW_STAGES);
+            }
+            if (elect_one()) tc_commit(tmem_full + 8 * acc.idx);
+            __syncwarp();
+            acc.advance(2);
+        }
+    } else {
+        // ------------------------------------------------ epilogue: warps 2..9, two per TMEM lane quarter (128 columns each)
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = quarter * 32 + lane;
+        const float4* cv4 = reinterpret_cast<const float4*>(tab + half * 128);
+        const float4* bv4 = reinterpret_cast<const float4*>(tab + SH_MID + half * 128);
+        const float4* wv4 = reinterpret_cast<const float4*>(tab + 2 * SH_MID + half * 128);
+        const float bias5 = (MODE == PW_FINAL && half == 0) ? __ldg(b5) : 0.f;
+        const float ri = __uint_as_float((254u - sh_layer_scale_exp(amax_in, bound)) << 23);     // 1 / layer scale
+        const size_t plane = (size_t)H * W;
+        float vmax = 0.f;
+        PwRing acc;
+        for (int i = 0; i < rounds; ++i) {
+            const int unit = unit_of(i);
+            const int tx = unit % TX, ty = (unit / TX) % TY, n = unit / (TX * TY);
+            const int py = ty * SH_TH + (row >> 5), px = tx * SH_TW + (row & 31);
+            const bool valid = unit >= 0 && py < H && px < W;
+            float* op = out + ((size_t)n * SH_MID + half * 128) * plane + (size_t)py * W + px;
+            mbar_wait(tmem_full + 8 * acc.idx, acc.phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * SH_MID + half * 128;
+            float dot = bias5;
+            uint32_t r[2][32];
+            tmem_ld32(taddr, r[0]);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                tmem_ld_wait_dep(r[ch & 1]);
+                if (ch + 1 < 4) tmem_ld32(taddr + (ch + 1) * 32, r[(ch + 1) & 1]);
+#pragma unroll
+                for (int i2 = 0; i2 < 8; ++i2) {
+                    const float4 cv = cv4[ch * 8 + i2], bv = bv4[ch * 8 + i2];
+                    const uint32_t* q = r[ch & 1] + 4 * i2;
+                    float4 v;
+                    v.x = fmaxf(fmaf(__uint_as_float(q[0]) * ri, cv.x, bv.x), 0.f);
+                    v.y = fmaxf(fmaf(__uint_as_float(q[1]) * ri, cv.y, bv.y), 0.f);
+                    v.z = fmaxf(fmaf(__uint_as_float(q[2]) * ri, cv.z, bv.z), 0.f);
+                    v.w = fmaxf(fmaf(__uint_as_float(q[3]) * ri, cv.w, bv.w), 0.f);
+                    if (MODE == PW_RELU_NCHW) {
+                        if (valid) {
+                            float* o = op + (size_t)(ch * 32 + i2 * 4) * plane;
+                            o[0] = v.x; o[plane] = v.y; o[2 * plane] = v.z; o[3 * plane] = v.w;
+                            vmax = fmaxf(fmaxf(vmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+                        }
+                    } else {
+                        const float4 wv = wv4[ch * 8 + i2];
+                        dot = fmaf(v.x, wv.x, dot); dot = fmaf(v.y, wv.y, dot); dot = fmaf(v.z, wv.z, dot); dot = fmaf(v.w, wv.w, dot);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + 8 * acc.idx);
+            if (MODE == PW_FINAL && valid) atomicAdd(out + ((size_t)n * H + py) * W + px, dot);
+            acc.advance(2);
+        }
+        if (MODE == PW_RELU_NCHW) {
+            const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
+            if (lane == 0 && wm) atomicMax(amax_out, wm);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                         // nobody leaves while a peer may still multicast into its shared memory
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+template <int MODE>
+static cudaError_t launch_pwm(int cl, int sms, cudaStream_t stream, const uint8_t* aimg, const unsigned* amax_in, const unsigned* bound,
+                              const uint8_t* bimg, const float* cinv, const float* bias2, const float* w5, const float* b5, float* out,
+                              unsigned* amax_out, int n_valid, int nkb, int H, int W, int TX, int TY, int TYV) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(PW_THREADS); cfg.dynamicSmemBytes = PW_SMEM_TOTAL; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    // persistent: as many clusters as can be resident at once
+    static int max_clusters[9] = {0};
+    if (!max_clusters[cl]) {
+        cfg.gridDim = dim3((sms / cl) * cl);
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, sh_pwm_kernel<MODE>, &cfg) != cudaSuccess || nc < 1) { cudaGetLastError(); nc = sms / cl; }
+        max_clusters[cl] = nc < sms / cl ? nc : sms / cl;
+    }
+    int clusters = max_clusters[cl];
+    if (clusters * cl > n_valid) clusters = (n_valid + cl - 1) / cl;
+    cfg.gridDim = dim3(clusters * cl);
+    return cudaLaunchKernelEx(&cfg, sh_pwm_kernel<MODE>, aimg, amax_in, bound, bimg, cinv, bias2, w5, b5, out, amax_out, n_valid, nkb, H, W,
+                              TX, TY, TYV);
+}
+
 // ---------------------------------------------------------------------------------------------- 1x1 conv GEMM on CTA pairs
 // (opt-in variant, MANET_SH_PW_PAIR=1; parity-tested, measured slightly slower than the single-CTA kernel)
 // Same GEMM with cta_group::2: one tcgen05.mma covers TWO units (M = 256, one unit per CTA of the pair) x 256 output
@@ -908,6 +1119,8 @@ static int launch_seghead_forward(const void* packed, int in_dim, ShSource src, 
         cudaFuncSetAttribute(sh_pw_kernel<PW_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_TOTAL);
         cudaFuncSetAttribute(sh_pw2_kernel<PW_RELU_NCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW2_SMEM_TOTAL);
         cudaFuncSetAttribute(sh_pw2_kernel<PW_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW2_SMEM_TOTAL);
+        cudaFuncSetAttribute(sh_pwm_kernel<PW_RELU_NCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_TOTAL);
+        cudaFuncSetAttribute(sh_pwm_kernel<PW_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_TOTAL);
         cudaFuncSetAttribute(sh_dw_kernel<SH_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
         cudaFuncSetAttribute(sh_dw_kernel<SH_IN_PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
         attr_done = true;
@@ -959,6 +1172,15 @@ static int launch_seghead_forward(const void* packed, int in_dim, ShSource src, 
         // (480p, N = 6): 64 / 51 us (single) against 72 / 54 us (pair) per layer / last layer -- halving the weight traffic
         // does not help, so operand supply is not what holds the tensor pipe at ~55 % (ncu: 72 % active in the last layer).
         static const bool single = [] { const char* e = getenv("MANET_SH_PW_PAIR"); return !(e && e[0] == '1'); }();
+        static const int mcast = [] { const char* e = getenv("MANET_SH_PW_CLUSTER"); const int v = e ? atoi(e) : 0; return (v == 2 || v == 4) ? v : 0; }();
+        if (mcast) {
+            const int TYV = (int)ceil_div64(H, SH_TH), n_valid = N * TYV * TX;
+            cudaError_t le = (i + 1 < SH_LAYERS)
+                ? launch_pwm<PW_RELU_NCHW>(mcast, sms, stream, aimg, amax + i, bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, y, amax + i + 1, n_valid, nkb, H, W, TX, TY, TYV)
+                : launch_pwm<PW_FINAL>(mcast, sms, stream, aimg, amax + i, bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, logits, amax + 7, n_valid, nkb, H, W, TX, TY, TYV);
+            if (le != cudaSuccess) { set_error("seghead: multicast GEMM launch: %s", cudaGetErrorString(le)); return (int)le; }
+            continue;
+        }
         const int grid2 = (units < sms ? units : sms) & ~1;
         if (single || grid2 < 2) {
             if (i + 1 < SH_LAYERS)

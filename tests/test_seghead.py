@@ -239,9 +239,10 @@ def test_gpu_propagation_sequence_with_head(golden, gpu_head):
 
 
 @pytest.mark.gpu
-def test_gpu_seghead_pair_gemm_variant(golden):
-    """The opt-in CTA-pair (cta_group::2) 1x1-conv kernel (MANET_SH_PW_PAIR=1, read once per process) gives the same
-    logits as the default kernel: run in a subprocess so the switch takes effect."""
+def test_gpu_seghead_gemm_variants(golden):
+    """The opt-in 1x1-conv kernels -- CTA pairs (cta_group::2, MANET_SH_PW_PAIR=1) and weight stages multicast inside a
+    cluster of 2 or 4 (MANET_SH_PW_CLUSTER) -- give the same logits as the default kernel.  The switches are read once
+    per process, so each variant runs in a subprocess."""
     import os
     import subprocess
     import sys
@@ -255,14 +256,17 @@ def test_gpu_seghead_pair_gemm_variant(golden):
         "x = torch.randn(3, 103, 37, 70, generator=torch.Generator().manual_seed(1)).cuda()\n"
         "np.save(sys.argv[1], head(x).cpu().numpy())\n")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    outs = []
-    for flag in ("0", "1"):
-        path = os.path.join(root, "gpurun_out", f"_pair_variant_{flag}.npy")
+    outs = {}
+    for name, env_add in (("default", {}), ("pair", {"MANET_SH_PW_PAIR": "1"}), ("mcast2", {"MANET_SH_PW_CLUSTER": "2"}),
+                          ("mcast4", {"MANET_SH_PW_CLUSTER": "4"})):
+        path = os.path.join(root, "gpurun_out", f"_gemm_variant_{name}.npy")
         os.makedirs(os.path.dirname(path), exist_ok=True)
-        env = dict(os.environ, MANET_SH_PW_PAIR=flag)
+        env = {k: v for k, v in os.environ.items() if k not in ("MANET_SH_PW_PAIR", "MANET_SH_PW_CLUSTER")}
+        env.update(env_add)
         subprocess.run([sys.executable, "-c", code, path], check=True, cwd=root, env=env, timeout=300)
-        outs.append(np.load(path))
-    assert logit_err(outs[1], outs[0]) <= 2e-6
+        outs[name] = np.load(path)
+    for name in ("pair", "mcast2", "mcast4"):
+        assert logit_err(outs[name], outs["default"]) <= 2e-6, name
 
 
 # ------------------------------------------------------------------------------------------------ frame glue (8f-3)
