@@ -31,7 +31,9 @@
 //   4x4 blocks (6.25 instead of 10 loaded floats per output), warp-level work items            238  57 % of issued instructions not FFMA
 //   one-pointer cp.async staging, taps through shared memory                                   162  (this file) issue 67 %, FMA pipe 44 %
 //   same with channel pairs on FFMA2 (7 warps per SM fit)                                      178  stall "wait": too few warps
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "umma_ptx.cuh"
@@ -42,6 +44,7 @@ constexpr int SH_MID = 256;              // cfg.MODEL_HEAD_EMBEDDING_DIM (config
 constexpr int SH_IN_PAD = 128;           // layer-1 channels (MODEL_SEMANTIC_EMBEDDING_DIM + 3 = 103) padded to 2 K blocks
 constexpr int SH_TH = 4, SH_TW = 32;     // pixel tile of one unit (a warp's 32 accumulator rows = one 128-byte run of a channel plane)
 constexpr int SH_UNIT = SH_TH * SH_TW;   // 128 rows = UMMA M
+constexpr int SH_XOFF = 0;               // (experiment knob: unit columns start at 32*tx - SH_XOFF)
 constexpr int SH_CHUNK = 16384;          // 128 rows x 128 B: one (k-block, part) of a unit
 constexpr int SH_LAYERS = 4;
 constexpr int SH_WROW = 52;              // per channel: 49 taps, bias, 2 pad (13 x 16 bytes)
@@ -197,12 +200,15 @@ sh_extras_kernel(const float* __restrict__ gmap, const float* __restrict__ lmap,
 // outputs from a 10x10 window (128-bit shared-memory loads): 6.25 loaded floats per output.  With 2x4 blocks
 // (10 per output) the kernel was shared-memory bound: 130 wavefronts against 98 FMA-issue cycles per channel.
 constexpr int DW_TH = 16, DW_TW = 32;              // warp tile = four units stacked vertically
-constexpr int DW_IH = DW_TH + 6, DW_IW = DW_TW + 6;
-constexpr int DW_PITCH = 40;                       // floats per staged row (16-byte aligned 128-bit loads)
+constexpr int DW_HALO_L = 4;                       // staged columns start 4 (not 3) left of the tile: a TMA box must start on a 16-byte multiple
+constexpr int DW_IH = DW_TH + 6, DW_IW = DW_TW + 8;
+constexpr int DW_PITCH = 40;                       // floats per staged row = DW_IW (16-byte aligned 128-bit loads)
 constexpr int DW_PLANE = DW_IH * DW_PITCH;         // 880 floats per channel plane
 constexpr int DW_WARPS = 4;
-constexpr int DW_WARP_FLOATS = 2 * DW_PLANE + 8 * DW_TH * DW_TW + 2 * 64;   // double-buffered input plane, 8 output planes, double-buffered taps
-constexpr int DW_SMEM = DW_WARPS * DW_WARP_FLOATS * 4;              // 94,720 B: two CTAs per SM
+constexpr int DW_PLANE_PAD = 896;                  // plane slot: 3584 B, a multiple of the 128-byte alignment a TMA box wants
+// per warp: double-buffered input plane, 8 output planes, double-buffered taps, two mbarriers (padded to 128 B multiples)
+constexpr int DW_WARP_FLOATS = 2 * DW_PLANE_PAD + 8 * DW_TH * DW_TW + 2 * 64 + 32;
+constexpr int DW_SMEM = DW_WARPS * DW_WARP_FLOATS * 4 + 128;        // 96,896 B: two CTAs per SM
 
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -213,18 +219,39 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
-template <int CP>
+// one TMA box = the 22 x 40 window of one channel plane (out-of-image elements arrive as zeros)
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, uint64_t map_addr, int x, int y, int z, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map_addr), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+
+// TMA = true (layers 2-4, whose input is this library's own [N,256,H,Wp] buffer with a 16-byte-multiple row pitch): the
+// window and the taps of a channel are fetched by ONE elected lane with a tensor-map box copy + a bulk copy that complete on
+// a per-warp mbarrier -- no per-row copies, address arithmetic or border predicates in the instruction stream.
+// TMA = false: per-row cp.async copies (any strides; the first layer reads the caller's tensors in place).
+template <int CP, bool TMA>
 __global__ void __launch_bounds__(DW_WARPS * 32, 2)
 sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned* __restrict__ amax_in,
              const unsigned* __restrict__ bound, uint8_t* __restrict__ Aimg, unsigned* __restrict__ counter,
-             int N, int H, int W, int TX2, int TY16) {
+             int N, int H, int W, int TX2, int TY16, const CUtensorMap* __restrict__ tmap) {
     pdl_enter();
-    extern __shared__ __align__(16) float dw_smem[];
+    extern __shared__ __align__(128) float dw_smem_raw[];
+    float* dw_smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dw_smem_raw) + 127) & ~(uintptr_t)127);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* inbuf = dw_smem + warp * DW_WARP_FLOATS;
-    float* outbuf = inbuf + 2 * DW_PLANE;
+    float* outbuf = inbuf + 2 * DW_PLANE_PAD;
     const float* wbuf = outbuf + 8 * DW_TH * DW_TW;
     const uint32_t in_s = smem_u32(inbuf), w_s = smem_u32(wbuf);
+    const uint32_t bar_s = w_s + 2 * 64 * 4;                       // two mbarriers, one per buffer
+    uint32_t ph = 0;                                               // their phase bits
+    const uint64_t tmap_addr = reinterpret_cast<uint64_t>(tmap);   // the tensor map lives in global memory (workspace)
+    if (TMA) {
+        if (lane == 0) {
+            mbar_init(bar_s, 1); mbar_init(bar_s + 8, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
     const int by = lane >> 3, bx = lane & 7;                       // this lane's 4x4 output block
     const float scale = __uint_as_float(sh_layer_scale_exp(amax_in, bound) << 23);
     constexpr size_t UNIT_BYTES = (size_t)(CP / 64) * 2 * SH_CHUNK;
@@ -239,7 +266,7 @@ sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned*
         // chunk fastest: the warps of an SM share a tile's input neighbourhood in L1/L2
         const int cid = item % CHUNKS, tile = item / CHUNKS;
         const int tx2 = tile % TX2, ty = (tile / TX2) % TY16, n = tile / (TX2 * TY16);
-        const int y0 = ty * DW_TH - 3, x0 = tx2 * DW_TW - 3;
+        const int y0 = ty * DW_TH - 3, x0 = tx2 * DW_TW - SH_XOFF - DW_HALO_L;
         uint8_t* img_tile = Aimg + (size_t)(((size_t)n * TY16 + ty) * 4 * TX2 + tx2) * UNIT_BYTES;   // unit (n, 4*ty + uy, tx2)
 
         // stage channel c: its 22 x 38 input window (zero outside the image / beyond the real channels: src-size 0 =
@@ -247,12 +274,22 @@ sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned*
         const bool interior = y0 >= 0 && y0 + DW_IH <= H && x0 >= 0 && x0 + DW_IW <= W;
         const unsigned rlo = (unsigned)max(0, -y0), rcnt = (unsigned)max(0, min(DW_IH, H - y0) - (int)rlo);
         auto issue = [&](int c, int buf) {
+            if (TMA) {
+                if (elect_one()) {
+                    const uint32_t bar = bar_s + 8 * buf;
+                    mbar_expect_tx(bar, DW_PLANE * 4 + SH_WROW * 4);
+                    tma_load_3d(in_s + (uint32_t)(buf * DW_PLANE_PAD) * 4, tmap_addr, x0, y0, n * CP + c, bar);
+                    bulk_g2s(w_s + (uint32_t)(buf * 64) * 4, dwW + (size_t)c * SH_WROW, SH_WROW * 4, bar);
+                }
+                __syncwarp();
+                return;
+            }
             const float* base; int64_t sy, sx;
             if (c < src.c0) { base = src.x + n * src.sn + c * src.sc; sy = src.sh; sx = src.sw; }
             else { base = src.extras + ((size_t)n * 3 + (c - src.c0)) * H * W; sy = W; sx = 1; }
             const float* p0 = base + (int64_t)y0 * sy + (int64_t)(x0 + lane) * sx;
             const float* p1 = p0 + 32 * sx;
-            const uint32_t dst = in_s + (uint32_t)(buf * DW_PLANE + lane) * 4;
+            const uint32_t dst = in_s + (uint32_t)(buf * DW_PLANE_PAD + lane) * 4;
             if (lane < SH_WROW / 4) cp_async16(w_s + (uint32_t)(buf * 64 + lane * 4) * 4, dwW + (size_t)c * SH_WROW + lane * 4);
             if (interior && c < C && sx == 1) {
                 // contiguous rows (every layer but a strided first-layer input): one pointer, the second copy at +32 floats
@@ -301,8 +338,14 @@ sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned*
 #pragma unroll 1
         for (int k = 0; k < 8; ++k) {
             const int c = cid * 8 + k, buf = k & 1;
-            if (k + 1 < 8) issue(c + 1, buf ^ 1); else cp_async_commit();
-            cp_async_wait<1>();
+            if (TMA) {
+                if (k + 1 < 8) issue(c + 1, buf ^ 1);
+                mbar_wait(bar_s + 8 * buf, (ph >> buf) & 1u);
+                ph ^= 1u << buf;
+            } else {
+                if (k + 1 < 8) issue(c + 1, buf ^ 1); else cp_async_commit();
+                cp_async_wait<1>();
+            }
             __syncwarp();
             float w[SH_WROW];
             {
@@ -313,22 +356,23 @@ sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned*
                     w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
                 }
             }
-            const float* pl = inbuf + buf * DW_PLANE + (4 * by) * DW_PITCH + 4 * bx;
+            const float* pl = inbuf + buf * DW_PLANE_PAD + (4 * by) * DW_PITCH + 4 * bx;
             float acc[4][4];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-            // window rows one ahead: the loads of row iy+1 are in flight while row iy is multiplied
+            // window rows one ahead: the loads of row iy+1 are in flight while row iy is multiplied.  The staged row starts
+            // one column left of the 3-pixel halo, so a lane reads three aligned float4 and uses elements 1..10.
             float4 na = *reinterpret_cast<const float4*>(pl), nb = *reinterpret_cast<const float4*>(pl + 4);
-            float2 nd = *reinterpret_cast<const float2*>(pl + 8);
+            float4 nd = *reinterpret_cast<const float4*>(pl + 8);
 #pragma unroll
             for (int iy = 0; iy < 10; ++iy) {
-                const float in[10] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w, nd.x, nd.y};
+                const float in[10] = {na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w, nd.x, nd.y, nd.z};
                 if (iy + 1 < 10) {
                     na = *reinterpret_cast<const float4*>(pl + (iy + 1) * DW_PITCH);
                     nb = *reinterpret_cast<const float4*>(pl + (iy + 1) * DW_PITCH + 4);
-                    nd = *reinterpret_cast<const float2*>(pl + (iy + 1) * DW_PITCH + 8);
+                    nd = *reinterpret_cast<const float4*>(pl + (iy + 1) * DW_PITCH + 8);
                 }
 #pragma unroll
                 for (int dx = 0; dx < 7; ++dx)
@@ -406,7 +450,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
 sh_pw_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ amax_in, const unsigned* __restrict__ bound,
              const uint8_t* __restrict__ Bimg, const float* __restrict__ cinv, const float* __restrict__ bias2,
              const float* __restrict__ w5, const float* __restrict__ b5, float* __restrict__ out, unsigned* __restrict__ amax_out,
-             int n_units, int nkb, int H, int W, int TX, int TY) {
+             int n_units, int nkb, int H, int W, int TX, int TY, int ldw) {
     pdl_enter();
 #ifdef PW_TRACE
     long long tr_a = 0, tr_b = 0, tr_c = 0, tr_t0 = clock64();
@@ -517,16 +561,16 @@ sh_pw_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ amax
         const float4* wv4 = reinterpret_cast<const float4*>(tab + 2 * SH_MID + half * 128);
         const float bias5 = (MODE == PW_FINAL && half == 0) ? __ldg(b5) : 0.f;
         const float ri = __uint_as_float((254u - sh_layer_scale_exp(amax_in, bound)) << 23);     // 1 / layer scale
-        const size_t plane = (size_t)H * W;
+        const size_t plane = (size_t)H * ldw;
         float vmax = 0.f;
         PwRing acc;
         for (int unit = n_units - 1 - (int)blockIdx.x; unit >= 0; unit -= (int)gridDim.x) {   // descending: see the kernel comment
             const int tx = unit % TX, ty = (unit / TX) % TY, n = unit / (TX * TY);
             if (ty * SH_TH >= H) continue;
-            const int py = ty * SH_TH + (row >> 5), px = tx * SH_TW + (row & 31);
-            const bool valid = py < H && px < W;
+            const int py = ty * SH_TH + (row >> 5), px = tx * SH_TW - SH_XOFF + (row & 31);
+            const bool valid = py < H && px >= 0 && px < W;
             // NCHW: a warp's 32 pixels are one 128-byte run of every channel plane
-            float* op = out + ((size_t)n * SH_MID + half * 128) * plane + (size_t)py * W + px;
+            float* op = out + ((size_t)n * SH_MID + half * 128) * plane + (size_t)py * ldw + px;
 #ifdef PW_TRACE
             long long c0 = clock64();
 #endif
@@ -617,7 +661,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
 sh_pwm_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ amax_in, const unsigned* __restrict__ bound,
               const uint8_t* __restrict__ Bimg, const float* __restrict__ cinv, const float* __restrict__ bias2,
               const float* __restrict__ w5, const float* __restrict__ b5, float* __restrict__ out, unsigned* __restrict__ amax_out,
-              int n_valid, int nkb, int H, int W, int TX, int TY, int TYV) {
+              int n_valid, int nkb, int H, int W, int TX, int TY, int TYV, int ldw) {
     pdl_enter();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -719,15 +763,15 @@ sh_pwm_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ ama
         const float4* wv4 = reinterpret_cast<const float4*>(tab + 2 * SH_MID + half * 128);
         const float bias5 = (MODE == PW_FINAL && half == 0) ? __ldg(b5) : 0.f;
         const float ri = __uint_as_float((254u - sh_layer_scale_exp(amax_in, bound)) << 23);     // 1 / layer scale
-        const size_t plane = (size_t)H * W;
+        const size_t plane = (size_t)H * ldw;
         float vmax = 0.f;
         PwRing acc;
         for (int i = 0; i < rounds; ++i) {
             const int unit = unit_of(i);
             const int tx = unit % TX, ty = (unit / TX) % TY, n = unit / (TX * TY);
-            const int py = ty * SH_TH + (row >> 5), px = tx * SH_TW + (row & 31);
-            const bool valid = unit >= 0 && py < H && px < W;
-            float* op = out + ((size_t)n * SH_MID + half * 128) * plane + (size_t)py * W + px;
+            const int py = ty * SH_TH + (row >> 5), px = tx * SH_TW - SH_XOFF + (row & 31);
+            const bool valid = unit >= 0 && py < H && px >= 0 && px < W;
+            float* op = out + ((size_t)n * SH_MID + half * 128) * plane + (size_t)py * ldw + px;
             mbar_wait(tmem_full + 8 * acc.idx, acc.phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * SH_MID + half * 128;
@@ -783,7 +827,7 @@ sh_pwm_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ ama
 template <int MODE>
 static cudaError_t launch_pwm(int cl, int sms, cudaStream_t stream, const uint8_t* aimg, const unsigned* amax_in, const unsigned* bound,
                               const uint8_t* bimg, const float* cinv, const float* bias2, const float* w5, const float* b5, float* out,
-                              unsigned* amax_out, int n_valid, int nkb, int H, int W, int TX, int TY, int TYV) {
+                              unsigned* amax_out, int n_valid, int nkb, int H, int W, int TX, int TY, int TYV, int ldw) {
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(PW_THREADS); cfg.dynamicSmemBytes = PW_SMEM_TOTAL; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -802,7 +846,7 @@ static cudaError_t launch_pwm(int cl, int sms, cudaStream_t stream, const uint8_
     if (clusters * cl > n_valid) clusters = (n_valid + cl - 1) / cl;
     cfg.gridDim = dim3(clusters * cl);
     return cudaLaunchKernelEx(&cfg, sh_pwm_kernel<MODE>, aimg, amax_in, bound, bimg, cinv, bias2, w5, b5, out, amax_out, n_valid, nkb, H, W,
-                              TX, TY, TYV);
+                              TX, TY, TYV, ldw);
 }
 
 // ---------------------------------------------------------------------------------------------- 1x1 conv GEMM on CTA pairs
@@ -835,7 +879,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PW_THREADS, 1)
 sh_pw2_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ amax_in, const unsigned* __restrict__ bound,
               const uint8_t* __restrict__ Bimg, const float* __restrict__ cinv, const float* __restrict__ bias2,
               const float* __restrict__ w5, const float* __restrict__ b5, float* __restrict__ out, unsigned* __restrict__ amax_out,
-              int n_units, int nkb, int H, int W, int TX, int TY) {
+              int n_units, int nkb, int H, int W, int TX, int TY, int ldw) {
     pdl_enter();
 #ifdef PW_TRACE
     long long tr_a = 0, tr_b = 0, tr_c = 0, tr_t0 = clock64();
@@ -990,7 +1034,7 @@ sh_pw2_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ ama
         const float4* wv4 = reinterpret_cast<const float4*>(tab + 2 * SH_MID + half * 128);
         const float bias5 = (MODE == PW_FINAL && half == 0) ? __ldg(b5) : 0.f;
         const float ri = __uint_as_float((254u - sh_layer_scale_exp(amax_in, bound)) << 23);     // 1 / layer scale
-        const size_t plane = (size_t)H * W;
+        const size_t plane = (size_t)H * ldw;
         const uint32_t r_tmem_empty = mapa_shared(tmem_empty, 0);
         float vmax = 0.f;
         PwRing acc;
@@ -998,9 +1042,9 @@ sh_pw2_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ ama
             if (!sh_unit_valid(2 * pair, TX, TY, H) && !sh_unit_valid(2 * pair + 1, TX, TY, H)) continue;
             const int unit = 2 * pair + (int)rank;
             const int tx = unit % TX, ty = (unit / TX) % TY, n = unit / (TX * TY);
-            const int py = ty * SH_TH + (row >> 5), px = tx * SH_TW + (row & 31);
-            const bool valid = py < H && px < W;
-            float* op = out + ((size_t)n * SH_MID + half * 128) * plane + (size_t)py * W + px;
+            const int py = ty * SH_TH + (row >> 5), px = tx * SH_TW - SH_XOFF + (row & 31);
+            const bool valid = py < H && px >= 0 && px < W;
+            float* op = out + ((size_t)n * SH_MID + half * 128) * plane + (size_t)py * ldw + px;
 #ifdef PW_TRACE
             long long c0 = clock64();
 #endif
@@ -1070,12 +1114,14 @@ sh_pw2_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ ama
 // ---------------------------------------------------------------------------------------------- host side
 size_t seghead_packed_bytes() { return sh_layout().total; }
 
-static inline int sh_tx2(int W) { return (int)ceil_div64(W, DW_TW); }
+static inline int sh_tx2(int W) { return (int)ceil_div64(W + SH_XOFF, DW_TW); }
+static inline int sh_wp(int W) { return (W + 3) & ~3; }          // activation row pitch: rows start on 16-byte multiples (TMA)
 static inline int sh_ty16(int H) { return (int)ceil_div64(H, DW_TH); }
 
 size_t seghead_workspace_bytes(int N, int H, int W) {
     const size_t px = (size_t)N * H * W, units = (size_t)N * sh_ty16(H) * sh_tx2(W) * 4;
-    return align_up(px * 3 * 4, 1024) + align_up(units * (SH_MID / 64) * 2 * SH_CHUNK, 1024) + align_up(px * SH_MID * 4, 1024) + 4096;
+    return align_up(px * 3 * 4, 1024) + align_up(units * (SH_MID / 64) * 2 * SH_CHUNK, 1024) +
+           align_up((size_t)N * H * sh_wp(W) * SH_MID * 4, 1024) + 4096;
 }
 
 // params: 50 device pointers, per layer (dw.weight [C,1,7,7], dw.bias, bn1.weight, bn1.bias, bn1.running_mean,
@@ -1106,6 +1152,31 @@ static int sh_sm_count() {
     return sms;
 }
 
+// Tensor map of the activation buffer y [N*256][H][Wp] (valid width W: columns beyond it and rows/columns outside the image
+// read as zeros), box = one channel's 22 x 40 window.  cuTensorMapEncodeTiled comes from the driver through the runtime's entry
+// point lookup (no link-time dependency on libcuda).  MANET_SH_DW_TMA=0 or any failure falls back to the cp.async path --
+// of the SAME kernel family, not a different implementation.
+static bool sh_encode_ymap(CUtensorMap* map, float* y, int N, int H, int W, int Wp) {
+    memset(map, 0, sizeof(*map));
+    static const bool off = [] { const char* e = getenv("MANET_SH_DW_TMA"); return e && e[0] == '0'; }();
+    if (off) return false;
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn enc = [] {
+        void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError(); fn = nullptr;
+        }
+        return reinterpret_cast<EncodeFn>(fn);
+    }();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N * SH_MID};
+    const cuuint64_t strides[2] = {(cuuint64_t)Wp * 4, (cuuint64_t)H * Wp * 4};
+    const cuuint32_t box[3] = {DW_PITCH, DW_IH, 1}, estr[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 struct ShParts { const float* gmap; const float* lmap; const int32_t* prev; const int32_t* ids; };
 
 static int launch_seghead_forward(const void* packed, int in_dim, ShSource src, const ShParts* parts, int N, int H, int W,
@@ -1121,8 +1192,9 @@ static int launch_seghead_forward(const void* packed, int in_dim, ShSource src, 
         cudaFuncSetAttribute(sh_pw2_kernel<PW_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW2_SMEM_TOTAL);
         cudaFuncSetAttribute(sh_pwm_kernel<PW_RELU_NCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_TOTAL);
         cudaFuncSetAttribute(sh_pwm_kernel<PW_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_TOTAL);
-        cudaFuncSetAttribute(sh_dw_kernel<SH_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
-        cudaFuncSetAttribute(sh_dw_kernel<SH_IN_PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
+        cudaFuncSetAttribute(sh_dw_kernel<SH_MID, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
+        cudaFuncSetAttribute(sh_dw_kernel<SH_MID, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
+        cudaFuncSetAttribute(sh_dw_kernel<SH_IN_PAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
         attr_done = true;
     }
     const ShLayout L = sh_layout();
@@ -1131,9 +1203,11 @@ static int launch_seghead_forward(const void* packed, int in_dim, ShSource src, 
     const int TX2 = sh_tx2(W), TY16 = sh_ty16(H), TX = TX2, TY = 4 * TY16, tiles = N * TX2 * TY16, units = 4 * tiles;
     Carver cv(ws, ws_bytes);
     unsigned* amax = cv.take<unsigned>(16, 1024);                 // [0] layer-1 input, [1..3] outputs of layers 1..3, [8..11] work counters
+    CUtensorMap* ymap_d = cv.take<CUtensorMap>(1, 128);
     float* extras = cv.take<float>(px * 3, 1024);
     uint8_t* aimg = cv.take<uint8_t>((size_t)units * (SH_MID / 64) * 2 * SH_CHUNK, 1024);
-    float* y = cv.take<float>(px * SH_MID, 1024);
+    const int Wp = sh_wp(W);
+    float* y = cv.take<float>((size_t)N * H * Wp * SH_MID, 1024);
     if (!cv.ok()) { set_error("seghead: workspace too small"); return MANET_E_WORKSPACE; }
 
     cudaError_t e = cudaMemsetAsync(logits, 0, px * sizeof(float), stream);
@@ -1151,18 +1225,31 @@ static int launch_seghead_forward(const void* packed, int in_dim, ShSource src, 
                  src.sh, src.sw, N, in_dim, H, W, amax);
     }
     const int grid = units < sms ? units : sms;
+    // the map is re-encoded only when the buffer or the shape changes (one 128-byte upload)
+    static thread_local struct { const void* y; int N, H, W; CUtensorMap* dst; bool ok; } cache = {nullptr, 0, 0, 0, nullptr, false};
+    if (cache.y != y || cache.N != N || cache.H != H || cache.W != W || cache.dst != ymap_d) {
+        CUtensorMap ymap;
+        bool ok = sh_encode_ymap(&ymap, y, N, H, W, Wp);
+        if (ok) ok = cudaMemcpyAsync(ymap_d, &ymap, sizeof(ymap), cudaMemcpyHostToDevice, stream) == cudaSuccess;
+        cache = {y, N, H, W, ymap_d, ok};
+    }
+    const bool use_tma = cache.ok;
+    const CUtensorMap* ymap = ymap_d;
     ShSource ysrc = {};
-    ysrc.x = y; ysrc.sn = (int64_t)SH_MID * H * W; ysrc.sc = (int64_t)H * W; ysrc.sh = W; ysrc.sw = 1; ysrc.c0 = SH_MID;
+    ysrc.x = y; ysrc.sn = (int64_t)SH_MID * H * Wp; ysrc.sc = (int64_t)H * Wp; ysrc.sh = Wp; ysrc.sw = 1; ysrc.c0 = SH_MID;
     for (int i = 0; i < SH_LAYERS; ++i) {
         const float* dwW = reinterpret_cast<const float*>(pk + L.l[i].dwW);
         const unsigned* bound = reinterpret_cast<const unsigned*>(pk + L.l[i].bound);
         const int dw_grid = (int)imin64(2 * sms, ceil_div64((int64_t)tiles * (L.l[i].cin_p / 8), DW_WARPS));
         if (i == 0)
-            launch_k(sh_dw_kernel<SH_IN_PAD>, dim3(dw_grid), dim3(DW_WARPS * 32), DW_SMEM, stream, src, in_dim, dwW,
-                     (const unsigned*)amax, bound, aimg, amax + 8 + i, N, H, W, TX2, TY16);
+            launch_k(sh_dw_kernel<SH_IN_PAD, false>, dim3(dw_grid), dim3(DW_WARPS * 32), DW_SMEM, stream, src, in_dim, dwW,
+                     (const unsigned*)amax, bound, aimg, amax + 8 + i, N, H, W, TX2, TY16, ymap);
+        else if (use_tma)
+            launch_k(sh_dw_kernel<SH_MID, true>, dim3(dw_grid), dim3(DW_WARPS * 32), DW_SMEM, stream, ysrc, SH_MID, dwW,
+                     (const unsigned*)(amax + i), bound, aimg, amax + 8 + i, N, H, W, TX2, TY16, ymap);
         else
-            launch_k(sh_dw_kernel<SH_MID>, dim3(dw_grid), dim3(DW_WARPS * 32), DW_SMEM, stream, ysrc, SH_MID, dwW,
-                     (const unsigned*)(amax + i), bound, aimg, amax + 8 + i, N, H, W, TX2, TY16);
+            launch_k(sh_dw_kernel<SH_MID, false>, dim3(dw_grid), dim3(DW_WARPS * 32), DW_SMEM, stream, ysrc, SH_MID, dwW,
+                     (const unsigned*)(amax + i), bound, aimg, amax + 8 + i, N, H, W, TX2, TY16, ymap);
         const float* cinv = reinterpret_cast<const float*>(pk + L.l[i].cinv);
         const float* bias2 = reinterpret_cast<const float*>(pk + L.l[i].bias2);
         const float* w5 = reinterpret_cast<const float*>(pk + L.w5);
@@ -1176,8 +1263,8 @@ static int launch_seghead_forward(const void* packed, int in_dim, ShSource src, 
         if (mcast) {
             const int TYV = (int)ceil_div64(H, SH_TH), n_valid = N * TYV * TX;
             cudaError_t le = (i + 1 < SH_LAYERS)
-                ? launch_pwm<PW_RELU_NCHW>(mcast, sms, stream, aimg, amax + i, bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, y, amax + i + 1, n_valid, nkb, H, W, TX, TY, TYV)
-                : launch_pwm<PW_FINAL>(mcast, sms, stream, aimg, amax + i, bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, logits, amax + 7, n_valid, nkb, H, W, TX, TY, TYV);
+                ? launch_pwm<PW_RELU_NCHW>(mcast, sms, stream, aimg, amax + i, bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, y, amax + i + 1, n_valid, nkb, H, W, TX, TY, TYV, Wp)
+                : launch_pwm<PW_FINAL>(mcast, sms, stream, aimg, amax + i, bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, logits, amax + 7, n_valid, nkb, H, W, TX, TY, TYV, W);
             if (le != cudaSuccess) { set_error("seghead: multicast GEMM launch: %s", cudaGetErrorString(le)); return (int)le; }
             continue;
         }
@@ -1185,17 +1272,17 @@ static int launch_seghead_forward(const void* packed, int in_dim, ShSource src, 
         if (single || grid2 < 2) {
             if (i + 1 < SH_LAYERS)
                 launch_k(sh_pw_kernel<PW_RELU_NCHW>, dim3(grid), dim3(PW_THREADS), PW_SMEM_TOTAL, stream, (const uint8_t*)aimg,
-                         (const unsigned*)(amax + i), bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, y, amax + i + 1, units, nkb, H, W, TX, TY);
+                         (const unsigned*)(amax + i), bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, y, amax + i + 1, units, nkb, H, W, TX, TY, Wp);
             else
                 launch_k(sh_pw_kernel<PW_FINAL>, dim3(grid), dim3(PW_THREADS), PW_SMEM_TOTAL, stream, (const uint8_t*)aimg,
-                         (const unsigned*)(amax + i), bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, logits, amax + 7, units, nkb, H, W, TX, TY);
+                         (const unsigned*)(amax + i), bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, logits, amax + 7, units, nkb, H, W, TX, TY, W);
         } else {
             if (i + 1 < SH_LAYERS)
                 launch_k(sh_pw2_kernel<PW_RELU_NCHW>, dim3(grid2), dim3(PW_THREADS), PW2_SMEM_TOTAL, stream, (const uint8_t*)aimg,
-                         (const unsigned*)(amax + i), bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, y, amax + i + 1, units, nkb, H, W, TX, TY);
+                         (const unsigned*)(amax + i), bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, y, amax + i + 1, units, nkb, H, W, TX, TY, Wp);
             else
                 launch_k(sh_pw2_kernel<PW_FINAL>, dim3(grid2), dim3(PW_THREADS), PW2_SMEM_TOTAL, stream, (const uint8_t*)aimg,
-                         (const unsigned*)(amax + i), bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, logits, amax + 7, units, nkb, H, W, TX, TY);
+                         (const unsigned*)(amax + i), bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, logits, amax + 7, units, nkb, H, W, TX, TY, W);
         }
     }
     return check_launch("seghead forward kernels");
