@@ -288,8 +288,10 @@ def run_own_arm(args, rank, local_rank, world):
     total_s, e2e_s, e2e_sync_s, serial_s, e2e_stream_s = (float(t[i]) for i in range(5))
 
     sharded = sharded_1080p_leg(dev, rank, world) if os.environ.get("MANET_BENCH_SHARDED", "1") == "1" else None
-    seghead = seghead_leg(dev) if rank == 0 and os.environ.get("MANET_BENCH_SEGHEAD", "1") == "1" else None
-    propagation = propagation_leg(dev) if rank == 0 and os.environ.get("MANET_BENCH_SEGHEAD", "1") == "1" else None
+    # the head / propagation legs describe one GPU; multi-GPU runs (independent sequences) report the scaling metric only
+    extra = world == 1 and os.environ.get("MANET_BENCH_SEGHEAD", "1") == "1"
+    seghead = seghead_leg(dev) if extra else None
+    propagation = propagation_leg(dev) if extra else None
 
     if rank == 0:
         peaks = load_peaks()
