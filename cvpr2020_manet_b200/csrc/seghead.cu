@@ -236,7 +236,9 @@ sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned*
              int N, int H, int W, int TX2, int TY16, const CUtensorMap* __restrict__ tmap) {
     pdl_enter();
     extern __shared__ __align__(128) float dw_smem_raw[];
-    float* dw_smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dw_smem_raw) + 127) & ~(uintptr_t)127);
+    // 128-byte alignment (TMA destination) by an OFFSET on the shared array: rounding the pointer through an integer makes
+    // the compiler forget the address space, and every window load becomes a generic LD instead of LDS (ncu source page)
+    float* dw_smem = dw_smem_raw + (((128u - (smem_u32(dw_smem_raw) & 127u)) & 127u) >> 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* inbuf = dw_smem + warp * DW_WARP_FLOATS;
     float* outbuf = inbuf + 2 * DW_PLANE_PAD;
