@@ -390,3 +390,25 @@ def test_gpu_rough_roi(h, w, dtype):
     got = engine.rough_ROI(lab.cuda())
     assert got.dtype == dtype
     assert torch.equal(got.cpu(), O.rough_roi(lab))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("in_dim", [8, 35, 128])
+def test_gpu_seghead_other_input_widths(in_dim):
+    """in_dim other than 103: whole zero chunks of the padded first layer (in_dim = 8, 35), no padding at all (128)."""
+    from cvpr2020_manet_b200.networks.seghead import DynamicSegHead
+    torch.manual_seed(in_dim)
+    head = DynamicSegHead(in_dim=in_dim).eval()
+    with torch.no_grad():
+        for layer in (head.layer1, head.layer2, head.layer3, head.layer4):
+            layer.conv1.weight.mul_(6.0)                 # keep some signal through the four blocks
+            for bn in (layer.bn1, layer.bn2):
+                bn.running_mean.normal_(0.0, 0.1)
+                bn.running_var.uniform_(0.5, 1.5)
+                bn.weight.uniform_(0.5, 1.5)
+                bn.bias.normal_(0.0, 0.2)
+    state = {k: v.detach().clone() for k, v in head.state_dict().items()}
+    x = torch.randn(2, in_dim, 19, 45, generator=torch.Generator().manual_seed(1))
+    want = O.dynamic_seghead_forward(state, x)
+    got = head.cuda()(x.cuda())
+    assert logit_err(got.cpu().numpy(), want.numpy()) <= LOGIT_RTOL
