@@ -233,7 +233,7 @@ template <int CP, bool TMA>
 __global__ void __launch_bounds__(DW_WARPS * 32, 2)
 sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned* __restrict__ amax_in,
              const unsigned* __restrict__ bound, uint8_t* __restrict__ Aimg, unsigned* __restrict__ counter,
-             int N, int H, int W, int TX2, int TY16, const CUtensorMap* __restrict__ tmap) {
+             int N, int H, int W, int TX2, int TY16, const CUtensorMap* __restrict__ tmap, int shared_kb0) {
     pdl_enter();
     extern __shared__ __align__(128) float dw_smem_raw[];
     // 128-byte alignment (TMA destination) by an OFFSET on the shared array: rounding the pointer through an integer makes
@@ -258,7 +258,11 @@ sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned*
     const float scale = __uint_as_float(sh_layer_scale_exp(amax_in, bound) << 23);
     constexpr size_t UNIT_BYTES = (size_t)(CP / 64) * 2 * SH_CHUNK;
     constexpr int CHUNKS = CP / 8;
-    const int n_items = N * TY16 * TX2 * CHUNKS;
+    // shared_kb0 (first layer fed by its parts): channels 0..63 are the current-frame embedding, identical for every object
+    // (IntVOS.py:665 repeats it), so their k-block is computed for object 0 only and the GEMM reads it from there;
+    // objects 1.. get just the second k-block (chunks CHUNKS/2 ..).
+    const int tiles_obj = TY16 * TX2;
+    const int n_items = shared_kb0 ? tiles_obj * (CHUNKS + (N - 1) * (CHUNKS / 2)) : N * tiles_obj * CHUNKS;
 
     for (;;) {
         int item = 0;
@@ -266,7 +270,9 @@ sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned*
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_items) break;
         // chunk fastest: the warps of an SM share a tile's input neighbourhood in L1/L2
-        const int cid = item % CHUNKS, tile = item / CHUNKS;
+        int cid, tile;
+        if (!shared_kb0 || item < tiles_obj * CHUNKS) { cid = item % CHUNKS; tile = item / CHUNKS; }
+        else { const int j = item - tiles_obj * CHUNKS; cid = CHUNKS / 2 + j % (CHUNKS / 2); tile = tiles_obj + j / (CHUNKS / 2); }
         const int tx2 = tile % TX2, ty = (tile / TX2) % TY16, n = tile / (TX2 * TY16);
         const int y0 = ty * DW_TH - 3, x0 = tx2 * DW_TW - SH_XOFF - DW_HALO_L;
         uint8_t* img_tile = Aimg + (size_t)(((size_t)n * TY16 + ty) * 4 * TX2 + tx2) * UNIT_BYTES;   // unit (n, 4*ty + uy, tx2)
@@ -452,7 +458,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1)
 sh_pw_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ amax_in, const unsigned* __restrict__ bound,
              const uint8_t* __restrict__ Bimg, const float* __restrict__ cinv, const float* __restrict__ bias2,
              const float* __restrict__ w5, const float* __restrict__ b5, float* __restrict__ out, unsigned* __restrict__ amax_out,
-             int n_units, int nkb, int H, int W, int TX, int TY, int ldw) {
+             int n_units, int nkb, int H, int W, int TX, int TY, int ldw, int shared_kb0) {
     pdl_enter();
 #ifdef PW_TRACE
     long long tr_a = 0, tr_b = 0, tr_c = 0, tr_t0 = clock64();
@@ -504,9 +510,11 @@ sh_pw_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ amax
 #endif
                 const uint32_t fb = full_b + 8 * st.idx;
                 const uint32_t dst = base + st.idx * PW_STAGE_BYTES;
+                // first layer fed by its parts: k-block 0 (embedding channels, the same for all objects) exists for object 0 only
+                const int aunit = (shared_kb0 && kb == 0) ? unit % (TX * TY) : unit;
                 if (elect_one()) {
                     mbar_expect_tx(fb, PW_STAGE_BYTES);
-                    bulk_g2s(dst, Aimg + (size_t)unit * unit_bytes + (size_t)kb * PW_A_BYTES, PW_A_BYTES, fb);
+                    bulk_g2s(dst, Aimg + (size_t)aunit * unit_bytes + (size_t)kb * PW_A_BYTES, PW_A_BYTES, fb);
                     bulk_g2s(dst + PW_A_BYTES, Bimg + (size_t)kb * PW_B_BYTES, PW_B_BYTES, fb);
                 }
                 __syncwarp();
@@ -1237,6 +1245,13 @@ static int launch_seghead_forward(const void* packed, int in_dim, ShSource src, 
     }
     const bool use_tma = cache.ok;
     const CUtensorMap* ymap = ymap_d;
+    // first layer, parts mode: the embedding k-block is shared by all objects (needs the default single-CTA GEMM, which
+    // knows where to fetch it; MANET_SH_SHARE_L1=0 turns the sharing off)
+    static const bool share_ok = [] {
+        const char* a = getenv("MANET_SH_PW_PAIR"); const char* b = getenv("MANET_SH_PW_CLUSTER"); const char* c = getenv("MANET_SH_SHARE_L1");
+        return !(a && a[0] == '1') && !(b && atoi(b) >= 2) && !(c && c[0] == '0');
+    }();
+    const int shared1 = (parts && share_ok && src.c0 >= 64 && N > 1) ? 1 : 0;
     ShSource ysrc = {};
     ysrc.x = y; ysrc.sn = (int64_t)SH_MID * H * Wp; ysrc.sc = (int64_t)H * Wp; ysrc.sh = Wp; ysrc.sw = 1; ysrc.c0 = SH_MID;
     for (int i = 0; i < SH_LAYERS; ++i) {
@@ -1245,13 +1260,13 @@ static int launch_seghead_forward(const void* packed, int in_dim, ShSource src, 
         const int dw_grid = (int)imin64(2 * sms, ceil_div64((int64_t)tiles * (L.l[i].cin_p / 8), DW_WARPS));
         if (i == 0)
             launch_k(sh_dw_kernel<SH_IN_PAD, false>, dim3(dw_grid), dim3(DW_WARPS * 32), DW_SMEM, stream, src, in_dim, dwW,
-                     (const unsigned*)amax, bound, aimg, amax + 8 + i, N, H, W, TX2, TY16, ymap);
+                     (const unsigned*)amax, bound, aimg, amax + 8 + i, N, H, W, TX2, TY16, ymap, shared1);
         else if (use_tma)
             launch_k(sh_dw_kernel<SH_MID, true>, dim3(dw_grid), dim3(DW_WARPS * 32), DW_SMEM, stream, ysrc, SH_MID, dwW,
-                     (const unsigned*)(amax + i), bound, aimg, amax + 8 + i, N, H, W, TX2, TY16, ymap);
+                     (const unsigned*)(amax + i), bound, aimg, amax + 8 + i, N, H, W, TX2, TY16, ymap, 0);
         else
             launch_k(sh_dw_kernel<SH_MID, false>, dim3(dw_grid), dim3(DW_WARPS * 32), DW_SMEM, stream, ysrc, SH_MID, dwW,
-                     (const unsigned*)(amax + i), bound, aimg, amax + 8 + i, N, H, W, TX2, TY16, ymap);
+                     (const unsigned*)(amax + i), bound, aimg, amax + 8 + i, N, H, W, TX2, TY16, ymap, 0);
         const float* cinv = reinterpret_cast<const float*>(pk + L.l[i].cinv);
         const float* bias2 = reinterpret_cast<const float*>(pk + L.l[i].bias2);
         const float* w5 = reinterpret_cast<const float*>(pk + L.w5);
@@ -1274,10 +1289,10 @@ static int launch_seghead_forward(const void* packed, int in_dim, ShSource src, 
         if (single || grid2 < 2) {
             if (i + 1 < SH_LAYERS)
                 launch_k(sh_pw_kernel<PW_RELU_NCHW>, dim3(grid), dim3(PW_THREADS), PW_SMEM_TOTAL, stream, (const uint8_t*)aimg,
-                         (const unsigned*)(amax + i), bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, y, amax + i + 1, units, nkb, H, W, TX, TY, Wp);
+                         (const unsigned*)(amax + i), bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, y, amax + i + 1, units, nkb, H, W, TX, TY, Wp, i == 0 ? shared1 : 0);
             else
                 launch_k(sh_pw_kernel<PW_FINAL>, dim3(grid), dim3(PW_THREADS), PW_SMEM_TOTAL, stream, (const uint8_t*)aimg,
-                         (const unsigned*)(amax + i), bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, logits, amax + 7, units, nkb, H, W, TX, TY, W);
+                         (const unsigned*)(amax + i), bound, pk + L.l[i].Bimg, cinv, bias2, w5, b5, logits, amax + 7, units, nkb, H, W, TX, TY, W, 0);
         } else {
             if (i + 1 < SH_LAYERS)
                 launch_k(sh_pw2_kernel<PW_RELU_NCHW>, dim3(grid2), dim3(PW_THREADS), PW2_SMEM_TOTAL, stream, (const uint8_t*)aimg,
