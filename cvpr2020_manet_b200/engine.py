@@ -117,6 +117,39 @@ def prop_seghead(ref_frame_embedding=None, previous_frame_embedding=None, curren
     return dic_tmp, global_map_tmp_dic, local_map_dics
 
 
+def int_seghead(ref_frame_embedding=None, ref_scribble_label=None, prev_round_label=None,
+                normalize_nearest_neighbor_distances=True, global_map_tmp_dic=None, local_map_dics=None, interaction_num=None,
+                seq_names=None, gt_ids=None, k_nearest_neighbors=1, frame_num=None, first_inter=True, inter_seghead=None):
+    """``IntVOS.int_seghead`` (IntVOS.py:683-764) with the reference's arguments and return forms; ``inter_seghead`` is the
+    module the reference keeps as ``self.inter_seghead`` (its ``IntSegHead``, IntVOS.py:463-486 -- dense convolutions, outside
+    this package's scope: pass the reference's own module).  On the sm_100a kernels: the local self-match of the annotated
+    frame (:709-711), its merge into the global-map memory (:716-723) and the local-map bookkeeping (:725-736).  The head's
+    input (:741-757: embedding repeated per object, scribble mask, previous-round mask) is assembled with torch ops."""
+    dic_tmp = {}
+    bs, c, h, w = ref_frame_embedding.size()
+    scale_scr = torch.nn.functional.interpolate(ref_scribble_label.float(), size=(h, w), mode="nearest").int()
+    if not first_inter:
+        scale_prev = torch.nn.functional.interpolate(prev_round_label.float(), size=(h, w), mode="nearest").int()
+    for n in range(bs):
+        gt_id = torch.arange(0, int(gt_ids[n]) + 1, dtype=torch.int32, device=ref_frame_embedding.device)
+        scr = scale_scr[n].permute(1, 2, 0)                                       # [h,w,1]
+        loc, _ = int_matching_step(ref_frame_embedding[n], scr[..., 0], int(gt_ids[n]), None, global_map_tmp_dic,
+                                   local_map_dics, seq_names[n], frame_num[n], interaction_num)
+        emb_rep = ref_frame_embedding[n].unsqueeze(0).repeat((gt_id.size(0), 1, 1, 1))
+        scr_mask = (scr.float() == gt_id.float()).unsqueeze(-1).permute(2, 3, 0, 1).float()
+        if not first_inter:
+            prev = scale_prev[n].permute(1, 2, 0)
+            prev_mask = (prev.float() == gt_id.float()).unsqueeze(-1).permute(2, 3, 0, 1).float()
+        else:
+            prev_mask = torch.zeros_like(scr_mask)
+            prev_mask[0] = 1.0
+        pred = inter_seghead(torch.cat((emb_rep, scr_mask, prev_mask), 1))
+        dic_tmp[seq_names[n]] = pred.permute(1, 0, 2, 3)
+    if local_map_dics is None:
+        return dic_tmp
+    return dic_tmp, local_map_dics
+
+
 def upsample_argmax(pred, size, want_full=True, want_small=True):
     """The label step of the propagation loop (test.py:253-256 followed by IntVOS.py:598-599): ``pred`` ``[1,N,h,w]``
     logits -> ``(labels [1,Hf,Wf] int64, small [h,w] int32)`` where ``labels = argmax(interpolate(pred, size, 'bilinear',

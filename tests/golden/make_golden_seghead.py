@@ -57,6 +57,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "seghead_ref.npz"), **out)
     print("wrote seghead_ref.npz", os.path.getsize(os.path.join(HERE, "seghead_ref.npz")) // 1024, "KB")
     prop_seghead_case(head)
+    int_seghead_case()
 
 
 def prop_seghead_case(head):
@@ -88,6 +89,46 @@ def prop_seghead_case(head):
             out[f"f{f}_pred"] = res[0]["s"].numpy()
     np.savez_compressed(os.path.join(HERE, "prop_seghead_ref.npz"), **out)
     print("wrote prop_seghead_ref.npz", {k: np.asarray(v).shape for k, v in out.items()})
+
+
+def int_seghead_case():
+    """The reference's own IntVOS.int_seghead (IntVOS.py:683-764) for two rounds on one sequence: the tensor its interaction
+    head receives (captured by a stand-in head) and the memories it leaves behind."""
+    import types
+    c, h, w, nobj, d = 12, 14, 18, 2, 3
+    mod = ref_shim.load_reference(test_mode=True, max_local_distance=d)
+    gen = torch.Generator().manual_seed(41)
+    embs = torch.stack([0.1 * torch.relu(torch.randn(c, h, w, generator=gen)) for _ in range(3)])
+    seen = []
+
+    def fake_head(x):
+        seen.append(x.detach().clone())
+        return torch.zeros(x.shape[0], 1, x.shape[2], x.shape[3])
+
+    fake_self = types.SimpleNamespace(inter_seghead=fake_head)
+    gmem, lmem = {}, ({}, {})
+    out = {"embs": embs.numpy(), "n_obj": nobj, "d": d}
+    with ref_shim.cpu_cuda_identity(), torch.no_grad():
+        for rnd, frame, first in ((1, 1, True), (2, 2, False)):
+            scr = torch.full((h, w), -1, dtype=torch.int32)
+            scr[2 + rnd, 2:10] = 0
+            scr[8, 4 + rnd:15] = 1
+            scr[10:13, 6 + rnd] = 2
+            prev_round = torch.randint(0, nobj + 1, (h // 2, w // 2), generator=gen).repeat_interleave(2, 0).repeat_interleave(2, 1).int()
+            res = mod.IntVOS.int_seghead(fake_self, ref_frame_embedding=embs[frame:frame + 1],
+                                         ref_scribble_label=scr.view(1, 1, h, w).float(),
+                                         prev_round_label=None if first else prev_round.view(1, 1, h, w).float(),
+                                         global_map_tmp_dic=gmem, local_map_dics=lmem, interaction_num=rnd, seq_names=["s"],
+                                         gt_ids=torch.tensor([nobj]), frame_num=[frame], first_inter=first)
+            out[f"r{rnd}_scribble"] = scr.numpy()
+            out[f"r{rnd}_prev_round"] = prev_round.numpy()
+            out[f"r{rnd}_to_cat"] = seen[-1].numpy()
+            out[f"r{rnd}_pred_shape"] = np.array(res[0]["s"].shape)
+    out["final_global_mem"] = gmem["s"][:3].numpy()
+    out["final_local_dist"] = lmem[1]["s"][:3, :3].numpy()
+    out["final_local_mem_is_ones"] = np.array(bool((lmem[0]["s"] == 1).all()))
+    np.savez_compressed(os.path.join(HERE, "int_seghead_ref.npz"), **out)
+    print("wrote int_seghead_ref.npz", {k: np.asarray(v).shape for k, v in out.items()})
 
 
 if __name__ == "__main__":

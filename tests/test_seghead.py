@@ -412,3 +412,39 @@ def test_gpu_seghead_other_input_widths(in_dim):
     want = O.dynamic_seghead_forward(state, x)
     got = head.cuda()(x.cuda())
     assert logit_err(got.cpu().numpy(), want.numpy()) <= LOGIT_RTOL
+
+
+@pytest.mark.gpu
+def test_gpu_int_seghead_matches_reference(golden):
+    """engine.int_seghead (the reference's signature, IntVOS.py:683-764) against the reference's own run: the tensor handed
+    to the interaction head is exact (embedding, scribble mask, previous-round mask), the memories within 1e-5."""
+    from cvpr2020_manet_b200 import engine
+    from cvpr2020_manet_b200.config import cfg
+    g = golden("int_seghead_ref")
+    saved = (cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE)
+    cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE = True, int(g["d"])
+    try:
+        embs = torch.from_numpy(g["embs"]).cuda()
+        _, c, h, w = embs.shape
+        nobj = int(g["n_obj"])
+        seen = []
+
+        def head(x):
+            seen.append(x)
+            return torch.zeros(x.shape[0], 1, x.shape[2], x.shape[3], device=x.device)
+
+        gm, lm = {}, ({}, {})
+        for rnd, frame, first in ((1, 1, True), (2, 2, False)):
+            scr = torch.from_numpy(g[f"r{rnd}_scribble"]).cuda()
+            prev_round = torch.from_numpy(g[f"r{rnd}_prev_round"]).cuda()
+            res, lm = engine.int_seghead(ref_frame_embedding=embs[frame:frame + 1], ref_scribble_label=scr.view(1, 1, h, w).float(),
+                                         prev_round_label=None if first else prev_round.view(1, 1, h, w).float(),
+                                         global_map_tmp_dic=gm, local_map_dics=lm, interaction_num=rnd, seq_names=["s"],
+                                         gt_ids=torch.tensor([nobj]), frame_num=[frame], first_inter=first, inter_seghead=head)
+            assert tuple(res["s"].shape) == tuple(g[f"r{rnd}_pred_shape"])
+            assert np.array_equal(seen[-1].cpu().numpy(), g[f"r{rnd}_to_cat"])
+        assert float(np.abs(gm["s"][:3].cpu().numpy() - g["final_global_mem"]).max()) <= 1e-5
+        assert np.array_equal(lm[1]["s"][:3, :3].cpu().numpy(), g["final_local_dist"])
+        assert bool((lm[0]["s"] == 1).all()) == bool(g["final_local_mem_is_ones"])
+    finally:
+        cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE = saved
