@@ -6,7 +6,7 @@ python - <<'PY'
 import json
 try:
     d=json.loads(open('gpurun_out/bench_short.log').read().strip().splitlines()[-1])
-    print('value',round(d['value'],1),'seghead ms',d['seghead']['ms'],'prop',d.get('propagation_50'))
+    print("value",round(d["value"],1),"seghead ms",d["seghead"]["ms"],"prop",d.get("propagation_50",{}).get("frames_per_s"),"session",d.get("session_8_rounds"))
 except Exception as e:
     print('parse failed',e); print(open('gpurun_out/bench_short.log').read()[-3000:])
 PY
