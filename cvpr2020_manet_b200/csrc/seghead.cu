@@ -6,10 +6,10 @@
 // one affine map at pack time (sh_pack_*).  Activations stay in the reference's NCHW layout between layers.
 //
 // Per layer:   x [N,Cin,H,W] --depthwise 7x7 + BN + ReLU--> a --1x1 conv Cin->256 + BN + ReLU--> y [N,256,H,W]
-//   * sh_dw_kernel   fp32 CUDA cores.  Work item = (16x32 pixel tile = four 128-row GEMM units, chunk of 8 channels),
-//     pulled by warps from an atomic counter.  A warp owns one channel at a time: each lane computes a 4x4 block of
-//     outputs from a 10x10 window read with 128-bit shared-memory loads, the 49 taps are warp-uniform registers.  The
-//     channel's input plane (22x38 with halo) and taps arrive through a per-warp double buffer filled by cp.async, so
+//   * sh_dw_kernel   fp32 CUDA cores.  Work item = (8x32 pixel tile = two 128-row GEMM units, chunk of 8 channels),
+//     pulled by warps from an atomic counter.  A warp works on a PAIR of channels at a time (lanes 0-15 / 16-31): each lane
+//     computes a 4x4 block of outputs from a 10x10 window read with 128-bit shared-memory loads, its 49 taps in registers.
+//     The pair's input planes (14x40 with halo) and taps arrive through a per-warp double buffer (TMA box / cp.async), so
 //     the loop over channels is a compact rolled loop with no CTA barrier.  Eight channels at a time are converted to
 //     the tensor-core operand: x*2^e = hi + lo in fp16, written as 16-byte chunks of the 128-byte-swizzled K-major
 //     shared-memory image of the unit.
@@ -195,20 +195,25 @@ sh_extras_kernel(const float* __restrict__ gmap, const float* __restrict__ lmap,
 }
 
 // ---------------------------------------------------------------------------------------------- depthwise 7x7
-// Work item = (16x32 pixel tile, chunk of 8 channels), pulled by WARPS from an atomic counter (warps are fully
-// independent: private double-buffered input plane, private 8-plane output block).  A lane computes a 4x4 block of
+// Work item = (8x32 pixel tile, chunk of 8 channels), pulled by WARPS from an atomic counter (warps are fully
+// independent: private double-buffered input planes, private 8-plane output block).  A lane computes a 4x4 block of
 // outputs from a 10x10 window (128-bit shared-memory loads): 6.25 loaded floats per output.  With 2x4 blocks
 // (10 per output) the kernel was shared-memory bound: 130 wavefronts against 98 FMA-issue cycles per channel.
-constexpr int DW_TH = 16, DW_TW = 32;              // warp tile = four units stacked vertically
+// The two half-warps work on two different channels of the same tile: same instruction count as one channel over a
+// 16x32 tile, but the 8-plane output block is 8 KB instead of 16 -> 12 instead of 8 warps per SM (137 -> 112 us per layer),
+// and 8-row tiles waste nothing of H = 120.
+constexpr int DW_TH = 8, DW_TW = 32;               // warp tile = two units stacked vertically; the warp works on TWO channels at a
+                                                   // time (lanes 0-15 / 16-31), so 8 output planes are 8 KB and 12 warps fit on an SM
 constexpr int DW_HALO_L = 4;                       // staged columns start 4 (not 3) left of the tile: a TMA box must start on a 16-byte multiple
 constexpr int DW_IH = DW_TH + 6, DW_IW = DW_TW + 8;
 constexpr int DW_PITCH = 40;                       // floats per staged row = DW_IW (16-byte aligned 128-bit loads)
-constexpr int DW_PLANE = DW_IH * DW_PITCH;         // 880 floats per channel plane
+constexpr int DW_PLANE = DW_IH * DW_PITCH;         // 560 floats per channel plane
 constexpr int DW_WARPS = 4;
-constexpr int DW_PLANE_PAD = 896;                  // plane slot: 3584 B, a multiple of the 128-byte alignment a TMA box wants
-// per warp: double-buffered input plane, 8 output planes, double-buffered taps, two mbarriers (padded to 128 B multiples)
-constexpr int DW_WARP_FLOATS = 2 * DW_PLANE_PAD + 8 * DW_TH * DW_TW + 2 * 64 + 32;
-constexpr int DW_SMEM = DW_WARPS * DW_WARP_FLOATS * 4 + 128;        // 96,896 B: two CTAs per SM
+constexpr int DW_PLANE_PAD = 1152;                 // slot of a channel PAIR (2 x 560 floats): 4608 B, a multiple of the 128 bytes a TMA box wants
+constexpr int DW_TAPS = 128;                       // slot of a pair's taps (2 x 52 floats)
+// per warp: double-buffered pair of input planes, 8 output planes, double-buffered taps, two mbarriers (a 128-byte multiple)
+constexpr int DW_WARP_FLOATS = 2 * DW_PLANE_PAD + 8 * DW_TH * DW_TW + 2 * DW_TAPS + 32;
+constexpr int DW_SMEM = DW_WARPS * DW_WARP_FLOATS * 4 + 128;        // 74,368 B: three CTAs per SM
 
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -219,7 +224,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
-// one TMA box = the 22 x 40 window of one channel plane (out-of-image elements arrive as zeros)
+// one TMA box = the 14 x 40 windows of a channel pair (out-of-image elements arrive as zeros)
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, uint64_t map_addr, int x, int y, int z, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"(dst), "l"(map_addr), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
@@ -230,7 +235,7 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, uint64_t map_addr, int
 // a per-warp mbarrier -- no per-row copies, address arithmetic or border predicates in the instruction stream.
 // TMA = false: per-row cp.async copies (any strides; the first layer reads the caller's tensors in place).
 template <int CP, bool TMA>
-__global__ void __launch_bounds__(DW_WARPS * 32, 2)
+__global__ void __launch_bounds__(DW_WARPS * 32, 3)
 sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned* __restrict__ amax_in,
              const unsigned* __restrict__ bound, uint8_t* __restrict__ Aimg, unsigned* __restrict__ counter,
              int N, int H, int W, int TX2, int TY16, const CUtensorMap* __restrict__ tmap, int shared_kb0) {
@@ -244,7 +249,7 @@ sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned*
     float* outbuf = inbuf + 2 * DW_PLANE_PAD;
     const float* wbuf = outbuf + 8 * DW_TH * DW_TW;
     const uint32_t in_s = smem_u32(inbuf), w_s = smem_u32(wbuf);
-    const uint32_t bar_s = w_s + 2 * 64 * 4;                       // two mbarriers, one per buffer
+    const uint32_t bar_s = w_s + 2 * DW_TAPS * 4;                  // two mbarriers, one per buffer
     uint32_t ph = 0;                                               // their phase bits
     const uint64_t tmap_addr = reinterpret_cast<uint64_t>(tmap);   // the tensor map lives in global memory (workspace)
     if (TMA) {
@@ -254,7 +259,8 @@ sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned*
         }
         __syncwarp();
     }
-    const int by = lane >> 3, bx = lane & 7;                       // this lane's 4x4 output block
+    const int half = lane >> 4;                                    // which channel of the pair this lane works on
+    const int by = (lane >> 3) & 1, bx = lane & 7;                 // this lane's 4x4 output block in the 8x32 tile
     const float scale = __uint_as_float(sh_layer_scale_exp(amax_in, bound) << 23);
     constexpr size_t UNIT_BYTES = (size_t)(CP / 64) * 2 * SH_CHUNK;
     constexpr int CHUNKS = CP / 8;
@@ -275,7 +281,7 @@ sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned*
         else { const int j = item - tiles_obj * CHUNKS; cid = CHUNKS / 2 + j % (CHUNKS / 2); tile = tiles_obj + j / (CHUNKS / 2); }
         const int tx2 = tile % TX2, ty = (tile / TX2) % TY16, n = tile / (TX2 * TY16);
         const int y0 = ty * DW_TH - 3, x0 = tx2 * DW_TW - SH_XOFF - DW_HALO_L;
-        uint8_t* img_tile = Aimg + (size_t)(((size_t)n * TY16 + ty) * 4 * TX2 + tx2) * UNIT_BYTES;   // unit (n, 4*ty + uy, tx2)
+        uint8_t* img_tile = Aimg + (size_t)(((size_t)n * TY16 + ty) * (DW_TH / SH_TH) * TX2 + tx2) * UNIT_BYTES;   // unit (n, 2*ty + uy, tx2)
 
         // stage channel c: its 22 x 38 input window (zero outside the image / beyond the real channels: src-size 0 =
         // zero fill) and its 49 taps + bias.  One pointer walks the rows; `interior` tiles skip the predicates.
@@ -285,45 +291,42 @@ sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned*
             if (TMA) {
                 if (elect_one()) {
                     const uint32_t bar = bar_s + 8 * buf;
-                    mbar_expect_tx(bar, DW_PLANE * 4 + SH_WROW * 4);
-                    tma_load_3d(in_s + (uint32_t)(buf * DW_PLANE_PAD) * 4, tmap_addr, x0, y0, n * CP + c, bar);
-                    bulk_g2s(w_s + (uint32_t)(buf * 64) * 4, dwW + (size_t)c * SH_WROW, SH_WROW * 4, bar);
+                    mbar_expect_tx(bar, 2 * DW_PLANE * 4 + 2 * SH_WROW * 4);
+                    tma_load_3d(in_s + (uint32_t)(buf * DW_PLANE_PAD) * 4, tmap_addr, x0, y0, n * CP + c, bar);    // box: 40 x 14 x 2 channels
+                    bulk_g2s(w_s + (uint32_t)(buf * DW_TAPS) * 4, dwW + (size_t)c * SH_WROW, 2 * SH_WROW * 4, bar);
                 }
                 __syncwarp();
                 return;
             }
-            const float* base; int64_t sy, sx;
-            if (c < src.c0) { base = src.x + n * src.sn + c * src.sc; sy = src.sh; sx = src.sw; }
-            else { base = src.extras + ((size_t)n * 3 + (c - src.c0)) * H * W; sy = W; sx = 1; }
-            const float* p0 = base + (int64_t)y0 * sy + (int64_t)(x0 + lane) * sx;
-            const float* p1 = p0 + 32 * sx;
-            const uint32_t dst = in_s + (uint32_t)(buf * DW_PLANE_PAD + lane) * 4;
-            if (lane < SH_WROW / 4) cp_async16(w_s + (uint32_t)(buf * 64 + lane * 4) * 4, dwW + (size_t)c * SH_WROW + lane * 4);
-            if (interior && c < C && sx == 1) {
-                // contiguous rows (every layer but a strided first-layer input): one pointer, the second copy at +32 floats
+            if (lane < 2 * SH_WROW / 4) cp_async16(w_s + (uint32_t)(buf * DW_TAPS + lane * 4) * 4, dwW + (size_t)c * SH_WROW + lane * 4);
 #pragma unroll
-                for (int r = 0; r < DW_IH; ++r) {
-                    cp_async4(dst + r * DW_PITCH * 4, p0, 4u);
-                    if (lane < DW_IW - 32) cp_async4(dst + (r * DW_PITCH + 32) * 4, p0 + 32, 4u);
-                    p0 += sy;
-                }
-            } else if (interior && c < C) {
+            for (int hh = 0; hh < 2; ++hh) {                   // the two channels of the pair, one plane each
+                const int ch = c + hh;
+                const float* base; int64_t sy, sx;
+                if (ch < src.c0) { base = src.x + n * src.sn + ch * src.sc; sy = src.sh; sx = src.sw; }
+                else { base = src.extras + ((size_t)n * 3 + (ch - src.c0)) * H * W; sy = W; sx = 1; }
+                const float* p0 = base + (int64_t)y0 * sy + (int64_t)(x0 + lane) * sx;
+                const float* p1 = p0 + 32 * sx;
+                const uint32_t dst = in_s + (uint32_t)(buf * DW_PLANE_PAD + hh * DW_PLANE + lane) * 4;
+                if (interior && ch < C && sx == 1) {
+                    // contiguous rows (every layer but a strided first-layer input): one pointer, the second copy at +32 floats
 #pragma unroll
-                for (int r = 0; r < DW_IH; ++r) {
-                    cp_async4(dst + r * DW_PITCH * 4, p0, 4u);
-                    if (lane < DW_IW - 32) cp_async4(dst + (r * DW_PITCH + 32) * 4, p1, 4u);
-                    p0 += sy; p1 += sy;
-                }
-            } else {
-                const bool cok = c < C;
-                const unsigned sz0 = (cok && (unsigned)(x0 + lane) < (unsigned)W) ? 4u : 0u;
-                const unsigned sz1 = (cok && (unsigned)(x0 + 32 + lane) < (unsigned)W) ? 4u : 0u;
+                    for (int r = 0; r < DW_IH; ++r) {
+                        cp_async4(dst + r * DW_PITCH * 4, p0, 4u);
+                        if (lane < DW_IW - 32) cp_async4(dst + (r * DW_PITCH + 32) * 4, p0 + 32, 4u);
+                        p0 += sy;
+                    }
+                } else {
+                    const bool cok = ch < C;
+                    const unsigned sz0 = (cok && (unsigned)(x0 + lane) < (unsigned)W) ? 4u : 0u;
+                    const unsigned sz1 = (cok && (unsigned)(x0 + 32 + lane) < (unsigned)W) ? 4u : 0u;
 #pragma unroll
-                for (int r = 0; r < DW_IH; ++r) {
-                    const bool rok = (unsigned)r - rlo < rcnt;
-                    cp_async4(dst + r * DW_PITCH * 4, p0, rok ? sz0 : 0u);
-                    if (lane < DW_IW - 32) cp_async4(dst + (r * DW_PITCH + 32) * 4, p1, rok ? sz1 : 0u);
-                    p0 += sy; p1 += sy;
+                    for (int r = 0; r < DW_IH; ++r) {
+                        const bool rok = (unsigned)r - rlo < rcnt;
+                        cp_async4(dst + r * DW_PITCH * 4, p0, rok ? sz0 : 0u);
+                        if (lane < DW_IW - 32) cp_async4(dst + (r * DW_PITCH + 32) * 4, p1, rok ? sz1 : 0u);
+                        p0 += sy; p1 += sy;
+                    }
                 }
             }
             cp_async_commit();
@@ -344,27 +347,27 @@ sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned*
 
         issue(cid * 8, 0);
 #pragma unroll 1
-        for (int k = 0; k < 8; ++k) {
-            const int c = cid * 8 + k, buf = k & 1;
+        for (int k = 0; k < 4; ++k) {                      // four channel pairs; this lane's channel is c + half
+            const int c = cid * 8 + 2 * k, buf = k & 1;
             if (TMA) {
-                if (k + 1 < 8) issue(c + 1, buf ^ 1);
+                if (k + 1 < 4) issue(c + 2, buf ^ 1);
                 mbar_wait(bar_s + 8 * buf, (ph >> buf) & 1u);
                 ph ^= 1u << buf;
             } else {
-                if (k + 1 < 8) issue(c + 1, buf ^ 1); else cp_async_commit();
+                if (k + 1 < 4) issue(c + 2, buf ^ 1); else cp_async_commit();
                 cp_async_wait<1>();
             }
             __syncwarp();
             float w[SH_WROW];
             {
-                const float4* wp = reinterpret_cast<const float4*>(wbuf + buf * 64);
+                const float4* wp = reinterpret_cast<const float4*>(wbuf + buf * DW_TAPS + half * SH_WROW);
 #pragma unroll
                 for (int q = 0; q < SH_WROW / 4; ++q) {
                     const float4 v = wp[q];
                     w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
                 }
             }
-            const float* pl = inbuf + buf * DW_PLANE_PAD + (4 * by) * DW_PITCH + 4 * bx;
+            const float* pl = inbuf + buf * DW_PLANE_PAD + half * DW_PLANE + (4 * by) * DW_PITCH + 4 * bx;
             float acc[4][4];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
@@ -401,7 +404,7 @@ sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned*
                 float4 v;
                 v.x = fmaxf(fmaf(acc[oy][0], scale, bs), 0.f); v.y = fmaxf(fmaf(acc[oy][1], scale, bs), 0.f);
                 v.z = fmaxf(fmaf(acc[oy][2], scale, bs), 0.f); v.w = fmaxf(fmaf(acc[oy][3], scale, bs), 0.f);
-                *reinterpret_cast<float4*>(outbuf + k * (DW_TH * DW_TW) + (4 * by + oy) * DW_TW + 4 * bx) = v;
+                *reinterpret_cast<float4*>(outbuf + (2 * k + half) * (DW_TH * DW_TW) + (4 * by + oy) * DW_TW + 4 * bx) = v;
             }
             __syncwarp();                   // plane reads done before the next prefetch may overwrite; out plane visible
         }
@@ -1129,7 +1132,7 @@ static inline int sh_wp(int W) { return (W + 3) & ~3; }          // activation r
 static inline int sh_ty16(int H) { return (int)ceil_div64(H, DW_TH); }
 
 size_t seghead_workspace_bytes(int N, int H, int W) {
-    const size_t px = (size_t)N * H * W, units = (size_t)N * sh_ty16(H) * sh_tx2(W) * 4;
+    const size_t px = (size_t)N * H * W, units = (size_t)N * sh_ty16(H) * sh_tx2(W) * (DW_TH / SH_TH);
     return align_up(px * 3 * 4, 1024) + align_up(units * (SH_MID / 64) * 2 * SH_CHUNK, 1024) +
            align_up((size_t)N * H * sh_wp(W) * SH_MID * 4, 1024) + 4096;
 }
@@ -1163,7 +1166,7 @@ static int sh_sm_count() {
 }
 
 // Tensor map of the activation buffer y [N*256][H][Wp] (valid width W: columns beyond it and rows/columns outside the image
-// read as zeros), box = one channel's 22 x 40 window.  cuTensorMapEncodeTiled comes from the driver through the runtime's entry
+// read as zeros), box = the 14 x 40 windows of a channel pair.  cuTensorMapEncodeTiled comes from the driver through the runtime's entry
 // point lookup (no link-time dependency on libcuda).  MANET_SH_DW_TMA=0 or any failure falls back to the cp.async path --
 // of the SAME kernel family, not a different implementation.
 static bool sh_encode_ymap(CUtensorMap* map, float* y, int N, int H, int W, int Wp) {
@@ -1182,7 +1185,7 @@ static bool sh_encode_ymap(CUtensorMap* map, float* y, int N, int H, int W, int 
     if (!enc) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N * SH_MID};
     const cuuint64_t strides[2] = {(cuuint64_t)Wp * 4, (cuuint64_t)H * Wp * 4};
-    const cuuint32_t box[3] = {DW_PITCH, DW_IH, 1}, estr[3] = {1, 1, 1};
+    const cuuint32_t box[3] = {DW_PITCH, DW_IH, 2}, estr[3] = {1, 1, 1};          // the windows of a channel pair
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -1210,7 +1213,7 @@ static int launch_seghead_forward(const void* packed, int in_dim, ShSource src, 
     const ShLayout L = sh_layout();
     const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
     const size_t px = (size_t)N * H * W;
-    const int TX2 = sh_tx2(W), TY16 = sh_ty16(H), TX = TX2, TY = 4 * TY16, tiles = N * TX2 * TY16, units = 4 * tiles;
+    const int TX2 = sh_tx2(W), TY16 = sh_ty16(H), TX = TX2, TY = (DW_TH / SH_TH) * TY16, tiles = N * TX2 * TY16, units = (DW_TH / SH_TH) * tiles;
     Carver cv(ws, ws_bytes);
     unsigned* amax = cv.take<unsigned>(16, 1024);                 // [0] layer-1 input, [1..3] outputs of layers 1..3, [8..11] work counters
     CUtensorMap* ymap_d = cv.take<CUtensorMap>(1, 128);
@@ -1257,7 +1260,7 @@ static int launch_seghead_forward(const void* packed, int in_dim, ShSource src, 
     for (int i = 0; i < SH_LAYERS; ++i) {
         const float* dwW = reinterpret_cast<const float*>(pk + L.l[i].dwW);
         const unsigned* bound = reinterpret_cast<const unsigned*>(pk + L.l[i].bound);
-        const int dw_grid = (int)imin64(2 * sms, ceil_div64((int64_t)tiles * (L.l[i].cin_p / 8), DW_WARPS));
+        const int dw_grid = (int)imin64(3 * sms, ceil_div64((int64_t)tiles * (L.l[i].cin_p / 8), DW_WARPS));
         if (i == 0)
             launch_k(sh_dw_kernel<SH_IN_PAD, false>, dim3(dw_grid), dim3(DW_WARPS * 32), DW_SMEM, stream, src, in_dim, dwW,
                      (const unsigned*)amax, bound, aimg, amax + 8 + i, N, H, W, TX2, TY16, ymap, shared1);
