@@ -11,8 +11,8 @@
 //     computes a 4x4 block of outputs from a 10x10 window read with 128-bit shared-memory loads, its 49 taps in registers.
 //     The pair's input planes (14x40 with halo) and taps arrive through a per-warp double buffer (TMA box / cp.async), so
 //     the loop over channels is a compact rolled loop with no CTA barrier.  Eight channels at a time are converted to
-//     the tensor-core operand: x*2^e = hi + lo in fp16, written as 16-byte chunks of the 128-byte-swizzled K-major
-//     shared-memory image of the unit.
+//     the tensor-core operand: x*2^e = hi + lo in fp16, written as 16-byte chunks of the K-major shared-memory image
+//     of the unit (no-swizzle canonical layout: a warp's 32 rows of one 8-channel column group are 512 contiguous bytes).
 //     The scale 2^e is one power of two per layer, derived on the device from a BOUND of the layer's outputs
 //     (sum|w'| * max|input| + max|b'|, the max coming from the previous kernel's epilogue): hi+lo carries 22
 //     significant bits of every element that matters and an absolute error below 2^-39 of the bound for the rest.
@@ -47,6 +47,10 @@ constexpr int SH_UNIT = SH_TH * SH_TW;   // 128 rows = UMMA M
 constexpr int SH_XOFF = 0;               // (experiment knob: unit columns start at 32*tx - SH_XOFF)
 constexpr int SH_CHUNK = 16384;          // 128 rows x 128 B: one (k-block, part) of a unit
 constexpr int SH_LAYERS = 4;
+// Activation operand image (A), per (unit, k-block, part) 16 KB WITHOUT swizzle: [column group of 8 channels (8)][row group (16)]
+// [8 rows x 16 B] -- a warp of the depthwise kernel owns one column group of 32 consecutive rows = 512 contiguous bytes per store
+constexpr uint32_t SH_A_LBO = 2048, SH_A_SBO = 128;     // bytes between core matrices along K / along M
+constexpr uint64_t SH_A_KSTEP = (2 * SH_A_LBO) >> 4;    // descriptor start-address step per K = 16 (two column groups)
 constexpr int SH_WROW = 52;              // per channel: 49 taps, bias, 2 pad (13 x 16 bytes)
 
 // ---------------------------------------------------------------------------------------------- packed parameters
@@ -337,8 +341,8 @@ sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned*
 #pragma unroll 1
             for (int j = 0; j < (DW_TH * DW_TW) / 32; ++j) {
                 const int px = lane + 32 * j, y = px >> 5, row = (y & 3) * SH_TW + (px & 31);
-                uint8_t* dst = img_tile + (size_t)(y >> 2) * TX2 * UNIT_BYTES + (size_t)((cid >> 3) * 2) * SH_CHUNK + (size_t)(row >> 3) * 1024 +
-                               (size_t)(row & 7) * 128 + (size_t)(((cid & 7) ^ (row & 7)) << 4);
+                uint8_t* dst = img_tile + (size_t)(y >> 2) * TX2 * UNIT_BYTES + (size_t)((cid >> 3) * 2) * SH_CHUNK + (size_t)(cid & 7) * SH_A_LBO +
+                               (size_t)row * 16;
                 *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
                 *reinterpret_cast<uint4*>(dst + SH_CHUNK) = make_uint4(0, 0, 0, 0);
             }
@@ -426,8 +430,7 @@ sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned*
                     const __half2 l = __floats2half2_rn(f[2 * q] - hf.x, f[2 * q + 1] - hf.y);
                     hi[q] = *reinterpret_cast<const uint32_t*>(&h); lo[q] = *reinterpret_cast<const uint32_t*>(&l);
                 }
-                uint8_t* dst = img_tile + (size_t)(y >> 2) * TX2 * UNIT_BYTES + (size_t)(kb * 2) * SH_CHUNK + (size_t)(row >> 3) * 1024 +
-                               (size_t)(row & 7) * 128 + (size_t)((c8 ^ (row & 7)) << 4);
+                uint8_t* dst = img_tile + (size_t)(y >> 2) * TX2 * UNIT_BYTES + (size_t)(kb * 2) * SH_CHUNK + (size_t)c8 * SH_A_LBO + (size_t)row * 16;
                 *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<uint4*>(dst + SH_CHUNK) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
@@ -549,12 +552,12 @@ sh_pw_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ amax
 #endif
                 tc_fence_after();
                 const uint32_t sA = base + st.idx * PW_STAGE_BYTES, sB = sA + PW_A_BYTES;
-                const uint64_t dAh = smem_desc_sw128(sA), dAl = smem_desc_sw128(sA + SH_CHUNK);
+                const uint64_t dAh = smem_desc_nosw(sA, SH_A_LBO, SH_A_SBO), dAl = smem_desc_nosw(sA + SH_CHUNK, SH_A_LBO, SH_A_SBO);
                 const uint64_t dBh = smem_desc_sw128(sB), dBl = smem_desc_sw128(sB + 2 * SH_CHUNK);
                 if (elect_one()) {
-                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, dAh + 2 * k, dBh + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, dAl + 2 * k, dBh + 2 * k, idesc, 1u);
-                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, dAh + 2 * k, dBl + 2 * k, idesc, 1u);
+                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, dAh + SH_A_KSTEP * k, dBh + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, dAl + SH_A_KSTEP * k, dBh + 2 * k, idesc, 1u);
+                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, dAh + SH_A_KSTEP * k, dBl + 2 * k, idesc, 1u);
                     tc_commit(empty_b + 8 * st.idx);
                 }
                 __syncwarp();
@@ -751,12 +754,12 @@ sh_pwm_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ ama
                 mbar_wait(full_b + 8 * st.idx, st.phase);
                 tc_fence_after();
                 const uint32_t sA = base + st.idx * PW_STAGE_BYTES, sB = sA + PW_A_BYTES;
-                const uint64_t dAh = smem_desc_sw128(sA), dAl = smem_desc_sw128(sA + SH_CHUNK);
+                const uint64_t dAh = smem_desc_nosw(sA, SH_A_LBO, SH_A_SBO), dAl = smem_desc_nosw(sA + SH_CHUNK, SH_A_LBO, SH_A_SBO);
                 const uint64_t dBh = smem_desc_sw128(sB), dBl = smem_desc_sw128(sB + 2 * SH_CHUNK);
                 if (elect_one()) {
-                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, dAh + 2 * k, dBh + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, dAl + 2 * k, dBh + 2 * k, idesc, 1u);
-                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, dAh + 2 * k, dBl + 2 * k, idesc, 1u);
+                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, dAh + SH_A_KSTEP * k, dBh + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, dAl + SH_A_KSTEP * k, dBh + 2 * k, idesc, 1u);
+                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, dAh + SH_A_KSTEP * k, dBl + 2 * k, idesc, 1u);
                     tc_commit_mcast(empty_b + 8 * st.idx, mask);
                 }
                 __syncwarp();
@@ -1002,14 +1005,14 @@ sh_pw2_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ ama
 #endif
                     tc_fence_after();
                     const int kb = sp >> 1;
-                    const uint64_t dA = smem_desc_sw128(base + PW2_SMEM_A + st.idx * PW2_STAGE_BYTES);
+                    const uint64_t dA = smem_desc_nosw(base + PW2_SMEM_A + st.idx * PW2_STAGE_BYTES, SH_A_LBO, SH_A_SBO);
                     const uint64_t dBh = smem_desc_sw128(base + (kb * 2) * SH_CHUNK), dBl = smem_desc_sw128(base + (kb * 2 + 1) * SH_CHUNK);
                     if (elect_one()) {
                         if ((sp & 1) == 0) {      // hi part: ah.wh, ah.wl
-                            for (int k4 = 0; k4 < 4; ++k4) umma2_f16(d_tmem, dA + 2 * k4, dBh + 2 * k4, idesc, (sp | k4) ? 1u : 0u);
-                            for (int k4 = 0; k4 < 4; ++k4) umma2_f16(d_tmem, dA + 2 * k4, dBl + 2 * k4, idesc, 1u);
+                            for (int k4 = 0; k4 < 4; ++k4) umma2_f16(d_tmem, dA + SH_A_KSTEP * k4, dBh + 2 * k4, idesc, (sp | k4) ? 1u : 0u);
+                            for (int k4 = 0; k4 < 4; ++k4) umma2_f16(d_tmem, dA + SH_A_KSTEP * k4, dBl + 2 * k4, idesc, 1u);
                         } else {                  // lo part: al.wh
-                            for (int k4 = 0; k4 < 4; ++k4) umma2_f16(d_tmem, dA + 2 * k4, dBh + 2 * k4, idesc, 1u);
+                            for (int k4 = 0; k4 < 4; ++k4) umma2_f16(d_tmem, dA + SH_A_KSTEP * k4, dBh + 2 * k4, idesc, 1u);
                         }
                         tc_commit2(empty_b + 8 * st.idx);
                     }

@@ -75,6 +75,12 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+// K-major operand WITHOUT swizzle ("interleaved" canonical layout): a core matrix is 8 rows x 16 bytes stored as 128 contiguous
+// bytes; `sbo` = byte distance between core matrices adjacent along M/N (8-row groups), `lbo` = along K (16-byte column groups).
+// Layout type 0.  A producer that owns one 16-byte column group of consecutive rows then writes full 128-byte lines.
+__device__ __forceinline__ uint64_t smem_desc_nosw(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
+}
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) at [4,6); a/b format F16 (0);
 // a/b K-major (0); n_dim = N>>3 at [17,23); m_dim = M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
