@@ -451,6 +451,44 @@ constexpr int PW_EPI_WARPS = 8;
 constexpr int PW_THREADS = 32 * (2 + PW_EPI_WARPS);
 enum { PW_RELU_NCHW = 0, PW_FINAL = 1 };
 
+// Epilogue of one unit for one thread (= one accumulator row = one pixel, 128 of the 256 output channels): un-scale, folded bias,
+// ReLU, then either the NCHW store of the activations (+ their running maximum, which sets the next layer's operand scale) or the
+// last layer's 256 -> 1 convolution as a dot product.  TMEM loads are software pipelined (32 columns in flight).
+template <int MODE>
+__device__ __forceinline__ float pw_epilogue_rows(uint32_t taddr, float ri, const float4* __restrict__ cv4, const float4* __restrict__ bv4,
+                                                  const float4* __restrict__ wv4, float bias5, bool valid, float* __restrict__ op,
+                                                  size_t plane, float& vmax) {
+    float dot = bias5;
+    uint32_t r[2][32];
+    tmem_ld32(taddr, r[0]);
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+        tmem_ld_wait_dep(r[ch & 1]);
+        if (ch + 1 < 4) tmem_ld32(taddr + (ch + 1) * 32, r[(ch + 1) & 1]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 cv = cv4[ch * 8 + i], bv = bv4[ch * 8 + i];
+            const uint32_t* q = r[ch & 1] + 4 * i;
+            float4 v;
+            v.x = fmaxf(fmaf(__uint_as_float(q[0]) * ri, cv.x, bv.x), 0.f);
+            v.y = fmaxf(fmaf(__uint_as_float(q[1]) * ri, cv.y, bv.y), 0.f);
+            v.z = fmaxf(fmaf(__uint_as_float(q[2]) * ri, cv.z, bv.z), 0.f);
+            v.w = fmaxf(fmaf(__uint_as_float(q[3]) * ri, cv.w, bv.w), 0.f);
+            if (MODE == 0) {                  // PW_RELU_NCHW
+                if (valid) {
+                    float* o = op + (size_t)(ch * 32 + i * 4) * plane;
+                    o[0] = v.x; o[plane] = v.y; o[2 * plane] = v.z; o[3 * plane] = v.w;
+                    vmax = fmaxf(fmaxf(vmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+                }
+            } else {
+                const float4 wv = wv4[ch * 8 + i];
+                dot = fmaf(v.x, wv.x, dot); dot = fmaf(v.y, wv.y, dot); dot = fmaf(v.z, wv.z, dot); dot = fmaf(v.w, wv.w, dot);
+            }
+        }
+    }
+    return dot;
+}
+
 struct PwRing {
     int idx; uint32_t phase;
     __device__ PwRing() : idx(0), phase(0) {}
@@ -596,34 +634,7 @@ sh_pw_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ amax
 #endif
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * SH_MID + half * 128;
-            float dot = bias5;
-            uint32_t r[2][32];
-            tmem_ld32(taddr, r[0]);
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                tmem_ld_wait_dep(r[ch & 1]);
-                if (ch + 1 < 4) tmem_ld32(taddr + (ch + 1) * 32, r[(ch + 1) & 1]);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float4 cv = cv4[ch * 8 + i], bv = bv4[ch * 8 + i];
-                    const uint32_t* q = r[ch & 1] + 4 * i;
-                    float4 v;
-                    v.x = fmaxf(fmaf(__uint_as_float(q[0]) * ri, cv.x, bv.x), 0.f);
-                    v.y = fmaxf(fmaf(__uint_as_float(q[1]) * ri, cv.y, bv.y), 0.f);
-                    v.z = fmaxf(fmaf(__uint_as_float(q[2]) * ri, cv.z, bv.z), 0.f);
-                    v.w = fmaxf(fmaf(__uint_as_float(q[3]) * ri, cv.w, bv.w), 0.f);
-                    if (MODE == PW_RELU_NCHW) {
-                        if (valid) {
-                            float* o = op + (size_t)(ch * 32 + i * 4) * plane;
-                            o[0] = v.x; o[plane] = v.y; o[2 * plane] = v.z; o[3 * plane] = v.w;
-                            vmax = fmaxf(fmaxf(vmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
-                        }
-                    } else {
-                        const float4 wv = wv4[ch * 8 + i];
-                        dot = fmaf(v.x, wv.x, dot); dot = fmaf(v.y, wv.y, dot); dot = fmaf(v.z, wv.z, dot); dot = fmaf(v.w, wv.w, dot);
-                    }
-                }
-            }
+            const float dot = pw_epilogue_rows<MODE>(taddr, ri, cv4, bv4, wv4, bias5, valid, op, plane, vmax);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty + 8 * acc.idx);
@@ -791,34 +802,7 @@ sh_pwm_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ ama
             mbar_wait(tmem_full + 8 * acc.idx, acc.phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * SH_MID + half * 128;
-            float dot = bias5;
-            uint32_t r[2][32];
-            tmem_ld32(taddr, r[0]);
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                tmem_ld_wait_dep(r[ch & 1]);
-                if (ch + 1 < 4) tmem_ld32(taddr + (ch + 1) * 32, r[(ch + 1) & 1]);
-#pragma unroll
-                for (int i2 = 0; i2 < 8; ++i2) {
-                    const float4 cv = cv4[ch * 8 + i2], bv = bv4[ch * 8 + i2];
-                    const uint32_t* q = r[ch & 1] + 4 * i2;
-                    float4 v;
-                    v.x = fmaxf(fmaf(__uint_as_float(q[0]) * ri, cv.x, bv.x), 0.f);
-                    v.y = fmaxf(fmaf(__uint_as_float(q[1]) * ri, cv.y, bv.y), 0.f);
-                    v.z = fmaxf(fmaf(__uint_as_float(q[2]) * ri, cv.z, bv.z), 0.f);
-                    v.w = fmaxf(fmaf(__uint_as_float(q[3]) * ri, cv.w, bv.w), 0.f);
-                    if (MODE == PW_RELU_NCHW) {
-                        if (valid) {
-                            float* o = op + (size_t)(ch * 32 + i2 * 4) * plane;
-                            o[0] = v.x; o[plane] = v.y; o[2 * plane] = v.z; o[3 * plane] = v.w;
-                            vmax = fmaxf(fmaxf(vmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
-                        }
-                    } else {
-                        const float4 wv = wv4[ch * 8 + i2];
-                        dot = fmaf(v.x, wv.x, dot); dot = fmaf(v.y, wv.y, dot); dot = fmaf(v.z, wv.z, dot); dot = fmaf(v.w, wv.w, dot);
-                    }
-                }
-            }
+            const float dot = pw_epilogue_rows<MODE>(taddr, ri, cv4, bv4, wv4, bias5, valid, op, plane, vmax);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty + 8 * acc.idx);
@@ -1070,34 +1054,7 @@ sh_pw2_kernel(const uint8_t* __restrict__ Aimg, const unsigned* __restrict__ ama
 #endif
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * SH_MID + half * 128;
-            float dot = bias5;
-            uint32_t r[2][32];
-            tmem_ld32(taddr, r[0]);
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                tmem_ld_wait_dep(r[ch & 1]);
-                if (ch + 1 < 4) tmem_ld32(taddr + (ch + 1) * 32, r[(ch + 1) & 1]);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float4 cv = cv4[ch * 8 + i], bv = bv4[ch * 8 + i];
-                    const uint32_t* q = r[ch & 1] + 4 * i;
-                    float4 v;
-                    v.x = fmaxf(fmaf(__uint_as_float(q[0]) * ri, cv.x, bv.x), 0.f);
-                    v.y = fmaxf(fmaf(__uint_as_float(q[1]) * ri, cv.y, bv.y), 0.f);
-                    v.z = fmaxf(fmaf(__uint_as_float(q[2]) * ri, cv.z, bv.z), 0.f);
-                    v.w = fmaxf(fmaf(__uint_as_float(q[3]) * ri, cv.w, bv.w), 0.f);
-                    if (MODE == PW_RELU_NCHW) {
-                        if (valid) {
-                            float* o = op + (size_t)(ch * 32 + i * 4) * plane;
-                            o[0] = v.x; o[plane] = v.y; o[2 * plane] = v.z; o[3 * plane] = v.w;
-                            vmax = fmaxf(fmaxf(vmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
-                        }
-                    } else {
-                        const float4 wv = wv4[ch * 8 + i];
-                        dot = fmaf(v.x, wv.x, dot); dot = fmaf(v.y, wv.y, dot); dot = fmaf(v.z, wv.z, dot); dot = fmaf(v.w, wv.w, dot);
-                    }
-                }
-            }
+            const float dot = pw_epilogue_rows<MODE>(taddr, ri, cv4, bv4, wv4, bias5, valid, op, plane, vmax);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(r_tmem_empty + 8 * acc.idx);
