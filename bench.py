@@ -287,12 +287,15 @@ def run_own_arm(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_s, e2e_s, e2e_sync_s, serial_s, e2e_stream_s = (float(t[i]) for i in range(5))
 
-    sharded = sharded_1080p_leg(dev, rank, world) if os.environ.get("MANET_BENCH_SHARDED", "1") == "1" else None
-    # the head / propagation legs describe one GPU; multi-GPU runs (independent sequences) report the scaling metric only
+    # the head / propagation legs describe one GPU; multi-GPU runs (independent sequences) report the scaling metric only.
+    # They run BEFORE the 1080p sharded-matching leg: right after that leg's ~0.2 s of back-to-back 28 ms tensor-core kernels the
+    # head's own leg read 0.81 ms instead of 0.62 ms (power management still settling), while the propagation leg a second later
+    # was unaffected.
     extra = world == 1 and os.environ.get("MANET_BENCH_SEGHEAD", "1") == "1"
     seghead = seghead_leg(dev) if extra else None
     propagation = propagation_leg(dev) if extra else None
     session = session_leg(dev) if extra else None
+    sharded = sharded_1080p_leg(dev, rank, world) if os.environ.get("MANET_BENCH_SHARDED", "1") == "1" else None
 
     if rank == 0:
         peaks = load_peaks()
