@@ -29,8 +29,11 @@
 //       a 40-60 KB straight-line body streams through the 32 KB instruction cache
 //   warp = channel, lane = 2x4 pixel block, compact rolled loop, NCHW, per-layer scale         247  shared-memory bound
 //   4x4 blocks (6.25 instead of 10 loaded floats per output), warp-level work items            238  57 % of issued instructions not FFMA
-//   one-pointer cp.async staging, taps through shared memory                                   162  (this file) issue 67 %, FMA pipe 44 %
+//   one-pointer cp.async staging, taps through shared memory                                   162  issue 67 %, FMA pipe 44 %
 //   same with channel pairs on FFMA2 (7 warps per SM fit)                                      178  stall "wait": too few warps
+//   TMA tensor-map staging (layers 2-4), LDS kept through the 128-byte alignment               137  issue 61 %, long_scoreboard
+//   two channels per warp (half-warps) over 8x32 tiles: 12 warps per SM, no padding in H       112  issue 70 %, FMA pipe 55 %
+//   no-swizzle operand image: conversion stores as 512-byte runs                               105  (this file) issue 76 %, FMA pipe 59 %
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
