@@ -448,3 +448,23 @@ def test_gpu_int_seghead_matches_reference(golden):
         assert bool((lm[0]["s"] == 1).all()) == bool(g["final_local_mem_is_ones"])
     finally:
         cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE = saved
+
+
+def test_reference_checkpoint_keys_load():
+    """A state_dict of the reference's own DynamicSegHead (IntVOS.py:510-525) loads into the drop-in module: same parameter and
+    buffer names and shapes (only BatchNorm's num_batches_tracked bookkeeping may differ)."""
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference tree not mounted")
+    from cvpr2020_manet_b200.networks.seghead import DynamicSegHead
+    ref = ref_shim.load_reference()
+    torch.manual_seed(3)
+    theirs = ref.DynamicSegHead().state_dict()
+    ours = DynamicSegHead()
+    result = ours.load_state_dict(theirs, strict=False)
+    assert [k for k in result.missing_keys if not k.endswith("num_batches_tracked")] == []
+    assert [k for k in result.unexpected_keys if not k.endswith("num_batches_tracked")] == []
+    mine = ours.state_dict()
+    for k, v in theirs.items():
+        if k in mine:
+            assert torch.equal(mine[k], v), k
