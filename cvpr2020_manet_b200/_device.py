@@ -29,14 +29,24 @@ def stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+_MAX_WORKSPACES = 32      # (device, stream, tag) entries kept; least recently used are dropped first
+
+
 def workspace(device: torch.device, nbytes: int, tag: str) -> torch.Tensor:
-    """A cached scratch buffer per (device, current stream, tag), grown on demand."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(),
-           stream_ptr(device), tag)
-    buf = _workspaces.get(key)
+    """A cached scratch buffer per (device, current stream, tag), grown on demand.  Kernels that use it are enqueued on
+    that stream only, so reuse is ordered by the stream; the cache is LRU-bounded so that code creating short-lived streams
+    does not accumulate one buffer per stream (a dropped buffer returns to torch's caching allocator, which ties a block
+    to the stream that was current when it was allocated -- the stream that used it)."""
+    dev_index = device.index if device.index is not None else torch.cuda.current_device()
+    stream = torch.cuda.current_stream(device)
+    key = (dev_index, stream.cuda_stream, tag)
+    buf = _workspaces.pop(key, None)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-        _workspaces[key] = buf
+        with torch.cuda.device(device):
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+    _workspaces[key] = buf                      # re-insert: most recently used last
+    while len(_workspaces) > _MAX_WORKSPACES:
+        _workspaces.pop(next(iter(_workspaces)))
     return buf
 
 

@@ -59,11 +59,15 @@ SIGNATURES = {
     "manet_seghead_pack": (c_int, [POINTER(_P), _I, _I, _F, _P, _P]),
     "manet_seghead_forward": (c_int, [_P, _I, _P, POINTER(_I64), _I, _I, _I, _P, _P, _SZ, _P]),
     "manet_seghead_forward_parts": (c_int, [_P, _P, _I64, _I64, _I64, _I, _P, _P, _P, _P, _I, _I, _I, _P, _P, _SZ, _P]),
+    "manet_seghead_forward_interaction": (c_int, [_P, _P, _I64, _I64, _I64, _I, _P, _P, _P, _I, _I, _I, _P, _P, _SZ, _P]),
     "manet_upsample_argmax": (c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "manet_rough_roi": (c_int, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "manet_profile_enable": (c_int, [_I]),
     "manet_profile_reset": (c_int, []),
     "manet_profile_read": (c_int, [_I, POINTER(c_float), _I, POINTER(c_int)]),
+    "manet_profile_launch_count": (ctypes.c_longlong, []),
+    "manet_profile_reset_launches": (c_int, []),
+    "manet_microbench_tmem_ld": (c_int, [_I, _I, _I, _I, POINTER(ctypes.c_longlong), _P]),
     "manet_session_create": (_P, [_I, _I, _I, _I, _I, _I]),
     "manet_session_destroy": (None, [_P]),
     "manet_session_host_buffers": (c_int, [_P] + [POINTER(_P)] * 7),

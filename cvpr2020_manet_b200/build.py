@@ -20,7 +20,7 @@ LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libmanet_b200.so")
 OBJDIR = os.path.join(PKG, "build")
 SOURCES = ["api.cu", "global_match_simt.cu", "global_match_umma.cu", "select_pixels.cu", "local_match.cu", "local_match_umma.cu",
-           "map_memory.cu", "correlation.cu", "seghead.cu", "frame_glue.cu"]
+           "map_memory.cu", "correlation.cu", "seghead.cu", "frame_glue.cu", "microbench.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -3,6 +3,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <new>
 
 #include "common.cuh"
@@ -65,9 +66,18 @@ int seghead_forward_tensor(const void*, int, const float*, const int64_t*, int, 
 int seghead_forward_parts(const void*, const float*, int64_t, int64_t, int64_t, int, const float*, const float*, const int32_t*,
                           const int32_t*, int, int, int, float*, void*, size_t, cudaStream_t);
 
+int seghead_forward_interaction(const void*, const float*, int64_t, int64_t, int64_t, int, const int32_t*, const int32_t*,
+                                const int32_t*, int, int, int, float*, void*, size_t, cudaStream_t);
+
 int launch_upsample_argmax(const float*, int, int, int, int, int, int64_t*, int32_t*, cudaStream_t);
 
 int launch_rough_roi(const int32_t*, int, int, int, int, int32_t*, int*, cudaStream_t);
+
+int launch_tmem_ld_bench(int, int, int, int, long long*, float*, cudaStream_t);
+
+// ---- launch counter (bench.py's gpu_launches): relaxed atomic, host threads may launch concurrently
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // ---- optional kernel timing pools
 struct ProfPool { cudaEvent_t* start; cudaEvent_t* stop; int cap; int n; };
@@ -85,20 +95,42 @@ void profile_end(int slot, cudaStream_t stream) {
     if (p.n < p.cap) { cudaEventRecord(p.stop[p.n], stream); ++p.n; }
 }
 
+// per-device caches (index = device ordinal): compute-capability major and SM count, 0 = not queried yet
+static std::atomic<int> g_cc_major[kMaxDevices];
+static std::atomic<int> g_sm_count[kMaxDevices];
+
 static int arch_ok() {
-    static int cached = -2;
-    if (cached != -2) return cached;
     int dev = 0, major = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    if (cudaGetDevice(&dev) != cudaSuccess) {
         set_error("no usable CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
         return MANET_E_ARCH;
     }
+    const bool cacheable = dev >= 0 && dev < kMaxDevices;
+    if (cacheable) major = g_cc_major[dev].load(std::memory_order_relaxed);
+    if (major == 0) {
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+            set_error("no usable CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+            return MANET_E_ARCH;
+        }
+        if (cacheable) g_cc_major[dev].store(major, std::memory_order_relaxed);
+    }
     if (major != 10) {
-        set_error("libmanet_b200 is built for sm_100a only; current device has compute capability %d.x", major);
+        set_error("libmanet_b200 is built for sm_100a only; device %d has compute capability %d.x", dev, major);
         return MANET_E_ARCH;
     }
-    cached = 0;
     return 0;
+}
+
+int device_sm_count() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    const bool cacheable = dev >= 0 && dev < kMaxDevices;
+    if (cacheable) sms = g_sm_count[dev].load(std::memory_order_relaxed);
+    if (sms <= 0) {
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        if (cacheable) g_sm_count[dev].store(sms, std::memory_order_relaxed);
+    }
+    return sms;
 }
 
 }  // namespace manet
@@ -329,6 +361,18 @@ int manet_seghead_forward_parts(const void* packed, const float* emb, int64_t em
                                  prev_labels, gt_ids, n_objects, H, W, logits, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int manet_seghead_forward_interaction(const void* packed, const float* emb, int64_t emb_ch_stride, int64_t emb_row_stride,
+                                      int64_t emb_col_stride, int C, const int32_t* scribble_labels,
+                                      const int32_t* prev_round_labels, const int32_t* gt_ids, int n_objects, int H, int W,
+                                      float* logits, void* workspace, size_t workspace_bytes, manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(packed && emb && scribble_labels && gt_ids && logits && workspace, "seghead forward (interaction): null pointer");
+    MANET_REQUIRE(C >= 1 && C + 2 <= 128, "seghead forward (interaction): embedding channels + 2 must be <= 128");
+    return seghead_forward_interaction(packed, emb, emb_ch_stride, emb_row_stride, emb_col_stride, C, scribble_labels,
+                                       prev_round_labels, gt_ids, n_objects, H, W, logits, workspace, workspace_bytes,
+                                       (cudaStream_t)stream);
+}
+
 int manet_upsample_argmax(const float* logits, int n_objects, int h, int w, int out_h, int out_w, int64_t* labels_full,
                           int32_t* labels_small, manet_stream_t stream) {
     MANET_ARCH();
@@ -406,6 +450,27 @@ int manet_profile_read(int slot, float* ms_out, int capacity, int* n_out) {
     return 0;
 }
 
+long long manet_profile_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int manet_profile_reset_launches(void) { g_launches.store(0, std::memory_order_relaxed); return 0; }
+
+int manet_microbench_tmem_ld(int mode, int iters, int warps, int ctas, long long* cycles_out_host, manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(cycles_out_host && ctas >= 1 && ctas <= 4096, "tmem_ld bench: null pointer / bad CTA count");
+    long long* d_cycles = nullptr; float* d_sink = nullptr;
+    cudaError_t e = cudaMalloc(&d_cycles, sizeof(long long) * ctas);
+    if (e == cudaSuccess) e = cudaMalloc(&d_sink, sizeof(float));
+    if (e != cudaSuccess) { cudaFree(d_cycles); set_error("tmem_ld bench: %s", cudaGetErrorString(e)); return (int)e; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_tmem_ld_bench(mode, iters, warps, ctas, d_cycles, d_sink, st);
+    if (!rc) {
+        e = cudaMemcpyAsync(cycles_out_host, d_cycles, sizeof(long long) * ctas, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error("tmem_ld bench: %s", cudaGetErrorString(e)); rc = (int)e; }
+    }
+    cudaFree(d_cycles); cudaFree(d_sink);
+    return rc;
+}
+
 // ------------------------------------------------------------------------------------------ session
 // Two input/output slots so that the host->device copy of step i+1 overlaps the kernels of step i
 // (manet_session_submit_host / manet_session_wait); manet_session_step_host is submit+wait on slot 0.
@@ -415,6 +480,7 @@ struct SessionSlot {
     float *d_ref, *d_prev, *d_cur, *d_out_g, *d_out_l, *d_raw_l; // device
     int32_t *d_ref_lab, *d_prev_lab;
     cudaEvent_t ev_up, ev_done;
+    bool submitted;                                             // ev_done has been recorded at least once
 };
 
 struct manet_session {
@@ -476,7 +542,7 @@ manet_session_t* manet_session_create(int H, int W, int C, int N, int max_distan
     int32_t* hid = new int32_t[N];
     for (int i = 0; i < N; ++i) hid[i] = i;
     cudaMemcpyAsync(s->d_ids, hid, N * 4, cudaMemcpyHostToDevice, s->stream);
-    fill_kernel<<<148 * 4, 256, 0, s->stream>>>(s->d_gmem, 1.0f, (int64_t)px * N * n_frames);
+    count_launch(), fill_kernel<<<148 * 4, 256, 0, s->stream>>>(s->d_gmem, 1.0f, (int64_t)px * N * n_frames);
     cudaMemsetAsync(s->d_lmem, 0, map * n_frames * kMemoryRounds, s->stream);
     cudaMemsetAsync(s->d_ldist, 0, sizeof(float) * n_frames * kMemoryRounds, s->stream);
     cudaStreamSynchronize(s->stream);
@@ -588,6 +654,9 @@ int manet_session_submit_host(manet_session_t* s, int slot, int frame, int inter
     MANET_REQUIRE(s && (slot == 0 || slot == 1), "session: null / bad slot");
     SessionSlot& t = s->slot[slot];
     int rc;
+    // A slot's device buffers are rewritten by this upload: order it after the slot's previous step on the DEVICE, so a caller
+    // that re-submits a slot without manet_session_wait cannot race the kernels still reading them (no host cost).
+    if (t.submitted) cudaStreamWaitEvent(s->copy_stream, t.ev_done, 0);
     if (flags & MANET_STEP_STREAM) {
         // Streaming propagation (test.py:237-259 driven from host memory): the annotated frame and its scribble labels
         // are uploaded when the sequence starts, and the previous frame of step i is the current frame of step i-1, which
@@ -622,6 +691,7 @@ int manet_session_submit_host(manet_session_t* s, int slot, int frame, int inter
     cudaMemcpyAsync(t.h_out_g, t.d_out_g, map, cudaMemcpyDeviceToHost, s->stream);
     cudaMemcpyAsync(t.h_out_l, t.d_out_l, map, cudaMemcpyDeviceToHost, s->stream);
     cudaEventRecord(t.ev_done, s->stream);
+    t.submitted = true;
     return check_launch("session submit");
 }
 

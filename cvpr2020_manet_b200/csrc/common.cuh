@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <mutex>
+
 #include "../../include/manet_b200.h"
 
 namespace manet {
@@ -26,8 +28,26 @@ int check_launch(const char* what);       // cudaGetLastError() -> code (+ messa
 // Optional per-kernel timing (bench.py's roofline leg): when enabled, launchers bracket the named
 // kernel with cudaEvents taken from a pool; see manet_profile_* in include/manet_b200.h.
 enum ProfileSlot { PROF_GLOBAL_UMMA = 0, PROF_LOCAL_WINDOW = 1, PROF_LOCAL_MIN = 2, PROF_SLOTS = 3 };
+void count_launch();                       // every launcher bumps this once per kernel launch (manet_profile_launch_count)
 void profile_begin(int slot, cudaStream_t stream);
 void profile_end(int slot, cudaStream_t stream);
+
+// Per-device one-time setup.  Function attributes (the >48 KB dynamic shared-memory opt-in) and device properties belong to
+// a device/context, not to the process: a host that drives several GPUs from one process (per-device threads, a session
+// on cuda:1 after cuda:0) must get them on each device.  `PerDevice::once(f)` runs f(device) the first time the CURRENT
+// device is seen by this call site (mutex-guarded; ~20 ns afterwards).
+constexpr int kMaxDevices = 64;
+struct PerDevice {
+    std::mutex mu; bool seen[kMaxDevices] = {};
+    template <typename F> void once(F f) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) dev = -1;
+        std::lock_guard<std::mutex> g(mu);
+        if (dev < 0 || dev >= kMaxDevices) { f(dev); return; }
+        if (!seen[dev]) { f(dev); seen[dev] = true; }
+    }
+};
+int device_sm_count();                     // multiprocessor count of the CURRENT device (cached per device)
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
@@ -76,6 +96,7 @@ static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 blo
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    count_launch();
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -156,7 +156,7 @@ static int fill_padded(const T* in, const int64_t* st, T* rin, int B, int C, int
     cudaError_t e = cudaMemsetAsync(rin, 0, bytes, stream);
     if (e != cudaSuccess) { set_error("correlation: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
     dim3 grid((W + 31) / 32, (C + 31) / 32, B * H);
-    nchw_to_padded_nhwc_kernel<T><<<grid, 256, 0, stream>>>(in, st[0], st[1], st[2], st[3], C, H, W, pad, rin);
+    count_launch(), nchw_to_padded_nhwc_kernel<T><<<grid, 256, 0, stream>>>(in, st[0], st[1], st[2], st[3], C, H, W, pad, rin);
     return check_launch("nchw_to_padded_nhwc_kernel");
 }
 
@@ -170,7 +170,7 @@ static int forward_t(const void* in1, const int64_t* s1v, const void* in2, const
     if ((rc = fill_padded<T>((const T*)in2, s2v, (T*)rin2, B, C, H, W, pad, stream))) return rc;
     if (oh == 0 || ow == 0) return 0;
     dim3 grid(ow, oh, B);
-    correlation_forward_kernel<T><<<grid, 128, 0, stream>>>((const T*)rin1, (const T*)rin2, (T*)out, C, H + 2 * pad, W + 2 * pad,
+    count_launch(), correlation_forward_kernel<T><<<grid, 128, 0, stream>>>((const T*)rin1, (const T*)rin2, (T*)out, C, H + 2 * pad, W + 2 * pad,
                                                            oc, oh, ow, ks, md, st1, st2);
     return check_launch("correlation_forward_kernel");
 }
@@ -186,9 +186,9 @@ static int backward_t(const void* in1, const int64_t* s1v, const void* in2, cons
     if ((rc = fill_padded<T>((const T*)in2, s2v, (T*)rin2, B, C, H, W, pad, stream))) return rc;
     int64_t total = (int64_t)B * C * H * W;
     unsigned grid = (unsigned)imin64(ceil_div64(total, 256), 148 * 16);
-    correlation_backward_kernel<T, 1><<<grid, 256, 0, stream>>>((const T*)rin2, (const T*)gout, gs[0], gs[1], gs[2], gs[3],
+    count_launch(), correlation_backward_kernel<T, 1><<<grid, 256, 0, stream>>>((const T*)rin2, (const T*)gout, gs[0], gs[1], gs[2], gs[3],
                                                                 (T*)gin1, B, C, H, W, pad, oc, oh, ow, ks, md, st1, st2);
-    correlation_backward_kernel<T, 2><<<grid, 256, 0, stream>>>((const T*)rin1, (const T*)gout, gs[0], gs[1], gs[2], gs[3],
+    count_launch(), correlation_backward_kernel<T, 2><<<grid, 256, 0, stream>>>((const T*)rin1, (const T*)gout, gs[0], gs[1], gs[2], gs[3],
                                                                 (T*)gin2, B, C, H, W, pad, oc, oh, ow, ks, md, st1, st2);
     return check_launch("correlation_backward_kernel");
 }

@@ -182,10 +182,10 @@ int launch_global_match_simt(const float* ref, int64_t rps, int64_t rcs, int64_t
     dim3 grid((unsigned)ceil_div64(M, TQ));
     if (mask != nullptr) {
         cudaFuncSetAttribute(global_match_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        global_match_simt_kernel<true><<<grid, SIMT_THREADS, dyn, stream>>>(ref, rps, rcs, R, nullptr, mask, query, qps, qcs, M, C, N, k, out);
+        count_launch(), global_match_simt_kernel<true><<<grid, SIMT_THREADS, dyn, stream>>>(ref, rps, rcs, R, nullptr, mask, query, qps, qcs, M, C, N, k, out);
     } else {
         cudaFuncSetAttribute(global_match_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        global_match_simt_kernel<false><<<grid, SIMT_THREADS, dyn, stream>>>(ref, rps, rcs, R, labels, nullptr, query, qps, qcs, M, C, N, k, out);
+        count_launch(), global_match_simt_kernel<false><<<grid, SIMT_THREADS, dyn, stream>>>(ref, rps, rcs, R, labels, nullptr, query, qps, qcs, M, C, N, k, out);
     }
     return check_launch("global_match_simt_kernel");
 }
@@ -194,7 +194,7 @@ int launch_pairwise_sqdist(const float* x, int64_t xps, int64_t xcs, int64_t n,
                            const float* y, int64_t yps, int64_t ycs, int64_t m,
                            int C, float* d, const float* ys_in, float* ys_out, cudaStream_t stream) {
     dim3 grid((unsigned)ceil_div64(m, TR), (unsigned)ceil_div64(n, TQ));
-    pairwise_sqdist_kernel<<<grid, SIMT_THREADS, 0, stream>>>(x, xps, xcs, n, y, yps, ycs, m, C, d, ys_in, ys_out);
+    count_launch(), pairwise_sqdist_kernel<<<grid, SIMT_THREADS, 0, stream>>>(x, xps, xcs, n, y, yps, ycs, m, C, d, ys_in, ys_out);
     return check_launch("pairwise_sqdist_kernel");
 }
 
@@ -205,13 +205,13 @@ __global__ void row_sqnorm_kernel(const float* __restrict__ x, int64_t ps, int64
 
 int launch_row_sqnorm(const float* x, int64_t ps, int64_t cs, int64_t n, int C, float* out, cudaStream_t stream) {
     if (n <= 0) return 0;
-    row_sqnorm_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, stream>>>(x, ps, cs, n, C, out);
+    count_launch(), row_sqnorm_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, stream>>>(x, ps, cs, n, C, out);
     return check_launch("row_sqnorm_kernel");
 }
 
 int launch_global_map_update(const float* nw, float* mem, float* out, int64_t n, int normalize, cudaStream_t stream) {
     if (n <= 0) return 0;
-    global_map_update_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, stream>>>(nw, mem, out, n, normalize);
+    count_launch(), global_map_update_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, stream>>>(nw, mem, out, n, normalize);
     return check_launch("global_map_update_kernel");
 }
 
@@ -305,7 +305,7 @@ int launch_global_match_argmin(const float* ref, int64_t rps, int64_t rcs, int64
     if (dyn > 160 * 1024) return fail_invalid("global match (argmin): too many objects");
     if (M == 0) return 0;
     cudaFuncSetAttribute(global_match_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    global_match_argmin_kernel<<<(unsigned)ceil_div64(M, TQ), SIMT_THREADS, dyn, stream>>>(ref, rps, rcs, R, labels, query, qps,
+    count_launch(), global_match_argmin_kernel<<<(unsigned)ceil_div64(M, TQ), SIMT_THREADS, dyn, stream>>>(ref, rps, rcs, R, labels, query, qps,
                                                                                              qcs, M, C, N, out, out_idx);
     return check_launch("global_match_argmin_kernel");
 }
@@ -314,7 +314,7 @@ int launch_global_match_backward(const float* ref, int64_t rps, int64_t rcs, con
                                  int64_t M, int C, int N, const int32_t* idx, const float* grad_out, float* grad_query,
                                  float* grad_ref, cudaStream_t stream) {
     if (M == 0) return 0;
-    global_match_backward_kernel<<<(unsigned)ceil_div64(M, 8), 256, 0, stream>>>(ref, rps, rcs, query, qps, qcs, M, C, N, idx,
+    count_launch(), global_match_backward_kernel<<<(unsigned)ceil_div64(M, 8), 256, 0, stream>>>(ref, rps, rcs, query, qps, qcs, M, C, N, idx,
                                                                                 grad_out, grad_query, grad_ref);
     return check_launch("global_match_backward_kernel");
 }

@@ -1006,26 +1006,24 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
     const int nb_ref = (int)ceil_div64(R, GM_CV_PIX), nb_q = (int)ceil_div64(p.M_pad, GM_CV_PIX);
     launch_k(gm_convert_kernel, dim3(nb_ref + nb_q + N), dim3(256), 0, stream, ref, rps, rcs, R, labels, query, qps, qcs, M, p.M_pad, C, N,
              nb_ref, nb_q, ctrl, Aimg, Bimg, xs, ysn, tile_obj);
-    static int sm_count = 0;
-    static int variant = 2;       // 0: single CTA, 1: multicast pair, 2: cta_group::2 pair (default)
-    if (sm_count == 0) {
-        int dev = 0; cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    // 0: single CTA, 1: multicast pair, 2: cta_group::2 pair (default); MANET_GM_VARIANT is an A/B switch for profiling
+    static const int variant = [] { const char* e1 = getenv("MANET_GM_VARIANT"); return (e1 && e1[0] >= '0' && e1[0] <= '2') ? e1[0] - '0' : 2; }();
+    static PerDevice attrs;
+    attrs.once([](int) {
         cudaFuncSetAttribute(gm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_TOTAL);
         cudaFuncSetAttribute(gm_umma_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_TOTAL);
         cudaFuncSetAttribute(gm_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_TOTAL);
-        const char* e1 = getenv("MANET_GM_VARIANT");               // A/B switch for profiling
-        if (e1 && e1[0] >= '0' && e1[0] <= '2') variant = e1[0] - '0';
-    }
+    });
+    const int sm_count = device_sm_count();
     const int ksteps = (C + 15) / 16;
     const int ksteps_lo = gm_fold_remainder(C) ? ksteps - 1 : ksteps;
     profile_begin(PROF_GLOBAL_UMMA, stream);
     if (variant == 1)
-        gm_umma_mc_kernel<<<sm_count & ~1, GM_THREADS, GM_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles / 2, N, ksteps, ksteps_lo);
+        count_launch(), gm_umma_mc_kernel<<<sm_count & ~1, GM_THREADS, GM_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles / 2, N, ksteps, ksteps_lo);
     else if (variant == 2)
         launch_k(gm_umma2_kernel, dim3(sm_count & ~1), dim3(GM_THREADS), (size_t)G2_SMEM_TOTAL, stream, Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles / 2, N, ksteps, ksteps_lo);
     else
-        gm_umma_kernel<<<sm_count, GM_THREADS, GM_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles, N, ksteps, ksteps_lo);
+        count_launch(), gm_umma_kernel<<<sm_count, GM_THREADS, GM_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles, N, ksteps, ksteps_lo);
     profile_end(PROF_GLOBAL_UMMA, stream);
     launch_k(gm_finalize_kernel, dim3((unsigned)ceil_div64(M * N, 256)), dim3(256), 0, stream, best, xs, ctrl, M, N, normalize, mem_frame, out);
     return check_launch("global match (tcgen05) kernels");

@@ -377,18 +377,15 @@ static int window_volume(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_s
         const int ngroups = (win + WDY - 1) / WDY;
         dim3 grid((w + WTX - 1) / WTX, (h + WTY - 1) / WTY);
         size_t smem = 2 * (size_t)(WCC * (WTY - 1 + ngroups * WDY) * 32 + WCC * WTY * WTX) * sizeof(float);
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(window_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-            attr_set = true;
-        }
+        static PerDevice attrs;
+        attrs.once([](int) { cudaFuncSetAttribute(window_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); });
         if (!guard) profile_begin(PROF_LOCAL_WINDOW, stream);
         launch_k(window_dist_kernel, grid, dim3(WTHREADS), smem, stream, (const float*)qs, (const float*)ps, C, h, w, wp, d, T, guard);
         if (!guard) profile_end(PROF_LOCAL_WINDOW, stream);
     } else {
         int64_t total = (int64_t)h * w * win * win;
         unsigned g = (unsigned)imin64(ceil_div64(total, 256), 148 * 32);
-        window_dist_generic_kernel<<<g, 256, 0, stream>>>(qs, ps, C, h, w, wp, d, T, guard);
+        count_launch(), window_dist_generic_kernel<<<g, 256, 0, stream>>>(qs, ps, C, h, w, wp, d, T, guard);
     }
     *T_out = T;
     return check_launch("local window kernels");
@@ -482,7 +479,7 @@ int launch_local_window_distances(const float* x, int64_t x_sy, int64_t x_sx, in
     const int L = (2 * d + 1) * (2 * d + 1);
     int64_t total = (int64_t)H * W * L;
     unsigned g = (unsigned)imin64(ceil_div64(total, 256), 148 * 32);
-    upsample_volume_kernel<<<g, 256, 0, stream>>>(mode != 0 ? T_tensor : T_simt, H, W, H / 2, W / 2, L, out, T_simt,
+    count_launch(), upsample_volume_kernel<<<g, 256, 0, stream>>>(mode != 0 ? T_tensor : T_simt, H, W, H / 2, W / 2, L, out, T_simt,
                                                   mode == 2 ? guard : nullptr);
     return check_launch("upsample_volume_kernel");
 }
@@ -617,7 +614,7 @@ int launch_local_match_argmin(const float* prev, int64_t p_sy, int64_t p_sx, int
     const size_t smem = (size_t)N * UP_STRIDE * 2 * sizeof(float);
     if (smem > 200 * 1024) return fail_invalid("local match: too many objects (N <= 100)");
     if (smem > 48 * 1024) cudaFuncSetAttribute(local_min_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    local_min_argmin_kernel<<<(unsigned)ceil_div64((int64_t)H * W, UP_WARPS), UP_STRIDE, smem, stream>>>(T, plab, gt_ids, H, W, H / 2,
+    count_launch(), local_min_argmin_kernel<<<(unsigned)ceil_div64((int64_t)H * W, UP_WARPS), UP_STRIDE, smem, stream>>>(T, plab, gt_ids, H, W, H / 2,
                                                                                                    W / 2, d, N, out, out_idx);
     return check_launch("local_min_argmin_kernel");
 }
@@ -645,12 +642,12 @@ int launch_local_match_backward(const float* prev, int64_t p_sy, int64_t p_sx, i
     cudaMemsetAsync(dqs, 0, (size_t)C * h * wp * sizeof(float), stream);
     cudaMemsetAsync(dps, 0, (size_t)C * h * wp * sizeof(float), stream);
     const int64_t tot = (int64_t)H * W * N;
-    local_scatter_dt_kernel<<<(unsigned)imin64(ceil_div64(tot, 256), 148 * 16), 256, 0, stream>>>(idx, grad_out, H, W, h, w, L, N, dT);
-    local_backward_dist_kernel<<<(unsigned)ceil_div64((int64_t)h * w, 8), 256, 0, stream>>>(qs, ps, T, dT, C, h, w, wp, d, dqs, dps);
+    count_launch(), local_scatter_dt_kernel<<<(unsigned)imin64(ceil_div64(tot, 256), 148 * 16), 256, 0, stream>>>(idx, grad_out, H, W, h, w, L, N, dT);
+    count_launch(), local_backward_dist_kernel<<<(unsigned)ceil_div64((int64_t)h * w, 8), 256, 0, stream>>>(qs, ps, T, dT, C, h, w, wp, d, dqs, dps);
     const int64_t tot2 = (int64_t)H * W * C;
     const unsigned g2 = (unsigned)imin64(ceil_div64(tot2, 256), 148 * 16);
-    if (grad_query) local_unpool_kernel<<<g2, 256, 0, stream>>>(dqs, C, H, W, h, w, wp, grad_query);
-    if (grad_prev) local_unpool_kernel<<<g2, 256, 0, stream>>>(dps, C, H, W, h, w, wp, grad_prev);
+    if (grad_query) count_launch(), local_unpool_kernel<<<g2, 256, 0, stream>>>(dqs, C, H, W, h, w, wp, grad_query);
+    if (grad_prev) count_launch(), local_unpool_kernel<<<g2, 256, 0, stream>>>(dps, C, H, W, h, w, wp, grad_prev);
     return check_launch("local match backward kernels");
 }
 

@@ -1067,12 +1067,11 @@ int launch_local_match_umma(const float* prev, int64_t p_sy, int64_t p_sx, int64
     P.plab8 = labels ? plab8 : nullptr; P.gt_ids = gt_ids; P.out = labels ? out : nullptr;
     P.T_vol = T_out ? Tvol : nullptr;
     P.H = H; P.W = W; P.C = C; P.N = labels ? N : 1; P.d = d;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDevice attrs;
+    attrs.once([](int) {
         cudaFuncSetAttribute(lm_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(lm_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_set = true;
-    }
+    });
     profile_begin(PROF_LOCAL_WINDOW, stream);
     if (labels) launch_k(lm_umma_kernel<false>, dim3(2 * n_tiles), dim3(LM_THREADS), (size_t)g.total, stream, P);
     else launch_k(lm_umma_kernel<true>, dim3(2 * n_tiles), dim3(LM_THREADS), (size_t)g.total, stream, P);

@@ -157,6 +157,7 @@ struct ShSource {
     const float* x; int64_t sn, sc, sh, sw;
     int c0;
     const float* extras;
+    int n_extra;                 // planes per object in `extras`: 3 (propagation head) or 2 (interaction head, IntVOS.py:741-757)
 };
 
 // max |x| over a strided [n,c,h,w] tensor -> atomicMax on float bits (one atomic per block: thousands of atomics on
@@ -199,6 +200,25 @@ sh_extras_kernel(const float* __restrict__ gmap, const float* __restrict__ lmap,
     }
     const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
     if ((threadIdx.x & 31) == 0 && wm) atomicMax(amax, wm);      // <= 8 per block, a few hundred in all
+}
+
+// Interaction head (IntVOS.py:741-757): extras[n][0] = (scribble == ids[n]), extras[n][1] = (prev_round == ids[n]), or, in the
+// first interaction round (prev_round == nullptr), 1 for object 0 and 0 for the others (IntVOS.py:754-755).
+__global__ void __launch_bounds__(256)
+sh_extras_int_kernel(const int32_t* __restrict__ scribble, const int32_t* __restrict__ prev_round, const int32_t* __restrict__ ids,
+                     int N, int HW, float* __restrict__ extras, unsigned* __restrict__ amax) {
+    pdl_enter();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        const int sl = __ldg(scribble + i);
+        const int pl = prev_round ? __ldg(prev_round + i) : 0;
+        for (int n = 0; n < N; ++n) {
+            const int id = __ldg(ids + n);
+            float* e = extras + (size_t)n * 2 * HW + i;
+            e[0] = (sl == id) ? 1.f : 0.f;
+            e[HW] = prev_round ? ((pl == id) ? 1.f : 0.f) : (n == 0 ? 1.f : 0.f);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(amax, __float_as_uint(1.0f));   // the planes are 0/1: a bound of 1 is exact enough
 }
 
 // ---------------------------------------------------------------------------------------------- depthwise 7x7
@@ -311,7 +331,7 @@ sh_dw_kernel(ShSource src, int C, const float* __restrict__ dwW, const unsigned*
                 const int ch = c + hh;
                 const float* base; int64_t sy, sx;
                 if (ch < src.c0) { base = src.x + n * src.sn + ch * src.sc; sy = src.sh; sx = src.sw; }
-                else { base = src.extras + ((size_t)n * 3 + (ch - src.c0)) * H * W; sy = W; sx = 1; }
+                else { base = src.extras + ((size_t)n * src.n_extra + (ch - src.c0)) * H * W; sy = W; sx = 1; }
                 const float* p0 = base + (int64_t)y0 * sy + (int64_t)(x0 + lane) * sx;
                 const float* p1 = p0 + 32 * sx;
                 const uint32_t dst = in_s + (uint32_t)(buf * DW_PLANE_PAD + hh * DW_PLANE + lane) * 4;
@@ -838,7 +858,7 @@ static cudaError_t launch_pwm(int cl, int sms, cudaStream_t stream, const uint8_
     attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     // persistent: as many clusters as can be resident at once
-    static int max_clusters[9] = {0};
+    static int max_clusters[9] = {0};      // occupancy of identical B200s: one query per process and cluster size is enough
     if (!max_clusters[cl]) {
         cfg.gridDim = dim3((sms / cl) * cl);
         int nc = 0;
@@ -848,6 +868,7 @@ static cudaError_t launch_pwm(int cl, int sms, cudaStream_t stream, const uint8_
     int clusters = max_clusters[cl];
     if (clusters * cl > n_valid) clusters = (n_valid + cl - 1) / cl;
     cfg.gridDim = dim3(clusters * cl);
+    count_launch();
     return cudaLaunchKernelEx(&cfg, sh_pwm_kernel<MODE>, aimg, amax_in, bound, bimg, cinv, bias2, w5, b5, out, amax_out, n_valid, nkb, H, W,
                               TX, TY, TYV, ldw);
 }
@@ -1122,11 +1143,7 @@ int launch_seghead_pack(const float* const* p, int in_dim, float eps, void* pack
     return check_launch("seghead pack kernels");
 }
 
-static int sh_sm_count() {
-    static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-    return sms;
-}
+static int sh_sm_count() { return device_sm_count(); }
 
 // Tensor map of the activation buffer y [N*256][H][Wp] (valid width W: columns beyond it and rows/columns outside the image
 // read as zeros), box = the 14 x 40 windows of a channel pair.  cuTensorMapEncodeTiled comes from the driver through the runtime's entry
@@ -1165,18 +1182,20 @@ static inline cudaError_t launch_sh(void (*kernel)(KArgs...), dim3 grid, dim3 bl
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = on ? 1 : 0;
+    count_launch();
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-struct ShParts { const float* gmap; const float* lmap; const int32_t* prev; const int32_t* ids; };
+struct ShParts { const float* gmap; const float* lmap; const int32_t* prev; const int32_t* ids;
+                 const int32_t* scribble; bool interaction; };   // interaction: scribble + prev (= previous round's labels or null)
 
 static int launch_seghead_forward(const void* packed, int in_dim, ShSource src, const ShParts* parts, int N, int H, int W,
                                   float* logits, void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (in_dim < 1 || in_dim > SH_IN_PAD) return fail_invalid("seghead: in_dim must be in [1, 128]");
     if (N < 1 || H < 1 || W < 1) return fail_invalid("seghead: bad sizes");
     if (ws_bytes < seghead_workspace_bytes(N, H, W)) { set_error("seghead: workspace too small"); return MANET_E_WORKSPACE; }
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDevice attrs;
+    attrs.once([](int) {
         cudaFuncSetAttribute(sh_pw_kernel<PW_RELU_NCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_TOTAL);
         cudaFuncSetAttribute(sh_pw_kernel<PW_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM_TOTAL);
         cudaFuncSetAttribute(sh_pw2_kernel<PW_RELU_NCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW2_SMEM_TOTAL);
@@ -1186,8 +1205,7 @@ static int launch_seghead_forward(const void* packed, int in_dim, ShSource src, 
         cudaFuncSetAttribute(sh_dw_kernel<SH_MID, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
         cudaFuncSetAttribute(sh_dw_kernel<SH_MID, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
         cudaFuncSetAttribute(sh_dw_kernel<SH_IN_PAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
-        attr_done = true;
-    }
+    });
     const ShLayout L = sh_layout();
     const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
     const size_t px = (size_t)N * H * W;
@@ -1208,9 +1226,13 @@ static int launch_seghead_forward(const void* packed, int in_dim, ShSource src, 
     if (parts) {
         launch_sh(sh_absmax_kernel, dim3((unsigned)imin64(ceil_div64((int64_t)src.c0 * H, 8), 4 * sms)), dim3(256), 0, stream, src.x, (int64_t)0, src.sc,
                  src.sh, src.sw, 1, src.c0, H, W, amax);
-        launch_sh(sh_extras_kernel, dim3((unsigned)imin64(ceil_div64((int64_t)H * W, 256), 2 * sms)), dim3(256), 0, stream,
-                 parts->gmap, parts->lmap, parts->prev, parts->ids, N, H * W, extras, amax);
-        src.extras = extras;
+        if (parts->interaction)
+            launch_sh(sh_extras_int_kernel, dim3((unsigned)imin64(ceil_div64((int64_t)H * W, 256), 2 * sms)), dim3(256), 0, stream,
+                     parts->scribble, parts->prev, parts->ids, N, H * W, extras, amax);
+        else
+            launch_sh(sh_extras_kernel, dim3((unsigned)imin64(ceil_div64((int64_t)H * W, 256), 2 * sms)), dim3(256), 0, stream,
+                     parts->gmap, parts->lmap, parts->prev, parts->ids, N, H * W, extras, amax);
+        src.extras = extras; src.n_extra = parts->interaction ? 2 : 3;
     } else {
         launch_sh(sh_absmax_kernel, dim3((unsigned)imin64(ceil_div64((int64_t)N * in_dim * H, 8), 4 * sms)), dim3(256), 0, stream, src.x, src.sn, src.sc,
                  src.sh, src.sw, N, in_dim, H, W, amax);
@@ -1298,8 +1320,17 @@ int seghead_forward_parts(const void* packed, const float* emb, int64_t sc, int6
                           void* ws, size_t ws_bytes, cudaStream_t stream) {
     ShSource s = {};
     s.x = emb; s.sn = 0; s.sc = sc; s.sh = sh; s.sw = sw; s.c0 = C0;
-    ShParts parts = {gmap, lmap, prev, ids};
+    ShParts parts = {gmap, lmap, prev, ids, nullptr, false};
     return launch_seghead_forward(packed, C0 + 3, s, &parts, N, H, W, logits, ws, ws_bytes, stream);
+}
+
+int seghead_forward_interaction(const void* packed, const float* emb, int64_t sc, int64_t sh, int64_t sw, int C0,
+                                const int32_t* scribble, const int32_t* prev_round, const int32_t* ids, int N, int H, int W,
+                                float* logits, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    ShSource s = {};
+    s.x = emb; s.sn = 0; s.sc = sc; s.sh = sh; s.sw = sw; s.c0 = C0;
+    ShParts parts = {nullptr, nullptr, prev_round, ids, scribble, true};
+    return launch_seghead_forward(packed, C0 + 2, s, &parts, N, H, W, logits, ws, ws_bytes, stream);
 }
 
 }  // namespace manet

@@ -111,13 +111,13 @@ int launch_select_labelled(const int32_t* labels, int64_t R, const float* emb, i
     int32_t* counts = cv.take<int32_t>(nb);
     int64_t* offsets = cv.take<int64_t>(nb);
     int64_t* src = cv.take<int64_t>(R);
-    select_count_kernel<<<(unsigned)nb, SEL_BLOCK, 0, stream>>>(labels, R, counts);
-    select_scan_kernel<<<1, 1024, 0, stream>>>(counts, (int)nb, offsets, count_dev);
-    select_scatter_kernel<<<(unsigned)nb, SEL_BLOCK, 0, stream>>>(labels, R, offsets, out_labels, src);
+    count_launch(), select_count_kernel<<<(unsigned)nb, SEL_BLOCK, 0, stream>>>(labels, R, counts);
+    count_launch(), select_scan_kernel<<<1, 1024, 0, stream>>>(counts, (int)nb, offsets, count_dev);
+    count_launch(), select_scatter_kernel<<<(unsigned)nb, SEL_BLOCK, 0, stream>>>(labels, R, offsets, out_labels, src);
     if (emb != nullptr && out_emb != nullptr) {
         int64_t want = ceil_div64(R * (int64_t)C, 256);
         unsigned grid = (unsigned)(want < 148 * 16 ? (want > 0 ? want : 1) : 148 * 16);
-        select_gather_kernel<<<grid, 256, 0, stream>>>(emb, ps, cs, C, src, count_dev, out_emb);
+        count_launch(), select_gather_kernel<<<grid, 256, 0, stream>>>(emb, ps, cs, C, src, count_dev, out_emb);
     }
     return check_launch("select_labelled kernels");
 }

@@ -46,11 +46,19 @@ def sharded_nearest_neighbor_features_per_object(reference_embeddings, query_emb
         from .networks.IntVOS import nearest_neighbor_features_per_object as match_fn
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if gt_ids is None:
+        # every rank must reduce a map of the SAME shape: derive the object count once from the full label map
+        # (unique(labels)[-1], IntVOS.py:193-194), never from a rank's own slice
+        gt_ids = int(reference_labels.max().item()) if reference_labels.numel() else 0
     c = reference_embeddings.shape[-1]
     ref_flat = reference_embeddings.reshape(-1, 1, c) if not _viewable(reference_embeddings) else reference_embeddings.view(-1, 1, c)
     lab_flat = reference_labels.reshape(-1, 1, 1)
     begin, end = shard_bounds(ref_flat.shape[0], world, rank)
     part, ids = match_fn(ref_flat[begin:end], query_embeddings, lab_flat[begin:end], 1, gt_ids, n_chunks)
+    h, w = query_embeddings.shape[:2]
+    if tuple(part.shape) != (1, h, w, int(gt_ids) + 1, 1):
+        raise RuntimeError(f"rank {rank}: partial map has shape {tuple(part.shape)}, expected {(1, h, w, int(gt_ids) + 1, 1)}; "
+                           "ranks would enter all_reduce(MIN) with different shapes")
     part = combine_partial_minima(part.contiguous(), group)
     if global_map_tmp_dic is not None:
         from .memory import global_map_read_update

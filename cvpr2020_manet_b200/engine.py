@@ -12,7 +12,7 @@ from . import _lib
 from ._device import check
 from .config import cfg
 from .memory import (global_map_read_update, local_map_init_for_annotated_frame, local_map_store_select)
-from .networks.IntVOS import (local_previous_frame_nearest_neighbor_features_per_object,
+from .networks.IntVOS import (_wants_grad, local_previous_frame_nearest_neighbor_features_per_object,
                               nearest_neighbor_features_per_object)
 
 
@@ -86,7 +86,18 @@ def prop_seghead(ref_frame_embedding=None, previous_frame_embedding=None, curren
             if seq not in global_map_tmp_dic:
                 global_map_tmp_dic[seq] = torch.ones((104, h, w, int(gt_ids[n]) + 1, 1), dtype=torch.float32, device=cur.device)
             mem_slot = global_map_tmp_dic[seq][int(frame_num[n])]
-        if normalize_nearest_neighbor_distances:
+        # Training (train_stage1.py:126 back-propagates through both matchers): the fused normalise/memory epilogue has no
+        # gradient, so the matchers run as autograd functions (raw distances) and the two cheap element-wise steps are
+        # torch ops exactly as the reference writes them (IntVOS.py:611-622, memory written detached).
+        grad_path = _wants_grad(ref, cur, prev)
+        if grad_path:
+            g, ids = nearest_neighbor_features_per_object(ref, cur, ref_label, k_nearest_neighbors, gt_ids[n], n_chunks=10)
+            if normalize_nearest_neighbor_distances:
+                g = (torch.sigmoid(g) - 0.5) * 2
+            if mem_slot is not None:
+                g = torch.where(g <= mem_slot.unsqueeze(0), g, mem_slot.unsqueeze(0))
+                global_map_tmp_dic[seq][int(frame_num[n])] = g.detach()[0]
+        elif normalize_nearest_neighbor_distances:
             g, ids = nearest_neighbor_features_per_object(ref, cur, ref_label, k_nearest_neighbors, gt_ids[n], n_chunks=10,
                                                           normalize=True, memory_frame=mem_slot)
         else:
@@ -96,6 +107,9 @@ def prop_seghead(ref_frame_embedding=None, previous_frame_embedding=None, curren
         if use_local_map:
             loc = local_previous_frame_nearest_neighbor_features_per_object(prev, cur, prev_label, ids,
                                                                             cfg.MODEL_MAX_LOCAL_DISTANCE)
+        elif grad_path:
+            loc, _ = nearest_neighbor_features_per_object(prev, cur, prev_label, k_nearest_neighbors, gt_ids[n], n_chunks=20)
+            loc = (torch.sigmoid(loc) - 0.5) * 2
         else:
             loc, _ = nearest_neighbor_features_per_object(prev, cur, prev_label, k_nearest_neighbors, gt_ids[n],
                                                           n_chunks=20, normalize=True)
@@ -103,6 +117,9 @@ def prop_seghead(ref_frame_embedding=None, previous_frame_embedding=None, curren
             loc, local_map_dics = local_map_store_select(local_map_dics, seq, frame_num[n], interaction_num,
                                                          start_annotated_frame, loc)
         if isinstance(dynamic_seghead, DynamicSegHead):
+            if grad_path:
+                raise NotImplementedError("this package's DynamicSegHead is the inference form (no gradients); for training pass "
+                                          "the reference's torch DynamicSegHead as dynamic_seghead (same state_dict)")
             pred = dynamic_seghead.forward_parts(current_frame_embedding[n], g, loc, prev_label, ids)
         else:
             to_cat_prev = (prev_label.float() == ids.float()).unsqueeze(-1).permute(2, 3, 0, 1).float()
@@ -120,11 +137,15 @@ def prop_seghead(ref_frame_embedding=None, previous_frame_embedding=None, curren
 def int_seghead(ref_frame_embedding=None, ref_scribble_label=None, prev_round_label=None,
                 normalize_nearest_neighbor_distances=True, global_map_tmp_dic=None, local_map_dics=None, interaction_num=None,
                 seq_names=None, gt_ids=None, k_nearest_neighbors=1, frame_num=None, first_inter=True, inter_seghead=None):
-    """``IntVOS.int_seghead`` (IntVOS.py:683-764) with the reference's arguments and return forms; ``inter_seghead`` is the
-    module the reference keeps as ``self.inter_seghead`` (its ``IntSegHead``, IntVOS.py:463-486 -- dense convolutions, outside
-    this package's scope: pass the reference's own module).  On the sm_100a kernels: the local self-match of the annotated
-    frame (:709-711), its merge into the global-map memory (:716-723) and the local-map bookkeeping (:725-736).  The head's
-    input (:741-757: embedding repeated per object, scribble mask, previous-round mask) is assembled with torch ops."""
+    """``IntVOS.int_seghead`` (IntVOS.py:683-764) with the reference's arguments and return forms.  ``inter_seghead`` is the
+    module the reference keeps as ``self.inter_seghead``: under its default configuration (config.py:52
+    ``MODEL_USEIntSeg=False``) that is ``DynamicSegHead(in_dim=C+2)`` (IntVOS.py:554) -- pass this package's
+    ``DynamicSegHead(in_dim=C+2)`` and the whole branch runs on the sm_100a kernels, the head fed by its parts (the 63 MB
+    ``repeat``/``cat`` of :741-757 is never built).  Any other callable (e.g. the reference's dense ``IntSegHead``,
+    IntVOS.py:463-486, for ``MODEL_USEIntSeg=True``) receives the assembled ``to_cat`` tensor.
+    On the sm_100a kernels either way: the local self-match of the annotated frame (:709-711), its merge into the
+    global-map memory (:716-723) and the local-map bookkeeping (:725-736)."""
+    from .networks.seghead import DynamicSegHead
     dic_tmp = {}
     bs, c, h, w = ref_frame_embedding.size()
     scale_scr = torch.nn.functional.interpolate(ref_scribble_label.float(), size=(h, w), mode="nearest").int()
@@ -135,15 +156,19 @@ def int_seghead(ref_frame_embedding=None, ref_scribble_label=None, prev_round_la
         scr = scale_scr[n].permute(1, 2, 0)                                       # [h,w,1]
         loc, _ = int_matching_step(ref_frame_embedding[n], scr[..., 0], int(gt_ids[n]), None, global_map_tmp_dic,
                                    local_map_dics, seq_names[n], frame_num[n], interaction_num)
-        emb_rep = ref_frame_embedding[n].unsqueeze(0).repeat((gt_id.size(0), 1, 1, 1))
-        scr_mask = (scr.float() == gt_id.float()).unsqueeze(-1).permute(2, 3, 0, 1).float()
-        if not first_inter:
-            prev = scale_prev[n].permute(1, 2, 0)
-            prev_mask = (prev.float() == gt_id.float()).unsqueeze(-1).permute(2, 3, 0, 1).float()
+        if isinstance(inter_seghead, DynamicSegHead):
+            pred = inter_seghead.forward_parts_interaction(ref_frame_embedding[n], scr[..., 0],
+                                                           None if first_inter else scale_prev[n, 0], gt_id)
         else:
-            prev_mask = torch.zeros_like(scr_mask)
-            prev_mask[0] = 1.0
-        pred = inter_seghead(torch.cat((emb_rep, scr_mask, prev_mask), 1))
+            emb_rep = ref_frame_embedding[n].unsqueeze(0).repeat((gt_id.size(0), 1, 1, 1))
+            scr_mask = (scr.float() == gt_id.float()).unsqueeze(-1).permute(2, 3, 0, 1).float()
+            if not first_inter:
+                prev = scale_prev[n].permute(1, 2, 0)
+                prev_mask = (prev.float() == gt_id.float()).unsqueeze(-1).permute(2, 3, 0, 1).float()
+            else:
+                prev_mask = torch.zeros_like(scr_mask)
+                prev_mask[0] = 1.0
+            pred = inter_seghead(torch.cat((emb_rep, scr_mask, prev_mask), 1))
         dic_tmp[seq_names[n]] = pred.permute(1, 0, 2, 3)
     if local_map_dics is None:
         return dic_tmp

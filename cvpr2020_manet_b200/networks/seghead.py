@@ -68,6 +68,8 @@ class DynamicSegHead(nn.Module):
         nn.init.kaiming_normal_(self.conv.weight, mode="fan_out", nonlinearity="relu")
         self._packed = None
         self._packed_key = None
+        self._packed_stream = None
+        self._packed_event = None
 
     # ------------------------------------------------------------------ parameter blob
     def _tensors(self):
@@ -92,6 +94,15 @@ class DynamicSegHead(nn.Module):
                 check(lib.manet_seghead_pack(ptrs, len(keep), self.in_dim, BN_EPS, blob.data_ptr(), stream_ptr(dev)),
                       "manet_seghead_pack")
             self._packed, self._packed_key = blob, key
+            # the blob is written on the stream that was current here: remember it so that a forward pass issued on another
+            # stream waits for the packing kernel instead of reading a partly written blob
+            self._packed_stream = torch.cuda.current_stream(dev)
+            self._packed_event = torch.cuda.Event()
+            self._packed_event.record(self._packed_stream)
+        else:
+            cur = torch.cuda.current_stream(self._packed.device)
+            if cur != self._packed_stream:
+                cur.wait_event(self._packed_event)
         return self._packed
 
     def _check_mode(self):
@@ -155,4 +166,43 @@ class DynamicSegHead(nn.Module):
             check(lib.manet_seghead_forward_parts(blob.data_ptr(), emb.data_ptr(), sc, sh, sw, c, g.data_ptr(), l.data_ptr(),
                                                   prev.data_ptr(), ids.data_ptr(), n, h, w, out.data_ptr(), ws.data_ptr(),
                                                   ws.numel(), stream_ptr(dev)), "manet_seghead_forward_parts")
+        return out
+
+    def forward_parts_interaction(self, ref_frame_embedding, scribble_label, prev_round_label, ref_obj_ids):
+        """The interaction head of the reference's default configuration (``IntVOS.inter_seghead =
+        DynamicSegHead(in_dim=C+2)``, IntVOS.py:554 with config.py:52) applied to ``to_cat`` of IntVOS.py:741-757 without
+        building it: ``ref_frame_embedding`` ``[C,H,W]`` (any strides), ``scribble_label`` ``[H,W]``/``[H,W,1]`` int32 at
+        embedding resolution, ``prev_round_label`` likewise or ``None`` in the first interaction round (the previous-round
+        channel is then 1 for object 0 and 0 for the others, :754-755), ``ref_obj_ids`` ``[N]`` int32.
+        Returns ``pred_`` = ``[N,1,H,W]``."""
+        self._check_mode()
+        emb = ref_frame_embedding
+        require_f32(emb, "ref_frame_embedding")
+        require_cuda(scribble_label, "scribble_label")
+        require_cuda(ref_obj_ids, "ref_obj_ids")
+        c, h, w = emb.shape
+        if c + 2 != self.in_dim:
+            raise ValueError(f"embedding has {c} channels, the interaction head expects {self.in_dim - 2}")
+        scr = scribble_label.reshape(-1).to(torch.int32).contiguous()
+        if scr.numel() != h * w:
+            raise ValueError("scribble_label must be [H,W]")
+        prev = None
+        if prev_round_label is not None:
+            require_cuda(prev_round_label, "prev_round_label")
+            prev = prev_round_label.reshape(-1).to(torch.int32).contiguous()
+            if prev.numel() != h * w:
+                raise ValueError("prev_round_label must be [H,W]")
+        ids = ref_obj_ids.reshape(-1).to(torch.int32).contiguous()
+        n = int(ids.numel())
+        dev = emb.device
+        out = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev)
+        lib = _lib.lib()
+        blob = self.packed()
+        ws = workspace(dev, int(lib.manet_seghead_workspace_bytes(n, h, w)), "seghead")
+        sc, sh, sw = emb.stride()
+        with torch.cuda.device(dev):
+            check(lib.manet_seghead_forward_interaction(blob.data_ptr(), emb.data_ptr(), sc, sh, sw, c, scr.data_ptr(),
+                                                        prev.data_ptr() if prev is not None else None, ids.data_ptr(), n, h, w,
+                                                        out.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)),
+                  "manet_seghead_forward_interaction")
         return out

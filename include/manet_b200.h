@@ -156,6 +156,11 @@ int manet_local_window_distances(const float* x, int64_t x_sy, int64_t x_sx, int
                                  const float* y, int64_t y_sy, int64_t y_sx, int64_t y_sc,
                                  int H, int W, int C, int max_distance, float* out,
                                  void* workspace, size_t workspace_bytes, manet_stream_t stream);
+int manet_seghead_forward_interaction(const void* packed, const float* emb, int64_t emb_ch_stride,
+                                      int64_t emb_row_stride, int64_t emb_col_stride, int C,
+                                      const int32_t* scribble_labels, const int32_t* prev_round_labels,
+                                      const int32_t* gt_ids, int n_objects, int H, int W, float* logits,
+                                      void* workspace, size_t workspace_bytes, manet_stream_t stream);
 
 int manet_local_window_distances_ex(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_sc,
                                     const float* y, int64_t y_sy, int64_t y_sx, int64_t y_sc,
@@ -262,6 +267,14 @@ int manet_correlation_backward(const void* in1, const int64_t* in1_strides,
  *                          strides), global_map / local_map = [H,W,n_objects] fp32 (the matchers'
  *                          [1,H,W,N,1] outputs), prev_labels [H,W] int32, gt_ids [n_objects] int32
  *                          (channel C+2 = prev_labels == gt_ids[n], IntVOS.py:663).
+ * manet_seghead_forward_interaction: the INTERACTION head of the reference's default configuration
+ *                          (config.py:52 MODEL_USEIntSeg=False -> IntVOS.py:554 `inter_seghead =
+ *                          DynamicSegHead(in_dim=C+2)`) fed by the parts of its `to_cat` (IntVOS.py:741-757):
+ *                          emb = annotated-frame embedding [C,H,W], channel C = scribble_labels == gt_ids[n],
+ *                          channel C+1 = prev_round_labels == gt_ids[n]; prev_round_labels == NULL is the first
+ *                          interaction round (channel C+1 = 1 for object 0, 0 otherwise, IntVOS.py:754-755).
+ *                          Labels are [H,W] int32 at embedding resolution.  `packed` must come from
+ *                          manet_seghead_pack(in_dim = C + 2).
  * in_dim <= 128, embed dim fixed at 256 (cfg.MODEL_HEAD_EMBEDDING_DIM).  Numerics: depthwise convs in
  * fp32; 1x1 convs as fp16 hi/lo split tensor-core products with fp32 accumulation (fp32 grade).
  * ------------------------------------------------------------------------------------------ */
@@ -307,6 +320,16 @@ int manet_rough_roi(const int32_t* labels, int batch, int H, int W, int dist, in
 int manet_profile_enable(int max_records);
 int manet_profile_reset(void);
 int manet_profile_read(int slot, float* ms_out, int capacity, int* n_out);
+/* number of kernels of this library launched by the calling process since the last manet_profile_reset_launches()
+ * (every launcher counts its own <<<>>>; cudaMemcpy/cudaMemset are not counted).  bench.py's `gpu_launches`. */
+long long manet_profile_launch_count(void);
+int manet_profile_reset_launches(void);
+
+/* Machine micro-benchmark behind DESIGN.md's TMEM read-out floor (no reference equivalent): `ctas` CTAs, `warps` (4, 8 or
+ * 16) warps each draining all 512 tensor-memory columns `iters` times with tcgen05.ld only (mode 0: .32x32b.x32, mode 1:
+ * .x64, mode 2: .x32 + the global-matching epilogue's three-input maxima).  cycles_out_host[ctas] receives clock64() ticks
+ * per CTA; bytes moved per CTA = iters * 128 lanes * 512 columns * 4.  Synchronous. */
+int manet_microbench_tmem_ld(int mode, int iters, int warps, int ctas, long long* cycles_out_host, manet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Host-buffer frame step: what one iteration of the propagation loop (test.py:237-259 ->

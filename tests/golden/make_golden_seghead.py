@@ -57,7 +57,9 @@ def main():
     np.savez_compressed(os.path.join(HERE, "seghead_ref.npz"), **out)
     print("wrote seghead_ref.npz", os.path.getsize(os.path.join(HERE, "seghead_ref.npz")) // 1024, "KB")
     prop_seghead_case(head)
+    prop_seghead_grad_case(head)
     int_seghead_case()
+    int_seghead_default_head_case()
 
 
 def prop_seghead_case(head):
@@ -129,6 +131,85 @@ def int_seghead_case():
     out["final_local_mem_is_ones"] = np.array(bool((lmem[0]["s"] == 1).all()))
     np.savez_compressed(os.path.join(HERE, "int_seghead_ref.npz"), **out)
     print("wrote int_seghead_ref.npz", {k: np.asarray(v).shape for k, v in out.items()})
+
+
+def prop_seghead_grad_case(head):
+    """Training form of IntVOS.prop_seghead (train_stage1.py:126: no memories, gradients into the embeddings): the
+    reference's own autograd through both matchers, the normalisation and its torch DynamicSegHead (eval-mode BN, weights of
+    seghead_ref.npz).  Records pred and d(sum(pred * weight))/d(embeddings)."""
+    import types
+    c, h, w, nobj, d = 100, 16, 20, 2, 3
+    mod = ref_shim.load_reference(test_mode=False, max_local_distance=d)
+    gen = torch.Generator().manual_seed(29)
+    embs = torch.stack([0.1 * torch.relu(torch.randn(c, h, w, generator=gen)) + 0.01 * torch.randn(c, h, w, generator=gen)
+                        for _ in range(3)]).requires_grad_(True)
+    ref_lab = torch.randint(0, nobj + 1, (h // 4, w // 4), generator=gen).repeat_interleave(4, 0).repeat_interleave(4, 1).int()
+    prev_lab = torch.randint(0, nobj + 1, (h // 2, w // 2), generator=gen).repeat_interleave(2, 0).repeat_interleave(2, 1).int()
+    weight = torch.randn(1, nobj + 1, h, w, generator=gen)
+    fake_self = types.SimpleNamespace()
+    with ref_shim.cpu_cuda_identity():
+        res = mod.IntVOS.prop_seghead(fake_self, ref_frame_embedding=embs[0:1], previous_frame_embedding=embs[1:2],
+                                      current_frame_embedding=embs[2:3], ref_scribble_label=ref_lab.view(1, 1, h, w).float(),
+                                      previous_frame_mask=prev_lab.view(1, 1, h, w).float(),
+                                      normalize_nearest_neighbor_distances=True, use_local_map=True, seq_names=["s"],
+                                      gt_ids=torch.tensor([nobj]), k_nearest_neighbors=1, global_map_tmp_dic=None,
+                                      local_map_dics=None, interaction_num=None, start_annotated_frame=None, frame_num=None,
+                                      dynamic_seghead=head)
+        pred = res["s"]
+        (pred * weight).sum().backward()
+    out = {"embs": embs.detach().numpy(), "ref_label": ref_lab.numpy(), "prev_label": prev_lab.numpy(), "weight": weight.numpy(),
+           "n_obj": nobj, "d": d, "pred": pred.detach().numpy(), "grad_embs": embs.grad.numpy()}
+    np.savez_compressed(os.path.join(HERE, "prop_seghead_grad_ref.npz"), **out)
+    print("wrote prop_seghead_grad_ref.npz", {k: np.asarray(v).shape for k, v in out.items()},
+          "max |grad|", float(embs.grad.abs().max()))
+
+
+def int_seghead_default_head_case():
+    """IntVOS.int_seghead (IntVOS.py:683-764) with the interaction head of the reference's DEFAULT configuration:
+    config.py:52 MODEL_USEIntSeg=False -> IntVOS.py:554 ``inter_seghead = DynamicSegHead(in_dim=C+2)``.  Two rounds (first
+    interaction, then one with a previous-round label map); logits recorded."""
+    import types
+    c, h, w, nobj, d = 100, 18, 26, 3, 4
+    mod = ref_shim.load_reference(test_mode=True, max_local_distance=d)
+    torch.manual_seed(19)
+    head = mod.DynamicSegHead(in_dim=c + 2)
+    gen = torch.Generator().manual_seed(43)
+    with torch.no_grad():
+        for name, m in head.named_modules():
+            if name.endswith("bn1") or name.endswith("bn2"):
+                k = m.weight.shape[0]
+                m.weight.copy_(0.5 + torch.rand(k, generator=gen))
+                m.bias.copy_(0.2 * torch.randn(k, generator=gen))
+                m.running_mean.copy_(0.1 * torch.randn(k, generator=gen))
+                m.running_var.copy_(0.5 + torch.rand(k, generator=gen))
+    head.eval()
+    embs = torch.stack([0.1 * torch.relu(torch.randn(c, h, w, generator=gen)) for _ in range(3)])
+    fake_self = types.SimpleNamespace(inter_seghead=head)
+    gmem, lmem = {}, ({}, {})
+    out = {"embs": embs.numpy(), "n_obj": nobj, "d": d}
+    with ref_shim.cpu_cuda_identity(), torch.no_grad():
+        for rnd, frame, first in ((1, 1, True), (2, 2, False)):
+            scr = torch.full((h, w), -1, dtype=torch.int32)
+            scr[2 + rnd, 2:12] = 0
+            scr[8, 4 + rnd:19] = 1
+            scr[10:15, 6 + rnd] = 2
+            scr[15, 20:24] = 3
+            prev_round = torch.randint(0, nobj + 1, (h // 2, w // 2), generator=gen).repeat_interleave(2, 0).repeat_interleave(2, 1).int()
+            res = mod.IntVOS.int_seghead(fake_self, ref_frame_embedding=embs[frame:frame + 1],
+                                         ref_scribble_label=scr.view(1, 1, h, w).float(),
+                                         prev_round_label=None if first else prev_round.view(1, 1, h, w).float(),
+                                         global_map_tmp_dic=gmem, local_map_dics=lmem, interaction_num=rnd, seq_names=["s"],
+                                         gt_ids=torch.tensor([nobj]), frame_num=[frame], first_inter=first)
+            out[f"r{rnd}_scribble"] = scr.numpy()
+            out[f"r{rnd}_prev_round"] = prev_round.numpy()
+            out[f"r{rnd}_pred"] = res[0]["s"].numpy()
+    out["final_global_mem"] = gmem["s"][:3].numpy()
+    for k, v in head.state_dict().items():
+        if not k.endswith("num_batches_tracked"):
+            out["p:" + k] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, "int_seghead_default_head_ref.npz"), **out)
+    print("wrote int_seghead_default_head_ref.npz", os.path.getsize(os.path.join(HERE, "int_seghead_default_head_ref.npz")) // 1024, "KB",
+          "logit range", float(out["r2_pred"].min()), float(out["r2_pred"].max()))
 
 
 if __name__ == "__main__":

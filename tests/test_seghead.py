@@ -450,6 +450,134 @@ def test_gpu_int_seghead_matches_reference(golden):
         cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE = saved
 
 
+def _int_to_cat(emb, scr, prev_round, ids):
+    """to_cat of IntVOS.py:741-757 (embedding repeated per object, scribble mask, previous-round mask / first-round one-hot)."""
+    rep = emb.unsqueeze(0).repeat(ids.numel(), 1, 1, 1)
+    scr_mask = (scr.float().unsqueeze(-1) == ids.float()).permute(2, 0, 1).unsqueeze(1).float()
+    if prev_round is None:
+        prev_mask = torch.zeros_like(scr_mask)
+        prev_mask[0] = 1.0
+    else:
+        prev_mask = (prev_round.float().unsqueeze(-1) == ids.float()).permute(2, 0, 1).unsqueeze(1).float()
+    return torch.cat((rep, scr_mask, prev_mask), 1)
+
+
+def test_oracle_default_interaction_head_matches_reference(golden):
+    """The reference's default interaction head (config.py:52 -> IntVOS.py:554: DynamicSegHead(in_dim=C+2)) through its own
+    int_seghead: the oracle's head on the restated to_cat reproduces the recorded logits."""
+    g = golden("int_seghead_default_head_ref")
+    state = load_state(g)
+    embs = torch.from_numpy(g["embs"])
+    ids = torch.arange(int(g["n_obj"]) + 1, dtype=torch.int32)
+    for rnd, frame, first in ((1, 1, True), (2, 2, False)):
+        scr = torch.from_numpy(g[f"r{rnd}_scribble"])
+        prev = None if first else torch.from_numpy(g[f"r{rnd}_prev_round"])
+        pred = O.dynamic_seghead_forward(state, _int_to_cat(embs[frame], scr, prev, ids)).permute(1, 0, 2, 3)
+        assert logit_err(pred.numpy(), g[f"r{rnd}_pred"]) <= 1e-6
+
+
+@pytest.mark.gpu
+def test_gpu_int_seghead_default_head_matches_reference(golden):
+    """engine.int_seghead with this package's DynamicSegHead(in_dim=C+2) as the interaction head -- the reference's default
+    configuration, whole branch on the sm_100a kernels, head fed by its parts -- against the reference's own logits."""
+    from cvpr2020_manet_b200 import engine
+    from cvpr2020_manet_b200.config import cfg
+    from cvpr2020_manet_b200.networks.seghead import DynamicSegHead
+    g = golden("int_seghead_default_head_ref")
+    saved = (cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE)
+    cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE = True, int(g["d"])
+    try:
+        embs = torch.from_numpy(g["embs"]).cuda()
+        _, c, h, w = embs.shape
+        nobj = int(g["n_obj"])
+        head = DynamicSegHead(in_dim=c + 2)
+        head.load_state_dict(load_state(g), strict=False)
+        head = head.cuda().eval()
+        gm, lm = {}, ({}, {})
+        for rnd, frame, first in ((1, 1, True), (2, 2, False)):
+            scr = torch.from_numpy(g[f"r{rnd}_scribble"]).cuda()
+            prev_round = torch.from_numpy(g[f"r{rnd}_prev_round"]).cuda()
+            res, lm = engine.int_seghead(ref_frame_embedding=embs[frame:frame + 1], ref_scribble_label=scr.view(1, 1, h, w).float(),
+                                         prev_round_label=None if first else prev_round.view(1, 1, h, w).float(),
+                                         global_map_tmp_dic=gm, local_map_dics=lm, interaction_num=rnd, seq_names=["s"],
+                                         gt_ids=torch.tensor([nobj]), frame_num=[frame], first_inter=first, inter_seghead=head)
+            assert tuple(res["s"].shape) == g[f"r{rnd}_pred"].shape
+            assert logit_err(res["s"].cpu().numpy(), g[f"r{rnd}_pred"]) <= LOGIT_RTOL, rnd
+            # the parts entry equals the dense entry on the assembled tensor (same kernels after layer 1's loader)
+            ids = torch.arange(nobj + 1, dtype=torch.int32).cuda()
+            dense = head(_int_to_cat(embs[frame], scr, None if first else prev_round, ids))
+            assert logit_err(dense.permute(1, 0, 2, 3).cpu().numpy(), g[f"r{rnd}_pred"]) <= LOGIT_RTOL
+        assert float(np.abs(gm["s"][:3].cpu().numpy() - g["final_global_mem"]).max()) <= 1e-5
+    finally:
+        cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE = saved
+
+
+@pytest.mark.gpu
+def test_gpu_int_seghead_default_head_480p(golden):
+    """The interaction head at the 480p / 5-object size against the CPU oracle (weights of the golden), both round forms."""
+    from cvpr2020_manet_b200.networks.seghead import DynamicSegHead
+    g = golden("int_seghead_default_head_ref")
+    state = load_state(g)
+    head = DynamicSegHead(in_dim=102)
+    head.load_state_dict(state, strict=False)
+    head = head.cuda().eval()
+    gen = torch.Generator().manual_seed(17)
+    emb = 0.1 * torch.relu(torch.randn(100, 120, 214, generator=gen))
+    ids = torch.arange(6, dtype=torch.int32)
+    scr = torch.full((120, 214), -1, dtype=torch.int32)
+    for o in range(6):
+        scr[10 + 17 * o, 20:160] = o
+    prev = torch.randint(0, 6, (15, 27), generator=gen).repeat_interleave(8, 0).repeat_interleave(8, 1)[:120, :214].int()
+    for prev_round in (None, prev):
+        want = O.dynamic_seghead_forward(state, _int_to_cat(emb, scr, prev_round, ids))
+        got = head.forward_parts_interaction(emb.cuda(), scr.cuda(), None if prev_round is None else prev_round.cuda(), ids.cuda())
+        assert got.shape == (6, 1, 120, 214)
+        assert logit_err(got.cpu().numpy(), want.numpy()) <= LOGIT_RTOL
+
+
+@pytest.mark.gpu
+def test_gpu_prop_seghead_under_grad_matches_reference(golden):
+    """Training form (train_stage1.py:126): engine.prop_seghead with gradients flowing into the embeddings through both
+    matchers (autograd functions over the sm_100a kernels) and a differentiable torch head, against pred and gradients
+    recorded from the reference's own autograd.  Tolerance on gradients: 2e-4 of the largest one (as tests/test_gpu_autograd)."""
+    from cvpr2020_manet_b200 import engine
+    from cvpr2020_manet_b200.config import cfg
+    g, gh = golden("prop_seghead_grad_ref"), golden("seghead_ref")
+    state = {k: v.cuda() for k, v in load_state(gh).items()}
+    saved = (cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE)
+    cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE = False, int(g["d"])
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False     # the torch head must be fp32 like the reference's
+    try:
+        embs = torch.from_numpy(g["embs"]).cuda().requires_grad_(True)
+        _, c, h, w = embs.shape
+        ref_lab = torch.from_numpy(g["ref_label"]).cuda()
+        prev_lab = torch.from_numpy(g["prev_label"]).cuda()
+        weight = torch.from_numpy(g["weight"]).cuda()
+        res = engine.prop_seghead(ref_frame_embedding=embs[0:1], previous_frame_embedding=embs[1:2],
+                                  current_frame_embedding=embs[2:3], ref_scribble_label=ref_lab.view(1, 1, h, w).float(),
+                                  previous_frame_mask=prev_lab.view(1, 1, h, w).float(), seq_names=["s"],
+                                  gt_ids=torch.tensor([int(g["n_obj"])]), k_nearest_neighbors=1, global_map_tmp_dic=None,
+                                  local_map_dics=None, dynamic_seghead=lambda x: O.dynamic_seghead_forward(state, x))
+        pred = res["s"]
+        assert logit_err(pred.detach().cpu().numpy(), g["pred"]) <= 2e-4
+        (pred * weight).sum().backward()
+        want = g["grad_embs"]
+        err = float(np.abs(embs.grad.cpu().numpy() - want).max() / np.abs(want).max())
+        assert err <= 2e-4, err
+        # this package's inference-form head cannot sit on the training path: loud failure, not a silent gradient cut
+        from cvpr2020_manet_b200.networks.seghead import DynamicSegHead
+        with pytest.raises(NotImplementedError):
+            engine.prop_seghead(ref_frame_embedding=embs[0:1], previous_frame_embedding=embs[1:2],
+                                current_frame_embedding=embs[2:3], ref_scribble_label=ref_lab.view(1, 1, h, w).float(),
+                                previous_frame_mask=prev_lab.view(1, 1, h, w).float(), seq_names=["s"],
+                                gt_ids=torch.tensor([int(g["n_obj"])]), k_nearest_neighbors=1,
+                                dynamic_seghead=DynamicSegHead().cuda().eval())
+    finally:
+        cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE = saved
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
 def test_reference_checkpoint_keys_load():
     """A state_dict of the reference's own DynamicSegHead (IntVOS.py:510-525) loads into the drop-in module: same parameter and
     buffer names and shapes (only BatchNorm's num_batches_tracked bookkeeping may differ)."""
