@@ -298,6 +298,7 @@ def run_own_arm(args, rank, local_rank, world):
     seghead = seghead_leg(dev) if extra else None
     propagation = propagation_leg(dev) if extra else None
     session = session_leg(dev) if extra else None
+    intvos_fwd = intvos_forward_leg(dev) if extra else None
     sharded = sharded_1080p_leg(dev, rank, world) if os.environ.get("MANET_BENCH_SHARDED", "1") == "1" else None
 
     if rank == 0:
@@ -356,6 +357,8 @@ def run_own_arm(args, rank, local_rank, world):
             line["propagation_50"] = propagation
         if session:
             line["session_8_rounds"] = session
+        if intvos_fwd:
+            line["intvos_forward"] = intvos_fwd
         if seghead:
             line["seghead"] = seghead
             line["frame_step_with_seghead"] = {"ms": total_s * 1e3 / K + seghead["ms"],
@@ -423,6 +426,63 @@ def seghead_leg(dev, iters=10):
         res["cpu_cores"] = os.cpu_count()
         res["max_abs_err_vs_oracle"] = float((out.cpu() - want).abs().max())
     return res
+
+
+def intvos_forward_leg(dev, iters=5):
+    """BASELINE config 2: full IntVOS forward on one synthetic 480p frame triple, 5 objects -- random-init DeepLabv3+ /
+    ResNet-101 + semantic embedding (torch/cuDNN: the caller of the hot path) -> global + local matching ->
+    DynamicSegHead, all through networks.deeplab.IntVOS.forward (IntVOS.py:556-575).  Two weight settings: the plain random
+    initialisation in eval mode (what the config names; identity batch norms let activations grow with depth, so the
+    embedding scale is arbitrary) and the same network with the embedding's last batch norm calibrated to unit variance on
+    this input (the scale a trained network's BN keeps).  Reports the local-matching guard statistic G and the engine that
+    served local matching on these ARCHITECTURE-generated embeddings."""
+    import torch
+    from cvpr2020_manet_b200.config import cfg
+    from cvpr2020_manet_b200.networks import IntVOS as api
+    from cvpr2020_manet_b200.networks.deeplab import IntVOS
+    saved = (cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE)
+    cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE = False, D_LOCAL
+    try:
+        torch.manual_seed(0)
+        model = IntVOS(cfg).to(dev).eval()
+        gen = torch.Generator().manual_seed(0)
+        x = torch.randn(3, 3, 480, 854, generator=gen).to(dev)
+        blob = lambda: torch.randint(0, N_IDS, (480 // 32, 854 // 32 + 1), generator=gen).repeat_interleave(32, 0).repeat_interleave(32, 1)[:480, :854]
+        ref_lab = blob().view(1, 1, 480, 854).float().to(dev)
+        prev_lab = blob().view(1, 1, 480, 854).float().to(dev)
+        n_obj = torch.tensor([N_IDS - 1])
+        out = {}
+        for setting in ("random_init_eval", "embedding_bn_calibrated"):
+            if setting == "embedding_bn_calibrated":
+                with torch.no_grad():
+                    pre = model.embedding_conv(model.relu1(model.bn1(model.seperate_conv(model.feature_extracter(x)))))
+                    model.bn2.running_mean.copy_(pre.mean(dim=(0, 2, 3)))
+                    model.bn2.running_var.copy_(pre.var(dim=(0, 2, 3)))
+            times, t_emb = [], []
+            for i in range(iters + 2):
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                with torch.no_grad():
+                    ev[0].record()
+                    emb = model.extract_feature(x)
+                    ev[1].record()
+                    res = model(x, ref_lab, prev_lab, seq_names=["s"], gt_ids=n_obj, k_nearest_neighbors=1)
+                    ev[2].record()
+                torch.cuda.synchronize()
+                if i >= 2:
+                    t_emb.append(ev[0].elapsed_time(ev[1])); times.append(ev[1].elapsed_time(ev[2]))
+            pred = res["s"]
+            stats = api.local_match_guard_stats(H, W, C, N_IDS, D_LOCAL, dev)
+            ms, ms_emb = sum(times) / len(times), sum(t_emb) / len(t_emb)
+            out[setting] = {"forward_ms": ms, "extract_feature_ms": ms_emb, "matching_and_head_ms": ms - ms_emb,
+                            "frames_per_s": 1e3 / ms, "logits_shape": list(pred.shape), "logits_finite": bool(torch.isfinite(pred).all()),
+                            "embedding_abs_max": float(emb.abs().max()), "embedding_sq_norm_mean": float((emb ** 2).sum(1).mean()),
+                            "local_guard": stats}
+        out["workload"] = ("IntVOS.forward: input [3,3,480,854] (reference, previous, current frame), 5 objects, no memories; "
+                           "DeepLabv3+/ResNet-101 + semantic embedding on torch/cuDNN (library code, default TF32 conv policy of "
+                           "torch), matching + DynamicSegHead on the sm_100a kernels; CUDA events, 5 iterations after 2 warm-ups")
+        return out
+    finally:
+        cfg.TEST_MODE, cfg.MODEL_MAX_LOCAL_DISTANCE = saved
 
 
 def propagation_leg(dev, T=50):

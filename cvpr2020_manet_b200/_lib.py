@@ -40,6 +40,7 @@ SIGNATURES = {
     "manet_select_labelled": (c_int, [_P, _I64, _P, _I64, _I64, _I, _P, _P, _P, _P, _SZ, _P]),
     "manet_local_match_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
     "manet_local_match": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _P, _P, _I, _I, _I, _I, _I, _P, _P, _SZ, _P]),
+    "manet_local_match_guard_stats": (c_int, [_P, _SZ, _I, _I, _I, _I, _I, POINTER(c_float), _P]),
     "manet_local_match_ex": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _P, _P, _I, _I, _I, _I, _I, c_uint32, _P, _P, _SZ, _P]),
     "manet_local_window_distances_ex": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I, _I, _I, _I, c_uint32, _P, _P, _SZ, _P]),
     "manet_local_window_distances": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I, _I, _I, _I, _P, _P, _SZ, _P]),

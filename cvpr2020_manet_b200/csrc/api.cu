@@ -59,6 +59,8 @@ int launch_correlation_forward(const void*, const int64_t*, const void*, const i
 int launch_correlation_backward(const void*, const int64_t*, const void*, const int64_t*, void*, void*, const void*,
                                 const int64_t*, void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 
+const float* lm_umma_stats_ptr(void*, size_t, int, int, int, int, int);
+
 size_t seghead_packed_bytes();
 size_t seghead_workspace_bytes(int N, int H, int W);
 int launch_seghead_pack(const float* const*, int, float, void*, cudaStream_t);
@@ -239,6 +241,19 @@ int manet_local_match_ex(const float* prev, int64_t p_sy, int64_t p_sx, int64_t 
     MANET_REQUIRE(prev && query && labels && gt_ids && out && workspace, "local match: null pointer");
     return launch_local_match(prev, p_sy, p_sx, p_sc, query, q_sy, q_sx, q_sc, labels, gt_ids, H, W, C, N, max_distance,
                               flags, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int manet_local_match_guard_stats(void* workspace, size_t workspace_bytes, int H, int W, int C, int N, int max_distance,
+                                  float* stats_host, manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(workspace && stats_host, "local match guard stats: null pointer");
+    const float* p = lm_umma_stats_ptr(workspace, workspace_bytes, H, W, C, N, max_distance);
+    stats_host[0] = stats_host[1] = -1.0f; stats_host[2] = kLocalGuardG;
+    if (!p) return 0;                         // the tcgen05 engine does not serve this shape: nothing to report
+    cudaError_t e = cudaMemcpyAsync(stats_host, p, 2 * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("local match guard stats: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
 }
 
 int manet_local_match(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_sc, const float* query, int64_t q_sy,

@@ -1018,6 +1018,32 @@ size_t lm_umma_workspace_bytes(int H, int W, int C, int d) {
            align_up(lm_img_bytes_b(g), 256) + align_up((size_t)g.HI * g.WI * sizeof(float), 256) + 2048;
 }
 
+struct LmCarve { float *Pq, *Pp, *blkmax, *blksum, *stats, *Tvol, *Xs, *Ys; uint8_t *plab8, *Aimg, *Bimg; };
+static LmCarve lm_carve(const LmGeom& g, int H, int d, void* ws, size_t ws_bytes) {
+    const int n_tiles = g.ntx * g.nty;
+    Carver cv(ws, ws_bytes);
+    LmCarve c;
+    c.Pq = cv.take<float>((size_t)g.h * g.w * g.Cp);
+    c.Pp = cv.take<float>((size_t)g.h * g.w * g.Cp);
+    c.blkmax = cv.take<float>(8192);
+    c.blksum = cv.take<float>((size_t)g.h * g.nbx * g.Cp);
+    c.plab8 = cv.take<uint8_t>((size_t)(H + 4 * d) * g.PW8);
+    c.stats = cv.take<float>(16);
+    c.Tvol = cv.take<float>((size_t)g.h * g.w * g.D2 * g.D2);
+    c.Aimg = cv.take<uint8_t>((size_t)n_tiles * LM_A_BYTES, 1024);
+    c.Xs = cv.take<float>((size_t)n_tiles * 128);
+    c.Bimg = cv.take<uint8_t>(lm_img_bytes_b(g), 1024);
+    c.Ys = cv.take<float>((size_t)g.HI * g.WI);
+    return c;
+}
+
+// where the last tcgen05 local match on this workspace left {operand scale, guard statistic G}; nullptr: shape not served by it
+const float* lm_umma_stats_ptr(void* ws, size_t ws_bytes, int H, int W, int C, int N, int d) {
+    LmGeom g;
+    if (!lm_geometry(H, W, C, N, d, &g) || ws_bytes < lm_umma_workspace_bytes(H, W, C, d)) return nullptr;
+    return lm_carve(g, H, d, ws, ws_bytes).stats;
+}
+
 // labels == nullptr: only the transformed half-resolution volume is produced (*T_out, [h][w][L]).
 int launch_local_match_umma(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_sc,
                             const float* query, int64_t q_sy, int64_t q_sx, int64_t q_sc,
@@ -1032,18 +1058,10 @@ int launch_local_match_umma(const float* prev, int64_t p_sy, int64_t p_sx, int64
     const int n_blk = 2 * g.h * g.nbx;
     if (n_blk > 8192) return fail_invalid("local match (tcgen05): frame too large");
     const int n_tiles = g.ntx * g.nty;
-    Carver cv(ws, ws_bytes);
-    float* Pq = cv.take<float>((size_t)g.h * g.w * g.Cp);
-    float* Pp = cv.take<float>((size_t)g.h * g.w * g.Cp);
-    float* blkmax = cv.take<float>(8192);
-    float* blksum = cv.take<float>((size_t)g.h * g.nbx * g.Cp);
-    uint8_t* plab8 = cv.take<uint8_t>((size_t)(H + 4 * d) * g.PW8);
-    float* stats = cv.take<float>(16);
-    float* Tvol = cv.take<float>((size_t)g.h * g.w * g.D2 * g.D2);
-    uint8_t* Aimg = cv.take<uint8_t>((size_t)n_tiles * LM_A_BYTES, 1024);
-    float* Xs = cv.take<float>((size_t)n_tiles * 128);
-    uint8_t* Bimg = cv.take<uint8_t>(lm_img_bytes_b(g), 1024);
-    float* Ys = cv.take<float>((size_t)g.HI * g.WI);
+    const LmCarve cvd = lm_carve(g, H, d, ws, ws_bytes);
+    float *Pq = cvd.Pq, *Pp = cvd.Pp, *blkmax = cvd.blkmax, *blksum = cvd.blksum, *stats = cvd.stats, *Tvol = cvd.Tvol, *Xs = cvd.Xs,
+          *Ys = cvd.Ys;
+    uint8_t *plab8 = cvd.plab8, *Aimg = cvd.Aimg, *Bimg = cvd.Bimg;
     LmPoolSrc a{query, q_sy, q_sx, q_sc, Pq}, b{prev, p_sy, p_sx, p_sc, Pp};
     LmAux aux{labels, gt_ids, labels ? plab8 : nullptr, H, W, 2 * d, g.PW8, N, labels ? out : nullptr, (int64_t)H * W * N, stats};
     const size_t pool_smem = (size_t)LM_POOL_PX * (g.Cp + 1) * sizeof(float);

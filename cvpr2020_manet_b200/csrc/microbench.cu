@@ -62,23 +62,27 @@ tmem_ld_bench_kernel(int iters, int warps, long long* __restrict__ cycles, float
                     acc0 = fmaxf(acc0, __uint_as_float(r[0]));
                 }
             } else {
-                uint32_t r[2][32];
-                tmem_ld32(taddr0, r[0]);
-                for (int c = 0; c < cols; c += 32) {
-                    const int b = (c >> 5) & 1;
-                    tmem_ld_wait_dep(r[b]);
-                    if (c + 32 < cols) tmem_ld32(taddr0 + c + 32, r[b ^ 1]);
-                    if (MODE == 2) {
+                // 128 columns at a time, fully unrolled exactly like gm_umma2_kernel's epilogue_half_tile (compile-time register
+                // indices: a run-time buffer index would push r[][] into local memory and measure that instead)
+                for (int c0 = 0; c0 < cols; c0 += 128) {
+                    uint32_t r[2][32];
+                    tmem_ld32(taddr0 + c0, r[0]);
 #pragma unroll
-                        for (int i = 0; i < 8; i += 2) {
-                            const uint32_t* q = r[b] + 4 * i;
-                            acc0 = fmaxf(fmaxf(acc0, __uint_as_float(q[0])), __uint_as_float(q[4]));
-                            acc1 = fmaxf(fmaxf(acc1, __uint_as_float(q[1])), __uint_as_float(q[5]));
-                            acc2 = fmaxf(fmaxf(acc2, __uint_as_float(q[2])), __uint_as_float(q[6]));
-                            acc3 = fmaxf(fmaxf(acc3, __uint_as_float(q[3])), __uint_as_float(q[7]));
+                    for (int ch = 0; ch < 4; ++ch) {
+                        tmem_ld_wait_dep(r[ch & 1]);
+                        if (ch + 1 < 4) tmem_ld32(taddr0 + c0 + (ch + 1) * 32, r[(ch + 1) & 1]);
+                        if (MODE == 2) {
+#pragma unroll
+                            for (int i = 0; i < 8; i += 2) {
+                                const uint32_t* q = r[ch & 1] + 4 * i;
+                                acc0 = fmaxf(fmaxf(acc0, __uint_as_float(q[0])), __uint_as_float(q[4]));
+                                acc1 = fmaxf(fmaxf(acc1, __uint_as_float(q[1])), __uint_as_float(q[5]));
+                                acc2 = fmaxf(fmaxf(acc2, __uint_as_float(q[2])), __uint_as_float(q[6]));
+                                acc3 = fmaxf(fmaxf(acc3, __uint_as_float(q[3])), __uint_as_float(q[7]));
+                            }
+                        } else {
+                            acc0 = fmaxf(acc0, __uint_as_float(r[ch & 1][0]));
                         }
-                    } else {
-                        acc0 = fmaxf(acc0, __uint_as_float(r[b][0]));
                     }
                 }
             }

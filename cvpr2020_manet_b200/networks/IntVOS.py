@@ -399,3 +399,26 @@ def local_previous_frame_nearest_neighbor_features_per_object(prev_frame_embeddi
                                      labels.data_ptr(), ids.data_ptr(), h, w, c, n_obj, d, _local_flags(), out.data_ptr(),
                                      ws.data_ptr(), ws.numel(), stream_ptr(dev)), "manet_local_match")
     return out
+
+
+def local_match_guard_stats(height, width, channels, n_objects, max_distance, device=None):
+    """Diagnostics of the last ``local_previous_frame_nearest_neighbor_features_per_object`` call of this shape on the
+    current stream: ``{"scale", "G", "threshold", "engine"}`` where ``G = max |x - mu|^2`` over both pooled frames is the
+    statistic the tcgen05 engine's device-side numerics guard compares with ``threshold``; ``engine`` names which kernels
+    produced the result.  Synchronises the stream."""
+    import ctypes
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    L = _lib.lib()
+    ws = workspace(dev, L.manet_local_match_workspace_bytes(height, width, channels, n_objects, int(max_distance)), "local")
+    buf = (ctypes.c_float * 3)()
+    with torch.cuda.device(dev):
+        check(L.manet_local_match_guard_stats(ws.data_ptr(), ws.numel(), height, width, channels, n_objects, int(max_distance), buf,
+                                              stream_ptr(dev)), "manet_local_match_guard_stats")
+    scale, g, thr = float(buf[0]), float(buf[1]), float(buf[2])
+    if g < 0 or FORCE_SIMT_LOCAL_ENGINE:
+        engine = "cuda-core (shape not served by the tcgen05 engine)" if g < 0 else "cuda-core (forced)"
+    elif FORCE_TENSOR_LOCAL_ENGINE or g <= thr:
+        engine = "tcgen05"
+    else:
+        engine = "cuda-core (numerics guard tripped)"
+    return {"scale": scale, "G": g, "threshold": thr, "engine": engine}

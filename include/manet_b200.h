@@ -136,6 +136,13 @@ int manet_local_match(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_s
                       const int32_t* labels, const int32_t* gt_ids,
                       int H, int W, int C, int N, int max_distance, float* out,
                       void* workspace, size_t workspace_bytes, manet_stream_t stream);
+/* Diagnostics for the tcgen05 local-matching engine's device-side numerics guard: after a manet_local_match[_ex] call on
+ * `workspace` (same H, W, C, N, max_distance) copies {operand scale, G, threshold} to stats_host[3], where G = max |x - mu|^2
+ * over both pooled frames; the tensor-core result is used iff G <= threshold (otherwise the exact CUDA-core kernels
+ * produced the output).  {-1, -1, threshold} when the shape is not served by the tcgen05 engine.  Synchronises `stream`. */
+int manet_local_match_guard_stats(void* workspace, size_t workspace_bytes, int H, int W, int C, int N, int max_distance,
+                                  float* stats_host, manet_stream_t stream);
+
 
 /* Same with flags.  manet_local_match == flags 0 = the guarded default: when the shape allows it
  * (max_distance <= 12, C <= 128, H,W >= 6, N <= 64 and within shared memory) the tcgen05 engine computes
