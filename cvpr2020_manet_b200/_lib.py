@@ -17,6 +17,7 @@ HEADER_PATH = os.path.join(os.path.dirname(PKG_DIR), "include", "manet_b200.h")
 GM_NORMALIZE = 1
 GM_DROP_UNLAB = 2
 GM_ENGINE_SIMT = 4
+GM_ENGINE_EXACT3 = 8
 LM_ENGINE_SIMT = 1
 LM_ENGINE_TENSOR = 2
 STEP_SERIAL = 16
@@ -45,6 +46,7 @@ SIGNATURES = {
     "manet_local_window_distances_ex": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I, _I, _I, _I, c_uint32, _P, _P, _SZ, _P]),
     "manet_local_window_distances": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I, _I, _I, _I, _P, _P, _SZ, _P]),
     "manet_global_match_argmin": (c_int, [_P, _I64, _I64, _I64, _P, _P, _I64, _I64, _I64, _I, _I, _P, _P, _P]),
+    "manet_global_match_argmin_ws": (c_int, [_P, _I64, _I64, _I64, _P, _P, _I64, _I64, _I64, _I, _I, c_uint32, _P, _P, _P, _SZ, _P]),
     "manet_global_match_backward": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I, _I, _P, _P, _P, _P, _P]),
     "manet_local_match_grad_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
     "manet_local_match_argmin": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _SZ, _P]),
@@ -68,6 +70,7 @@ SIGNATURES = {
     "manet_profile_read": (c_int, [_I, POINTER(c_float), _I, POINTER(c_int)]),
     "manet_profile_launch_count": (ctypes.c_longlong, []),
     "manet_profile_reset_launches": (c_int, []),
+    "manet_set_option": (c_int, [c_char_p, _I]),
     "manet_microbench_tmem_ld": (c_int, [_I, _I, _I, _I, POINTER(ctypes.c_longlong), _P]),
     "manet_session_create": (_P, [_I, _I, _I, _I, _I, _I]),
     "manet_session_destroy": (None, [_P]),

@@ -32,9 +32,9 @@ int launch_pairwise_sqdist(const float*, int64_t, int64_t, int64_t, const float*
 int launch_row_sqnorm(const float*, int64_t, int64_t, int64_t, int, float*, cudaStream_t);
 int launch_global_map_update(const float*, float*, float*, int64_t, int, cudaStream_t);
 bool gm_umma_supported(int C, int N, int k);
-size_t gm_umma_workspace_bytes(int64_t M, int64_t R, int N);
+size_t gm_umma_workspace_bytes(int64_t M, int64_t R, int N, int C);
 int launch_global_match_umma(const float*, int64_t, int64_t, int64_t, const int32_t*, const float*, int64_t, int64_t, int64_t,
-                             int, int, int, float*, float*, void*, size_t, cudaStream_t);
+                             int, int, int, float*, float*, int32_t*, int, void*, size_t, cudaStream_t);
 size_t select_workspace_bytes(int64_t R);
 int launch_select_labelled(const int32_t*, int64_t, const float*, int64_t, int64_t, int, int32_t*, float*, int64_t*, void*,
                            size_t, cudaStream_t);
@@ -75,6 +75,7 @@ int launch_upsample_argmax(const float*, int, int, int, int, int, int64_t*, int3
 
 int launch_rough_roi(const int32_t*, int, int, int, int, int32_t*, int*, cudaStream_t);
 
+int gm_set_option(const char*, int);
 int launch_tmem_ld_bench(int, int, int, int, long long*, float*, cudaStream_t);
 
 // ---- launch counter (bench.py's gpu_launches): relaxed atomic, host threads may launch concurrently
@@ -159,7 +160,7 @@ const char* manet_last_error(void) { return g_err; }
 int manet_check_device(void) { return arch_ok(); }
 
 size_t manet_global_match_workspace_bytes(int64_t M, int64_t R, int C, int N, int k) {
-    if (gm_umma_supported(C, N, k)) return gm_umma_workspace_bytes(M, R, N);
+    if (gm_umma_supported(C, N, k)) return gm_umma_workspace_bytes(M, R, N, C);
     return 256;
 }
 
@@ -175,7 +176,8 @@ int manet_global_match(const float* ref, int64_t ref_pix_stride, int64_t ref_ch_
     const int normalize = (flags & MANET_GM_NORMALIZE) ? 1 : 0;
     if (!(flags & MANET_GM_ENGINE_SIMT) && gm_umma_supported(C, N, k))
         return launch_global_match_umma(ref, ref_pix_stride, ref_ch_stride, R, labels, query, q_pix_stride, q_ch_stride, M,
-                                        C, N, normalize, mem_frame, out, workspace, workspace_bytes, st);
+                                        C, N, normalize, mem_frame, out, nullptr, (flags & MANET_GM_ENGINE_EXACT3) ? 1 : 0, workspace,
+                                        workspace_bytes, st);
     // CUDA-core engine: k > 1, C > 128, N > 64, or forced.  Labels outside [0,N) (incl. -1) never
     // match, so MANET_GM_DROP_UNLAB needs no extra work here.
     if (M == 0) return 0;
@@ -287,6 +289,19 @@ int manet_global_match_argmin(const float* ref, int64_t ref_pix_stride, int64_t 
     MANET_REQUIRE(M >= 0 && R >= 0 && C >= 1 && N >= 1, "global match (argmin): bad sizes");
     return launch_global_match_argmin(ref, ref_pix_stride, ref_ch_stride, R, labels, query, q_pix_stride, q_ch_stride, M, C, N,
                                       out, out_idx, (cudaStream_t)stream);
+}
+
+int manet_global_match_argmin_ws(const float* ref, int64_t ref_pix_stride, int64_t ref_ch_stride, int64_t R,
+                                 const int32_t* labels, const float* query, int64_t q_pix_stride, int64_t q_ch_stride,
+                                 int64_t M, int C, int N, uint32_t flags, float* out, int32_t* out_idx, void* workspace,
+                                 size_t workspace_bytes, manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(query && out && out_idx && workspace && (R == 0 || (ref && labels)), "global match (argmin): null pointer");
+    MANET_REQUIRE(M >= 0 && R >= 0 && C >= 1 && N >= 1, "global match (argmin): bad sizes");
+    MANET_REQUIRE(gm_umma_supported(C, N, 1), "global match (argmin, tcgen05): needs C <= 128 and N <= 64");
+    (void)flags;     // labels outside [0, N) -- including -1 -- never match: MANET_GM_DROP_UNLAB needs no extra work
+    return launch_global_match_umma(ref, ref_pix_stride, ref_ch_stride, R, labels, query, q_pix_stride, q_ch_stride, M, C, N, 0,
+                                    nullptr, out, out_idx, 0, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int manet_global_match_backward(const float* ref, int64_t ref_pix_stride, int64_t ref_ch_stride, int64_t R,
@@ -463,6 +478,11 @@ int manet_profile_read(int slot, float* ms_out, int capacity, int* n_out) {
     }
     *n_out = n;
     return 0;
+}
+
+int manet_set_option(const char* name, int value) {
+    if (!name) return -1;
+    return gm_set_option(name, value);
 }
 
 long long manet_profile_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

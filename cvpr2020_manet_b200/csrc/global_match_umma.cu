@@ -25,6 +25,7 @@
 // Tiles are 128 (queries) x 256 (references), accumulators double-buffered in TMEM (2 x 256
 // columns) so the epilogue of tile t overlaps the MMAs of tile t+1.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "umma_ptx.cuh"
@@ -54,6 +55,13 @@ struct GmCtrl {
     int n_rtiles;                  // number of 256-row reference tiles
     float scale_q, scale_r;        // power-of-two operand scales
     int bias_fold;                 // 1: -s/2*|r|^2 travels through the GEMM (gm_bias_plan), epilogue is a bare max
+    // ---- filter-and-refine engine (gm_fr_kernel + gm_refine_kernel + gm_rescan_kernel)
+    unsigned rh_max_bits[GM_MAXN]; // per object: max over its reference rows of |hi part|_2 (scaled units), float bits
+    unsigned rl_max_bits[GM_MAXN]; // ... of |lo part|_2
+    unsigned bias_max_bits[GM_MAXN]; // ... of |s/2 |r|^2|
+    int seg_first[GM_MAXN + 1];    // first segment of each object (a segment = seg_tiles consecutive 256-row tiles of one object)
+    int n_segs;
+    int rescan_count;              // entries pushed to the rescan work list
 };
 
 // Row-max of (accumulator + ysn) over this warp's 128 columns of one tile.  TMEM loads are software
@@ -221,25 +229,35 @@ __device__ __forceinline__ void split8(const float (&v)[8], float s, uint4& hi, 
 // then each (row, 16-byte chunk) is converted by one thread so that 8 consecutive lanes write one
 // full 128-byte line of the swizzled tile image.
 constexpr int GM_CV_PIX = 128;
+// Extra products of the pre-pass for the filter-and-refine engine (all null / 0 for the three-product engine):
+// exact fp32 pixel-major copies of both operands (what the refinement evaluates), per-query-row norms of the fp16 hi / lo
+// parts (the rigorous error bound of the one-product filter), the original index of every bucketed reference row (arg-min),
+// and the segment tables.  `seg_tiles` = tiles per segment (host-chosen so that the candidate-key array stays bounded).
+struct GmFrPre {
+    float* q32; float* r32; float2* qn; int* src_idx; int* tile_seg; int* seg_tile0;
+    int C4; int seg_tiles; int skip_lo;
+};
 __global__ void __launch_bounds__(256)
 gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64_t R, const int32_t* __restrict__ labels,
                   const float* __restrict__ query, int64_t qps, int64_t qcs, int64_t M, int64_t M_pad, int C, int N,
                   int nb_ref, int nb_q, GmCtrl* __restrict__ ctrl, uint8_t* __restrict__ Aimg, uint8_t* __restrict__ Bimg,
-                  float* __restrict__ xs, float* __restrict__ ysn, int* __restrict__ tile_obj) {
+                  float* __restrict__ xs, float* __restrict__ ysn, int* __restrict__ tile_obj, const GmFrPre fr) {
     pdl_enter();
     __shared__ float tile[64][GM_CV_PIX + 1];
     __shared__ int off[GM_MAXN + 1];
     __shared__ int bcnt[GM_MAXN], bbase[GM_MAXN];
     __shared__ int64_t pos_s[GM_CV_PIX];
-    __shared__ float rowsq[GM_CV_PIX];
+    __shared__ float rowsq[GM_CV_PIX], rowh[GM_CV_PIX], rowl[GM_CV_PIX];
+    __shared__ int lab_s[GM_CV_PIX];
+    __shared__ unsigned omax[3][GM_MAXN];
     const int t = threadIdx.x;
     if (t == 0) {
         int o = 0;
         for (int i = 0; i < N; ++i) { off[i] = o; o += (ctrl->counts[i] + GM_BN - 1) / GM_BN * GM_BN; }
         off[N] = o;
     }
-    if (t < GM_MAXN) bcnt[t] = 0;
-    if (t < GM_CV_PIX) { rowsq[t] = 0.f; pos_s[t] = -1; }
+    if (t < GM_MAXN) { bcnt[t] = 0; omax[0][t] = omax[1][t] = omax[2][t] = 0u; }
+    if (t < GM_CV_PIX) { rowsq[t] = rowh[t] = rowl[t] = 0.f; pos_s[t] = -1; lab_s[t] = -1; }
     __syncthreads();
     const float s_q = pow2_scale(ctrl->absmax_bits[1]);
     const float s_r = pow2_scale(ctrl->absmax_bits[0]);
@@ -254,6 +272,19 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
         if (t == 0) { ctrl->n_rtiles = off[N] / GM_BN; ctrl->scale_q = s_q; ctrl->scale_r = s_r; ctrl->bias_fold = bias.on ? 1 : 0; }
         for (int o = 0; o < N; ++o)
             for (int tl = off[o] / GM_BN + t; tl < off[o + 1] / GM_BN; tl += 256) tile_obj[tl] = o;
+        if (fr.tile_seg != nullptr) {
+            // segments: runs of fr.seg_tiles consecutive tiles of one object; tile -> segment, segment -> first tile
+            const int S = fr.seg_tiles;
+            int s0 = 0;
+            for (int o = 0; o < N; ++o) {
+                const int t0 = off[o] / GM_BN, t1 = off[o + 1] / GM_BN, ns = (t1 - t0 + S - 1) / S;
+                if (t == 0) ctrl->seg_first[o] = s0;
+                for (int tl = t0 + t; tl < t1; tl += 256) fr.tile_seg[tl] = s0 + (tl - t0) / S;
+                for (int j = t; j < ns; j += 256) fr.seg_tile0[s0 + j] = t0 + j * S;
+                s0 += ns;
+            }
+            if (t == 0) { ctrl->seg_first[N] = s0; ctrl->n_segs = s0; fr.seg_tile0[s0] = off[N] / GM_BN; }
+        }
     }
     if (b >= nb_ref + nb_q) {
         // bucket padding rows: zero operands, -inf bias (never wins the row max)
@@ -263,9 +294,9 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
             const uint4 z = make_uint4(0, 0, 0, 0);
             for (int j = 0; j < nchunks; ++j) {
                 *reinterpret_cast<uint4*>(Bimg + image_chunk_offset(pos, 0, j)) = z;
-                *reinterpret_cast<uint4*>(Bimg + image_chunk_offset(pos, 1, j)) = z;
+                if (!fr.skip_lo) *reinterpret_cast<uint4*>(Bimg + image_chunk_offset(pos, 1, j)) = z;
             }
-            ysn[pos] = -INFINITY;
+            ysn[pos] = -3.0e38f;                             // finite: the filter engine ORs index bits into the sum (no NaNs)
             if (bias.on) {                                  // columns 12..15 of the folded step: v1..v4
                 __half v[4] = {__float2half_rn(-65504.f), __float2half_rn(0.f), __float2half_rn(0.f), __float2half_rn(-65504.f)};
                 *reinterpret_cast<uint2*>(Bimg + image_chunk_offset(pos, 0, j_fold + 1) + 8) = *reinterpret_cast<uint2*>(v);
@@ -289,7 +320,11 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
         __syncthreads();
         if (t < N && bcnt[t]) bbase[t] = atomicAdd(&ctrl->cursors[t], bcnt[t]);
         __syncthreads();
-        if (keep) pos_s[t] = (int64_t)off[lab] + bbase[lab] + rank;
+        if (keep) {
+            pos_s[t] = (int64_t)off[lab] + bbase[lab] + rank;
+            lab_s[t] = lab;
+            if (fr.src_idx != nullptr) fr.src_idx[pos_s[t]] = (int)(p0 + t);
+        }
     } else if (t < GM_CV_PIX && p0 + t < M_pad) {
         pos_s[t] = p0 + t;
     }
@@ -317,6 +352,27 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
             sq += __shfl_xor_sync(0xffffffffu, sq, 2);
             sq += __shfl_xor_sync(0xffffffffu, sq, 4);
             const int64_t pos = pos_s[row];
+            if (fr.q32 != nullptr) {
+                // |hi|^2 and |lo|^2 of this row (scaled units) and the exact fp32 copy, 32 contiguous bytes per thread
+                float hs = 0.f, ls = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float x = v[k] * scale;
+                    const float h = __half2float(__float2half_rn(x));
+                    const float l = __half2float(__float2half_rn(x - h));
+                    hs = fmaf(h, h, hs); ls = fmaf(l, l, ls);
+                }
+                hs += __shfl_xor_sync(0xffffffffu, hs, 1); ls += __shfl_xor_sync(0xffffffffu, ls, 1);
+                hs += __shfl_xor_sync(0xffffffffu, hs, 2); ls += __shfl_xor_sync(0xffffffffu, ls, 2);
+                hs += __shfl_xor_sync(0xffffffffu, hs, 4); ls += __shfl_xor_sync(0xffffffffu, ls, 4);
+                if (chk == 0) { rowh[row] += hs; rowl[row] += ls; }
+                const int c0 = kb * 64 + chk * 8;
+                if (pos >= 0 && c0 < fr.C4) {
+                    float* dst = (is_ref ? fr.r32 : fr.q32) + (size_t)pos * fr.C4 + c0;
+                    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                    if (c0 + 4 < fr.C4) *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
+            }
             if (pos >= 0 && j < nchunks) {
                 uint4 hi, lo;
                 if (fold && j >= j_fold) {
@@ -341,7 +397,7 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
                     split8(v, scale, hi, lo);
                 }
                 *reinterpret_cast<uint4*>(img + image_chunk_offset(pos, 0, j)) = hi;
-                *reinterpret_cast<uint4*>(img + image_chunk_offset(pos, 1, j)) = lo;
+                if (!fr.skip_lo) *reinterpret_cast<uint4*>(img + image_chunk_offset(pos, 1, j)) = lo;
             }
             if (chk == 0) rowsq[row] += sq;                // one lane per row and slab: no race
         }
@@ -366,6 +422,26 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
         }
         if (bias.on)
             *reinterpret_cast<uint2*>(img + image_chunk_offset(pos, 0, j_fold + 1) + 8) = *reinterpret_cast<uint2*>(v);
+        if (fr.q32 != nullptr) {
+            // upper bounds (rounded up a little: they enter an error bound) of |hi|_2 and |lo|_2
+            const float nh = sqrtf(rowh[t]) * 1.000001f, nl = sqrtf(rowl[t]) * 1.000001f;
+            if (is_ref) {
+                const int lab = lab_s[t];
+                atomicMax(&omax[0][lab], __float_as_uint(nh));
+                atomicMax(&omax[1][lab], __float_as_uint(nl));
+                atomicMax(&omax[2][lab], __float_as_uint(0.5f * (s_q * s_r) * rowsq[t]));
+            } else {
+                fr.qn[pos] = make_float2(nh, nl);
+            }
+        }
+    }
+    if (fr.q32 != nullptr && is_ref) {
+        __syncthreads();
+        if (t < N) {
+            if (omax[0][t]) atomicMax(&ctrl->rh_max_bits[t], omax[0][t]);
+            if (omax[1][t]) atomicMax(&ctrl->rl_max_bits[t], omax[1][t]);
+            if (omax[2][t]) atomicMax(&ctrl->bias_max_bits[t], omax[2][t]);
+        }
     }
 }
 
@@ -954,13 +1030,465 @@ __global__ void gm_finalize_kernel(const int* __restrict__ best, const float* __
     out[i] = v;
 }
 
+// ------------------------------------------------------------------------------------ filter-and-refine engine
+// The three-product kernel above spends 19 tensor-core K steps per tile to get fp32-grade distances for EVERY (query,
+// reference) pair, although only the per-object minimum survives.  This engine spends 7: one product of the fp16 hi parts
+// (+ the folded bias) FILTERS the candidates, and the survivors -- almost always one pair of neighbouring reference rows
+// per (query, object) -- are re-evaluated EXACTLY in fp32 from the original operands.  Exactness does not rest on luck:
+//
+//   approximate score  s~ = qh.rh + bias   (tensor core)          true score  s = q^.r^ + bias   (q^ = s_q q, r^ = s_r r)
+//   |s~ - s| <= |ql||rh| + |qh||rl| + |ql||rl| + tau  =: E        (Cauchy-Schwarz on the dropped cross terms; the row norms
+//                                                                   come from the pre-pass, tau covers the accumulator and
+//                                                                   the 6 index bits written into each key)
+//   => the reference row with the largest TRUE score has  s~ >= max s~ - 2E.
+//
+// The epilogue therefore keeps, per query row and per SEGMENT-half (128 columns of seg_tiles consecutive tiles of one
+// object), the two largest keys; a key is the maximum of two neighbouring columns with the pair's index in its low
+// mantissa bits.  gm_refine_kernel takes every key within Delta = 2E of the row's best, evaluates sum (q-r)^2 in fp32 for
+// the two rows it names and keeps the smallest; where BOTH keys of a segment-half are within Delta a third candidate could
+// hide behind them, so that segment-half is re-scanned exactly (gm_rescan_kernel, a work list that is empty for all but
+// near-tied data).  The result is the true per-object minimum of the fp32 distances whatever the data; only the speed
+// depends on how many near-ties there are.
+constexpr int FR_GROUPS = GM_BN / 2 / 2;                        // pairs of columns per 128-column half tile
+constexpr uint32_t FR_KEY_MASK = 0xFFFFFFC0u;                   // ... whose index takes the low 6 mantissa bits of a key
+static_assert(FR_GROUPS == 64, "the key layout assumes 64 column pairs per half tile");
+constexpr float FR_NEG = -3.0e38f;
+
+__device__ __forceinline__ float fr_key(float v, int g) { return __uint_as_float((__float_as_uint(v) & FR_KEY_MASK) | (uint32_t)g); }
+
+// two largest keys of this warp's 128 columns of one accumulator tile
+template <bool BIAS_IN_ACC>
+__device__ __forceinline__ void fr_half_tile_top2(uint32_t taddr, const float4* __restrict__ yv, float& M1, float& M2) {
+    uint32_t r[2][32];
+    float a1 = FR_NEG, a2 = FR_NEG, b1 = FR_NEG, b2 = FR_NEG;           // two independent chains
+    tmem_ld32(taddr, r[0]);
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+        float4 y[8];
+        if (!BIAS_IN_ACC) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y[i] = __ldg(yv + ch * 8 + i);
+        }
+        tmem_ld_wait_dep(r[ch & 1]);
+        if (ch + 1 < 4) tmem_ld32(taddr + (ch + 1) * 32, r[(ch + 1) & 1]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {                                   // columns 4i .. 4i+3 = groups 2i, 2i+1 of this chunk
+            float x0 = __uint_as_float(r[ch & 1][4 * i]), x1 = __uint_as_float(r[ch & 1][4 * i + 1]);
+            float x2 = __uint_as_float(r[ch & 1][4 * i + 2]), x3 = __uint_as_float(r[ch & 1][4 * i + 3]);
+            if (!BIAS_IN_ACC) { x0 += y[i].x; x1 += y[i].y; x2 += y[i].z; x3 += y[i].w; }
+            const float ka = fr_key(fmaxf(x0, x1), ch * 16 + 2 * i), kb = fr_key(fmaxf(x2, x3), ch * 16 + 2 * i + 1);
+            const float hi = fmaxf(ka, kb), lo = fminf(ka, kb);
+            if (i & 1) { const float t = fminf(b1, hi); b2 = fmaxf(fmaxf(b2, t), lo); b1 = fmaxf(b1, hi); }
+            else       { const float t = fminf(a1, hi); a2 = fmaxf(fmaxf(a2, t), lo); a1 = fmaxf(a1, hi); }
+        }
+    }
+    M1 = fmaxf(a1, b1);
+    M2 = fmaxf(fmaxf(fminf(a1, b1), a2), b2);
+}
+
+// first tile of the next segment (or of the next query tile pair) at or after linear tile index x
+__device__ __forceinline__ long long fr_snap(long long x, long long total, int n_rtiles, const int* __restrict__ tile_seg,
+                                             const int* __restrict__ seg_tile0) {
+    if (x >= total) return total;
+    const long long m = x / n_rtiles; const int rt = (int)(x % n_rtiles);
+    const int sg = __ldg(tile_seg + rt);
+    if (__ldg(seg_tile0 + sg) == rt) return x;
+    return m * n_rtiles + __ldg(seg_tile0 + sg + 1);          // seg_tile0[n_segs] = n_rtiles: rolls over to the next m
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
+gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg, const float* __restrict__ ysn,
+             const int* __restrict__ tile_seg, const int* __restrict__ seg_tile0, const GmCtrl* __restrict__ ctrl,
+             float2* __restrict__ keys, uint32_t* __restrict__ tags, int64_t M_pad, int n_mpairs, int ksteps, int seg_tiles) {
+    pdl_enter();
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    const uint32_t sA = base;                                  // 32 KB: hi part of this CTA's 128 query rows
+    const uint32_t sB = base + 2 * GM_CHUNK_BYTES;             // ring of G2_STAGES x 32 KB: hi part of this CTA's half of a tile
+    const uint32_t bars = base + 2 * GM_CHUNK_BYTES + G2_STAGES * G2_STAGE_BYTES;
+    const uint32_t full_b = bars + 0;            // [4]  local bytes landed
+    const uint32_t empty_b = bars + 32;          // [4]  stage free (multicast commit)
+    const uint32_t peer_full = bars + 64;        // [4]  leader only: peer's half landed
+    const uint32_t a_full = bars + 96;
+    const uint32_t a_empty = bars + 104;
+    const uint32_t peer_a_full = bars + 112;     // leader only
+    const uint32_t tmem_full = bars + 120;       // [2]
+    const uint32_t tmem_empty = bars + 136;      // [2]  leader only, 16 arrivals
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 2 * GM_CHUNK_BYTES + G2_STAGES * G2_STAGE_BYTES + 160);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int n_rtiles = ctrl->n_rtiles;
+    const bool bias_in_acc = ctrl->bias_fold != 0;
+    const long long total = (long long)n_mpairs * n_rtiles;
+    const int n_clusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
+    // contiguous ranges of tiles, cut at segment boundaries: a (query row, segment-half) is reduced by exactly one warp
+    const long long t_begin = fr_snap(total * cid / n_clusters, total, n_rtiles, tile_seg, seg_tile0);
+    const long long t_end = fr_snap(total * (cid + 1) / n_clusters, total, n_rtiles, tile_seg, seg_tile0);
+
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < G2_STAGES; ++i) { mbar_init(full_b + 8 * i, 1); mbar_init(empty_b + 8 * i, 1); mbar_init(peer_full + 8 * i, 1); }
+            mbar_init(a_full, 1); mbar_init(a_empty, 1); mbar_init(peer_a_full, 1);
+            for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, 2 * GM_EPI_WARPS); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------ producer (both CTAs: hi part of own A rows, of own half of B)
+        Ring st; uint32_t ae_phase = 0; long long cur_m = -1;
+        for (long long tile = t_begin; tile < t_end; ++tile) {
+            const long long m = tile / n_rtiles; const long long rt = tile % n_rtiles;
+            if (m != cur_m) {
+                mbar_wait(a_empty, ae_phase ^ 1); ae_phase ^= 1;
+                if (elect_one()) {
+                    mbar_expect_tx(a_full, 2 * GM_CHUNK_BYTES);
+                    bulk_g2s(sA, Aimg + (size_t)(2 * m + rank) * GM_UNIT_BYTES, 2 * GM_CHUNK_BYTES, a_full);
+                }
+                __syncwarp();
+                cur_m = m;
+            }
+            mbar_wait(empty_b + 8 * st.idx, st.phase ^ 1);
+            if (elect_one()) {
+                mbar_expect_tx(full_b + 8 * st.idx, G2_STAGE_BYTES);
+                bulk_g2s(sB + st.idx * G2_STAGE_BYTES, Bimg + (size_t)(2 * rt + rank) * GM_UNIT_BYTES, G2_STAGE_BYTES, full_b + 8 * st.idx);
+            }
+            __syncwarp();
+            st.advance(G2_STAGES);
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            // -------------------------------------------- MMA issuer: qh.rh only, `ksteps` K steps per 256 x 256 tile
+            constexpr uint32_t idesc = idesc_f16(2 * GM_BM, GM_BN);
+            const uint64_t descA = smem_desc_sw128(sA);
+            Ring st, acc; uint32_t af_phase = 0; long long cur_m = -1;
+            for (long long tile = t_begin; tile < t_end; ++tile) {
+                const long long m = tile / n_rtiles;
+                if (m != cur_m) { mbar_wait(a_full, af_phase); mbar_wait_cluster(peer_a_full, af_phase); af_phase ^= 1; cur_m = m; }
+                mbar_wait_cluster(tmem_empty + 8 * acc.idx, acc.phase ^ 1);
+                mbar_wait(full_b + 8 * st.idx, st.phase);
+                mbar_wait_cluster(peer_full + 8 * st.idx, st.phase);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc.idx * GM_BN;
+                const uint64_t descB = smem_desc_sw128(sB + st.idx * G2_STAGE_BYTES);
+                const bool last_of_m = (tile + 1 == t_end) || ((tile + 1) / n_rtiles != m);
+                if (elect_one()) {
+                    for (int k = 0; k < ksteps; ++k) {
+                        const uint64_t o = (uint64_t)((k >> 2) * (GM_CHUNK_BYTES >> 4) + (k & 3) * 2);
+                        umma2_f16(d_tmem, descA + o, descB + o, idesc, k > 0);
+                    }
+                    tc_commit2(empty_b + 8 * st.idx);
+                    tc_commit2(tmem_full + 8 * acc.idx);
+                    if (last_of_m) tc_commit2(a_empty);
+                }
+                __syncwarp();
+                st.advance(G2_STAGES);
+                acc.advance(2);
+            }
+        } else {
+            // -------------------------------------------- peer: forward "landed" to the leader
+            const uint32_t r_peer_full = mapa_shared(peer_full, 0), r_peer_a = mapa_shared(peer_a_full, 0);
+            Ring st; uint32_t af_phase = 0; long long cur_m = -1;
+            for (long long tile = t_begin; tile < t_end; ++tile) {
+                const long long m = tile / n_rtiles;
+                if (m != cur_m) {
+                    mbar_wait(a_full, af_phase); af_phase ^= 1;
+                    if (elect_one()) mbar_arrive_remote(r_peer_a);
+                    __syncwarp();
+                    cur_m = m;
+                }
+                mbar_wait(full_b + 8 * st.idx, st.phase);
+                if (elect_one()) mbar_arrive_remote(r_peer_full + 8 * st.idx);
+                __syncwarp();
+                st.advance(G2_STAGES);
+            }
+        }
+    } else {
+        // ------------------------------------------------ epilogue (warps 2..9 of both CTAs): per-segment top-2 keys
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = quarter * 32 + lane;
+        const uint32_t r_tmem_empty = mapa_shared(tmem_empty, 0);
+        Ring acc;
+        float V1 = FR_NEG, V2 = FR_NEG; uint32_t T1 = 0, T2 = 0;           // running top-2 of the open segment, tile offsets
+        for (long long tile = t_begin; tile < t_end; ++tile) {
+            const long long m = tile / n_rtiles; const int rt = (int)(tile % n_rtiles);
+            const int sg = __ldg(tile_seg + rt);
+            const uint32_t toff = (uint32_t)(rt - __ldg(seg_tile0 + sg));
+            mbar_wait(tmem_full + 8 * acc.idx, acc.phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * GM_BN + half * (GM_BN / 2);
+            float M1, M2;
+            if (bias_in_acc) fr_half_tile_top2<true>(taddr, nullptr, M1, M2);
+            else fr_half_tile_top2<false>(taddr, reinterpret_cast<const float4*>(ysn + (size_t)rt * GM_BN + half * (GM_BN / 2)), M1, M2);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(r_tmem_empty + 8 * acc.idx);
+            acc.advance(2);
+            // merge this tile's two best into the segment's
+            if (M1 > V1) {
+                if (M2 > V1) { V2 = M2; T2 = toff; } else { V2 = V1; T2 = T1; }
+                V1 = M1; T1 = toff;
+            } else if (M1 > V2) { V2 = M1; T2 = toff; }
+            const bool seg_ends = (tile + 1 == t_end) || ((tile + 1) / n_rtiles != m) || (__ldg(tile_seg + rt + 1) != sg);
+            if (seg_ends) {
+                const size_t e = ((size_t)sg * 2 + half) * (size_t)M_pad + (size_t)(2 * m + rank) * GM_BM + row;
+                keys[e] = make_float2(V1, V2);
+                if (seg_tiles > 1) tags[e] = T1 | (T2 << 16);
+                V1 = V2 = FR_NEG; T1 = T2 = 0;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+constexpr int FR_SMEM_TOTAL = 2 * GM_CHUNK_BYTES + G2_STAGES * G2_STAGE_BYTES + 256 + 1024;
+
+// ---- refinement
+struct FrParams {
+    const float2* keys; const uint32_t* tags; const float* q32; const float* r32; const float2* qn; const int* src_idx;
+    const int* seg_tile0; GmCtrl* ctrl;
+    int4* rescan; int rescan_cap;
+    unsigned long long* best64;        // arg-min mode: (distance bits << 32 | original reference index) per (query, object)
+    float* out; float* mem; int32_t* out_idx;
+    int64_t M, M_pad; int N, C4, seg_tiles, normalize;
+};
+
+__device__ __forceinline__ unsigned long long fr_pack(float d, int idx) {
+    return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)idx;      // d >= 0: integer order == float order
+}
+
+// exact squared distance of query row `qrow` to reference rows pos, pos+1, by the 8 lanes of a quarter warp (sub = lane & 7);
+// every lane of the quarter returns both sums
+__device__ __forceinline__ void fr_pair_dist(const float* __restrict__ q32, const float* __restrict__ r32, int C4, int64_t qrow,
+                                             int64_t pos, int sub, float& d0, float& d1) {
+    const float4* q = reinterpret_cast<const float4*>(q32 + (size_t)qrow * C4);
+    const float4* ra = reinterpret_cast<const float4*>(r32 + (size_t)pos * C4);
+    const float4* rb = reinterpret_cast<const float4*>(r32 + (size_t)(pos + 1) * C4);
+    float s0 = 0.f, s1 = 0.f;
+    for (int c = sub; c < (C4 >> 2); c += 8) {
+        const float4 x = __ldg(q + c), a = __ldg(ra + c), b = __ldg(rb + c);
+        float t;
+        t = x.x - a.x; s0 = fmaf(t, t, s0); t = x.y - a.y; s0 = fmaf(t, t, s0); t = x.z - a.z; s0 = fmaf(t, t, s0); t = x.w - a.w; s0 = fmaf(t, t, s0);
+        t = x.x - b.x; s1 = fmaf(t, t, s1); t = x.y - b.y; s1 = fmaf(t, t, s1); t = x.z - b.z; s1 = fmaf(t, t, s1); t = x.w - b.w; s1 = fmaf(t, t, s1);
+    }
+#pragma unroll
+    for (int sft = 1; sft < 8; sft <<= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, sft); s1 += __shfl_xor_sync(0xffffffffu, s1, sft); }
+    d0 = s0; d1 = s1;
+}
+
+// exact minimum over the real rows of one segment-half for one query row, by a whole warp: lane l takes rows l, l+32, ...
+// of each 128-row half tile.  Returns the packed (distance, original index) minimum in every lane.
+__device__ __forceinline__ unsigned long long fr_warp_rescan(const FrParams& P, int64_t qrow, int obj, int entry, int lane) {
+    const int sg = entry >> 1, half = entry & 1;
+    const int t0 = __ldg(P.seg_tile0 + sg), t1 = min(__ldg(P.seg_tile0 + sg + 1), t0 + P.seg_tiles);
+    const int64_t end = (int64_t)P.ctrl->offsets[obj] + P.ctrl->counts[obj];
+    const float4* q = reinterpret_cast<const float4*>(P.q32 + (size_t)qrow * P.C4);
+    unsigned long long best = fr_pack(INFINITY, 0x7fffffff);
+    for (int rt = t0; rt < t1; ++rt) {
+        for (int j = lane; j < GM_BN / 2; j += 32) {
+            const int64_t pos = (int64_t)rt * GM_BN + half * (GM_BN / 2) + j;
+            if (pos >= end) continue;
+            const float4* r = reinterpret_cast<const float4*>(P.r32 + (size_t)pos * P.C4);
+            // same summation order as fr_pair_dist (eight interleaved partial sums, pairwise tree): a pair's distance has ONE
+            // value whichever path evaluates it, so results do not depend on the order of the reference pixels
+            float p[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int c0 = 0; c0 < (P.C4 >> 2); c0 += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (c0 + u < (P.C4 >> 2)) {
+                        const float4 x = __ldg(q + c0 + u), a = __ldg(r + c0 + u);
+                        float t;
+                        t = x.x - a.x; p[u] = fmaf(t, t, p[u]); t = x.y - a.y; p[u] = fmaf(t, t, p[u]);
+                        t = x.z - a.z; p[u] = fmaf(t, t, p[u]); t = x.w - a.w; p[u] = fmaf(t, t, p[u]);
+                    }
+                }
+            }
+            const float s = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+            const unsigned long long v = fr_pack(s, __ldg(P.src_idx + pos));
+            best = v < best ? v : best;
+        }
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, sft); best = o < best ? o : best; }
+    return best;
+}
+
+// write one (query, object) result: raw distance, or normalised (+ running min with the global-map memory slot)
+__device__ __forceinline__ void fr_store(const FrParams& P, int64_t i, unsigned long long v) {
+    if (P.best64 != nullptr) { P.best64[i] = v; return; }
+    float d = __uint_as_float((unsigned)(v >> 32));
+    if (P.normalize) d = sigmoid_norm(d);
+    if (P.mem != nullptr) { const float old = P.mem[i]; d = (d <= old) ? d : old; P.mem[i] = d; }
+    P.out[i] = d;
+}
+// fold a later (rescan) result into what fr_store wrote; values are >= 0, so integer order is float order
+__device__ __forceinline__ void fr_merge(const FrParams& P, int64_t i, unsigned long long v) {
+    if (P.best64 != nullptr) { atomicMin(P.best64 + i, v); return; }
+    float d = __uint_as_float((unsigned)(v >> 32));
+    if (P.normalize) d = sigmoid_norm(d);
+    atomicMin(reinterpret_cast<int*>(P.out + i), __float_as_int(d));
+    if (P.mem != nullptr) atomicMin(reinterpret_cast<int*>(P.mem + i), __float_as_int(d));
+}
+
+// one warp = 32 consecutive query rows x one object
+__global__ void __launch_bounds__(256)
+gm_refine_kernel(const FrParams P) {
+    pdl_enter();
+    const int lane = threadIdx.x & 31;
+    const int64_t row0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;
+    const int obj = blockIdx.y;
+    if (row0 >= P.M) return;
+    const int64_t row = row0 + lane;
+    const bool valid = row < P.M;
+    const int count = P.ctrl->counts[obj];
+    if (count == 0) {                                                   // absent object: the reference's 1e20 padding survives the min
+        if (valid) fr_store(P, row * P.N + obj, fr_pack(kWrongLabelPad, 0x7fffffff));
+        return;
+    }
+    const int e0 = 2 * P.ctrl->seg_first[obj], e1 = 2 * P.ctrl->seg_first[obj + 1];
+    const int64_t end = (int64_t)P.ctrl->offsets[obj] + count;
+    // Delta = 2E (see the header of this section), in the units of the accumulator
+    float delta = 0.f;
+    if (valid) {
+        const float2 n = P.qn[row];
+        const float Bh = __uint_as_float(P.ctrl->rh_max_bits[obj]), Bl = __uint_as_float(P.ctrl->rl_max_bits[obj]);
+        const float bias = __uint_as_float(P.ctrl->bias_max_bits[obj]);
+        delta = 2.0f * (n.y * Bh + n.x * Bl + n.y * Bl) + 6.2e-5f * (n.x * Bh + bias);      // 6.2e-5 ~ 2^-14: accumulator + index bits, both sides
+        delta = delta * 1.0001f + 1e-30f;
+    }
+    const size_t rq = valid ? (size_t)row : (size_t)row0;               // rows beyond M read row0's keys (results discarded)
+    float V = FR_NEG;
+    for (int e = e0; e < e1; ++e) V = fmaxf(V, P.keys[(size_t)e * P.M_pad + rq].x);
+    const float thr = V - delta;
+    // candidates: up to two per lane are evaluated here, everything else goes to the rescan list
+    int cand0 = 0, cand1 = 0, ncand = 0;
+    unsigned long long best = fr_pack(INFINITY, 0x7fffffff);
+    for (int e = e0; e < e1; ++e) {
+        const float2 k = P.keys[(size_t)e * P.M_pad + rq];
+        const bool c1 = valid && k.x >= thr, c2 = valid && k.y >= thr;
+        bool need = c1 && (c2 || ncand == 2);
+        if (c1 && !need) {
+            uint32_t toff = 0;
+            if (P.seg_tiles > 1) toff = P.tags[(size_t)e * P.M_pad + rq] & 0xffffu;
+            const int cd = (e << 22) | ((int)toff << 6) | (int)(__float_as_uint(k.x) & 63u);     // e < 2^10: FR_MAX_SEGS
+            if (ncand == 0) cand0 = cd; else cand1 = cd;
+            ++ncand;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, need);
+        if (mask) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&P.ctrl->rescan_count, __popc(mask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int slot = base + __popc(mask & ((1u << lane) - 1u));
+            if (need && slot < P.rescan_cap) { P.rescan[slot] = make_int4((int)(row & 0x7fffffff), obj, e, (int)(row >> 31)); need = false; }
+            // list full (pathological near-tie counts): rescan right here, one lane's segment-half at a time
+            unsigned over = __ballot_sync(0xffffffffu, need);
+            while (over) {
+                const int src = __ffs(over) - 1;
+                const unsigned long long v = fr_warp_rescan(P, row0 + src, obj, e, lane);
+                if (lane == src) best = v < best ? v : best;
+                over &= over - 1;
+            }
+        }
+    }
+    // evaluate: in round r the quarter warp k handles lane 4r + k's candidate
+#pragma unroll 1
+    for (int ci = 0; ci < 2; ++ci) {
+        if (!__ballot_sync(0xffffffffu, ncand > ci)) break;
+#pragma unroll 1
+        for (int r = 0; r < 8; ++r) {
+            const int src = 4 * r + (lane >> 3);
+            const int has = __shfl_sync(0xffffffffu, ncand, src) > ci;
+            const int cd = __shfl_sync(0xffffffffu, ci == 0 ? cand0 : cand1, src);
+            float d0 = INFINITY, d1 = INFINITY; int64_t pos = 0;
+            if (has) {
+                const int e = (int)((unsigned)cd >> 22), toff = (cd >> 6) & 0xffff, g = cd & 63;
+                pos = ((int64_t)__ldg(P.seg_tile0 + (e >> 1)) + toff) * GM_BN + (e & 1) * (GM_BN / 2) + 2 * g;
+                fr_pair_dist(P.q32, P.r32, P.C4, row0 + src, min(pos, end - 1), lane & 7, d0, d1);   // clamp: pos < end always holds for a
+                if (pos >= end) d0 = INFINITY;                                                       // real candidate; padding pairs are cut here
+                if (pos + 1 >= end) d1 = INFINITY;
+            }
+            // hand the result to its owner: lane L was served in round L >> 2 by quarter L & 3
+            const int from = 8 * (lane & 3);
+            const float r0 = __shfl_sync(0xffffffffu, d0, from), r1 = __shfl_sync(0xffffffffu, d1, from);
+            const long long rp = __shfl_sync(0xffffffffu, (long long)pos, from);
+            if ((lane >> 2) == r && ncand > ci) {
+                if (r0 < INFINITY) { const unsigned long long v = fr_pack(r0, __ldg(P.src_idx + rp)); best = v < best ? v : best; }
+                if (r1 < INFINITY) { const unsigned long long v = fr_pack(r1, __ldg(P.src_idx + rp + 1)); best = v < best ? v : best; }
+            }
+        }
+    }
+    if (valid) fr_store(P, row * P.N + obj, best);
+}
+
+// the rescan work list (normally empty): one warp per entry
+__global__ void __launch_bounds__(256)
+gm_rescan_kernel(const FrParams P) {
+    pdl_enter();
+    const int lane = threadIdx.x & 31;
+    const int n = min(P.ctrl->rescan_count, P.rescan_cap);
+    const int nwarps = gridDim.x * 8;
+    for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += nwarps) {
+        const int4 it = P.rescan[i];
+        const int64_t row = (int64_t)(unsigned)it.x | ((int64_t)it.w << 31);
+        const unsigned long long v = fr_warp_rescan(P, row, it.y, it.z, lane);
+        if (lane == 0) fr_merge(P, row * P.N + it.y, v);
+    }
+}
+
+// arg-min mode: unpack (distance, index) pairs
+__global__ void gm_unpack_kernel(const unsigned long long* __restrict__ best64, const GmCtrl* __restrict__ ctrl, int64_t M, int N,
+                                 float* __restrict__ out, int32_t* __restrict__ out_idx) {
+    pdl_enter();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * N) return;
+    const unsigned long long v = best64[i];
+    const bool absent = ctrl->counts[i % N] == 0;
+    out[i] = __uint_as_float((unsigned)(v >> 32));
+    if (out_idx != nullptr) out_idx[i] = absent ? -1 : (int)(v & 0xffffffffu);
+}
+
 // ------------------------------------------------------------------------------------ host side
 struct GmPlan {
     int64_t M_pad, R_pad_max; int n_mtiles, max_rtiles;
     size_t off_ctrl, off_tile_obj, off_xs, off_ysn, off_best, off_A, off_B, total;
+    // filter-and-refine engine (fr == false: shape not served by it, the three-product engine runs)
+    bool fr; int seg_tiles, max_segs, C4, rescan_cap;
+    size_t off_tile_seg, off_seg_tile0, off_qn, off_q32, off_r32, off_src, off_keys, off_tags, off_rescan, off_best64;
 };
 
-static GmPlan gm_plan(int64_t M, int64_t R, int N) {
+// test / A-B knobs (manet_set_option): force at least this many tiles per segment, shrink the rescan list
+static int g_opt_seg_tiles = 0, g_opt_rescan_cap = 0;
+int gm_set_option(const char* name, int value) {
+    int* slot = !strcmp(name, "gm_fr_seg_tiles") ? &g_opt_seg_tiles : !strcmp(name, "gm_fr_rescan_cap") ? &g_opt_rescan_cap : nullptr;
+    if (!slot) return -1;
+    const int old = *slot; *slot = value; return old;
+}
+
+constexpr size_t FR_KEYS_BYTES_CAP = (size_t)256 << 20;      // candidate keys: 8 bytes per (query row, segment half)
+constexpr int FR_MAX_SEGS = 500;                             // the refinement packs an entry index into 10 bits
+constexpr int FR_RESCAN_CAP = 1 << 20;
+
+static GmPlan gm_plan(int64_t M, int64_t R, int N, int C) {
     GmPlan p;
     p.M_pad = ceil_div64(M > 0 ? M : 1, 2 * GM_BM) * (2 * GM_BM);   // CTA pairs own 256 query rows
     p.n_mtiles = (int)(p.M_pad / GM_BM);
@@ -974,21 +1502,51 @@ static GmPlan gm_plan(int64_t M, int64_t R, int N) {
     p.off_best = o; o = align_up(o + (size_t)p.M_pad * N * sizeof(int), 1024);
     p.off_A = o; o = align_up(o + (size_t)p.n_mtiles * GM_UNIT_BYTES, 1024);
     p.off_B = o; o = align_up(o + (size_t)(p.R_pad_max / GM_UNIT_ROWS) * GM_UNIT_BYTES, 1024);
+    // segments: as fine as the key-array budget and the 10-bit entry index allow (seg_tiles = 1 at 480p)
+    const int64_t segs_by_mem = (int64_t)(FR_KEYS_BYTES_CAP / ((size_t)p.M_pad * 2 * sizeof(float2)));
+    const int64_t seg_budget = (segs_by_mem < FR_MAX_SEGS ? segs_by_mem : FR_MAX_SEGS) - N;
+    p.fr = seg_budget >= 1 && p.max_rtiles < 65536 * 4;
+    p.seg_tiles = 1; p.max_segs = 0; p.C4 = (C + 3) & ~3; p.rescan_cap = FR_RESCAN_CAP;
+    p.off_tile_seg = p.off_seg_tile0 = p.off_qn = p.off_q32 = p.off_r32 = p.off_src = p.off_keys = p.off_tags = p.off_rescan = p.off_best64 = 0;
+    if (p.fr) {
+        p.seg_tiles = (int)ceil_div64(p.max_rtiles, seg_budget);
+        if (g_opt_seg_tiles > p.seg_tiles) p.seg_tiles = g_opt_seg_tiles;
+        if (g_opt_rescan_cap > 0) p.rescan_cap = g_opt_rescan_cap;
+        if (p.seg_tiles > 65535) p.fr = false;
+    }
+    if (p.fr) {
+        p.max_segs = (int)ceil_div64(p.max_rtiles, p.seg_tiles) + N;
+        p.off_tile_seg = o; o = align_up(o + (size_t)(p.max_rtiles + 1) * sizeof(int), 1024);
+        p.off_seg_tile0 = o; o = align_up(o + (size_t)(p.max_segs + 1) * sizeof(int), 1024);
+        p.off_qn = o; o = align_up(o + (size_t)p.M_pad * sizeof(float2), 1024);
+        p.off_q32 = o; o = align_up(o + (size_t)p.M_pad * p.C4 * sizeof(float), 1024);
+        p.off_r32 = o; o = align_up(o + (size_t)(p.R_pad_max + 1) * p.C4 * sizeof(float), 1024);
+        p.off_src = o; o = align_up(o + (size_t)(p.R_pad_max + 1) * sizeof(int), 1024);
+        p.off_keys = o; o = align_up(o + (size_t)p.max_segs * 2 * p.M_pad * sizeof(float2), 1024);
+        p.off_tags = o; if (p.seg_tiles > 1) o = align_up(o + (size_t)p.max_segs * 2 * p.M_pad * sizeof(uint32_t), 1024);
+        p.off_rescan = o; o = align_up(o + (size_t)p.rescan_cap * sizeof(int4), 1024);
+        p.off_best64 = o; o = align_up(o + (size_t)(M > 0 ? M : 1) * N * sizeof(unsigned long long), 1024);
+    }
     p.total = o + 1024;     // slack so the base can be aligned to 1024 bytes
     return p;
 }
 
 bool gm_umma_supported(int C, int N, int k) { return k == 1 && C >= 1 && C <= GM_MAXC && N >= 1 && N <= GM_MAXN; }
 
-size_t gm_umma_workspace_bytes(int64_t M, int64_t R, int N) { return gm_plan(M, R, N).total; }
+size_t gm_umma_workspace_bytes(int64_t M, int64_t R, int N, int C) { return gm_plan(M, R, N, C).total; }
 
+// engine: 0 = filter-and-refine (default where the plan allows it), 1 = three-product (every pair at fp32 grade).
+// out_idx != nullptr: arg-min mode (raw distances + original index of the nearest reference pixel; filter-and-refine only).
 int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t R, const int32_t* labels,
                              const float* query, int64_t qps, int64_t qcs, int64_t M, int C, int N,
-                             int normalize, float* mem_frame, float* out, void* ws, size_t ws_bytes,
+                             int normalize, float* mem_frame, float* out, int32_t* out_idx, int engine, void* ws, size_t ws_bytes,
                              cudaStream_t stream) {
-    GmPlan p = gm_plan(M, R, N);
+    GmPlan p = gm_plan(M, R, N, C);
     if (ws_bytes < p.total) { set_error("global match: workspace too small (%zu < %zu)", ws_bytes, p.total); return MANET_E_WORKSPACE; }
     if (M <= 0) return 0;
+    static const int forced = [] { const char* e1 = getenv("MANET_GM_ENGINE"); return (e1 && (e1[0] == '3' || e1[0] == 'e')) ? 1 : 0; }();
+    const bool use_fr = p.fr && engine == 0 && !forced;
+    if (out_idx != nullptr && !use_fr) return fail_invalid("global match (arg-min): shape not served by the filter-and-refine engine");
     uint8_t* wbase = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(ws), 1024));
     GmCtrl* ctrl = reinterpret_cast<GmCtrl*>(wbase + p.off_ctrl);
     int* tile_obj = reinterpret_cast<int*>(wbase + p.off_tile_obj);
@@ -997,15 +1555,24 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
     int* best = reinterpret_cast<int*>(wbase + p.off_best);
     uint8_t* Aimg = wbase + p.off_A;
     uint8_t* Bimg = wbase + p.off_B;
+    GmFrPre pre;
+    memset(&pre, 0, sizeof(pre));
+    if (use_fr) {
+        pre.q32 = reinterpret_cast<float*>(wbase + p.off_q32); pre.r32 = reinterpret_cast<float*>(wbase + p.off_r32);
+        pre.qn = reinterpret_cast<float2*>(wbase + p.off_qn); pre.src_idx = reinterpret_cast<int*>(wbase + p.off_src);
+        pre.tile_seg = reinterpret_cast<int*>(wbase + p.off_tile_seg); pre.seg_tile0 = reinterpret_cast<int*>(wbase + p.off_seg_tile0);
+        pre.C4 = p.C4; pre.seg_tiles = p.seg_tiles; pre.skip_lo = 1;
+    }
 
     cudaError_t e = cudaMemsetAsync(ctrl, 0, sizeof(GmCtrl), stream);
     if (e != cudaSuccess) { set_error("global match: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
     const int64_t items = R + M;
     dim3 g1((unsigned)(ceil_div64(items, 256) < 148 * 8 ? ceil_div64(items, 256) : 148 * 8), GM_SCAN_CG);
-    launch_k(gm_scan_kernel, g1, dim3(256), 0, stream, ref, rps, rcs, R, labels, query, qps, qcs, M, C, N, ctrl, best, p.M_pad * N);
+    launch_k(gm_scan_kernel, g1, dim3(256), 0, stream, ref, rps, rcs, R, labels, query, qps, qcs, M, C, N, ctrl, best,
+             use_fr ? (int64_t)0 : p.M_pad * N);
     const int nb_ref = (int)ceil_div64(R, GM_CV_PIX), nb_q = (int)ceil_div64(p.M_pad, GM_CV_PIX);
     launch_k(gm_convert_kernel, dim3(nb_ref + nb_q + N), dim3(256), 0, stream, ref, rps, rcs, R, labels, query, qps, qcs, M, p.M_pad, C, N,
-             nb_ref, nb_q, ctrl, Aimg, Bimg, xs, ysn, tile_obj);
+             nb_ref, nb_q, ctrl, Aimg, Bimg, xs, ysn, tile_obj, pre);
     // 0: single CTA, 1: multicast pair, 2: cta_group::2 pair (default); MANET_GM_VARIANT is an A/B switch for profiling
     static const int variant = [] { const char* e1 = getenv("MANET_GM_VARIANT"); return (e1 && e1[0] >= '0' && e1[0] <= '2') ? e1[0] - '0' : 2; }();
     static PerDevice attrs;
@@ -1013,10 +1580,35 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
         cudaFuncSetAttribute(gm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_TOTAL);
         cudaFuncSetAttribute(gm_umma_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_TOTAL);
         cudaFuncSetAttribute(gm_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_TOTAL);
+        cudaFuncSetAttribute(gm_fr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FR_SMEM_TOTAL);
     });
     const int sm_count = device_sm_count();
     const int ksteps = (C + 15) / 16;
     const int ksteps_lo = gm_fold_remainder(C) ? ksteps - 1 : ksteps;
+    if (use_fr) {
+        FrParams F;
+        memset(&F, 0, sizeof(F));
+        F.keys = reinterpret_cast<const float2*>(wbase + p.off_keys); F.tags = reinterpret_cast<const uint32_t*>(wbase + p.off_tags);
+        F.q32 = pre.q32; F.r32 = pre.r32; F.qn = pre.qn; F.src_idx = pre.src_idx; F.seg_tile0 = pre.seg_tile0; F.ctrl = ctrl;
+        F.rescan = reinterpret_cast<int4*>(wbase + p.off_rescan); F.rescan_cap = p.rescan_cap;
+        F.best64 = out_idx != nullptr ? reinterpret_cast<unsigned long long*>(wbase + p.off_best64) : nullptr;
+        F.out = out; F.mem = mem_frame; F.out_idx = out_idx;
+        F.M = M; F.M_pad = p.M_pad; F.N = N; F.C4 = p.C4; F.seg_tiles = p.seg_tiles; F.normalize = normalize;
+        profile_begin(PROF_GLOBAL_UMMA, stream);
+        launch_k(gm_fr_kernel, dim3(sm_count & ~1), dim3(GM_THREADS), (size_t)FR_SMEM_TOTAL, stream, (const uint8_t*)Aimg, (const uint8_t*)Bimg,
+                 (const float*)ysn, (const int*)pre.tile_seg, (const int*)pre.seg_tile0, (const GmCtrl*)ctrl,
+                 reinterpret_cast<float2*>(wbase + p.off_keys), reinterpret_cast<uint32_t*>(wbase + p.off_tags), p.M_pad, p.n_mtiles / 2,
+                 ksteps, p.seg_tiles);
+        profile_end(PROF_GLOBAL_UMMA, stream);
+        profile_begin(PROF_GLOBAL_REFINE, stream);
+        launch_k(gm_refine_kernel, dim3((unsigned)ceil_div64(M, 256), (unsigned)N), dim3(256), 0, stream, F);
+        launch_k(gm_rescan_kernel, dim3((unsigned)(2 * sm_count)), dim3(256), 0, stream, F);
+        profile_end(PROF_GLOBAL_REFINE, stream);
+        if (out_idx != nullptr)
+            launch_k(gm_unpack_kernel, dim3((unsigned)ceil_div64(M * N, 256)), dim3(256), 0, stream, (const unsigned long long*)F.best64,
+                     (const GmCtrl*)ctrl, M, N, out, out_idx);
+        return check_launch("global match (tcgen05 filter-and-refine) kernels");
+    }
     profile_begin(PROF_GLOBAL_UMMA, stream);
     if (variant == 1)
         count_launch(), gm_umma_mc_kernel<<<sm_count & ~1, GM_THREADS, GM_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles / 2, N, ksteps, ksteps_lo);

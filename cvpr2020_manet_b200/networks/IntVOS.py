@@ -22,6 +22,7 @@ WRONG_LABEL_PADDING_DISTANCE = 1e20   # IntVOS.py:17
 FORCE_SIMT_LOCAL_ENGINE = False       # same for local matching (exact difference form on CUDA cores)
 FORCE_TENSOR_LOCAL_ENGINE = False     # tests/benchmarks: tcgen05 local engine without the device-side numerics guard
 FORCE_SIMT_ENGINE = False             # debugging/tests: route global matching to the fp32 CUDA-core kernel
+FORCE_EXACT3_ENGINE = False           # tests / A-B: tcgen05 three-product kernel instead of the filter-and-refine engine
 
 
 # --------------------------------------------------------------------------- autograd
@@ -41,11 +42,21 @@ class _GlobalMatchK1(torch.autograd.Function):
         dev = qry.device
         out = torch.empty((m, n_obj, 1), dtype=torch.float32, device=dev)
         idx = torch.empty((m, n_obj), dtype=torch.int32, device=dev)
+        L = _lib.lib()
         with torch.cuda.device(dev):
-            check(_lib.lib().manet_global_match_argmin(
-                ref.data_ptr() if r else None, rps, rcs, r, labels_i32.data_ptr() if r else None,
-                qry.data_ptr(), qps, qcs, m, c, n_obj, out.data_ptr(), idx.data_ptr(), stream_ptr(dev)),
-                "manet_global_match_argmin")
+            if c <= 128 and n_obj <= 64 and not FORCE_SIMT_ENGINE:
+                # the tensor-core filter-and-refine engine emits the arg-min reference pixel for free: training's forward
+                # (train_stage1.py:126) costs what inference costs
+                ws = workspace(dev, L.manet_global_match_workspace_bytes(m, r, c, n_obj, 1), "global")
+                check(L.manet_global_match_argmin_ws(
+                    ref.data_ptr() if r else None, rps, rcs, r, labels_i32.data_ptr() if r else None,
+                    qry.data_ptr(), qps, qcs, m, c, n_obj, 0, out.data_ptr(), idx.data_ptr(), ws.data_ptr(), ws.numel(),
+                    stream_ptr(dev)), "manet_global_match_argmin_ws")
+            else:
+                check(L.manet_global_match_argmin(
+                    ref.data_ptr() if r else None, rps, rcs, r, labels_i32.data_ptr() if r else None,
+                    qry.data_ptr(), qps, qcs, m, c, n_obj, out.data_ptr(), idx.data_ptr(), stream_ptr(dev)),
+                    "manet_global_match_argmin")
         ctx.save_for_backward(reference_embeddings, query_embeddings, idx)
         ctx.n_obj = n_obj
         ctx.mark_non_differentiable(idx)
@@ -210,6 +221,8 @@ def _global_match_raw(ref, r, rps, rcs, labels_i32, qry, m, qps, qcs, c, n_obj, 
     L = _lib.lib()
     if FORCE_SIMT_ENGINE:
         flags |= _lib.GM_ENGINE_SIMT
+    if FORCE_EXACT3_ENGINE:
+        flags |= _lib.GM_ENGINE_EXACT3
     out = torch.empty((m, n_obj, 1), dtype=torch.float32, device=dev)
     ws_bytes = L.manet_global_match_workspace_bytes(m, r, c, n_obj, k)
     ws = workspace(dev, ws_bytes, "global")

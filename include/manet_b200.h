@@ -41,6 +41,9 @@ typedef void* manet_stream_t; /* a cudaStream_t */
 #define MANET_GM_NORMALIZE   1u /* apply (sigmoid(x)-0.5)*2 to the result (IntVOS.py:611-612) */
 #define MANET_GM_DROP_UNLAB  2u /* drop reference pixels labelled -1 first (cfg.TEST_MODE, IntVOS.py:135-136) */
 #define MANET_GM_ENGINE_SIMT 4u /* force the fp32 CUDA-core kernel instead of the tcgen05 kernel */
+#define MANET_GM_ENGINE_EXACT3 8u /* tcgen05, but the three-product kernel (every query x reference pair at fp32 grade, 19 K steps
+                                   * per tile) instead of the default filter-and-refine engine (one product filters candidates,
+                                   * the survivors are re-evaluated exactly in fp32, 7 K steps per tile); same results */
 /* local-match flag (the *_ex entry points) */
 #define MANET_LM_ENGINE_SIMT 1u /* force the fp32 CUDA-core kernels (exact difference form) instead of the tcgen05 kernel */
 #define MANET_LM_ENGINE_TENSOR 2u /* force the tcgen05 kernels without the device-side numerics guard (see manet_local_match_ex) */
@@ -187,6 +190,14 @@ int manet_global_match_argmin(const float* ref, int64_t ref_pix_stride, int64_t 
                               const int32_t* labels, const float* query, int64_t q_pix_stride,
                               int64_t q_ch_stride, int64_t M, int C, int N, float* out, int32_t* out_idx,
                               manet_stream_t stream);
+/* The same outputs from the tcgen05 filter-and-refine engine (k = 1, C <= 128, N <= 64): the forward pass of training
+ * (train_stage1.py:126) then costs what inference costs.  workspace: manet_global_match_workspace_bytes(M, R, C, N, 1).
+ * Ties in distance resolve to the lowest reference index. */
+int manet_global_match_argmin_ws(const float* ref, int64_t ref_pix_stride, int64_t ref_ch_stride, int64_t R,
+                                 const int32_t* labels, const float* query, int64_t q_pix_stride, int64_t q_ch_stride,
+                                 int64_t M, int C, int N, uint32_t flags, float* out, int32_t* out_idx,
+                                 void* workspace, size_t workspace_bytes, manet_stream_t stream);
+
 /* grad_query [M,C] = sum_o 2 g (q - r*), grad_ref [R,C] -= 2 g (q - r*) (grad_ref must be zeroed by
  * the caller; either output may be NULL). */
 int manet_global_match_backward(const float* ref, int64_t ref_pix_stride, int64_t ref_ch_stride, int64_t R,
@@ -331,6 +342,13 @@ int manet_profile_read(int slot, float* ms_out, int capacity, int* n_out);
  * (every launcher counts its own <<<>>>; cudaMemcpy/cudaMemset are not counted).  bench.py's `gpu_launches`. */
 long long manet_profile_launch_count(void);
 int manet_profile_reset_launches(void);
+
+/* Test / A-B knobs of the engines (process-wide; returns the previous value, -1 for an unknown name):
+ *   "gm_fr_seg_tiles"  : at least this many 256-reference tiles per segment in the filter-and-refine global-matching
+ *                        engine (0 = automatic: as fine as the key-array budget allows, 1 at 480p)
+ *   "gm_fr_rescan_cap" : capacity of its rescan work list (0 = default 2^20; tiny values exercise the in-place fallback)
+ * Set them before the workspace size is queried: they change the workspace layout. */
+int manet_set_option(const char* name, int value);
 
 /* Machine micro-benchmark behind DESIGN.md's TMEM read-out floor (no reference equivalent): `ctas` CTAs, `warps` (4, 8 or
  * 16) warps each draining all 512 tensor-memory columns `iters` times with tcgen05.ld only (mode 0: .32x32b.x32, mode 1:
