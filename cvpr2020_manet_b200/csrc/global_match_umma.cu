@@ -1279,7 +1279,7 @@ __device__ __forceinline__ unsigned long long fr_pack(float d, int idx) {
 // exact squared distance of query row `qrow` to reference rows pos, pos+1, by the 8 lanes of a quarter warp (sub = lane & 7);
 // every lane of the quarter returns both sums
 __device__ __forceinline__ void fr_pair_dist(const float* __restrict__ q32, const float* __restrict__ r32, int C4, int64_t qrow,
-                                             int64_t pos, int sub, float& d0, float& d1) {
+                                             int64_t pos, int sub, unsigned qmask, float& d0, float& d1) {
     const float4* q = reinterpret_cast<const float4*>(q32 + (size_t)qrow * C4);
     const float4* ra = reinterpret_cast<const float4*>(r32 + (size_t)pos * C4);
     const float4* rb = reinterpret_cast<const float4*>(r32 + (size_t)(pos + 1) * C4);
@@ -1291,7 +1291,7 @@ __device__ __forceinline__ void fr_pair_dist(const float* __restrict__ q32, cons
         t = x.x - b.x; s1 = fmaf(t, t, s1); t = x.y - b.y; s1 = fmaf(t, t, s1); t = x.z - b.z; s1 = fmaf(t, t, s1); t = x.w - b.w; s1 = fmaf(t, t, s1);
     }
 #pragma unroll
-    for (int sft = 1; sft < 8; sft <<= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, sft); s1 += __shfl_xor_sync(0xffffffffu, s1, sft); }
+    for (int sft = 1; sft < 8; sft <<= 1) { s0 += __shfl_xor_sync(qmask, s0, sft); s1 += __shfl_xor_sync(qmask, s1, sft); }
     d0 = s0; d1 = s1;
 }
 
@@ -1423,7 +1423,8 @@ gm_refine_kernel(const FrParams P) {
             if (has) {
                 const int e = (int)((unsigned)cd >> 22), toff = (cd >> 6) & 0xffff, g = cd & 63;
                 pos = ((int64_t)__ldg(P.seg_tile0 + (e >> 1)) + toff) * GM_BN + (e & 1) * (GM_BN / 2) + 2 * g;
-                fr_pair_dist(P.q32, P.r32, P.C4, row0 + src, min(pos, end - 1), lane & 7, d0, d1);   // clamp: pos < end always holds for a
+                // only the quarter warps that have a candidate get here: their shuffles name just their own 8 lanes
+                fr_pair_dist(P.q32, P.r32, P.C4, row0 + src, min(pos, end - 1), lane & 7, 0xffu << (lane & 24), d0, d1);   // clamp: pos < end holds for a
                 if (pos >= end) d0 = INFINITY;                                                       // real candidate; padding pairs are cut here
                 if (pos + 1 >= end) d1 = INFINITY;
             }
