@@ -70,6 +70,7 @@ SIGNATURES = {
     "manet_profile_read": (c_int, [_I, POINTER(c_float), _I, POINTER(c_int)]),
     "manet_profile_launch_count": (ctypes.c_longlong, []),
     "manet_profile_reset_launches": (c_int, []),
+    "manet_global_match_stats": (c_int, [_P, POINTER(c_int32), _P]),
     "manet_set_option": (c_int, [c_char_p, _I]),
     "manet_microbench_tmem_ld": (c_int, [_I, _I, _I, _I, POINTER(ctypes.c_longlong), _P]),
     "manet_session_create": (_P, [_I, _I, _I, _I, _I, _I]),

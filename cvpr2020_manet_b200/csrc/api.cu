@@ -76,6 +76,7 @@ int launch_upsample_argmax(const float*, int, int, int, int, int, int64_t*, int3
 int launch_rough_roi(const int32_t*, int, int, int, int, int32_t*, int*, cudaStream_t);
 
 int gm_set_option(const char*, int);
+int gm_read_stats(void*, int*, cudaStream_t);
 int launch_tmem_ld_bench(int, int, int, int, long long*, float*, cudaStream_t);
 
 // ---- launch counter (bench.py's gpu_launches): relaxed atomic, host threads may launch concurrently
@@ -478,6 +479,12 @@ int manet_profile_read(int slot, float* ms_out, int capacity, int* n_out) {
     }
     *n_out = n;
     return 0;
+}
+
+int manet_global_match_stats(void* workspace, int32_t* stats_host, manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(workspace && stats_host, "global match stats: null pointer");
+    return gm_read_stats(workspace, stats_host, (cudaStream_t)stream);
 }
 
 int manet_set_option(const char* name, int value) {

@@ -1049,41 +1049,67 @@ __global__ void gm_finalize_kernel(const int* __restrict__ best, const float* __
 // hide behind them, so that segment-half is re-scanned exactly (gm_rescan_kernel, a work list that is empty for all but
 // near-tied data).  The result is the true per-object minimum of the fp32 distances whatever the data; only the speed
 // depends on how many near-ties there are.
-constexpr int FR_GROUPS = GM_BN / 2 / 2;                        // pairs of columns per 128-column half tile
-constexpr uint32_t FR_KEY_MASK = 0xFFFFFFC0u;                   // ... whose index takes the low 6 mantissa bits of a key
-static_assert(FR_GROUPS == 64, "the key layout assumes 64 column pairs per half tile");
+constexpr int FR_GROUP_COLS = 4;                                // neighbouring reference columns that share one key
+constexpr int FR_GROUPS = GM_BN / 2 / FR_GROUP_COLS;            // groups per 128-column half tile
+constexpr uint32_t FR_KEY_MASK = 0xFFFFFFE0u;                   // ... whose index takes the low 5 mantissa bits of a key
+static_assert(FR_GROUPS == 32, "the key layout assumes 32 column groups per half tile");
 constexpr float FR_NEG = -3.0e38f;
 
-__device__ __forceinline__ float fr_key(float v, int g) { return __uint_as_float((__float_as_uint(v) & FR_KEY_MASK) | (uint32_t)g); }
+// (v & mask) | g in ONE LOP3: a LOP3 takes one immediate, so the group index must sit in a register.  The caller derives
+// the sixteen indices of a chunk pair from a run-time zero (a kernel argument ptxas cannot fold), once per kernel.
+__device__ __forceinline__ float fr_key(float v, uint32_t greg) {
+    uint32_t k;
+    asm("lop3.b32 %0, %1, 0xFFFFFFE0, %2, 0xEA;" : "=r"(k) : "r"(__float_as_uint(v)), "r"(greg));    // (a & b) | c
+    return __uint_as_float(k);
+}
 
-// two largest keys of this warp's 128 columns of one accumulator tile
+// Two largest keys of this warp's 128 columns of one accumulator tile.  Instruction budget (alu pipe, 2 cycles per warp
+// instruction and scheduler): per 8 columns 4 maxima + 2 keys + 5 for the top-2 update = 176 per half tile and thread,
+// 704 cycles per tile and SM -- below the 896 cycles of the tile's 7 MMAs.  The loop over the two 64-column halves is
+// NOT unrolled: fully unrolled, the two instantiations are ~50 KB of code and the eight epilogue warps thrash the
+// instruction cache.
 template <bool BIAS_IN_ACC>
-__device__ __forceinline__ void fr_half_tile_top2(uint32_t taddr, const float4* __restrict__ yv, float& M1, float& M2) {
+__device__ __forceinline__ void fr_half_tile_top2(uint32_t taddr, const float4* __restrict__ yv, const uint32_t (&gidx)[16], float& M1, float& M2) {
     uint32_t r[2][32];
-    float a1 = FR_NEG, a2 = FR_NEG, b1 = FR_NEG, b2 = FR_NEG;           // two independent chains
+    M1 = FR_NEG; M2 = FR_NEG;
     tmem_ld32(taddr, r[0]);
+#pragma unroll 1
+    for (int cp = 0; cp < 2; ++cp) {                                    // chunk pair: columns 64 cp .. 64 cp + 63
+        float a1 = FR_NEG, a2 = FR_NEG, b1 = FR_NEG, b2 = FR_NEG;       // two independent chains
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-        float4 y[8];
-        if (!BIAS_IN_ACC) {
+        for (int h = 0; h < 2; ++h) {
+            float4 y[8];
+            if (!BIAS_IN_ACC) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) y[i] = __ldg(yv + ch * 8 + i);
+                for (int i = 0; i < 8; ++i) y[i] = __ldg(yv + (2 * cp + h) * 8 + i);
+            }
+            tmem_ld_wait_dep(r[h]);
+            if (h == 0) tmem_ld32(taddr + (2 * cp + 1) * 32, r[1]);
+            else if (cp == 0) tmem_ld32(taddr + 64, r[0]);
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {                            // columns 4i .. 4i+7 of this chunk = two groups
+                float x[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x[k] = __uint_as_float(r[h][4 * i + k]);
+                if (!BIAS_IN_ACC) {
+                    x[0] += y[i].x; x[1] += y[i].y; x[2] += y[i].z; x[3] += y[i].w;
+                    x[4] += y[i + 1].x; x[5] += y[i + 1].y; x[6] += y[i + 1].z; x[7] += y[i + 1].w;
+                }
+                const float ka = fr_key(fmaxf(fmaxf(fmaxf(x[0], x[1]), x[2]), x[3]), gidx[h * 8 + i]);
+                const float kb = fr_key(fmaxf(fmaxf(fmaxf(x[4], x[5]), x[6]), x[7]), gidx[h * 8 + i + 1]);
+                const float hi = fmaxf(ka, kb), lo = fminf(ka, kb);
+                if (i & 2) { const float t = fminf(b1, hi); b2 = fmaxf(fmaxf(b2, t), lo); b1 = fmaxf(b1, hi); }
+                else       { const float t = fminf(a1, hi); a2 = fmaxf(fmaxf(a2, t), lo); a1 = fmaxf(a1, hi); }
+            }
         }
-        tmem_ld_wait_dep(r[ch & 1]);
-        if (ch + 1 < 4) tmem_ld32(taddr + (ch + 1) * 32, r[(ch + 1) & 1]);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {                                   // columns 4i .. 4i+3 = groups 2i, 2i+1 of this chunk
-            float x0 = __uint_as_float(r[ch & 1][4 * i]), x1 = __uint_as_float(r[ch & 1][4 * i + 1]);
-            float x2 = __uint_as_float(r[ch & 1][4 * i + 2]), x3 = __uint_as_float(r[ch & 1][4 * i + 3]);
-            if (!BIAS_IN_ACC) { x0 += y[i].x; x1 += y[i].y; x2 += y[i].z; x3 += y[i].w; }
-            const float ka = fr_key(fmaxf(x0, x1), ch * 16 + 2 * i), kb = fr_key(fmaxf(x2, x3), ch * 16 + 2 * i + 1);
-            const float hi = fmaxf(ka, kb), lo = fminf(ka, kb);
-            if (i & 1) { const float t = fminf(b1, hi); b2 = fmaxf(fmaxf(b2, t), lo); b1 = fmaxf(b1, hi); }
-            else       { const float t = fminf(a1, hi); a2 = fmaxf(fmaxf(a2, t), lo); a1 = fmaxf(a1, hi); }
-        }
+        // the pair's two best (4-bit group index so far) get the pair's bit and meet the running two
+        const uint32_t cbit = (uint32_t)cp << 4;
+        const float c1 = __uint_as_float(__float_as_uint(fmaxf(a1, b1)) | cbit);
+        const float c2 = __uint_as_float(__float_as_uint(fmaxf(fmaxf(fminf(a1, b1), a2), b2)) | cbit);
+        const float t = fminf(M1, c1);
+        M2 = fmaxf(fmaxf(M2, t), c2);
+        M1 = fmaxf(M1, c1);
     }
-    M1 = fmaxf(a1, b1);
-    M2 = fmaxf(fmaxf(fminf(a1, b1), a2), b2);
 }
 
 // first tile of the next segment (or of the next query tile pair) at or after linear tile index x
@@ -1099,7 +1125,8 @@ __device__ __forceinline__ long long fr_snap(long long x, long long total, int n
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
 gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg, const float* __restrict__ ysn,
              const int* __restrict__ tile_seg, const int* __restrict__ seg_tile0, const GmCtrl* __restrict__ ctrl,
-             float2* __restrict__ keys, uint32_t* __restrict__ tags, int64_t M_pad, int n_mpairs, int ksteps, int seg_tiles) {
+             float2* __restrict__ keys, uint32_t* __restrict__ tags, int64_t M_pad, int n_mpairs, int ksteps, int seg_tiles,
+             int rt_zero) {
     pdl_enter();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -1149,8 +1176,9 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
     if (warp == 0) {
         // ------------------------------------------------ producer (both CTAs: hi part of own A rows, of own half of B)
         Ring st; uint32_t ae_phase = 0; long long cur_m = -1;
-        for (long long tile = t_begin; tile < t_end; ++tile) {
-            const long long m = tile / n_rtiles; const long long rt = tile % n_rtiles;
+        long long m = n_rtiles ? t_begin / n_rtiles : 0; int rt = n_rtiles ? (int)(t_begin % n_rtiles) : 0;   // one division per kernel, not per tile
+        for (long long tile = t_begin; tile < t_end; ++tile, ++rt) {
+            if (rt == n_rtiles) { rt = 0; ++m; }
             if (m != cur_m) {
                 mbar_wait(a_empty, ae_phase ^ 1); ae_phase ^= 1;
                 if (elect_one()) {
@@ -1174,8 +1202,9 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
             constexpr uint32_t idesc = idesc_f16(2 * GM_BM, GM_BN);
             const uint64_t descA = smem_desc_sw128(sA);
             Ring st, acc; uint32_t af_phase = 0; long long cur_m = -1;
-            for (long long tile = t_begin; tile < t_end; ++tile) {
-                const long long m = tile / n_rtiles;
+            long long m = n_rtiles ? t_begin / n_rtiles : 0; int rt = n_rtiles ? (int)(t_begin % n_rtiles) : 0;
+            for (long long tile = t_begin; tile < t_end; ++tile, ++rt) {
+                if (rt == n_rtiles) { rt = 0; ++m; }
                 if (m != cur_m) { mbar_wait(a_full, af_phase); mbar_wait_cluster(peer_a_full, af_phase); af_phase ^= 1; cur_m = m; }
                 mbar_wait_cluster(tmem_empty + 8 * acc.idx, acc.phase ^ 1);
                 mbar_wait(full_b + 8 * st.idx, st.phase);
@@ -1183,7 +1212,7 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc.idx * GM_BN;
                 const uint64_t descB = smem_desc_sw128(sB + st.idx * G2_STAGE_BYTES);
-                const bool last_of_m = (tile + 1 == t_end) || ((tile + 1) / n_rtiles != m);
+                const bool last_of_m = (tile + 1 == t_end) || (rt + 1 == n_rtiles);
                 if (elect_one()) {
                     for (int k = 0; k < ksteps; ++k) {
                         const uint64_t o = (uint64_t)((k >> 2) * (GM_CHUNK_BYTES >> 4) + (k & 3) * 2);
@@ -1201,8 +1230,9 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
             // -------------------------------------------- peer: forward "landed" to the leader
             const uint32_t r_peer_full = mapa_shared(peer_full, 0), r_peer_a = mapa_shared(peer_a_full, 0);
             Ring st; uint32_t af_phase = 0; long long cur_m = -1;
-            for (long long tile = t_begin; tile < t_end; ++tile) {
-                const long long m = tile / n_rtiles;
+            long long m = n_rtiles ? t_begin / n_rtiles : 0; int rt = n_rtiles ? (int)(t_begin % n_rtiles) : 0;
+            for (long long tile = t_begin; tile < t_end; ++tile, ++rt) {
+                if (rt == n_rtiles) { rt = 0; ++m; }
                 if (m != cur_m) {
                     mbar_wait(a_full, af_phase); af_phase ^= 1;
                     if (elect_one()) mbar_arrive_remote(r_peer_a);
@@ -1222,17 +1252,25 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
         const int row = quarter * 32 + lane;
         const uint32_t r_tmem_empty = mapa_shared(tmem_empty, 0);
         Ring acc;
+        uint32_t gidx[16];                                                 // group indices 0..15 in registers (see fr_key)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) gidx[i] = (uint32_t)(rt_zero + i);
         float V1 = FR_NEG, V2 = FR_NEG; uint32_t T1 = 0, T2 = 0;           // running top-2 of the open segment, tile offsets
-        for (long long tile = t_begin; tile < t_end; ++tile) {
-            const long long m = tile / n_rtiles; const int rt = (int)(tile % n_rtiles);
-            const int sg = __ldg(tile_seg + rt);
-            const uint32_t toff = (uint32_t)(rt - __ldg(seg_tile0 + sg));
+        long long m = n_rtiles ? t_begin / n_rtiles : 0; int rt = n_rtiles ? (int)(t_begin % n_rtiles) : 0;
+        int sg = (t_begin < t_end) ? __ldg(tile_seg + rt) : 0;
+        int sg_t0 = (t_begin < t_end) ? __ldg(seg_tile0 + sg) : 0, sg_t1 = (t_begin < t_end) ? __ldg(seg_tile0 + sg + 1) : 0;
+        for (long long tile = t_begin; tile < t_end; ++tile, ++rt) {
+            if (rt == n_rtiles) { rt = 0; ++m; }
+            if (rt < sg_t0 || rt >= sg_t1) {                               // entered another segment (segments never span objects)
+                sg = __ldg(tile_seg + rt); sg_t0 = __ldg(seg_tile0 + sg); sg_t1 = __ldg(seg_tile0 + sg + 1);
+            }
+            const uint32_t toff = (uint32_t)(rt - sg_t0);
             mbar_wait(tmem_full + 8 * acc.idx, acc.phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * GM_BN + half * (GM_BN / 2);
             float M1, M2;
-            if (bias_in_acc) fr_half_tile_top2<true>(taddr, nullptr, M1, M2);
-            else fr_half_tile_top2<false>(taddr, reinterpret_cast<const float4*>(ysn + (size_t)rt * GM_BN + half * (GM_BN / 2)), M1, M2);
+            if (bias_in_acc) fr_half_tile_top2<true>(taddr, nullptr, gidx, M1, M2);
+            else fr_half_tile_top2<false>(taddr, reinterpret_cast<const float4*>(ysn + (size_t)rt * GM_BN + half * (GM_BN / 2)), gidx, M1, M2);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(r_tmem_empty + 8 * acc.idx);
@@ -1242,7 +1280,7 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
                 if (M2 > V1) { V2 = M2; T2 = toff; } else { V2 = V1; T2 = T1; }
                 V1 = M1; T1 = toff;
             } else if (M1 > V2) { V2 = M1; T2 = toff; }
-            const bool seg_ends = (tile + 1 == t_end) || ((tile + 1) / n_rtiles != m) || (__ldg(tile_seg + rt + 1) != sg);
+            const bool seg_ends = (tile + 1 == t_end) || (rt + 1 >= sg_t1) || (rt + 1 - sg_t0 >= seg_tiles);
             if (seg_ends) {
                 const size_t e = ((size_t)sg * 2 + half) * (size_t)M_pad + (size_t)(2 * m + rank) * GM_BM + row;
                 keys[e] = make_float2(V1, V2);
@@ -1276,23 +1314,33 @@ __device__ __forceinline__ unsigned long long fr_pack(float d, int idx) {
     return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)idx;      // d >= 0: integer order == float order
 }
 
-// exact squared distance of query row `qrow` to reference rows pos, pos+1, by the 8 lanes of a quarter warp (sub = lane & 7);
-// every lane of the quarter returns both sums
-__device__ __forceinline__ void fr_pair_dist(const float* __restrict__ q32, const float* __restrict__ r32, int C4, int64_t qrow,
-                                             int64_t pos, int sub, unsigned qmask, float& d0, float& d1) {
+// exact squared distances of query row `qrow` to the FR_GROUP_COLS reference rows pos .. pos+3, by the 8 lanes of a quarter
+// warp (sub = lane & 7; qmask names those lanes); every lane of the quarter returns all four sums
+__device__ __forceinline__ void fr_group_dist(const float* __restrict__ q32, const float* __restrict__ r32, int C4, int64_t qrow,
+                                              int64_t pos, int sub, unsigned qmask, float (&d)[FR_GROUP_COLS]) {
     const float4* q = reinterpret_cast<const float4*>(q32 + (size_t)qrow * C4);
-    const float4* ra = reinterpret_cast<const float4*>(r32 + (size_t)pos * C4);
-    const float4* rb = reinterpret_cast<const float4*>(r32 + (size_t)(pos + 1) * C4);
-    float s0 = 0.f, s1 = 0.f;
-    for (int c = sub; c < (C4 >> 2); c += 8) {
-        const float4 x = __ldg(q + c), a = __ldg(ra + c), b = __ldg(rb + c);
-        float t;
-        t = x.x - a.x; s0 = fmaf(t, t, s0); t = x.y - a.y; s0 = fmaf(t, t, s0); t = x.z - a.z; s0 = fmaf(t, t, s0); t = x.w - a.w; s0 = fmaf(t, t, s0);
-        t = x.x - b.x; s1 = fmaf(t, t, s1); t = x.y - b.y; s1 = fmaf(t, t, s1); t = x.z - b.z; s1 = fmaf(t, t, s1); t = x.w - b.w; s1 = fmaf(t, t, s1);
+    const float4* r = reinterpret_cast<const float4*>(r32 + (size_t)pos * C4);
+    const int nc = C4 >> 2;
+    float s[FR_GROUP_COLS] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = sub; c < nc; c += 8) {
+        const float4 x = __ldg(q + c);
+        float4 a[FR_GROUP_COLS];
+#pragma unroll
+        for (int k = 0; k < FR_GROUP_COLS; ++k) a[k] = __ldg(r + (size_t)k * nc + c);
+#pragma unroll
+        for (int k = 0; k < FR_GROUP_COLS; ++k) {
+            float t;
+            t = x.x - a[k].x; s[k] = fmaf(t, t, s[k]); t = x.y - a[k].y; s[k] = fmaf(t, t, s[k]);
+            t = x.z - a[k].z; s[k] = fmaf(t, t, s[k]); t = x.w - a[k].w; s[k] = fmaf(t, t, s[k]);
+        }
     }
 #pragma unroll
-    for (int sft = 1; sft < 8; sft <<= 1) { s0 += __shfl_xor_sync(qmask, s0, sft); s1 += __shfl_xor_sync(qmask, s1, sft); }
-    d0 = s0; d1 = s1;
+    for (int sft = 1; sft < 8; sft <<= 1) {
+#pragma unroll
+        for (int k = 0; k < FR_GROUP_COLS; ++k) s[k] += __shfl_xor_sync(qmask, s[k], sft);
+    }
+#pragma unroll
+    for (int k = 0; k < FR_GROUP_COLS; ++k) d[k] = s[k];
 }
 
 // exact minimum over the real rows of one segment-half for one query row, by a whole warp: lane l takes rows l, l+32, ...
@@ -1389,7 +1437,7 @@ gm_refine_kernel(const FrParams P) {
         if (c1 && !need) {
             uint32_t toff = 0;
             if (P.seg_tiles > 1) toff = P.tags[(size_t)e * P.M_pad + rq] & 0xffffu;
-            const int cd = (e << 22) | ((int)toff << 6) | (int)(__float_as_uint(k.x) & 63u);     // e < 2^10: FR_MAX_SEGS
+            const int cd = (e << 22) | ((int)toff << 6) | (int)(__float_as_uint(k.x) & (uint32_t)(FR_GROUPS - 1));     // e < 2^10: FR_MAX_SEGS
             if (ncand == 0) cand0 = cd; else cand1 = cd;
             ++ncand;
         }
@@ -1419,22 +1467,26 @@ gm_refine_kernel(const FrParams P) {
             const int src = 4 * r + (lane >> 3);
             const int has = __shfl_sync(0xffffffffu, ncand, src) > ci;
             const int cd = __shfl_sync(0xffffffffu, ci == 0 ? cand0 : cand1, src);
-            float d0 = INFINITY, d1 = INFINITY; int64_t pos = 0;
+            float d[FR_GROUP_COLS] = {INFINITY, INFINITY, INFINITY, INFINITY}; int64_t pos = 0;
             if (has) {
-                const int e = (int)((unsigned)cd >> 22), toff = (cd >> 6) & 0xffff, g = cd & 63;
-                pos = ((int64_t)__ldg(P.seg_tile0 + (e >> 1)) + toff) * GM_BN + (e & 1) * (GM_BN / 2) + 2 * g;
-                // only the quarter warps that have a candidate get here: their shuffles name just their own 8 lanes
-                fr_pair_dist(P.q32, P.r32, P.C4, row0 + src, min(pos, end - 1), lane & 7, 0xffu << (lane & 24), d0, d1);   // clamp: pos < end holds for a
-                if (pos >= end) d0 = INFINITY;                                                       // real candidate; padding pairs are cut here
-                if (pos + 1 >= end) d1 = INFINITY;
+                const int e = (int)((unsigned)cd >> 22), toff = (cd >> 6) & 0xffff, g = cd & (FR_GROUPS - 1);
+                pos = ((int64_t)__ldg(P.seg_tile0 + (e >> 1)) + toff) * GM_BN + (e & 1) * (GM_BN / 2) + FR_GROUP_COLS * g;
+                // only the quarter warps that have a candidate get here: their shuffles name just their own 8 lanes.  Rows beyond
+                // the object's last one (bucket padding, r32 holds nothing there) are read but cut below; r32 has slack rows.
+                fr_group_dist(P.q32, P.r32, P.C4, row0 + src, pos, lane & 7, 0xffu << (lane & 24), d);
+#pragma unroll
+                for (int k = 0; k < FR_GROUP_COLS; ++k) if (pos + k >= end) d[k] = INFINITY;
             }
             // hand the result to its owner: lane L was served in round L >> 2 by quarter L & 3
             const int from = 8 * (lane & 3);
-            const float r0 = __shfl_sync(0xffffffffu, d0, from), r1 = __shfl_sync(0xffffffffu, d1, from);
             const long long rp = __shfl_sync(0xffffffffu, (long long)pos, from);
-            if ((lane >> 2) == r && ncand > ci) {
-                if (r0 < INFINITY) { const unsigned long long v = fr_pack(r0, __ldg(P.src_idx + rp)); best = v < best ? v : best; }
-                if (r1 < INFINITY) { const unsigned long long v = fr_pack(r1, __ldg(P.src_idx + rp + 1)); best = v < best ? v : best; }
+#pragma unroll
+            for (int k = 0; k < FR_GROUP_COLS; ++k) {
+                const float rk = __shfl_sync(0xffffffffu, d[k], from);
+                if ((lane >> 2) == r && ncand > ci && rk < INFINITY) {
+                    const unsigned long long v = fr_pack(rk, __ldg(P.src_idx + rp + k));
+                    best = v < best ? v : best;
+                }
             }
         }
     }
@@ -1521,8 +1573,8 @@ static GmPlan gm_plan(int64_t M, int64_t R, int N, int C) {
         p.off_seg_tile0 = o; o = align_up(o + (size_t)(p.max_segs + 1) * sizeof(int), 1024);
         p.off_qn = o; o = align_up(o + (size_t)p.M_pad * sizeof(float2), 1024);
         p.off_q32 = o; o = align_up(o + (size_t)p.M_pad * p.C4 * sizeof(float), 1024);
-        p.off_r32 = o; o = align_up(o + (size_t)(p.R_pad_max + 1) * p.C4 * sizeof(float), 1024);
-        p.off_src = o; o = align_up(o + (size_t)(p.R_pad_max + 1) * sizeof(int), 1024);
+        p.off_r32 = o; o = align_up(o + (size_t)(p.R_pad_max + FR_GROUP_COLS) * p.C4 * sizeof(float), 1024);
+        p.off_src = o; o = align_up(o + (size_t)(p.R_pad_max + FR_GROUP_COLS) * sizeof(int), 1024);
         p.off_keys = o; o = align_up(o + (size_t)p.max_segs * 2 * p.M_pad * sizeof(float2), 1024);
         p.off_tags = o; if (p.seg_tiles > 1) o = align_up(o + (size_t)p.max_segs * 2 * p.M_pad * sizeof(uint32_t), 1024);
         p.off_rescan = o; o = align_up(o + (size_t)p.rescan_cap * sizeof(int4), 1024);
@@ -1530,6 +1582,19 @@ static GmPlan gm_plan(int64_t M, int64_t R, int N, int C) {
     }
     p.total = o + 1024;     // slack so the base can be aligned to 1024 bytes
     return p;
+}
+
+// {reference tiles, segments, rescan-list entries, bias folded into the GEMM} of the last call on this workspace
+int gm_read_stats(void* ws, int* host4, cudaStream_t stream) {
+    const uint8_t* wbase = reinterpret_cast<const uint8_t*>(align_up(reinterpret_cast<size_t>(ws), 1024));
+    const GmCtrl* ctrl = reinterpret_cast<const GmCtrl*>(wbase);
+    cudaError_t e = cudaMemcpyAsync(&host4[0], &ctrl->n_rtiles, sizeof(int), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&host4[1], &ctrl->n_segs, sizeof(int), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&host4[2], &ctrl->rescan_count, sizeof(int), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&host4[3], &ctrl->bias_fold, sizeof(int), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { set_error("global match stats: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
 }
 
 bool gm_umma_supported(int C, int N, int k) { return k == 1 && C >= 1 && C <= GM_MAXC && N >= 1 && N <= GM_MAXN; }
@@ -1599,7 +1664,7 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
         launch_k(gm_fr_kernel, dim3(sm_count & ~1), dim3(GM_THREADS), (size_t)FR_SMEM_TOTAL, stream, (const uint8_t*)Aimg, (const uint8_t*)Bimg,
                  (const float*)ysn, (const int*)pre.tile_seg, (const int*)pre.seg_tile0, (const GmCtrl*)ctrl,
                  reinterpret_cast<float2*>(wbase + p.off_keys), reinterpret_cast<uint32_t*>(wbase + p.off_tags), p.M_pad, p.n_mtiles / 2,
-                 ksteps, p.seg_tiles);
+                 ksteps, p.seg_tiles, 0);
         profile_end(PROF_GLOBAL_UMMA, stream);
         profile_begin(PROF_GLOBAL_REFINE, stream);
         launch_k(gm_refine_kernel, dim3((unsigned)ceil_div64(M, 256), (unsigned)N), dim3(256), 0, stream, F);

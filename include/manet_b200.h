@@ -343,6 +343,11 @@ int manet_profile_read(int slot, float* ms_out, int capacity, int* n_out);
 long long manet_profile_launch_count(void);
 int manet_profile_reset_launches(void);
 
+/* Diagnostics of the last tcgen05 manet_global_match / _argmin_ws call on `workspace`: stats_host[4] = {256-reference
+ * tiles, segments, entries the filter-and-refine engine pushed to its rescan work list (near-tied candidates; 0 for
+ * well-separated data), 1 if the |r|^2 bias travelled through the GEMM}.  Synchronises `stream`. */
+int manet_global_match_stats(void* workspace, int32_t* stats_host, manet_stream_t stream);
+
 /* Test / A-B knobs of the engines (process-wide; returns the previous value, -1 for an unknown name):
  *   "gm_fr_seg_tiles"  : at least this many 256-reference tiles per segment in the filter-and-refine global-matching
  *                        engine (0 = automatic: as fine as the key-array budget allows, 1 at 480p)
