@@ -1273,7 +1273,7 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
             else fr_half_tile_top2<false>(taddr, reinterpret_cast<const float4*>(ysn + (size_t)rt * GM_BN + half * (GM_BN / 2)), gidx, M1, M2);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_remote(r_tmem_empty + 8 * acc.idx);
+            if (lane == 0) mbar_arrive_remote_nofence(r_tmem_empty + 8 * acc.idx);
             acc.advance(2);
             // merge this tile's two best into the segment's
             if (M1 > V1) {
@@ -1322,16 +1322,28 @@ __device__ __forceinline__ void fr_group_dist(const float* __restrict__ q32, con
     const float4* r = reinterpret_cast<const float4*>(r32 + (size_t)pos * C4);
     const int nc = C4 >> 2;
     float s[FR_GROUP_COLS] = {0.f, 0.f, 0.f, 0.f};
-    for (int c = sub; c < nc; c += 8) {
-        const float4 x = __ldg(q + c);
-        float4 a[FR_GROUP_COLS];
+    // the kernel is a chain of dependent L2 round trips: all ten loads of two chunk iterations go out before the arithmetic
+    // (chunks sub, sub+8 | sub+16, sub+24: the summation order is what fr_warp_rescan reproduces)
+    for (int c = sub; c < nc; c += 16) {
+        const bool two = c + 8 < nc;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 x0 = __ldg(q + c), x1 = two ? __ldg(q + c + 8) : z;
+        float4 a0[FR_GROUP_COLS], a1[FR_GROUP_COLS];
 #pragma unroll
-        for (int k = 0; k < FR_GROUP_COLS; ++k) a[k] = __ldg(r + (size_t)k * nc + c);
+        for (int k = 0; k < FR_GROUP_COLS; ++k) { a0[k] = __ldg(r + (size_t)k * nc + c); a1[k] = two ? __ldg(r + (size_t)k * nc + c + 8) : z; }
 #pragma unroll
         for (int k = 0; k < FR_GROUP_COLS; ++k) {
             float t;
-            t = x.x - a[k].x; s[k] = fmaf(t, t, s[k]); t = x.y - a[k].y; s[k] = fmaf(t, t, s[k]);
-            t = x.z - a[k].z; s[k] = fmaf(t, t, s[k]); t = x.w - a[k].w; s[k] = fmaf(t, t, s[k]);
+            t = x0.x - a0[k].x; s[k] = fmaf(t, t, s[k]); t = x0.y - a0[k].y; s[k] = fmaf(t, t, s[k]);
+            t = x0.z - a0[k].z; s[k] = fmaf(t, t, s[k]); t = x0.w - a0[k].w; s[k] = fmaf(t, t, s[k]);
+        }
+        if (two) {
+#pragma unroll
+            for (int k = 0; k < FR_GROUP_COLS; ++k) {
+                float t;
+                t = x1.x - a1[k].x; s[k] = fmaf(t, t, s[k]); t = x1.y - a1[k].y; s[k] = fmaf(t, t, s[k]);
+                t = x1.z - a1[k].z; s[k] = fmaf(t, t, s[k]); t = x1.w - a1[k].w; s[k] = fmaf(t, t, s[k]);
+            }
         }
     }
 #pragma unroll
@@ -1345,14 +1357,15 @@ __device__ __forceinline__ void fr_group_dist(const float* __restrict__ q32, con
 
 // exact minimum over the real rows of one segment-half for one query row, by a whole warp: lane l takes rows l, l+32, ...
 // of each 128-row half tile.  Returns the packed (distance, original index) minimum in every lane.
-__device__ __forceinline__ unsigned long long fr_warp_rescan(const FrParams& P, int64_t qrow, int obj, int entry, int lane) {
+__device__ __forceinline__ unsigned long long fr_warp_rescan(const FrParams& P, int64_t qrow, int obj, int entry, int lane,
+                                                             int col0 = 0, int ncol = GM_BN / 2) {
     const int sg = entry >> 1, half = entry & 1;
     const int t0 = __ldg(P.seg_tile0 + sg), t1 = min(__ldg(P.seg_tile0 + sg + 1), t0 + P.seg_tiles);
     const int64_t end = (int64_t)P.ctrl->offsets[obj] + P.ctrl->counts[obj];
     const float4* q = reinterpret_cast<const float4*>(P.q32 + (size_t)qrow * P.C4);
     unsigned long long best = fr_pack(INFINITY, 0x7fffffff);
     for (int rt = t0; rt < t1; ++rt) {
-        for (int j = lane; j < GM_BN / 2; j += 32) {
+        for (int j = col0 + lane; j < col0 + ncol; j += 32) {
             const int64_t pos = (int64_t)rt * GM_BN + half * (GM_BN / 2) + j;
             if (pos >= end) continue;
             const float4* r = reinterpret_cast<const float4*>(P.r32 + (size_t)pos * P.C4);
@@ -1424,68 +1437,105 @@ gm_refine_kernel(const FrParams P) {
         delta = delta * 1.0001f + 1e-30f;
     }
     const size_t rq = valid ? (size_t)row : (size_t)row0;               // rows beyond M read row0's keys (results discarded)
+    // Both passes over the segment halves load FR_BATCH keys at a time with independent loads: the kernel's time is the
+    // length of its chain of dependent L2 round trips, not its instruction count.
+    constexpr int FR_BATCH = 8;
     float V = FR_NEG;
-    for (int e = e0; e < e1; ++e) V = fmaxf(V, P.keys[(size_t)e * P.M_pad + rq].x);
+    for (int eb = e0; eb < e1; eb += FR_BATCH) {
+        float kx[FR_BATCH];
+#pragma unroll
+        for (int u = 0; u < FR_BATCH; ++u) kx[u] = (eb + u < e1) ? __ldg(&P.keys[(size_t)(eb + u) * P.M_pad + rq].x) : FR_NEG;
+#pragma unroll
+        for (int u = 0; u < FR_BATCH; ++u) V = fmaxf(V, kx[u]);
+    }
     const float thr = V - delta;
     // candidates: up to two per lane are evaluated here, everything else goes to the rescan list
     int cand0 = 0, cand1 = 0, ncand = 0;
     unsigned long long best = fr_pack(INFINITY, 0x7fffffff);
-    for (int e = e0; e < e1; ++e) {
-        const float2 k = P.keys[(size_t)e * P.M_pad + rq];
-        const bool c1 = valid && k.x >= thr, c2 = valid && k.y >= thr;
-        bool need = c1 && (c2 || ncand == 2);
-        if (c1 && !need) {
-            uint32_t toff = 0;
-            if (P.seg_tiles > 1) toff = P.tags[(size_t)e * P.M_pad + rq] & 0xffffu;
-            const int cd = (e << 22) | ((int)toff << 6) | (int)(__float_as_uint(k.x) & (uint32_t)(FR_GROUPS - 1));     // e < 2^10: FR_MAX_SEGS
-            if (ncand == 0) cand0 = cd; else cand1 = cd;
-            ++ncand;
+    for (int eb = e0; eb < e1; eb += FR_BATCH) {
+        float2 kk[FR_BATCH]; uint32_t tg[FR_BATCH];
+#pragma unroll
+        for (int u = 0; u < FR_BATCH; ++u) {
+            const bool in = eb + u < e1;
+            kk[u] = in ? __ldg(&P.keys[(size_t)(eb + u) * P.M_pad + rq]) : make_float2(FR_NEG, FR_NEG);
+            tg[u] = (in && P.seg_tiles > 1) ? __ldg(&P.tags[(size_t)(eb + u) * P.M_pad + rq]) : 0u;
         }
-        const unsigned mask = __ballot_sync(0xffffffffu, need);
-        if (mask) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&P.ctrl->rescan_count, __popc(mask));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            const int slot = base + __popc(mask & ((1u << lane) - 1u));
-            if (need && slot < P.rescan_cap) { P.rescan[slot] = make_int4((int)(row & 0x7fffffff), obj, e, (int)(row >> 31)); need = false; }
-            // list full (pathological near-tie counts): rescan right here, one lane's segment-half at a time
-            unsigned over = __ballot_sync(0xffffffffu, need);
-            while (over) {
-                const int src = __ffs(over) - 1;
-                const unsigned long long v = fr_warp_rescan(P, row0 + src, obj, e, lane);
-                if (lane == src) best = v < best ? v : best;
-                over &= over - 1;
+#pragma unroll
+        for (int u = 0; u < FR_BATCH; ++u) {
+            const int e = eb + u;
+            if (e >= e1) break;                                         // uniform
+            const float2 k = kk[u];
+            const bool c1 = valid && k.x >= thr, c2 = valid && k.y >= thr;
+            bool need = c1 && (c2 || ncand == 2);
+            if (c1 && !need) {
+                const int cd = (e << 22) | ((int)(tg[u] & 0xffffu) << 6) | (int)(__float_as_uint(k.x) & (uint32_t)(FR_GROUPS - 1));   // e < 2^10: FR_MAX_SEGS
+                if (ncand == 0) cand0 = cd; else cand1 = cd;
+                ++ncand;
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, need);
+            if (mask) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&P.ctrl->rescan_count, __popc(mask));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const int slot = base + __popc(mask & ((1u << lane) - 1u));
+                if (need && slot < P.rescan_cap) { P.rescan[slot] = make_int4((int)(row & 0x7fffffff), obj, e, (int)(row >> 31)); need = false; }
+                // list full (pathological near-tie counts): rescan right here, one lane's segment-half at a time
+                unsigned over = __ballot_sync(0xffffffffu, need);
+                while (over) {
+                    const int src = __ffs(over) - 1;
+                    const unsigned long long v = fr_warp_rescan(P, row0 + src, obj, e, lane);
+                    if (lane == src) best = v < best ? v : best;
+                    over &= over - 1;
+                }
             }
         }
     }
-    // evaluate: in round r the quarter warp k handles lane 4r + k's candidate
+    // Evaluate.  First candidates (every lane has one unless its best segment half went to the rescan list): round r, quarter
+    // warp k serves lane 4r + k.  Second candidates are rare: their lanes are served four at a time from a ballot.
 #pragma unroll 1
     for (int ci = 0; ci < 2; ++ci) {
-        if (!__ballot_sync(0xffffffffu, ncand > ci)) break;
+        unsigned todo = __ballot_sync(0xffffffffu, ncand > ci);
 #pragma unroll 1
-        for (int r = 0; r < 8; ++r) {
-            const int src = 4 * r + (lane >> 3);
-            const int has = __shfl_sync(0xffffffffu, ncand, src) > ci;
-            const int cd = __shfl_sync(0xffffffffu, ci == 0 ? cand0 : cand1, src);
+        for (int r = 0; todo != 0u; ++r) {
+            int src;                                                    // the lane this quarter warp serves (-1: none)
+            unsigned served;
+            if (ci == 0) { src = 4 * r + (lane >> 3); served = 0xfu << (4 * r); if (!((todo >> src) & 1u)) src = -1; }
+            else {
+                // k-th set bit of `todo` for quarter k
+                unsigned t = todo; served = 0u; src = -1;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int b = t ? __ffs(t) - 1 : -1;
+                    if (b >= 0) { served |= 1u << b; t &= t - 1; }
+                    if (q == (lane >> 3)) src = b;
+                }
+            }
+            todo &= ~served;
+            const int cd = __shfl_sync(0xffffffffu, ci == 0 ? cand0 : cand1, src < 0 ? 0 : src);
             float d[FR_GROUP_COLS] = {INFINITY, INFINITY, INFINITY, INFINITY}; int64_t pos = 0;
-            if (has) {
+            int sidx[FR_GROUP_COLS] = {0, 0, 0, 0};
+            if (src >= 0) {
                 const int e = (int)((unsigned)cd >> 22), toff = (cd >> 6) & 0xffff, g = cd & (FR_GROUPS - 1);
                 pos = ((int64_t)__ldg(P.seg_tile0 + (e >> 1)) + toff) * GM_BN + (e & 1) * (GM_BN / 2) + FR_GROUP_COLS * g;
-                // only the quarter warps that have a candidate get here: their shuffles name just their own 8 lanes.  Rows beyond
+                if ((lane & 7) < FR_GROUP_COLS) sidx[0] = __ldg(P.src_idx + pos + (lane & 7));      // goes out with the row loads
+                // only the quarter warps that serve a lane get here: their shuffles name just their own 8 lanes.  Rows beyond
                 // the object's last one (bucket padding, r32 holds nothing there) are read but cut below; r32 has slack rows.
                 fr_group_dist(P.q32, P.r32, P.C4, row0 + src, pos, lane & 7, 0xffu << (lane & 24), d);
 #pragma unroll
                 for (int k = 0; k < FR_GROUP_COLS; ++k) if (pos + k >= end) d[k] = INFINITY;
-            }
-            // hand the result to its owner: lane L was served in round L >> 2 by quarter L & 3
-            const int from = 8 * (lane & 3);
-            const long long rp = __shfl_sync(0xffffffffu, (long long)pos, from);
 #pragma unroll
-            for (int k = 0; k < FR_GROUP_COLS; ++k) {
-                const float rk = __shfl_sync(0xffffffffu, d[k], from);
-                if ((lane >> 2) == r && ncand > ci && rk < INFINITY) {
-                    const unsigned long long v = fr_pack(rk, __ldg(P.src_idx + rp + k));
-                    best = v < best ? v : best;
+                for (int k = 1; k < FR_GROUP_COLS; ++k) sidx[k] = __shfl_sync(0xffu << (lane & 24), sidx[0], (lane & 24) + k);
+                sidx[0] = __shfl_sync(0xffu << (lane & 24), sidx[0], lane & 24);
+            }
+            // hand the results to their owners: every lane asks each quarter's first lane whom it served
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int who = __shfl_sync(0xffffffffu, src, 8 * q);
+#pragma unroll
+                for (int k = 0; k < FR_GROUP_COLS; ++k) {
+                    const float rk = __shfl_sync(0xffffffffu, d[k], 8 * q);
+                    const int ik = __shfl_sync(0xffffffffu, sidx[k], 8 * q);
+                    if (who == lane && rk < INFINITY) { const unsigned long long v = fr_pack(rk, ik); best = v < best ? v : best; }
                 }
             }
         }
@@ -1493,17 +1543,17 @@ gm_refine_kernel(const FrParams P) {
     if (valid) fr_store(P, row * P.N + obj, best);
 }
 
-// the rescan work list (normally empty): one warp per entry
+// the rescan work list (normally empty): four warps per entry, a quarter of each 128-column half tile each
 __global__ void __launch_bounds__(256)
 gm_rescan_kernel(const FrParams P) {
     pdl_enter();
     const int lane = threadIdx.x & 31;
     const int n = min(P.ctrl->rescan_count, P.rescan_cap);
     const int nwarps = gridDim.x * 8;
-    for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += nwarps) {
-        const int4 it = P.rescan[i];
+    for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < 4 * n; i += nwarps) {
+        const int4 it = P.rescan[i >> 2];
         const int64_t row = (int64_t)(unsigned)it.x | ((int64_t)it.w << 31);
-        const unsigned long long v = fr_warp_rescan(P, row, it.y, it.z, lane);
+        const unsigned long long v = fr_warp_rescan(P, row, it.y, it.z, lane, (i & 3) * 32, 32);
         if (lane == 0) fr_merge(P, row * P.N + it.y, v);
     }
 }

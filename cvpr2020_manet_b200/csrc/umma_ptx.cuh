@@ -110,6 +110,14 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Remote arrive without the cluster-scope release fence (the form CUTLASS's ClusterBarrier::arrive uses: release at CTA scope).
+// For signals that publish no memory -- "I have finished READING this accumulator" after tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync -- the cluster-scope release of mbar_arrive_remote is pure cost: it compiles to
+// MEMBAR.ALL.GPU + ERRBAR and waits for every outstanding global store of the thread (ncu: 29 % of the epilogue's time
+// in gm_fr_kernel, whose epilogue stores its keys right before).
+__device__ __forceinline__ void mbar_arrive_remote_nofence(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
