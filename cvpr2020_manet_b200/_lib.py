@@ -18,11 +18,13 @@ GM_NORMALIZE = 1
 GM_DROP_UNLAB = 2
 GM_ENGINE_SIMT = 4
 GM_ENGINE_EXACT3 = 8
+GM_REUSE_REF = 128
 LM_ENGINE_SIMT = 1
 LM_ENGINE_TENSOR = 2
 STEP_SERIAL = 16
 STEP_STREAM = 32
 STEP_STREAM_RESET = 64
+STEP_NO_REF_CACHE = 256
 DT_F32, DT_F16, DT_F64 = 0, 1, 2
 
 _I64, _I, _P, _SZ, _F = c_int64, c_int, c_void_p, c_size_t, c_float

@@ -34,7 +34,7 @@ int launch_global_map_update(const float*, float*, float*, int64_t, int, cudaStr
 bool gm_umma_supported(int C, int N, int k);
 size_t gm_umma_workspace_bytes(int64_t M, int64_t R, int N, int C);
 int launch_global_match_umma(const float*, int64_t, int64_t, int64_t, const int32_t*, const float*, int64_t, int64_t, int64_t,
-                             int, int, int, float*, float*, int32_t*, int, void*, size_t, cudaStream_t);
+                             int, int, int, float*, float*, int32_t*, int, int, void*, size_t, cudaStream_t);
 size_t select_workspace_bytes(int64_t R);
 int launch_select_labelled(const int32_t*, int64_t, const float*, int64_t, int64_t, int, int32_t*, float*, int64_t*, void*,
                            size_t, cudaStream_t);
@@ -177,8 +177,8 @@ int manet_global_match(const float* ref, int64_t ref_pix_stride, int64_t ref_ch_
     const int normalize = (flags & MANET_GM_NORMALIZE) ? 1 : 0;
     if (!(flags & MANET_GM_ENGINE_SIMT) && gm_umma_supported(C, N, k))
         return launch_global_match_umma(ref, ref_pix_stride, ref_ch_stride, R, labels, query, q_pix_stride, q_ch_stride, M,
-                                        C, N, normalize, mem_frame, out, nullptr, (flags & MANET_GM_ENGINE_EXACT3) ? 1 : 0, workspace,
-                                        workspace_bytes, st);
+                                        C, N, normalize, mem_frame, out, nullptr, (flags & MANET_GM_ENGINE_EXACT3) ? 1 : 0,
+                                        (flags & MANET_GM_REUSE_REF) ? 1 : 0, workspace, workspace_bytes, st);
     // CUDA-core engine: k > 1, C > 128, N > 64, or forced.  Labels outside [0,N) (incl. -1) never
     // match, so MANET_GM_DROP_UNLAB needs no extra work here.
     if (M == 0) return 0;
@@ -300,9 +300,10 @@ int manet_global_match_argmin_ws(const float* ref, int64_t ref_pix_stride, int64
     MANET_REQUIRE(query && out && out_idx && workspace && (R == 0 || (ref && labels)), "global match (argmin): null pointer");
     MANET_REQUIRE(M >= 0 && R >= 0 && C >= 1 && N >= 1, "global match (argmin): bad sizes");
     MANET_REQUIRE(gm_umma_supported(C, N, 1), "global match (argmin, tcgen05): needs C <= 128 and N <= 64");
-    (void)flags;     // labels outside [0, N) -- including -1 -- never match: MANET_GM_DROP_UNLAB needs no extra work
+    // labels outside [0, N) -- including -1 -- never match: MANET_GM_DROP_UNLAB needs no extra work
     return launch_global_match_umma(ref, ref_pix_stride, ref_ch_stride, R, labels, query, q_pix_stride, q_ch_stride, M, C, N, 0,
-                                    nullptr, out, out_idx, 0, workspace, workspace_bytes, (cudaStream_t)stream);
+                                    nullptr, out, out_idx, 0, (flags & MANET_GM_REUSE_REF) ? 1 : 0, workspace, workspace_bytes,
+                                    (cudaStream_t)stream);
 }
 
 int manet_global_match_backward(const float* ref, int64_t ref_pix_stride, int64_t ref_ch_stride, int64_t R,
@@ -538,6 +539,9 @@ struct manet_session {
     float* d_ldist;       // [n_frames, 9]
     void *ws_g, *ws_l; size_t ws_g_bytes, ws_l_bytes;
     long long stream_count;   // MANET_STEP_STREAM: steps since the sequence started (ring of three frame buffers)
+    // reference operands cached in ws_g by the last global match (MANET_GM_REUSE_REF): valid while these device buffers have
+    // not been re-uploaded (the annotated frame and its scribble labels are constant along a propagation, test.py:237-259)
+    const float* cached_ref; const int32_t* cached_ref_lab; bool ref_cache_valid;
 };
 
 static __global__ void fill_kernel(float* p, float v, int64_t n) {
@@ -629,6 +633,7 @@ int manet_session_host_buffers(manet_session_t* s, float** ref, float** prev, fl
 
 static int session_upload_slot(manet_session_t* s, int slot, cudaStream_t st) {
     SessionSlot& t = s->slot[slot];
+    if (s->cached_ref == t.d_ref || s->cached_ref_lab == t.d_ref_lab) s->ref_cache_valid = false;     // the reference is rewritten
     const size_t px = (size_t)s->H * s->W, emb = px * s->C * sizeof(float);
     cudaMemcpyAsync(t.d_ref, t.h_ref, emb, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(t.d_cur, t.h_cur, emb, cudaMemcpyHostToDevice, st);
@@ -658,7 +663,10 @@ static int session_step_slot(manet_session_t* s, int slot, int frame, int intera
     // own stream so its small kernels can fill the machine around the (tensor-bound) global-matching GEMM.
     const bool fork = !(flags & MANET_STEP_SERIAL);
     cudaStream_t ls = fork ? s->local_stream : s->stream;
-    const uint32_t gm_flags = (flags & ~(MANET_STEP_SERIAL | MANET_STEP_STREAM | MANET_STEP_STREAM_RESET)) | MANET_GM_NORMALIZE;
+    const bool reuse = !(flags & MANET_STEP_NO_REF_CACHE) && s->ref_cache_valid && s->cached_ref == in->ref && s->cached_ref_lab == in->ref_lab;
+    const uint32_t gm_flags = (flags & ~(MANET_STEP_SERIAL | MANET_STEP_STREAM | MANET_STEP_STREAM_RESET | MANET_STEP_NO_REF_CACHE | MANET_GM_REUSE_REF)) |
+                              MANET_GM_NORMALIZE | (reuse ? MANET_GM_REUSE_REF : 0u);
+    s->cached_ref = in->ref; s->cached_ref_lab = in->ref_lab; s->ref_cache_valid = true;
     if (fork) {
         cudaEventRecord(s->ev_fork, s->stream);
         cudaStreamWaitEvent(s->local_stream, s->ev_fork, 0);
@@ -709,6 +717,7 @@ int manet_session_submit_host(manet_session_t* s, int slot, int frame, int inter
         const long long i = s->stream_count;
         const size_t px = (size_t)s->H * s->W, emb = px * s->C * sizeof(float);
         if (i == 0) {
+            s->ref_cache_valid = false;                          // a new annotated frame / scribble
             cudaMemcpyAsync(s->slot[0].d_ref, t.h_ref, emb, cudaMemcpyHostToDevice, s->copy_stream);
             cudaMemcpyAsync(s->slot[0].d_ref_lab, t.h_ref_lab, px * 4, cudaMemcpyHostToDevice, s->copy_stream);
             cudaMemcpyAsync(ring[2], t.h_prev, emb, cudaMemcpyHostToDevice, s->copy_stream);

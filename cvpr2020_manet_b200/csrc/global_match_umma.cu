@@ -48,21 +48,27 @@ constexpr int GM_SMEM_BAR = GM_SMEM_A + GM_STAGES * GM_STAGE_BYTES;
 constexpr int GM_SMEM_TOTAL = GM_SMEM_BAR + 256 + 1024;     // + barriers + alignment slack
 
 struct GmCtrl {
-    unsigned absmax_bits[2];       // |x| max as raw bits: [0] reference, [1] query
+    // ---- per call ("frame side"): what a call with MANET_GM_REUSE_REF resets and recomputes
+    unsigned absmax_q_bits;        // |x| max of the query as raw float bits
+    int rescan_count;              // entries pushed to the rescan work list
+    float scale_q;                 // power-of-two operand scale of the query
+    int bias_fold;                 // 1: -s/2*|r|^2 travels through the GEMM (gm_bias_plan), epilogue is a bare max
+    // ---- reference side: built by a full call, kept by a reusing one
+    unsigned absmax_r_bits;        // |x| max of the reference
+    float scale_r;
     int counts[GM_MAXN];           // labelled reference pixels per object
     int cursors[GM_MAXN];          // scatter cursors
     int offsets[GM_MAXN + 1];      // first row of each (256-padded) bucket
     int n_rtiles;                  // number of 256-row reference tiles
-    float scale_q, scale_r;        // power-of-two operand scales
-    int bias_fold;                 // 1: -s/2*|r|^2 travels through the GEMM (gm_bias_plan), epilogue is a bare max
-    // ---- filter-and-refine engine (gm_fr_kernel + gm_refine_kernel + gm_rescan_kernel)
+    // filter-and-refine engine (gm_fr_kernel + gm_refine_kernel + gm_rescan_kernel)
     unsigned rh_max_bits[GM_MAXN]; // per object: max over its reference rows of |hi part|_2 (scaled units), float bits
     unsigned rl_max_bits[GM_MAXN]; // ... of |lo part|_2
-    unsigned bias_max_bits[GM_MAXN]; // ... of |s/2 |r|^2|
+    unsigned rsq_max_bits[GM_MAXN]; // ... of |r|^2 (unscaled; the bias bound is s_q s_r / 2 times this)
     int seg_first[GM_MAXN + 1];    // first segment of each object (a segment = seg_tiles consecutive 256-row tiles of one object)
     int n_segs;
-    int rescan_count;              // entries pushed to the rescan work list
 };
+constexpr size_t GM_CTRL_FRAME_BYTES = 16;      // the per-call prefix of GmCtrl
+
 
 // Row-max of (accumulator + ysn) over this warp's 128 columns of one tile.  TMEM loads are software
 // pipelined (chunk c+1 is in flight while chunk c is reduced) and four independent maxima break the
@@ -204,7 +210,7 @@ gm_scan_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64_t 
     if (t < 2) {
         unsigned m = 0;
         for (int w = 0; w < 8; ++w) m = max(m, red[t][w]);
-        if (m) atomicMax(&ctrl->absmax_bits[t], m);      // non-negative floats order like unsigned ints
+        if (m) atomicMax(t == 0 ? &ctrl->absmax_r_bits : &ctrl->absmax_q_bits, m);      // non-negative floats order like unsigned ints
     }
     if (cg == 0 && t < N && hist[t]) atomicAdd(&ctrl->counts[t], hist[t]);
 }
@@ -235,7 +241,9 @@ constexpr int GM_CV_PIX = 128;
 // and the segment tables.  `seg_tiles` = tiles per segment (host-chosen so that the candidate-key array stays bounded).
 struct GmFrPre {
     float* q32; float* r32; float2* qn; int* src_idx; int* tile_seg; int* seg_tile0;
+    float* rsq;                    // |r|^2 of every bucketed reference row: lets a later call rebuild the bias for a new query scale
     int C4; int seg_tiles; int skip_lo;
+    int reuse;                     // MANET_GM_REUSE_REF: the reference side of the workspace is valid; convert the query, refresh the bias
 };
 __global__ void __launch_bounds__(256)
 gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64_t R, const int32_t* __restrict__ labels,
@@ -259,15 +267,17 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
     if (t < GM_MAXN) { bcnt[t] = 0; omax[0][t] = omax[1][t] = omax[2][t] = 0u; }
     if (t < GM_CV_PIX) { rowsq[t] = rowh[t] = rowl[t] = 0.f; pos_s[t] = -1; lab_s[t] = -1; }
     __syncthreads();
-    const float s_q = pow2_scale(ctrl->absmax_bits[1]);
-    const float s_r = pow2_scale(ctrl->absmax_bits[0]);
+    const float s_q = pow2_scale(ctrl->absmax_q_bits);
+    const float s_r = pow2_scale(ctrl->absmax_r_bits);
     const int nchunks = ((C + 15) / 16) * 2;
     const int rem = max(C % 16, 1);
     const bool fold = gm_fold_remainder(C);
     const int j_fold = nchunks - 2;                        // first 16-byte chunk of the last k-step
-    const GmBiasPlan bias = gm_bias_plan(C, s_q, s_r, ctrl->absmax_bits[0]);
+    const GmBiasPlan bias = gm_bias_plan(C, s_q, s_r, ctrl->absmax_r_bits);
     const int b = blockIdx.x;
-    if (b == 0) {
+    if (b == 0 && fr.reuse) {
+        if (t == 0) { ctrl->scale_q = s_q; ctrl->bias_fold = bias.on ? 1 : 0; }
+    } else if (b == 0) {
         if (t <= N) ctrl->offsets[t] = off[t];
         if (t == 0) { ctrl->n_rtiles = off[N] / GM_BN; ctrl->scale_q = s_q; ctrl->scale_r = s_r; ctrl->bias_fold = bias.on ? 1 : 0; }
         for (int o = 0; o < N; ++o)
@@ -285,6 +295,30 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
             }
             if (t == 0) { ctrl->seg_first[N] = s0; ctrl->n_segs = s0; fr.seg_tile0[s0] = off[N] / GM_BN; }
         }
+    }
+    if (fr.reuse && b >= nb_ref + nb_q) {
+        // Reference side reused (nb_ref == 0): the operand image, norms, tables and fp32 copy of the bucketed reference are
+        // still valid; only what depends on the QUERY's scale is refreshed -- the bias -s_q s_r/2 |r|^2 of every real row
+        // (ysn and the three fp16 pieces in the folded K step).  Bucket padding rows do not depend on it.
+        const int64_t pos = (int64_t)(b - nb_q) * GM_CV_PIX + t;
+        if (t < GM_CV_PIX && pos < off[N]) {
+            int o = 0;
+            while (o + 1 < N && pos >= off[o + 1]) ++o;
+            if (pos < (int64_t)off[o] + ctrl->counts[o]) {
+                const float bval = -0.5f * (s_q * s_r) * fr.rsq[pos];
+                ysn[pos] = bval;
+                if (bias.on) {
+                    __half v[4];
+                    const __half v1 = __float2half_rn(bval / bias.c1);
+                    const float r1 = bval - bias.c1 * __half2float(v1);
+                    const __half v2 = __float2half_rn(r1 / bias.c2);
+                    const float r2 = r1 - bias.c2 * __half2float(v2);
+                    v[0] = v1; v[1] = v2; v[2] = __float2half_rn(r2 / bias.c3); v[3] = __float2half_rn(0.f);
+                    *reinterpret_cast<uint2*>(Bimg + image_chunk_offset(pos, 0, j_fold + 1) + 8) = *reinterpret_cast<uint2*>(v);
+                }
+            }
+        }
+        return;
     }
     if (b >= nb_ref + nb_q) {
         // bucket padding rows: zero operands, -inf bias (never wins the row max)
@@ -409,6 +443,7 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
         if (is_ref) {
             const float bval = -0.5f * (s_q * s_r) * rowsq[t];
             ysn[pos] = bval;
+            if (fr.rsq != nullptr) fr.rsq[pos] = rowsq[t];
             // three-piece fp16 split of the bias against the weights c1 > c2 > c3 (each step is exact in fp32)
             const __half v1 = __float2half_rn(bval / bias.c1);
             const float r1 = bval - bias.c1 * __half2float(v1);
@@ -429,7 +464,7 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
                 const int lab = lab_s[t];
                 atomicMax(&omax[0][lab], __float_as_uint(nh));
                 atomicMax(&omax[1][lab], __float_as_uint(nl));
-                atomicMax(&omax[2][lab], __float_as_uint(0.5f * (s_q * s_r) * rowsq[t]));
+                atomicMax(&omax[2][lab], __float_as_uint(rowsq[t]));
             } else {
                 fr.qn[pos] = make_float2(nh, nl);
             }
@@ -440,7 +475,7 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
         if (t < N) {
             if (omax[0][t]) atomicMax(&ctrl->rh_max_bits[t], omax[0][t]);
             if (omax[1][t]) atomicMax(&ctrl->rl_max_bits[t], omax[1][t]);
-            if (omax[2][t]) atomicMax(&ctrl->bias_max_bits[t], omax[2][t]);
+            if (omax[2][t]) atomicMax(&ctrl->rsq_max_bits[t], omax[2][t]);
         }
     }
 }
@@ -1054,6 +1089,7 @@ constexpr int FR_GROUPS = GM_BN / 2 / FR_GROUP_COLS;            // groups per 12
 constexpr uint32_t FR_KEY_MASK = 0xFFFFFFE0u;                   // ... whose index takes the low 5 mantissa bits of a key
 static_assert(FR_GROUPS == 32, "the key layout assumes 32 column groups per half tile");
 constexpr float FR_NEG = -3.0e38f;
+constexpr int FR_ACC_BUFS = 4;                                  // accumulator buffers of GM_BN / 2 = 128 tensor-memory columns
 
 // (v & mask) | g in ONE LOP3: a LOP3 takes one immediate, so the group index must sit in a register.  The caller derives
 // the sixteen indices of a chunk pair from a run-time zero (a kernel argument ptxas cannot fold), once per kernel.
@@ -1063,53 +1099,44 @@ __device__ __forceinline__ float fr_key(float v, uint32_t greg) {
     return __uint_as_float(k);
 }
 
-// Two largest keys of this warp's 128 columns of one accumulator tile.  Instruction budget (alu pipe, 2 cycles per warp
-// instruction and scheduler): per 8 columns 4 maxima + 2 keys + 5 for the top-2 update = 176 per half tile and thread,
-// 704 cycles per tile and SM -- below the 896 cycles of the tile's 7 MMAs.  The loop over the two 64-column halves is
-// NOT unrolled: fully unrolled, the two instantiations are ~50 KB of code and the eight epilogue warps thrash the
-// instruction cache.
+// Two largest keys of one 64-column unit of an accumulator (this warp's share of a 128-column sub-tile), 4-bit group index.
+// Instruction budget (alu pipe, 2 cycles per warp instruction and scheduler): per 8 columns 4 maxima + 2 keys + 5 for the
+// top-2 update = 88 per unit and thread -- 176 per 256-column tile, 704 cycles per tile and SM, below the 896 cycles of
+// the tile's 14 half-width MMAs.
 template <bool BIAS_IN_ACC>
-__device__ __forceinline__ void fr_half_tile_top2(uint32_t taddr, const float4* __restrict__ yv, const uint32_t (&gidx)[16], float& M1, float& M2) {
+__device__ __forceinline__ void fr_unit_top2(uint32_t taddr, const float4* __restrict__ yv, const uint32_t (&gidx)[16], float& c1, float& c2) {
     uint32_t r[2][32];
-    M1 = FR_NEG; M2 = FR_NEG;
     tmem_ld32(taddr, r[0]);
-#pragma unroll 1
-    for (int cp = 0; cp < 2; ++cp) {                                    // chunk pair: columns 64 cp .. 64 cp + 63
-        float a1 = FR_NEG, a2 = FR_NEG, b1 = FR_NEG, b2 = FR_NEG;       // two independent chains
+    tmem_ld32(taddr + 32, r[1]);
+    float4 y[16];
+    if (!BIAS_IN_ACC) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float4 y[8];
-            if (!BIAS_IN_ACC) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) y[i] = __ldg(yv + (2 * cp + h) * 8 + i);
-            }
-            tmem_ld_wait_dep(r[h]);
-            if (h == 0) tmem_ld32(taddr + (2 * cp + 1) * 32, r[1]);
-            else if (cp == 0) tmem_ld32(taddr + 64, r[0]);
-#pragma unroll
-            for (int i = 0; i < 8; i += 2) {                            // columns 4i .. 4i+7 of this chunk = two groups
-                float x[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) x[k] = __uint_as_float(r[h][4 * i + k]);
-                if (!BIAS_IN_ACC) {
-                    x[0] += y[i].x; x[1] += y[i].y; x[2] += y[i].z; x[3] += y[i].w;
-                    x[4] += y[i + 1].x; x[5] += y[i + 1].y; x[6] += y[i + 1].z; x[7] += y[i + 1].w;
-                }
-                const float ka = fr_key(fmaxf(fmaxf(fmaxf(x[0], x[1]), x[2]), x[3]), gidx[h * 8 + i]);
-                const float kb = fr_key(fmaxf(fmaxf(fmaxf(x[4], x[5]), x[6]), x[7]), gidx[h * 8 + i + 1]);
-                const float hi = fmaxf(ka, kb), lo = fminf(ka, kb);
-                if (i & 2) { const float t = fminf(b1, hi); b2 = fmaxf(fmaxf(b2, t), lo); b1 = fmaxf(b1, hi); }
-                else       { const float t = fminf(a1, hi); a2 = fmaxf(fmaxf(a2, t), lo); a1 = fmaxf(a1, hi); }
-            }
-        }
-        // the pair's two best (4-bit group index so far) get the pair's bit and meet the running two
-        const uint32_t cbit = (uint32_t)cp << 4;
-        const float c1 = __uint_as_float(__float_as_uint(fmaxf(a1, b1)) | cbit);
-        const float c2 = __uint_as_float(__float_as_uint(fmaxf(fmaxf(fminf(a1, b1), a2), b2)) | cbit);
-        const float t = fminf(M1, c1);
-        M2 = fmaxf(fmaxf(M2, t), c2);
-        M1 = fmaxf(M1, c1);
+        for (int i = 0; i < 16; ++i) y[i] = __ldg(yv + i);
     }
+    tmem_ld_wait_dep(r[0]);                                             // tcgen05.wait::ld covers both loads
+    tmem_ld_wait_dep(r[1]);
+    float a1 = FR_NEG, a2 = FR_NEG, b1 = FR_NEG, b2 = FR_NEG;           // two independent chains
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {                                // columns 4i .. 4i+7 of this chunk = two groups
+            float x[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = __uint_as_float(r[h][4 * i + k]);
+            if (!BIAS_IN_ACC) {
+                const float4 y0 = y[h * 8 + i], y1 = y[h * 8 + i + 1];
+                x[0] += y0.x; x[1] += y0.y; x[2] += y0.z; x[3] += y0.w;
+                x[4] += y1.x; x[5] += y1.y; x[6] += y1.z; x[7] += y1.w;
+            }
+            const float ka = fr_key(fmaxf(fmaxf(fmaxf(x[0], x[1]), x[2]), x[3]), gidx[h * 8 + i]);
+            const float kb = fr_key(fmaxf(fmaxf(fmaxf(x[4], x[5]), x[6]), x[7]), gidx[h * 8 + i + 1]);
+            const float hi = fmaxf(ka, kb), lo = fminf(ka, kb);
+            if (i & 2) { const float t = fminf(b1, hi); b2 = fmaxf(fmaxf(b2, t), lo); b1 = fmaxf(b1, hi); }
+            else       { const float t = fminf(a1, hi); a2 = fmaxf(fmaxf(a2, t), lo); a1 = fmaxf(a1, hi); }
+        }
+    }
+    c1 = fmaxf(a1, b1);
+    c2 = fmaxf(fmaxf(fminf(a1, b1), a2), b2);
 }
 
 // first tile of the next segment (or of the next query tile pair) at or after linear tile index x
@@ -1141,9 +1168,13 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
     const uint32_t a_full = bars + 96;
     const uint32_t a_empty = bars + 104;
     const uint32_t peer_a_full = bars + 112;     // leader only
-    const uint32_t tmem_full = bars + 120;       // [2]
-    const uint32_t tmem_empty = bars + 136;      // [2]  leader only, 16 arrivals
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 2 * GM_CHUNK_BYTES + G2_STAGES * G2_STAGE_BYTES + 160);
+    // FOUR accumulator buffers of 128 columns: a 256-reference tile is issued as two half-width MMA groups, so the issuer
+    // runs up to three sub-tiles ahead of the epilogue.  With two 256-column buffers the hand-off latency (remote arrive
+    // -> issue -> commit -> wake-up, ~800 cycles) sat on the critical path of every tile (ncu: the epilogue warps spent a
+    // third of their time waiting for the accumulator).
+    const uint32_t tmem_full = bars + 120;       // [4]
+    const uint32_t tmem_empty = bars + 152;      // [4]  leader only, 16 arrivals
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 2 * GM_CHUNK_BYTES + G2_STAGES * G2_STAGE_BYTES + 192);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -1160,7 +1191,7 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
         if (lane == 0) {
             for (int i = 0; i < G2_STAGES; ++i) { mbar_init(full_b + 8 * i, 1); mbar_init(empty_b + 8 * i, 1); mbar_init(peer_full + 8 * i, 1); }
             mbar_init(a_full, 1); mbar_init(a_empty, 1); mbar_init(peer_a_full, 1);
-            for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, 2 * GM_EPI_WARPS); }
+            for (int i = 0; i < FR_ACC_BUFS; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, 2 * GM_EPI_WARPS); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -1198,33 +1229,40 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
         }
     } else if (warp == 1) {
         if (leader) {
-            // -------------------------------------------- MMA issuer: qh.rh only, `ksteps` K steps per 256 x 256 tile
-            constexpr uint32_t idesc = idesc_f16(2 * GM_BM, GM_BN);
+            // -------------------------------------------- MMA issuer: qh.rh only, `ksteps` K steps per 256 x 128 sub-tile
+            constexpr uint32_t idesc = idesc_f16(2 * GM_BM, GM_BN / 2);
             const uint64_t descA = smem_desc_sw128(sA);
             Ring st, acc; uint32_t af_phase = 0; long long cur_m = -1;
             long long m = n_rtiles ? t_begin / n_rtiles : 0; int rt = n_rtiles ? (int)(t_begin % n_rtiles) : 0;
             for (long long tile = t_begin; tile < t_end; ++tile, ++rt) {
                 if (rt == n_rtiles) { rt = 0; ++m; }
                 if (m != cur_m) { mbar_wait(a_full, af_phase); mbar_wait_cluster(peer_a_full, af_phase); af_phase ^= 1; cur_m = m; }
-                mbar_wait_cluster(tmem_empty + 8 * acc.idx, acc.phase ^ 1);
                 mbar_wait(full_b + 8 * st.idx, st.phase);
                 mbar_wait_cluster(peer_full + 8 * st.idx, st.phase);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc.idx * GM_BN;
                 const uint64_t descB = smem_desc_sw128(sB + st.idx * G2_STAGE_BYTES);
                 const bool last_of_m = (tile + 1 == t_end) || (rt + 1 == n_rtiles);
-                if (elect_one()) {
-                    for (int k = 0; k < ksteps; ++k) {
-                        const uint64_t o = (uint64_t)((k >> 2) * (GM_CHUNK_BYTES >> 4) + (k & 3) * 2);
-                        umma2_f16(d_tmem, descA + o, descB + o, idesc, k > 0);
+#pragma unroll 1
+                for (int sub = 0; sub < 2; ++sub) {
+                    // sub-tile `sub`: rows [64 sub, 64 sub + 64) of each CTA's half of the B tile (8 KB into every 16 KB k-block)
+                    mbar_wait_cluster(tmem_empty + 8 * acc.idx, acc.phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc.idx * (GM_BN / 2);
+                    const uint64_t dB = descB + (uint64_t)(sub * ((GM_CHUNK_BYTES / 2) >> 4));
+                    if (elect_one()) {
+                        for (int k = 0; k < ksteps; ++k) {
+                            const uint64_t o = (uint64_t)((k >> 2) * (GM_CHUNK_BYTES >> 4) + (k & 3) * 2);
+                            umma2_f16(d_tmem, descA + o, dB + o, idesc, k > 0);
+                        }
+                        tc_commit2(tmem_full + 8 * acc.idx);
+                        if (sub == 1) {
+                            tc_commit2(empty_b + 8 * st.idx);
+                            if (last_of_m) tc_commit2(a_empty);
+                        }
                     }
-                    tc_commit2(empty_b + 8 * st.idx);
-                    tc_commit2(tmem_full + 8 * acc.idx);
-                    if (last_of_m) tc_commit2(a_empty);
+                    __syncwarp();
+                    acc.advance(FR_ACC_BUFS);
                 }
-                __syncwarp();
                 st.advance(G2_STAGES);
-                acc.advance(2);
             }
         } else {
             // -------------------------------------------- peer: forward "landed" to the leader
@@ -1265,16 +1303,27 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
                 sg = __ldg(tile_seg + rt); sg_t0 = __ldg(seg_tile0 + sg); sg_t1 = __ldg(seg_tile0 + sg + 1);
             }
             const uint32_t toff = (uint32_t)(rt - sg_t0);
-            mbar_wait(tmem_full + 8 * acc.idx, acc.phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * GM_BN + half * (GM_BN / 2);
-            float M1, M2;
-            if (bias_in_acc) fr_half_tile_top2<true>(taddr, nullptr, gidx, M1, M2);
-            else fr_half_tile_top2<false>(taddr, reinterpret_cast<const float4*>(ysn + (size_t)rt * GM_BN + half * (GM_BN / 2)), gidx, M1, M2);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_remote_nofence(r_tmem_empty + 8 * acc.idx);
-            acc.advance(2);
+            float M1 = FR_NEG, M2 = FR_NEG;
+#pragma unroll 1
+            for (int sub = 0; sub < 2; ++sub) {
+                // this warp's 64 columns of sub-tile `sub` are tile rows [128 half + 64 sub, +64): group index = 16 sub + g
+                mbar_wait(tmem_full + 8 * acc.idx, acc.phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * (GM_BN / 2) + half * (GM_BN / 4);
+                float c1, c2;
+                if (bias_in_acc) fr_unit_top2<true>(taddr, nullptr, gidx, c1, c2);
+                else fr_unit_top2<false>(taddr, reinterpret_cast<const float4*>(ysn + (size_t)rt * GM_BN + half * (GM_BN / 2) + sub * (GM_BN / 4)), gidx, c1, c2);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote_nofence(r_tmem_empty + 8 * acc.idx);
+                acc.advance(FR_ACC_BUFS);
+                const uint32_t sbit = (uint32_t)sub << 4;
+                c1 = __uint_as_float(__float_as_uint(c1) | sbit);
+                c2 = __uint_as_float(__float_as_uint(c2) | sbit);
+                const float t = fminf(M1, c1);
+                M2 = fmaxf(fmaxf(M2, t), c2);
+                M1 = fmaxf(M1, c1);
+            }
             // merge this tile's two best into the segment's
             if (M1 > V1) {
                 if (M2 > V1) { V2 = M2; T2 = toff; } else { V2 = V1; T2 = T1; }
@@ -1432,7 +1481,7 @@ gm_refine_kernel(const FrParams P) {
     if (valid) {
         const float2 n = P.qn[row];
         const float Bh = __uint_as_float(P.ctrl->rh_max_bits[obj]), Bl = __uint_as_float(P.ctrl->rl_max_bits[obj]);
-        const float bias = __uint_as_float(P.ctrl->bias_max_bits[obj]);
+        const float bias = 0.5f * (P.ctrl->scale_q * P.ctrl->scale_r) * __uint_as_float(P.ctrl->rsq_max_bits[obj]) * 1.000001f;
         delta = 2.0f * (n.y * Bh + n.x * Bl + n.y * Bl) + 6.2e-5f * (n.x * Bh + bias);      // 6.2e-5 ~ 2^-14: accumulator + index bits, both sides
         delta = delta * 1.0001f + 1e-30f;
     }
@@ -1576,7 +1625,7 @@ struct GmPlan {
     size_t off_ctrl, off_tile_obj, off_xs, off_ysn, off_best, off_A, off_B, total;
     // filter-and-refine engine (fr == false: shape not served by it, the three-product engine runs)
     bool fr; int seg_tiles, max_segs, C4, rescan_cap;
-    size_t off_tile_seg, off_seg_tile0, off_qn, off_q32, off_r32, off_src, off_keys, off_tags, off_rescan, off_best64;
+    size_t off_tile_seg, off_seg_tile0, off_qn, off_q32, off_r32, off_src, off_rsq, off_keys, off_tags, off_rescan, off_best64;
 };
 
 // test / A-B knobs (manet_set_option): force at least this many tiles per segment, shrink the rescan list
@@ -1610,7 +1659,7 @@ static GmPlan gm_plan(int64_t M, int64_t R, int N, int C) {
     const int64_t seg_budget = (segs_by_mem < FR_MAX_SEGS ? segs_by_mem : FR_MAX_SEGS) - N;
     p.fr = seg_budget >= 1 && p.max_rtiles < 65536 * 4;
     p.seg_tiles = 1; p.max_segs = 0; p.C4 = (C + 3) & ~3; p.rescan_cap = FR_RESCAN_CAP;
-    p.off_tile_seg = p.off_seg_tile0 = p.off_qn = p.off_q32 = p.off_r32 = p.off_src = p.off_keys = p.off_tags = p.off_rescan = p.off_best64 = 0;
+    p.off_tile_seg = p.off_seg_tile0 = p.off_qn = p.off_q32 = p.off_r32 = p.off_src = p.off_rsq = p.off_keys = p.off_tags = p.off_rescan = p.off_best64 = 0;
     if (p.fr) {
         p.seg_tiles = (int)ceil_div64(p.max_rtiles, seg_budget);
         if (g_opt_seg_tiles > p.seg_tiles) p.seg_tiles = g_opt_seg_tiles;
@@ -1625,6 +1674,7 @@ static GmPlan gm_plan(int64_t M, int64_t R, int N, int C) {
         p.off_q32 = o; o = align_up(o + (size_t)p.M_pad * p.C4 * sizeof(float), 1024);
         p.off_r32 = o; o = align_up(o + (size_t)(p.R_pad_max + FR_GROUP_COLS) * p.C4 * sizeof(float), 1024);
         p.off_src = o; o = align_up(o + (size_t)(p.R_pad_max + FR_GROUP_COLS) * sizeof(int), 1024);
+        p.off_rsq = o; o = align_up(o + (size_t)(p.R_pad_max + FR_GROUP_COLS) * sizeof(float), 1024);
         p.off_keys = o; o = align_up(o + (size_t)p.max_segs * 2 * p.M_pad * sizeof(float2), 1024);
         p.off_tags = o; if (p.seg_tiles > 1) o = align_up(o + (size_t)p.max_segs * 2 * p.M_pad * sizeof(uint32_t), 1024);
         p.off_rescan = o; o = align_up(o + (size_t)p.rescan_cap * sizeof(int4), 1024);
@@ -1655,8 +1705,8 @@ size_t gm_umma_workspace_bytes(int64_t M, int64_t R, int N, int C) { return gm_p
 // out_idx != nullptr: arg-min mode (raw distances + original index of the nearest reference pixel; filter-and-refine only).
 int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t R, const int32_t* labels,
                              const float* query, int64_t qps, int64_t qcs, int64_t M, int C, int N,
-                             int normalize, float* mem_frame, float* out, int32_t* out_idx, int engine, void* ws, size_t ws_bytes,
-                             cudaStream_t stream) {
+                             int normalize, float* mem_frame, float* out, int32_t* out_idx, int engine, int reuse_ref, void* ws,
+                             size_t ws_bytes, cudaStream_t stream) {
     GmPlan p = gm_plan(M, R, N, C);
     if (ws_bytes < p.total) { set_error("global match: workspace too small (%zu < %zu)", ws_bytes, p.total); return MANET_E_WORKSPACE; }
     if (M <= 0) return 0;
@@ -1677,18 +1727,28 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
         pre.q32 = reinterpret_cast<float*>(wbase + p.off_q32); pre.r32 = reinterpret_cast<float*>(wbase + p.off_r32);
         pre.qn = reinterpret_cast<float2*>(wbase + p.off_qn); pre.src_idx = reinterpret_cast<int*>(wbase + p.off_src);
         pre.tile_seg = reinterpret_cast<int*>(wbase + p.off_tile_seg); pre.seg_tile0 = reinterpret_cast<int*>(wbase + p.off_seg_tile0);
+        pre.rsq = reinterpret_cast<float*>(wbase + p.off_rsq);
         pre.C4 = p.C4; pre.seg_tiles = p.seg_tiles; pre.skip_lo = 1;
     }
+    // MANET_GM_REUSE_REF (filter-and-refine engine only; otherwise a full rebuild, which is always correct): the reference side
+    // of the workspace -- bucketed operand image, fp32 copy, norms, tables -- was left by the previous call and is kept;
+    // this call scans and converts the query only and refreshes the bias for the query's scale.
+    const bool reuse = use_fr && reuse_ref != 0 && R > 0;
+    pre.reuse = reuse ? 1 : 0;
 
-    cudaError_t e = cudaMemsetAsync(ctrl, 0, sizeof(GmCtrl), stream);
+    profile_begin(PROF_GLOBAL_PREPASS, stream);
+    cudaError_t e = cudaMemsetAsync(ctrl, 0, reuse ? GM_CTRL_FRAME_BYTES : sizeof(GmCtrl), stream);
     if (e != cudaSuccess) { set_error("global match: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
-    const int64_t items = R + M;
+    const int64_t R_scan = reuse ? 0 : R;
+    const int64_t items = R_scan + M;
     dim3 g1((unsigned)(ceil_div64(items, 256) < 148 * 8 ? ceil_div64(items, 256) : 148 * 8), GM_SCAN_CG);
-    launch_k(gm_scan_kernel, g1, dim3(256), 0, stream, ref, rps, rcs, R, labels, query, qps, qcs, M, C, N, ctrl, best,
+    launch_k(gm_scan_kernel, g1, dim3(256), 0, stream, ref, rps, rcs, R_scan, labels, query, qps, qcs, M, C, N, ctrl, best,
              use_fr ? (int64_t)0 : p.M_pad * N);
-    const int nb_ref = (int)ceil_div64(R, GM_CV_PIX), nb_q = (int)ceil_div64(p.M_pad, GM_CV_PIX);
-    launch_k(gm_convert_kernel, dim3(nb_ref + nb_q + N), dim3(256), 0, stream, ref, rps, rcs, R, labels, query, qps, qcs, M, p.M_pad, C, N,
+    const int nb_ref = (int)ceil_div64(R_scan, GM_CV_PIX), nb_q = (int)ceil_div64(p.M_pad, GM_CV_PIX);
+    const int nb_tail = reuse ? (int)(p.R_pad_max / GM_CV_PIX) : N;            // bias refresh blocks | bucket padding blocks
+    launch_k(gm_convert_kernel, dim3(nb_ref + nb_q + nb_tail), dim3(256), 0, stream, ref, rps, rcs, R_scan, labels, query, qps, qcs, M, p.M_pad, C, N,
              nb_ref, nb_q, ctrl, Aimg, Bimg, xs, ysn, tile_obj, pre);
+    profile_end(PROF_GLOBAL_PREPASS, stream);
     // 0: single CTA, 1: multicast pair, 2: cta_group::2 pair (default); MANET_GM_VARIANT is an A/B switch for profiling
     static const int variant = [] { const char* e1 = getenv("MANET_GM_VARIANT"); return (e1 && e1[0] >= '0' && e1[0] <= '2') ? e1[0] - '0' : 2; }();
     static PerDevice attrs;
@@ -1718,8 +1778,10 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
         profile_end(PROF_GLOBAL_UMMA, stream);
         profile_begin(PROF_GLOBAL_REFINE, stream);
         launch_k(gm_refine_kernel, dim3((unsigned)ceil_div64(M, 256), (unsigned)N), dim3(256), 0, stream, F);
-        launch_k(gm_rescan_kernel, dim3((unsigned)(2 * sm_count)), dim3(256), 0, stream, F);
         profile_end(PROF_GLOBAL_REFINE, stream);
+        profile_begin(PROF_GLOBAL_RESCAN, stream);
+        launch_k(gm_rescan_kernel, dim3((unsigned)(2 * sm_count)), dim3(256), 0, stream, F);
+        profile_end(PROF_GLOBAL_RESCAN, stream);
         if (out_idx != nullptr)
             launch_k(gm_unpack_kernel, dim3((unsigned)ceil_div64(M * N, 256)), dim3(256), 0, stream, (const unsigned long long*)F.best64,
                      (const GmCtrl*)ctrl, M, N, out, out_idx);

@@ -12,13 +12,13 @@ from . import _lib
 from ._device import check
 from .config import cfg
 from .memory import (global_map_read_update, local_map_init_for_annotated_frame, local_map_store_select)
-from .networks.IntVOS import (_wants_grad, local_previous_frame_nearest_neighbor_features_per_object,
+from .networks.IntVOS import (ReferenceOperands, _wants_grad, local_previous_frame_nearest_neighbor_features_per_object,
                               nearest_neighbor_features_per_object)
 
 
 def prop_matching_step(ref_emb, prev_emb, cur_emb, ref_scribble_label, prev_label, n_objects,
                        k_nearest_neighbors=1, max_distance=None, global_map_tmp_dic=None, local_map_dics=None,
-                       seq_name="seq", frame=0, interaction_num=1, start_annotated_frame=0):
+                       seq_name="seq", frame=0, interaction_num=1, start_annotated_frame=0, reference_cache=None):
     """``ref_emb/prev_emb/cur_emb``: ``[C,H,W]`` CUDA tensors; labels ``[H,W]`` int32 at embedding
     resolution; ``n_objects`` = gt_ids[n].  Returns ``(global_map, local_map)``, both ``[1,H,W,N,1]``."""
     d = cfg.MODEL_MAX_LOCAL_DISTANCE if max_distance is None else max_distance
@@ -31,7 +31,8 @@ def prop_matching_step(ref_emb, prev_emb, cur_emb, ref_scribble_label, prev_labe
                                                       device=cur.device)
         mem_slot = global_map_tmp_dic[seq_name][int(frame)]
     g, ids = nearest_neighbor_features_per_object(ref, cur, ref_scribble_label.unsqueeze(-1), k_nearest_neighbors,
-                                                  n_objects, n_chunks=10, normalize=True, memory_frame=mem_slot)
+                                                  n_objects, n_chunks=10, normalize=True, memory_frame=mem_slot,
+                                                  reference_cache=reference_cache)
     loc = local_previous_frame_nearest_neighbor_features_per_object(prev, cur, prev_label.unsqueeze(-1), ids, d)
     if local_map_dics is not None:
         loc, local_map_dics = local_map_store_select(local_map_dics, seq_name, frame, interaction_num,
@@ -224,11 +225,13 @@ def propagate_sequence(embedding_memory, frames, ref_frame, ref_scribble_label, 
     out = {}
     prev_frame, prev_small = int(ref_frame), prev_label_small
     ids = torch.arange(0, int(n_objects) + 1, dtype=torch.int32, device=embedding_memory.device)
+    ref_ops = ReferenceOperands()          # the annotated frame and its scribble are constant along the loop: convert them once
+    ref_emb = embedding_memory[ref_frame]
     for f in frames:
         f = int(f)
-        g, loc = prop_matching_step(embedding_memory[ref_frame], embedding_memory[prev_frame], embedding_memory[f],
+        g, loc = prop_matching_step(ref_emb, embedding_memory[prev_frame], embedding_memory[f],
                                     ref_scribble_label, prev_small, n_objects, 1, max_distance, global_map_tmp_dic,
-                                    local_map_dics, seq_name, f, interaction_num, ref_frame)
+                                    local_map_dics, seq_name, f, interaction_num, ref_frame, ref_ops)
         pred = dynamic_seghead.forward_parts(embedding_memory[f], g, loc, prev_small, ids).permute(1, 0, 2, 3)
         full, prev_small = upsample_argmax(pred, size, want_full=keep_full)
         if keep_full:
@@ -311,8 +314,10 @@ class MatchingSession:
     def upload(self):
         check(self._lib.manet_session_upload(self._h), "manet_session_upload")
 
-    def step_device(self, frame, interaction_num=1, start_annotated_frame=0, drop_unlabelled=True, serial=False):
-        flags = (_lib.GM_DROP_UNLAB if drop_unlabelled else 0) | (_lib.STEP_SERIAL if serial else 0)
+    def step_device(self, frame, interaction_num=1, start_annotated_frame=0, drop_unlabelled=True, serial=False, ref_cache=True):
+        """``ref_cache=False`` forces the full global-matching pre-pass (the first frame of a sequence); by default the session
+        keeps the reference-side operands while the annotated frame has not been uploaded again."""
+        flags = (_lib.GM_DROP_UNLAB if drop_unlabelled else 0) | (_lib.STEP_SERIAL if serial else 0) | (0 if ref_cache else _lib.STEP_NO_REF_CACHE)
         check(self._lib.manet_session_step_device(self._h, frame, interaction_num, start_annotated_frame, flags),
               "manet_session_step_device")
 

@@ -216,7 +216,35 @@ def _selected_pixel(ref_labels_flat, ref_emb_flat):
     return out_lab, out_emb
 
 
-def _global_match_raw(ref, r, rps, rcs, labels_i32, qry, m, qps, qcs, c, n_obj, k, flags=0, mem_frame=None):
+class ReferenceOperands:
+    """Keeps the reference side of global matching between calls (not in the reference: there every frame rebuilds
+    everything).  Along a propagation the annotated frame and its scribble labels are constant (test.py:237-259); pass one
+    ``ReferenceOperands`` object as ``reference_cache=`` to every ``nearest_neighbor_features_per_object`` call of that
+    propagation and, from the second call on, only the query is scanned and converted (``MANET_GM_REUSE_REF``).  The object
+    owns a private workspace and remembers which tensors it was built from (storage pointer, strides, in-place version
+    counter, shapes, object count, TEST_MODE, stream): any difference triggers a full rebuild, so results never depend on it."""
+
+    def __init__(self):
+        self.ws = None
+        self.key = None
+        self.keep = None          # the tensors the key describes stay alive: their addresses cannot be recycled under the cache
+
+    def prepare(self, dev, nbytes, key):
+        """-> (workspace, reuse?)"""
+        if self.ws is None or self.ws.numel() < nbytes or self.ws.device != dev:
+            with torch.cuda.device(dev):
+                self.ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+            self.key = None
+        reuse = self.key is not None and self.key == key
+        self.key = key
+        return self.ws, reuse
+
+    def invalidate(self):
+        self.key = None
+        self.keep = None
+
+
+def _global_match_raw(ref, r, rps, rcs, labels_i32, qry, m, qps, qcs, c, n_obj, k, flags=0, mem_frame=None, cache=None, cache_key=None):
     dev = qry.device
     L = _lib.lib()
     if FORCE_SIMT_ENGINE:
@@ -225,7 +253,12 @@ def _global_match_raw(ref, r, rps, rcs, labels_i32, qry, m, qps, qcs, c, n_obj, 
         flags |= _lib.GM_ENGINE_EXACT3
     out = torch.empty((m, n_obj, 1), dtype=torch.float32, device=dev)
     ws_bytes = L.manet_global_match_workspace_bytes(m, r, c, n_obj, k)
-    ws = workspace(dev, ws_bytes, "global")
+    if cache is not None and k == 1:
+        ws, reuse = cache.prepare(dev, ws_bytes, cache_key + (m, r, c, n_obj, flags, stream_ptr(dev)))
+        if reuse:
+            flags |= _lib.GM_REUSE_REF
+    else:
+        ws = workspace(dev, ws_bytes, "global")
     with torch.cuda.device(dev):
         check(L.manet_global_match(
             ref.data_ptr() if r else None, rps, rcs, r, labels_i32.data_ptr() if r else None,
@@ -273,7 +306,7 @@ def _nearest_neighbor_features_per_object_in_chunks(reference_embeddings_flat, q
 
 def nearest_neighbor_features_per_object(reference_embeddings, query_embeddings, reference_labels,
                                          k_nearest_neighbors, gt_ids=None, n_chunks=100, *,
-                                         normalize=False, memory_frame=None):
+                                         normalize=False, memory_frame=None, reference_cache=None):
     """Distance from every query pixel to its nearest reference pixel of each object
     (IntVOS.py:160-210).
 
@@ -284,7 +317,8 @@ def nearest_neighbor_features_per_object(reference_embeddings, query_embeddings,
 
     Keyword-only extensions (not in the reference): ``normalize=True`` fuses the caller-side
     ``(sigmoid(x)-0.5)*2`` of IntVOS.py:611-612; ``memory_frame`` (a ``[h,w,N,1]`` slice of the
-    global-map memory) additionally fuses the running-min update of IntVOS.py:620-622.
+    global-map memory) additionally fuses the running-min update of IntVOS.py:620-622; ``reference_cache`` (a
+    ``ReferenceOperands``) keeps the converted reference between the calls of one propagation.
     """
     assert reference_embeddings.size()[:2] == reference_labels.size()[:2]
     require_f32(query_embeddings, "query_embeddings")
@@ -322,7 +356,13 @@ def nearest_neighbor_features_per_object(reference_embeddings, query_embeddings,
         return out.view(1, h, w, n_obj, 1), ids
     if normalize:
         flags |= _lib.GM_NORMALIZE
-    out = _global_match_raw(ref, r, rps, rcs, labels, qry, m, qps, qcs, c, n_obj, k, flags, mem)
+    cache_key = None
+    if reference_cache is not None:
+        cache_key = (ref.data_ptr(), ref._version, tuple(ref.shape), tuple(ref.stride()), reference_labels.data_ptr(),
+                     reference_labels._version, tuple(reference_labels.shape), tuple(reference_labels.stride()),
+                     str(reference_labels.dtype), bool(cfg.TEST_MODE))
+        reference_cache.keep = (reference_embeddings, reference_labels)
+    out = _global_match_raw(ref, r, rps, rcs, labels, qry, m, qps, qcs, c, n_obj, k, flags, mem, reference_cache, cache_key)
     return out.view(1, h, w, n_obj, 1), ids
 
 

@@ -44,6 +44,12 @@ typedef void* manet_stream_t; /* a cudaStream_t */
 #define MANET_GM_ENGINE_EXACT3 8u /* tcgen05, but the three-product kernel (every query x reference pair at fp32 grade, 19 K steps
                                    * per tile) instead of the default filter-and-refine engine (one product filters candidates,
                                    * the survivors are re-evaluated exactly in fp32, 7 K steps per tile); same results */
+#define MANET_GM_REUSE_REF 128u /* the reference side of `workspace` is still valid: the PREVIOUS manet_global_match /
+                                 * _argmin_ws call on this workspace had the same reference embeddings, labels, R, M, C, N (the
+                                 * annotated frame and its scribble are constant along a propagation, test.py:237-259) and nothing
+                                 * else used the workspace since.  Only the query is scanned and converted (and the bias refreshed
+                                 * for its scale): the per-frame pre-pass halves.  Results are identical to a full call.  Honoured
+                                 * by the filter-and-refine engine; otherwise ignored (full rebuild). */
 /* local-match flag (the *_ex entry points) */
 #define MANET_LM_ENGINE_SIMT 1u /* force the fp32 CUDA-core kernels (exact difference form) instead of the tcgen05 kernel */
 #define MANET_LM_ENGINE_TENSOR 2u /* force the tcgen05 kernels without the device-side numerics guard (see manet_local_match_ex) */
@@ -57,6 +63,10 @@ typedef void* manet_stream_t; /* a cudaStream_t */
  * alternating slots 0,1 and wait for step i before submitting step i+2 (the usual two-slot protocol). */
 #define MANET_STEP_STREAM        32u
 #define MANET_STEP_STREAM_RESET  64u
+/* A session keeps the reference-side operands of global matching (bucketed tensor-core image, fp32 copy, tables) between steps
+ * for as long as the annotated frame and its labels have not been uploaded again (MANET_GM_REUSE_REF): a propagation converts
+ * only the new frame.  This flag forces the full pre-pass (what the first frame of a sequence pays). */
+#define MANET_STEP_NO_REF_CACHE 256u
 
 /* dtype codes for the Correlation op (AT_DISPATCH_FLOATING_TYPES_AND_HALF, correlation_cuda_kernel.cu:386) */
 #define MANET_DT_F32 0
@@ -331,8 +341,9 @@ int manet_rough_roi(const int32_t* labels, int batch, int H, int W, int dist, in
 /* ------------------------------------------------------------------------------------------
  * Optional kernel timing for benchmarks (no reference equivalent).  After
  * manet_profile_enable(n) the launchers bracket their dominant kernels with CUDA events on the
- * launching stream (slot 0: tcgen05 global-matching kernel, 1: local window-distance kernel,
- * 2: local upsample/mask/min kernel), up to n records per slot.  manet_profile_read returns the
+ * launching stream (slot 0: tcgen05 global-matching kernel, 1: local main kernel, 2: local pre-pass,
+ * 3: global-matching refinement kernel, 4: its rescan kernel, 5: global-matching pre-pass = memset + scan + convert),
+ * up to n records per slot.  manet_profile_read returns the
  * per-launch durations in milliseconds (synchronise the stream first).  enable(0) turns it off.
  * ------------------------------------------------------------------------------------------ */
 int manet_profile_enable(int max_records);

@@ -185,3 +185,36 @@ def test_tiny_and_degenerate_inputs(api):
     assert bool((run(api, ref, qry, lab, 3) == 0).all())                   # exact zeros (difference form), thousands of ties
     zeros = torch.zeros(400, C).cuda()
     assert bool((run(api, zeros, zeros[:50], lab[:400], 3) == 0).all())
+
+
+def test_reference_cache_gives_identical_results(api):
+    """MANET_GM_REUSE_REF: along a propagation only the query changes; the cached reference side must give bit-identical
+    maps, also when the query's power-of-two scale changes between frames (the bias is rebuilt for it) and with the fused
+    normalise + memory epilogue; a changed reference (in-place edit bumps the version counter) forces a rebuild."""
+    gen = torch.Generator().manual_seed(31)
+    C, H, W, n_obj = 100, 40, 54, 4
+    ref = (0.1 * torch.relu(torch.randn(C, H, W, generator=gen))).cuda().permute(1, 2, 0)
+    lab = torch.randint(-1, n_obj, (H, W, 1), generator=gen).int().cuda()
+    cache = api.ReferenceOperands()
+    from cvpr2020_manet_b200.config import cfg
+    saved = cfg.TEST_MODE
+    cfg.TEST_MODE = True
+    try:
+        for i, scale in enumerate((1.0, 1.0, 37.0, 0.01, 1.0)):
+            qry = (scale * 0.1 * torch.relu(torch.randn(C, H, W, generator=gen))).cuda().permute(1, 2, 0)
+            want, _ = api.nearest_neighbor_features_per_object(ref, qry, lab, 1, torch.tensor(n_obj - 1))
+            got, _ = api.nearest_neighbor_features_per_object(ref, qry, lab, 1, torch.tensor(n_obj - 1), reference_cache=cache)
+            assert torch.equal(got, want), i
+            mem_a = torch.rand(H, W, n_obj, 1, generator=gen).cuda()
+            mem_b = mem_a.clone()
+            want, _ = api.nearest_neighbor_features_per_object(ref, qry, lab, 1, torch.tensor(n_obj - 1), normalize=True, memory_frame=mem_a)
+            got, _ = api.nearest_neighbor_features_per_object(ref, qry, lab, 1, torch.tensor(n_obj - 1), normalize=True, memory_frame=mem_b,
+                                                              reference_cache=cache)
+            assert torch.equal(got, want) and torch.equal(mem_a, mem_b), i
+        lab[:5] = 0                                  # in-place edit: the cache must notice and rebuild
+        qry = (0.1 * torch.relu(torch.randn(C, H, W, generator=gen))).cuda().permute(1, 2, 0)
+        want, _ = api.nearest_neighbor_features_per_object(ref, qry, lab, 1, torch.tensor(n_obj - 1))
+        got, _ = api.nearest_neighbor_features_per_object(ref, qry, lab, 1, torch.tensor(n_obj - 1), reference_cache=cache)
+        assert torch.equal(got, want)
+    finally:
+        cfg.TEST_MODE = saved
