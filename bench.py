@@ -201,10 +201,10 @@ def run_own_arm(args, rank, local_rank, world):
 
     K, Wm = args.steps, args.warmup
 
-    def timed_pass(serial):
+    def timed_pass(serial, ref_cache=True):
         """K steps, one CUDA-event pair per step on the launching stream, L2 flushed between steps."""
         for i in range(Wm):
-            sess.step_device(1 + i % 100, 1, 0, serial=serial)
+            sess.step_device(1 + i % 100, 1, 0, serial=serial, ref_cache=ref_cache)
         sess.sync()
         L.manet_profile_reset()
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
@@ -215,7 +215,7 @@ def run_own_arm(args, rank, local_rank, world):
             for i in range(K):
                 flush_buf.fill_(i & 0xFF)                      # L2 flush, outside the timed events
                 starts[i].record(stream)
-                sess.step_device(1 + (Wm + i) % 100, 1, 0, serial=serial)
+                sess.step_device(1 + (Wm + i) % 100, 1, 0, serial=serial, ref_cache=ref_cache)
                 stops[i].record(stream)
         sess.sync()
         barrier()
@@ -232,6 +232,7 @@ def run_own_arm(args, rank, local_rank, world):
     total_s, wall_dev = timed_pass(serial=False)
     launches_total = int(L.manet_profile_launch_count())          # warm-up + timed steps of the headline pass, counted by the library
     gpu_launches = launches_total * K // (K + Wm)                  # every step launches the same kernels
+    nocache_s, _ = timed_pass(serial=False, ref_cache=False)      # every step rebuilds the reference side (a sequence's first frame)
     L.manet_profile_enable(K + 4)
     serial_s, _ = timed_pass(serial=True)
     # kernel timings recorded inside the library on the launching stream (serial pass)
@@ -289,10 +290,10 @@ def run_own_arm(args, rank, local_rank, world):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
-    t = torch.tensor([total_s, e2e_s, e2e_sync_s, serial_s, e2e_stream_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_s, e2e_s, e2e_sync_s, serial_s, e2e_stream_s, nocache_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_s, e2e_s, e2e_sync_s, serial_s, e2e_stream_s = (float(t[i]) for i in range(5))
+    total_s, e2e_s, e2e_sync_s, serial_s, e2e_stream_s, nocache_s = (float(t[i]) for i in range(6))
 
     # the head / propagation legs describe one GPU; multi-GPU runs (independent sequences) report the scaling metric only.
     # They run BEFORE the 1080p sharded-matching leg: right after that leg's ~0.2 s of back-to-back 28 ms tensor-core kernels the
@@ -348,6 +349,7 @@ def run_own_arm(args, rank, local_rank, world):
                 "config": {"workload": WORKLOAD, "parallelism": f"{world} independent sequences (1 per GPU), no data-path collective",
                            "l2": "flushed between timed steps (256 MiB write outside the event pair)",
                            "streams": "local-matching branch forked onto a second stream, joined before the step's end event",
+                           "reference_operands": "steady state of a propagation: the annotated frame's operands are kept between steps (see first_frame for the rebuild-every-step figure)",
                            "timing": "CUDA events per step on the launching stream, summed; max over ranks"},
                 "e2e": {"value": world * K / e2e_stream_s, "unit": "frames/s", "h2d_bytes_per_step": sess.h2d_bytes_per_streamed_step,
                         "d2h_bytes_per_step": sess.d2h_bytes_per_step, "ms_per_step": e2e_stream_s * 1e3 / K,
@@ -362,6 +364,10 @@ def run_own_arm(args, rank, local_rank, world):
                                               "PCIe-bound, this was r01's e2e.value",
                                       "sync_value": world * K / e2e_sync_s, "sync_ms_per_step": e2e_sync_s * 1e3 / K}},
                 "single_stream": {"value": world * K / serial_s, "ms_per_step": serial_s * 1e3 / K},
+                "first_frame": {"value": world * K / nocache_s, "ms_per_step": nocache_s * 1e3 / K,
+                                "note": "MANET_STEP_NO_REF_CACHE: the reference side of global matching (annotated frame: bucketing, tensor-core "
+                                        "image, fp32 copy) rebuilt every step -- what the first frame of a propagation pays; `value` is the steady "
+                                        "state of the loop (test.py:237-259: annotated frame and scribble constant), which converts only the new frame"},
                 "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline,
                 "wall_s_timed_region": wall_dev}
         if sharded:

@@ -1086,10 +1086,9 @@ __global__ void gm_finalize_kernel(const int* __restrict__ best, const float* __
 // depends on how many near-ties there are.
 constexpr int FR_GROUP_COLS = 4;                                // neighbouring reference columns that share one key
 constexpr int FR_GROUPS = GM_BN / 2 / FR_GROUP_COLS;            // groups per 128-column half tile
-constexpr uint32_t FR_KEY_MASK = 0xFFFFFFE0u;                   // ... whose index takes the low 5 mantissa bits of a key
+                                                                // ... whose index takes the low 5 mantissa bits of a key (fr_key)
 static_assert(FR_GROUPS == 32, "the key layout assumes 32 column groups per half tile");
 constexpr float FR_NEG = -3.0e38f;
-constexpr int FR_ACC_BUFS = 4;                                  // accumulator buffers of GM_BN / 2 = 128 tensor-memory columns
 
 // (v & mask) | g in ONE LOP3: a LOP3 takes one immediate, so the group index must sit in a register.  The caller derives
 // the sixteen indices of a chunk pair from a run-time zero (a kernel argument ptxas cannot fold), once per kernel.
@@ -1149,49 +1148,54 @@ __device__ __forceinline__ long long fr_snap(long long x, long long total, int n
     return m * n_rtiles + __ldg(seg_tile0 + sg + 1);          // seg_tile0[n_segs] = n_rtiles: rolls over to the next m
 }
 
+// Work item = (query QUAD q = 512 query rows = two cta_group::2 tiles, reference tile rt): the pair of CTAs keeps TWO A tiles
+// in shared memory and runs both against every B stage, so a B stage (32 KB per CTA) feeds 2 x 7 MMAs.  With one A tile per
+// stage the one-product GEMM sits at the L2 -> SM limit (32 KB per 896 MMA cycles and SM = 5.3 KB/clk over the chip against
+// ~6 KB/clk of L2 bandwidth); the second A tile halves that.  Accumulator buffer a (256 tensor-memory columns) belongs to A
+// tile a: the epilogue of (q, rt, 0) overlaps the MMAs of (q, rt, 1) and so on.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
 gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg, const float* __restrict__ ysn,
              const int* __restrict__ tile_seg, const int* __restrict__ seg_tile0, const GmCtrl* __restrict__ ctrl,
-             float2* __restrict__ keys, uint32_t* __restrict__ tags, int64_t M_pad, int n_mpairs, int ksteps, int seg_tiles,
+             float2* __restrict__ keys, uint32_t* __restrict__ tags, int64_t M_pad, int n_quads, int ksteps, int seg_tiles,
              int rt_zero) {
     pdl_enter();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - raw);
-    const uint32_t sA = base;                                  // 32 KB: hi part of this CTA's 128 query rows
-    const uint32_t sB = base + 2 * GM_CHUNK_BYTES;             // ring of G2_STAGES x 32 KB: hi part of this CTA's half of a tile
-    const uint32_t bars = base + 2 * GM_CHUNK_BYTES + G2_STAGES * G2_STAGE_BYTES;
+    constexpr int A_BYTES = 2 * GM_CHUNK_BYTES;                // hi part of 128 query rows: two k-blocks of 16 KB
+    const uint32_t sA = base;                                  // two A tiles
+    const uint32_t sB = base + 2 * A_BYTES;                    // ring of G2_STAGES x 32 KB: hi part of this CTA's half of a B tile
+    constexpr int BAR_OFF = 2 * A_BYTES + G2_STAGES * G2_STAGE_BYTES;
+    const uint32_t bars = base + BAR_OFF;
     const uint32_t full_b = bars + 0;            // [4]  local bytes landed
     const uint32_t empty_b = bars + 32;          // [4]  stage free (multicast commit)
     const uint32_t peer_full = bars + 64;        // [4]  leader only: peer's half landed
     const uint32_t a_full = bars + 96;
     const uint32_t a_empty = bars + 104;
     const uint32_t peer_a_full = bars + 112;     // leader only
-    // FOUR accumulator buffers of 128 columns: a 256-reference tile is issued as two half-width MMA groups, so the issuer
-    // runs up to three sub-tiles ahead of the epilogue.  With two 256-column buffers the hand-off latency (remote arrive
-    // -> issue -> commit -> wake-up, ~800 cycles) sat on the critical path of every tile (ncu: the epilogue warps spent a
-    // third of their time waiting for the accumulator).
-    const uint32_t tmem_full = bars + 120;       // [4]
-    const uint32_t tmem_empty = bars + 152;      // [4]  leader only, 16 arrivals
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 2 * GM_CHUNK_BYTES + G2_STAGES * G2_STAGE_BYTES + 192);
+    const uint32_t tmem_full = bars + 120;       // [2]
+    const uint32_t tmem_empty = bars + 136;      // [2]  leader only, 16 arrivals
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + BAR_OFF + 160);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int n_rtiles = ctrl->n_rtiles;
     const bool bias_in_acc = ctrl->bias_fold != 0;
-    const long long total = (long long)n_mpairs * n_rtiles;
+    const long long total = (long long)n_quads * n_rtiles;
     const int n_clusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
-    // contiguous ranges of tiles, cut at segment boundaries: a (query row, segment-half) is reduced by exactly one warp
+    // contiguous ranges of items, cut at segment boundaries: a (query row, segment-half) is reduced by exactly one warp
     const long long t_begin = fr_snap(total * cid / n_clusters, total, n_rtiles, tile_seg, seg_tile0);
     const long long t_end = fr_snap(total * (cid + 1) / n_clusters, total, n_rtiles, tile_seg, seg_tile0);
+    const long long q_begin = n_rtiles ? t_begin / n_rtiles : 0;              // one division per kernel, not per item
+    const int rt_begin = n_rtiles ? (int)(t_begin % n_rtiles) : 0;
 
     if (warp == 1) {
         if (lane == 0) {
             for (int i = 0; i < G2_STAGES; ++i) { mbar_init(full_b + 8 * i, 1); mbar_init(empty_b + 8 * i, 1); mbar_init(peer_full + 8 * i, 1); }
             mbar_init(a_full, 1); mbar_init(a_empty, 1); mbar_init(peer_a_full, 1);
-            for (int i = 0; i < FR_ACC_BUFS; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, 2 * GM_EPI_WARPS); }
+            for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + 8 * i, 1); mbar_init(tmem_empty + 8 * i, 2 * GM_EPI_WARPS); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -1205,19 +1209,20 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ------------------------------------------------ producer (both CTAs: hi part of own A rows, of own half of B)
-        Ring st; uint32_t ae_phase = 0; long long cur_m = -1;
-        long long m = n_rtiles ? t_begin / n_rtiles : 0; int rt = n_rtiles ? (int)(t_begin % n_rtiles) : 0;   // one division per kernel, not per tile
-        for (long long tile = t_begin; tile < t_end; ++tile, ++rt) {
-            if (rt == n_rtiles) { rt = 0; ++m; }
-            if (m != cur_m) {
+        // ------------------------------------------------ producer (both CTAs: hi parts of own A rows, of own half of B)
+        Ring st; uint32_t ae_phase = 0; long long cur_q = -1;
+        long long q = q_begin; int rt = rt_begin;
+        for (long long item = t_begin; item < t_end; ++item, ++rt) {
+            if (rt == n_rtiles) { rt = 0; ++q; }
+            if (q != cur_q) {
                 mbar_wait(a_empty, ae_phase ^ 1); ae_phase ^= 1;
                 if (elect_one()) {
-                    mbar_expect_tx(a_full, 2 * GM_CHUNK_BYTES);
-                    bulk_g2s(sA, Aimg + (size_t)(2 * m + rank) * GM_UNIT_BYTES, 2 * GM_CHUNK_BYTES, a_full);
+                    mbar_expect_tx(a_full, 2 * A_BYTES);
+                    bulk_g2s(sA, Aimg + (size_t)(4 * q + rank) * GM_UNIT_BYTES, A_BYTES, a_full);               // query tile pair 2q
+                    bulk_g2s(sA + A_BYTES, Aimg + (size_t)(4 * q + 2 + rank) * GM_UNIT_BYTES, A_BYTES, a_full);   // query tile pair 2q + 1
                 }
                 __syncwarp();
-                cur_m = m;
+                cur_q = q;
             }
             mbar_wait(empty_b + 8 * st.idx, st.phase ^ 1);
             if (elect_one()) {
@@ -1229,53 +1234,53 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
         }
     } else if (warp == 1) {
         if (leader) {
-            // -------------------------------------------- MMA issuer: qh.rh only, `ksteps` K steps per 256 x 128 sub-tile
-            constexpr uint32_t idesc = idesc_f16(2 * GM_BM, GM_BN / 2);
-            const uint64_t descA = smem_desc_sw128(sA);
-            Ring st, acc; uint32_t af_phase = 0; long long cur_m = -1;
-            long long m = n_rtiles ? t_begin / n_rtiles : 0; int rt = n_rtiles ? (int)(t_begin % n_rtiles) : 0;
-            for (long long tile = t_begin; tile < t_end; ++tile, ++rt) {
-                if (rt == n_rtiles) { rt = 0; ++m; }
-                if (m != cur_m) { mbar_wait(a_full, af_phase); mbar_wait_cluster(peer_a_full, af_phase); af_phase ^= 1; cur_m = m; }
+            // -------------------------------------------- MMA issuer: qh.rh only, `ksteps` K steps per 256 x 256 tile, two tiles per B stage
+            constexpr uint32_t idesc = idesc_f16(2 * GM_BM, GM_BN);
+            const uint64_t descA0 = smem_desc_sw128(sA), descA1 = smem_desc_sw128(sA + A_BYTES);
+            Ring st; uint32_t af_phase = 0, acc_phase = 0; long long cur_q = -1;
+            long long q = q_begin; int rt = rt_begin;
+            for (long long item = t_begin; item < t_end; ++item, ++rt) {
+                if (rt == n_rtiles) { rt = 0; ++q; }
+                if (q != cur_q) { mbar_wait(a_full, af_phase); mbar_wait_cluster(peer_a_full, af_phase); af_phase ^= 1; cur_q = q; }
                 mbar_wait(full_b + 8 * st.idx, st.phase);
                 mbar_wait_cluster(peer_full + 8 * st.idx, st.phase);
                 const uint64_t descB = smem_desc_sw128(sB + st.idx * G2_STAGE_BYTES);
-                const bool last_of_m = (tile + 1 == t_end) || (rt + 1 == n_rtiles);
+                const bool last_of_q = (item + 1 == t_end) || (rt + 1 == n_rtiles);
 #pragma unroll 1
-                for (int sub = 0; sub < 2; ++sub) {
-                    // sub-tile `sub`: rows [64 sub, 64 sub + 64) of each CTA's half of the B tile (8 KB into every 16 KB k-block)
-                    mbar_wait_cluster(tmem_empty + 8 * acc.idx, acc.phase ^ 1);
+                for (int a = 0; a < 2; ++a) {
+                    // nothing is acquired through this barrier ("the accumulator has been read"): a plain wait is enough
+                    mbar_wait(tmem_empty + 8 * a, acc_phase ^ 1);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + acc.idx * (GM_BN / 2);
-                    const uint64_t dB = descB + (uint64_t)(sub * ((GM_CHUNK_BYTES / 2) >> 4));
+                    const uint32_t d_tmem = tmem_base + a * GM_BN;
+                    const uint64_t dA = a ? descA1 : descA0;
                     if (elect_one()) {
                         for (int k = 0; k < ksteps; ++k) {
                             const uint64_t o = (uint64_t)((k >> 2) * (GM_CHUNK_BYTES >> 4) + (k & 3) * 2);
-                            umma2_f16(d_tmem, descA + o, dB + o, idesc, k > 0);
+                            umma2_f16(d_tmem, dA + o, descB + o, idesc, k > 0);
                         }
-                        tc_commit2(tmem_full + 8 * acc.idx);
-                        if (sub == 1) {
+                        tc_commit2(tmem_full + 8 * a);
+                        if (a == 1) {
                             tc_commit2(empty_b + 8 * st.idx);
-                            if (last_of_m) tc_commit2(a_empty);
+                            if (last_of_q) tc_commit2(a_empty);
                         }
                     }
                     __syncwarp();
-                    acc.advance(FR_ACC_BUFS);
                 }
+                acc_phase ^= 1;
                 st.advance(G2_STAGES);
             }
         } else {
             // -------------------------------------------- peer: forward "landed" to the leader
             const uint32_t r_peer_full = mapa_shared(peer_full, 0), r_peer_a = mapa_shared(peer_a_full, 0);
-            Ring st; uint32_t af_phase = 0; long long cur_m = -1;
-            long long m = n_rtiles ? t_begin / n_rtiles : 0; int rt = n_rtiles ? (int)(t_begin % n_rtiles) : 0;
-            for (long long tile = t_begin; tile < t_end; ++tile, ++rt) {
-                if (rt == n_rtiles) { rt = 0; ++m; }
-                if (m != cur_m) {
+            Ring st; uint32_t af_phase = 0; long long cur_q = -1;
+            long long q = q_begin; int rt = rt_begin;
+            for (long long item = t_begin; item < t_end; ++item, ++rt) {
+                if (rt == n_rtiles) { rt = 0; ++q; }
+                if (q != cur_q) {
                     mbar_wait(a_full, af_phase); af_phase ^= 1;
                     if (elect_one()) mbar_arrive_remote(r_peer_a);
                     __syncwarp();
-                    cur_m = m;
+                    cur_q = q;
                 }
                 mbar_wait(full_b + 8 * st.idx, st.phase);
                 if (elect_one()) mbar_arrive_remote(r_peer_full + 8 * st.idx);
@@ -1289,54 +1294,63 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
         const int half = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         const uint32_t r_tmem_empty = mapa_shared(tmem_empty, 0);
-        Ring acc;
+        uint32_t acc_phase = 0;
         uint32_t gidx[16];                                                 // group indices 0..15 in registers (see fr_key)
 #pragma unroll
         for (int i = 0; i < 16; ++i) gidx[i] = (uint32_t)(rt_zero + i);
-        float V1 = FR_NEG, V2 = FR_NEG; uint32_t T1 = 0, T2 = 0;           // running top-2 of the open segment, tile offsets
-        long long m = n_rtiles ? t_begin / n_rtiles : 0; int rt = n_rtiles ? (int)(t_begin % n_rtiles) : 0;
-        int sg = (t_begin < t_end) ? __ldg(tile_seg + rt) : 0;
-        int sg_t0 = (t_begin < t_end) ? __ldg(seg_tile0 + sg) : 0, sg_t1 = (t_begin < t_end) ? __ldg(seg_tile0 + sg + 1) : 0;
-        for (long long tile = t_begin; tile < t_end; ++tile, ++rt) {
-            if (rt == n_rtiles) { rt = 0; ++m; }
-            if (rt < sg_t0 || rt >= sg_t1) {                               // entered another segment (segments never span objects)
-                sg = __ldg(tile_seg + rt); sg_t0 = __ldg(seg_tile0 + sg); sg_t1 = __ldg(seg_tile0 + sg + 1);
-            }
+        // running top-2 of the open segment (key, tile offset) for each of the two query tiles
+        float V1[2] = {FR_NEG, FR_NEG}, V2[2] = {FR_NEG, FR_NEG}; uint32_t T1[2] = {0, 0}, T2[2] = {0, 0};
+        long long q = q_begin; int rt = rt_begin;
+        const bool any = t_begin < t_end;
+        int sg = any ? __ldg(tile_seg + rt) : 0;
+        int sg_t0 = any ? __ldg(seg_tile0 + sg) : 0, sg_t1 = any ? __ldg(seg_tile0 + sg + 1) : 0;
+        for (long long item = t_begin; item < t_end; ++item, ++rt) {
+            if (rt == n_rtiles) { rt = 0; ++q; }
+            // the next item's segment, fetched now (two dependent loads) and used an item later
+            int nrt = rt + 1; if (nrt == n_rtiles) nrt = 0;
+            const bool more = item + 1 < t_end;
+            const int nsg = more ? __ldg(tile_seg + nrt) : sg;
+            const int nsg_t0 = more ? __ldg(seg_tile0 + nsg) : 0, nsg_t1 = more ? __ldg(seg_tile0 + nsg + 1) : 0;
             const uint32_t toff = (uint32_t)(rt - sg_t0);
-            float M1 = FR_NEG, M2 = FR_NEG;
-#pragma unroll 1
-            for (int sub = 0; sub < 2; ++sub) {
-                // this warp's 64 columns of sub-tile `sub` are tile rows [128 half + 64 sub, +64): group index = 16 sub + g
-                mbar_wait(tmem_full + 8 * acc.idx, acc.phase);
+            const bool seg_ends = !more || nrt == 0 || nsg != sg;
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                mbar_wait(tmem_full + 8 * a, acc_phase);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc.idx * (GM_BN / 2) + half * (GM_BN / 4);
-                float c1, c2;
-                if (bias_in_acc) fr_unit_top2<true>(taddr, nullptr, gidx, c1, c2);
-                else fr_unit_top2<false>(taddr, reinterpret_cast<const float4*>(ysn + (size_t)rt * GM_BN + half * (GM_BN / 2) + sub * (GM_BN / 4)), gidx, c1, c2);
+                float M1 = FR_NEG, M2 = FR_NEG;
+#pragma unroll 1
+                for (int u = 0; u < 2; ++u) {
+                    // unit u = this warp's columns [64 u, 64 u + 64) of its half = tile rows [128 half + 64 u, +64): group 16 u + g
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * GM_BN + half * (GM_BN / 2) + u * (GM_BN / 4);
+                    float c1, c2;
+                    if (bias_in_acc) fr_unit_top2<true>(taddr, nullptr, gidx, c1, c2);
+                    else fr_unit_top2<false>(taddr, reinterpret_cast<const float4*>(ysn + (size_t)rt * GM_BN + half * (GM_BN / 2) + u * (GM_BN / 4)), gidx, c1, c2);
+                    const uint32_t ubit = (uint32_t)u << 4;
+                    c1 = __uint_as_float(__float_as_uint(c1) | ubit);
+                    c2 = __uint_as_float(__float_as_uint(c2) | ubit);
+                    const float t = fminf(M1, c1);
+                    M2 = fmaxf(fmaxf(M2, t), c2);
+                    M1 = fmaxf(M1, c1);
+                }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_remote_nofence(r_tmem_empty + 8 * acc.idx);
-                acc.advance(FR_ACC_BUFS);
-                const uint32_t sbit = (uint32_t)sub << 4;
-                c1 = __uint_as_float(__float_as_uint(c1) | sbit);
-                c2 = __uint_as_float(__float_as_uint(c2) | sbit);
-                const float t = fminf(M1, c1);
-                M2 = fmaxf(fmaxf(M2, t), c2);
-                M1 = fmaxf(M1, c1);
+                if (lane == 0) mbar_arrive_remote_nofence(r_tmem_empty + 8 * a);
+                // merge this tile's two best into the segment's
+                if (M1 > V1[a]) {
+                    if (M2 > V1[a]) { V2[a] = M2; T2[a] = toff; } else { V2[a] = V1[a]; T2[a] = T1[a]; }
+                    V1[a] = M1; T1[a] = toff;
+                } else if (M1 > V2[a]) { V2[a] = M1; T2[a] = toff; }
+                if (seg_ends) {
+                    const size_t e = ((size_t)sg * 2 + half) * (size_t)M_pad + (size_t)(4 * q + 2 * a + rank) * GM_BM + row;
+                    keys[e] = make_float2(V1[a], V2[a]);
+                    if (seg_tiles > 1) tags[e] = T1[a] | (T2[a] << 16);
+                    V1[a] = V2[a] = FR_NEG; T1[a] = T2[a] = 0;
+                }
             }
-            // merge this tile's two best into the segment's
-            if (M1 > V1) {
-                if (M2 > V1) { V2 = M2; T2 = toff; } else { V2 = V1; T2 = T1; }
-                V1 = M1; T1 = toff;
-            } else if (M1 > V2) { V2 = M1; T2 = toff; }
-            const bool seg_ends = (tile + 1 == t_end) || (rt + 1 >= sg_t1) || (rt + 1 - sg_t0 >= seg_tiles);
-            if (seg_ends) {
-                const size_t e = ((size_t)sg * 2 + half) * (size_t)M_pad + (size_t)(2 * m + rank) * GM_BM + row;
-                keys[e] = make_float2(V1, V2);
-                if (seg_tiles > 1) tags[e] = T1 | (T2 << 16);
-                V1 = V2 = FR_NEG; T1 = T2 = 0;
-            }
+            acc_phase ^= 1;
+            sg = nsg; sg_t0 = nsg_t0; sg_t1 = nsg_t1;
         }
+        (void)sg_t1;
     }
 
     tc_fence_before();
@@ -1347,7 +1361,7 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
-constexpr int FR_SMEM_TOTAL = 2 * GM_CHUNK_BYTES + G2_STAGES * G2_STAGE_BYTES + 256 + 1024;
+constexpr int FR_SMEM_TOTAL = 4 * GM_CHUNK_BYTES + G2_STAGES * G2_STAGE_BYTES + 256 + 1024;
 
 // ---- refinement
 struct FrParams {
@@ -1404,22 +1418,69 @@ __device__ __forceinline__ void fr_group_dist(const float* __restrict__ q32, con
     for (int k = 0; k < FR_GROUP_COLS; ++k) d[k] = s[k];
 }
 
-// exact minimum over the real rows of one segment-half for one query row, by a whole warp: lane l takes rows l, l+32, ...
-// of each 128-row half tile.  Returns the packed (distance, original index) minimum in every lane.
+// exact minimum over the real rows of (a column range of) one segment-half for one query row, by a whole warp: lane l takes
+// rows l, l+32, ... of each 128-row half tile.  The query row is staged in the warp's shared-memory slab `q_sm` (GM_MAXC
+// floats); a reference row is fetched with all of its loads in flight at once.  Returns the packed (distance, original
+// index) minimum in every lane.
 __device__ __forceinline__ unsigned long long fr_warp_rescan(const FrParams& P, int64_t qrow, int obj, int entry, int lane,
-                                                             int col0 = 0, int ncol = GM_BN / 2) {
+                                                             float* __restrict__ q_sm, int col0 = 0, int ncol = GM_BN / 2) {
     const int sg = entry >> 1, half = entry & 1;
     const int t0 = __ldg(P.seg_tile0 + sg), t1 = min(__ldg(P.seg_tile0 + sg + 1), t0 + P.seg_tiles);
     const int64_t end = (int64_t)P.ctrl->offsets[obj] + P.ctrl->counts[obj];
-    const float4* q = reinterpret_cast<const float4*>(P.q32 + (size_t)qrow * P.C4);
+    const int nc = P.C4 >> 2;                                           // float4 chunks per row (<= 32)
+    __syncwarp();
+    if (lane < nc) reinterpret_cast<float4*>(q_sm)[lane] = __ldg(reinterpret_cast<const float4*>(P.q32 + (size_t)qrow * P.C4) + lane);
+    __syncwarp();
+    const float4* q = reinterpret_cast<const float4*>(q_sm);
     unsigned long long best = fr_pack(INFINITY, 0x7fffffff);
     for (int rt = t0; rt < t1; ++rt) {
         for (int j = col0 + lane; j < col0 + ncol; j += 32) {
             const int64_t pos = (int64_t)rt * GM_BN + half * (GM_BN / 2) + j;
             if (pos >= end) continue;
             const float4* r = reinterpret_cast<const float4*>(P.r32 + (size_t)pos * P.C4);
-            // same summation order as fr_pair_dist (eight interleaved partial sums, pairwise tree): a pair's distance has ONE
-            // value whichever path evaluates it, so results do not depend on the order of the reference pixels
+            const int sidx = __ldg(P.src_idx + pos);
+            // same summation order as fr_group_dist (eight interleaved partial sums over chunks c = u, u+8, ..., pairwise tree):
+            // a pair's distance has ONE value whichever path evaluates it, so results do not depend on the reference order
+            float p[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 16) {
+                float4 a[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) a[u] = (c0 + u < nc) ? __ldg(r + c0 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    if (c0 + u < nc) {
+                        const float4 x = q[c0 + u];
+                        float t;
+                        t = x.x - a[u].x; p[u & 7] = fmaf(t, t, p[u & 7]); t = x.y - a[u].y; p[u & 7] = fmaf(t, t, p[u & 7]);
+                        t = x.z - a[u].z; p[u & 7] = fmaf(t, t, p[u & 7]); t = x.w - a[u].w; p[u & 7] = fmaf(t, t, p[u & 7]);
+                    }
+                }
+            }
+            const float sum = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+            const unsigned long long v = fr_pack(sum, sidx);
+            best = v < best ? v : best;
+        }
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, sft); best = o < best ? o : best; }
+    return best;
+}
+
+// gm_refine_kernel's overflow path (taken only when the rescan list is full): the same scan with a small register budget
+// (eight chunks per batch, operands straight from global memory) -- it must not set the register count of that kernel.
+// Same summation order, hence the same values, as fr_warp_rescan / fr_group_dist.
+__device__ __forceinline__ unsigned long long fr_warp_rescan_cold(const FrParams& P, int64_t qrow, int obj, int entry, int lane) {
+    const int sg = entry >> 1, half = entry & 1;
+    const int t0 = __ldg(P.seg_tile0 + sg), t1 = min(__ldg(P.seg_tile0 + sg + 1), t0 + P.seg_tiles);
+    const int64_t end = (int64_t)P.ctrl->offsets[obj] + P.ctrl->counts[obj];
+    const float4* q = reinterpret_cast<const float4*>(P.q32 + (size_t)qrow * P.C4);
+    unsigned long long best = fr_pack(INFINITY, 0x7fffffff);
+    for (int rt = t0; rt < t1; ++rt) {
+        for (int j = lane; j < GM_BN / 2; j += 32) {
+            const int64_t pos = (int64_t)rt * GM_BN + half * (GM_BN / 2) + j;
+            if (pos >= end) continue;
+            const float4* r = reinterpret_cast<const float4*>(P.r32 + (size_t)pos * P.C4);
             float p[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             for (int c0 = 0; c0 < (P.C4 >> 2); c0 += 8) {
 #pragma unroll
@@ -1432,8 +1493,8 @@ __device__ __forceinline__ unsigned long long fr_warp_rescan(const FrParams& P, 
                     }
                 }
             }
-            const float s = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
-            const unsigned long long v = fr_pack(s, __ldg(P.src_idx + pos));
+            const float sum = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+            const unsigned long long v = fr_pack(sum, __ldg(P.src_idx + pos));
             best = v < best ? v : best;
         }
     }
@@ -1463,7 +1524,9 @@ __device__ __forceinline__ void fr_merge(const FrParams& P, int64_t i, unsigned 
 __global__ void __launch_bounds__(256)
 gm_refine_kernel(const FrParams P) {
     pdl_enter();
-    const int lane = threadIdx.x & 31;
+    __shared__ float res_d[8][32][FR_GROUP_COLS];                        // exact distances / original indices of a served lane's group
+    __shared__ int res_i[8][32][FR_GROUP_COLS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t row0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;
     const int obj = blockIdx.y;
     if (row0 >= P.M) return;
@@ -1532,7 +1595,7 @@ gm_refine_kernel(const FrParams P) {
                 unsigned over = __ballot_sync(0xffffffffu, need);
                 while (over) {
                     const int src = __ffs(over) - 1;
-                    const unsigned long long v = fr_warp_rescan(P, row0 + src, obj, e, lane);
+                    const unsigned long long v = fr_warp_rescan_cold(P, row0 + src, obj, e, lane);
                     if (lane == src) best = v < best ? v : best;
                     over &= over - 1;
                 }
@@ -1576,18 +1639,21 @@ gm_refine_kernel(const FrParams P) {
                 for (int k = 1; k < FR_GROUP_COLS; ++k) sidx[k] = __shfl_sync(0xffu << (lane & 24), sidx[0], (lane & 24) + k);
                 sidx[0] = __shfl_sync(0xffu << (lane & 24), sidx[0], lane & 24);
             }
-            // hand the results to their owners: every lane asks each quarter's first lane whom it served
+            // hand the results to their owners through the warp's shared-memory slab
+            if (src >= 0 && (lane & 7) == 0) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int who = __shfl_sync(0xffffffffu, src, 8 * q);
-#pragma unroll
-                for (int k = 0; k < FR_GROUP_COLS; ++k) {
-                    const float rk = __shfl_sync(0xffffffffu, d[k], 8 * q);
-                    const int ik = __shfl_sync(0xffffffffu, sidx[k], 8 * q);
-                    if (who == lane && rk < INFINITY) { const unsigned long long v = fr_pack(rk, ik); best = v < best ? v : best; }
-                }
+                for (int k = 0; k < FR_GROUP_COLS; ++k) { res_d[wid][src][k] = d[k]; res_i[wid][src][k] = sidx[k]; }
             }
         }
+        __syncwarp();
+        if (ncand > ci) {
+#pragma unroll
+            for (int k = 0; k < FR_GROUP_COLS; ++k) {
+                const float rk = res_d[wid][lane][k];
+                if (rk < INFINITY) { const unsigned long long v = fr_pack(rk, res_i[wid][lane][k]); best = v < best ? v : best; }
+            }
+        }
+        __syncwarp();
     }
     if (valid) fr_store(P, row * P.N + obj, best);
 }
@@ -1596,13 +1662,14 @@ gm_refine_kernel(const FrParams P) {
 __global__ void __launch_bounds__(256)
 gm_rescan_kernel(const FrParams P) {
     pdl_enter();
+    __shared__ __align__(16) float q_slab[8][GM_MAXC];
     const int lane = threadIdx.x & 31;
     const int n = min(P.ctrl->rescan_count, P.rescan_cap);
     const int nwarps = gridDim.x * 8;
     for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < 4 * n; i += nwarps) {
         const int4 it = P.rescan[i >> 2];
         const int64_t row = (int64_t)(unsigned)it.x | ((int64_t)it.w << 31);
-        const unsigned long long v = fr_warp_rescan(P, row, it.y, it.z, lane, (i & 3) * 32, 32);
+        const unsigned long long v = fr_warp_rescan(P, row, it.y, it.z, lane, q_slab[threadIdx.x >> 5], (i & 3) * 32, 32);
         if (lane == 0) fr_merge(P, row * P.N + it.y, v);
     }
 }
@@ -1642,7 +1709,7 @@ constexpr int FR_RESCAN_CAP = 1 << 20;
 
 static GmPlan gm_plan(int64_t M, int64_t R, int N, int C) {
     GmPlan p;
-    p.M_pad = ceil_div64(M > 0 ? M : 1, 2 * GM_BM) * (2 * GM_BM);   // CTA pairs own 256 query rows
+    p.M_pad = ceil_div64(M > 0 ? M : 1, 4 * GM_BM) * (4 * GM_BM);   // CTA pairs own 256 query rows; the filter engine works on quads of 512
     p.n_mtiles = (int)(p.M_pad / GM_BM);
     p.R_pad_max = ceil_div64((R > 0 ? R : 1) + (int64_t)N * (GM_BN - 1), GM_BN) * GM_BN;
     p.max_rtiles = (int)(p.R_pad_max / GM_BN);
@@ -1773,7 +1840,7 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
         profile_begin(PROF_GLOBAL_UMMA, stream);
         launch_k(gm_fr_kernel, dim3(sm_count & ~1), dim3(GM_THREADS), (size_t)FR_SMEM_TOTAL, stream, (const uint8_t*)Aimg, (const uint8_t*)Bimg,
                  (const float*)ysn, (const int*)pre.tile_seg, (const int*)pre.seg_tile0, (const GmCtrl*)ctrl,
-                 reinterpret_cast<float2*>(wbase + p.off_keys), reinterpret_cast<uint32_t*>(wbase + p.off_tags), p.M_pad, p.n_mtiles / 2,
+                 reinterpret_cast<float2*>(wbase + p.off_keys), reinterpret_cast<uint32_t*>(wbase + p.off_tags), p.M_pad, p.n_mtiles / 4,
                  ksteps, p.seg_tiles, 0);
         profile_end(PROF_GLOBAL_UMMA, stream);
         profile_begin(PROF_GLOBAL_REFINE, stream);
