@@ -1388,12 +1388,14 @@ __device__ __forceinline__ void fr_group_dist(const float* __restrict__ q32, con
     // the kernel is a chain of dependent L2 round trips: all ten loads of two chunk iterations go out before the arithmetic
     // (chunks sub, sub+8 | sub+16, sub+24: the summation order is what fr_warp_rescan reproduces)
     for (int c = sub; c < nc; c += 16) {
+        // UNCONDITIONAL loads (the second chunk's index is clamped, its contribution masked): predicated loads were issued
+        // one by one, each waiting for the previous one's use
         const bool two = c + 8 < nc;
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 x0 = __ldg(q + c), x1 = two ? __ldg(q + c + 8) : z;
+        const int c2 = two ? c + 8 : nc - 1;
+        const float4 x0 = __ldg(q + c), x1 = __ldg(q + c2);
         float4 a0[FR_GROUP_COLS], a1[FR_GROUP_COLS];
 #pragma unroll
-        for (int k = 0; k < FR_GROUP_COLS; ++k) { a0[k] = __ldg(r + (size_t)k * nc + c); a1[k] = two ? __ldg(r + (size_t)k * nc + c + 8) : z; }
+        for (int k = 0; k < FR_GROUP_COLS; ++k) { a0[k] = __ldg(r + (size_t)k * nc + c); a1[k] = __ldg(r + (size_t)k * nc + c2); }
 #pragma unroll
         for (int k = 0; k < FR_GROUP_COLS; ++k) {
             float t;
@@ -1444,9 +1446,9 @@ __device__ __forceinline__ unsigned long long fr_warp_rescan(const FrParams& P, 
             float p[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c0 = 0; c0 < 32; c0 += 16) {
-                float4 a[16];
+                float4 a[16];                                            // unconditional loads (clamped index): all in flight at once
 #pragma unroll
-                for (int u = 0; u < 16; ++u) a[u] = (c0 + u < nc) ? __ldg(r + c0 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int u = 0; u < 16; ++u) a[u] = __ldg(r + min(c0 + u, nc - 1));
 #pragma unroll
                 for (int u = 0; u < 16; ++u) {
                     if (c0 + u < nc) {
@@ -1521,7 +1523,7 @@ __device__ __forceinline__ void fr_merge(const FrParams& P, int64_t i, unsigned 
 }
 
 // one warp = 32 consecutive query rows x one object
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 gm_refine_kernel(const FrParams P) {
     pdl_enter();
     __shared__ float res_d[8][32][FR_GROUP_COLS];                        // exact distances / original indices of a served lane's group
