@@ -188,6 +188,16 @@ gm_scan_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64_t 
         }
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         int c = c_begin;
+        // sixteen loads in flight per thread: the pass is a handful of memory round trips, not a bandwidth problem
+        for (; c + 16 <= c_end; c += 16) {
+            float v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = __ldg(p + (int64_t)(c + u) * cs);
+#pragma unroll
+            for (int u = 0; u < 16; u += 4) {
+                a0 = fmaxf(a0, fabsf(v[u])); a1 = fmaxf(a1, fabsf(v[u + 1])); a2 = fmaxf(a2, fabsf(v[u + 2])); a3 = fmaxf(a3, fabsf(v[u + 3]));
+            }
+        }
         for (; c + 4 <= c_end; c += 4) {
             a0 = fmaxf(a0, fabsf(__ldg(p + (int64_t)c * cs)));
             a1 = fmaxf(a1, fabsf(__ldg(p + (int64_t)(c + 1) * cs)));
@@ -367,10 +377,17 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
     for (int kb = 0; kb * 64 < C; ++kb) {
         __syncthreads();                                   // pos_s ready / previous slab consumed
         const float* sp = src + (p0 + px) * ps;
-#pragma unroll 8
-        for (int c = chalf; c < 64; c += 2) {
-            const int ch = kb * 64 + c;
-            tile[c][px] = (px_ok && ch < C) ? __ldg(sp + (int64_t)ch * cs) : 0.f;
+        {
+            // the slab's 32 loads of this thread all go out before the first shared-memory store (latency, not bandwidth,
+            // bounds this kernel: its grid is a single wave)
+            float v[32];
+#pragma unroll
+            for (int u = 0; u < 32; ++u) {
+                const int ch = kb * 64 + chalf + 2 * u;
+                v[u] = (px_ok && ch < C) ? __ldg(sp + (int64_t)ch * cs) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 32; ++u) tile[chalf + 2 * u][px] = v[u];
         }
         __syncthreads();
 #pragma unroll
@@ -1402,13 +1419,14 @@ __device__ __forceinline__ void fr_group_dist(const float* __restrict__ q32, con
             t = x0.x - a0[k].x; s[k] = fmaf(t, t, s[k]); t = x0.y - a0[k].y; s[k] = fmaf(t, t, s[k]);
             t = x0.z - a0[k].z; s[k] = fmaf(t, t, s[k]); t = x0.w - a0[k].w; s[k] = fmaf(t, t, s[k]);
         }
-        if (two) {
+        // no branch around the second chunk (a branch lets the compiler sink its loads next to their use): a masked-out chunk
+        // contributes (a - a)^2 = 0
 #pragma unroll
-            for (int k = 0; k < FR_GROUP_COLS; ++k) {
-                float t;
-                t = x1.x - a1[k].x; s[k] = fmaf(t, t, s[k]); t = x1.y - a1[k].y; s[k] = fmaf(t, t, s[k]);
-                t = x1.z - a1[k].z; s[k] = fmaf(t, t, s[k]); t = x1.w - a1[k].w; s[k] = fmaf(t, t, s[k]);
-            }
+        for (int k = 0; k < FR_GROUP_COLS; ++k) {
+            const float4 y = two ? x1 : a1[k];
+            float t;
+            t = y.x - a1[k].x; s[k] = fmaf(t, t, s[k]); t = y.y - a1[k].y; s[k] = fmaf(t, t, s[k]);
+            t = y.z - a1[k].z; s[k] = fmaf(t, t, s[k]); t = y.w - a1[k].w; s[k] = fmaf(t, t, s[k]);
         }
     }
 #pragma unroll
@@ -1451,12 +1469,11 @@ __device__ __forceinline__ unsigned long long fr_warp_rescan(const FrParams& P, 
                 for (int u = 0; u < 16; ++u) a[u] = __ldg(r + min(c0 + u, nc - 1));
 #pragma unroll
                 for (int u = 0; u < 16; ++u) {
-                    if (c0 + u < nc) {
-                        const float4 x = q[c0 + u];
-                        float t;
-                        t = x.x - a[u].x; p[u & 7] = fmaf(t, t, p[u & 7]); t = x.y - a[u].y; p[u & 7] = fmaf(t, t, p[u & 7]);
-                        t = x.z - a[u].z; p[u & 7] = fmaf(t, t, p[u & 7]); t = x.w - a[u].w; p[u & 7] = fmaf(t, t, p[u & 7]);
-                    }
+                    // branch-free: a chunk beyond the row contributes (a - a)^2 = 0 (q_sm holds GM_MAXC floats, reads stay inside)
+                    const float4 x = (c0 + u < nc) ? q[c0 + u] : a[u];
+                    float t;
+                    t = x.x - a[u].x; p[u & 7] = fmaf(t, t, p[u & 7]); t = x.y - a[u].y; p[u & 7] = fmaf(t, t, p[u & 7]);
+                    t = x.z - a[u].z; p[u & 7] = fmaf(t, t, p[u & 7]); t = x.w - a[u].w; p[u & 7] = fmaf(t, t, p[u & 7]);
                 }
             }
             const float sum = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
@@ -1523,7 +1540,7 @@ __device__ __forceinline__ void fr_merge(const FrParams& P, int64_t i, unsigned 
 }
 
 // one warp = 32 consecutive query rows x one object
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 gm_refine_kernel(const FrParams P) {
     pdl_enter();
     __shared__ float res_d[8][32][FR_GROUP_COLS];                        // exact distances / original indices of a served lane's group

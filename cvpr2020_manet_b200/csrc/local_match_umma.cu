@@ -676,34 +676,50 @@ lm_umma_kernel(const LmParams P) {
 #ifdef LM_TRACE
         tr_e1 = clock64() - tr0;
 #endif
-        for (int q = 0; q < n_stages; ++q) {
-            const int kb = q % nkb, hf = (q / nkb) & 1, c = q / (2 * nkb);
-            const int buf = c & 1, sl = q % nst, use = q / nst;
-            if (kb == 0 && hf == 0) { TR(tr_w1, mbar_wait_sleep(tmem_empty + 8 * buf, ((c >> 1) & 1) ^ 1)); }
-            TR(tr_w2, mbar_wait_sleep(b_full + 8 * sl, use & 1));
+        // One unit = (row chunk c, row pair hf) = nkb consecutive ring stages.  ORDER MATTERS FOR ACCURACY: the tensor core
+        // adds into its fp32 accumulator with truncation, and each of those truncations is relative to the accumulator's
+        // magnitude at that moment.  The three small products (ql.ph, qh.pl, ql.pl: 2^-11 of the result) are therefore
+        // issued FIRST, for all K steps of the unit, while the accumulator is still tiny; only the qh.ph steps -- 7 of the
+        // unit's 28 MMAs -- run at full magnitude.  (Interleaved per K step, as before, all 28 did.)
+        for (int u = 0; u < n_stages / nkb; ++u) {
+            const int q0 = u * nkb, hf = u & 1, c = u >> 1;
+            const int buf = c & 1;
+            if (hf == 0) { TR(tr_w1, mbar_wait_sleep(tmem_empty + 8 * buf, ((c >> 1) & 1) ^ 1)); }
+            for (int kb = 0; kb < nkb; ++kb) { TR(tr_w2, mbar_wait_sleep(b_full + 8 * ((q0 + kb) % nst), ((q0 + kb) / nst) & 1)); }
             tc_fence_after();
 #ifdef LM_TRACE
-            if (q == 0) tr_e2 = clock64() - tr0;
-            if (q == 1) tr_e3 = clock64() - tr0;
+            if (u == 0) tr_e2 = clock64() - tr0;
+            if (u == 1) tr_e3 = clock64() - tr0;
 #endif
             const uint32_t d_tmem = tmem_base + buf * 256 + hf * 2 * WB;
-            const uint64_t dB_hi = smem_desc_sw128(base + G.off_B + sl * stage_bytes);
-            const uint64_t dB_lo = smem_desc_sw128(base + G.off_B + sl * stage_bytes + 2 * row_bytes);
-            const int ks = min(ksteps - 4 * kb, 4);
-            const uint32_t a_off = (uint32_t)(kb * 32);
             if (elect_one()) {
-                for (int k = 0; k < ks; ++k) {
-                    const uint64_t o = (uint64_t)(2 * k);
-                    const uint32_t ac = a_off + 8u * (uint32_t)k;
-                    umma_f16_ts(d_tmem, tA_hi + ac, dB_hi + o, idesc, (kb | k) ? 1u : 0u);
-                    umma_f16_ts(d_tmem, tA_lo + ac, dB_hi + o, idesc, 1u);
-                    umma_f16_ts(d_tmem, tA_hi + ac, dB_lo + o, idesc, 1u);
+                uint32_t acc = 0u;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const int sl = (q0 + kb) % nst;
+                    const uint64_t dB_hi = smem_desc_sw128(base + G.off_B + sl * stage_bytes);
+                    const uint64_t dB_lo = smem_desc_sw128(base + G.off_B + sl * stage_bytes + 2 * row_bytes);
+                    const int ks = min(ksteps - 4 * kb, 4);
+                    const uint32_t a_off = (uint32_t)(kb * 32);
+                    for (int k = 0; k < ks; ++k) {
+                        const uint64_t o = (uint64_t)(2 * k);
+                        const uint32_t ac = a_off + 8u * (uint32_t)k;
 #ifndef LM_DROP_LOLO
-                    umma_f16_ts(d_tmem, tA_lo + ac, dB_lo + o, idesc, 1u);
+                        umma_f16_ts(d_tmem, tA_lo + ac, dB_lo + o, idesc, acc); acc = 1u;
 #endif
+                        umma_f16_ts(d_tmem, tA_lo + ac, dB_hi + o, idesc, acc); acc = 1u;
+                        umma_f16_ts(d_tmem, tA_hi + ac, dB_lo + o, idesc, 1u);
+                    }
                 }
-                tc_commit(b_empty + 8 * sl);
-                if (kb == nkb - 1) tc_commit(tmem_full + 16 * buf + 8 * hf);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const int sl = (q0 + kb) % nst;
+                    const uint64_t dB_hi = smem_desc_sw128(base + G.off_B + sl * stage_bytes);
+                    const int ks = min(ksteps - 4 * kb, 4);
+                    const uint32_t a_off = (uint32_t)(kb * 32);
+                    for (int k = 0; k < ks; ++k)
+                        umma_f16_ts(d_tmem, tA_hi + a_off + 8u * (uint32_t)k, dB_hi + (uint64_t)(2 * k), idesc, 1u);
+                    tc_commit(b_empty + 8 * sl);
+                }
+                tc_commit(tmem_full + 16 * buf + 8 * hf);
             }
             __syncwarp();
         }

@@ -14,4 +14,4 @@ except Exception as e:
     print('parse failed',e); print(open('gpurun_out/bench.log').read()[-3000:])
 PY
 timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:"gm_fr_kernel|gm_refine_kernel|gm_rescan_kernel" -s 6 -c 3 -f -o gpurun_out/r02_gm_fr2 python scripts/gm_once.py 4 > gpurun_out/ncu_gm.log 2>&1; echo "ncu rc=$?"; tail -2 gpurun_out/ncu_gm.log
-timeout -s KILL 120 python scripts/gm_reuse_probe.py 2>&1 | tail -3
+timeout -s KILL 120 python scripts/gm_reuse_probe.py 2>&1 | tail -3; timeout -s KILL 200 python scripts/lm_error_vs_g.py gpurun_out/r02_lm_error_vs_g.json 2>&1 | tail -14
