@@ -1582,7 +1582,6 @@ gm_refine_kernel(const FrParams P) {
     const float thr = V - delta;
     // candidates: up to two per lane are evaluated here, everything else goes to the rescan list
     int cand0 = 0, cand1 = 0, ncand = 0;
-    int inline_budget = 6;                                              // warp-uniform
     unsigned long long best = fr_pack(INFINITY, 0x7fffffff);
     for (int eb = e0; eb < e1; eb += FR_BATCH) {
         float2 kk[FR_BATCH]; uint32_t tg[FR_BATCH];
@@ -1604,17 +1603,9 @@ gm_refine_kernel(const FrParams P) {
                 if (ncand == 0) cand0 = cd; else cand1 = cd;
                 ++ncand;
             }
-            unsigned mask = __ballot_sync(0xffffffffu, need);
-            // A few near-ties per warp are the normal case (about one segment half in 150 at 480p): they are rescanned right here
-            // by the whole warp.  Only a warp that keeps finding them -- heavily tied data -- hands the rest to the work list,
-            // where every entry gets four warps of gm_rescan_kernel.
-            while (mask && inline_budget > 0) {
-                const int src = __ffs(mask) - 1;
-                const unsigned long long v = fr_warp_rescan_cold(P, row0 + src, obj, e, lane);
-                if (lane == src) { best = v < best ? v : best; need = false; }
-                mask &= mask - 1;
-                --inline_budget;
-            }
+            // (rescanning the occasional near-tie right here, by the whole warp, was tried: the 31 idle lanes' wait made the
+            // kernel 50 us slower than handing the entries to gm_rescan_kernel, which costs 19 us in all)
+            const unsigned mask = __ballot_sync(0xffffffffu, need);
             if (mask) {
                 int base = 0;
                 if (lane == 0) base = atomicAdd(&P.ctrl->rescan_count, __popc(mask));
