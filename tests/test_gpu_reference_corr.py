@@ -31,6 +31,9 @@ CASES = [  # B, C, H, W, pad, kernel, max_disp, stride1, stride2
     (2, 16, 21, 19, 6, 1, 6, 1, 2),
     (1, 8, 24, 32, 4, 1, 4, 2, 2),
     (2, 5, 9, 11, 0, 1, 0, 1, 1),
+    (2, 16, 23, 45, 3, 1, 5, 1, 1),       # fast path (k = 1, strides 1, C % 4 == 0) with pad != max_displacement, ragged tiles
+    (1, 64, 17, 70, 7, 1, 7, 1, 1),       # fast path, even number of 16-byte words per pixel (padded shared-memory pitch)
+    (1, 128, 12, 33, 16, 1, 16, 1, 1),    # fast path at its limits: C = 128, max_displacement = 16
 ]
 
 
