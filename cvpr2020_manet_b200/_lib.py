@@ -19,6 +19,7 @@ GM_DROP_UNLAB = 2
 GM_ENGINE_SIMT = 4
 GM_ENGINE_EXACT3 = 8
 GM_REUSE_REF = 128
+GM_ENGINE_FR = 512
 LM_ENGINE_SIMT = 1
 LM_ENGINE_TENSOR = 2
 STEP_SERIAL = 16

@@ -27,7 +27,7 @@ int check_launch(const char* what);       // cudaGetLastError() -> code (+ messa
 
 // Optional per-kernel timing (bench.py's roofline leg): when enabled, launchers bracket the named
 // kernel with cudaEvents taken from a pool; see manet_profile_* in include/manet_b200.h.
-enum ProfileSlot { PROF_GLOBAL_UMMA = 0, PROF_LOCAL_WINDOW = 1, PROF_LOCAL_MIN = 2, PROF_GLOBAL_REFINE = 3, PROF_GLOBAL_RESCAN = 4, PROF_GLOBAL_PREPASS = 5, PROF_SLOTS = 6 };
+enum ProfileSlot { PROF_GLOBAL_UMMA = 0, PROF_LOCAL_WINDOW = 1, PROF_LOCAL_MIN = 2, PROF_GLOBAL_REFINE = 3, PROF_GLOBAL_RESCAN = 4, PROF_GLOBAL_PREPASS = 5, PROF_GLOBAL_EXACT3 = 6, PROF_SLOTS = 7 };
 void count_launch();                       // every launcher bumps this once per kernel launch (manet_profile_launch_count)
 void profile_begin(int slot, cudaStream_t stream);
 void profile_end(int slot, cudaStream_t stream);

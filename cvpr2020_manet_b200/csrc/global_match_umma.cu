@@ -66,7 +66,16 @@ struct GmCtrl {
     unsigned rsq_max_bits[GM_MAXN]; // ... of |r|^2 (unscaled; the bias bound is s_q s_r / 2 times this)
     int seg_first[GM_MAXN + 1];    // first segment of each object (a segment = seg_tiles consecutive 256-row tiles of one object)
     int n_segs;
+    int engine;                    // which kernel chain serves this reference set: GM_ENG_FR or GM_ENG_EXACT3 (decided by the pre-pass)
 };
+// The filter-and-refine engine pays a fixed ~80 us at 480p for its refinement (proportional to queries x objects, independent
+// of the reference set) and saves ~0.95 us per 256-reference tile on the GEMM: measured break-even ~85 tiles (22 000 labelled
+// reference pixels).  Scribble references (rounds >= 2 of an interactive session: 10^2..10^3 labelled pixels, the count is
+// only known on the device because unlabelled pixels are dropped there) are served by the three-product kernel, dense
+// references (first round, 1080p memory frames) by filter-and-refine.  Both chains are enqueued; the one that is not
+// needed exits at once.
+constexpr int GM_ENG_FR = 0, GM_ENG_EXACT3 = 1;
+constexpr int FR_MIN_TILES = 85;
 constexpr size_t GM_CTRL_FRAME_BYTES = 16;      // the per-call prefix of GmCtrl
 
 
@@ -252,7 +261,8 @@ constexpr int GM_CV_PIX = 128;
 struct GmFrPre {
     float* q32; float* r32; float2* qn; int* src_idx; int* tile_seg; int* seg_tile0;
     float* rsq;                    // |r|^2 of every bucketed reference row: lets a later call rebuild the bias for a new query scale
-    int C4; int seg_tiles; int skip_lo;
+    int C4; int seg_tiles;
+    int force_engine;              // -1: the pre-pass decides from the number of reference tiles; else GM_ENG_*
     int reuse;                     // MANET_GM_REUSE_REF: the reference side of the workspace is valid; convert the query, refresh the bias
 };
 __global__ void __launch_bounds__(256)
@@ -277,6 +287,10 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
     if (t < GM_MAXN) { bcnt[t] = 0; omax[0][t] = omax[1][t] = omax[2][t] = 0u; }
     if (t < GM_CV_PIX) { rowsq[t] = rowh[t] = rowl[t] = 0.f; pos_s[t] = -1; lab_s[t] = -1; }
     __syncthreads();
+    // engine of this call (uniform over the grid: a function of the label histogram, which the scan kernel completed)
+    const int eng = fr.q32 == nullptr ? GM_ENG_EXACT3 : fr.force_engine >= 0 ? fr.force_engine : fr.reuse ? ctrl->engine
+                                      : (off[N] / GM_BN >= FR_MIN_TILES ? GM_ENG_FR : GM_ENG_EXACT3);
+    const bool fr_on = eng == GM_ENG_FR, skip_lo = fr_on;
     const float s_q = pow2_scale(ctrl->absmax_q_bits);
     const float s_r = pow2_scale(ctrl->absmax_r_bits);
     const int nchunks = ((C + 15) / 16) * 2;
@@ -289,10 +303,10 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
         if (t == 0) { ctrl->scale_q = s_q; ctrl->bias_fold = bias.on ? 1 : 0; }
     } else if (b == 0) {
         if (t <= N) ctrl->offsets[t] = off[t];
-        if (t == 0) { ctrl->n_rtiles = off[N] / GM_BN; ctrl->scale_q = s_q; ctrl->scale_r = s_r; ctrl->bias_fold = bias.on ? 1 : 0; }
+        if (t == 0) { ctrl->n_rtiles = off[N] / GM_BN; ctrl->scale_q = s_q; ctrl->scale_r = s_r; ctrl->bias_fold = bias.on ? 1 : 0; ctrl->engine = eng; }
         for (int o = 0; o < N; ++o)
             for (int tl = off[o] / GM_BN + t; tl < off[o + 1] / GM_BN; tl += 256) tile_obj[tl] = o;
-        if (fr.tile_seg != nullptr) {
+        if (fr_on) {
             // segments: runs of fr.seg_tiles consecutive tiles of one object; tile -> segment, segment -> first tile
             const int S = fr.seg_tiles;
             int s0 = 0;
@@ -338,7 +352,7 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
             const uint4 z = make_uint4(0, 0, 0, 0);
             for (int j = 0; j < nchunks; ++j) {
                 *reinterpret_cast<uint4*>(Bimg + image_chunk_offset(pos, 0, j)) = z;
-                if (!fr.skip_lo) *reinterpret_cast<uint4*>(Bimg + image_chunk_offset(pos, 1, j)) = z;
+                if (!skip_lo) *reinterpret_cast<uint4*>(Bimg + image_chunk_offset(pos, 1, j)) = z;
             }
             ysn[pos] = -3.0e38f;                             // finite: the filter engine ORs index bits into the sum (no NaNs)
             if (bias.on) {                                  // columns 12..15 of the folded step: v1..v4
@@ -367,7 +381,7 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
         if (keep) {
             pos_s[t] = (int64_t)off[lab] + bbase[lab] + rank;
             lab_s[t] = lab;
-            if (fr.src_idx != nullptr) fr.src_idx[pos_s[t]] = (int)(p0 + t);
+            if (fr_on) fr.src_idx[pos_s[t]] = (int)(p0 + t);
         }
     } else if (t < GM_CV_PIX && p0 + t < M_pad) {
         pos_s[t] = p0 + t;
@@ -403,7 +417,7 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
             sq += __shfl_xor_sync(0xffffffffu, sq, 2);
             sq += __shfl_xor_sync(0xffffffffu, sq, 4);
             const int64_t pos = pos_s[row];
-            if (fr.q32 != nullptr) {
+            if (fr_on) {
                 // |hi|^2 and |lo|^2 of this row (scaled units) and the exact fp32 copy, 32 contiguous bytes per thread
                 float hs = 0.f, ls = 0.f;
 #pragma unroll
@@ -448,7 +462,7 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
                     split8(v, scale, hi, lo);
                 }
                 *reinterpret_cast<uint4*>(img + image_chunk_offset(pos, 0, j)) = hi;
-                if (!fr.skip_lo) *reinterpret_cast<uint4*>(img + image_chunk_offset(pos, 1, j)) = lo;
+                if (!skip_lo) *reinterpret_cast<uint4*>(img + image_chunk_offset(pos, 1, j)) = lo;
             }
             if (chk == 0) rowsq[row] += sq;                // one lane per row and slab: no race
         }
@@ -460,7 +474,7 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
         if (is_ref) {
             const float bval = -0.5f * (s_q * s_r) * rowsq[t];
             ysn[pos] = bval;
-            if (fr.rsq != nullptr) fr.rsq[pos] = rowsq[t];
+            if (fr.rsq != nullptr) fr.rsq[pos] = rowsq[t];      // kept for either engine: a reusing call rebuilds the bias from it
             // three-piece fp16 split of the bias against the weights c1 > c2 > c3 (each step is exact in fp32)
             const __half v1 = __float2half_rn(bval / bias.c1);
             const float r1 = bval - bias.c1 * __half2float(v1);
@@ -474,7 +488,7 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
         }
         if (bias.on)
             *reinterpret_cast<uint2*>(img + image_chunk_offset(pos, 0, j_fold + 1) + 8) = *reinterpret_cast<uint2*>(v);
-        if (fr.q32 != nullptr) {
+        if (fr_on) {
             // upper bounds (rounded up a little: they enter an error bound) of |hi|_2 and |lo|_2
             const float nh = sqrtf(rowh[t]) * 1.000001f, nl = sqrtf(rowl[t]) * 1.000001f;
             if (is_ref) {
@@ -487,7 +501,7 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
             }
         }
     }
-    if (fr.q32 != nullptr && is_ref) {
+    if (fr_on && is_ref) {
         __syncthreads();
         if (t < N) {
             if (omax[0][t]) atomicMax(&ctrl->rh_max_bits[t], omax[0][t]);
@@ -680,6 +694,7 @@ gm_umma2_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bi
                 const int* __restrict__ tile_obj, const GmCtrl* __restrict__ ctrl, int* __restrict__ best,
                 int n_mpairs, int N, int ksteps, int ksteps_lo) {
     pdl_enter();
+    if (ctrl->engine != GM_ENG_EXACT3) return;          // this reference set is served by the filter-and-refine chain (uniform over the grid)
 #ifdef GM_TRACE
     long long tr_wait_full = 0, tr_epi = 0, tr_mma_wait_acc = 0, tr_mma_wait_b = 0, tr_total = clock64();
 #endif
@@ -1067,6 +1082,7 @@ __global__ void gm_finalize_kernel(const int* __restrict__ best, const float* __
                                    const GmCtrl* __restrict__ ctrl, int64_t M, int N, int normalize,
                                    float* __restrict__ mem, float* __restrict__ out) {
     pdl_enter();
+    if (ctrl->engine != GM_ENG_EXACT3) return;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M * N) return;
     const int64_t m = i / N; const int o = (int)(i % N);
@@ -1176,6 +1192,7 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
              float2* __restrict__ keys, uint32_t* __restrict__ tags, int64_t M_pad, int n_quads, int ksteps, int seg_tiles,
              int rt_zero) {
     pdl_enter();
+    if (ctrl->engine != GM_ENG_FR) return;              // served by the three-product chain (uniform over the grid: nothing allocated yet)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -1546,6 +1563,7 @@ gm_refine_kernel(const FrParams P) {
     __shared__ float res_d[8][32][FR_GROUP_COLS];                        // exact distances / original indices of a served lane's group
     __shared__ int res_i[8][32][FR_GROUP_COLS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (P.ctrl->engine != GM_ENG_FR) return;
     const int64_t row0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;
     const int obj = blockIdx.y;
     if (row0 >= P.M) return;
@@ -1684,6 +1702,7 @@ __global__ void __launch_bounds__(256)
 gm_rescan_kernel(const FrParams P) {
     pdl_enter();
     __shared__ __align__(16) float q_slab[8][GM_MAXC];
+    if (P.ctrl->engine != GM_ENG_FR) return;
     const int lane = threadIdx.x & 31;
     const int n = min(P.ctrl->rescan_count, P.rescan_cap);
     const int nwarps = gridDim.x * 8;
@@ -1798,9 +1817,17 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
     GmPlan p = gm_plan(M, R, N, C);
     if (ws_bytes < p.total) { set_error("global match: workspace too small (%zu < %zu)", ws_bytes, p.total); return MANET_E_WORKSPACE; }
     if (M <= 0) return 0;
-    static const int forced = [] { const char* e1 = getenv("MANET_GM_ENGINE"); return (e1 && (e1[0] == '3' || e1[0] == 'e')) ? 1 : 0; }();
-    const bool use_fr = p.fr && engine == 0 && !forced;
-    if (out_idx != nullptr && !use_fr) return fail_invalid("global match (arg-min): shape not served by the filter-and-refine engine");
+    // engine: 0 = automatic (the pre-pass picks filter-and-refine for dense reference sets, the three-product kernel for
+    // scribbles; both chains are enqueued and the other one exits at once), 1 = three-product forced (flag / MANET_GM_ENGINE=exact3),
+    // 2 = filter-and-refine forced (MANET_GM_ENGINE=fr; arg-min mode)
+    static const int env_engine = [] { const char* e1 = getenv("MANET_GM_ENGINE"); return !e1 ? 0 : (e1[0] == '3' || e1[0] == 'e') ? 1 : (e1[0] == 'f') ? 2 : 0; }();
+    int mode = engine ? engine : env_engine;            // engine argument: 1 = MANET_GM_ENGINE_EXACT3, 2 = MANET_GM_ENGINE_FR
+    if (out_idx != nullptr) mode = 2;
+    if (!p.fr) {
+        if (mode == 2) return fail_invalid("global match: shape not served by the filter-and-refine engine");
+        mode = 1;
+    }
+    const bool run_fr = mode != 1, run_x3 = mode != 2;
     uint8_t* wbase = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(ws), 1024));
     GmCtrl* ctrl = reinterpret_cast<GmCtrl*>(wbase + p.off_ctrl);
     int* tile_obj = reinterpret_cast<int*>(wbase + p.off_tile_obj);
@@ -1811,17 +1838,18 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
     uint8_t* Bimg = wbase + p.off_B;
     GmFrPre pre;
     memset(&pre, 0, sizeof(pre));
-    if (use_fr) {
+    pre.force_engine = mode == 1 ? GM_ENG_EXACT3 : mode == 2 ? GM_ENG_FR : -1;
+    if (run_fr) {
         pre.q32 = reinterpret_cast<float*>(wbase + p.off_q32); pre.r32 = reinterpret_cast<float*>(wbase + p.off_r32);
         pre.qn = reinterpret_cast<float2*>(wbase + p.off_qn); pre.src_idx = reinterpret_cast<int*>(wbase + p.off_src);
         pre.tile_seg = reinterpret_cast<int*>(wbase + p.off_tile_seg); pre.seg_tile0 = reinterpret_cast<int*>(wbase + p.off_seg_tile0);
-        pre.rsq = reinterpret_cast<float*>(wbase + p.off_rsq);
-        pre.C4 = p.C4; pre.seg_tiles = p.seg_tiles; pre.skip_lo = 1;
+        pre.C4 = p.C4; pre.seg_tiles = p.seg_tiles;
     }
-    // MANET_GM_REUSE_REF (filter-and-refine engine only; otherwise a full rebuild, which is always correct): the reference side
-    // of the workspace -- bucketed operand image, fp32 copy, norms, tables -- was left by the previous call and is kept;
-    // this call scans and converts the query only and refreshes the bias for the query's scale.
-    const bool reuse = use_fr && reuse_ref != 0 && R > 0;
+    if (p.fr) pre.rsq = reinterpret_cast<float*>(wbase + p.off_rsq);
+    // MANET_GM_REUSE_REF: the reference side of the workspace -- bucketed operand image, fp32 copy, norms, tables, engine choice --
+    // was left by the previous call and is kept; this call scans and converts the query only and refreshes the bias for the
+    // query's scale.  (Needs the |r|^2 array, i.e. a plan with the filter-and-refine layout; otherwise a full rebuild.)
+    const bool reuse = p.fr && reuse_ref != 0 && R > 0;
     pre.reuse = reuse ? 1 : 0;
 
     profile_begin(PROF_GLOBAL_PREPASS, stream);
@@ -1831,13 +1859,14 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
     const int64_t items = R_scan + M;
     dim3 g1((unsigned)(ceil_div64(items, 256) < 148 * 8 ? ceil_div64(items, 256) : 148 * 8), GM_SCAN_CG);
     launch_k(gm_scan_kernel, g1, dim3(256), 0, stream, ref, rps, rcs, R_scan, labels, query, qps, qcs, M, C, N, ctrl, best,
-             use_fr ? (int64_t)0 : p.M_pad * N);
+             run_x3 ? p.M_pad * N : (int64_t)0);
     const int nb_ref = (int)ceil_div64(R_scan, GM_CV_PIX), nb_q = (int)ceil_div64(p.M_pad, GM_CV_PIX);
     const int nb_tail = reuse ? (int)(p.R_pad_max / GM_CV_PIX) : N;            // bias refresh blocks | bucket padding blocks
     launch_k(gm_convert_kernel, dim3(nb_ref + nb_q + nb_tail), dim3(256), 0, stream, ref, rps, rcs, R_scan, labels, query, qps, qcs, M, p.M_pad, C, N,
              nb_ref, nb_q, ctrl, Aimg, Bimg, xs, ysn, tile_obj, pre);
     profile_end(PROF_GLOBAL_PREPASS, stream);
-    // 0: single CTA, 1: multicast pair, 2: cta_group::2 pair (default); MANET_GM_VARIANT is an A/B switch for profiling
+    // 0: single CTA, 1: multicast pair, 2: cta_group::2 pair (default); MANET_GM_VARIANT is an A/B switch for profiling (needs a forced
+    // three-product engine: the variants 0 and 1 do not look at the engine choice)
     static const int variant = [] { const char* e1 = getenv("MANET_GM_VARIANT"); return (e1 && e1[0] >= '0' && e1[0] <= '2') ? e1[0] - '0' : 2; }();
     static PerDevice attrs;
     attrs.once([](int) {
@@ -1849,7 +1878,7 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
     const int sm_count = device_sm_count();
     const int ksteps = (C + 15) / 16;
     const int ksteps_lo = gm_fold_remainder(C) ? ksteps - 1 : ksteps;
-    if (use_fr) {
+    if (run_fr) {
         FrParams F;
         memset(&F, 0, sizeof(F));
         F.keys = reinterpret_cast<const float2*>(wbase + p.off_keys); F.tags = reinterpret_cast<const uint32_t*>(wbase + p.off_tags);
@@ -1873,17 +1902,18 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
         if (out_idx != nullptr)
             launch_k(gm_unpack_kernel, dim3((unsigned)ceil_div64(M * N, 256)), dim3(256), 0, stream, (const unsigned long long*)F.best64,
                      (const GmCtrl*)ctrl, M, N, out, out_idx);
-        return check_launch("global match (tcgen05 filter-and-refine) kernels");
     }
-    profile_begin(PROF_GLOBAL_UMMA, stream);
-    if (variant == 1)
-        count_launch(), gm_umma_mc_kernel<<<sm_count & ~1, GM_THREADS, GM_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles / 2, N, ksteps, ksteps_lo);
-    else if (variant == 2)
-        launch_k(gm_umma2_kernel, dim3(sm_count & ~1), dim3(GM_THREADS), (size_t)G2_SMEM_TOTAL, stream, Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles / 2, N, ksteps, ksteps_lo);
-    else
-        count_launch(), gm_umma_kernel<<<sm_count, GM_THREADS, GM_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles, N, ksteps, ksteps_lo);
-    profile_end(PROF_GLOBAL_UMMA, stream);
-    launch_k(gm_finalize_kernel, dim3((unsigned)ceil_div64(M * N, 256)), dim3(256), 0, stream, best, xs, ctrl, M, N, normalize, mem_frame, out);
+    if (run_x3) {
+        profile_begin(PROF_GLOBAL_EXACT3, stream);
+        if (variant == 1 && mode == 1)
+            count_launch(), gm_umma_mc_kernel<<<sm_count & ~1, GM_THREADS, GM_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles / 2, N, ksteps, ksteps_lo);
+        else if (variant == 0 && mode == 1)
+            count_launch(), gm_umma_kernel<<<sm_count, GM_THREADS, GM_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles, N, ksteps, ksteps_lo);
+        else
+            launch_k(gm_umma2_kernel, dim3(sm_count & ~1), dim3(GM_THREADS), (size_t)G2_SMEM_TOTAL, stream, Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles / 2, N, ksteps, ksteps_lo);
+        launch_k(gm_finalize_kernel, dim3((unsigned)ceil_div64(M * N, 256)), dim3(256), 0, stream, best, xs, ctrl, M, N, normalize, mem_frame, out);
+        profile_end(PROF_GLOBAL_EXACT3, stream);
+    }
     return check_launch("global match (tcgen05) kernels");
 }
 

@@ -22,7 +22,8 @@ WRONG_LABEL_PADDING_DISTANCE = 1e20   # IntVOS.py:17
 FORCE_SIMT_LOCAL_ENGINE = False       # same for local matching (exact difference form on CUDA cores)
 FORCE_TENSOR_LOCAL_ENGINE = False     # tests/benchmarks: tcgen05 local engine without the device-side numerics guard
 FORCE_SIMT_ENGINE = False             # debugging/tests: route global matching to the fp32 CUDA-core kernel
-FORCE_EXACT3_ENGINE = False           # tests / A-B: tcgen05 three-product kernel instead of the filter-and-refine engine
+FORCE_EXACT3_ENGINE = False           # tests / A-B: tcgen05 three-product kernel whatever the reference size
+FORCE_FR_ENGINE = False               # tests / A-B: tcgen05 filter-and-refine kernels whatever the reference size
 
 
 # --------------------------------------------------------------------------- autograd
@@ -251,6 +252,8 @@ def _global_match_raw(ref, r, rps, rcs, labels_i32, qry, m, qps, qcs, c, n_obj, 
         flags |= _lib.GM_ENGINE_SIMT
     if FORCE_EXACT3_ENGINE:
         flags |= _lib.GM_ENGINE_EXACT3
+    elif FORCE_FR_ENGINE:
+        flags |= _lib.GM_ENGINE_FR
     out = torch.empty((m, n_obj, 1), dtype=torch.float32, device=dev)
     ws_bytes = L.manet_global_match_workspace_bytes(m, r, c, n_obj, k)
     if cache is not None and k == 1:

@@ -44,6 +44,11 @@ typedef void* manet_stream_t; /* a cudaStream_t */
 #define MANET_GM_ENGINE_EXACT3 8u /* tcgen05, but the three-product kernel (every query x reference pair at fp32 grade, 19 K steps
                                    * per tile) instead of the default filter-and-refine engine (one product filters candidates,
                                    * the survivors are re-evaluated exactly in fp32, 7 K steps per tile); same results */
+#define MANET_GM_ENGINE_FR 512u /* tcgen05, filter-and-refine kernels whatever the size of the reference set.  By default the
+                                  * library decides on the DEVICE (the labelled count is only known there): dense reference sets
+                                  * (>= ~22 000 labelled pixels: first-round ROI references, 1080p memory frames) go to
+                                  * filter-and-refine, scribbles to the three-product kernel; both kernel chains are enqueued and
+                                  * the one that is not needed exits at once. */
 #define MANET_GM_REUSE_REF 128u /* the reference side of `workspace` is still valid: the PREVIOUS manet_global_match /
                                  * _argmin_ws call on this workspace had the same reference embeddings, labels, R, M, C, N (the
                                  * annotated frame and its scribble are constant along a propagation, test.py:237-259) and nothing

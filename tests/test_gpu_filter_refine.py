@@ -61,12 +61,12 @@ def brute_force(ref, qry, lab, n_obj):
 
 
 def run(api, ref, qry, lab, n_obj, engine="fr"):
-    api.FORCE_SIMT_ENGINE, api.FORCE_EXACT3_ENGINE = engine == "simt", engine == "exact3"
+    api.FORCE_SIMT_ENGINE, api.FORCE_EXACT3_ENGINE, api.FORCE_FR_ENGINE = engine == "simt", engine == "exact3", engine == "fr"
     try:
         out, _ = api.nearest_neighbor_features_per_object(ref.unsqueeze(1), qry.unsqueeze(1), lab.view(-1, 1, 1), 1,
                                                           torch.tensor(n_obj - 1))
     finally:
-        api.FORCE_SIMT_ENGINE = api.FORCE_EXACT3_ENGINE = False
+        api.FORCE_SIMT_ENGINE = api.FORCE_EXACT3_ENGINE = api.FORCE_FR_ENGINE = False
     return out.reshape(qry.shape[0], n_obj)
 
 
@@ -195,11 +195,22 @@ def test_reference_cache_gives_identical_results(api):
     C, H, W, n_obj = 100, 40, 54, 4
     ref = (0.1 * torch.relu(torch.randn(C, H, W, generator=gen))).cuda().permute(1, 2, 0)
     lab = torch.randint(-1, n_obj, (H, W, 1), generator=gen).int().cuda()
-    cache = api.ReferenceOperands()
     from cvpr2020_manet_b200.config import cfg
     saved = cfg.TEST_MODE
     cfg.TEST_MODE = True
     try:
+        for forced in ("fr", "exact3", "auto"):       # the cache serves both tensor engines (auto picks by reference size)
+            api.FORCE_FR_ENGINE, api.FORCE_EXACT3_ENGINE = forced == "fr", forced == "exact3"
+            _reference_cache_case(api, ref, lab, C, H, W, n_obj, gen)
+    finally:
+        api.FORCE_FR_ENGINE = api.FORCE_EXACT3_ENGINE = False
+        cfg.TEST_MODE = saved
+
+
+def _reference_cache_case(api, ref, lab, C, H, W, n_obj, gen):
+    cache = api.ReferenceOperands()
+    lab = lab.clone()
+    for _ in range(1):
         for i, scale in enumerate((1.0, 1.0, 37.0, 0.01, 1.0)):
             qry = (scale * 0.1 * torch.relu(torch.randn(C, H, W, generator=gen))).cuda().permute(1, 2, 0)
             want, _ = api.nearest_neighbor_features_per_object(ref, qry, lab, 1, torch.tensor(n_obj - 1))
@@ -216,5 +227,3 @@ def test_reference_cache_gives_identical_results(api):
         want, _ = api.nearest_neighbor_features_per_object(ref, qry, lab, 1, torch.tensor(n_obj - 1))
         got, _ = api.nearest_neighbor_features_per_object(ref, qry, lab, 1, torch.tensor(n_obj - 1), reference_cache=cache)
         assert torch.equal(got, want)
-    finally:
-        cfg.TEST_MODE = saved

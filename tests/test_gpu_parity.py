@@ -56,13 +56,14 @@ def cuda(x):
 
 
 # ------------------------------------------------------------------ global matching
-@pytest.mark.parametrize("engine", ["tcgen05", "tcgen05-exact3", "simt"])
+@pytest.mark.parametrize("engine", ["tcgen05", "tcgen05-fr", "tcgen05-exact3", "simt"])
 @pytest.mark.parametrize("name", GLOBAL)
 def test_global_matches_reference_golden(api, golden, cfg_guard, name, engine, monkeypatch):
     g = golden(name)
     k = int(g["k"])
     monkeypatch.setattr(api, "FORCE_SIMT_ENGINE", engine == "simt")
     monkeypatch.setattr(api, "FORCE_EXACT3_ENGINE", engine == "tcgen05-exact3")
+    monkeypatch.setattr(api, "FORCE_FR_ENGINE", engine == "tcgen05-fr")
     cfg_guard.TEST_MODE = bool(g["test_mode"])
     ref = cuda(g["ref_chw"]).permute(1, 2, 0)
     qry = cuda(g["query_chw"]).permute(1, 2, 0)
