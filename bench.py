@@ -8,7 +8,8 @@ One "step" = what the propagation loop does per frame before the segmentation he
 frame against the annotated frame (+ normalisation + global-map memory min), local matching
 against the previous frame (+ local-map memory store/select).  Workload: synthetic DAVIS-480p
 embeddings (C=100, 120x214 at stride 4), 5 objects (N=6 ids), max_distance=12 (the reference
-default, config.py:50), k=1, every reference pixel labelled (R = M = 25 680).
+default, config.py:50), k=1, every reference pixel labelled (R = M = 25 680; cfg.TEST_MODE off: no
+unlabelled pixels to drop -- the scribble regime is what the propagation_50 / session_8_rounds legs run).
 
   value : frames/s with inputs resident in HBM (CUDA events on the launching stream, L2 flushed
           between steps), whole job over all ranks (independent sequences per GPU: weak scaling)
@@ -204,7 +205,7 @@ def run_own_arm(args, rank, local_rank, world):
     def timed_pass(serial, ref_cache=True):
         """K steps, one CUDA-event pair per step on the launching stream, L2 flushed between steps."""
         for i in range(Wm):
-            sess.step_device(1 + i % 100, 1, 0, serial=serial, ref_cache=ref_cache)
+            sess.step_device(1 + i % 100, 1, 0, drop_unlabelled=False, serial=serial, ref_cache=ref_cache)
         sess.sync()
         L.manet_profile_reset()
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
@@ -215,7 +216,7 @@ def run_own_arm(args, rank, local_rank, world):
             for i in range(K):
                 flush_buf.fill_(i & 0xFF)                      # L2 flush, outside the timed events
                 starts[i].record(stream)
-                sess.step_device(1 + (Wm + i) % 100, 1, 0, serial=serial, ref_cache=ref_cache)
+                sess.step_device(1 + (Wm + i) % 100, 1, 0, drop_unlabelled=False, serial=serial, ref_cache=ref_cache)
                 stops[i].record(stream)
         sess.sync()
         barrier()
@@ -252,22 +253,22 @@ def run_own_arm(args, rank, local_rank, world):
     for k in ("ref", "prev", "cur", "ref_labels", "prev_labels"):
         sess.slots[1][k][:] = sess.slots[0][k]
     for _ in range(min(3, Wm)):
-        sess.step_host(50, 1, 0)
+        sess.step_host(50, 1, 0, drop_unlabelled=False)
     barrier()
     t0 = time.perf_counter()
     for i in range(K):
-        sess.step_host(1 + i % 100, 1, 0)
+        sess.step_host(1 + i % 100, 1, 0, drop_unlabelled=False)
     e2e_sync_s = time.perf_counter() - t0
     barrier()
     checksum = 0.0
     t0 = time.perf_counter()
     for i in range(min(2, K)):
-        sess.submit_host(i % 2, 1 + i % 100, 1, 0)
+        sess.submit_host(i % 2, 1 + i % 100, 1, 0, drop_unlabelled=False)
     for i in range(K):
         og, ol = sess.wait(i % 2)
         checksum += float(og[0, 0, 0]) + float(ol[-1, -1, -1])      # the host reads the step's result
         if i + 2 < K:
-            sess.submit_host(i % 2, 1 + (i + 2) % 100, 1, 0)
+            sess.submit_host(i % 2, 1 + (i + 2) % 100, 1, 0, drop_unlabelled=False)
     e2e_s = time.perf_counter() - t0
     barrier()
     # streaming propagation (MANET_STEP_STREAM) -- the headline e2e: the sequence starts in the untimed warm-up (its first
@@ -275,17 +276,17 @@ def run_own_arm(args, rank, local_rank, world):
     # test.py:237); every timed step uploads its own new inputs (the new frame's embedding + the previous frame's labels)
     # from pinned host memory and downloads both result maps.
     for i in range(Wm):
-        sess.submit_host(i % 2, 1 + i % 100, 1, 0, stream=True, reset=(i == 0))
+        sess.submit_host(i % 2, 1 + i % 100, 1, 0, drop_unlabelled=False, stream=True, reset=(i == 0))
         sess.wait(i % 2)
     barrier()
     t0 = time.perf_counter()
     for i in range(min(2, K)):
-        sess.submit_host((Wm + i) % 2, 1 + (Wm + i) % 100, 1, 0, stream=True)
+        sess.submit_host((Wm + i) % 2, 1 + (Wm + i) % 100, 1, 0, drop_unlabelled=False, stream=True)
     for i in range(K):
         og, ol = sess.wait((Wm + i) % 2)
         checksum += float(og[0, 0, 0]) + float(ol[-1, -1, -1])
         if i + 2 < K:
-            sess.submit_host((Wm + i) % 2, 1 + (Wm + i + 2) % 100, 1, 0, stream=True)
+            sess.submit_host((Wm + i) % 2, 1 + (Wm + i + 2) % 100, 1, 0, drop_unlabelled=False, stream=True)
     e2e_stream_s = time.perf_counter() - t0
     barrier()
     clocks = sampler.stop() if rank == 0 else None

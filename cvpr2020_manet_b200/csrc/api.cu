@@ -177,7 +177,8 @@ int manet_global_match(const float* ref, int64_t ref_pix_stride, int64_t ref_ch_
     const int normalize = (flags & MANET_GM_NORMALIZE) ? 1 : 0;
     if (!(flags & MANET_GM_ENGINE_SIMT) && gm_umma_supported(C, N, k))
         return launch_global_match_umma(ref, ref_pix_stride, ref_ch_stride, R, labels, query, q_pix_stride, q_ch_stride, M,
-                                        C, N, normalize, mem_frame, out, nullptr, (flags & MANET_GM_ENGINE_EXACT3) ? 1 : (flags & MANET_GM_ENGINE_FR) ? 2 : 0,
+                                        C, N, normalize, mem_frame, out, nullptr,
+                                        ((flags & MANET_GM_ENGINE_EXACT3) ? 1 : (flags & MANET_GM_ENGINE_FR) ? 2 : 0) | ((flags & MANET_GM_DROP_UNLAB) ? 4 : 0),
                                         (flags & MANET_GM_REUSE_REF) ? 1 : 0, workspace, workspace_bytes, st);
     // CUDA-core engine: k > 1, C > 128, N > 64, or forced.  Labels outside [0,N) (incl. -1) never
     // match, so MANET_GM_DROP_UNLAB needs no extra work here.

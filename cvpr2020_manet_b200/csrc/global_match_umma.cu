@@ -235,13 +235,17 @@ gm_scan_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64_t 
 }
 
 // split x*s into fp16 hi + lo, 8 channels -> two 16-byte chunks
-__device__ __forceinline__ void split8(const float (&v)[8], float s, uint4& hi, uint4& lo) {
+__device__ __forceinline__ void split8(const float (&v)[8], float s, uint4& hi, uint4& lo, float& hs, float& ls) {
     __half h[8], l[8];
+    hs = 0.f; ls = 0.f;                                   // |hi|^2, |lo|^2 of the eight channels (the filter engine's error bound)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        float x = v[i] * s;
+        const float x = v[i] * s;
         h[i] = __float2half_rn(x);
-        l[i] = __float2half_rn(x - __half2float(h[i]));
+        const float hf = __half2float(h[i]);
+        l[i] = __float2half_rn(x - hf);
+        const float lf = __half2float(l[i]);
+        hs = fmaf(hf, hf, hs); ls = fmaf(lf, lf, ls);
     }
     hi = *reinterpret_cast<uint4*>(h);
     lo = *reinterpret_cast<uint4*>(l);
@@ -417,16 +421,11 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
             sq += __shfl_xor_sync(0xffffffffu, sq, 2);
             sq += __shfl_xor_sync(0xffffffffu, sq, 4);
             const int64_t pos = pos_s[row];
+            uint4 hi8, lo8;
+            float hs, ls;
+            split8(v, scale, hi8, lo8, hs, ls);
             if (fr_on) {
                 // |hi|^2 and |lo|^2 of this row (scaled units) and the exact fp32 copy, 32 contiguous bytes per thread
-                float hs = 0.f, ls = 0.f;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float x = v[k] * scale;
-                    const float h = __half2float(__float2half_rn(x));
-                    const float l = __half2float(__float2half_rn(x - h));
-                    hs = fmaf(h, h, hs); ls = fmaf(l, l, ls);
-                }
                 hs += __shfl_xor_sync(0xffffffffu, hs, 1); ls += __shfl_xor_sync(0xffffffffu, ls, 1);
                 hs += __shfl_xor_sync(0xffffffffu, hs, 2); ls += __shfl_xor_sync(0xffffffffu, ls, 2);
                 hs += __shfl_xor_sync(0xffffffffu, hs, 4); ls += __shfl_xor_sync(0xffffffffu, ls, 4);
@@ -459,7 +458,7 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
                     hi = *reinterpret_cast<uint4*>(comb);
                     lo = make_uint4(0, 0, 0, 0);
                 } else {
-                    split8(v, scale, hi, lo);
+                    hi = hi8; lo = lo8;
                 }
                 *reinterpret_cast<uint4*>(img + image_chunk_offset(pos, 0, j)) = hi;
                 if (!skip_lo) *reinterpret_cast<uint4*>(img + image_chunk_offset(pos, 1, j)) = lo;
@@ -1821,7 +1820,14 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
     // scribbles; both chains are enqueued and the other one exits at once), 1 = three-product forced (flag / MANET_GM_ENGINE=exact3),
     // 2 = filter-and-refine forced (MANET_GM_ENGINE=fr; arg-min mode)
     static const int env_engine = [] { const char* e1 = getenv("MANET_GM_ENGINE"); return !e1 ? 0 : (e1[0] == '3' || e1[0] == 'e') ? 1 : (e1[0] == 'f') ? 2 : 0; }();
-    int mode = engine ? engine : env_engine;            // engine argument: 1 = MANET_GM_ENGINE_EXACT3, 2 = MANET_GM_ENGINE_FR
+    int mode = (engine & 3) ? (engine & 3) : env_engine;            // engine argument: 1 = MANET_GM_ENGINE_EXACT3, 2 = MANET_GM_ENGINE_FR
+    if (mode == 0) {
+        // What the host can settle itself: R bounds the labelled count, so a small R is a three-product case for sure; a large R
+        // without MANET_GM_DROP_UNLAB (bit 2 of `engine`: the caller expects unlabelled pixels) is taken as dense.  Only "large
+        // R, may be sparse" -- a scribble on a full frame -- is left to the device, at the price of one idle kernel chain.
+        if (ceil_div64(R, GM_BN) < FR_MIN_TILES) mode = 1;
+        else if (!(engine & 4)) mode = 2;
+    }
     if (out_idx != nullptr) mode = 2;
     if (!p.fr) {
         if (mode == 2) return fail_invalid("global match: shape not served by the filter-and-refine engine");
