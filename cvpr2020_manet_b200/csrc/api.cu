@@ -531,6 +531,7 @@ struct manet_session {
     int H, W, C, N, d, n_frames;
     cudaStream_t stream;          // compute (+ device->host) stream: global-matching branch, joins
     cudaStream_t local_stream;    // local-matching branch (independent of the global branch until the join)
+    bool global_first;            // enqueue order of the two branches (the global branch is the critical path)
     cudaStream_t copy_stream;     // host->device stream
     cudaEvent_t ev_fork, ev_join;
     SessionSlot slot[2];
@@ -557,8 +558,15 @@ manet_session_t* manet_session_create(int H, int W, int C, int N, int max_distan
     memset(s, 0, sizeof(*s));
     s->H = H; s->W = W; s->C = C; s->N = N; s->d = max_distance; s->n_frames = n_frames;
     const size_t px = (size_t)H * W, emb = px * C * sizeof(float), map = px * N * sizeof(float);
-    bool ok = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&s->local_stream, cudaStreamNonBlocking) == cudaSuccess &&
+    // MANET_STEP_ORDER=local: enqueue the local branch first (the round-1 order); MANET_STEP_PRIO=0: equal stream priorities.
+    const char* e_order = getenv("MANET_STEP_ORDER");
+    const char* e_prio = getenv("MANET_STEP_PRIO");
+    s->global_first = !(e_order && !strcmp(e_order, "local"));
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    const bool use_prio = !(e_prio && !strcmp(e_prio, "0"));
+    bool ok = cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, use_prio ? prio_hi : 0) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&s->local_stream, cudaStreamNonBlocking, use_prio ? prio_lo : 0) == cudaSuccess &&
               cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) == cudaSuccess;
@@ -668,10 +676,15 @@ static int session_step_slot(manet_session_t* s, int slot, int frame, int intera
     const uint32_t gm_flags = (flags & ~(MANET_STEP_SERIAL | MANET_STEP_STREAM | MANET_STEP_STREAM_RESET | MANET_STEP_NO_REF_CACHE | MANET_GM_REUSE_REF)) |
                               MANET_GM_NORMALIZE | (reuse ? MANET_GM_REUSE_REF : 0u);
     s->cached_ref = in->ref; s->cached_ref_lab = in->ref_lab; s->ref_cache_valid = true;
+    // The global branch is the step's critical path (~240 us against ~70 us): it is enqueued first so that the host's
+    // launch latency for the local branch's seven small kernels hides under it, and it runs on the higher-priority stream so
+    // that its CTAs win whenever both branches have blocks pending.
+    const bool global_first = !fork || s->global_first;
     if (fork) {
         cudaEventRecord(s->ev_fork, s->stream);
         cudaStreamWaitEvent(s->local_stream, s->ev_fork, 0);
-    } else {
+    }
+    if (global_first) {
         int rc0 = manet_global_match(in->ref, 1, px, px, in->ref_lab, in->cur, 1, px, px, s->C, s->N, 1, gm_flags,
                                      s->d_gmem + (size_t)frame * n, t.d_out_g, s->ws_g, s->ws_g_bytes, s->stream);
         if (rc0) return rc0;
@@ -686,9 +699,11 @@ static int session_step_slot(manet_session_t* s, int slot, int frame, int intera
     if (rc) return rc;
     if (fork) {
         cudaEventRecord(s->ev_join, s->local_stream);
-        rc = manet_global_match(in->ref, 1, px, px, in->ref_lab, in->cur, 1, px, px, s->C, s->N, 1, gm_flags,
-                                s->d_gmem + (size_t)frame * n, t.d_out_g, s->ws_g, s->ws_g_bytes, s->stream);
-        if (rc) return rc;
+        if (!global_first) {
+            rc = manet_global_match(in->ref, 1, px, px, in->ref_lab, in->cur, 1, px, px, s->C, s->N, 1, gm_flags,
+                                    s->d_gmem + (size_t)frame * n, t.d_out_g, s->ws_g, s->ws_g_bytes, s->stream);
+            if (rc) return rc;
+        }
         cudaStreamWaitEvent(s->stream, s->ev_join, 0);
     }
     return check_launch("session step");

@@ -27,6 +27,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "umma_ptx.cuh"
 
@@ -41,6 +43,7 @@ constexpr int GM_CHUNK_BYTES = 16384;  // one (unit, part, k-block): 128 rows x 
 constexpr int GM_UNIT_BYTES = 4 * GM_CHUNK_BYTES;
 constexpr int GM_EPI_WARPS = 8;           // two warps per TMEM lane quarter, each takes half of the columns
 constexpr int GM_THREADS = 32 * (2 + GM_EPI_WARPS);
+constexpr int FR_THREADS = 32 * (4 + GM_EPI_WARPS);   // filter kernel: a utility warp group (two of its warps idle) + two epilogue warp groups
 constexpr int GM_STAGES = 4;
 constexpr int GM_STAGE_BYTES = 2 * GM_CHUNK_BYTES;           // one (part, k-block) of a 256-row tile: 256 rows x 128 B
 constexpr int GM_SMEM_A = GM_UNIT_BYTES;
@@ -1122,52 +1125,46 @@ constexpr int FR_GROUPS = GM_BN / 2 / FR_GROUP_COLS;            // groups per 12
 static_assert(FR_GROUPS == 32, "the key layout assumes 32 column groups per half tile");
 constexpr float FR_NEG = -3.0e38f;
 
-// (v & mask) | g in ONE LOP3: a LOP3 takes one immediate, so the group index must sit in a register.  The caller derives
-// the sixteen indices of a chunk pair from a run-time zero (a kernel argument ptxas cannot fold), once per kernel.
-__device__ __forceinline__ float fr_key(float v, uint32_t greg) {
+// (v & mask) | g in ONE LOP3: a LOP3 takes one immediate, so either the mask or the group index must sit in a register.
+// The mask does (one register for all keys; the caller derives it from a run-time zero, a kernel argument ptxas cannot
+// fold, or the compiler would turn the pair back into two instructions); the group index is the immediate.
+template <int G>
+__device__ __forceinline__ float fr_key(float v, uint32_t maskreg) {
     uint32_t k;
-    asm("lop3.b32 %0, %1, 0xFFFFFFE0, %2, 0xEA;" : "=r"(k) : "r"(__float_as_uint(v)), "r"(greg));    // (a & b) | c
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(k) : "r"(__float_as_uint(v)), "r"(maskreg), "n"(G));    // (a & b) | c
     return __uint_as_float(k);
 }
 
-// Two largest keys of one 64-column unit of an accumulator (this warp's share of a 128-column sub-tile), 4-bit group index.
+// Columns 8I .. 8I+7 of the 32-column unit U of an accumulator row = groups 8U + 2I and 8U + 2I + 1 of the half tile, folded
+// into one of the two running top-2 chains (a1 >= a2, b1 >= b2; two chains so that consecutive updates do not wait for
+// each other).
 // Instruction budget (alu pipe, 2 cycles per warp instruction and scheduler): per 8 columns 4 maxima + 2 keys + 5 for the
-// top-2 update = 88 per unit and thread -- 176 per 256-column tile, 704 cycles per tile and SM, below the 896 cycles of
-// the tile's 14 half-width MMAs.
-template <bool BIAS_IN_ACC>
-__device__ __forceinline__ void fr_unit_top2(uint32_t taddr, const float4* __restrict__ yv, const uint32_t (&gidx)[16], float& c1, float& c2) {
-    uint32_t r[2][32];
-    tmem_ld32(taddr, r[0]);
-    tmem_ld32(taddr + 32, r[1]);
-    float4 y[16];
+// top-2 update = 44 per unit and thread -- 176 per 256-column tile, 704 cycles per tile and SM, below the 896 cycles of
+// the tile's 7 MMAs.
+template <bool BIAS_IN_ACC, int U, int I>
+__device__ __forceinline__ void fr_pair(const uint32_t (&r)[32], const float4 (&y)[8], const uint32_t maskreg, float& c1, float& c2) {
+    float x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = __uint_as_float(r[8 * I + k]);
     if (!BIAS_IN_ACC) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) y[i] = __ldg(yv + i);
+        const float4 y0 = y[2 * I], y1 = y[2 * I + 1];
+        x[0] += y0.x; x[1] += y0.y; x[2] += y0.z; x[3] += y0.w;
+        x[4] += y1.x; x[5] += y1.y; x[6] += y1.z; x[7] += y1.w;
     }
-    tmem_ld_wait_dep(r[0]);                                             // tcgen05.wait::ld covers both loads
-    tmem_ld_wait_dep(r[1]);
-    float a1 = FR_NEG, a2 = FR_NEG, b1 = FR_NEG, b2 = FR_NEG;           // two independent chains
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-#pragma unroll
-        for (int i = 0; i < 8; i += 2) {                                // columns 4i .. 4i+7 of this chunk = two groups
-            float x[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) x[k] = __uint_as_float(r[h][4 * i + k]);
-            if (!BIAS_IN_ACC) {
-                const float4 y0 = y[h * 8 + i], y1 = y[h * 8 + i + 1];
-                x[0] += y0.x; x[1] += y0.y; x[2] += y0.z; x[3] += y0.w;
-                x[4] += y1.x; x[5] += y1.y; x[6] += y1.z; x[7] += y1.w;
-            }
-            const float ka = fr_key(fmaxf(fmaxf(fmaxf(x[0], x[1]), x[2]), x[3]), gidx[h * 8 + i]);
-            const float kb = fr_key(fmaxf(fmaxf(fmaxf(x[4], x[5]), x[6]), x[7]), gidx[h * 8 + i + 1]);
-            const float hi = fmaxf(ka, kb), lo = fminf(ka, kb);
-            if (i & 2) { const float t = fminf(b1, hi); b2 = fmaxf(fmaxf(b2, t), lo); b1 = fmaxf(b1, hi); }
-            else       { const float t = fminf(a1, hi); a2 = fmaxf(fmaxf(a2, t), lo); a1 = fmaxf(a1, hi); }
-        }
-    }
-    c1 = fmaxf(a1, b1);
-    c2 = fmaxf(fmaxf(fminf(a1, b1), a2), b2);
+    const float ka = fr_key<8 * U + 2 * I>(fmaxf(fmaxf(fmaxf(x[0], x[1]), x[2]), x[3]), maskreg);
+    const float kb = fr_key<8 * U + 2 * I + 1>(fmaxf(fmaxf(fmaxf(x[4], x[5]), x[6]), x[7]), maskreg);
+    const float hi = fmaxf(ka, kb), lo = fminf(ka, kb);
+    const float t = fminf(c1, hi);
+    c2 = fmaxf(fmaxf(c2, t), lo);
+    c1 = fmaxf(c1, hi);
+}
+template <bool BIAS_IN_ACC, int U>
+__device__ __forceinline__ void fr_unit32(const uint32_t (&r)[32], const float4 (&y)[8], const uint32_t maskreg,
+                                          float& a1, float& a2, float& b1, float& b2) {
+    fr_pair<BIAS_IN_ACC, U, 0>(r, y, maskreg, a1, a2);
+    fr_pair<BIAS_IN_ACC, U, 1>(r, y, maskreg, b1, b2);
+    fr_pair<BIAS_IN_ACC, U, 2>(r, y, maskreg, a1, a2);
+    fr_pair<BIAS_IN_ACC, U, 3>(r, y, maskreg, b1, b2);
 }
 
 // first tile of the next segment (or of the next query tile pair) at or after linear tile index x
@@ -1185,13 +1182,21 @@ __device__ __forceinline__ long long fr_snap(long long x, long long total, int n
 // stage the one-product GEMM sits at the L2 -> SM limit (32 KB per 896 MMA cycles and SM = 5.3 KB/clk over the chip against
 // ~6 KB/clk of L2 bandwidth); the second A tile halves that.  Accumulator buffer a (256 tensor-memory columns) belongs to A
 // tile a: the epilogue of (q, rt, 0) overlaps the MMAs of (q, rt, 1) and so on.
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
+// SEG1: every reference tile is its own segment (seg_tiles == 1, the case whenever the key array fits its cap: all of 480p) --
+// the segment tables are the identity, a tile's two best keys go straight to memory and the running per-segment state, its
+// merge and the table loads drop out of the epilogue's instruction stream (which is what bounds this kernel).
+template <bool SEG1>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FR_THREADS, 1)
 gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg, const float* __restrict__ ysn,
              const int* __restrict__ tile_seg, const int* __restrict__ seg_tile0, const GmCtrl* __restrict__ ctrl,
              float2* __restrict__ keys, uint32_t* __restrict__ tags, int64_t M_pad, int n_quads, int ksteps, int seg_tiles,
              int rt_zero) {
     pdl_enter();
     if (ctrl->engine != GM_ENG_FR) return;              // served by the three-product chain (uniform over the grid: nothing allocated yet)
+#ifdef FR_TRACE
+    long long tr_total = clock64(), tr_mma_acc = 0, tr_mma_b = 0, tr_epi_full = 0, tr_prod = 0;
+    unsigned long long tr_ns0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_ns0));
+#endif
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -1219,9 +1224,11 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
     const long long total = (long long)n_quads * n_rtiles;
     const int n_clusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
     // contiguous ranges of items, cut at segment boundaries: a (query row, segment-half) is reduced by exactly one warp
-    const long long t_begin = fr_snap(total * cid / n_clusters, total, n_rtiles, tile_seg, seg_tile0);
-    const long long t_end = fr_snap(total * (cid + 1) / n_clusters, total, n_rtiles, tile_seg, seg_tile0);
-    const long long q_begin = n_rtiles ? t_begin / n_rtiles : 0;              // one division per kernel, not per item
+    const long long t_begin = SEG1 ? total * cid / n_clusters : fr_snap(total * cid / n_clusters, total, n_rtiles, tile_seg, seg_tile0);
+    const long long t_end = SEG1 ? total * (cid + 1) / n_clusters : fr_snap(total * (cid + 1) / n_clusters, total, n_rtiles, tile_seg, seg_tile0);
+    // (one division per kernel, not per item; the per-role loops below count in 32 bits: a range holds far fewer than 2^31 items)
+    const int q_begin = n_rtiles ? (int)(t_begin / n_rtiles) : 0;
+    const int n_items = (int)(t_end - t_begin);
     const int rt_begin = n_rtiles ? (int)(t_begin % n_rtiles) : 0;
 
     if (warp == 1) {
@@ -1241,11 +1248,17 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Registers: an SM sub-partition holds three of the twelve warps, 170 registers each.  The utility warp group (producer,
+    // MMA issuer / forwarder, two idle warps) hands most of its share to the two epilogue warp groups, whose reduction then
+    // keeps its unit buffers and loop state in registers.
+    // (each setmaxnreg sits inside its role's branch: ptxas budgets the code a setmaxnreg dominates)
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
         // ------------------------------------------------ producer (both CTAs: hi parts of own A rows, of own half of B)
-        Ring st; uint32_t ae_phase = 0; long long cur_q = -1;
-        long long q = q_begin; int rt = rt_begin;
-        for (long long item = t_begin; item < t_end; ++item, ++rt) {
+        Ring st; uint32_t ae_phase = 0; int cur_q = -1;
+        int q = q_begin, rt = rt_begin;
+        for (int it = 0; it < n_items; ++it, ++rt) {
             if (rt == n_rtiles) { rt = 0; ++q; }
             if (q != cur_q) {
                 mbar_wait(a_empty, ae_phase ^ 1); ae_phase ^= 1;
@@ -1257,7 +1270,13 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
                 __syncwarp();
                 cur_q = q;
             }
+#ifdef FR_TRACE
+            long long p0 = clock64();
+#endif
             mbar_wait(empty_b + 8 * st.idx, st.phase ^ 1);
+#ifdef FR_TRACE
+            tr_prod += clock64() - p0;
+#endif
             if (elect_one()) {
                 mbar_expect_tx(full_b + 8 * st.idx, G2_STAGE_BYTES);
                 bulk_g2s(sB + st.idx * G2_STAGE_BYTES, Bimg + (size_t)(2 * rt + rank) * GM_UNIT_BYTES, G2_STAGE_BYTES, full_b + 8 * st.idx);
@@ -1270,20 +1289,32 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
             // -------------------------------------------- MMA issuer: qh.rh only, `ksteps` K steps per 256 x 256 tile, two tiles per B stage
             constexpr uint32_t idesc = idesc_f16(2 * GM_BM, GM_BN);
             const uint64_t descA0 = smem_desc_sw128(sA), descA1 = smem_desc_sw128(sA + A_BYTES);
-            Ring st; uint32_t af_phase = 0, acc_phase = 0; long long cur_q = -1;
-            long long q = q_begin; int rt = rt_begin;
-            for (long long item = t_begin; item < t_end; ++item, ++rt) {
+            Ring st; uint32_t af_phase = 0, acc_phase = 0; int cur_q = -1;
+            int q = q_begin, rt = rt_begin;
+            for (int it = 0; it < n_items; ++it, ++rt) {
                 if (rt == n_rtiles) { rt = 0; ++q; }
                 if (q != cur_q) { mbar_wait(a_full, af_phase); mbar_wait_cluster(peer_a_full, af_phase); af_phase ^= 1; cur_q = q; }
+#ifdef FR_TRACE
+                long long m0 = clock64();
+#endif
                 mbar_wait(full_b + 8 * st.idx, st.phase);
                 mbar_wait_cluster(peer_full + 8 * st.idx, st.phase);
+#ifdef FR_TRACE
+                tr_mma_b += clock64() - m0;
+#endif
                 const uint64_t descB = smem_desc_sw128(sB + st.idx * G2_STAGE_BYTES);
-                const bool last_of_q = (item + 1 == t_end) || (rt + 1 == n_rtiles);
+                const bool last_of_q = (it + 1 == n_items) || (rt + 1 == n_rtiles);
 #pragma unroll 1
                 for (int a = 0; a < 2; ++a) {
                     // nothing is acquired through this barrier ("the accumulator has been read"): a plain wait is enough
+#ifdef FR_TRACE
+                    long long m1 = clock64();
+#endif
                     mbar_wait(tmem_empty + 8 * a, acc_phase ^ 1);
                     tc_fence_after();
+#ifdef FR_TRACE
+                    tr_mma_acc += clock64() - m1;
+#endif
                     const uint32_t d_tmem = tmem_base + a * GM_BN;
                     const uint64_t dA = a ? descA1 : descA0;
                     if (elect_one()) {
@@ -1305,9 +1336,9 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
         } else {
             // -------------------------------------------- peer: forward "landed" to the leader
             const uint32_t r_peer_full = mapa_shared(peer_full, 0), r_peer_a = mapa_shared(peer_a_full, 0);
-            Ring st; uint32_t af_phase = 0; long long cur_q = -1;
-            long long q = q_begin; int rt = rt_begin;
-            for (long long item = t_begin; item < t_end; ++item, ++rt) {
+            Ring st; uint32_t af_phase = 0; int cur_q = -1;
+            int q = q_begin, rt = rt_begin;
+            for (int it = 0; it < n_items; ++it, ++rt) {
                 if (rt == n_rtiles) { rt = 0; ++q; }
                 if (q != cur_q) {
                     mbar_wait(a_full, af_phase); af_phase ^= 1;
@@ -1321,71 +1352,127 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
                 st.advance(G2_STAGES);
             }
         }
+    }
     } else {
-        // ------------------------------------------------ epilogue (warps 2..9 of both CTAs): per-segment top-2 keys
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        // ------------------------------------------------ epilogue (warps 4..11 of both CTAs): per-segment top-2 keys
+        // The eight warps leave the tmem_full wait in lock step, so a load-then-reduce loop exposes every tcgen05.ld latency
+        // (measured: 1477 cycles per tile against 930 of alu-pipe work).  The accumulator is therefore read as a stream of
+        // 32-column units, one unit ahead of the arithmetic ACROSS tile boundaries: while unit u is reduced, unit u+1 -- or
+        // the first unit of the next tile, after its tmem_full wait -- is in flight.  The accumulator buffer goes back to
+        // the MMA issuer as soon as its last unit has landed in registers, before that unit is reduced.
         const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int half = (warp - 4) >> 2;
         const int row = quarter * 32 + lane;
         const uint32_t r_tmem_empty = mapa_shared(tmem_empty, 0);
+        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * (GM_BN / 2);
         uint32_t acc_phase = 0;
-        uint32_t gidx[16];                                                 // group indices 0..15 in registers (see fr_key)
-#pragma unroll
-        for (int i = 0; i < 16; ++i) gidx[i] = (uint32_t)(rt_zero + i);
+        const uint32_t maskreg = ~(uint32_t)(FR_GROUPS - 1) + (uint32_t)rt_zero;      // the key mask, in a register (see fr_key)
+        uint32_t R[2][32];
         // running top-2 of the open segment (key, tile offset) for each of the two query tiles
         float V1[2] = {FR_NEG, FR_NEG}, V2[2] = {FR_NEG, FR_NEG}; uint32_t T1[2] = {0, 0}, T2[2] = {0, 0};
-        long long q = q_begin; int rt = rt_begin;
-        const bool any = t_begin < t_end;
-        int sg = any ? __ldg(tile_seg + rt) : 0;
-        int sg_t0 = any ? __ldg(seg_tile0 + sg) : 0, sg_t1 = any ? __ldg(seg_tile0 + sg + 1) : 0;
-        for (long long item = t_begin; item < t_end; ++item, ++rt) {
-            if (rt == n_rtiles) { rt = 0; ++q; }
-            // the next item's segment, fetched now (two dependent loads) and used an item later
-            int nrt = rt + 1; if (nrt == n_rtiles) nrt = 0;
-            const bool more = item + 1 < t_end;
-            const int nsg = more ? __ldg(tile_seg + nrt) : sg;
-            const int nsg_t0 = more ? __ldg(seg_tile0 + nsg) : 0, nsg_t1 = more ? __ldg(seg_tile0 + nsg + 1) : 0;
-            const uint32_t toff = (uint32_t)(rt - sg_t0);
-            const bool seg_ends = !more || nrt == 0 || nsg != sg;
+        int q = q_begin, rt = rt_begin;
+        const bool any = n_items > 0;
+        int sg = 0, sg_t0 = 0;
+        if (!SEG1 && any) { sg = __ldg(tile_seg + rt); sg_t0 = __ldg(seg_tile0 + sg); }
+        // SEG1: where this thread's keys of (q, rt, a = 0) go; a = 1 is 2 * GM_BM entries further on
+        float2* kp = keys + ((size_t)rt * 2 + half) * (size_t)M_pad + (size_t)(4 * q + rank) * GM_BM + row;
+#if defined(FR_EXP_NOLOAD)
+#define FR_LD(addr, dst) do { asm volatile("" : "+r"(dst[0]), "+r"(dst[31]) : "r"(addr)); } while (0)     /* experiment: arithmetic only */
 #pragma unroll
-            for (int a = 0; a < 2; ++a) {
-                mbar_wait(tmem_full + 8 * a, acc_phase);
-                tc_fence_after();
-                float M1 = FR_NEG, M2 = FR_NEG;
-#pragma unroll 1
-                for (int u = 0; u < 2; ++u) {
-                    // unit u = this warp's columns [64 u, 64 u + 64) of its half = tile rows [128 half + 64 u, +64): group 16 u + g
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * GM_BN + half * (GM_BN / 2) + u * (GM_BN / 4);
-                    float c1, c2;
-                    if (bias_in_acc) fr_unit_top2<true>(taddr, nullptr, gidx, c1, c2);
-                    else fr_unit_top2<false>(taddr, reinterpret_cast<const float4*>(ysn + (size_t)rt * GM_BN + half * (GM_BN / 2) + u * (GM_BN / 4)), gidx, c1, c2);
-                    const uint32_t ubit = (uint32_t)u << 4;
-                    c1 = __uint_as_float(__float_as_uint(c1) | ubit);
-                    c2 = __uint_as_float(__float_as_uint(c2) | ubit);
-                    const float t = fminf(M1, c1);
-                    M2 = fmaxf(fmaxf(M2, t), c2);
-                    M1 = fmaxf(M1, c1);
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote_nofence(r_tmem_empty + 8 * a);
+        for (int i = 0; i < 32; ++i) { R[0][i] = (uint32_t)(rt_zero + i * 77); R[1][i] = (uint32_t)(rt_zero + i * 131); }
+#else
+#define FR_LD(addr, dst) tmem_ld32(addr, dst)
+#endif
+        if (any) { mbar_wait(tmem_full, 0); tc_fence_after(); FR_LD(tbase, R[0]); }
+        for (int it = 0; it < n_items; ++it, ++rt) {
+            if (rt == n_rtiles) {
+                rt = 0; ++q;
+                if (SEG1) kp = keys + (size_t)half * (size_t)M_pad + (size_t)(4 * q + rank) * GM_BM + row;
+            }
+            const bool more = it + 1 < n_items;
+            int nsg = 0, nsg_t0 = 0; uint32_t toff = 0; bool seg_ends = true;
+            if (!SEG1) {
+                // the next item's segment, fetched now (two dependent loads) and used an item later
+                int nrt = rt + 1; if (nrt == n_rtiles) nrt = 0;
+                nsg = more ? __ldg(tile_seg + nrt) : sg;
+                nsg_t0 = more ? __ldg(seg_tile0 + nsg) : 0;
+                toff = (uint32_t)(rt - sg_t0);
+                seg_ends = !more || nrt == 0 || nsg != sg;
+            }
+            auto do_tile = [&](auto bias_c, const int a, float& V1a, float& V2a, uint32_t& T1a, uint32_t& T2a) {
+                constexpr bool BIAS = decltype(bias_c)::value;
+                const float4* yv = reinterpret_cast<const float4*>(ysn + (size_t)rt * GM_BN + half * (GM_BN / 2));
+                float a1 = FR_NEG, a2 = FR_NEG, b1 = FR_NEG, b2 = FR_NEG;
+                auto unit = [&](auto uc) {
+                    constexpr int u = decltype(uc)::value;
+                    float4 y[8];
+                    if (!BIAS) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) y[i] = __ldg(yv + u * 8 + i);
+                    }
+                    tmem_ld_wait_dep(R[u & 1]);
+                    // (ptxas tracks tcgen05.ld by scoreboard and hoists these loads further than written, registers permitting)
+                    if (u < 3) FR_LD(tbase + a * GM_BN + (u + 1) * 32, R[(u + 1) & 1]);
+                    else {
+                        // every column of this tile is in registers (or reduced): the buffer goes back now
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_remote_nofence(r_tmem_empty + 8 * a);
+#ifdef FR_TRACE
+                        long long e0 = clock64();
+#endif
+                        if (a == 0) mbar_wait(tmem_full + 8, acc_phase);
+                        else if (more) mbar_wait(tmem_full, acc_phase ^ 1);
+#ifdef FR_TRACE
+                        tr_epi_full += clock64() - e0;
+#endif
+                        if (a == 0) { tc_fence_after(); FR_LD(tbase + GM_BN, R[0]); }
+                        else if (more) { tc_fence_after(); FR_LD(tbase, R[0]); }
+                    }
+#if defined(FR_EXP_NOCOMPUTE)
+                    a2 = fmaxf(a2, __uint_as_float(R[u & 1][0])); b2 = fmaxf(b2, __uint_as_float(R[u & 1][31]));     // experiment: loads only
+#else
+                    fr_unit32<BIAS, u>(R[u & 1], y, maskreg, a1, a2, b1, b2);
+#endif
+                };
+                unit(std::integral_constant<int, 0>{}); unit(std::integral_constant<int, 1>{});
+                unit(std::integral_constant<int, 2>{}); unit(std::integral_constant<int, 3>{});
+                const float M1 = fmaxf(a1, b1), M2 = fmaxf(fmaxf(fminf(a1, b1), a2), b2);
+                if (SEG1) { kp[a * 2 * GM_BM] = make_float2(M1, M2); return; }
                 // merge this tile's two best into the segment's
-                if (M1 > V1[a]) {
-                    if (M2 > V1[a]) { V2[a] = M2; T2[a] = toff; } else { V2[a] = V1[a]; T2[a] = T1[a]; }
-                    V1[a] = M1; T1[a] = toff;
-                } else if (M1 > V2[a]) { V2[a] = M1; T2[a] = toff; }
+                if (M1 > V1a) {
+                    if (M2 > V1a) { V2a = M2; T2a = toff; } else { V2a = V1a; T2a = T1a; }
+                    V1a = M1; T1a = toff;
+                } else if (M1 > V2a) { V2a = M1; T2a = toff; }
                 if (seg_ends) {
                     const size_t e = ((size_t)sg * 2 + half) * (size_t)M_pad + (size_t)(4 * q + 2 * a + rank) * GM_BM + row;
-                    keys[e] = make_float2(V1[a], V2[a]);
-                    if (seg_tiles > 1) tags[e] = T1[a] | (T2[a] << 16);
-                    V1[a] = V2[a] = FR_NEG; T1[a] = T2[a] = 0;
+                    keys[e] = make_float2(V1a, V2a);
+                    if (seg_tiles > 1) tags[e] = T1a | (T2a << 16);
+                    V1a = V2a = FR_NEG; T1a = T2a = 0;
                 }
+            };
+            if (bias_in_acc) {
+                do_tile(std::true_type{}, 0, V1[0], V2[0], T1[0], T2[0]);
+                do_tile(std::true_type{}, 1, V1[1], V2[1], T1[1], T2[1]);
+            } else {
+                do_tile(std::false_type{}, 0, V1[0], V2[0], T1[0], T2[0]);
+                do_tile(std::false_type{}, 1, V1[1], V2[1], T1[1], T2[1]);
             }
             acc_phase ^= 1;
-            sg = nsg; sg_t0 = nsg_t0; sg_t1 = nsg_t1;
+            sg = nsg; sg_t0 = nsg_t0;
+            kp += 2 * (size_t)M_pad;
         }
-        (void)sg_t1;
     }
 
+#ifdef FR_TRACE
+    if ((blockIdx.x == 0 || blockIdx.x == 1 || blockIdx.x == 80) && lane == 0 && (warp <= 1 || warp == 4 || warp == 11))
+    {
+        unsigned long long tr_ns1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_ns1));
+        printf("cta %d warp %d items %d total %lld clk %llu ns | prod wait_empty %lld | mma wait_acc %lld wait_b %lld | epi wait_full %lld\n", blockIdx.x, warp,
+               n_items, clock64() - tr_total, tr_ns1 - tr_ns0, tr_prod, tr_mma_acc, tr_mma_b, tr_epi_full);
+    }
+#endif
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
@@ -1879,7 +1966,8 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
         cudaFuncSetAttribute(gm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_TOTAL);
         cudaFuncSetAttribute(gm_umma_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_TOTAL);
         cudaFuncSetAttribute(gm_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_TOTAL);
-        cudaFuncSetAttribute(gm_fr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FR_SMEM_TOTAL);
+        cudaFuncSetAttribute(gm_fr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FR_SMEM_TOTAL);
+        cudaFuncSetAttribute(gm_fr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FR_SMEM_TOTAL);
     });
     const int sm_count = device_sm_count();
     const int ksteps = (C + 15) / 16;
@@ -1894,7 +1982,7 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
         F.out = out; F.mem = mem_frame; F.out_idx = out_idx;
         F.M = M; F.M_pad = p.M_pad; F.N = N; F.C4 = p.C4; F.seg_tiles = p.seg_tiles; F.normalize = normalize;
         profile_begin(PROF_GLOBAL_UMMA, stream);
-        launch_k(gm_fr_kernel, dim3(sm_count & ~1), dim3(GM_THREADS), (size_t)FR_SMEM_TOTAL, stream, (const uint8_t*)Aimg, (const uint8_t*)Bimg,
+        launch_k(p.seg_tiles == 1 ? gm_fr_kernel<true> : gm_fr_kernel<false>, dim3(sm_count & ~1), dim3(FR_THREADS), (size_t)FR_SMEM_TOTAL, stream, (const uint8_t*)Aimg, (const uint8_t*)Bimg,
                  (const float*)ysn, (const int*)pre.tile_seg, (const int*)pre.seg_tile0, (const GmCtrl*)ctrl,
                  reinterpret_cast<float2*>(wbase + p.off_keys), reinterpret_cast<uint32_t*>(wbase + p.off_tags), p.M_pad, p.n_mtiles / 4,
                  ksteps, p.seg_tiles, 0);
