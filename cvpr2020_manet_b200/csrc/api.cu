@@ -145,6 +145,7 @@ using namespace manet;
 #define MANET_ARCH() do { int _a = arch_ok(); if (_a) return _a; } while (0)
 
 namespace manet {
+StepGates& step_gates() { static thread_local StepGates g; return g; }
 bool pdl_enabled() {
     static int cached = -1;
     // measured on B200 (bench.py, 40 steps): one stream 0.3461 -> 0.3428 ms per step with the attribute, two streams
@@ -532,6 +533,8 @@ struct manet_session {
     cudaStream_t stream;          // compute (+ device->host) stream: global-matching branch, joins
     cudaStream_t local_stream;    // local-matching branch (independent of the global branch until the join)
     bool global_first;            // enqueue order of the two branches (the global branch is the critical path)
+    bool gate_local;              // local branch's main kernel waits for the global branch's GEMM kernel (see session_step_slot)
+    cudaEvent_t ev_gemm;
     cudaStream_t copy_stream;     // host->device stream
     cudaEvent_t ev_fork, ev_join;
     SessionSlot slot[2];
@@ -562,6 +565,8 @@ manet_session_t* manet_session_create(int H, int W, int C, int N, int max_distan
     const char* e_order = getenv("MANET_STEP_ORDER");
     const char* e_prio = getenv("MANET_STEP_PRIO");
     s->global_first = !(e_order && !strcmp(e_order, "local"));
+    const char* e_gate = getenv("MANET_STEP_GATE");                 // MANET_STEP_GATE=1: experiment, see session_step_slot
+    s->gate_local = e_gate && !strcmp(e_gate, "1");
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     const bool use_prio = !(e_prio && !strcmp(e_prio, "0"));
@@ -569,7 +574,8 @@ manet_session_t* manet_session_create(int H, int W, int C, int N, int max_distan
               cudaStreamCreateWithPriority(&s->local_stream, cudaStreamNonBlocking, use_prio ? prio_lo : 0) == cudaSuccess &&
               cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
-              cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) == cudaSuccess;
+              cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&s->ev_gemm, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i) {
         SessionSlot& t = s->slot[i];
         ok = ok && cudaMallocHost(&t.h_ref, emb) == cudaSuccess && cudaMallocHost(&t.h_prev, emb) == cudaSuccess &&
@@ -622,6 +628,7 @@ void manet_session_destroy(manet_session_t* s) {
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
+    if (s->ev_gemm) cudaEventDestroy(s->ev_gemm);
     delete s;
 }
 
@@ -684,13 +691,23 @@ static int session_step_slot(manet_session_t* s, int slot, int frame, int intera
         cudaEventRecord(s->ev_fork, s->stream);
         cudaStreamWaitEvent(s->local_stream, s->ev_fork, 0);
     }
+    // MANET_STEP_GATE=1 (experiment, off by default): hold the local branch's tensor kernel (lm_umma_kernel, ~40 us) back until
+    // the global branch's persistent GEMM kernel has finished, so that it overlaps the refinement instead of occupying SMs
+    // when that kernel -- one CTA per SM, the whole register file -- wants to start.  Measured on B200 (bench.py, 30 steps):
+    // 0.256 ms per step with the gate against 0.242 ms without: the refinement is the worse neighbour.
+    const bool gate = fork && global_first && s->gate_local;
+    StepGates& gates = step_gates();
+    gates.after_global_gemm = gate ? s->ev_gemm : nullptr;
     if (global_first) {
         int rc0 = manet_global_match(in->ref, 1, px, px, in->ref_lab, in->cur, 1, px, px, s->C, s->N, 1, gm_flags,
                                      s->d_gmem + (size_t)frame * n, t.d_out_g, s->ws_g, s->ws_g_bytes, s->stream);
         if (rc0) return rc0;
     }
+    gates.after_global_gemm = nullptr;
+    gates.local_main_gate = gate ? s->ev_gemm : nullptr;
     int rc = manet_local_match(in->prev, s->W, 1, px, in->cur, s->W, 1, px, in->prev_lab, s->d_ids, s->H, s->W, s->C, s->N,
                                s->d, t.d_raw_l, s->ws_l, s->ws_l_bytes, ls);
+    gates.local_main_gate = nullptr;
     if (rc) return rc;
     int df = frame - start_annotated_frame; if (df < 0) df = -df;
     rc = manet_local_map_store_select(t.d_raw_l, s->d_lmem + (size_t)frame * kMemoryRounds * n,

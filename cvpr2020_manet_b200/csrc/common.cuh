@@ -85,6 +85,11 @@ __device__ __forceinline__ void pdl_enter() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
+// Cross-branch ordering inside one propagation step (set by the session around its two launcher calls, per host thread):
+// the global-matching launcher records `after_global_gemm` right after its GEMM kernel, the local-matching launcher makes its
+// main kernel wait for `local_main_gate`.  See session_step_slot (api.cu) for why.
+struct StepGates { cudaEvent_t after_global_gemm = nullptr; cudaEvent_t local_main_gate = nullptr; };
+StepGates& step_gates();
 bool pdl_enabled();                        // MANET_PDL=1 in the environment turns the attribute on (measured: a wash, see api.cu)
 
 template <typename... KArgs, typename... Args>

@@ -307,7 +307,7 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
     const GmBiasPlan bias = gm_bias_plan(C, s_q, s_r, ctrl->absmax_r_bits);
     const int b = blockIdx.x;
     if (b == 0 && fr.reuse) {
-        if (t == 0) { ctrl->scale_q = s_q; ctrl->bias_fold = bias.on ? 1 : 0; }
+        if (t == 0) { ctrl->scale_q = s_q; ctrl->bias_fold = bias.on ? 1 : 0; ctrl->rescan_count = 0; }
     } else if (b == 0) {
         if (t <= N) ctrl->offsets[t] = off[t];
         if (t == 0) { ctrl->n_rtiles = off[N] / GM_BN; ctrl->scale_q = s_q; ctrl->scale_r = s_r; ctrl->bias_fold = bias.on ? 1 : 0; ctrl->engine = eng; }
@@ -1081,9 +1081,12 @@ gm_umma_mc_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ 
 // out[m,o] = |q_m|^2 - (2/s) * max_r (s*(q.r) - s/2*|r|^2)  (= min_r |q-r|^2), 1e20 for absent objects;
 // optional normalisation and global-map memory merge fused (IntVOS.py:611-622).
 __global__ void gm_finalize_kernel(const int* __restrict__ best, const float* __restrict__ xs,
-                                   const GmCtrl* __restrict__ ctrl, int64_t M, int N, int normalize,
+                                   GmCtrl* __restrict__ ctrl, int64_t M, int N, int normalize,
                                    float* __restrict__ mem, float* __restrict__ out) {
     pdl_enter();
+    // the pre-pass has consumed the query's |x| max: cleared here for the next call on this workspace (a call that reuses the
+    // reference side does not memset the control block)
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctrl->absmax_q_bits = 0u;
     if (ctrl->engine != GM_ENG_EXACT3) return;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M * N) return;
@@ -1649,6 +1652,7 @@ gm_refine_kernel(const FrParams P) {
     __shared__ float res_d[8][32][FR_GROUP_COLS];                        // exact distances / original indices of a served lane's group
     __shared__ int res_i[8][32][FR_GROUP_COLS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) P.ctrl->absmax_q_bits = 0u;      // see gm_finalize_kernel
     if (P.ctrl->engine != GM_ENG_FR) return;
     const int64_t row0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;
     const int obj = blockIdx.y;
@@ -1946,8 +1950,12 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
     pre.reuse = reuse ? 1 : 0;
 
     profile_begin(PROF_GLOBAL_PREPASS, stream);
-    cudaError_t e = cudaMemsetAsync(ctrl, 0, reuse ? GM_CTRL_FRAME_BYTES : sizeof(GmCtrl), stream);
-    if (e != cudaSuccess) { set_error("global match: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+    // a call that reuses the reference side finds the per-call prefix already clean: the previous call's last kernels zeroed
+    // the query's |x| max, its pre-pass zeroes the rescan counter (one launch less on the critical path)
+    if (!reuse) {
+        cudaError_t e = cudaMemsetAsync(ctrl, 0, sizeof(GmCtrl), stream);
+        if (e != cudaSuccess) { set_error("global match: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+    }
     const int64_t R_scan = reuse ? 0 : R;
     const int64_t items = R_scan + M;
     dim3 g1((unsigned)(ceil_div64(items, 256) < 148 * 8 ? ceil_div64(items, 256) : 148 * 8), GM_SCAN_CG);
@@ -1987,6 +1995,7 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
                  reinterpret_cast<float2*>(wbase + p.off_keys), reinterpret_cast<uint32_t*>(wbase + p.off_tags), p.M_pad, p.n_mtiles / 4,
                  ksteps, p.seg_tiles, 0);
         profile_end(PROF_GLOBAL_UMMA, stream);
+        if (step_gates().after_global_gemm) cudaEventRecord(step_gates().after_global_gemm, stream);
         profile_begin(PROF_GLOBAL_REFINE, stream);
         launch_k(gm_refine_kernel, dim3((unsigned)ceil_div64(M, 256), (unsigned)N), dim3(256), 0, stream, F);
         profile_end(PROF_GLOBAL_REFINE, stream);
@@ -2005,7 +2014,8 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
             count_launch(), gm_umma_kernel<<<sm_count, GM_THREADS, GM_SMEM_TOTAL, stream>>>(Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles, N, ksteps, ksteps_lo);
         else
             launch_k(gm_umma2_kernel, dim3(sm_count & ~1), dim3(GM_THREADS), (size_t)G2_SMEM_TOTAL, stream, Aimg, Bimg, ysn, tile_obj, ctrl, best, p.n_mtiles / 2, N, ksteps, ksteps_lo);
-        launch_k(gm_finalize_kernel, dim3((unsigned)ceil_div64(M * N, 256)), dim3(256), 0, stream, best, xs, ctrl, M, N, normalize, mem_frame, out);
+        if (!run_fr && step_gates().after_global_gemm) cudaEventRecord(step_gates().after_global_gemm, stream);
+        launch_k(gm_finalize_kernel, dim3((unsigned)ceil_div64(M * N, 256)), dim3(256), 0, stream, (const int*)best, (const float*)xs, ctrl, M, N, normalize, mem_frame, out);
         profile_end(PROF_GLOBAL_EXACT3, stream);
     }
     return check_launch("global match (tcgen05) kernels");

@@ -1107,6 +1107,7 @@ int launch_local_match_umma(const float* prev, int64_t p_sy, int64_t p_sx, int64
         cudaFuncSetAttribute(lm_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     profile_begin(PROF_LOCAL_WINDOW, stream);
+    if (step_gates().local_main_gate) cudaStreamWaitEvent(stream, step_gates().local_main_gate, 0);
     if (labels) launch_k(lm_umma_kernel<false>, dim3(2 * n_tiles), dim3(LM_THREADS), (size_t)g.total, stream, P);
     else launch_k(lm_umma_kernel<true>, dim3(2 * n_tiles), dim3(LM_THREADS), (size_t)g.total, stream, P);
     profile_end(PROF_LOCAL_WINDOW, stream);
