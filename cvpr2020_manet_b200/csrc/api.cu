@@ -570,8 +570,9 @@ manet_session_t* manet_session_create(int H, int W, int C, int N, int max_distan
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     const bool use_prio = !(e_prio && !strcmp(e_prio, "0"));
-    bool ok = cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, use_prio ? prio_hi : 0) == cudaSuccess &&
-              cudaStreamCreateWithPriority(&s->local_stream, cudaStreamNonBlocking, use_prio ? prio_lo : 0) == cudaSuccess &&
+    const bool swap_prio = e_prio && !strcmp(e_prio, "swap");       // experiment: the local branch on the high-priority stream
+    bool ok = cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, !use_prio ? 0 : swap_prio ? prio_lo : prio_hi) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&s->local_stream, cudaStreamNonBlocking, !use_prio ? 0 : swap_prio ? prio_hi : prio_lo) == cudaSuccess &&
               cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) == cudaSuccess &&

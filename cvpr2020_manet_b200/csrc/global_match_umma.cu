@@ -1116,12 +1116,13 @@ __global__ void gm_finalize_kernel(const int* __restrict__ best, const float* __
 //   => the reference row with the largest TRUE score has  s~ >= max s~ - 2E.
 //
 // The epilogue therefore keeps, per query row and per SEGMENT-half (128 columns of seg_tiles consecutive tiles of one
-// object), the two largest keys; a key is the maximum of two neighbouring columns with the pair's index in its low
-// mantissa bits.  gm_refine_kernel takes every key within Delta = 2E of the row's best, evaluates sum (q-r)^2 in fp32 for
-// the two rows it names and keeps the smallest; where BOTH keys of a segment-half are within Delta a third candidate could
-// hide behind them, so that segment-half is re-scanned exactly (gm_rescan_kernel, a work list that is empty for all but
-// near-tied data).  The result is the true per-object minimum of the fp32 distances whatever the data; only the speed
-// depends on how many near-ties there are.
+// object), the two largest keys; a key is the maximum of four neighbouring columns with the group's index in its low
+// mantissa bits.  gm_refine_kernel evaluates sum (q-r)^2 in fp32 for the four rows the row's largest key names; that fixes
+// the best TRUE score found so far, S >= max s~ - E, and an unevaluated row can still win only if its s~ >= S - E.  Every
+// other key in that window has its group evaluated too; where BOTH keys of a segment-half are in the window a third
+// candidate could hide behind them, so that segment-half is re-scanned exactly (gm_rescan_kernel, a work list of a few
+// hundred entries at 480p).  The result is the true per-object minimum of the fp32 distances whatever the data; only the
+// speed depends on how many near-ties there are.
 constexpr int FR_GROUP_COLS = 4;                                // neighbouring reference columns that share one key
 constexpr int FR_GROUPS = GM_BN / 2 / FR_GROUP_COLS;            // groups per 128-column half tile
                                                                 // ... whose index takes the low 5 mantissa bits of a key (fr_key)
@@ -1192,7 +1193,7 @@ template <bool SEG1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FR_THREADS, 1)
 gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg, const float* __restrict__ ysn,
              const int* __restrict__ tile_seg, const int* __restrict__ seg_tile0, const GmCtrl* __restrict__ ctrl,
-             float2* __restrict__ keys, uint32_t* __restrict__ tags, int64_t M_pad, int n_quads, int ksteps, int seg_tiles,
+             float* __restrict__ keys, int64_t ky_off, uint32_t* __restrict__ tags, int64_t M_pad, int n_quads, int ksteps, int seg_tiles,
              int rt_zero) {
     pdl_enter();
     if (ctrl->engine != GM_ENG_FR) return;              // served by the three-product chain (uniform over the grid: nothing allocated yet)
@@ -1379,7 +1380,8 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
         int sg = 0, sg_t0 = 0;
         if (!SEG1 && any) { sg = __ldg(tile_seg + rt); sg_t0 = __ldg(seg_tile0 + sg); }
         // SEG1: where this thread's keys of (q, rt, a = 0) go; a = 1 is 2 * GM_BM entries further on
-        float2* kp = keys + ((size_t)rt * 2 + half) * (size_t)M_pad + (size_t)(4 * q + rank) * GM_BM + row;
+        // (first keys and second keys are two arrays, ky_off apart: the refinement reads all of the first, few of the second)
+        float* kp = keys + ((size_t)rt * 2 + half) * (size_t)M_pad + (size_t)(4 * q + rank) * GM_BM + row;
 #if defined(FR_EXP_NOLOAD)
 #define FR_LD(addr, dst) do { asm volatile("" : "+r"(dst[0]), "+r"(dst[31]) : "r"(addr)); } while (0)     /* experiment: arithmetic only */
 #pragma unroll
@@ -1442,7 +1444,7 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
                 unit(std::integral_constant<int, 0>{}); unit(std::integral_constant<int, 1>{});
                 unit(std::integral_constant<int, 2>{}); unit(std::integral_constant<int, 3>{});
                 const float M1 = fmaxf(a1, b1), M2 = fmaxf(fmaxf(fminf(a1, b1), a2), b2);
-                if (SEG1) { kp[a * 2 * GM_BM] = make_float2(M1, M2); return; }
+                if (SEG1) { kp[a * 2 * GM_BM] = M1; kp[ky_off + a * 2 * GM_BM] = M2; return; }
                 // merge this tile's two best into the segment's
                 if (M1 > V1a) {
                     if (M2 > V1a) { V2a = M2; T2a = toff; } else { V2a = V1a; T2a = T1a; }
@@ -1450,7 +1452,7 @@ gm_fr_kernel(const uint8_t* __restrict__ Aimg, const uint8_t* __restrict__ Bimg,
                 } else if (M1 > V2a) { V2a = M1; T2a = toff; }
                 if (seg_ends) {
                     const size_t e = ((size_t)sg * 2 + half) * (size_t)M_pad + (size_t)(4 * q + 2 * a + rank) * GM_BM + row;
-                    keys[e] = make_float2(V1a, V2a);
+                    keys[e] = V1a; keys[ky_off + e] = V2a;
                     if (seg_tiles > 1) tags[e] = T1a | (T2a << 16);
                     V1a = V2a = FR_NEG; T1a = T2a = 0;
                 }
@@ -1488,7 +1490,7 @@ constexpr int FR_SMEM_TOTAL = 4 * GM_CHUNK_BYTES + G2_STAGES * G2_STAGE_BYTES + 
 
 // ---- refinement
 struct FrParams {
-    const float2* keys; const uint32_t* tags; const float* q32; const float* r32; const float2* qn; const int* src_idx;
+    const float* kx; const float* ky; const uint32_t* tags; const float* q32; const float* r32; const float2* qn; const float* xs; const int* src_idx;
     const int* seg_tile0; GmCtrl* ctrl;
     int4* rescan; int rescan_cap;
     unsigned long long* best64;        // arg-min mode: (distance bits << 32 | original reference index) per (query, object)
@@ -1548,6 +1550,8 @@ __device__ __forceinline__ void fr_group_dist(const float* __restrict__ q32, con
 // rows l, l+32, ... of each 128-row half tile.  The query row is staged in the warp's shared-memory slab `q_sm` (GM_MAXC
 // floats); a reference row is fetched with all of its loads in flight at once.  Returns the packed (distance, original
 // index) minimum in every lane.
+// RB = reference-row chunks fetched per batch (8 or 16: the order of the additions does not depend on it)
+template <int RB>
 __device__ __forceinline__ unsigned long long fr_warp_rescan(const FrParams& P, int64_t qrow, int obj, int entry, int lane,
                                                              float* __restrict__ q_sm, int col0 = 0, int ncol = GM_BN / 2) {
     const int sg = entry >> 1, half = entry & 1;
@@ -1569,12 +1573,12 @@ __device__ __forceinline__ unsigned long long fr_warp_rescan(const FrParams& P, 
             // a pair's distance has ONE value whichever path evaluates it, so results do not depend on the reference order
             float p[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int c0 = 0; c0 < 32; c0 += 16) {
-                float4 a[16];                                            // unconditional loads (clamped index): all in flight at once
+            for (int c0 = 0; c0 < 32; c0 += RB) {
+                float4 a[RB];                                            // unconditional loads (clamped index): all in flight at once
 #pragma unroll
-                for (int u = 0; u < 16; ++u) a[u] = __ldg(r + min(c0 + u, nc - 1));
+                for (int u = 0; u < RB; ++u) a[u] = __ldg(r + min(c0 + u, nc - 1));
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
+                for (int u = 0; u < RB; ++u) {
                     // branch-free: a chunk beyond the row contributes (a - a)^2 = 0 (q_sm holds GM_MAXC floats, reads stay inside)
                     const float4 x = (c0 + u < nc) ? q[c0 + u] : a[u];
                     float t;
@@ -1645,7 +1649,15 @@ __device__ __forceinline__ void fr_merge(const FrParams& P, int64_t i, unsigned 
     if (P.mem != nullptr) atomicMin(reinterpret_cast<int*>(P.mem + i), __float_as_int(d));
 }
 
-// one warp = 32 consecutive query rows x one object
+// one warp = 32 consecutive query rows x one object.
+//   pass 1   the largest key V of the row and where it sits
+//   round 0  the group that key names is evaluated exactly: the best TRUE score found so far, S = s_q s_r/2 (|q|^2 - d*),
+//            is now known (to fp32 rounding), and  S >= V - E
+//   pass 2   an unevaluated row j can still win only if  s_j >= S,  and  s_j <= s~_j + E  -- so only keys >= S - E matter
+//            (a window of E below the best instead of the 2E the approximate maximum alone would give: half the second
+//            candidates, half the rescans); where both keys of a segment half pass, a third could hide behind them and
+//            the half goes to the rescan list
+//   round 1  the (rare) second candidates
 __global__ void __launch_bounds__(256, 3)
 gm_refine_kernel(const FrParams P) {
     pdl_enter();
@@ -1666,81 +1678,56 @@ gm_refine_kernel(const FrParams P) {
     }
     const int e0 = 2 * P.ctrl->seg_first[obj], e1 = 2 * P.ctrl->seg_first[obj + 1];
     const int64_t end = (int64_t)P.ctrl->offsets[obj] + count;
-    // Delta = 2E (see the header of this section), in the units of the accumulator
-    float delta = 0.f;
-    if (valid) {
-        const float2 n = P.qn[row];
-        const float Bh = __uint_as_float(P.ctrl->rh_max_bits[obj]), Bl = __uint_as_float(P.ctrl->rl_max_bits[obj]);
-        const float bias = 0.5f * (P.ctrl->scale_q * P.ctrl->scale_r) * __uint_as_float(P.ctrl->rsq_max_bits[obj]) * 1.000001f;
-        delta = 2.0f * (n.y * Bh + n.x * Bl + n.y * Bl) + 6.2e-5f * (n.x * Bh + bias);      // 6.2e-5 ~ 2^-14: accumulator + index bits, both sides
-        delta = delta * 1.0001f + 1e-30f;
-    }
     const size_t rq = valid ? (size_t)row : (size_t)row0;               // rows beyond M read row0's keys (results discarded)
-    // Both passes over the segment halves load FR_BATCH keys at a time with independent loads: the kernel's time is the
-    // length of its chain of dependent L2 round trips, not its instruction count.
+    const float half_ss = 0.5f * (P.ctrl->scale_q * P.ctrl->scale_r);
+    // E (see the header of this section), in the units of the accumulator, rounded up
+    float E = 0.f, qsq = 0.f;
+    {
+        const float2 n = P.qn[rq];
+        const float Bh = __uint_as_float(P.ctrl->rh_max_bits[obj]), Bl = __uint_as_float(P.ctrl->rl_max_bits[obj]);
+        const float bias = half_ss * __uint_as_float(P.ctrl->rsq_max_bits[obj]) * 1.000001f;
+        E = (n.y * Bh + n.x * Bl + n.y * Bl) + 3.1e-5f * (n.x * Bh + bias);      // 3.1e-5 ~ 2^-15: accumulator + index bits
+        E = E * 1.0001f + 1e-30f;
+        qsq = P.xs[rq];
+    }
+    // One pass over the first keys, FR_BATCH independent loads at a time (the kernel's time is the length of its chain of
+    // dependent L2 round trips): the three largest and their segment halves.  Everything that can matter later lies within
+    // 2E of the largest, and more than three such halves are rare (they take the slow path below).
     constexpr int FR_BATCH = 8;
-    float V = FR_NEG;
+    float K0 = FR_NEG, K1 = FR_NEG, K2 = FR_NEG; int h0 = e0, h1 = e0, h2 = e0;
     for (int eb = e0; eb < e1; eb += FR_BATCH) {
         float kx[FR_BATCH];
 #pragma unroll
-        for (int u = 0; u < FR_BATCH; ++u) kx[u] = (eb + u < e1) ? __ldg(&P.keys[(size_t)(eb + u) * P.M_pad + rq].x) : FR_NEG;
+        for (int u = 0; u < FR_BATCH; ++u) kx[u] = (eb + u < e1) ? __ldg(P.kx + (size_t)(eb + u) * P.M_pad + rq) : FR_NEG;
 #pragma unroll
-        for (int u = 0; u < FR_BATCH; ++u) V = fmaxf(V, kx[u]);
+        for (int u = 0; u < FR_BATCH; ++u) {
+            const float k = kx[u]; const int e = eb + u;
+            const bool g0 = k > K0, g1 = k > K1, g2 = k > K2;
+            K2 = g1 ? K1 : (g2 ? k : K2); h2 = g1 ? h1 : (g2 ? e : h2);
+            K1 = g0 ? K0 : (g1 ? k : K1); h1 = g0 ? h0 : (g1 ? e : h1);
+            K0 = g0 ? k : K0;             h0 = g0 ? e : h0;
+        }
     }
-    const float thr = V - delta;
-    // candidates: up to two per lane are evaluated here, everything else goes to the rescan list
-    int cand0 = 0, cand1 = 0, ncand = 0;
+    // second keys (and tile offsets) of those three halves; a row with fewer than three halves repeats a valid address
+    float Y0, Y1, Y2; uint32_t t0 = 0, t1 = 0, t2 = 0;
+    Y0 = __ldg(P.ky + (size_t)h0 * P.M_pad + rq); Y1 = __ldg(P.ky + (size_t)h1 * P.M_pad + rq); Y2 = __ldg(P.ky + (size_t)h2 * P.M_pad + rq);
+    if (P.seg_tiles > 1) {
+        t0 = __ldg(&P.tags[(size_t)h0 * P.M_pad + rq]); t1 = __ldg(&P.tags[(size_t)h1 * P.M_pad + rq]); t2 = __ldg(&P.tags[(size_t)h2 * P.M_pad + rq]);
+    }
+    // candidate = (segment half e < 2^10: FR_MAX_SEGS, tile offset within the segment, group within the half tile)
+    const int cand0 = (h0 << 22) | ((int)(t0 & 0xffffu) << 6) | (int)(__float_as_uint(K0) & (uint32_t)(FR_GROUPS - 1));
+    int cand1 = 0; bool have1 = false;
     unsigned long long best = fr_pack(INFINITY, 0x7fffffff);
-    for (int eb = e0; eb < e1; eb += FR_BATCH) {
-        float2 kk[FR_BATCH]; uint32_t tg[FR_BATCH];
-#pragma unroll
-        for (int u = 0; u < FR_BATCH; ++u) {
-            const bool in = eb + u < e1;
-            kk[u] = in ? __ldg(&P.keys[(size_t)(eb + u) * P.M_pad + rq]) : make_float2(FR_NEG, FR_NEG);
-            tg[u] = (in && P.seg_tiles > 1) ? __ldg(&P.tags[(size_t)(eb + u) * P.M_pad + rq]) : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < FR_BATCH; ++u) {
-            const int e = eb + u;
-            if (e >= e1) break;                                         // uniform
-            const float2 k = kk[u];
-            const bool c1 = valid && k.x >= thr, c2 = valid && k.y >= thr;
-            bool need = c1 && (c2 || ncand == 2);
-            if (c1 && !need) {
-                const int cd = (e << 22) | ((int)(tg[u] & 0xffffu) << 6) | (int)(__float_as_uint(k.x) & (uint32_t)(FR_GROUPS - 1));   // e < 2^10: FR_MAX_SEGS
-                if (ncand == 0) cand0 = cd; else cand1 = cd;
-                ++ncand;
-            }
-            // (rescanning the occasional near-tie right here, by the whole warp, was tried: the 31 idle lanes' wait made the
-            // kernel 50 us slower than handing the entries to gm_rescan_kernel, which costs 19 us in all)
-            const unsigned mask = __ballot_sync(0xffffffffu, need);
-            if (mask) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&P.ctrl->rescan_count, __popc(mask));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                const int slot = base + __popc(mask & ((1u << lane) - 1u));
-                if (need && slot < P.rescan_cap) { P.rescan[slot] = make_int4((int)(row & 0x7fffffff), obj, e, (int)(row >> 31)); need = false; }
-                // list full (pathological near-tie counts): rescan right here, one lane's segment-half at a time
-                unsigned over = __ballot_sync(0xffffffffu, need);
-                while (over) {
-                    const int src = __ffs(over) - 1;
-                    const unsigned long long v = fr_warp_rescan_cold(P, row0 + src, obj, e, lane);
-                    if (lane == src) best = v < best ? v : best;
-                    over &= over - 1;
-                }
-            }
-        }
-    }
-    // Evaluate.  First candidates (every lane has one unless its best segment half went to the rescan list): round r, quarter
-    // warp k serves lane 4r + k.  Second candidates are rare: their lanes are served four at a time from a ballot.
 #pragma unroll 1
     for (int ci = 0; ci < 2; ++ci) {
-        unsigned todo = __ballot_sync(0xffffffffu, ncand > ci);
+        // Evaluate.  Round 0: every lane has a candidate; quarter warp k serves lane 4r + k in step r.  Round 1: the lanes with a
+        // second candidate are served four at a time from a ballot.
+        unsigned todo = __ballot_sync(0xffffffffu, ci == 0 ? true : have1);
 #pragma unroll 1
         for (int r = 0; todo != 0u; ++r) {
             int src;                                                    // the lane this quarter warp serves (-1: none)
             unsigned served;
-            if (ci == 0) { src = 4 * r + (lane >> 3); served = 0xfu << (4 * r); if (!((todo >> src) & 1u)) src = -1; }
+            if (ci == 0) { src = 4 * r + (lane >> 3); served = 0xfu << (4 * r); }
             else {
                 // k-th set bit of `todo` for quarter k
                 unsigned t = todo; served = 0u; src = -1;
@@ -1761,7 +1748,8 @@ gm_refine_kernel(const FrParams P) {
                 if ((lane & 7) < FR_GROUP_COLS) sidx[0] = __ldg(P.src_idx + pos + (lane & 7));      // goes out with the row loads
                 // only the quarter warps that serve a lane get here: their shuffles name just their own 8 lanes.  Rows beyond
                 // the object's last one (bucket padding, r32 holds nothing there) are read but cut below; r32 has slack rows.
-                fr_group_dist(P.q32, P.r32, P.C4, row0 + src, pos, lane & 7, 0xffu << (lane & 24), d);
+                // (A row beyond M is served like the last real row: its result is discarded.)
+                fr_group_dist(P.q32, P.r32, P.C4, min(row0 + src, P.M - 1), pos, lane & 7, 0xffu << (lane & 24), d);
 #pragma unroll
                 for (int k = 0; k < FR_GROUP_COLS; ++k) if (pos + k >= end) d[k] = INFINITY;
 #pragma unroll
@@ -1775,7 +1763,7 @@ gm_refine_kernel(const FrParams P) {
             }
         }
         __syncwarp();
-        if (ncand > ci) {
+        if (ci == 0 || have1) {
 #pragma unroll
             for (int k = 0; k < FR_GROUP_COLS; ++k) {
                 const float rk = res_d[wid][lane][k];
@@ -1783,11 +1771,78 @@ gm_refine_kernel(const FrParams P) {
             }
         }
         __syncwarp();
+        if (ci == 1) break;
+        // ---- which other keys can still hide a better row
+        float thr;
+        {
+            const float dstar = __uint_as_float((unsigned)(best >> 32));
+            // S rounded DOWN, minus E: (C + 2) 2^-24 < 8e-6 per fp32 sum -- |q|^2, d*, and the rival's own distance.  An infinite
+            // d* (the group was all bucket padding) leaves thr = -inf: everything is a candidate.
+            const float S = half_ss * (qsq - dstar);
+            thr = S - E - 2.5e-5f * half_ss * (qsq + dstar) - 1e-30f;
+            if (!(dstar < INFINITY)) thr = -INFINITY;
+        }
+        // a segment half goes to the rescan list (or, list full, is scanned right here)
+        auto push = [&](bool need, int e) {
+            const unsigned mask = __ballot_sync(0xffffffffu, need);
+            if (mask == 0u) return;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&P.ctrl->rescan_count, __popc(mask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int slot = base + __popc(mask & ((1u << lane) - 1u));
+            if (need && slot < P.rescan_cap) { P.rescan[slot] = make_int4((int)(row & 0x7fffffff), obj, e, (int)(row >> 31)); need = false; }
+            // list full (pathological near-tie counts): one lane's segment half at a time, by the whole warp
+            // (doing this for EVERY near-tie was tried: the 31 idle lanes' wait made the kernel 50 us slower than the list)
+            unsigned over = __ballot_sync(0xffffffffu, need);
+            while (over) {
+                const int src = __ffs(over) - 1;
+                const int es = __shfl_sync(0xffffffffu, e, src);
+                const unsigned long long v = fr_warp_rescan_cold(P, row0 + src, obj, es, lane);
+                if (lane == src) best = v < best ? v : best;
+                over &= over - 1;
+            }
+        };
+        // the three remembered halves.  Both keys pass: a third one could hide behind them -> the whole half.  Only the first
+        // passes: its group -- already evaluated for half 0, the lane's one extra slot otherwise, the whole half if that is taken.
+        const bool real1 = h1 != h0, real2 = h2 != h1 && h2 != h0;      // fewer than three halves: repeats
+        {
+            const bool c2 = valid && Y0 >= thr;
+            push(c2, h0);
+        }
+        {
+            const bool c1 = valid && real1 && K1 >= thr, c2 = c1 && Y1 >= thr;
+            if (c1 && !c2) { cand1 = (h1 << 22) | ((int)(t1 & 0xffffu) << 6) | (int)(__float_as_uint(K1) & (uint32_t)(FR_GROUPS - 1)); have1 = true; }
+            push(c2, h1);
+        }
+        bool ovf;
+        {
+            const bool c1 = valid && real2 && K2 >= thr, c2 = c1 && Y2 >= thr;
+            const bool fresh = c1 && !c2;
+            if (fresh && !have1) { cand1 = (h2 << 22) | ((int)(t2 & 0xffffu) << 6) | (int)(__float_as_uint(K2) & (uint32_t)(FR_GROUPS - 1)); }
+            push(c2 || (fresh && have1), h2);
+            have1 = have1 || fresh;
+            ovf = c1;                                                   // the third passes: a fourth might
+        }
+        // slow path: some lane may have more than three halves in its window -- every further one goes to the list whole
+        if (__any_sync(0xffffffffu, ovf)) {
+            for (int eb = e0; eb < e1; eb += FR_BATCH) {
+                float kx[FR_BATCH];
+#pragma unroll
+                for (int u = 0; u < FR_BATCH; ++u) kx[u] = (eb + u < e1) ? __ldg(P.kx + (size_t)(eb + u) * P.M_pad + rq) : FR_NEG;
+#pragma unroll
+                for (int u = 0; u < FR_BATCH; ++u) {
+                    const int e = eb + u;
+                    if (e >= e1) break;                                 // uniform
+                    push(ovf && kx[u] >= thr && e != h0 && e != h1 && e != h2, e);
+                }
+            }
+        }
     }
     if (valid) fr_store(P, row * P.N + obj, best);
 }
 
-// the rescan work list (normally empty): four warps per entry, a quarter of each 128-column half tile each
+// the rescan work list (normally short: ~350 entries at 480p with dense labels): four warps per entry, a quarter of each
+// 128-column half tile each.  (A 64-register variant with twice the blocks and half the loads per batch was slower.)
 __global__ void __launch_bounds__(256)
 gm_rescan_kernel(const FrParams P) {
     pdl_enter();
@@ -1799,7 +1854,7 @@ gm_rescan_kernel(const FrParams P) {
     for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < 4 * n; i += nwarps) {
         const int4 it = P.rescan[i >> 2];
         const int64_t row = (int64_t)(unsigned)it.x | ((int64_t)it.w << 31);
-        const unsigned long long v = fr_warp_rescan(P, row, it.y, it.z, lane, q_slab[threadIdx.x >> 5], (i & 3) * 32, 32);
+        const unsigned long long v = fr_warp_rescan<16>(P, row, it.y, it.z, lane, q_slab[threadIdx.x >> 5], (i & 3) * 32, 32);
         if (lane == 0) fr_merge(P, row * P.N + it.y, v);
     }
 }
@@ -1983,8 +2038,8 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
     if (run_fr) {
         FrParams F;
         memset(&F, 0, sizeof(F));
-        F.keys = reinterpret_cast<const float2*>(wbase + p.off_keys); F.tags = reinterpret_cast<const uint32_t*>(wbase + p.off_tags);
-        F.q32 = pre.q32; F.r32 = pre.r32; F.qn = pre.qn; F.src_idx = pre.src_idx; F.seg_tile0 = pre.seg_tile0; F.ctrl = ctrl;
+        F.kx = reinterpret_cast<const float*>(wbase + p.off_keys); F.ky = F.kx + (size_t)p.max_segs * 2 * p.M_pad; F.tags = reinterpret_cast<const uint32_t*>(wbase + p.off_tags);
+        F.q32 = pre.q32; F.r32 = pre.r32; F.qn = pre.qn; F.xs = xs; F.src_idx = pre.src_idx; F.seg_tile0 = pre.seg_tile0; F.ctrl = ctrl;
         F.rescan = reinterpret_cast<int4*>(wbase + p.off_rescan); F.rescan_cap = p.rescan_cap;
         F.best64 = out_idx != nullptr ? reinterpret_cast<unsigned long long*>(wbase + p.off_best64) : nullptr;
         F.out = out; F.mem = mem_frame; F.out_idx = out_idx;
@@ -1992,7 +2047,7 @@ int launch_global_match_umma(const float* ref, int64_t rps, int64_t rcs, int64_t
         profile_begin(PROF_GLOBAL_UMMA, stream);
         launch_k(p.seg_tiles == 1 ? gm_fr_kernel<true> : gm_fr_kernel<false>, dim3(sm_count & ~1), dim3(FR_THREADS), (size_t)FR_SMEM_TOTAL, stream, (const uint8_t*)Aimg, (const uint8_t*)Bimg,
                  (const float*)ysn, (const int*)pre.tile_seg, (const int*)pre.seg_tile0, (const GmCtrl*)ctrl,
-                 reinterpret_cast<float2*>(wbase + p.off_keys), reinterpret_cast<uint32_t*>(wbase + p.off_tags), p.M_pad, p.n_mtiles / 4,
+                 reinterpret_cast<float*>(wbase + p.off_keys), (int64_t)p.max_segs * 2 * p.M_pad, reinterpret_cast<uint32_t*>(wbase + p.off_tags), p.M_pad, p.n_mtiles / 4,
                  ksteps, p.seg_tiles, 0);
         profile_end(PROF_GLOBAL_UMMA, stream);
         if (step_gates().after_global_gemm) cudaEventRecord(step_gates().after_global_gemm, stream);
