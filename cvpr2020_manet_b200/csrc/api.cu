@@ -524,7 +524,7 @@ struct SessionSlot {
     int32_t *h_ref_lab, *h_prev_lab;
     float *d_ref, *d_prev, *d_cur, *d_out_g, *d_out_l, *d_raw_l; // device
     int32_t *d_ref_lab, *d_prev_lab;
-    cudaEvent_t ev_up, ev_done;
+    cudaEvent_t ev_up, ev_comp, ev_done;                          // inputs uploaded | kernels done | maps downloaded
     bool submitted;                                             // ev_done has been recorded at least once
 };
 
@@ -536,6 +536,7 @@ struct manet_session {
     bool gate_local;              // local branch's main kernel waits for the global branch's GEMM kernel (see session_step_slot)
     cudaEvent_t ev_gemm;
     cudaStream_t copy_stream;     // host->device stream
+    cudaStream_t down_stream;     // device->host stream (the two result maps)
     cudaEvent_t ev_fork, ev_join;
     SessionSlot slot[2];
     int32_t* d_ids;
@@ -574,6 +575,7 @@ manet_session_t* manet_session_create(int H, int W, int C, int N, int max_distan
     bool ok = cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, !use_prio ? 0 : swap_prio ? prio_lo : prio_hi) == cudaSuccess &&
               cudaStreamCreateWithPriority(&s->local_stream, cudaStreamNonBlocking, !use_prio ? 0 : swap_prio ? prio_hi : prio_lo) == cudaSuccess &&
               cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&s->down_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&s->ev_gemm, cudaEventDisableTiming) == cudaSuccess;
@@ -588,6 +590,7 @@ manet_session_t* manet_session_create(int H, int W, int C, int N, int max_distan
              cudaMalloc(&t.d_out_l, map) == cudaSuccess && cudaMalloc(&t.d_raw_l, map) == cudaSuccess &&
              cudaMalloc(&t.d_ref_lab, px * 4) == cudaSuccess && cudaMalloc(&t.d_prev_lab, px * 4) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&t.ev_up, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&t.ev_comp, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&t.ev_done, cudaEventDisableTiming) == cudaSuccess;
     }
     ok = ok && cudaMalloc(&s->d_ids, N * 4) == cudaSuccess && cudaMalloc(&s->d_gmem, map * n_frames) == cudaSuccess &&
@@ -621,12 +624,14 @@ void manet_session_destroy(manet_session_t* s) {
         cudaFree(t.d_ref); cudaFree(t.d_prev); cudaFree(t.d_cur); cudaFree(t.d_out_g); cudaFree(t.d_out_l); cudaFree(t.d_raw_l);
         cudaFree(t.d_ref_lab); cudaFree(t.d_prev_lab);
         if (t.ev_up) cudaEventDestroy(t.ev_up);
+        if (t.ev_comp) cudaEventDestroy(t.ev_comp);
         if (t.ev_done) cudaEventDestroy(t.ev_done);
     }
     cudaFree(s->d_ids); cudaFree(s->d_gmem); cudaFree(s->d_lmem); cudaFree(s->d_ldist); cudaFree(s->ws_g); cudaFree(s->ws_l);
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->local_stream) cudaStreamDestroy(s->local_stream);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+    if (s->down_stream) cudaStreamDestroy(s->down_stream);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->ev_gemm) cudaEventDestroy(s->ev_gemm);
@@ -772,10 +777,14 @@ int manet_session_submit_host(manet_session_t* s, int slot, int frame, int inter
         rc = session_step_slot(s, slot, frame, interaction_num, start_annotated_frame, flags);
         if (rc) return rc;
     }
+    // The two maps go back on their own stream (and copy engine): on the compute stream they would sit between this step's
+    // kernels and the next step's (the other slot's) -- ~40 us per step of a pipelined caller.
     const size_t map = (size_t)s->H * s->W * s->N * sizeof(float);
-    cudaMemcpyAsync(t.h_out_g, t.d_out_g, map, cudaMemcpyDeviceToHost, s->stream);
-    cudaMemcpyAsync(t.h_out_l, t.d_out_l, map, cudaMemcpyDeviceToHost, s->stream);
-    cudaEventRecord(t.ev_done, s->stream);
+    cudaEventRecord(t.ev_comp, s->stream);
+    cudaStreamWaitEvent(s->down_stream, t.ev_comp, 0);
+    cudaMemcpyAsync(t.h_out_g, t.d_out_g, map, cudaMemcpyDeviceToHost, s->down_stream);
+    cudaMemcpyAsync(t.h_out_l, t.d_out_l, map, cudaMemcpyDeviceToHost, s->down_stream);
+    cudaEventRecord(t.ev_done, s->down_stream);
     t.submitted = true;
     return check_launch("session submit");
 }
@@ -797,6 +806,7 @@ int manet_session_sync(manet_session_t* s) {
     MANET_REQUIRE(s, "session: null");
     cudaError_t e = cudaStreamSynchronize(s->copy_stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->down_stream);
     if (e != cudaSuccess) { set_error("session sync: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;
 }
