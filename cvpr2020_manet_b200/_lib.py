@@ -71,6 +71,7 @@ SIGNATURES = {
     "manet_profile_enable": (c_int, [_I]),
     "manet_profile_reset": (c_int, []),
     "manet_profile_read": (c_int, [_I, POINTER(c_float), _I, POINTER(c_int)]),
+    "manet_profile_read_span": (c_int, [_I, _I, POINTER(c_float), POINTER(c_float), _I, POINTER(c_int)]),
     "manet_profile_launch_count": (ctypes.c_longlong, []),
     "manet_profile_reset_launches": (c_int, []),
     "manet_global_match_stats": (c_int, [_P, POINTER(c_int32), _P]),

@@ -484,6 +484,20 @@ int manet_profile_read(int slot, float* ms_out, int capacity, int* n_out) {
     return 0;
 }
 
+int manet_profile_read_span(int slot, int ref_slot, float* start_ms, float* stop_ms, int capacity, int* n_out) {
+    MANET_REQUIRE(slot >= 0 && slot < PROF_SLOTS && ref_slot >= 0 && ref_slot < PROF_SLOTS && n_out && start_ms && stop_ms, "profile: bad slot");
+    ProfPool& p = g_prof[slot]; ProfPool& r = g_prof[ref_slot];
+    int n = p.n < r.n ? p.n : r.n;
+    if (n > capacity) n = capacity;
+    for (int i = 0; i < n; ++i) {
+        cudaError_t e = cudaEventElapsedTime(&start_ms[i], r.start[i], p.start[i]);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&stop_ms[i], r.start[i], p.stop[i]);
+        if (e != cudaSuccess) { set_error("profile: %s (synchronise the streams first)", cudaGetErrorString(e)); return (int)e; }
+    }
+    *n_out = n;
+    return 0;
+}
+
 int manet_global_match_stats(void* workspace, int32_t* stats_host, manet_stream_t stream) {
     MANET_ARCH();
     MANET_REQUIRE(workspace && stats_host, "global match stats: null pointer");

@@ -354,6 +354,9 @@ int manet_rough_roi(const int32_t* labels, int batch, int H, int W, int dist, in
 int manet_profile_enable(int max_records);
 int manet_profile_reset(void);
 int manet_profile_read(int slot, float* ms_out, int capacity, int* n_out);
+/* where a slot's records lie on the time axis: start/stop of record i relative to the START of record i of `ref_slot` (ms, may
+ * be negative) -- the timeline of a step whose branches run on different streams */
+int manet_profile_read_span(int slot, int ref_slot, float* start_ms, float* stop_ms, int capacity, int* n_out);
 /* number of kernels of this library launched by the calling process since the last manet_profile_reset_launches()
  * (every launcher counts its own <<<>>>; cudaMemcpy/cudaMemset are not counted).  bench.py's `gpu_launches`. */
 long long manet_profile_launch_count(void);
