@@ -312,8 +312,9 @@ def run_own_arm(args, rank, local_rank, world):
         k_ms = prof["global_tcgen05"]
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("global_tcgen05_dram_bytes_per_launch")
+        tfile = json.load(open(tpath)) if os.path.exists(tpath) else {}
+        traffic = tfile.get("global_exact3_dram_bytes_per_launch" if GM_EXACT3 else "global_tcgen05_dram_bytes_per_launch")
+        lm_inst = tfile.get("lm_umma_inst_executed")
         # slot 6 = the three-product chain: enqueued as well, exits at once when the pre-pass picked filter-and-refine (and vice versa)
         r_ms = (prof.get("global_refine") or 0.0) + (prof.get("global_rescan") or 0.0) + (prof.get("global_exact3") or 0.0)
         # the matching core = the tensor-core filter kernel + the exact refinement (refine + rescan); `achieved` charges both
@@ -343,7 +344,12 @@ def run_own_arm(args, rank, local_rank, world):
                               "main_kernel_ms": prof["local_main"], "prepass_ms": prof["local_prepass"],
                               "achieved_gbs": (ALGO_BYTES_LOCAL / ((prof["local_main"] + prof["local_prepass"]) * 1e-3) / 1e9)
                               if prof["local_main"] and prof["local_prepass"] else None,
-                              "peak_gbs": peaks["hbm_gbs"]}}
+                              "peak_gbs": peaks["hbm_gbs"],
+                              # what bounds lm_umma_kernel in fact: warp instructions / (4 schedulers x SMs x SM clock), from the
+                              # instruction count of the round's ncu capture (profiles/roofline_traffic.json)
+                              "issue_bound_us": (lm_inst / (4.0 * 148 * 1.965e9) * 1e6) if lm_inst else None,
+                              "issue_bound_note": "smsp__inst_executed.sum of lm_umma_kernel / (4 IPC x 148 SMs x 1.965 GHz); the kernel runs "
+                                                  "one CTA per SM (201 KB shared memory) at ~48 % issue-active"}}
         line = {"metric": "matched frames/sec (global+local, 480p, 5 obj)", "value": world * K / total_s,
                 "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": total_s * 1e3 / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (results are exact fp32 distances; candidates are filtered by an fp16 tensor-core GEMM with fp32 accumulate)",
