@@ -38,6 +38,7 @@ SIGNATURES = {
     "manet_global_match_workspace_bytes": (_SZ, [_I64, _I64, _I, _I, _I]),
     "manet_global_match": (c_int, [_P, _I64, _I64, _I64, _P, _P, _I64, _I64, _I64, _I, _I, _I, c_uint32, _P, _P, _P, _SZ, _P]),
     "manet_global_match_masked": (c_int, [_P, _I64, _I64, _I64, _P, _P, _I64, _I64, _I64, _I, _I, _I, _P, _P, _SZ, _P]),
+    "manet_global_match_topk": (c_int, [_P, _I64, _I64, _I64, _P, _P, _I64, _I64, _I64, _I, _I, _I, _P, _P]),
     "manet_pairwise_sqdist": (c_int, [_P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _I, _P, _P, _P, _P]),
     "manet_row_sqnorm": (c_int, [_P, _I64, _I64, _I64, _I, _P, _P]),
     "manet_select_labelled_workspace_bytes": (_SZ, [_I64]),

@@ -26,7 +26,7 @@ int check_launch(const char* what) {
 
 // implemented in the kernel translation units
 int launch_global_match_simt(const float*, int64_t, int64_t, int64_t, const int32_t*, const uint8_t*, const float*, int64_t,
-                             int64_t, int64_t, int, int, int, float*, cudaStream_t);
+                             int64_t, int64_t, int, int, int, float*, cudaStream_t, float* lists_out = nullptr);
 int launch_pairwise_sqdist(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, int64_t, int, float*,
                            const float*, float*, cudaStream_t);
 int launch_row_sqnorm(const float*, int64_t, int64_t, int64_t, int, float*, cudaStream_t);
@@ -189,6 +189,17 @@ int manet_global_match(const float* ref, int64_t ref_pix_stride, int64_t ref_ch_
     if (rc) return rc;
     if (normalize || mem_frame) return launch_global_map_update(out, mem_frame, out, M * N, normalize, st);
     return 0;
+}
+
+int manet_global_match_topk(const float* ref, int64_t ref_pix_stride, int64_t ref_ch_stride, int64_t R, const int32_t* labels,
+                            const float* query, int64_t q_pix_stride, int64_t q_ch_stride, int64_t M, int C, int N, int k,
+                            float* out_lists, manet_stream_t stream) {
+    MANET_ARCH();
+    MANET_REQUIRE(query && out_lists && (R == 0 || (ref && labels)), "global match (top-k): null pointer");
+    MANET_REQUIRE(M >= 0 && R >= 0 && C >= 1 && N >= 1 && k >= 1 && k <= 64, "global match (top-k): bad sizes");
+    if (M == 0) return 0;
+    return launch_global_match_simt(ref, ref_pix_stride, ref_ch_stride, R, labels, nullptr, query, q_pix_stride, q_ch_stride, M, C, N, k,
+                                    nullptr, (cudaStream_t)stream, out_lists);
 }
 
 int manet_global_match_masked(const float* ref, int64_t ref_pix_stride, int64_t ref_ch_stride, int64_t R,

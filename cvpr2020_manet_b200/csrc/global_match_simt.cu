@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(SIMT_THREADS)
 global_match_simt_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64_t R,
                          const int32_t* __restrict__ labels, const uint8_t* __restrict__ mask,
                          const float* __restrict__ query, int64_t qps, int64_t qcs, int64_t M,
-                         int C, int N, int k, float* __restrict__ out) {
+                         int C, int N, int k, float* __restrict__ out, float* __restrict__ lists_out) {
     __shared__ float Qs[CK][TQ + 1];
     __shared__ float Rs[CK][TR + 1];
     __shared__ float D[TQ][TR + 1];
@@ -113,6 +113,10 @@ global_match_simt_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs
         const int m = p % TQ, o = p / TQ;
         if (m0 + m >= M) continue;
         const float* L = lists + (size_t)p * k;
+        if (lists_out != nullptr) {              // the k smallest distances themselves (ascending, +inf = fewer than k matches)
+            for (int j = 0; j < k; ++j) lists_out[((m0 + m) * N + o) * k + j] = L[j];
+            continue;
+        }
         float res;
         if (k == 1) {
             res = (L[0] == INFINITY) ? kWrongLabelPad : L[0];
@@ -176,16 +180,16 @@ __global__ void global_map_update_kernel(const float* __restrict__ nw, float* __
 int launch_global_match_simt(const float* ref, int64_t rps, int64_t rcs, int64_t R,
                              const int32_t* labels, const uint8_t* mask,
                              const float* query, int64_t qps, int64_t qcs, int64_t M,
-                             int C, int N, int k, float* out, cudaStream_t stream) {
+                             int C, int N, int k, float* out, cudaStream_t stream, float* lists_out) {
     size_t dyn = (size_t)N * TQ * k * sizeof(float);
     if (dyn > 160 * 1024) return fail_invalid("global match: N*k too large for the CUDA-core kernel (N*k <= 640)");
     dim3 grid((unsigned)ceil_div64(M, TQ));
     if (mask != nullptr) {
         cudaFuncSetAttribute(global_match_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        count_launch(), global_match_simt_kernel<true><<<grid, SIMT_THREADS, dyn, stream>>>(ref, rps, rcs, R, nullptr, mask, query, qps, qcs, M, C, N, k, out);
+        count_launch(), global_match_simt_kernel<true><<<grid, SIMT_THREADS, dyn, stream>>>(ref, rps, rcs, R, nullptr, mask, query, qps, qcs, M, C, N, k, out, lists_out);
     } else {
         cudaFuncSetAttribute(global_match_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        count_launch(), global_match_simt_kernel<false><<<grid, SIMT_THREADS, dyn, stream>>>(ref, rps, rcs, R, labels, nullptr, query, qps, qcs, M, C, N, k, out);
+        count_launch(), global_match_simt_kernel<false><<<grid, SIMT_THREADS, dyn, stream>>>(ref, rps, rcs, R, labels, nullptr, query, qps, qcs, M, C, N, k, out, lists_out);
     }
     return check_launch("global_match_simt_kernel");
 }

@@ -369,6 +369,37 @@ def nearest_neighbor_features_per_object(reference_embeddings, query_embeddings,
     return out.view(1, h, w, n_obj, 1), ids
 
 
+def k_smallest_distances_per_object(reference_embeddings, query_embeddings, reference_labels, k_nearest_neighbors, gt_ids):
+    """The ``k`` smallest squared distances from every query pixel to the reference pixels of each object, ascending, ``+inf``
+    where an object has fewer than ``k`` reference pixels: ``[h,w,N,k]``.  This is what ONE reference-axis shard contributes
+    when ``k_nearest_neighbors > 1``: the reference averages the k smallest over all reference pixels (IntVOS.py:86-94), so
+    shards are merged list-wise (``mean_of_k_smallest``), not by a minimum."""
+    require_f32(query_embeddings, "query_embeddings")
+    h, w, c = query_embeddings.size()
+    labels = as_i32_labels(reference_labels, "reference_labels")
+    n_obj = int(gt_ids) + 1
+    ref, r, c2, rps, rcs = pixel_view(reference_embeddings, "reference_embeddings")
+    qry, m, _, qps, qcs = pixel_view(query_embeddings, "query_embeddings")
+    if c != c2:
+        raise RuntimeError("feature dims differ")
+    k = int(k_nearest_neighbors)
+    out = torch.empty(h, w, n_obj, k, dtype=torch.float32, device=query_embeddings.device)
+    _lib.check(_lib.lib().manet_global_match_topk(ref.data_ptr() if r else None, rps, rcs, r, labels.data_ptr() if r else None,
+                                                  qry.data_ptr(), qps, qcs, m, c, n_obj, k, out.data_ptr(),
+                                                  stream_ptr(query_embeddings.device)), "manet_global_match_topk")
+    return out
+
+
+def mean_of_k_smallest(lists, k_nearest_neighbors):
+    """IntVOS.py:86-94 on candidate lists ``[..., K]`` (K >= k; the union of several shards' lists): the k smallest, slots
+    without a valid distance (>= 1e20, here +inf) take the largest valid one (0 when there is none), then the mean."""
+    k = int(k_nearest_neighbors)
+    d = torch.sort(lists, dim=-1).values[..., :k]
+    valid = d < WRONG_LABEL_PADDING_DISTANCE
+    pad = torch.where(valid, d, torch.zeros_like(d)).max(dim=-1, keepdim=True).values
+    return torch.where(valid, d, pad.expand_as(d)).mean(dim=-1, keepdim=True)
+
+
 # --------------------------------------------------------------------------- local matching
 def _hwc_strides(t, name):
     require_f32(t, name)

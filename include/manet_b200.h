@@ -111,6 +111,13 @@ int manet_global_match(const float* ref, int64_t ref_pix_stride, int64_t ref_ch_
                        float* mem_frame, float* out,
                        void* workspace, size_t workspace_bytes, manet_stream_t stream);
 
+/* The k smallest per-object distances themselves, ascending, +inf where an object has fewer than k reference pixels:
+ * out_lists [M][N][k] fp32 (CUDA-core engine).  What a reference-axis shard contributes when k_nearest_neighbors > 1
+ * (IntVOS.py:86-94 averages the k smallest over ALL reference pixels: shards are merged list-wise, not by min). */
+int manet_global_match_topk(const float* ref, int64_t ref_pix_stride, int64_t ref_ch_stride, int64_t R, const int32_t* labels,
+                            const float* query, int64_t q_pix_stride, int64_t q_ch_stride, int64_t M, int C, int N, int k,
+                            float* out_lists, manet_stream_t stream);
+
 /* Same reduction with an explicit mask instead of labels: wrong_label_mask[o*R + r] != 0 means
  * reference r does NOT belong to object o (the [N,R] bool tensor of IntVOS.py:137, consumed by
  * _nn_features_per_object_for_chunk, IntVOS.py:62-97).  CUDA-core fp32 kernel. */

@@ -524,6 +524,35 @@ def test_global_k_greater_than_one_matches_oracle(api, cfg_guard):
                                                  lab.cuda().unsqueeze(-1)[:1, :2], 5, torch.tensor(N - 1))
 
 
+def test_global_k_smallest_lists_merge_like_unsharded(api, cfg_guard):
+    """k_nearest_neighbors > 1 over reference-axis shards (distributed._sharded_k_nearest): the per-shard lists of the k
+    smallest distances, merged, give exactly what the unsharded call gives -- and the lists are what the oracle's distances say."""
+    from oracle import manet_oracle as O
+    gen = torch.Generator().manual_seed(21)
+    C, H, W, N = 24, 12, 13, 4
+    ref_chw, qry_chw = torch.rand(C, H, W, generator=gen), torch.rand(C, H, W, generator=gen)
+    lab = torch.randint(0, N, (H, W), generator=gen).int()
+    lab[lab == 3] = 1
+    lab[-1, -2:] = 3                                     # object 3: two pixels, both in the last shard
+    ref, qry, labg = ref_chw.cuda().permute(1, 2, 0), qry_chw.cuda().permute(1, 2, 0), lab.cuda().unsqueeze(-1)
+    rf, lf = ref.reshape(-1, 1, C), labg.reshape(-1, 1, 1)
+    for k in (2, 4):
+        whole, _ = api.nearest_neighbor_features_per_object(ref, qry, labg, k, torch.tensor(N - 1))
+        lists_all = api.k_smallest_distances_per_object(ref, qry, labg, k, N - 1)
+        assert lists_all.shape == (H, W, N, k)
+        merged_all = api.mean_of_k_smallest(lists_all, k).view_as(whole)
+        assert torch.allclose(merged_all, whole, rtol=2e-6, atol=0)      # the kernel sums the k slots in order, torch.mean pairwise
+        for world in (2, 3):
+            bounds = [(r * rf.shape[0] // world, (r + 1) * rf.shape[0] // world) for r in range(world)]
+            parts = [api.k_smallest_distances_per_object(rf[b:e], qry, lf[b:e], k, N - 1) for b, e in bounds]
+            merged = api.mean_of_k_smallest(torch.cat(parts, dim=-1), k).view_as(whole)
+            assert torch.equal(merged, merged_all), (k, world)        # the same k distances, whichever shard listed them
+        want, _ = O.global_match(ref_chw.permute(1, 2, 0), qry_chw.permute(1, 2, 0), lab.unsqueeze(-1), k, torch.tensor(N - 1), n_chunks=1)
+        assert raw_close(whole.cpu().numpy(), want.numpy()) <= RAW_RTOL
+        # an object with fewer than k pixels: +inf in the slots beyond them
+        assert bool(torch.isinf(lists_all[..., 3, 2:]).all()) and bool(torch.isfinite(lists_all[..., 3, :2]).all())
+
+
 @pytest.mark.parametrize("engine", LOCAL_ENGINES)
 def test_local_edge_shapes_and_ids(api, engine, monkeypatch):
     """Odd sizes, window larger than the half-resolution frame, one object, non-consecutive / duplicate

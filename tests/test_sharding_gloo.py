@@ -30,6 +30,26 @@ def _worker(rank, world, port, ret):
         want, _ = O.global_match(ref, qry, lab, 1, torch.tensor(3), n_chunks=1)
         ok = bool(torch.equal(got, want)) and got.shape == (1, 6, 7, 4, 1)
         ok = ok and bool((got[..., 1, 0] == 1e20).all()) and bool((got[..., 3, 0] == 1e20).all())
+        # k_nearest_neighbors > 1: every shard lists its k smallest distances, the lists are all-gathered and merged
+        # (IntVOS.py:86-94 averages over ALL reference pixels).  The list builder here is the oracle's distance function.
+        def topk(r, q, l, k, g):
+            d, _ = O.pairwise_sqdist(q.reshape(-1, q.shape[-1]), r.reshape(-1, r.shape[-1]))          # [m, n]
+            n_obj = int(g) + 1
+            lf = l.reshape(-1)
+            out = torch.full((d.shape[0], n_obj, k), float("inf"))
+            for o in range(n_obj):
+                cols = d[:, lf == o]
+                if cols.shape[1]:
+                    srt = torch.sort(cols, dim=1).values[:, :k]
+                    out[:, o, :srt.shape[1]] = srt
+            return out.view(q.shape[0], q.shape[1], n_obj, k)
+
+        for k in (2, 5):
+            got_k, _ = D.sharded_nearest_neighbor_features_per_object(ref, qry, lab, k, torch.tensor(3), topk_fn=topk)
+            want_k, _ = O.global_match(ref, qry, lab, k, torch.tensor(3), n_chunks=1)
+            ok = ok and got_k.shape == want_k.shape and bool(torch.allclose(got_k, want_k, rtol=1e-6, atol=1e-6))
+            # absent objects: no valid distance at all -> the reference's rule gives 0 (pad = max of an all-masked row)
+            ok = ok and bool(torch.equal(got_k[..., 1, 0], want_k[..., 1, 0]))
         ret[rank] = ok
     finally:
         dist.destroy_process_group()
