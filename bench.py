@@ -175,6 +175,27 @@ def cpu_baseline_leg():
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank to the CPUs local to its GPU BEFORE the session allocates its pinned staging buffers (first touch places
+    them).  With N ranks each streaming ~10 MB per step through host memory, staging buffers on the far NUMA node were the
+    e2e limiter at N = 8.  Multi-rank runs only: the single-rank CPU baseline leg wants every core."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bus
+        node = int(open(base + "/numa_node").read().strip())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"pci": bus, "numa_node": node, "cpus_bound": len(allowed)}
+    except Exception as e:      # no sysfs / attribute: run unbound
+        return {"error": str(e)[:120]}
+
+
 def run_own_arm(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -192,6 +213,7 @@ def run_own_arm(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     sess = engine.MatchingSession(H, W, C, N_IDS, D_LOCAL, n_frames=104)
     ref, prev, cur, ref_lab, prev_lab = synth_inputs(1000 + rank)
     sess.ref[:], sess.prev[:], sess.cur[:] = ref.numpy(), prev.numpy(), cur.numpy()
@@ -372,6 +394,7 @@ def run_own_arm(args, rank, local_rank, world):
                                               "PCIe-bound, this was r01's e2e.value",
                                       "sync_value": world * K / e2e_sync_s, "sync_ms_per_step": e2e_sync_s * 1e3 / K}},
                 "single_stream": {"value": world * K / serial_s, "ms_per_step": serial_s * 1e3 / K},
+                "host_binding": numa,
                 "first_frame": {"value": world * K / nocache_s, "ms_per_step": nocache_s * 1e3 / K,
                                 "note": "MANET_STEP_NO_REF_CACHE: the reference side of global matching (annotated frame: bucketing, tensor-core "
                                         "image, fp32 copy) rebuilt every step -- what the first frame of a propagation pays; `value` is the steady "

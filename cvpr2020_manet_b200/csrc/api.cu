@@ -562,6 +562,9 @@ struct manet_session {
     cudaEvent_t ev_gemm;
     cudaStream_t copy_stream;     // host->device stream
     cudaStream_t down_stream;     // device->host stream (the two result maps)
+    cudaStream_t aux_stream;      // the local branch's guarded CUDA-core kernels (beside its tensor kernel)
+    cudaEvent_t ev_aux_fork, ev_aux_join;
+    bool use_aux;
     cudaEvent_t ev_fork, ev_join;
     SessionSlot slot[2];
     int32_t* d_ids;
@@ -593,6 +596,10 @@ manet_session_t* manet_session_create(int H, int W, int C, int N, int max_distan
     s->global_first = !(e_order && !strcmp(e_order, "local"));
     const char* e_gate = getenv("MANET_STEP_GATE");                 // MANET_STEP_GATE=1: experiment, see session_step_slot
     s->gate_local = e_gate && !strcmp(e_gate, "1");
+    // MANET_STEP_AUX=1 (experiment, off): the guarded CUDA-core kernels on a side stream beside lm_umma_kernel (StepGates).
+    // Measured (bench.py, 30 steps, same box): 0.244-0.246 ms per step with it, 0.238-0.239 without.
+    const char* e_aux = getenv("MANET_STEP_AUX");
+    s->use_aux = e_aux && !strcmp(e_aux, "1");
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     const bool use_prio = !(e_prio && !strcmp(e_prio, "0"));
@@ -601,6 +608,9 @@ manet_session_t* manet_session_create(int H, int W, int C, int N, int max_distan
               cudaStreamCreateWithPriority(&s->local_stream, cudaStreamNonBlocking, !use_prio ? 0 : swap_prio ? prio_hi : prio_lo) == cudaSuccess &&
               cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&s->down_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&s->aux_stream, cudaStreamNonBlocking, use_prio ? prio_lo : 0) == cudaSuccess &&
+              cudaEventCreateWithFlags(&s->ev_aux_fork, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&s->ev_aux_join, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&s->ev_gemm, cudaEventDisableTiming) == cudaSuccess;
@@ -657,6 +667,9 @@ void manet_session_destroy(manet_session_t* s) {
     if (s->local_stream) cudaStreamDestroy(s->local_stream);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->down_stream) cudaStreamDestroy(s->down_stream);
+    if (s->aux_stream) cudaStreamDestroy(s->aux_stream);
+    if (s->ev_aux_fork) cudaEventDestroy(s->ev_aux_fork);
+    if (s->ev_aux_join) cudaEventDestroy(s->ev_aux_join);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->ev_gemm) cudaEventDestroy(s->ev_gemm);
@@ -736,9 +749,11 @@ static int session_step_slot(manet_session_t* s, int slot, int frame, int intera
     }
     gates.after_global_gemm = nullptr;
     gates.local_main_gate = gate ? s->ev_gemm : nullptr;
+    if (s->use_aux && !(flags & MANET_STEP_SERIAL)) { gates.aux_stream = s->aux_stream; gates.ev_aux_fork = s->ev_aux_fork; gates.ev_aux_join = s->ev_aux_join; }
     int rc = manet_local_match(in->prev, s->W, 1, px, in->cur, s->W, 1, px, in->prev_lab, s->d_ids, s->H, s->W, s->C, s->N,
                                s->d, t.d_raw_l, s->ws_l, s->ws_l_bytes, ls);
     gates.local_main_gate = nullptr;
+    gates.aux_stream = nullptr; gates.ev_aux_fork = gates.ev_aux_join = nullptr;
     if (rc) return rc;
     int df = frame - start_annotated_frame; if (df < 0) df = -df;
     rc = manet_local_map_store_select(t.d_raw_l, s->d_lmem + (size_t)frame * kMemoryRounds * n,

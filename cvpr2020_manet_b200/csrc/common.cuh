@@ -88,7 +88,13 @@ __device__ __forceinline__ void pdl_enter() {
 // Cross-branch ordering inside one propagation step (set by the session around its two launcher calls, per host thread):
 // the global-matching launcher records `after_global_gemm` right after its GEMM kernel, the local-matching launcher makes its
 // main kernel wait for `local_main_gate`.  See session_step_slot (api.cu) for why.
-struct StepGates { cudaEvent_t after_global_gemm = nullptr; cudaEvent_t local_main_gate = nullptr; };
+// `aux_stream` (+ its two events): the local-matching launcher puts the CUDA-core kernels that stand behind the tensor engine's
+// numerics guard there, forked after the pre-pass and joined after them, so that their three launches -- which exit at once
+// whenever the guard holds -- run beside lm_umma_kernel instead of lengthening the local branch by ~10 us.
+struct StepGates {
+    cudaEvent_t after_global_gemm = nullptr; cudaEvent_t local_main_gate = nullptr;
+    cudaStream_t aux_stream = nullptr; cudaEvent_t ev_aux_fork = nullptr; cudaEvent_t ev_aux_join = nullptr;
+};
 StepGates& step_gates();
 bool pdl_enabled();                        // MANET_PDL=1 in the environment turns the attribute on (measured: a wash, see api.cu)
 

@@ -445,10 +445,19 @@ int launch_local_match(const float* prev, int64_t p_sy, int64_t p_sx, int64_t p_
     }
     float* T = nullptr;
     int32_t* plab = nullptr;
-    int rc = window_volume(query, q_sy, q_sx, q_sc, prev, p_sy, p_sx, p_sc, H, W, C, d, simt_ws, simt_bytes, stream, &T, labels, &plab,
+    // behind the guard the CUDA-core kernels may run on a side stream, beside the tensor engine's main kernel (StepGates)
+    const StepGates& gates = step_gates();
+    const bool side = guard != nullptr && gates.aux_stream != nullptr;
+    cudaStream_t fs = side ? gates.aux_stream : stream;
+    int rc = window_volume(query, q_sy, q_sx, q_sc, prev, p_sy, p_sx, p_sc, H, W, C, d, simt_ws, simt_bytes, fs, &T, labels, &plab,
                            guard);
     if (rc) return rc;
-    return simt_masked_min(T, plab, gt_ids, H, W, N, d, out, guard, stream);
+    rc = simt_masked_min(T, plab, gt_ids, H, W, N, d, out, guard, fs);
+    if (side) {
+        cudaEventRecord(gates.ev_aux_join, fs);
+        cudaStreamWaitEvent(stream, gates.ev_aux_join, 0);
+    }
+    return rc;
 }
 
 int launch_local_window_distances(const float* x, int64_t x_sy, int64_t x_sx, int64_t x_sc,

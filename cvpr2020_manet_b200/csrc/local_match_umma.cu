@@ -1096,6 +1096,10 @@ int launch_local_match_umma(const float* prev, int64_t p_sy, int64_t p_sx, int64
     CP.Aimg = Aimg; CP.Xs = Xs; CP.Bimg = Bimg; CP.Ys = Ys; CP.stats = stats; CP.mub = mub; CP.g = g;
     launch_k(lm_convert_kernel, dim3(g.HI * (g.WI >> 5) + 4 * n_tiles), dim3(256), 0, stream, CP);
     profile_end(PROF_LOCAL_MIN, stream);
+    if (guarded && step_gates().aux_stream) {             // the guard value exists from here on: the fallback branch forks now
+        cudaEventRecord(step_gates().ev_aux_fork, stream);
+        cudaStreamWaitEvent(step_gates().aux_stream, step_gates().ev_aux_fork, 0);
+    }
     P.Aimg = Aimg; P.Xs = Xs; P.Bimg = Bimg; P.Ys = Ys; P.stats = stats; P.guarded = guarded ? 1 : 0;
     if (guard_out) *guard_out = stats;
     P.plab8 = labels ? plab8 : nullptr; P.gt_ids = gt_ids; P.out = labels ? out : nullptr;
