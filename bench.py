@@ -180,6 +180,7 @@ def bind_to_gpu_numa_node(local_rank):
     them).  With N ranks each streaming ~10 MB per step through host memory, staging buffers on the far NUMA node were the
     e2e limiter at N = 8.  Multi-rank runs only: the single-rank CPU baseline leg wants every core."""
     try:
+        import torch
         pr = torch.cuda.get_device_properties(local_rank)
         bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
         base = "/sys/bus/pci/devices/" + bus
