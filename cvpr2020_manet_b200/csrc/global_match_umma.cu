@@ -285,7 +285,9 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
     __shared__ float rowsq[GM_CV_PIX], rowh[GM_CV_PIX], rowl[GM_CV_PIX];
     __shared__ int lab_s[GM_CV_PIX];
     __shared__ unsigned omax[3][GM_MAXN];
+    __shared__ int fold_g[16], fold_i[16];                  // folded K step: position within the step -> (product group, channel)
     const int t = threadIdx.x;
+    if (t >= 32 && t < 48) { const int rm = max(C % 16, 1); fold_g[t - 32] = (t - 32) / rm; fold_i[t - 32] = (t - 32) % rm; }
     if (t == 0) {
         int o = 0;
         for (int i = 0; i < N; ++i) { off[i] = o; o += (ctrl->counts[i] + GM_BN - 1) / GM_BN * GM_BN; }
@@ -450,7 +452,8 @@ gm_convert_kernel(const float* __restrict__ ref, int64_t rps, int64_t rcs, int64
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const int p16 = (j - j_fold) * 8 + k;          // position within the 16-wide k-step
-                        const int g = p16 / rem, i = p16 - g * rem;    // group 0..2 (>=3: zero padding), channel i
+                        const int g = fold_g[p16], i = fold_i[p16];    // group 0..2 (>=3: zero padding), channel i  (a table: an
+                                                                       // integer division by the run-time `rem` cost ~25 instructions here)
                         float x = 0.f;
                         if (g < 3) x = tile[(C - rem) - kb * 64 + i][row] * scale;
                         const __half h = __float2half_rn(x);
