@@ -71,9 +71,9 @@ struct GmCtrl {
     int n_segs;
     int engine;                    // which kernel chain serves this reference set: GM_ENG_FR or GM_ENG_EXACT3 (decided by the pre-pass)
 };
-// The filter-and-refine engine pays a fixed ~80 us at 480p for its refinement (proportional to queries x objects, independent
-// of the reference set) and saves ~0.95 us per 256-reference tile on the GEMM: measured break-even ~85 tiles (22 000 labelled
-// reference pixels).  Scribble references (rounds >= 2 of an interactive session: 10^2..10^3 labelled pixels, the count is
+// The filter-and-refine engine pays a fixed ~70 us at 480p for its refinement (proportional to queries x objects, independent
+// of the reference set) and saves ~1.2 us per 256-reference tile on the GEMM: the break-even is kept at 85 tiles (22 000
+// labelled reference pixels; measured with the first version of the engine, ~60 tiles with this one).  Scribble references (rounds >= 2 of an interactive session: 10^2..10^3 labelled pixels, the count is
 // only known on the device because unlabelled pixels are dropped there) are served by the three-product kernel, dense
 // references (first round, 1080p memory frames) by filter-and-refine.  Both chains are enqueued; the one that is not
 // needed exits at once.
@@ -1109,14 +1109,14 @@ __global__ void gm_finalize_kernel(const int* __restrict__ best, const float* __
 // ------------------------------------------------------------------------------------ filter-and-refine engine
 // The three-product kernel above spends 19 tensor-core K steps per tile to get fp32-grade distances for EVERY (query,
 // reference) pair, although only the per-object minimum survives.  This engine spends 7: one product of the fp16 hi parts
-// (+ the folded bias) FILTERS the candidates, and the survivors -- almost always one pair of neighbouring reference rows
-// per (query, object) -- are re-evaluated EXACTLY in fp32 from the original operands.  Exactness does not rest on luck:
+// (+ the folded bias) FILTERS the candidates, and the survivors -- almost always one group of four neighbouring reference
+// rows per (query, object) -- are re-evaluated EXACTLY in fp32 from the original operands.  Exactness does not rest on luck:
 //
 //   approximate score  s~ = qh.rh + bias   (tensor core)          true score  s = q^.r^ + bias   (q^ = s_q q, r^ = s_r r)
 //   |s~ - s| <= |ql||rh| + |qh||rl| + |ql||rl| + tau  =: E        (Cauchy-Schwarz on the dropped cross terms; the row norms
 //                                                                   come from the pre-pass, tau covers the accumulator and
-//                                                                   the 6 index bits written into each key)
-//   => the reference row with the largest TRUE score has  s~ >= max s~ - 2E.
+//                                                                   the 5 index bits written into each key)
+//   => the reference row with the largest TRUE score has  s~ >= max s~ - 2E  (and  s~ >= S - E  once a true score S is known).
 //
 // The epilogue therefore keeps, per query row and per SEGMENT-half (128 columns of seg_tiles consecutive tiles of one
 // object), the two largest keys; a key is the maximum of four neighbouring columns with the group's index in its low
