@@ -72,13 +72,13 @@ struct GmCtrl {
     int engine;                    // which kernel chain serves this reference set: GM_ENG_FR or GM_ENG_EXACT3 (decided by the pre-pass)
 };
 // The filter-and-refine engine pays a fixed ~70 us at 480p for its refinement (proportional to queries x objects, independent
-// of the reference set) and saves ~1.2 us per 256-reference tile on the GEMM: the break-even is kept at 85 tiles (22 000
-// labelled reference pixels; measured with the first version of the engine, ~60 tiles with this one).  Scribble references (rounds >= 2 of an interactive session: 10^2..10^3 labelled pixels, the count is
+// of the reference set) and saves ~1.2 us per 256-reference tile on the GEMM: measured break-even ~48 tiles (12 000 labelled
+// reference pixels; scripts/gm_breakeven.py: 40 tiles 130 vs 138 us, 56 tiles 160 vs 153 us, 100 tiles 255 vs 199 us).  Scribble references (rounds >= 2 of an interactive session: 10^2..10^3 labelled pixels, the count is
 // only known on the device because unlabelled pixels are dropped there) are served by the three-product kernel, dense
 // references (first round, 1080p memory frames) by filter-and-refine.  Both chains are enqueued; the one that is not
 // needed exits at once.
 constexpr int GM_ENG_FR = 0, GM_ENG_EXACT3 = 1;
-constexpr int FR_MIN_TILES = 85;
+constexpr int FR_MIN_TILES = 48;
 constexpr size_t GM_CTRL_FRAME_BYTES = 16;      // the per-call prefix of GmCtrl
 
 
