@@ -349,6 +349,25 @@ def test_host_buffer_session_equals_device_api(api, cfg_guard):
     w5 = engine.prop_matching_step(ref.cuda(), prev.cuda(), cur.cuda(), rl.cuda(), pl.cuda(), N - 1, 1, d, gm, lm, "x", 5, 1, 1)
     assert np.array_equal(a_g, w4[0][0, :, :, :, 0].cpu().numpy()) and np.array_equal(a_l, w4[1][0, :, :, :, 0].cpu().numpy())
     assert np.array_equal(b_g, w5[0][0, :, :, :, 0].cpu().numpy()) and np.array_equal(b_l, w5[1][0, :, :, :, 0].cpu().numpy())
+    # a slot re-submitted WITHOUT waiting for it: uploads, kernels and the downloads (on their own stream) of the two steps are
+    # ordered on the device -- the wait returns the second step's maps
+    s.submit_host(0, 6, 1, 1)
+    s.submit_host(0, 7, 1, 1)
+    c_g, c_l = (x.copy() for x in s.wait(0))
+    engine.prop_matching_step(ref.cuda(), prev.cuda(), cur.cuda(), rl.cuda(), pl.cuda(), N - 1, 1, d, gm, lm, "x", 6, 1, 1)
+    w7 = engine.prop_matching_step(ref.cuda(), prev.cuda(), cur.cuda(), rl.cuda(), pl.cuda(), N - 1, 1, d, gm, lm, "x", 7, 1, 1)
+    assert np.array_equal(c_g, w7[0][0, :, :, :, 0].cpu().numpy()) and np.array_equal(c_l, w7[1][0, :, :, :, 0].cpu().numpy())
+    # the library's timeline view of a two-stream step: every profiled kernel group starts after the global pre-pass begins
+    import ctypes
+    from cvpr2020_manet_b200 import _lib
+    L = _lib.lib()
+    L.manet_profile_enable(4); L.manet_profile_reset()
+    s.step_host(3, 2, 6); s.sync()
+    a, b, n = (ctypes.c_float * 4)(), (ctypes.c_float * 4)(), ctypes.c_int(0)
+    for slot in (5, 2, 1):                                # global pre-pass, local pre-pass, local main kernel
+        _lib.check(L.manet_profile_read_span(slot, 5, a, b, 4, ctypes.byref(n)), "span")
+        assert n.value == 1 and b[0] > a[0] and (slot != 5 or a[0] == 0.0)
+    L.manet_profile_enable(0)
     s.close()
 
 
