@@ -5,6 +5,8 @@ from __future__ import annotations
 
 import ctypes
 
+import os
+
 import numpy as np
 import torch
 
@@ -30,14 +32,53 @@ def prop_matching_step(ref_emb, prev_emb, cur_emb, ref_scribble_label, prev_labe
             global_map_tmp_dic[seq_name] = torch.ones((104, h, w, int(n_objects) + 1, 1), dtype=torch.float32,
                                                       device=cur.device)
         mem_slot = global_map_tmp_dic[seq_name][int(frame)]
-    g, ids = nearest_neighbor_features_per_object(ref, cur, ref_scribble_label.unsqueeze(-1), k_nearest_neighbors,
-                                                  n_objects, n_chunks=10, normalize=True, memory_frame=mem_slot,
-                                                  reference_cache=reference_cache)
-    loc = local_previous_frame_nearest_neighbor_features_per_object(prev, cur, prev_label.unsqueeze(-1), ids, d)
-    if local_map_dics is not None:
-        loc, local_map_dics = local_map_store_select(local_map_dics, seq_name, frame, interaction_num,
-                                                     start_annotated_frame, loc)
+    def local_branch(ids):
+        loc = local_previous_frame_nearest_neighbor_features_per_object(prev, cur, prev_label.unsqueeze(-1), ids, d)
+        if local_map_dics is not None:
+            loc, _ = local_map_store_select(local_map_dics, seq_name, frame, interaction_num, start_annotated_frame, loc)
+        return loc
+
+    # The two branches share nothing until the head reads both maps (IntVOS.py:609-661): without autograd in play the local
+    # branch runs on a side stream beside the global one (MANET_PROP_STREAMS=0: one stream), as in the C-ABI session.
+    needs_grad = torch.is_grad_enabled() and (ref_emb.requires_grad or prev_emb.requires_grad or cur_emb.requires_grad)
+    if needs_grad or not cur.is_cuda or os.environ.get("MANET_PROP_STREAMS", "1") == "0":
+        g, ids = nearest_neighbor_features_per_object(ref, cur, ref_scribble_label.unsqueeze(-1), k_nearest_neighbors,
+                                                      n_objects, n_chunks=10, normalize=True, memory_frame=mem_slot,
+                                                      reference_cache=reference_cache)
+        return g, local_branch(ids)
+    dev = cur.device
+    main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+    ids = torch.arange(0, int(n_objects) + 1, dtype=torch.int32, device=dev)
+    if local_map_dics is not None:                          # the persistent memories are created on the caller's stream
+        from .memory import _ensure_local
+        h, w = cur.shape[:2]
+        _ensure_local(local_map_dics, seq_name, torch.empty((1, h, w, int(n_objects) + 1, 1), device="meta"), ones=False,
+                      device=dev)
+    side.wait_stream(main)                                  # the inputs (and the ids) are ready
+    g, _ = nearest_neighbor_features_per_object(ref, cur, ref_scribble_label.unsqueeze(-1), k_nearest_neighbors,
+                                                n_objects, n_chunks=10, normalize=True, memory_frame=mem_slot,
+                                                reference_cache=reference_cache)
+    # the result is handed over in a buffer of the CALLER's stream (filled on the side stream, before the join): a side-stream
+    # allocation consumed on the caller's stream would need record_stream, which keeps the caching allocator from reusing it
+    # until an event query succeeds -- measured as 100-300 ms stalls in a loop that runs far ahead of the GPU
+    h, w = cur.shape[:2]
+    loc = torch.empty((1, h, w, int(n_objects) + 1, 1), dtype=torch.float32, device=dev)
+    with torch.cuda.stream(side):
+        loc.copy_(local_branch(ids))
+    main.wait_stream(side)
     return g, loc
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    """One side stream per device for the local branch of prop_matching_step."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return st
 
 
 def int_matching_step(ref_emb, scribble_label, n_objects, max_distance=None, global_map_tmp_dic=None,

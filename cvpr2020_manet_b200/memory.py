@@ -50,9 +50,9 @@ def normalize_distances(nn_features):
     return out
 
 
-def _ensure_local(local_map_dics, seq_name, like, ones):
+def _ensure_local(local_map_dics, seq_name, like, ones, device=None):
     maps, dists = local_map_dics
-    dev = like.device
+    dev = like.device if device is None else device
     if seq_name not in dists:
         dists[seq_name] = torch.zeros(MEMORY_FRAMES, MEMORY_ROUNDS, dtype=torch.float32, device=dev)
     if seq_name not in maps:
